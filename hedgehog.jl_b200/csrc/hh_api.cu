@@ -1,0 +1,225 @@
+// hh_api.cu — extern "C" surface of libhedgehog_mc.so: context lifetime and the thin wrappers
+// that lock the context and forward to the kernels' host drivers. See include/hedgehog_mc.h.
+#include <cstring>
+#include <new>
+
+#include "hh_ctx.h"
+
+static thread_local std::string g_create_error;
+
+namespace hh {
+int tangent_sums(hh_ctx *ctx, const hh_model *model, const hh_tangent *tangents, int ntangents, const hh_sim *sim,
+                 const hh_payoff *payoffs, int npayoffs, double *sums, double *kernel_ms);
+int lsm_american(hh_ctx *ctx, const hh_model *model, const hh_sim *sim, const hh_payoff *payoff, int degree,
+                 double step_discount, const hh_comm *comm, hh_lsm_result *out, int32_t *stop_idx, double *stop_val,
+                 double *spot_paths);
+int bk_chf(hh_ctx *ctx, const hh_model *model, double tau, const double *V0, const double *VT, int n, const double *a,
+           int na, double *out_re, double *out_im);
+int bk_log_besseli(hh_ctx *ctx, double nu, const double *z_re, const double *z_im, int n, double *out_re,
+                   double *out_im);
+int bk_european_launch(hh_ctx *ctx, const hh_model *model, const hh_sim *sim, const hh_payoff *payoffs, int npayoffs,
+                       int want_terminal);
+int fp64_peak(hh_ctx *ctx, double *tflops, double *ms);
+}  // namespace hh
+
+extern "C" {
+
+int hh_version(void) { return HH_VERSION; }
+
+void hh_default_bk_config(hh_bk_config *out) {
+  if (!out) return;
+  out->n_std = 5;              // sample_from_cf.jl:27
+  out->h_fd = 1e-2;            // :50
+  out->cf_tol = 1e-3;          // :75
+  out->atol = 1e-4;            // :110
+  out->maxiter_newton = 10;    // :111
+  out->maxiter_bisection = 100;  // :112
+  out->max_terms = 4096;
+}
+
+int hh_create(hh_ctx **out, int device) {
+  if (!out) return HH_ERR_ARG;
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    g_create_error = std::string("no usable CUDA device: ") + cudaGetErrorString(e) +
+                     " (libhedgehog_mc has no CPU fallback)";
+    return HH_ERR_CUDA;
+  }
+  if (device < 0 || device >= ndev) {
+    g_create_error = "device index out of range";
+    return HH_ERR_ARG;
+  }
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) {
+    g_create_error = cudaGetErrorString(e);
+    return HH_ERR_CUDA;
+  }
+  if (prop.major != 10) {
+    g_create_error = "libhedgehog_mc is built for sm_100a only; device is sm_" + std::to_string(prop.major) +
+                     std::to_string(prop.minor);
+    return HH_ERR_CUDA;
+  }
+  hh_ctx *ctx = new (std::nothrow) hh_ctx();
+  if (!ctx) return HH_ERR_NOMEM;
+  ctx->device = device;
+  ctx->sm_count = prop.multiProcessorCount;
+  ctx->cc_major = prop.major;
+  ctx->cc_minor = prop.minor;
+  ctx->total_mem = prop.totalGlobalMem;
+  bool ok = cudaSetDevice(device) == cudaSuccess &&
+            cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaEventCreate(&ctx->ev0) == cudaSuccess && cudaEventCreate(&ctx->ev1) == cudaSuccess &&
+            cudaEventCreate(&ctx->ev2) == cudaSuccess;
+  if (!ok) {
+    g_create_error = std::string("context setup failed: ") + cudaGetErrorString(cudaGetLastError());
+    delete ctx;
+    return HH_ERR_CUDA;
+  }
+  ctx->stream = ctx->own_stream;
+  *out = ctx;
+  return HH_OK;
+}
+
+int hh_destroy(hh_ctx *ctx) {
+  if (!ctx) return HH_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  hh::DeviceBuffer *bufs[] = {&ctx->d_payoffs,  &ctx->d_partials, &ctx->d_final, &ctx->d_terminal,
+                              &ctx->d_seeds,    &ctx->d_normals,  &ctx->d_tangents, &ctx->d_grid,
+                              &ctx->d_cash,     &ctx->d_tau,      &ctx->d_lsm_partials, &ctx->d_lsm_state,
+                              &ctx->d_misc};
+  for (auto *b : bufs) b->release();
+  if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+  cudaEventDestroy(ctx->ev0);
+  cudaEventDestroy(ctx->ev1);
+  cudaEventDestroy(ctx->ev2);
+  cudaStreamDestroy(ctx->own_stream);
+  delete ctx;
+  return HH_OK;
+}
+
+const char *hh_last_error(hh_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int hh_set_stream(hh_ctx *ctx, void *cuda_stream) {
+  if (!ctx) return HH_ERR_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  ctx->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+  return HH_OK;
+}
+
+int hh_device_info(hh_ctx *ctx, int32_t *sm_count, int32_t *cc_major, int32_t *cc_minor, size_t *total_mem) {
+  if (!ctx) return HH_ERR_ARG;
+  if (sm_count) *sm_count = ctx->sm_count;
+  if (cc_major) *cc_major = ctx->cc_major;
+  if (cc_minor) *cc_minor = ctx->cc_minor;
+  if (total_mem) *total_mem = ctx->total_mem;
+  return HH_OK;
+}
+
+int hh_bench_fp64_peak(hh_ctx *ctx, double *tflops, double *ms) {
+  if (!ctx) return HH_ERR_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  return hh::fp64_peak(ctx, tflops, ms);
+}
+
+int hh_mc_european_launch(hh_ctx *ctx, const hh_model *model, const hh_sim *sim, const hh_payoff *payoffs, int npayoffs,
+                          int want_terminal) {
+  if (!ctx) return HH_ERR_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (sim && sim->scheme == HH_SCHEME_HESTON_BK) {
+    int rc = hh::validate_model_sim(ctx, model, sim);
+    if (rc) return rc;
+    return hh::bk_european_launch(ctx, model, sim, payoffs, npayoffs, want_terminal);
+  }
+  return hh::european_launch(ctx, model, sim, payoffs, npayoffs, want_terminal);
+}
+
+int hh_mc_european_collect(hh_ctx *ctx, double discount, hh_result *results, double *terminal, size_t terminal_len) {
+  if (!ctx) return HH_ERR_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  return hh::european_collect(ctx, discount, results, terminal, terminal_len);
+}
+
+int hh_mc_european(hh_ctx *ctx, const hh_model *model, const hh_sim *sim, const hh_payoff *payoffs, int npayoffs,
+                   double discount, hh_result *results, double *terminal, size_t terminal_len) {
+  int rc = hh_mc_european_launch(ctx, model, sim, payoffs, npayoffs, terminal != nullptr);
+  if (rc) return rc;
+  return hh_mc_european_collect(ctx, discount, results, terminal, terminal_len);
+}
+
+int hh_mc_european_tangent_sums(hh_ctx *ctx, const hh_model *model, const hh_tangent *tangents, int ntangents,
+                                const hh_sim *sim, const hh_payoff *payoffs, int npayoffs, double *sums,
+                                double *kernel_ms) {
+  if (!ctx) return HH_ERR_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  return hh::tangent_sums(ctx, model, tangents, ntangents, sim, payoffs, npayoffs, sums, kernel_ms);
+}
+
+int hh_mc_european_tangent(hh_ctx *ctx, const hh_model *model, const hh_tangent *tangents, int ntangents,
+                           const hh_sim *sim, const hh_payoff *payoffs, int npayoffs, double discount,
+                           hh_result *results, double *tangent_results, double *tangent_stderr) {
+  if (!ctx) return HH_ERR_ARG;
+  if (!results || !tangent_results || ntangents < 1 || npayoffs < 1) {
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    return ctx->fail(HH_ERR_ARG, "tangent: results/tangent_results NULL or empty request");
+  }
+  const int stride = 2 + 2 * ntangents;
+  double *sums = new (std::nothrow) double[(size_t)npayoffs * stride];
+  if (!sums) return HH_ERR_NOMEM;
+  double ms = 0.0;
+  int rc = hh_mc_european_tangent_sums(ctx, model, tangents, ntangents, sim, payoffs, npayoffs, sums, &ms);
+  if (rc == HH_OK) {
+    const double N = (double)sim->n_paths;
+    for (int k = 0; k < npayoffs; ++k) {
+      const double *s = sums + (size_t)k * stride;
+      hh_result *r = &results[k];
+      memset(r, 0, sizeof *r);
+      r->sum = s[0];
+      r->sumsq = s[1];
+      r->n = sim->n_paths;
+      const double mean = s[0] / N;
+      r->price = discount * mean;
+      double var = N > 1 ? (s[1] - N * mean * mean) / (N - 1) : 0.0;
+      r->std_error = discount * sqrt((var > 0 ? var : 0) / N);
+      r->kernel_ms = ms;
+      for (int p = 0; p < ntangents; ++p) {
+        // price = D * mean(payoff)  =>  d price = dD * mean(payoff) + D * mean(d payoff)   (montecarlo.jl:489-490)
+        const double dmean = s[2 + p] / N;
+        tangent_results[(size_t)k * ntangents + p] = tangents[p].ddiscount * mean + discount * dmean;
+        if (tangent_stderr) {
+          double tv = N > 1 ? (s[2 + ntangents + p] - N * dmean * dmean) / (N - 1) : 0.0;
+          tangent_stderr[(size_t)k * ntangents + p] = discount * sqrt((tv > 0 ? tv : 0) / N);
+        }
+      }
+    }
+  }
+  delete[] sums;
+  return rc;
+}
+
+int hh_lsm_american(hh_ctx *ctx, const hh_model *model, const hh_sim *sim, const hh_payoff *payoff, int degree,
+                    double step_discount, const hh_comm *comm, hh_lsm_result *out, int32_t *stop_idx, double *stop_val,
+                    double *spot_paths) {
+  if (!ctx) return HH_ERR_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  return hh::lsm_american(ctx, model, sim, payoff, degree, step_discount, comm, out, stop_idx, stop_val, spot_paths);
+}
+
+int hh_bk_chf(hh_ctx *ctx, const hh_model *model, double tau, const double *V0, const double *VT, int n, const double *a,
+              int na, double *out_re, double *out_im) {
+  if (!ctx) return HH_ERR_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  return hh::bk_chf(ctx, model, tau, V0, VT, n, a, na, out_re, out_im);
+}
+
+int hh_bk_log_besseli(hh_ctx *ctx, double nu, const double *z_re, const double *z_im, int n, double *out_re,
+                      double *out_im) {
+  if (!ctx) return HH_ERR_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  return hh::bk_log_besseli(ctx, nu, z_re, z_im, n, out_re, out_im);
+}
+
+}  // extern "C"

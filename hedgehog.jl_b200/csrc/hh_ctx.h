@@ -1,0 +1,94 @@
+// hh_ctx.h — the opaque context behind the C ABI: one CUDA device, one stream, growable device
+// scratch, last-error text. Host-side only.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <mutex>
+#include <string>
+
+#include "../../include/hedgehog_mc.h"
+
+namespace hh {
+
+struct DeviceBuffer {
+  void *ptr = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&ptr, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() {
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+    cap = 0;
+  }
+  template <class T>
+  T *as() const {
+    return static_cast<T *>(ptr);
+  }
+};
+
+struct PendingEuropean {
+  bool active = false;
+  int npay = 0;
+  int nblocks = 0;
+  int64_t n = 0;
+  bool anti = false;
+  bool want_terminal = false;
+};
+
+}  // namespace hh
+
+struct hh_ctx {
+  int device = 0;
+  int sm_count = 0;
+  int cc_major = 0, cc_minor = 0;
+  size_t total_mem = 0;
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
+  std::mutex mu;
+  std::string err;
+
+  hh::DeviceBuffer d_payoffs, d_partials, d_final, d_terminal, d_seeds, d_normals, d_tangents;
+  hh::DeviceBuffer d_grid, d_cash, d_tau, d_lsm_partials, d_lsm_state, d_misc;
+  void *h_pinned = nullptr;  // small pinned staging area for results
+  size_t h_pinned_cap = 0;
+  hh::PendingEuropean pend;
+
+  int fail(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    err = buf;
+    return code;
+  }
+  int fail_cuda(cudaError_t e, const char *what, const char *file, int line) {
+    int code = (e == cudaErrorMemoryAllocation) ? HH_ERR_NOMEM : HH_ERR_CUDA;
+    return fail(code, "CUDA error %d (%s) in %s at %s:%d", (int)e, cudaGetErrorString(e), what, file, line);
+  }
+};
+
+#define HH_CUDA(ctx, call)                                                   \
+  do {                                                                       \
+    cudaError_t _e = (call);                                                 \
+    if (_e != cudaSuccess) return (ctx)->fail_cuda(_e, #call, __FILE__, __LINE__); \
+  } while (0)
+
+namespace hh {
+// implemented in hh_european.cu
+int european_launch(hh_ctx *ctx, const hh_model *model, const hh_sim *sim, const hh_payoff *payoffs, int npayoffs,
+                    int want_terminal);
+int european_collect(hh_ctx *ctx, double discount, hh_result *results, double *terminal, size_t terminal_len);
+int validate_model_sim(hh_ctx *ctx, const hh_model *model, const hh_sim *sim);
+}  // namespace hh

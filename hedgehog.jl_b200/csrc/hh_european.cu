@@ -1,0 +1,638 @@
+// hh_european.cu — European Monte Carlo: path simulation + payoff + reduction in ONE kernel,
+// for prices (T = double) and for pathwise forward-mode Greeks (T = Dual<P>).
+//
+// Replaces, for solve(::PricingProblem, ::MonteCarlo) (reference src/pricing_methods/montecarlo.jl:478-493):
+//   sde_problem / simulate_paths (:140-231, :342-375)  -> in-register stepping, Philox normals in-kernel
+//   final_sample (:384-402)                             -> exp of the log state at expiry
+//   reduce_payoffs + mean (:428-432, :490)              -> fused block reduction of sum / sum of squares
+// and, for solve(::GreekProblem, ::ForwardAD, method) (src/greeks/greeks_problem.jl:249-262), the Dual that
+// ForwardDiff pushes through all of the above.
+//
+// Layout: one trajectory (or antithetic pair) per thread, state in registers for all steps; no HBM
+// traffic in the step loop. After a batch of 256 trajectories the block evaluates every payoff on the
+// batch from shared memory ("payoff transpose": thread = (strike, path group)), so up to 256 strikes are
+// priced on the same paths with register accumulators and a fixed summation order.
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "hh_ctx.h"
+#include "hh_paths.cuh"
+
+namespace hh {
+
+constexpr int kThreads = 256;
+constexpr int kMaxTan = 8;
+
+enum : int { K_GBM_EM = 0, K_GBM_TERMINAL = 1, K_GBM_STEPS = 2, K_HESTON_EM = 3 };
+
+struct TangentPack {  // d(parameter)/d(direction p), zero-padded to the kernel's P
+  double x0[kMaxTan], S0[kMaxTan], dt_drift[kMaxTan], sigma[kMaxTan], sig_sqdt[kMaxTan], mu[kMaxTan], sd[kMaxTan];
+  double v0[kMaxTan], r[kMaxTan], kappa[kMaxTan], theta[kMaxTan], xi[kMaxTan];
+  double a11[kMaxTan], a12[kMaxTan], a21[kMaxTan], a22[kMaxTan];
+};
+
+struct EuroArgs {
+  int64_t n, path_offset;
+  uint64_t base_seed;
+  const uint64_t *seeds;
+  const double *normals;
+  double *terminal;
+  const hh_payoff *payoffs;
+  double *partials;  // [grid][npay][nacc]
+  int npay, kp_log2, n_steps, split, parity;
+  PathParams<double> p;
+};
+
+// number of accumulators per (block, payoff): sum, sumsq, nonfinite, then per tangent: dsum, dsumsq
+template <class T>
+__host__ __device__ constexpr int nacc_of() { return 3 + 2 * num_traits<T>::ntan; }
+
+template <class T>
+__device__ __forceinline__ T lift(double v, const double *dv) {
+  if constexpr (num_traits<T>::ntan == 0) {
+    return v;
+  } else {
+    T r;
+    r.v = v;
+#pragma unroll
+    for (int i = 0; i < num_traits<T>::ntan; ++i) r.d[i] = dv[i];
+    return r;
+  }
+}
+
+template <class T>
+__device__ __forceinline__ T zero() {
+  if constexpr (num_traits<T>::ntan == 0) {
+    return 0.0;
+  } else {
+    T r;
+    r.v = 0.0;
+#pragma unroll
+    for (int i = 0; i < num_traits<T>::ntan; ++i) r.d[i] = 0.0;
+    return r;
+  }
+}
+
+template <class T>
+__device__ __forceinline__ PathParams<T> lift_params(const PathParams<double> &p, const TangentPack *t) {
+  if constexpr (num_traits<T>::ntan == 0) {
+    return p;
+  } else {
+    PathParams<T> q;
+    q.dt = p.dt;
+    q.sqdt = p.sqdt;
+    q.x0 = lift<T>(p.x0, t->x0);
+    q.S0 = lift<T>(p.S0, t->S0);
+    q.dt_drift = lift<T>(p.dt_drift, t->dt_drift);
+    q.sigma = lift<T>(p.sigma, t->sigma);
+    q.sig_sqdt = lift<T>(p.sig_sqdt, t->sig_sqdt);
+    q.mu = lift<T>(p.mu, t->mu);
+    q.sd = lift<T>(p.sd, t->sd);
+    q.v0 = lift<T>(p.v0, t->v0);
+    q.r = lift<T>(p.r, t->r);
+    q.kappa = lift<T>(p.kappa, t->kappa);
+    q.theta = lift<T>(p.theta, t->theta);
+    q.xi = lift<T>(p.xi, t->xi);
+    q.a11 = lift<T>(p.a11, t->a11);
+    q.a12 = lift<T>(p.a12, t->a12);
+    q.a21 = lift<T>(p.a21, t->a21);
+    q.a22 = lift<T>(p.a22, t->a22);
+    return q;
+  }
+}
+
+// Where a trajectory's standard normals come from: in-kernel Philox (native) or the caller's buffer (parity).
+struct NormalSource {
+  uint64_t key, idx;
+  const double *z;
+  __device__ __forceinline__ NormalSource(const EuroArgs &a, bool parity, int64_t i, int per_path) {
+    z = nullptr;
+    key = idx = 0;
+    if (parity) {
+      z = a.normals + (size_t)i * (size_t)per_path;
+    } else if (a.seeds) {
+      key = a.seeds[i];
+    } else {
+      key = a.base_seed;
+      idx = (uint64_t)(a.path_offset + i);
+    }
+  }
+  // both normals of Philox block n (parity: elements 2n, 2n+1 of this trajectory's slice)
+  __device__ __forceinline__ void pair(bool parity, int n, double &z1, double &z2) const {
+    if (parity) {
+      z1 = z[2 * n];
+      z2 = z[2 * n + 1];
+    } else {
+      normal_pair(key, idx, (uint32_t)n, 0u, z1, z2);
+    }
+  }
+};
+
+// ---- one trajectory (or antithetic pair) -> terminal spot(s) in number type T ---------------------------
+template <int KIND, class T, bool ANTI>
+__device__ __forceinline__ void simulate(const EuroArgs &a, const PathParams<T> &p, bool parity, bool split, int64_t i,
+                                         T &Sp, T &Sm) {
+  const int M = a.n_steps;
+  if constexpr (KIND == K_GBM_TERMINAL) {
+    // marginal_law + final_sample, montecarlo.jl:293-303, 384-390
+    NormalSource src(a, parity, i, 1);
+    double z1, z2;
+    if (parity) z1 = src.z[0];
+    else src.pair(false, 0, z1, z2);
+    const T X = fma_(p.sd, z1, p.mu);
+    Sp = exp_(X);
+    if (ANTI) Sm = exp_(p.mu * 2.0 - X);
+  } else if constexpr (KIND == K_GBM_EM || KIND == K_GBM_STEPS) {
+    NormalSource src(a, parity, i, M);
+    T sp = KIND == K_GBM_EM ? p.x0 : p.S0;
+    T sm = sp;
+#pragma unroll 1
+    for (int n = 0; n < M; n += 2) {
+      double za, zb;
+      if (parity) {
+        za = src.z[n];
+        zb = n + 1 < M ? src.z[n + 1] : 0.0;
+      } else {
+        src.pair(false, n >> 1, za, zb);
+      }
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        if (n + h < M) {
+          const double z = h ? zb : za;
+          if constexpr (KIND == K_GBM_EM) {
+            const double dW = p.sqdt * z;
+            gbm_em_step(p, sp, dW);
+            if (ANTI) gbm_em_step(p, sm, -dW);  // NoiseGrid(t, -W) montecarlo.jl:258
+          } else {
+            gbm_exact_step(p, sp, z, 1.0);
+            if (ANTI) gbm_exact_step(p, sm, z, -1.0);  // sigma -> -sigma, same normals (montecarlo.jl:270-284)
+          }
+        }
+      }
+    }
+    if constexpr (KIND == K_GBM_EM) {
+      Sp = exp_(sp);  // final_sample montecarlo.jl:398
+      if (ANTI) Sm = exp_(sm);
+    } else {
+      Sp = sp;
+      if (ANTI) Sm = sm;
+    }
+  } else {
+    NormalSource src(a, parity, i, 2 * M);
+    T xp = p.x0, vp = p.v0, xm = p.x0, vm = p.v0;
+#pragma unroll 1
+    for (int n = 0; n < M; ++n) {
+      double z1, z2;
+      src.pair(parity, n, z1, z2);
+      const T dW1 = fma_(p.a12, z2, p.a11 * z1);
+      const T dW2 = fma_(p.a22, z2, p.a21 * z1);
+      heston_em_step(p, split, xp, vp, dW1, dW2);
+      if (ANTI) heston_em_step(p, split, xm, vm, -dW1, -dW2);
+    }
+    Sp = exp_(xp);
+    if (ANTI) Sm = exp_(xm);
+  }
+}
+
+// PARITY / SPLIT: 0 or 1 = compile-time, 2 = read from the arguments (used by the tangent kernels to
+// keep the number of instantiations down).
+template <int KIND, class T, bool ANTI, int PARITY, int SPLIT>
+__global__ void __launch_bounds__(kThreads) european_kernel(const EuroArgs a, const TangentPack *__restrict__ tpack) {
+  constexpr int NT = num_traits<T>::ntan;
+  constexpr int NACC = nacc_of<T>();
+  constexpr int NV = 1 + NT;                 // values per terminal state: S, dS_1..dS_NT
+  constexpr int NSIDE = ANTI ? 2 : 1;
+  constexpr int STAGE = NV * NSIDE * kThreads;
+  constexpr int RED = NACC * kThreads;
+  __shared__ double smem[STAGE > RED ? STAGE : RED];
+
+  const bool parity = PARITY == 2 ? a.parity != 0 : PARITY == 1;
+  const bool split = SPLIT == 2 ? a.split != 0 : SPLIT == 1;
+  const PathParams<T> p = lift_params<T>(a.p, tpack);
+
+  const int tid = threadIdx.x;
+  const int KP = 1 << a.kp_log2;        // payoffs padded to a power of two <= 256
+  const int k = tid & (KP - 1);         // my strike
+  const int g = tid >> a.kp_log2;       // my path group
+  const int G = kThreads >> a.kp_log2;  // number of path groups
+  double strike = 0.0, cp = 0.0;
+  if (k < a.npay) {
+    strike = a.payoffs[k].strike;
+    cp = a.payoffs[k].cp;
+  }
+  double acc[NACC];
+#pragma unroll
+  for (int c = 0; c < NACC; ++c) acc[c] = 0.0;
+
+  for (int64_t base = (int64_t)blockIdx.x * kThreads; base < a.n; base += (int64_t)gridDim.x * kThreads) {
+    const int64_t i = base + tid;
+    T Sp = zero<T>(), Sm = zero<T>();
+    if (i < a.n) {
+      simulate<KIND, T, ANTI>(a, p, parity, split, i, Sp, Sm);
+      if (a.terminal) {  // MonteCarloSolution.ensemble: (plus | minus), montecarlo.jl:400-402, 492
+        a.terminal[i] = value(Sp);
+        if (ANTI) a.terminal[a.n + i] = value(Sm);
+      }
+    }
+    smem[tid] = value(Sp);
+#pragma unroll
+    for (int q = 0; q < NT; ++q) smem[(1 + q) * kThreads + tid] = tangent(Sp, q);
+    if (ANTI) {
+      smem[NV * kThreads + tid] = value(Sm);
+#pragma unroll
+      for (int q = 0; q < NT; ++q) smem[(NV + 1 + q) * kThreads + tid] = tangent(Sm, q);
+    }
+    __syncthreads();
+    const int64_t rem = a.n - base;
+    const int nvalid = rem < kThreads ? (int)rem : kThreads;
+    if (k < a.npay) {
+      for (int j = g; j < nvalid; j += G) {
+        const double sp = smem[j];
+        const double ep = cp * (sp - strike);
+        double pay = fmax(ep, 0.0);  // payoffs.jl:154-156
+        const double ip = ep > 0.0 ? cp : 0.0;
+        bool bad = !isfinite(sp);
+        double im = 0.0;
+        if (ANTI) {
+          const double sm = smem[NV * kThreads + j];
+          const double em = cp * (sm - strike);
+          pay = 0.5 * (pay + fmax(em, 0.0));  // reduce_payoffs montecarlo.jl:430-432
+          im = em > 0.0 ? cp : 0.0;
+          bad = bad || !isfinite(sm);
+        }
+        acc[0] += pay;
+        acc[1] = fma(pay, pay, acc[1]);
+        if (k == 0 && bad) acc[2] += 1.0;
+#pragma unroll
+        for (int q = 0; q < NT; ++q) {
+          double dpay = ip * smem[(1 + q) * kThreads + j];  // cp 1{cp(S-K)>0} dS
+          if (ANTI) dpay = 0.5 * (dpay + im * smem[(NV + 1 + q) * kThreads + j]);
+          acc[3 + q] += dpay;
+          acc[3 + NT + q] = fma(dpay, dpay, acc[3 + NT + q]);
+        }
+      }
+    }
+    __syncthreads();
+  }
+
+  // fixed-order reduction over the path groups that share a strike
+#pragma unroll
+  for (int c = 0; c < NACC; ++c) smem[c * kThreads + tid] = acc[c];
+  __syncthreads();
+  if (tid < a.npay) {
+    double *out = a.partials + ((size_t)blockIdx.x * a.npay + tid) * NACC;
+    for (int c = 0; c < NACC; ++c) {
+      double t = 0.0;
+      for (int gg = 0; gg < G; ++gg) t += smem[c * kThreads + (gg << a.kp_log2) + tid];
+      out[c] = t;
+    }
+  }
+}
+
+// Sum the per-block partials in a fixed order: one block per payoff.
+__global__ void __launch_bounds__(kThreads) finalize_kernel(const double *partials, int nblocks, int npay, int nacc,
+                                                            double *out) {
+  __shared__ double scratch[kThreads / 32];
+  const int k = blockIdx.x;
+  for (int c = 0; c < nacc; ++c) {
+    double v = 0.0;
+    for (int b = threadIdx.x; b < nblocks; b += kThreads) v += partials[((size_t)b * npay + k) * nacc + c];
+    const double t = block_sum<kThreads>(v, scratch);
+    if (threadIdx.x == 0) out[(size_t)k * nacc + c] = t;
+  }
+}
+
+// ---- host side --------------------------------------------------------------------------------------
+
+int validate_model_sim(hh_ctx *ctx, const hh_model *m, const hh_sim *s) {
+  if (!m || !s) return ctx->fail(HH_ERR_ARG, "model/sim is NULL");
+  if (s->n_paths <= 0) return ctx->fail(HH_ERR_ARG, "n_paths must be positive (got %lld)", (long long)s->n_paths);
+  if (s->scheme != HH_SCHEME_EXACT_TERMINAL && s->n_steps <= 0)
+    return ctx->fail(HH_ERR_ARG, "n_steps must be positive (got %d)", s->n_steps);
+  if (s->vr != HH_VR_NONE && s->vr != HH_VR_ANTITHETIC)
+    return ctx->fail(HH_ERR_ARG, "unknown variance reduction %d", s->vr);
+  if (s->rng_mode != HH_RNG_NORMALS && s->rng_mode != HH_RNG_PHILOX)
+    return ctx->fail(HH_ERR_ARG, "unknown rng_mode %d", s->rng_mode);
+  if (s->rng_mode == HH_RNG_NORMALS && !s->normals)
+    return ctx->fail(HH_ERR_ARG, "rng_mode = HH_RNG_NORMALS needs a normals buffer");
+  if (m->kind == HH_MODEL_GBM) {
+    if (s->scheme != HH_SCHEME_EM && s->scheme != HH_SCHEME_EXACT_TERMINAL && s->scheme != HH_SCHEME_EXACT_STEPS)
+      return ctx->fail(HH_ERR_ARG, "scheme %d is not defined for LognormalDynamics", s->scheme);
+  } else if (m->kind == HH_MODEL_HESTON) {
+    if (s->scheme != HH_SCHEME_EM && s->scheme != HH_SCHEME_HESTON_BK)
+      return ctx->fail(HH_ERR_ARG, "scheme %d is not defined for HestonDynamics", s->scheme);
+    // Q5: Antithetic + HestonBroadieKaya calls mean(::LogHestonDistribution), which does not exist (montecarlo.jl:387)
+    if (s->scheme == HH_SCHEME_HESTON_BK && s->vr == HH_VR_ANTITHETIC)
+      return ctx->fail(HH_ERR_UNSUPPORTED, "Antithetic + HestonBroadieKaya is a MethodError in the reference (Q5)");
+  } else {
+    return ctx->fail(HH_ERR_ARG, "unknown model kind %d", m->kind);
+  }
+  if (!(m->S0 > 0.0)) return ctx->fail(HH_ERR_ARG, "spot must be positive");
+  if (!(m->T > 0.0)) return ctx->fail(HH_ERR_ARG, "time to expiry must be positive");
+  return HH_OK;
+}
+
+template <int KIND, class T, bool ANTI, int PARITY, int SPLIT>
+static cudaError_t launch_one(const EuroArgs &a, const TangentPack *tp, int sm_count, cudaStream_t st, int *nblocks,
+                              bool query_only) {
+  auto kern = european_kernel<KIND, T, ANTI, PARITY, SPLIT>;
+  int occ = 0;
+  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, 0);
+  if (e != cudaSuccess) return e;
+  if (occ < 1) occ = 1;
+  const int64_t batches = (a.n + kThreads - 1) / kThreads;
+  int64_t grid = (int64_t)sm_count * occ;  // persistent: one wave, grid-stride over batches
+  if (grid > batches) grid = batches;
+  *nblocks = (int)grid;
+  if (query_only) return cudaSuccess;
+  kern<<<(unsigned)grid, kThreads, 0, st>>>(a, tp);
+  return cudaGetLastError();
+}
+
+// plain pricing: PARITY and SPLIT are compile-time
+template <int KIND, bool ANTI>
+static cudaError_t launch_plain(const EuroArgs &a, int sm_count, cudaStream_t st, int *nb, bool q) {
+  if (KIND == K_HESTON_EM) {
+    if (a.parity) {
+      if (a.split) return launch_one<KIND, double, ANTI, 1, 1>(a, nullptr, sm_count, st, nb, q);
+      return launch_one<KIND, double, ANTI, 1, 0>(a, nullptr, sm_count, st, nb, q);
+    }
+    if (a.split) return launch_one<KIND, double, ANTI, 0, 1>(a, nullptr, sm_count, st, nb, q);
+    return launch_one<KIND, double, ANTI, 0, 0>(a, nullptr, sm_count, st, nb, q);
+  }
+  if (a.parity) return launch_one<KIND, double, ANTI, 1, 0>(a, nullptr, sm_count, st, nb, q);
+  return launch_one<KIND, double, ANTI, 0, 0>(a, nullptr, sm_count, st, nb, q);
+}
+
+template <int KIND, int P>
+static cudaError_t launch_tan(const EuroArgs &a, const TangentPack *tp, bool anti, int sm_count, cudaStream_t st,
+                              int *nb, bool q) {
+  if (anti) return launch_one<KIND, Dual<P>, true, 2, 2>(a, tp, sm_count, st, nb, q);
+  return launch_one<KIND, Dual<P>, false, 2, 2>(a, tp, sm_count, st, nb, q);
+}
+
+template <int KIND>
+static cudaError_t launch_kind(const EuroArgs &a, const TangentPack *tp, int P, bool anti, int sm_count,
+                               cudaStream_t st, int *nb, bool q) {
+  switch (P) {
+    case 0: return anti ? launch_plain<KIND, true>(a, sm_count, st, nb, q) : launch_plain<KIND, false>(a, sm_count, st, nb, q);
+    case 1: return launch_tan<KIND, 1>(a, tp, anti, sm_count, st, nb, q);
+    case 2: return launch_tan<KIND, 2>(a, tp, anti, sm_count, st, nb, q);
+    case 4: return launch_tan<KIND, 4>(a, tp, anti, sm_count, st, nb, q);
+    default: return launch_tan<KIND, 8>(a, tp, anti, sm_count, st, nb, q);
+  }
+}
+
+static cudaError_t launch_any(int kind, const EuroArgs &a, const TangentPack *tp, int P, bool anti, int sm_count,
+                              cudaStream_t st, int *nb, bool q) {
+  switch (kind) {
+    case K_GBM_EM: return launch_kind<K_GBM_EM>(a, tp, P, anti, sm_count, st, nb, q);
+    case K_GBM_TERMINAL: return launch_kind<K_GBM_TERMINAL>(a, tp, P, anti, sm_count, st, nb, q);
+    case K_GBM_STEPS: return launch_kind<K_GBM_STEPS>(a, tp, P, anti, sm_count, st, nb, q);
+    default: return launch_kind<K_HESTON_EM>(a, tp, P, anti, sm_count, st, nb, q);
+  }
+}
+
+// Scalars derived on the host from the model, and their tangents (chain rule through the same formulas).
+static int build_args(hh_ctx *ctx, const hh_model *m, const hh_sim *s, const hh_tangent *tg, int ntan, EuroArgs &a,
+                      TangentPack &tp, int &kind) {
+  memset(&a, 0, sizeof a);
+  memset(&tp, 0, sizeof tp);
+  const int nsteps = s->scheme == HH_SCHEME_EXACT_TERMINAL ? 1 : s->n_steps;
+  a.n = s->n_paths;
+  a.path_offset = s->path_offset;
+  a.base_seed = s->base_seed;
+  a.n_steps = nsteps;
+  a.split = (m->flags & HH_FLAG_SPLIT_STEP) ? 1 : 0;
+  a.parity = s->rng_mode == HH_RNG_NORMALS;
+  PathParams<double> &p = a.p;
+  const double dt = m->T / nsteps;  // montecarlo.jl:349
+  const double sqdt = sqrt(dt);
+  p.dt = dt;
+  p.sqdt = sqdt;
+  p.x0 = log(m->S0);
+  p.S0 = m->S0;
+  p.r = m->r;
+  for (int q = 0; q < ntan; ++q) {
+    tp.x0[q] = tg[q].dS0 / m->S0;
+    tp.S0[q] = tg[q].dS0;
+    tp.r[q] = tg[q].dr;
+  }
+  if (m->kind == HH_MODEL_GBM) {
+    p.sigma = m->sigma;
+    const double drift = m->r - 0.5 * (m->sigma * m->sigma);
+    for (int q = 0; q < ntan; ++q) tp.sigma[q] = tg[q].dsigma;
+    if (s->scheme == HH_SCHEME_EXACT_TERMINAL) {
+      kind = K_GBM_TERMINAL;
+      const double alpha = m->T;
+      const double c = (m->flags & HH_FLAG_Q1_SQRT_MEAN) ? sqrt(alpha) : alpha;  // Q1, montecarlo.jl:302
+      p.mu = log(m->S0) + (m->r - m->sigma * m->sigma / 2) * c;
+      p.sd = m->sigma * sqrt(alpha);
+      for (int q = 0; q < ntan; ++q) {
+        tp.mu[q] = tg[q].dS0 / m->S0 + (tg[q].dr - m->sigma * tg[q].dsigma) * c;
+        tp.sd[q] = tg[q].dsigma * sqrt(alpha);
+      }
+    } else {
+      kind = s->scheme == HH_SCHEME_EM ? K_GBM_EM : K_GBM_STEPS;
+      p.dt_drift = s->scheme == HH_SCHEME_EM ? dt * drift : drift * dt;
+      p.sig_sqdt = m->sigma * sqdt;
+      for (int q = 0; q < ntan; ++q) {
+        tp.dt_drift[q] = (tg[q].dr - m->sigma * tg[q].dsigma) * dt;
+        tp.sig_sqdt[q] = tg[q].dsigma * sqdt;
+      }
+    }
+  } else {
+    kind = K_HESTON_EM;
+    p.v0 = m->V0;
+    p.kappa = m->kappa;
+    p.theta = m->theta;
+    p.xi = m->xi;
+    p.a11 = sqdt * m->m11;
+    p.a12 = sqdt * m->m12;
+    p.a21 = sqdt * m->m21;
+    p.a22 = sqdt * m->m22;
+    for (int q = 0; q < ntan; ++q) {
+      tp.v0[q] = tg[q].dV0;
+      tp.kappa[q] = tg[q].dkappa;
+      tp.theta[q] = tg[q].dtheta;
+      tp.xi[q] = tg[q].dxi;
+      tp.a11[q] = sqdt * tg[q].dm11;
+      tp.a12[q] = sqdt * tg[q].dm12;
+      tp.a21[q] = sqdt * tg[q].dm21;
+      tp.a22[q] = sqdt * tg[q].dm22;
+    }
+  }
+  (void)ctx;
+  return HH_OK;
+}
+
+static int upload_inputs(hh_ctx *ctx, const hh_model *m, const hh_sim *s, const hh_payoff *payoffs, int npay,
+                         EuroArgs &a) {
+  cudaStream_t st = ctx->stream;
+  const int64_t N = s->n_paths;
+  const int ncomp = m->kind == HH_MODEL_HESTON ? 2 : 1;
+  a.npay = npay;
+  a.kp_log2 = 0;
+  while ((1 << a.kp_log2) < npay) a.kp_log2++;
+  HH_CUDA(ctx, ctx->d_payoffs.ensure(sizeof(hh_payoff) * (size_t)npay));
+  HH_CUDA(ctx, cudaMemcpyAsync(ctx->d_payoffs.ptr, payoffs, sizeof(hh_payoff) * (size_t)npay, cudaMemcpyHostToDevice, st));
+  a.payoffs = ctx->d_payoffs.as<hh_payoff>();
+  if (a.parity) {
+    const size_t bytes = sizeof(double) * (size_t)N * (size_t)a.n_steps * (size_t)ncomp;
+    HH_CUDA(ctx, ctx->d_normals.ensure(bytes));
+    HH_CUDA(ctx, cudaMemcpyAsync(ctx->d_normals.ptr, s->normals, bytes, cudaMemcpyHostToDevice, st));
+    a.normals = ctx->d_normals.as<double>();
+  } else if (s->seeds) {
+    const size_t bytes = sizeof(uint64_t) * (size_t)N;
+    HH_CUDA(ctx, ctx->d_seeds.ensure(bytes));
+    HH_CUDA(ctx, cudaMemcpyAsync(ctx->d_seeds.ptr, s->seeds, bytes, cudaMemcpyHostToDevice, st));
+    a.seeds = ctx->d_seeds.as<uint64_t>();
+  }
+  return HH_OK;
+}
+
+int european_launch(hh_ctx *ctx, const hh_model *m, const hh_sim *s, const hh_payoff *payoffs, int npay,
+                    int want_terminal) {
+  int rc = validate_model_sim(ctx, m, s);
+  if (rc) return rc;
+  if (npay < 1 || npay > kThreads || !payoffs)
+    return ctx->fail(HH_ERR_ARG, "npayoffs must be in [1, %d] (got %d)", kThreads, npay);
+  if (s->scheme == HH_SCHEME_HESTON_BK) return ctx->fail(HH_ERR_UNSUPPORTED, "use the Broadie-Kaya driver");
+  if (s->precision != HH_PREC_F64) return ctx->fail(HH_ERR_UNSUPPORTED, "f32 fast mode is not built in this version");
+
+  const int64_t N = s->n_paths;
+  const bool anti = s->vr == HH_VR_ANTITHETIC;
+  EuroArgs a;
+  TangentPack tp;
+  int kind = 0;
+  build_args(ctx, m, s, nullptr, 0, a, tp, kind);
+
+  HH_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  rc = upload_inputs(ctx, m, s, payoffs, npay, a);
+  if (rc) return rc;
+  if (want_terminal) {
+    HH_CUDA(ctx, ctx->d_terminal.ensure(sizeof(double) * (size_t)N * (anti ? 2 : 1)));
+    a.terminal = ctx->d_terminal.as<double>();
+  }
+  constexpr int NACC = nacc_of<double>();
+  int nblocks = 0;
+  HH_CUDA(ctx, launch_any(kind, a, nullptr, 0, anti, ctx->sm_count, st, &nblocks, true));
+  HH_CUDA(ctx, ctx->d_partials.ensure(sizeof(double) * (size_t)nblocks * npay * NACC));
+  HH_CUDA(ctx, ctx->d_final.ensure(sizeof(double) * (size_t)npay * NACC));
+  a.partials = ctx->d_partials.as<double>();
+
+  HH_CUDA(ctx, cudaEventRecord(ctx->ev0, st));
+  HH_CUDA(ctx, launch_any(kind, a, nullptr, 0, anti, ctx->sm_count, st, &nblocks, false));
+  finalize_kernel<<<npay, kThreads, 0, st>>>(a.partials, nblocks, npay, NACC, ctx->d_final.as<double>());
+  HH_CUDA(ctx, cudaGetLastError());
+  HH_CUDA(ctx, cudaEventRecord(ctx->ev1, st));
+
+  ctx->pend.active = true;
+  ctx->pend.npay = npay;
+  ctx->pend.nblocks = nblocks;
+  ctx->pend.n = N;
+  ctx->pend.anti = anti;
+  ctx->pend.want_terminal = want_terminal != 0;
+  return HH_OK;
+}
+
+int european_collect(hh_ctx *ctx, double discount, hh_result *results, double *terminal, size_t terminal_len) {
+  if (!ctx->pend.active) return ctx->fail(HH_ERR_ARG, "collect without a pending launch");
+  const int npay = ctx->pend.npay;
+  const int64_t N = ctx->pend.n;
+  constexpr int NACC = nacc_of<double>();
+  if (!results) return ctx->fail(HH_ERR_ARG, "results is NULL");
+  const size_t tlen = (size_t)N * (ctx->pend.anti ? 2 : 1);
+  if (terminal) {
+    if (!ctx->pend.want_terminal) return ctx->fail(HH_ERR_ARG, "terminal requested at collect but not at launch");
+    if (terminal_len < tlen) return ctx->fail(HH_ERR_ARG, "terminal buffer too short: %zu < %zu", terminal_len, tlen);
+  }
+  HH_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  std::vector<double> fin((size_t)npay * NACC);
+  HH_CUDA(ctx, cudaMemcpyAsync(fin.data(), ctx->d_final.ptr, sizeof(double) * fin.size(), cudaMemcpyDeviceToHost, st));
+  if (terminal)
+    HH_CUDA(ctx, cudaMemcpyAsync(terminal, ctx->d_terminal.ptr, sizeof(double) * tlen, cudaMemcpyDeviceToHost, st));
+  HH_CUDA(ctx, cudaStreamSynchronize(st));
+  ctx->pend.active = false;
+  float ms = 0.f;
+  HH_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+  for (int k = 0; k < npay; ++k) {
+    hh_result *r = &results[k];
+    memset(r, 0, sizeof *r);
+    r->sum = fin[(size_t)k * NACC + 0];
+    r->sumsq = fin[(size_t)k * NACC + 1];
+    r->n = N;
+    const double mean = r->sum / (double)N;
+    r->price = discount * mean;  // montecarlo.jl:489-490
+    double var = N > 1 ? (r->sumsq - (double)N * mean * mean) / (double)(N - 1) : 0.0;
+    if (var < 0) var = 0;
+    r->std_error = discount * sqrt(var / (double)N);
+    r->n_nonfinite = (int64_t)fin[2];
+    r->kernel_ms = ms;
+  }
+  return HH_OK;
+}
+
+int tangent_sums(hh_ctx *ctx, const hh_model *m, const hh_tangent *tg, int ntan, const hh_sim *s,
+                 const hh_payoff *payoffs, int npay, double *sums, double *kernel_ms) {
+  int rc = validate_model_sim(ctx, m, s);
+  if (rc) return rc;
+  if (!tg || ntan < 1 || ntan > kMaxTan) return ctx->fail(HH_ERR_ARG, "ntangents must be in [1, %d] (got %d)", kMaxTan, ntan);
+  if (npay < 1 || npay > kThreads || !payoffs || !sums)
+    return ctx->fail(HH_ERR_ARG, "npayoffs must be in [1, %d] and payoffs/sums non-NULL", kThreads);
+  if (s->scheme == HH_SCHEME_HESTON_BK)
+    return ctx->fail(HH_ERR_UNSUPPORTED, "pathwise tangents are not defined through the Broadie-Kaya sampler");
+  if (s->precision != HH_PREC_F64) return ctx->fail(HH_ERR_UNSUPPORTED, "tangents run in f64 only");
+
+  const bool anti = s->vr == HH_VR_ANTITHETIC;
+  const int P = ntan <= 1 ? 1 : ntan <= 2 ? 2 : ntan <= 4 ? 4 : 8;
+  const int NACC = 3 + 2 * P;
+  EuroArgs a;
+  TangentPack tp;
+  int kind = 0;
+  build_args(ctx, m, s, tg, ntan, a, tp, kind);
+
+  HH_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  rc = upload_inputs(ctx, m, s, payoffs, npay, a);
+  if (rc) return rc;
+  HH_CUDA(ctx, ctx->d_tangents.ensure(sizeof(TangentPack)));
+  HH_CUDA(ctx, cudaMemcpyAsync(ctx->d_tangents.ptr, &tp, sizeof tp, cudaMemcpyHostToDevice, st));
+  const TangentPack *dtp = ctx->d_tangents.as<TangentPack>();
+
+  int nblocks = 0;
+  HH_CUDA(ctx, launch_any(kind, a, dtp, P, anti, ctx->sm_count, st, &nblocks, true));
+  HH_CUDA(ctx, ctx->d_partials.ensure(sizeof(double) * (size_t)nblocks * npay * NACC));
+  HH_CUDA(ctx, ctx->d_final.ensure(sizeof(double) * (size_t)npay * NACC));
+  a.partials = ctx->d_partials.as<double>();
+
+  HH_CUDA(ctx, cudaEventRecord(ctx->ev0, st));
+  HH_CUDA(ctx, launch_any(kind, a, dtp, P, anti, ctx->sm_count, st, &nblocks, false));
+  finalize_kernel<<<npay, kThreads, 0, st>>>(a.partials, nblocks, npay, NACC, ctx->d_final.as<double>());
+  HH_CUDA(ctx, cudaGetLastError());
+  HH_CUDA(ctx, cudaEventRecord(ctx->ev1, st));
+
+  std::vector<double> fin((size_t)npay * NACC);
+  HH_CUDA(ctx, cudaMemcpyAsync(fin.data(), ctx->d_final.ptr, sizeof(double) * fin.size(), cudaMemcpyDeviceToHost, st));
+  HH_CUDA(ctx, cudaStreamSynchronize(st));
+  float ms = 0.f;
+  HH_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+  if (kernel_ms) *kernel_ms = ms;
+  const int stride = 2 + 2 * ntan;
+  for (int k = 0; k < npay; ++k) {
+    const double *f = fin.data() + (size_t)k * NACC;
+    double *o = sums + (size_t)k * stride;
+    o[0] = f[0];
+    o[1] = f[1];
+    for (int q = 0; q < ntan; ++q) {
+      o[2 + q] = f[3 + q];
+      o[2 + ntan + q] = f[3 + P + q];
+    }
+  }
+  return HH_OK;
+}
+
+}  // namespace hh

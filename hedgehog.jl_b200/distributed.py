@@ -1,0 +1,60 @@
+"""Multi-GPU plumbing: one process per GPU (torchrun), paths sharded by global trajectory index.
+
+The data path has no collective: each rank simulates its own contiguous block of trajectories with
+disjoint Philox counters. Only the partial sums [sum, sumsq, n] (and, for LSM, the per-date regression
+moments) are sum-allreduced — NCCL on GPU boxes, gloo in the CPU tests.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _abi as abi
+
+
+def allreduce_sum_f64(v: np.ndarray, group=None) -> np.ndarray:
+    import torch
+    import torch.distributed as dist
+    t = torch.from_numpy(np.ascontiguousarray(v, dtype=np.float64).copy())
+    if dist.get_backend(group) == "nccl":
+        t = t.cuda()
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t.cpu().numpy().reshape(np.shape(v))
+
+
+class _DevArray:
+    """Wrap a raw device pointer for torch.as_tensor (zero copy) via __cuda_array_interface__."""
+
+    def __init__(self, ptr: int, count: int, stream: int):
+        self.__cuda_array_interface__ = {"shape": (count,), "typestr": "<f8", "data": (ptr, False), "version": 3,
+                                         "strides": None, "stream": stream or 1}
+
+
+def make_comm(shard, group=None):
+    """hh_comm whose callback sum-allreduces a device buffer in place with torch.distributed (NCCL)."""
+    import torch
+    import torch.distributed as dist
+    rank, world = shard
+
+    def _cb(user, dev_ptr, count, stream):
+        try:
+            if dist.get_backend(group) == "nccl":
+                ext = torch.cuda.ExternalStream(stream) if stream else torch.cuda.current_stream()
+                with torch.cuda.stream(ext):
+                    t = torch.as_tensor(_DevArray(dev_ptr, count, stream), device="cuda")
+                    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+                ext.synchronize()
+            else:  # gloo (CPU tests with an injected engine): dev_ptr is a host pointer
+                buf = (C.c_double * count).from_address(dev_ptr)
+                t = torch.frombuffer(buf, dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+            return 0
+        except Exception as e:  # never let an exception cross the C boundary
+            import sys
+            print(f"[hedgehog.jl_b200] allreduce callback failed: {e!r}", file=sys.stderr)
+            return 1
+
+    cb = abi.hh_allreduce_fn(_cb)
+    comm = abi.hh_comm(cb, None, rank, world)
+    return comm, cb

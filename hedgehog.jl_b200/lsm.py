@@ -1,0 +1,43 @@
+"""solve(::PricingProblem{American}, ::LSM) on the GPU — mirror of src/pricing_methods/least_squares_montecarlo.jl:99-136."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _abi as abi
+from . import api
+
+
+def solve_lsm(prob, method, *, engine=None, shard=None, group=None, stopping_info=True, spot_paths=False):
+    """`stopping_info` / `spot_paths` choose whether LSMSolution carries the per-column (tau, value) pairs and the
+    (nsteps+1) x ncols spot matrix (4 GB at config C3, hence off by default; the reference always returns both)."""
+    if not isinstance(prob.payoff.exercise_style, api.American):
+        raise TypeError("solve(::PricingProblem, ::LSM) is defined for American exercise")
+    mc = method.mc_method
+    eng = engine or api.default_engine()
+    shard, reduce = api._shard_and_reduce(shard, group)
+    mdl = api._model_of(prob, mc)
+    sim = api._sim_of(mc, api._scheme_of(mc, for_lsm=True), shard)
+    m = prob.market_inputs
+    T = api.yearfrac(m.referenceDate, prob.payoff.expiry)                                 # lsm.jl:104
+    step_discount = api.df(m.rate, api.add_yearfrac(m.referenceDate, T / sim.n_steps))   # lsm.jl:110
+    comm = None
+    keep = None
+    if reduce is not None:
+        from .distributed import make_comm
+        comm, keep = make_comm(shard, group)
+    out, tau, val, paths = eng.lsm_american(mdl, sim, (prob.payoff.strike, prob.payoff.call_put()), method.degree,
+                                            step_discount, want_stopping=stopping_info, want_paths=spot_paths, comm=comm)
+    del keep
+    s = np.array([out.sum, out.sumsq, float(out.n)])
+    if reduce is not None:
+        s = reduce(s)
+    n = s[2]
+    mean = s[0] / n
+    var = max((s[1] - n * mean * mean) / (n - 1), 0.0) if n > 1 else 0.0
+    info = list(zip(tau.tolist(), val.tolist())) if stopping_info else None
+    stats = {"kernel_ms": out.kernel_ms, "path_ms": out.path_ms, "regress_ms": out.regress_ms,
+             "n_dates_skipped": out.n_dates_skipped, "n_cols_local": int(out.n), "n_cols_total": int(n)}
+    return api.LSMSolution(prob, method, float(mean), info, None if paths is None else paths.T,
+                           float(np.sqrt(var / n)), stats)

@@ -1,0 +1,12 @@
+"""Import shim: the package directory is `hedgehog.jl_b200/` (a dot is not importable), so load it by path
+under the module name `hedgehog_jl_b200`."""
+import importlib.util as _u
+import os as _os
+import sys as _sys
+
+_dir = _os.path.join(_os.path.dirname(_os.path.abspath(__file__)), "hedgehog.jl_b200")
+_spec = _u.spec_from_file_location("hedgehog_jl_b200", _os.path.join(_dir, "__init__.py"),
+                                   submodule_search_locations=[_dir])
+_mod = _u.module_from_spec(_spec)
+_sys.modules["hedgehog_jl_b200"] = _mod
+_spec.loader.exec_module(_mod)

@@ -1,0 +1,223 @@
+/*
+ * hedgehog_mc.h — C ABI of libhedgehog_mc.so, the B200 (sm_100a) Monte Carlo pricing path.
+ *
+ * This is the drop-in boundary for the hot path of aleCombi/Hedgehog.jl (reference paths are
+ * relative to the reference checkout):
+ *
+ *   solve(::PricingProblem{VanillaOption{..European..}}, ::MonteCarlo)   src/pricing_methods/montecarlo.jl:478-493
+ *   solve(::PricingProblem{VanillaOption{..American..}}, ::LSM)          src/pricing_methods/least_squares_montecarlo.jl:99-136
+ *   solve(::GreekProblem / ::BatchGreekProblem, ::ForwardAD, method)     src/greeks/greeks_problem.jl:249-262,559-568
+ *
+ * The reference is pure Julia and has no FFI of its own; a Julia host file binds these entry
+ * points with `ccall` (see INTEGRATION.md and hedgehog.jl_b200/julia/HedgehogB200.jl).
+ *
+ * Conventions
+ *   - plain C, POD structs only, no exceptions cross the boundary;
+ *   - return code 0 = OK, <0 = argument error, >0 = CUDA error class; text via hh_last_error();
+ *   - the caller owns every buffer it passes; the library never keeps a caller pointer past
+ *     return; device memory, streams and events live inside the opaque hh_ctx;
+ *   - nullable outputs (terminal values, stopping info, spot paths) are only materialised /
+ *     copied to the host when the pointer is non-null;
+ *   - calls on one hh_ctx are serialised by an internal mutex; each call blocks until its
+ *     results are on the host (the *_launch/_collect pair splits that for benchmarking);
+ *   - there is NO CPU fallback: every entry point fails with HH_ERR_CUDA if no sm_100 GPU
+ *     is usable.
+ */
+#ifndef HEDGEHOG_MC_H
+#define HEDGEHOG_MC_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HH_VERSION 100 /* 0.1.0 */
+
+/* ---- error codes ------------------------------------------------------------------- */
+#define HH_OK 0
+#define HH_ERR_ARG (-1)         /* bad argument (mirrors the reference's ArgumentError, montecarlo.jl:65-66) */
+#define HH_ERR_UNSUPPORTED (-2) /* combination the reference itself cannot run (e.g. Q5: Antithetic + BK) */
+#define HH_ERR_CUDA 1           /* CUDA runtime failure, see hh_last_error */
+#define HH_ERR_NOMEM 2          /* device allocation failed */
+#define HH_ERR_COMM 3           /* the caller-supplied allreduce callback failed */
+
+/* ---- enums (int32 in the structs) ---------------------------------------------------- */
+/* dynamics: LognormalDynamics / HestonDynamics                montecarlo.jl:15,22 */
+#define HH_MODEL_GBM 0
+#define HH_MODEL_HESTON 1
+
+/* strategy                                                    montecarlo.jl:93,108,115 */
+#define HH_SCHEME_EM 0             /* EulerMaruyama: log-space EM, montecarlo.jl:166-202 + heston.jl:7-52 */
+#define HH_SCHEME_EXACT_TERMINAL 1 /* BlackScholesExact, European path: one draw from marginal_law, montecarlo.jl:293-303,454-459 */
+#define HH_SCHEME_EXACT_STEPS 2    /* BlackScholesExact as NoiseProblem (LSM path generator), S-space, montecarlo.jl:140-159 */
+#define HH_SCHEME_HESTON_BK 3      /* HestonBroadieKaya, heston.jl:125-300 + sample_from_cf.jl */
+
+/* variance reduction                                           montecarlo.jl:36,43 */
+#define HH_VR_NONE 0
+#define HH_VR_ANTITHETIC 1
+
+#define HH_PREC_F64 0
+#define HH_PREC_F32 1 /* fast mode: f32 state and normals, f64 accumulation */
+
+#define HH_RNG_PHILOX 0  /* in-kernel Philox4x32-10 + Box-Muller */
+#define HH_RNG_NORMALS 1 /* parity mode: consume caller-supplied standard normals */
+
+/* hh_model.flags */
+#define HH_FLAG_SPLIT_STEP 1u   /* EM{split=true}: diffusion evaluated at K = u + dt f(u) [StochasticDiffEq default] */
+#define HH_FLAG_Q1_SQRT_MEAN 2u /* marginal_law puts sqrt(alpha) in the mean (montecarlo.jl:302); off = alpha */
+
+typedef struct hh_ctx hh_ctx;
+
+/* Model scalars, extracted on the host exactly as the reference does
+ * (T: montecarlo.jl:147; r = zero_rate(rate, 0.0): :150; sigma: :151; Heston fields: :201). */
+typedef struct hh_model {
+  int32_t kind;  /* HH_MODEL_* */
+  uint32_t flags; /* HH_FLAG_* */
+  double S0;     /* spot */
+  double r;      /* flat zero rate used in the drift */
+  double T;      /* yearfrac(referenceDate, expiry), ACT/365 */
+  double sigma;  /* GBM volatility (FlatVolSurface) */
+  double V0, kappa, theta, xi, rho; /* Heston: initial var, mean reversion, long-run var, vol-of-vol, correlation */
+  /* Factor M of the Brownian correlation, M M^T = [1 rho; rho 1]:  dW = sqrt(dt) * M * (Z1, Z2)^T.
+   * Any factor gives the same law; it only fixes how parity-mode normals map to increments
+   * (CorrelatedWienerProcess, heston.jl:18-20). */
+  double m11, m12, m21, m22;
+} hh_model;
+
+/* Broadie-Kaya tolerances; defaults are the reference's keyword defaults
+ * (sample_from_cf.jl:27 n=5, :50 h=1e-2, :75 cf_tol=1e-3, :110-112 atol=1e-4, 10, 100). */
+typedef struct hh_bk_config {
+  int32_t n_std;            /* n in h = pi/(mean + n*sd) */
+  int32_t maxiter_newton;   /* secant evaluations */
+  int32_t maxiter_bisection;
+  int32_t max_terms;        /* safety cap on the Fourier series length (reference: 10^9) */
+  double h_fd;              /* finite-difference step for the CF moments */
+  double cf_tol;
+  double atol;
+} hh_bk_config;
+
+/* SimulationConfig (montecarlo.jl:58-79) + execution knobs. */
+typedef struct hh_sim {
+  int64_t n_paths;     /* trajectories simulated by THIS call (pairs when antithetic) */
+  int64_t path_offset; /* global index of the first local trajectory (multi-GPU shards); 0 on one GPU */
+  int32_t n_steps;     /* config.steps; dt = T / n_steps (montecarlo.jl:349) */
+  int32_t scheme;      /* HH_SCHEME_* */
+  int32_t vr;          /* HH_VR_* */
+  int32_t precision;   /* HH_PREC_* */
+  int32_t rng_mode;    /* HH_RNG_* */
+  int32_t reserved;
+  uint64_t base_seed;  /* Philox key when seeds == NULL; counter carries the global path index */
+  const uint64_t *seeds;  /* host, nullable: one key per local trajectory (config.seeds), len >= n_paths */
+  const double *normals;  /* host, parity mode only: Z[path][step][component] contiguous */
+  hh_bk_config bk;
+} hh_sim;
+
+/* VanillaOption payoff max(cp*(S-K),0)                          payoffs.jl:154-156 */
+typedef struct hh_payoff {
+  double strike;
+  double cp; /* +1 call, -1 put */
+} hh_payoff;
+
+typedef struct hh_result {
+  double sum;    /* sum over local trajectories of the (pair-averaged) payoff */
+  double sumsq;  /* sum of squares of the same */
+  int64_t n;     /* trajectories contributing */
+  double price;  /* discount * sum / n   (montecarlo.jl:490) */
+  double std_error; /* discount * sample std / sqrt(n); not in the reference */
+  int64_t n_nonfinite; /* terminal values that were NaN/Inf */
+  int64_t n_fallback;  /* BK inversions that fell back (the reference @warns, sample_from_cf.jl:125,131) */
+  double kernel_ms;    /* device time of the kernels of this call (CUDA events on the ctx stream) */
+} hh_result;
+
+/* One tangent direction = d(model)/d(parameter) plus d(discount)/d(parameter). */
+typedef struct hh_tangent {
+  double dS0, dr, dsigma, dV0, dkappa, dtheta, dxi;
+  double dm11, dm12, dm21, dm22; /* derivative of the correlation factor (rho sensitivity) */
+  double ddiscount;
+} hh_tangent;
+
+typedef struct hh_lsm_result {
+  double sum, sumsq; /* of discount^tau * value over local columns */
+  int64_t n;         /* local columns (2*n_paths when antithetic) */
+  double price;      /* mean(discount^tau * value)   least_squares_montecarlo.jl:132-133 */
+  double std_error;
+  int64_t n_dates_skipped; /* dates with no in-the-money path (:122) */
+  double kernel_ms;
+  double path_ms; /* path generation + store */
+  double regress_ms; /* backward induction */
+} hh_lsm_result;
+
+/* Sum-allreduce of `count` doubles living in DEVICE memory, in place, ordered after work already
+ * enqueued on `cuda_stream`. Supplied by a multi-GPU host (torch.distributed / NCCL); NULL on one GPU. */
+typedef int (*hh_allreduce_fn)(void *user, void *dev_ptr, size_t count, void *cuda_stream);
+typedef struct hh_comm {
+  hh_allreduce_fn allreduce_sum_f64;
+  void *user;
+  int32_t rank, world;
+} hh_comm;
+
+/* ---- lifetime --------------------------------------------------------------------------- */
+int hh_version(void);
+int hh_create(hh_ctx **out, int device);
+int hh_destroy(hh_ctx *ctx);
+const char *hh_last_error(hh_ctx *ctx); /* ctx may be NULL: last error of hh_create on this thread */
+/* Run on a caller-owned CUDA stream (e.g. torch's current stream); NULL restores the ctx stream. */
+int hh_set_stream(hh_ctx *ctx, void *cuda_stream);
+int hh_device_info(hh_ctx *ctx, int32_t *sm_count, int32_t *cc_major, int32_t *cc_minor, size_t *total_mem);
+void hh_default_bk_config(hh_bk_config *out);
+/* Measured FP64 peak of this GPU: a register-resident DFMA-chain microbenchmark (2 FLOP per DFMA).
+ * MEASURED_PEAKS.json holds no FP64 figure, so bench.py's roofline denominator comes from here. */
+int hh_bench_fp64_peak(hh_ctx *ctx, double *tflops, double *ms);
+
+/* ---- European Monte Carlo: solve(::PricingProblem, ::MonteCarlo), montecarlo.jl:478-493 ------
+ * One simulation prices `npayoffs` vanilla payoffs on the same paths (npayoffs = 1 is the
+ * reference's solve; >1 is the strike grid of BasketPricingProblem, src/calibration/basket.jl:35-38).
+ * `terminal`: nullable; S_T per trajectory (MonteCarloSolution.ensemble, montecarlo.jl:492),
+ * length n_paths (NoVR) or 2*n_paths (antithetic: [plus | minus], montecarlo.jl:400-402). */
+int hh_mc_european(hh_ctx *ctx, const hh_model *model, const hh_sim *sim, const hh_payoff *payoffs,
+                   int npayoffs, double discount, hh_result *results, double *terminal,
+                   size_t terminal_len);
+
+/* Split form: launch enqueues the kernels (inputs uploaded first), collect waits and reads back. */
+int hh_mc_european_launch(hh_ctx *ctx, const hh_model *model, const hh_sim *sim,
+                          const hh_payoff *payoffs, int npayoffs, int want_terminal);
+int hh_mc_european_collect(hh_ctx *ctx, double discount, hh_result *results, double *terminal,
+                           size_t terminal_len);
+
+/* ---- pathwise forward-mode Greeks: ForwardDiff through solve, greeks_problem.jl:249-262 ------
+ * Propagates `ntangents` dual directions through the same simulation.
+ * tangent_results[k*ntangents + p] = d price_k / d direction_p (product rule with ddiscount applied);
+ * tangent_stderr likewise (nullable). */
+int hh_mc_european_tangent(hh_ctx *ctx, const hh_model *model, const hh_tangent *tangents,
+                           int ntangents, const hh_sim *sim, const hh_payoff *payoffs, int npayoffs,
+                           double discount, hh_result *results, double *tangent_results,
+                           double *tangent_stderr);
+/* Raw sums for multi-GPU reduction: out[k*(2+2*ntangents) + {0: sum payoff, 1: sum payoff^2,
+ * 2+p: sum dpayoff_p, 2+ntangents+p: sum dpayoff_p^2}] over local trajectories. */
+int hh_mc_european_tangent_sums(hh_ctx *ctx, const hh_model *model, const hh_tangent *tangents,
+                                int ntangents, const hh_sim *sim, const hh_payoff *payoffs,
+                                int npayoffs, double *sums, double *kernel_ms);
+
+/* ---- American LSM: solve(::PricingProblem{American}, ::LSM), least_squares_montecarlo.jl:99-136 --
+ * stop_idx/stop_val: nullable, stopping_info[(tau, value)] per column (:112,:163-164);
+ * spot_paths: nullable, (n_steps+1) x ncols, column-major like the reference Matrix (:50);
+ * comm: nullable; when set, the per-date regression moments are sum-allreduced across ranks. */
+int hh_lsm_american(hh_ctx *ctx, const hh_model *model, const hh_sim *sim, const hh_payoff *payoff,
+                    int degree, double step_discount, const hh_comm *comm, hh_lsm_result *out,
+                    int32_t *stop_idx, double *stop_val, double *spot_paths);
+
+/* ---- Broadie-Kaya deterministic pieces (parity probes; heston.jl:184-212, sample_from_cf.jl:50-96) --
+ * Evaluate Phi(a_j) of the integrated variance for n independent (V0, VT) pairs on the GPU.
+ * a: [n][na]; out_re/out_im: [n][na]; the angle is unwrapped along j as the reference does. */
+int hh_bk_chf(hh_ctx *ctx, const hh_model *model, double tau, const double *V0, const double *VT,
+              int n, const double *a, int na, double *out_re, double *out_im);
+/* log I_nu(z) for complex z, real order nu > -1 (SpecialFunctions.besseli, heston.jl:173,207). */
+int hh_bk_log_besseli(hh_ctx *ctx, double nu, const double *z_re, const double *z_im, int n,
+                      double *out_re, double *out_im);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HEDGEHOG_MC_H */
