@@ -178,8 +178,11 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     eng = hh.default_engine(local_rank)
-    stream = torch.cuda.current_stream()
-    eng.set_stream(stream.cuda_stream)  # so torch.cuda.Event brackets exactly the library's kernels
+    # a non-default torch stream shared with the library, so torch.cuda.Event brackets exactly its kernels
+    # (torch's legacy default stream is the NULL handle, which hh_set_stream treats as "use the ctx stream")
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    eng.set_stream(stream.cuda_stream)
 
     def barrier():
         if world > 1:
