@@ -25,12 +25,13 @@ __device__ __forceinline__ u32x4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_
                                                uint32_t k1) {
 #pragma unroll
   for (int r = 0; r < 10; ++r) {
-    const uint64_t p0 = (uint64_t)kPhiloxM0 * c0;  // IMAD.WIDE.U32
-    const uint64_t p1 = (uint64_t)kPhiloxM1 * c2;
-    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;  // LOP3
-    const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
-    c1 = (uint32_t)p1;
-    c3 = (uint32_t)p0;
+    uint32_t lo0, hi0, lo1, hi1;  // one IMAD.WIDE.U32 each
+    asm("{ .reg .b64 t; mul.wide.u32 t, %2, %3; mov.b64 {%0, %1}, t; }" : "=r"(lo0), "=r"(hi0) : "r"(c0), "r"(kPhiloxM0));
+    asm("{ .reg .b64 t; mul.wide.u32 t, %2, %3; mov.b64 {%0, %1}, t; }" : "=r"(lo1), "=r"(hi1) : "r"(c2), "r"(kPhiloxM1));
+    const uint32_t n0 = hi1 ^ c1 ^ k0;  // LOP3
+    const uint32_t n2 = hi0 ^ c3 ^ k1;
+    c1 = lo1;
+    c3 = lo0;
     c0 = n0;
     c2 = n2;
     k0 += kPhiloxW0;
@@ -39,23 +40,20 @@ __device__ __forceinline__ u32x4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_
   return u32x4{c0, c1, c2, c3};
 }
 
-// (0,1] and [0,1) uniforms with 53 bits, exactly as the oracle builds them.
-__device__ __forceinline__ double u01_open_low(uint32_t lo, uint32_t hi) {
-  const uint64_t x = ((uint64_t)hi << 32) | lo;
-  return (double)((x >> 11) + 1) * 0x1.0p-53;
+// 52-bit uniforms from one Philox block, exactly as the oracle builds them (oracle/hh_oracle.c: hho_normal_pair):
+//   u1 = 1 - n1 2^-52 in [2^-52, 1 - 2^-52],  u2 = n2 2^-52 in [0, 1)
+__device__ __forceinline__ double u01_for_log(uint32_t w0, uint32_t w1) {
+  return 2.0 - __hiloint2double((int)(0x3FF00000u | (w1 & 0xFFFFFu)), (int)(w0 | 1u));
 }
-__device__ __forceinline__ double u01_open_high(uint32_t lo, uint32_t hi) {
-  const uint64_t x = ((uint64_t)hi << 32) | lo;
-  return (double)(x >> 11) * 0x1.0p-53;
+__device__ __forceinline__ double u01_for_angle(uint32_t w2, uint32_t w3) {
+  return __hiloint2double((int)(0x3FF00000u | (w3 & 0xFFFFFu)), (int)w2) - 1.0;
 }
 
-// One Box-Muller pair in binary64.
-__device__ __forceinline__ void normal_pair(uint64_t key, uint64_t idx, uint32_t block, uint32_t stream, double &z1,
-                                            double &z2) {
-  const u32x4 w = philox4x32_10((uint32_t)idx, (uint32_t)(idx >> 32), block, stream, (uint32_t)key,
-                                (uint32_t)(key >> 32));
-  const double u1 = u01_open_low(w.x, w.y);
-  const double u2 = u01_open_high(w.z, w.w);
+// One Box-Muller pair in binary64 through the CUDA math library: the reference implementation of the
+// mapping; the pricing kernels use the table-driven version in hh_fastnormal.cuh.
+__device__ __forceinline__ void normal_pair_libm(const u32x4 w, double &z1, double &z2) {
+  const double u1 = u01_for_log(w.x, w.y);
+  const double u2 = u01_for_angle(w.z, w.w);
   const double r = sqrt(-2.0 * log(u1));
   double s, c;
   sincospi(2.0 * u2, &s, &c);

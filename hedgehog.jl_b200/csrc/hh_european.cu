@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "hh_ctx.h"
+#include "hh_fastnormal.cuh"
 #include "hh_paths.cuh"
 
 namespace hh {
@@ -42,6 +43,7 @@ struct EuroArgs {
   double *partials;  // [grid][npay][nacc]
   int npay, kp_log2, n_steps, split, parity;
   PathParams<double> p;
+  HestonFolded f;
 };
 
 // number of accumulators per (block, payoff): sum, sumsq, nonfinite, then per tangent: dsum, dsumsq
@@ -106,8 +108,11 @@ __device__ __forceinline__ PathParams<T> lift_params(const PathParams<double> &p
 struct NormalSource {
   uint64_t key, idx;
   const double *z;
-  __device__ __forceinline__ NormalSource(const EuroArgs &a, bool parity, int64_t i, int per_path) {
+  const FastNormalTables *tb;
+  __device__ __forceinline__ NormalSource(const EuroArgs &a, const FastNormalTables *tables, bool parity, int64_t i,
+                                          int per_path) {
     z = nullptr;
+    tb = tables;
     key = idx = 0;
     if (parity) {
       z = a.normals + (size_t)i * (size_t)per_path;
@@ -124,19 +129,21 @@ struct NormalSource {
       z1 = z[2 * n];
       z2 = z[2 * n + 1];
     } else {
-      normal_pair(key, idx, (uint32_t)n, 0u, z1, z2);
+      const u32x4 w = philox4x32_10((uint32_t)idx, (uint32_t)(idx >> 32), (uint32_t)n, 0u, (uint32_t)key,
+                                    (uint32_t)(key >> 32));
+      fast_normal_pair(tb, w.x, w.y, w.z, w.w, z1, z2);
     }
   }
 };
 
 // ---- one trajectory (or antithetic pair) -> terminal spot(s) in number type T ---------------------------
-template <int KIND, class T, bool ANTI>
-__device__ __forceinline__ void simulate(const EuroArgs &a, const PathParams<T> &p, bool parity, bool split, int64_t i,
-                                         T &Sp, T &Sm) {
+template <int KIND, class T, bool ANTI, bool FAST>
+__device__ __forceinline__ void simulate(const EuroArgs &a, const PathParams<T> &p, const FastNormalTables *tb,
+                                         bool parity, bool split, int64_t i, T &Sp, T &Sm) {
   const int M = a.n_steps;
   if constexpr (KIND == K_GBM_TERMINAL) {
     // marginal_law + final_sample, montecarlo.jl:293-303, 384-390
-    NormalSource src(a, parity, i, 1);
+    NormalSource src(a, tb, parity, i, 1);
     double z1, z2;
     if (parity) z1 = src.z[0];
     else src.pair(false, 0, z1, z2);
@@ -144,7 +151,7 @@ __device__ __forceinline__ void simulate(const EuroArgs &a, const PathParams<T> 
     Sp = exp_(X);
     if (ANTI) Sm = exp_(p.mu * 2.0 - X);
   } else if constexpr (KIND == K_GBM_EM || KIND == K_GBM_STEPS) {
-    NormalSource src(a, parity, i, M);
+    NormalSource src(a, tb, parity, i, M);
     T sp = KIND == K_GBM_EM ? p.x0 : p.S0;
     T sm = sp;
 #pragma unroll 1
@@ -179,16 +186,29 @@ __device__ __forceinline__ void simulate(const EuroArgs &a, const PathParams<T> 
       if (ANTI) Sm = sm;
     }
   } else {
-    NormalSource src(a, parity, i, 2 * M);
+    NormalSource src(a, tb, parity, i, 2 * M);
     T xp = p.x0, vp = p.v0, xm = p.x0, vm = p.v0;
+    if constexpr (FAST) {
+      // native-RNG pricing: constants pre-folded on the host, branch-free sqrt (hh_fastnormal.cuh)
 #pragma unroll 1
-    for (int n = 0; n < M; ++n) {
-      double z1, z2;
-      src.pair(parity, n, z1, z2);
-      const T dW1 = fma_(p.a12, z2, p.a11 * z1);
-      const T dW2 = fma_(p.a22, z2, p.a21 * z1);
-      heston_em_step(p, split, xp, vp, dW1, dW2);
-      if (ANTI) heston_em_step(p, split, xm, vm, -dW1, -dW2);
+      for (int n = 0; n < M; ++n) {
+        double z1, z2;
+        src.pair(false, n, z1, z2);
+        const double dW1 = fma(p.a12, z2, p.a11 * z1);
+        const double dW2 = fma(a.f.b22, z2, a.f.b21 * z1);  // xi * dW2
+        heston_em_step_fast(a.f, split, xp, vp, dW1, dW2);
+        if (ANTI) heston_em_step_fast(a.f, split, xm, vm, -dW1, -dW2);
+      }
+    } else {
+#pragma unroll 1
+      for (int n = 0; n < M; ++n) {
+        double z1, z2;
+        src.pair(parity, n, z1, z2);
+        const T dW1 = fma_(p.a12, z2, p.a11 * z1);
+        const T dW2 = fma_(p.a22, z2, p.a21 * z1);
+        heston_em_step(p, split, xp, vp, dW1, dW2);
+        if (ANTI) heston_em_step(p, split, xm, vm, -dW1, -dW2);
+      }
     }
     Sp = exp_(xp);
     if (ANTI) Sm = exp_(xm);
@@ -207,6 +227,12 @@ __global__ void __launch_bounds__(kThreads) european_kernel(const EuroArgs a, co
   constexpr int RED = NACC * kThreads;
   __shared__ double smem[STAGE > RED ? STAGE : RED];
 
+  __shared__ FastNormalTables s_tables;  // Box-Muller lookup tables (native-RNG mode)
+  if (PARITY != 1) {
+    load_fast_tables(&s_tables);
+    __syncthreads();
+  }
+  constexpr bool FAST = KIND == K_HESTON_EM && NT == 0 && PARITY == 0;
   const bool parity = PARITY == 2 ? a.parity != 0 : PARITY == 1;
   const bool split = SPLIT == 2 ? a.split != 0 : SPLIT == 1;
   const PathParams<T> p = lift_params<T>(a.p, tpack);
@@ -229,7 +255,7 @@ __global__ void __launch_bounds__(kThreads) european_kernel(const EuroArgs a, co
     const int64_t i = base + tid;
     T Sp = zero<T>(), Sm = zero<T>();
     if (i < a.n) {
-      simulate<KIND, T, ANTI>(a, p, parity, split, i, Sp, Sm);
+      simulate<KIND, T, ANTI, FAST>(a, p, &s_tables, parity, split, i, Sp, Sm);
       if (a.terminal) {  // MonteCarloSolution.ensemble: (plus | minus), montecarlo.jl:400-402, 492
         a.terminal[i] = value(Sp);
         if (ANTI) a.terminal[a.n + i] = value(Sm);
@@ -452,6 +478,12 @@ static int build_args(hh_ctx *ctx, const hh_model *m, const hh_sim *s, const hh_
     p.a12 = sqdt * m->m12;
     p.a21 = sqdt * m->m21;
     p.a22 = sqdt * m->m22;
+    a.f.rdt = m->r * dt;
+    a.f.neg_half_dt = -0.5 * dt;
+    a.f.neg_kdt = -(m->kappa * dt);
+    a.f.ktdt = m->kappa * m->theta * dt;
+    a.f.b21 = m->xi * p.a21;
+    a.f.b22 = m->xi * p.a22;
     for (int q = 0; q < ntan; ++q) {
       tp.v0[q] = tg[q].dV0;
       tp.kappa[q] = tg[q].dkappa;
@@ -470,6 +502,7 @@ static int build_args(hh_ctx *ctx, const hh_model *m, const hh_sim *s, const hh_
 static int upload_inputs(hh_ctx *ctx, const hh_model *m, const hh_sim *s, const hh_payoff *payoffs, int npay,
                          EuroArgs &a) {
   cudaStream_t st = ctx->stream;
+  HH_CUDA(ctx, upload_fast_tables(ctx->device, st));
   const int64_t N = s->n_paths;
   const int ncomp = m->kind == HH_MODEL_HESTON ? 2 : 1;
   a.npay = npay;

@@ -1,0 +1,134 @@
+// hh_fastnormal.cuh — the native-RNG Box-Muller pair, built for the FP64 pipe of sm_100a.
+//
+// The FP64 pipe (64 lanes per SM) bounds the Heston kernel, so everything that is not a DFMA is pushed off
+// it: range reduction and exponent handling are integer bit operations on the Philox words, the
+// logarithm and the sine/cosine read small shared-memory tables (LSU pipe) and finish with short
+// polynomials, and the square root is one MUFU.RSQ64H seed plus one cubically convergent refinement.
+// No int<->double conversion instructions, no slow-path branches.
+//
+//   bits -> uniforms (restated bit for bit in oracle/hh_oracle.c: hho_normal_pair)
+//     y1 = double{hi = 0x3FF00000 | (w1 & 0xFFFFF), lo = w0 | 1},  u1 = 2 - y1   in [2^-52, 1 - 2^-52]
+//     n2 = (w3 & 0xFFFFF) << 32 | w2,                              theta = 2 pi n2 2^-52
+//   z1 = sqrt(-2 ln u1) cos(theta),  z2 = sqrt(-2 ln u1) sin(theta)
+//
+// Accuracy: each normal is within ~4e-16 (absolute) of the libm evaluation of the same formulas, checked
+// per path against the oracle by tests/test_gpu_european.py.
+#pragma once
+#include "hh_device.cuh"
+#include "hh_tables.h"
+
+namespace hh {
+
+struct FastNormalTables {
+  double2 log_tab[tables::kLogBuckets];  // {rcp_i, -2 ln c_i}
+  double2 trig_tab[tables::kTrigN];      // {cos, sin}(2 pi j / 256)
+  double exp_tab[tables::kExpN];         // 2 k ln 2
+};
+
+// device-global copy of the generated tables; one per translation unit (no -rdc), uploaded once per device
+static __device__ FastNormalTables g_fast_tables;
+
+static inline cudaError_t upload_fast_tables(int device, cudaStream_t st) {
+  static bool done[64] = {};
+  if (device >= 0 && device < 64 && done[device]) return cudaSuccess;
+  static FastNormalTables h;  // static: must outlive the async copy
+  for (int i = 0; i < tables::kLogBuckets; ++i) h.log_tab[i] = make_double2(tables::kLogTab[i][0], tables::kLogTab[i][1]);
+  for (int i = 0; i < tables::kTrigN; ++i) h.trig_tab[i] = make_double2(tables::kTrigTab[i][0], tables::kTrigTab[i][1]);
+  for (int i = 0; i < tables::kExpN; ++i) h.exp_tab[i] = tables::kExpTab[i];
+  cudaError_t e = cudaMemcpyToSymbolAsync(g_fast_tables, &h, sizeof h, 0, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e == cudaSuccess && device >= 0 && device < 64) done[device] = true;
+  return e;
+}
+
+__device__ __forceinline__ void load_fast_tables(FastNormalTables *s) {
+  const double *src = reinterpret_cast<const double *>(&g_fast_tables);
+  double *dst = reinterpret_cast<double *>(s);
+  constexpr int n = sizeof(FastNormalTables) / sizeof(double);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
+}
+
+// Polynomial coefficients that need all 64 bits live in constant memory so that DFMA takes them as a
+// c[bank][offset] operand (no per-iteration UMOV / MOV pairs).
+struct FastNormalConsts {
+  double third, neg_two_fifths, neg_two_thirds;     // -2 ln(1+r) series
+  double two_pi_2m52, magic;                        // angle scaling, 1.5 * 2^52
+  double s5, s3;                                    // sin: 1/120, -1/6
+  double c6, c4;                                    // cos: -1/720, 1/24
+  double tiny;                                      // 1e-300
+};
+__constant__ FastNormalConsts kFN = {0x1.5555555555555p-2, -0.4, -0x1.5555555555555p-1,
+                                     0x1.921fb54442d18p-50, 6755399441055744.0,
+                                     0x1.1111111111111p-7, -0x1.5555555555555p-3,
+                                     -0x1.6c16c16c16c17p-10, 0x1.5555555555555p-5, 1e-300};
+
+// max(x, 0) and max(x, 1e-300) for finite x through the integer pipe (no DSETP on the FP64 pipe):
+// a negative double has its sign bit set; non-negative doubles order like their high words.
+__device__ __forceinline__ double max0_bits(double x) {
+  const int hi = __double2hiint(x), lo = __double2loint(x);
+  const int keep = ~(hi >> 31);
+  return __hiloint2double(hi & keep, lo & keep);
+}
+__device__ __forceinline__ double max_tiny_bits(double x) {
+  const int hi = __double2hiint(x), lo = __double2loint(x);
+  const bool small = hi < 0x01a56e1f;  // hi word of 1e-300 (= 0x01a56e1fc2f8f359); also catches negatives
+  return __hiloint2double(small ? 0x01a56e1f : hi, small ? (int)0xc2f8f359 : lo);
+}
+
+__device__ __forceinline__ double rsqrt_seed(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));  // MUFU.RSQ64H
+  return y;
+}
+
+// sqrt(x) for x in [1e-300, 1e300]: seed + one cubic refinement, 6 FP64 instructions, ~1e-16 relative.
+__device__ __forceinline__ double fast_sqrt_pos(double x) {
+  const double y0 = rsqrt_seed(x);
+  const double t = y0 * y0;
+  const double e = fma(-x, t, 1.0);
+  const double h = fma(e, 0.375, 0.5);
+  const double g = y0 * e;
+  const double y = fma(h, g, y0);
+  return x * y;
+}
+
+__device__ __forceinline__ void fast_normal_pair(const FastNormalTables *__restrict__ tb, uint32_t w0, uint32_t w1,
+                                                 uint32_t w2, uint32_t w3, double &z1, double &z2) {
+  // ---- R2 = -2 ln(u1) ---------------------------------------------------------------------------------
+  const double y1 = __hiloint2double((int)(0x3FF00000u | (w1 & 0xFFFFFu)), (int)(w0 | 1u));
+  const double u1 = 2.0 - y1;  // exact
+  const uint32_t uh = (uint32_t)__double2hiint(u1);
+  const int k = 1023 - (int)(uh >> 20);              // u1 = f 2^-k, f in [1,2), k >= 1
+  const uint32_t m20 = uh & 0xFFFFFu;
+  const int i = (int)((m20 + 0x1000u) >> 13);        // nearest of the 129 bucket centres 1 + i/128
+  const double f = __hiloint2double((int)(m20 | 0x3FF00000u), __double2loint(u1));
+  const double2 lt = tb->log_tab[i];
+  const double L = tb->exp_tab[k - (i >= tables::kLogSplit ? 1 : 0)] + lt.y;
+  const double r = fma(f, lt.x, -1.0);               // exact up to one rounding: rcp_i has 24 bits
+  double p = kFN.third;                              // -2 ln(1+r) = r (-2 + r (1 + r (-2/3 + r (1/2 + r (-2/5 + r/3)))))
+  p = fma(p, r, kFN.neg_two_fifths);
+  p = fma(p, r, 0.5);
+  p = fma(p, r, kFN.neg_two_thirds);
+  p = fma(p, r, 1.0);
+  p = fma(p, r, -2.0);
+  const double R2 = fma(p, r, L);
+  const double rad = fast_sqrt_pos(R2);
+
+  // ---- (cos, sin)(2 pi n2 2^-52) ---------------------------------------------------------------------------
+  const uint32_t h2 = w3 & 0xFFFFFu;                 // high 20 bits of the 52-bit angle
+  const uint32_t j = (h2 + 0x800u) >> 12;            // nearest of 256 table angles (j in [0, 256])
+  // s = n2 - j 2^44 in [-2^43, 2^43) as a double via the 1.5*2^52 magic constant (exact)
+  const int shi = (int)(0x43380000u + h2) - (int)(j << 12);
+  const double sd = __hiloint2double(shi, (int)w2) - kFN.magic;
+  const double d = sd * kFN.two_pi_2m52;             // delta = s 2^-52 2 pi
+  const double2 cs = tb->trig_tab[j & 255u];
+  const double d2 = d * d;
+  const double d3 = d * d2;
+  const double sn = fma(d3, fma(d2, kFN.s5, kFN.s3), d);           // sin(delta)
+  const double cm = d2 * fma(d2, fma(d2, kFN.c6, kFN.c4), -0.5);   // cos(delta) - 1
+  const double rc = rad * cs.x, rs = rad * cs.y;
+  z1 = fma(rc, cm, fma(-rs, sn, rc));
+  z2 = fma(rs, cm, fma(rc, sn, rs));
+}
+
+}  // namespace hh

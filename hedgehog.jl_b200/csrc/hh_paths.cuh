@@ -9,6 +9,7 @@
 //   sqrt at 0 therefore sees a zero tangent and stays finite (the reference would produce NaN there).
 #pragma once
 #include "hh_device.cuh"
+#include "hh_fastnormal.cuh"
 
 namespace hh {
 
@@ -164,6 +165,22 @@ __device__ __forceinline__ void heston_em_step(const PathParams<T> &p, bool spli
   const T s = sqrt0(split ? K2 : v);
   x = fma_(s, dW1, K1);
   v = fma_(p.xi * s, dW2, K2);
+}
+
+// The same step for the native-RNG pricing kernel: constants folded on the host, xi folded into dW2, and the
+// branch-free square root. sqrt(max(., 1e-300)) replaces sqrt(max(., 0)): the difference (1e-150) is far below
+// one ulp of the state.
+struct HestonFolded {
+  double rdt, neg_half_dt, neg_kdt, ktdt, b21, b22;
+};
+__device__ __forceinline__ void heston_em_step_fast(const HestonFolded &f, bool split, double &x, double &v, double dW1,
+                                                    double xi_dW2) {
+  const double vplus = max0_bits(v);
+  const double K1 = fma(f.neg_half_dt, vplus, x + f.rdt);
+  const double K2 = fma(f.neg_kdt, vplus, v + f.ktdt);
+  const double s = fast_sqrt_pos(max_tiny_bits(split ? K2 : v));
+  x = fma(s, dW1, K1);
+  v = fma(s, xi_dW2, K2);
 }
 
 // LogGBMProblem under EM (heston.jl:33-52): x' = (x + dt (r - sigma^2/2)) + sigma dW

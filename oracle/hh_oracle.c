@@ -77,10 +77,13 @@ void hho_normal_pair(uint64_t key, uint64_t idx, uint32_t block, uint32_t stream
   uint32_t k[2] = {(uint32_t)key, (uint32_t)(key >> 32)};
   uint32_t w[4];
   hho_philox4x32_10(ctr, k, w);
-  uint64_t x1 = ((uint64_t)w[1] << 32) | w[0];
-  uint64_t x2 = ((uint64_t)w[3] << 32) | w[2];
-  double u1 = (double)((x1 >> 11) + 1) * 0x1.0p-53; /* (0,1] */
-  double u2 = (double)(x2 >> 11) * 0x1.0p-53;       /* [0,1) */
+  /* bits -> uniforms, the library's convention (hedgehog.jl_b200/csrc/hh_fastnormal.cuh):
+   *   u1 = 1 - n1 2^-52, n1 = (w1 & 0xFFFFF) << 32 | (w0 | 1)   in [2^-52, 1 - 2^-52]
+   *   u2 = n2 2^-52,     n2 = (w3 & 0xFFFFF) << 32 | w2         in [0, 1)                */
+  uint64_t n1 = ((uint64_t)(w[1] & 0xFFFFFu) << 32) | (w[0] | 1u);
+  uint64_t n2 = ((uint64_t)(w[3] & 0xFFFFFu) << 32) | w[2];
+  double u1 = 1.0 - (double)n1 * 0x1.0p-52; /* exact */
+  double u2 = (double)n2 * 0x1.0p-52;       /* exact */
   double r = sqrt(-2.0 * log(u1));
   double s, c;
   sincospi_ref(2.0 * u2, &s, &c);
