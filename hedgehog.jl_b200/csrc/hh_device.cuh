@@ -40,6 +40,41 @@ __device__ __forceinline__ u32x4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_
   return u32x4{c0, c1, c2, c3};
 }
 
+// Philox with a precomputed key schedule: in base_seed mode the ten round keys are uniform across the grid and
+// sit in the kernel arguments (constant bank), so the rounds are 2 IMAD.WIDE + 2 LOP3 with no key arithmetic
+// and no registers for the schedule.
+struct PhiloxRoundKeys {
+  uint32_t k0[10], k1[10];
+};
+__host__ __device__ __forceinline__ PhiloxRoundKeys philox_round_keys(uint64_t key) {
+  PhiloxRoundKeys rk;
+  uint32_t a = (uint32_t)key, b = (uint32_t)(key >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    rk.k0[r] = a;
+    rk.k1[r] = b;
+    a += kPhiloxW0;
+    b += kPhiloxW1;
+  }
+  return rk;
+}
+__device__ __forceinline__ u32x4 philox4x32_10_rk(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                  const PhiloxRoundKeys &rk) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t lo0, hi0, lo1, hi1;
+    asm("{ .reg .b64 t; mul.wide.u32 t, %2, %3; mov.b64 {%0, %1}, t; }" : "=r"(lo0), "=r"(hi0) : "r"(c0), "r"(kPhiloxM0));
+    asm("{ .reg .b64 t; mul.wide.u32 t, %2, %3; mov.b64 {%0, %1}, t; }" : "=r"(lo1), "=r"(hi1) : "r"(c2), "r"(kPhiloxM1));
+    const uint32_t n0 = hi1 ^ c1 ^ rk.k0[r];
+    const uint32_t n2 = hi0 ^ c3 ^ rk.k1[r];
+    c1 = lo1;
+    c3 = lo0;
+    c0 = n0;
+    c2 = n2;
+  }
+  return u32x4{c0, c1, c2, c3};
+}
+
 // 52-bit uniforms from one Philox block, exactly as the oracle builds them (oracle/hh_oracle.c: hho_normal_pair):
 //   u1 = 1 - n1 2^-52 in [2^-52, 1 - 2^-52],  u2 = n2 2^-52 in [0, 1)
 __device__ __forceinline__ double u01_for_log(uint32_t w0, uint32_t w1) {

@@ -13,6 +13,7 @@
 // batch from shared memory ("payoff transpose": thread = (strike, path group)), so up to 256 strikes are
 // priced on the same paths with register accumulators and a fixed summation order.
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -44,6 +45,7 @@ struct EuroArgs {
   int npay, kp_log2, n_steps, split, parity;
   PathParams<double> p;
   HestonFolded f;
+  PhiloxRoundKeys rk;  // round keys of base_seed (uniform across threads when seeds == NULL)
 };
 
 // number of accumulators per (block, payoff): sum, sumsq, nonfinite, then per tangent: dsum, dsumsq
@@ -316,6 +318,116 @@ __global__ void __launch_bounds__(kThreads) european_kernel(const EuroArgs a, co
   }
 }
 
+// ---- the headline kernel: Heston Euler-Maruyama, Float64, native RNG (config C2) -----------------------------
+// Same trajectory arithmetic and payoff transpose as european_kernel, specialised for throughput:
+//   UKEY  the Philox round keys are uniform (base_seed mode) and come from the kernel arguments (constant bank),
+//         which removes 20 registers of key schedule per thread;
+//   ILP   trajectories advanced per thread in lock step (independent dependency chains for the FP64 pipe).
+template <bool ANTI, bool SPLIT, bool UKEY, int ILP, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB) heston_fast_kernel(const EuroArgs a) {
+  constexpr int NSIDE = ANTI ? 2 : 1;
+  constexpr int NACC = 3;
+  constexpr int STAGE = NSIDE * kThreads;
+  constexpr int RED = NACC * kThreads;
+  __shared__ double smem[STAGE > RED ? STAGE : RED];
+  __shared__ FastNormalTables s_tables;
+  load_fast_tables(&s_tables);
+  __syncthreads();
+
+  const int tid = threadIdx.x;
+  const int KP = 1 << a.kp_log2;
+  const int k = tid & (KP - 1);
+  const int g = tid >> a.kp_log2;
+  const int G = kThreads >> a.kp_log2;
+  double strike = 0.0, cp = 0.0;
+  if (k < a.npay) {
+    strike = a.payoffs[k].strike;
+    cp = a.payoffs[k].cp;
+  }
+  double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0;
+  const int M = a.n_steps;
+  constexpr int64_t kBatch = (int64_t)kThreads * ILP;
+
+  for (int64_t base = (int64_t)blockIdx.x * kBatch; base < a.n; base += (int64_t)gridDim.x * kBatch) {
+    double xp[ILP], vp[ILP], xm[ILP], vm[ILP];
+    uint32_t c0[ILP], c1[ILP];
+    PhiloxRoundKeys rk[UKEY ? 1 : ILP];
+#pragma unroll
+    for (int j = 0; j < ILP; ++j) {
+      const int64_t i = base + (int64_t)j * kThreads + tid;
+      const int64_t ic = i < a.n ? i : a.n - 1;  // tail lanes repeat the last trajectory; never accumulated
+      xp[j] = xm[j] = a.p.x0;
+      vp[j] = vm[j] = a.p.v0;
+      if (UKEY) {
+        const uint64_t idx = (uint64_t)(a.path_offset + ic);
+        c0[j] = (uint32_t)idx;
+        c1[j] = (uint32_t)(idx >> 32);
+      } else {
+        c0[j] = c1[j] = 0u;
+        rk[UKEY ? 0 : j] = philox_round_keys(a.seeds[ic]);
+      }
+    }
+#pragma unroll 1
+    for (int n = 0; n < M; ++n) {
+#pragma unroll
+      for (int j = 0; j < ILP; ++j) {
+        const u32x4 w = philox4x32_10_rk(c0[j], c1[j], (uint32_t)n, 0u, UKEY ? a.rk : rk[UKEY ? 0 : j]);
+        double z1, z2;
+        fast_normal_pair(&s_tables, w.x, w.y, w.z, w.w, z1, z2);
+        const double dW1 = fma(a.p.a12, z2, a.p.a11 * z1);
+        const double dW2 = fma(a.f.b22, z2, a.f.b21 * z1);  // xi * dW2
+        heston_em_step_fast(a.f, SPLIT, xp[j], vp[j], dW1, dW2);
+        if (ANTI) heston_em_step_fast(a.f, SPLIT, xm[j], vm[j], -dW1, -dW2);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < ILP; ++j) {
+      const int64_t sub = base + (int64_t)j * kThreads;
+      if (sub >= a.n) break;
+      const int64_t i = sub + tid;
+      const double Sp = exp(xp[j]);
+      const double Sm = ANTI ? exp(xm[j]) : 0.0;
+      if (a.terminal && i < a.n) {
+        a.terminal[i] = Sp;
+        if (ANTI) a.terminal[a.n + i] = Sm;
+      }
+      smem[tid] = Sp;
+      if (ANTI) smem[kThreads + tid] = Sm;
+      __syncthreads();
+      const int64_t rem = a.n - sub;
+      const int nvalid = rem < kThreads ? (int)rem : kThreads;
+      if (k < a.npay) {
+        for (int q = g; q < nvalid; q += G) {
+          const double sp = smem[q];
+          double pay = fmax(cp * (sp - strike), 0.0);  // payoffs.jl:154-156
+          bool bad = !isfinite(sp);
+          if (ANTI) {
+            const double sm = smem[kThreads + q];
+            pay = 0.5 * (pay + fmax(cp * (sm - strike), 0.0));  // reduce_payoffs montecarlo.jl:430-432
+            bad = bad || !isfinite(sm);
+          }
+          acc0 += pay;
+          acc1 = fma(pay, pay, acc1);
+          if (k == 0 && bad) acc2 += 1.0;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  smem[tid] = acc0;
+  smem[kThreads + tid] = acc1;
+  smem[2 * kThreads + tid] = acc2;
+  __syncthreads();
+  if (tid < a.npay) {
+    double *out = a.partials + ((size_t)blockIdx.x * a.npay + tid) * NACC;
+    for (int c = 0; c < NACC; ++c) {
+      double t = 0.0;
+      for (int gg = 0; gg < G; ++gg) t += smem[c * kThreads + (gg << a.kp_log2) + tid];
+      out[c] = t;
+    }
+  }
+}
+
 // Sum the per-block partials in a fixed order: one block per payoff.
 __global__ void __launch_bounds__(kThreads) finalize_kernel(const double *partials, int nblocks, int npay, int nacc,
                                                             double *out) {
@@ -410,8 +522,53 @@ static cudaError_t launch_kind(const EuroArgs &a, const TangentPack *tp, int P, 
   }
 }
 
+template <bool ANTI, bool SPLIT, bool UKEY, int ILP, int MINB>
+static cudaError_t launch_fast_one(const EuroArgs &a, int sm_count, cudaStream_t st, int *nblocks, bool query_only) {
+  auto kern = heston_fast_kernel<ANTI, SPLIT, UKEY, ILP, MINB>;
+  int occ = 0;
+  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, 0);
+  if (e != cudaSuccess) return e;
+  if (occ < 1) occ = 1;
+  const int64_t batch = (int64_t)kThreads * ILP;
+  const int64_t batches = (a.n + batch - 1) / batch;
+  int64_t grid = (int64_t)sm_count * occ;
+  if (grid > batches) grid = batches;
+  *nblocks = (int)grid;
+  if (query_only) return cudaSuccess;
+  kern<<<(unsigned)grid, kThreads, 0, st>>>(a);
+  return cudaGetLastError();
+}
+
+// variant: tuning knob (HH_HESTON_VARIANT) — 0 is the shipped default
+template <bool ANTI, bool SPLIT, bool UKEY>
+static cudaError_t launch_fast_v(const EuroArgs &a, int variant, int sm_count, cudaStream_t st, int *nb, bool q) {
+  switch (variant) {
+    // measured on B200, 1e7 x 252 (tools/time_heston.py): ILP 2 / 2 blocks per SM 12.75 ms, ILP 1 / 4 blocks 13.42 ms,
+    // ILP 1 / 6 blocks 13.83 ms — the kernel is issue-bound, occupancy hardly matters
+    case 1: return launch_fast_one<ANTI, SPLIT, UKEY, 1, 4>(a, sm_count, st, nb, q);
+    case 2: return launch_fast_one<ANTI, SPLIT, UKEY, 1, 6>(a, sm_count, st, nb, q);
+    case 3: return launch_fast_one<ANTI, SPLIT, UKEY, 2, 3>(a, sm_count, st, nb, q);
+    default: return launch_fast_one<ANTI, SPLIT, UKEY, 2, 2>(a, sm_count, st, nb, q);
+  }
+}
+
+static cudaError_t launch_fast(const EuroArgs &a, bool anti, int sm_count, cudaStream_t st, int *nb, bool q) {
+  static const int variant = getenv("HH_HESTON_VARIANT") ? atoi(getenv("HH_HESTON_VARIANT")) : 0;
+  const bool ukey = a.seeds == nullptr;
+#define HH_FAST(A, S, U) return launch_fast_v<A, S, U>(a, variant, sm_count, st, nb, q)
+  if (anti) {
+    if (a.split) { if (ukey) HH_FAST(true, true, true); else HH_FAST(true, true, false); }
+    else { if (ukey) HH_FAST(true, false, true); else HH_FAST(true, false, false); }
+  } else {
+    if (a.split) { if (ukey) HH_FAST(false, true, true); else HH_FAST(false, true, false); }
+    else { if (ukey) HH_FAST(false, false, true); else HH_FAST(false, false, false); }
+  }
+#undef HH_FAST
+}
+
 static cudaError_t launch_any(int kind, const EuroArgs &a, const TangentPack *tp, int P, bool anti, int sm_count,
                               cudaStream_t st, int *nb, bool q) {
+  if (kind == K_HESTON_EM && P == 0 && !a.parity) return launch_fast(a, anti, sm_count, st, nb, q);
   switch (kind) {
     case K_GBM_EM: return launch_kind<K_GBM_EM>(a, tp, P, anti, sm_count, st, nb, q);
     case K_GBM_TERMINAL: return launch_kind<K_GBM_TERMINAL>(a, tp, P, anti, sm_count, st, nb, q);
@@ -432,6 +589,7 @@ static int build_args(hh_ctx *ctx, const hh_model *m, const hh_sim *s, const hh_
   a.n_steps = nsteps;
   a.split = (m->flags & HH_FLAG_SPLIT_STEP) ? 1 : 0;
   a.parity = s->rng_mode == HH_RNG_NORMALS;
+  a.rk = philox_round_keys(s->base_seed);
   PathParams<double> &p = a.p;
   const double dt = m->T / nsteps;  // montecarlo.jl:349
   const double sqdt = sqrt(dt);

