@@ -1,10 +1,6 @@
 // temporary: entry points under construction
 #include "hh_ctx.h"
 namespace hh {
-int lsm_american(hh_ctx *ctx, const hh_model *, const hh_sim *, const hh_payoff *, int, double, const hh_comm *,
-                 hh_lsm_result *, int32_t *, double *, double *) {
-  return ctx->fail(HH_ERR_UNSUPPORTED, "LSM not built yet");
-}
 int bk_chf(hh_ctx *ctx, const hh_model *, double, const double *, const double *, int, const double *, int, double *,
            double *) {
   return ctx->fail(HH_ERR_UNSUPPORTED, "BK not built yet");

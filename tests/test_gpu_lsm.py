@@ -1,0 +1,120 @@
+"""GPU parity tests for Longstaff-Schwartz (solve(::PricingProblem{American}, ::LSM), least_squares_montecarlo.jl:99-136)
+through the C ABI, against the CPU oracle (Householder QR on the raw Vandermonde, like Polynomials.fit) and CRR.
+
+Bars: stored spot paths rel 1e-12 (same normals / same Philox stream); exercise decisions identical except where
+payoff and fitted continuation tie within rounding (the oracle's QR on raw monomials of S ~ 100 is itself only good to
+~1e-9 there), so flips are counted and bounded, and the price must agree to 1e-9 relative when no decision flipped."""
+import datetime as dt
+import math
+
+import numpy as np
+import pytest
+
+import hedgehog_jl_b200 as hh
+from hedgehog_jl_b200 import _abi as abi
+from hedgehog_jl_b200.engine import SimSpec
+from helpers import gbm_model, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _run_both(cuda, oracle, m, sim, payoff, degree, D):
+    og, tg, vg, pg = cuda.lsm_american(m, sim, payoff, degree, D, want_stopping=True, want_paths=True)
+    oo, to, vo, po = oracle.lsm_american(m, sim, payoff, degree, D, want_stopping=True, want_paths=True)
+    return (og, tg, vg, pg), (oo, to, vo, po)
+
+
+def _check(g, o, max_flip_frac=2e-4):
+    (og, tg, vg, pg), (oo, to, vo, po) = g, o
+    assert rel_err(pg, po) < 1e-12
+    assert og.n == oo.n
+    flips = int(np.sum(tg != to))
+    assert flips <= max(2, max_flip_frac * len(to)), flips
+    same = tg == to
+    assert rel_err(vg[same] + 1.0, vo[same] + 1.0) < 1e-12
+    if flips == 0:
+        assert abs(og.price - oo.price) <= 1e-9 * abs(oo.price)
+        assert abs(og.std_error - oo.std_error) <= 1e-7 * abs(oo.std_error)
+    else:  # a flipped decision moves one column's cash flow by the (tiny) tie gap
+        assert abs(og.price - oo.price) <= 1e-6 * abs(oo.price)
+    assert og.n_dates_skipped == oo.n_dates_skipped
+    return flips
+
+
+@pytest.mark.parametrize("anti", [False, True])
+@pytest.mark.parametrize("degree", [2, 3, 5])
+def test_lsm_parity_mode(cuda, oracle, anti, degree):
+    n, steps = 4097, 20  # odd column count when not antithetic
+    m = gbm_model(S0=100.0, r=0.05, sigma=0.2, T=1.0)
+    z = np.random.Generator(np.random.Philox(21)).standard_normal((n, steps, 1))
+    sim = SimSpec(n_paths=n, n_steps=steps, scheme=abi.HH_SCHEME_EXACT_STEPS, vr=int(anti), rng_mode=abi.HH_RNG_NORMALS, normals=z)
+    D = math.exp(-m.r * m.T / steps)
+    _check(*_run_both(cuda, oracle, m, sim, (100.0, -1.0), degree, D))
+
+
+@pytest.mark.parametrize("cp,strike", [(-1.0, 100.0), (-1.0, 110.0), (1.0, 100.0)])
+def test_lsm_native_rng_matches_oracle(cuda, oracle, cp, strike):
+    n, steps = 50_000, 50
+    m = gbm_model(S0=100.0 if cp < 0 else 120.0, r=0.05 if cp < 0 else 0.15, sigma=0.25, T=0.5)
+    sim = SimSpec(n_paths=n, n_steps=steps, scheme=abi.HH_SCHEME_EXACT_STEPS, vr=abi.HH_VR_ANTITHETIC, base_seed=12345)
+    D = math.exp(-m.r * m.T / steps)
+    _check(*_run_both(cuda, oracle, m, sim, (strike, cp), 4, D))
+
+
+def test_lsm_per_path_seeds(cuda, oracle):
+    n, steps = 20_000, 30
+    m = gbm_model()
+    seeds = np.random.Generator(np.random.Philox(12345)).integers(0, 2**64, size=n, dtype=np.uint64)
+    sim = SimSpec(n_paths=n, n_steps=steps, scheme=abi.HH_SCHEME_EXACT_STEPS, seeds=seeds)
+    _check(*_run_both(cuda, oracle, m, sim, (100.0, -1.0), 3, math.exp(-m.r * m.T / steps)))
+
+
+def test_reference_american_put_test_through_solve(cuda):
+    """test/agreement/american_options.jl:9-52: 50 000 x 100, antithetic, degree 5 vs CRR(1000), rtol 0.02."""
+    from oracle import anchors as A
+    ref, exp = dt.date(2020, 1, 1), dt.date(2021, 1, 1)
+    prob = hh.PricingProblem(hh.VanillaOption(100.0, exp, hh.American(), hh.Put(), hh.Spot()),
+                             hh.BlackScholesInputs(ref, 0.05, 100.0, 0.2))
+    seeds = np.random.Generator(np.random.Philox(12345)).integers(0, 2**64, size=50_000, dtype=np.uint64)
+    cfg = hh.SimulationConfig(50_000, steps=100, seeds=seeds, variance_reduction=hh.Antithetic())
+    sol = hh.solve(prob, hh.LSM(hh.LognormalDynamics(), hh.BlackScholesExact(), cfg, 5), engine=cuda, spot_paths=True)
+    crr = A.crr_price(100.0, 100.0, 0.05, 0.2, 366 / 365, 1000, cp=-1, american=True)
+    assert sol.price == pytest.approx(crr, rel=0.02)
+    assert sol.spot_paths.shape == (101, 100_000)
+    assert np.all(sol.spot_paths[0] == 100.0)
+    assert len(sol.stopping_info) == 100_000
+    taus = np.array([t for t, _ in sol.stopping_info])
+    assert taus.min() >= 1 and taus.max() == 100
+    assert sol.price > A.bs_price(100.0, 100.0, 0.05, 0.2, 366 / 365, cp=-1)  # American >= European (:148-202)
+
+
+def test_lsm_three_sigma_vs_crr_at_scale(cuda):
+    """Config C3 parameters at 2e6 paths: within 3 standard errors + the known LSM low bias (<0.5%) of CRR."""
+    from oracle import anchors as A
+    m = gbm_model(S0=100.0, r=0.05, sigma=0.2, T=1.0)
+    steps = 50
+    sim = SimSpec(n_paths=2_000_000, n_steps=steps, scheme=abi.HH_SCHEME_EXACT_STEPS, base_seed=12345)
+    out, *_ = cuda.lsm_american(m, sim, (100.0, -1.0), 3, math.exp(-m.r * m.T / steps))
+    crr = A.crr_price(100.0, 100.0, 0.05, 0.2, 1.0, 2000, cp=-1, american=True)
+    assert abs(out.price - crr) < 3 * out.std_error + 5e-3 * crr, (out.price, crr, out.std_error)
+    assert out.n == 2_000_000 and out.n_dates_skipped == 0
+
+
+def test_lsm_edge_cases(cuda, oracle):
+    m = gbm_model()
+    # one exercise date: no regression at all, price = D * mean(payoff(S_T))
+    sim = SimSpec(n_paths=1000, n_steps=1, scheme=abi.HH_SCHEME_EXACT_STEPS, base_seed=1)
+    _check(*_run_both(cuda, oracle, m, sim, (100.0, -1.0), 3, math.exp(-m.r)))
+    # deep out of the money: every date is skipped (least_squares_montecarlo.jl:122), price = 0
+    sim = SimSpec(n_paths=999, n_steps=10, scheme=abi.HH_SCHEME_EXACT_STEPS, base_seed=1)
+    g, o = _run_both(cuda, oracle, m, sim, (1.0, -1.0), 3, 0.99)
+    _check(g, o)
+    assert g[0].n_dates_skipped == 9 and g[0].price == 0.0
+    # degree 0 and a single trajectory
+    sim = SimSpec(n_paths=1, n_steps=5, scheme=abi.HH_SCHEME_EXACT_STEPS, base_seed=1)
+    _check(*_run_both(cuda, oracle, m, sim, (100.0, -1.0), 0, 0.99))
+    # argument errors
+    with pytest.raises(ValueError):
+        cuda.lsm_american(m, SimSpec(n_paths=10, n_steps=5, scheme=abi.HH_SCHEME_EXACT_STEPS), (100.0, -1.0), 99, 0.99)
+    with pytest.raises(NotImplementedError):  # Q7: only the S-space generator is meaningful
+        cuda.lsm_american(m, SimSpec(n_paths=10, n_steps=5, scheme=abi.HH_SCHEME_EM), (100.0, -1.0), 3, 0.99)

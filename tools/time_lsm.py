@@ -1,0 +1,28 @@
+#!/usr/bin/env python
+"""Times config C3 (American put LSM under GBM): usage python tools/time_lsm.py [paths] [dates] [degree]"""
+import math
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import hedgehog_jl_b200 as hh
+from hedgehog_jl_b200 import _abi as abi
+from hedgehog_jl_b200.engine import SimSpec
+
+n = int(float(sys.argv[1])) if len(sys.argv) > 1 else 10_000_000
+steps = int(sys.argv[2]) if len(sys.argv) > 2 else 50
+deg = int(sys.argv[3]) if len(sys.argv) > 3 else 3
+eng = hh.default_engine(0)
+m = abi.hh_model()
+m.kind, m.flags = abi.HH_MODEL_GBM, abi.HH_FLAG_SPLIT_STEP
+m.S0, m.r, m.T, m.sigma = 100.0, 0.05, 1.0, 0.2
+best = None
+for rep in range(4):
+    sim = SimSpec(n_paths=n, n_steps=steps, scheme=abi.HH_SCHEME_EXACT_STEPS, base_seed=12345 + rep)
+    out, *_ = eng.lsm_american(m, sim, (100.0, -1.0), deg, math.exp(-m.r * m.T / steps))
+    if best is None or out.kernel_ms < best.kernel_ms:
+        best = out
+gb = n * steps * 32 / 1e9
+print(f"paths={n} dates={steps} degree={deg} price={best.price:.5f} se={best.std_error:.5f} path_ms={best.path_ms:.3f} "
+      f"regress_ms={best.regress_ms:.3f} total_ms={best.kernel_ms:.3f} algorithmic_GBps={gb / (best.kernel_ms * 1e-3):.1f} "
+      f"regress_GBps(24B/col-date)={n * (steps) * 24 / 1e9 / (best.regress_ms * 1e-3):.1f}")
