@@ -113,6 +113,10 @@ SYMBOLS = {
                                   _dp, _dp]),
     "hh_bk_chf": (C.c_int, [C.c_void_p, C.POINTER(hh_model), C.c_double, _dp, _dp, C.c_int, _dp, C.c_int, _dp, _dp]),
     "hh_bk_log_besseli": (C.c_int, [C.c_void_p, C.c_double, _dp, _dp, C.c_int, _dp, _dp]),
+    "hh_bk_integral": (C.c_int, [C.c_void_p, C.POINTER(hh_model), C.c_double, C.POINTER(hh_bk_config), _dp, _dp, _dp,
+                                 C.c_int, _dp]),
+    "hh_bk_variance": (C.c_int, [C.c_void_p, C.POINTER(hh_model), C.c_double, _dp, C.c_int, C.c_uint64, _dp]),
+    "hh_bk_last_stats": (C.c_int, [C.c_void_p, _dp]),
 }
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libhedgehog_mc.so")

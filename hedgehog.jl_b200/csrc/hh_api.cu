@@ -19,6 +19,9 @@ int bk_log_besseli(hh_ctx *ctx, double nu, const double *z_re, const double *z_i
                    double *out_im);
 int bk_european_launch(hh_ctx *ctx, const hh_model *model, const hh_sim *sim, const hh_payoff *payoffs, int npayoffs,
                        int want_terminal);
+int bk_integral(hh_ctx *ctx, const hh_model *m, double tau, const hh_bk_config *cfg, const double *V0, const double *VT,
+                const double *U, int n, double *out8);
+int bk_variance(hh_ctx *ctx, const hh_model *m, double tau, const double *V0, int n, uint64_t seed, double *VT);
 int fp64_peak(hh_ctx *ctx, double *tflops, double *ms);
 }  // namespace hh
 
@@ -90,7 +93,7 @@ int hh_destroy(hh_ctx *ctx) {
   hh::DeviceBuffer *bufs[] = {&ctx->d_payoffs,  &ctx->d_partials, &ctx->d_final, &ctx->d_terminal,
                               &ctx->d_seeds,    &ctx->d_normals,  &ctx->d_tangents, &ctx->d_grid,
                               &ctx->d_cash,     &ctx->d_tau,      &ctx->d_lsm_partials, &ctx->d_lsm_state,
-                              &ctx->d_misc};
+                              &ctx->d_misc,     &ctx->d_counters};
   for (auto *b : bufs) b->release();
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
   cudaEventDestroy(ctx->ev0);
@@ -220,6 +223,26 @@ int hh_bk_log_besseli(hh_ctx *ctx, double nu, const double *z_re, const double *
   if (!ctx) return HH_ERR_ARG;
   std::lock_guard<std::mutex> lk(ctx->mu);
   return hh::bk_log_besseli(ctx, nu, z_re, z_im, n, out_re, out_im);
+}
+
+int hh_bk_integral(hh_ctx *ctx, const hh_model *model, double tau, const hh_bk_config *cfg, const double *V0,
+                   const double *VT, const double *u, int n, double *out8) {
+  if (!ctx) return HH_ERR_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  return hh::bk_integral(ctx, model, tau, cfg, V0, VT, u, n, out8);
+}
+
+int hh_bk_variance(hh_ctx *ctx, const hh_model *model, double tau, const double *V0, int n, uint64_t seed, double *VT) {
+  if (!ctx) return HH_ERR_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  return hh::bk_variance(ctx, model, tau, V0, n, seed, VT);
+}
+
+int hh_bk_last_stats(hh_ctx *ctx, double *out5) {
+  if (!ctx || !out5) return HH_ERR_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  for (int i = 0; i < 5; ++i) out5[i] = ctx->bk_stats[i];
+  return HH_OK;
 }
 
 }  // extern "C"

@@ -1,0 +1,278 @@
+// hh_bessel.cuh — log I_nu(z) for complex z and real order nu > -1, and the Broadie-Kaya characteristic function of
+// the integrated variance that needs it. Host + device code (the host build is only used by tools/bk_host_check.cu to
+// validate the arithmetic on a CPU-only box; the product calls the device build).
+//
+// Replaces SpecialFunctions.besseli(nu, z) [AMOS zbesi] at the reference's call sites
+//   src/distributions/heston.jl:173  log(besseli(nu, z_kappa))          real z
+//   src/distributions/heston.jl:207  log(besseli(nu, z_gamma_unwrapped)) complex z
+// The LOG is returned directly, so arguments the reference overflows on (|Re z| > 709) stay finite here.
+//
+// Method (w = z reflected into Re w >= 0;  I_nu(z) = exp(+-i pi nu) I_nu(-z) otherwise):
+//   |w| <= 5             ascending series  (w/2)^nu sum_k (w^2/4)^k / (k! Gamma(nu+k+1))      (cancellation <= e^5)
+//   |w| >= 20 + nu^2/2   Hankel expansion with BOTH exponentials (DLMF 10.40.5)
+//   otherwise            continued fractions: CF1 for I'/I (modified Lentz), Steed's CF2 for K_mu, K_mu+1, |mu| <= 1/2,
+//                        and the Wronskian I K' - I' K = -1/w (Temme 1975; Thompson & Barnett 1987 for complex w);
+//                        orders in (-1, 0) are reached from nu + 1 through I_(nu) = I'_(nu+1) + ((nu+1)/w) I_(nu+1).
+#pragma once
+#include <cmath>
+
+#ifdef __CUDACC__
+#define HH_HD __host__ __device__ __forceinline__
+#else
+#define HH_HD inline
+#endif
+
+namespace hh {
+
+struct cplx {
+  double re, im;
+};
+HH_HD cplx mk(double re, double im = 0.0) { return cplx{re, im}; }
+HH_HD cplx operator+(cplx a, cplx b) { return cplx{a.re + b.re, a.im + b.im}; }
+HH_HD cplx operator-(cplx a, cplx b) { return cplx{a.re - b.re, a.im - b.im}; }
+HH_HD cplx operator-(cplx a) { return cplx{-a.re, -a.im}; }
+HH_HD cplx operator*(cplx a, cplx b) { return cplx{a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re}; }
+HH_HD cplx operator*(double s, cplx a) { return cplx{s * a.re, s * a.im}; }
+HH_HD cplx operator*(cplx a, double s) { return cplx{s * a.re, s * a.im}; }
+HH_HD cplx operator+(cplx a, double s) { return cplx{a.re + s, a.im}; }
+HH_HD cplx operator+(double s, cplx a) { return cplx{a.re + s, a.im}; }
+HH_HD cplx operator-(cplx a, double s) { return cplx{a.re - s, a.im}; }
+HH_HD cplx operator-(double s, cplx a) { return cplx{s - a.re, -a.im}; }
+HH_HD cplx conj(cplx a) { return cplx{a.re, -a.im}; }
+HH_HD double cabs2(cplx a) { return a.re * a.re + a.im * a.im; }
+HH_HD double cabs(cplx a) { return hypot(a.re, a.im); }
+HH_HD double carg(cplx a) { return atan2(a.im, a.re); }
+HH_HD cplx operator/(cplx a, cplx b) {
+  // Smith's algorithm (no spurious overflow)
+  if (fabs(b.re) >= fabs(b.im)) {
+    const double r = b.im / b.re, d = b.re + b.im * r;
+    return cplx{(a.re + a.im * r) / d, (a.im - a.re * r) / d};
+  }
+  const double r = b.re / b.im, d = b.re * r + b.im;
+  return cplx{(a.re * r + a.im) / d, (a.im * r - a.re) / d};
+}
+HH_HD cplx operator/(double s, cplx b) { return mk(s) / b; }
+HH_HD cplx operator/(cplx a, double s) { return cplx{a.re / s, a.im / s}; }
+HH_HD cplx cexp_(cplx a) {
+  const double e = exp(a.re);
+  double s, c;
+  sincos(a.im, &s, &c);
+  return cplx{e * c, e * s};
+}
+HH_HD cplx clog_(cplx a) { return cplx{log(cabs(a)), carg(a)}; }
+HH_HD cplx csqrt_(cplx a) {
+  // principal branch, Re >= 0
+  const double m = cabs(a);
+  if (m == 0.0) return cplx{0.0, 0.0};
+  if (a.re >= 0.0) {
+    const double t = sqrt(0.5 * (m + a.re));
+    return cplx{t, 0.5 * a.im / t};
+  }
+  const double t = sqrt(0.5 * (m - a.re));
+  return cplx{0.5 * fabs(a.im) / t, a.im >= 0.0 ? t : -t};
+}
+
+constexpr double kBesselPi = 3.14159265358979323846;
+
+// ---- ascending series: |w| <= 5 ------------------------------------------------------------------------
+HH_HD cplx log_besseli_series(double nu, double lgam_nu1, cplx w) {
+  const cplx q = 0.25 * (w * w);
+  cplx term = mk(1.0), sum = mk(1.0);
+#pragma unroll 1
+  for (int k = 1; k < 60; ++k) {
+    term = term * q / ((double)k * (nu + (double)k));
+    sum = sum + term;
+    if (cabs2(term) < 1e-34 * cabs2(sum)) break;
+  }
+  // (w/2)^nu / Gamma(nu+1) * sum
+  return nu * clog_(0.5 * w) - lgam_nu1 + clog_(sum);
+}
+
+// ---- Hankel expansion: |w| large, Re w >= 0 -----------------------------------------------------------------
+HH_HD cplx log_besseli_asymptotic(double nu, cplx w) {
+  const double mu4 = 4.0 * nu * nu;
+  const cplx iw = 1.0 / w;
+  cplx t = mk(1.0), s1 = mk(1.0), s2 = mk(1.0);
+  double last = 1.0;
+#pragma unroll 1
+  for (int k = 1; k < 60; ++k) {
+    const double odd = (double)(2 * k - 1);
+    t = t * iw * ((mu4 - odd * odd) / (8.0 * (double)k));  // a_k / w^k
+    const double m = cabs(t);
+    if (m > last) break;  // the expansion has started to diverge
+    last = m;
+    s1 = (k & 1) ? s1 - t : s1 + t;
+    s2 = s2 + t;
+    if (m < 1e-17) break;
+  }
+  // I = e^w / sqrt(2 pi w) [ s1 + e^{-2w +- i pi (nu + 1/2)} s2 ],  + for Im w >= 0
+  const double sgn = w.im >= 0.0 ? 1.0 : -1.0;
+  const cplx e2 = cexp_(cplx{-2.0 * w.re, -2.0 * w.im + sgn * kBesselPi * (nu + 0.5)});
+  return w - 0.5 * clog_((2.0 * kBesselPi) * w) + clog_(s1 + e2 * s2);
+}
+
+// ---- continued fractions + Wronskian: 2 <= |w|, Re w >= 0, order xnu >= 0 ------------------------------------------
+// Returns log I_xnu(w); if dlog is non-null also I'_xnu / I_xnu.
+HH_HD cplx log_besseli_cf(double xnu, cplx x, cplx *ratio_deriv) {
+  const double EPS = 1e-16, FPMIN = 1e-200;
+  const int nl = (int)(xnu + 0.5);
+  const double xmu = xnu - (double)nl, xmu2 = xmu * xmu;
+  const cplx xi = 1.0 / x, xi2 = 2.0 * xi;
+  // CF1: h = I'_xnu / I_xnu
+  cplx h = xnu * xi;
+  if (fabs(h.re) + fabs(h.im) < FPMIN) h = mk(FPMIN);
+  cplx b = xnu * xi2, d = mk(0.0), c = h;
+  const int maxit = 400 + 2 * (int)cabs(x);
+#pragma unroll 1
+  for (int i = 0; i < maxit; ++i) {
+    b = b + xi2;
+    d = 1.0 / (b + d);
+    c = b + 1.0 / c;
+    const cplx del = c * d;
+    h = del * h;
+    if (fabs(del.re - 1.0) + fabs(del.im) < EPS) break;
+  }
+  // downward recurrence to order xmu
+  cplx ril = mk(1.0), ripl = h, ril1 = ril, rip1 = ripl;
+  cplx fact = xnu * xi;
+#pragma unroll 1
+  for (int l = nl; l >= 1; --l) {
+    const cplx ritemp = fact * ril + ripl;
+    fact = fact - xi;
+    ripl = fact * ritemp + ril;
+    ril = ritemp;
+    // rescale to stay in range (ratios are all that matter)
+    const double m = cabs2(ril);
+    if (m > 1e200) {
+      const double sc = 1e-100;
+      ril = sc * ril; ripl = sc * ripl; ril1 = sc * ril1; rip1 = sc * rip1;
+    }
+  }
+  const cplx f = ripl / ril;
+  // CF2 (Steed): K_mu and K_mu+1, scaled by e^{x}
+  cplx bb = 2.0 * (1.0 + x);
+  cplx dd = 1.0 / bb, hh2 = dd, delh = dd;
+  cplx q1 = mk(0.0), q2 = mk(1.0);
+  const double a1 = 0.25 - xmu2;
+  cplx q = mk(a1), cc = mk(a1);
+  double a = -a1;
+  cplx s = 1.0 + q * delh;
+#pragma unroll 1
+  for (int i = 2; i < 2000; ++i) {
+    a -= 2.0 * (double)(i - 1);
+    cc = (-a / (double)i) * cc;
+    const cplx qnew = (q1 - bb * q2) / a;
+    q1 = q2;
+    q2 = qnew;
+    q = q + cc * qnew;
+    bb = bb + 2.0;
+    dd = 1.0 / (bb + a * dd);
+    delh = (bb * dd - 1.0) * delh;
+    hh2 = hh2 + delh;
+    const cplx dels = q * delh;
+    s = s + dels;
+    if (cabs2(dels) < EPS * EPS * cabs2(s)) break;
+  }
+  hh2 = a1 * hh2;
+  const cplx rkmu = csqrt_((0.5 * kBesselPi) * xi) / s;          // K_mu e^{x}
+  const cplx rk1 = rkmu * (xmu + x + 0.5 - hh2) * xi;             // K_mu+1 e^{x}
+  const cplx rkmup = xmu * xi * rkmu - rk1;                        // K'_mu e^{x}
+  const cplx rimu_scaled = xi / (f * rkmu - rkmup);                // I_mu e^{-x}
+  if (ratio_deriv) *ratio_deriv = h;
+  // I_xnu = I_mu * ril1 / ril
+  return x + clog_(rimu_scaled) + clog_(ril1 / ril);
+}
+
+// Host-prepared constants of one order.
+struct BesselOrder {
+  double nu;        // order, > -1
+  double lgam_nu1;  // lgamma(nu + 1)
+  double r_asym;    // |w| from which the Hankel expansion is used
+};
+inline BesselOrder make_bessel_order(double nu) {
+  BesselOrder o;
+  o.nu = nu;
+  o.lgam_nu1 = lgamma(nu + 1.0);
+  o.r_asym = 20.0 + 0.5 * nu * nu;
+  return o;
+}
+
+// log I_nu(z), any complex z != 0. The imaginary part is a valid argument of I_nu(z) (branch unspecified).
+HH_HD cplx log_besseli(const BesselOrder &o, cplx z) {
+  const double nu = o.nu;
+  cplx w = z;
+  double rot = 0.0;  // I_nu(z) = e^{i rot} I_nu(w)
+  if (z.re < 0.0) {
+    w = -z;
+    rot = (z.im >= 0.0 ? 1.0 : -1.0) * kBesselPi * nu;
+  }
+  const double aw = cabs(w);
+  cplx r;
+  if (aw <= 5.0) {
+    r = log_besseli_series(nu, o.lgam_nu1, w);
+  } else if (aw >= o.r_asym) {
+    r = log_besseli_asymptotic(nu, w);
+  } else if (nu >= 0.0) {
+    r = log_besseli_cf(nu, w, nullptr);
+  } else {
+    // I_nu = I'_(nu+1) + ((nu+1)/w) I_(nu+1)
+    cplx dl;
+    const cplx l1 = log_besseli_cf(nu + 1.0, w, &dl);
+    r = l1 + clog_(dl + (nu + 1.0) / w);
+  }
+  r.im += rot;
+  return r;
+}
+
+// ---- Broadie-Kaya: characteristic function of int_0^tau V ds given (V0, VT) ------------------------------------------
+// HestonCFIterator + evaluate_chf, src/distributions/heston.jl:150-212.
+struct BkParams {
+  double kappa, xi2, tau;  // xi2 = sigma^2 (vol of vol squared)
+  double zeta_k, eta_k;    // :167-168
+  double wk;               // z_kappa = sqrt(V0 VT) wk  (:169)
+  double h_fd, cf_tol, atol;
+  int n_std, max_terms;
+  BesselOrder ord;         // nu = d/2 - 1  (:164-165)
+  // transition constants (sample_V_T :128-131, sample_log_S_T :285-297)
+  double dof, c_scale, lam_scale;  // d, c, lambda = lam_scale * V
+  double r_tau, kappa_theta_tau, rho_over_xi, one_m_rho2, rho, theta;
+};
+
+struct BkCf {       // per (V0, VT) pair: HestonCFIterator
+  double sv;        // sqrt(V0 VT)
+  double vsum_s;    // (V0 + VT) / sigma^2
+  cplx logIk;       // log I_nu(z_kappa)
+};
+
+HH_HD BkCf bk_cf_init(const BkParams &p, double V0, double VT) {
+  BkCf it;
+  it.sv = sqrt(V0 * VT);
+  it.vsum_s = (V0 + VT) / p.xi2;
+  it.logIk = log_besseli(p.ord, mk(it.sv * p.wk));
+  return it;
+}
+
+// Phi(a) with the unwrapped angle of z_gamma carried in theta_prev (NaN = first evaluation), heston.jl:184-212.
+HH_HD cplx bk_chf(const BkParams &p, const BkCf &it, double a, double &theta_prev) {
+  const cplx g = csqrt_(cplx{p.kappa * p.kappa, -2.0 * p.xi2 * a});        // gamma            :190
+  const cplx eg = cexp_(-(p.tau * g));
+  const cplx omeg = 1.0 - eg;
+  const cplx zeta_g = omeg / g;                                              // :191
+  const cplx eta_g = g * (1.0 + eg) / omeg;                                   // :192
+  const cplx zg = (it.sv * 4.0) * g * cexp_((-0.5 * p.tau) * g) / p.xi2 / omeg;  // nu_gamma         :193
+  const double th = carg(zg);                                                 // :198
+  double thu = th;
+  if (!(theta_prev != theta_prev)) {                                          // :199-205
+    double dlt = th - theta_prev;
+    dlt -= 2.0 * kBesselPi * nearbyint(dlt / (2.0 * kBesselPi));
+    thu = theta_prev + dlt;
+  }
+  theta_prev = thu;
+  cplx logIg = log_besseli(p.ord, zg);                                        // :206-207
+  logIg.im += p.ord.nu * (thu - th);
+  // phi = exp(-(g - k) tau / 2) (zeta_k / zeta_g) exp((V0+VT)/s^2 (eta_k - eta_g)) exp(logIg - logIk)   :195-211
+  const cplx ex = (-0.5 * p.tau) * (g - p.kappa) + it.vsum_s * (p.eta_k - eta_g) + (logIg - it.logIk);
+  return (p.zeta_k / zeta_g) * cexp_(ex);
+}
+
+}  // namespace hh

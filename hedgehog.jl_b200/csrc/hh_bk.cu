@@ -1,0 +1,572 @@
+// hh_bk.cu — Broadie-Kaya exact simulation of the Heston model: MonteCarlo(HestonDynamics(), HestonBroadieKaya(), cfg).
+//
+// Replaces (reference paths):
+//   rand(rng, ::LogHestonDistribution)        src/distributions/heston.jl:246-259     one exact transition
+//   sample_V_T                                :125-133     V' = c * NoncentralChisq(d, lambda)
+//   sample_integral_V -> sample_from_cf       :140-143, src/distributions/sample_from_cf.jl:27-41
+//       moments_from_cf :50-64, cdf_from_cf :75-96, inverse_cdf :105-135
+//   sample_log_S_T                            heston.jl:278-300
+//   HestonNoise stepping (multi-date)         :82-91  (restart from (S, V) each date)
+//
+// One trajectory per thread, all dates in registers. Per transition the thread
+//   1. draws V' (noncentral chi-square: chi2(d-1) + (Z + sqrt(lambda))^2 for d > 1, Poisson mixture otherwise;
+//      gamma variates by Marsaglia-Tsang) from its own Philox counter stream,
+//   2. evaluates the characteristic function of int V at +-h0, 0 (finite-difference moments, as the reference),
+//   3. evaluates Phi(h j) ONCE per term into a shared-memory table c_j = (2/pi) Re Phi(h j) / j — the reference
+//      recomputes the whole series (one complex Bessel function per term) for every root-finder iteration although
+//      it does not depend on x (sample_from_cf.jl:38, 84-93); terms beyond the table spill to a global slab,
+//   4. inverts F(x) = h x / pi + sum_j c_j sin(h j x) at its uniform by safeguarded Newton inside [0, mean + 11 sd],
+//      to machine precision (the reference accepts |F(x) - u| <= 1e-4; any root of the same F satisfies that),
+//   5. draws log S'.
+// Payoffs are then reduced from the terminal spots by hh_european.cu's terminal_payoff kernel.
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "hh_bessel.cuh"
+#include "hh_ctx.h"
+#include "hh_device.cuh"
+
+namespace hh {
+
+constexpr int kBkThreads = 128;
+constexpr int kBkTable = 96;  // table entries per thread in shared memory (kBkThreads * kBkTable * 8 B = 96 KB)
+
+// terminal spots -> payoff sums (hh_european.cu)
+int terminal_payoffs_launch(hh_ctx *ctx, const double *d_terminal, int64_t n, const hh_payoff *payoffs, int npay,
+                            int64_t extra_nonfinite);
+
+struct BkRng {  // Philox counter stream of one trajectory: counter = (idx_lo, idx_hi, date, draw)
+  uint32_t c0, c1, c2, draw, k0, k1;
+  __device__ __forceinline__ u32x4 block() { return philox4x32_10(c0, c1, c2, draw++, k0, k1); }
+  __device__ __forceinline__ void normals(double &z1, double &z2) { normal_pair_libm(block(), z1, z2); }
+  __device__ __forceinline__ void uniforms(double &u1, double &u2) {  // both in (0, 1)
+    const u32x4 w = block();
+    u1 = u01_for_log(w.x, w.y);
+    u2 = u01_for_log(w.z, w.w);
+  }
+};
+
+// Gamma(alpha, 1), alpha > 0 (Marsaglia & Tsang 2000; alpha < 1 through Gamma(alpha + 1) U^(1/alpha)).
+__device__ double bk_gamma(BkRng &rng, double alpha) {
+  double boost = 1.0;
+  if (alpha < 1.0) {
+    double u, u_;
+    rng.uniforms(u, u_);
+    boost = pow(u, 1.0 / alpha);
+    alpha += 1.0;
+  }
+  const double d = alpha - 1.0 / 3.0, c = 1.0 / sqrt(9.0 * d);
+  for (int it = 0; it < 1000; ++it) {
+    double z, z_, u, u_;
+    rng.normals(z, z_);
+    const double t = 1.0 + c * z;
+    if (t <= 0.0) continue;
+    const double v = t * t * t;
+    rng.uniforms(u, u_);
+    const double z2 = z * z;
+    if (u < 1.0 - 0.0331 * z2 * z2 || log(u) < 0.5 * z2 + d * (1.0 - v + log(v))) return boost * d * v;
+  }
+  return boost * d;  // unreachable in practice (acceptance > 95% per round)
+}
+
+// Poisson(mu): sequential inversion for mu < 30, PTRS transformed rejection (Hoermann 1993) above.
+__device__ double bk_poisson(BkRng &rng, double mu) {
+  if (mu <= 0.0) return 0.0;
+  if (mu < 30.0) {
+    double u, u_;
+    rng.uniforms(u, u_);
+    double p = exp(-mu), s = p, k = 0.0;
+    while (u > s && k < 500.0) {
+      k += 1.0;
+      p *= mu / k;
+      s += p;
+    }
+    return k;
+  }
+  const double slam = sqrt(mu), loglam = log(mu);
+  const double b = 0.931 + 2.53 * slam, a = -0.059 + 0.02483 * b;
+  const double invalpha = 1.1239 + 1.1328 / (b - 3.4), vr = 0.9277 - 3.6224 / (b - 2.0);
+  for (int it = 0; it < 1000; ++it) {
+    double U, V;
+    rng.uniforms(U, V);
+    U -= 0.5;
+    const double us = 0.5 - fabs(U);
+    const double k = floor((2.0 * a / us + b) * U + mu + 0.43);
+    if (us >= 0.07 && V <= vr) return k;
+    if (k < 0.0 || (us < 0.013 && V > us)) continue;
+    if (log(V) + log(invalpha) - log(a / (us * us) + b) <= -mu + k * loglam - lgamma(k + 1.0)) return k;
+  }
+  return floor(mu);
+}
+
+// NoncentralChisq(d, lambda): heston.jl:131 (Distributions.jl [upstream]; any exact sampler has the same law)
+__device__ double bk_ncx2(BkRng &rng, double dof, double lam) {
+  if (dof > 1.0) {
+    double z, z_;
+    rng.normals(z, z_);
+    const double s = z + sqrt(lam);
+    return 2.0 * bk_gamma(rng, 0.5 * (dof - 1.0)) + s * s;
+  }
+  const double n = bk_poisson(rng, 0.5 * lam);
+  return 2.0 * bk_gamma(rng, 0.5 * dof + n);
+}
+
+struct BkInversion {
+  double mean, var, h, x, resid;
+  int J, status, iters;  // status: 0 Newton inside the bracket, 1 unbracketed secant accepted, 2 fell back to max_guess
+};
+
+// Coefficient table: the first `cap` entries in shared memory (stride = blockDim.x doubles), the rest in a global slab.
+struct BkTable {
+  double *sh;
+  double *slab;
+  int64_t slab_stride;
+  int cap, sh_stride;
+  __device__ __forceinline__ double get(int j) const {
+    return j < cap ? sh[j * sh_stride] : slab[(int64_t)(j - cap) * slab_stride];
+  }
+  __device__ __forceinline__ void set(int j, double v) const {
+    if (j < cap) sh[j * sh_stride] = v;
+    else slab[(int64_t)(j - cap) * slab_stride] = v;
+  }
+};
+
+// F(x) - u and F'(x) for F(x) = h x / pi + sum_j c_j sin(j h x)   (cdf_from_cf, sample_from_cf.jl:75-96)
+__device__ __forceinline__ void bk_cdf(const BkTable &tb, int J, double h, double x, double &F, double &dF) {
+  const double th = h * x;
+  double s1, c1;
+  sincos(th, &s1, &c1);
+  const double two_c = 2.0 * c1;
+  double sp = 0.0, s = s1;    // sin((j-1) th), sin(j th)
+  double cp = 1.0, c = c1;    // cos((j-1) th), cos(j th)
+  double acc = 0.0, dacc = 0.0;
+  for (int j = 1; j <= J; ++j) {
+    const double cj = tb.get(j - 1);
+    acc = fma(cj, s, acc);
+    dacc = fma(cj * (double)j, c, dacc);
+    const double sn = fma(two_c, s, -sp), cn = fma(two_c, c, -cp);
+    sp = s; s = sn;
+    cp = c; c = cn;
+  }
+  F = h * x / kBesselPi + acc;
+  dF = h / kBesselPi + h * dacc;
+}
+
+// sample_from_cf (sample_from_cf.jl:27-41) for a given uniform u.
+__device__ BkInversion bk_sample_integral(const BkParams &p, double V0, double VT, double u, const BkTable &tb) {
+  BkInversion r;
+  const BkCf it = bk_cf_init(p, V0, VT);
+  // moments_from_cf :50-64 — the three evaluations share the unwrapping state, in the reference's order
+  double th = nan("");
+  const cplx pp = bk_chf(p, it, p.h_fd, th);
+  const cplx p0 = bk_chf(p, it, 0.0, th);
+  const cplx pm = bk_chf(p, it, -p.h_fd, th);
+  const double mean = (pp.im - pm.im) / (2.0 * p.h_fd);                                  // real(-i (pp - pm) / 2h)
+  const double var = -(pp.re - 2.0 * p0.re + pm.re) / (p.h_fd * p.h_fd) - mean * mean;  // :60-61
+  const double s2 = fmax(var, 1e-12);                                                    // :32
+  const double sd = sqrt(s2);
+  const double ns = mean + sd * normcdfinv(u);                                           // :33
+  const double guess = ns > 0.0 ? ns : mean * 0.01;                                      // :34
+  const double max_guess = mean + 11.0 * sd;                                             // :35
+  const double h = kBesselPi / (mean + (double)p.n_std * sd);                            // :37
+  r.mean = mean;
+  r.var = var;
+  r.h = h;
+  // series coefficients, x-independent (:84-93)
+  th = nan("");
+  int J = 0;
+  const double stop = kBesselPi * p.cf_tol / 2.0;
+  for (int j = 1; j <= p.max_terms; ++j) {
+    const cplx phi = bk_chf(p, it, h * (double)j, th);
+    tb.set(j - 1, (2.0 / kBesselPi) * phi.re / (double)j);
+    J = j;
+    if (cabs(phi) / (double)j < stop) break;
+  }
+  r.J = J;
+  // inverse_cdf :105-135
+  double F, dF;
+  bk_cdf(tb, J, h, max_guess, F, dF);
+  const double fmax_ = F - u;
+  int iters = 1;
+  if (fmax_ >= 0.0 && u > 0.0) {
+    // bracket [0, max_guess]: f(0) = -u < 0 <= f(max_guess); safeguarded Newton from the reference's initial guess
+    double lo = 0.0, hi = max_guess;
+    double x = fmin(fmax(guess, 0.0), max_guess);
+    double f = 0.0;
+    for (int k = 0; k < 100; ++k) {
+      bk_cdf(tb, J, h, x, F, dF);
+      ++iters;
+      f = F - u;
+      if (f < 0.0) lo = x; else hi = x;
+      if (fabs(f) <= 1e-15 || hi - lo <= 1e-15 * max_guess) break;
+      double xn = dF > 0.0 ? x - f / dF : -1.0;
+      if (!(xn > lo && xn < hi)) xn = 0.5 * (lo + hi);
+      if (xn == x) break;
+      x = xn;
+    }
+    r.x = x;
+    r.resid = f;
+    r.status = 0;
+  } else if (u <= 0.0) {
+    r.x = 0.0;
+    r.resid = 0.0;
+    r.status = 0;
+  } else {
+    // F(max_guess) < u: no sign change. The reference first lets its secant iteration run (<= maxiter evaluations) and
+    // accepts x >= 0 with |F(x) - u| <= atol; otherwise it returns max_guess with a warning (:123-126).
+    double x0 = guess, x1 = guess * 1.001 + 1e-12, f0, f1;
+    bk_cdf(tb, J, h, x0, F, dF);
+    f0 = F - u;
+    bk_cdf(tb, J, h, x1, F, dF);
+    f1 = F - u;
+    iters += 2;
+    for (int k = 2; k < 10; ++k) {
+      if (f1 == f0) break;
+      const double x2 = x1 - f1 * (x1 - x0) / (f1 - f0);
+      x0 = x1; f0 = f1; x1 = x2;
+      bk_cdf(tb, J, h, x1, F, dF);
+      f1 = F - u;
+      ++iters;
+    }
+    if (isfinite(x1) && x1 >= 0.0 && fabs(f1) <= p.atol) {
+      r.x = x1;
+      r.resid = f1;
+      r.status = 1;
+    } else {
+      r.x = max_guess;
+      r.resid = fmax_;
+      r.status = 2;
+    }
+  }
+  r.iters = iters;
+  return r;
+}
+
+struct BkArgs {
+  int64_t n, path_offset;
+  uint64_t base_seed;
+  const uint64_t *seeds;
+  int n_dates;
+  BkParams p;
+  double x0, v0;
+  double *terminal;  // S_T per trajectory
+  double *vterm;     // nullable: V_T per trajectory
+  double *slab;
+  int64_t slab_stride;
+  unsigned long long *counters;  // [0] fallbacks, [1] sum J, [2] sum root-finder evaluations, [3] transitions, [4] unbracketed accepted
+};
+
+__global__ void __launch_bounds__(kBkThreads) bk_paths_kernel(const BkArgs a) {
+  extern __shared__ double s_tab[];
+  BkTable tb;
+  tb.sh = s_tab + threadIdx.x;
+  tb.sh_stride = kBkThreads;
+  tb.cap = kBkTable;
+  tb.slab = a.slab + ((int64_t)blockIdx.x * kBkThreads + threadIdx.x);
+  tb.slab_stride = a.slab_stride;
+  const BkParams &p = a.p;
+  unsigned long long nfall = 0, sumJ = 0, sumIt = 0, ntr = 0, nsec = 0;
+  for (int64_t i = (int64_t)blockIdx.x * kBkThreads + threadIdx.x; i < a.n; i += (int64_t)gridDim.x * kBkThreads) {
+    BkRng rng;
+    uint64_t key = a.base_seed, idx = (uint64_t)(a.path_offset + i);
+    if (a.seeds) {
+      key = a.seeds[i];
+      idx = 0;
+    }
+    rng.c0 = (uint32_t)idx;
+    rng.c1 = (uint32_t)(idx >> 32);
+    rng.k0 = (uint32_t)key;
+    rng.k1 = (uint32_t)(key >> 32);
+    double x = a.x0, v = a.v0;
+    for (int n = 0; n < a.n_dates; ++n) {
+      rng.c2 = (uint32_t)n;
+      rng.draw = 0;
+      // 1. V' (sample_V_T)
+      const double vt = fmax(p.c_scale * bk_ncx2(rng, p.dof, p.lam_scale * v), 1e-300);
+      // 2.-4. int V (sample_integral_V)
+      double u, z, dummy;
+      rng.uniforms(u, dummy);
+      const BkInversion inv = bk_sample_integral(p, fmax(v, 1e-300), vt, u, tb);
+      // 5. log S' (sample_log_S_T)
+      rng.normals(z, dummy);
+      const double mu = x + p.r_tau - 0.5 * inv.x + p.rho_over_xi * (vt - v - p.kappa_theta_tau + p.kappa * inv.x);
+      x = mu + sqrt(p.one_m_rho2 * inv.x) * z;
+      v = vt;
+      nfall += inv.status == 2;
+      nsec += inv.status == 1;
+      sumJ += (unsigned)inv.J;
+      sumIt += (unsigned)inv.iters;
+      ++ntr;
+    }
+    a.terminal[i] = exp(x);
+    if (a.vterm) a.vterm[i] = v;
+  }
+  // warp-aggregate the statistics
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    nfall += __shfl_down_sync(0xffffffffu, nfall, o);
+    sumJ += __shfl_down_sync(0xffffffffu, sumJ, o);
+    sumIt += __shfl_down_sync(0xffffffffu, sumIt, o);
+    ntr += __shfl_down_sync(0xffffffffu, ntr, o);
+    nsec += __shfl_down_sync(0xffffffffu, nsec, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(&a.counters[0], nfall);
+    atomicAdd(&a.counters[1], sumJ);
+    atomicAdd(&a.counters[2], sumIt);
+    atomicAdd(&a.counters[3], ntr);
+    atomicAdd(&a.counters[4], nsec);
+  }
+}
+
+// ---- probes (parity of the deterministic pieces) ---------------------------------------------------------------------
+__global__ void bk_chf_kernel(const BkParams p, const double *V0, const double *VT, int n, const double *a, int na,
+                              double *ore, double *oim) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const BkCf it = bk_cf_init(p, V0[i], VT[i]);
+  double th = nan("");
+  for (int j = 0; j < na; ++j) {
+    const cplx r = bk_chf(p, it, a[(size_t)i * na + j], th);
+    ore[(size_t)i * na + j] = r.re;
+    oim[(size_t)i * na + j] = r.im;
+  }
+}
+
+__global__ void bk_log_besseli_kernel(const BesselOrder o, const double *zr, const double *zi, int n, double *ore, double *oim) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const cplx r = log_besseli(o, cplx{zr[i], zi[i]});
+  ore[i] = r.re;
+  oim[i] = r.im;
+}
+
+// out[i] = {x, mean, var, h, J, status, resid, iters}
+__global__ void __launch_bounds__(kBkThreads) bk_integral_kernel(const BkParams p, const double *V0, const double *VT,
+                                                                 const double *U, int n, double *out, double *slab,
+                                                                 int64_t slab_stride) {
+  extern __shared__ double s_tab[];
+  BkTable tb;
+  tb.sh = s_tab + threadIdx.x;
+  tb.sh_stride = kBkThreads;
+  tb.cap = kBkTable;
+  tb.slab = slab + ((int64_t)blockIdx.x * kBkThreads + threadIdx.x);
+  tb.slab_stride = slab_stride;
+  const int i = blockIdx.x * kBkThreads + threadIdx.x;
+  if (i >= n) return;
+  const BkInversion r = bk_sample_integral(p, V0[i], VT[i], U[i], tb);
+  double *o = out + (size_t)i * 8;
+  o[0] = r.x; o[1] = r.mean; o[2] = r.var; o[3] = r.h;
+  o[4] = (double)r.J; o[5] = (double)r.status; o[6] = r.resid; o[7] = (double)r.iters;
+}
+
+__global__ void bk_variance_kernel(const BkParams p, const double *V0, int n, uint64_t seed, double *VT) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  BkRng rng;
+  rng.c0 = (uint32_t)i;
+  rng.c1 = 0;
+  rng.c2 = 0;
+  rng.draw = 0;
+  rng.k0 = (uint32_t)seed;
+  rng.k1 = (uint32_t)(seed >> 32);
+  VT[i] = p.c_scale * bk_ncx2(rng, p.dof, p.lam_scale * V0[i]);
+}
+
+// ---- host side ---------------------------------------------------------------------------------------------------------
+static int make_params(hh_ctx *ctx, const hh_model *m, double tau, const hh_bk_config *cfg, BkParams &p) {
+  if (!(m->kappa > 0.0)) return ctx->fail(HH_ERR_ARG, "Broadie-Kaya needs kappa > 0");
+  if (m->xi == 0.0) return ctx->fail(HH_ERR_ARG, "Broadie-Kaya needs a non-zero vol of vol");
+  if (!(m->theta > 0.0)) return ctx->fail(HH_ERR_ARG, "Broadie-Kaya needs theta > 0");
+  if (!(tau > 0.0)) return ctx->fail(HH_ERR_ARG, "transition horizon must be positive");
+  memset(&p, 0, sizeof p);
+  p.kappa = m->kappa;
+  p.xi2 = m->xi * m->xi;
+  p.tau = tau;
+  const double E = -expm1(-m->kappa * tau);
+  p.zeta_k = E / m->kappa;                                             // heston.jl:167
+  p.eta_k = m->kappa * (1.0 + exp(-m->kappa * tau)) / E;                // :168
+  p.wk = 4.0 * m->kappa * exp(-0.5 * m->kappa * tau) / p.xi2 / E;      // :169
+  p.dof = 4.0 * m->kappa * m->theta / p.xi2;                           // :128
+  p.ord = make_bessel_order(0.5 * p.dof - 1.0);                        // :165
+  p.lam_scale = 4.0 * m->kappa * exp(-m->kappa * tau) / (p.xi2 * E);   // :129
+  p.c_scale = p.xi2 * E / (4.0 * m->kappa);                            // :130
+  hh_bk_config c;
+  if (cfg && cfg->n_std > 0) c = *cfg;
+  else hh_default_bk_config(&c);
+  p.h_fd = c.h_fd;
+  p.cf_tol = c.cf_tol;
+  p.atol = c.atol;
+  p.n_std = c.n_std;
+  p.max_terms = c.max_terms > 0 ? c.max_terms : 4096;
+  if (p.max_terms > 4096) p.max_terms = 4096;
+  p.r_tau = m->r * tau;
+  p.kappa_theta_tau = m->kappa * m->theta * tau;
+  p.rho_over_xi = m->rho / m->xi;
+  p.one_m_rho2 = 1.0 - m->rho * m->rho;
+  p.rho = m->rho;
+  p.theta = m->theta;
+  return HH_OK;
+}
+
+static int ensure_slab(hh_ctx *ctx, int nblocks, const BkParams &p, double **slab, int64_t *stride) {
+  const int64_t threads = (int64_t)nblocks * kBkThreads;
+  const int64_t extra = p.max_terms > kBkTable ? p.max_terms - kBkTable : 0;
+  HH_CUDA(ctx, ctx->d_grid.ensure(sizeof(double) * (size_t)(threads * extra + 1)));
+  *slab = ctx->d_grid.as<double>();
+  *stride = threads;
+  return HH_OK;
+}
+
+static int bk_set_smem(hh_ctx *ctx) {
+  static bool done[64] = {};
+  if (ctx->device < 64 && done[ctx->device]) return HH_OK;
+  const int bytes = kBkThreads * kBkTable * (int)sizeof(double);
+  HH_CUDA(ctx, cudaFuncSetAttribute(bk_paths_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  HH_CUDA(ctx, cudaFuncSetAttribute(bk_integral_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  if (ctx->device < 64) done[ctx->device] = true;
+  return HH_OK;
+}
+
+int bk_european_launch(hh_ctx *ctx, const hh_model *m, const hh_sim *s, const hh_payoff *payoffs, int npay,
+                       int want_terminal) {
+  if (npay < 1 || npay > 256 || !payoffs) return ctx->fail(HH_ERR_ARG, "npayoffs must be in [1, 256] (got %d)", npay);
+  if (s->rng_mode != HH_RNG_PHILOX)
+    return ctx->fail(HH_ERR_UNSUPPORTED, "Broadie-Kaya draws from the in-kernel Philox stream only; the deterministic "
+                                         "pieces have their own parity probes (hh_bk_chf, hh_bk_integral)");
+  if (s->precision != HH_PREC_F64) return ctx->fail(HH_ERR_UNSUPPORTED, "Broadie-Kaya runs in f64 only");
+  const int ndates = s->n_steps > 0 ? s->n_steps : 1;
+  BkArgs a;
+  memset(&a, 0, sizeof a);
+  int rc = make_params(ctx, m, m->T / ndates, &s->bk, a.p);
+  if (rc) return rc;
+  const int64_t N = s->n_paths;
+  HH_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  rc = bk_set_smem(ctx);
+  if (rc) return rc;
+  const int smem = kBkThreads * kBkTable * (int)sizeof(double);
+  int occ = 1;
+  HH_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bk_paths_kernel, kBkThreads, smem));
+  if (occ < 1) occ = 1;
+  const int64_t want_blocks = (N + kBkThreads - 1) / kBkThreads;
+  int64_t grid = (int64_t)ctx->sm_count * occ;
+  if (grid > want_blocks) grid = want_blocks;
+  rc = ensure_slab(ctx, (int)grid, a.p, &a.slab, &a.slab_stride);
+  if (rc) return rc;
+  HH_CUDA(ctx, ctx->d_terminal.ensure(sizeof(double) * (size_t)N));
+  HH_CUDA(ctx, ctx->d_counters.ensure(sizeof(unsigned long long) * 8));
+  HH_CUDA(ctx, cudaMemsetAsync(ctx->d_counters.ptr, 0, sizeof(unsigned long long) * 8, st));
+  a.n = N;
+  a.path_offset = s->path_offset;
+  a.base_seed = s->base_seed;
+  if (s->seeds) {
+    const size_t bytes = sizeof(uint64_t) * (size_t)N;
+    HH_CUDA(ctx, ctx->d_seeds.ensure(bytes));
+    HH_CUDA(ctx, cudaMemcpyAsync(ctx->d_seeds.ptr, s->seeds, bytes, cudaMemcpyHostToDevice, st));
+    a.seeds = ctx->d_seeds.as<uint64_t>();
+  }
+  a.n_dates = ndates;
+  a.x0 = log(m->S0);
+  a.v0 = m->V0;
+  a.terminal = ctx->d_terminal.as<double>();
+  a.counters = ctx->d_counters.as<unsigned long long>();
+  HH_CUDA(ctx, cudaEventRecord(ctx->ev0, st));
+  bk_paths_kernel<<<(unsigned)grid, kBkThreads, smem, st>>>(a);
+  HH_CUDA(ctx, cudaGetLastError());
+  rc = terminal_payoffs_launch(ctx, a.terminal, N, payoffs, npay, 0);
+  if (rc) return rc;
+  ctx->pend.want_terminal = want_terminal != 0;
+  ctx->pend.bk = true;
+  return HH_OK;
+}
+
+int bk_chf(hh_ctx *ctx, const hh_model *m, double tau, const double *V0, const double *VT, int n, const double *a, int na,
+           double *out_re, double *out_im) {
+  if (!m || !V0 || !VT || !a || !out_re || !out_im || n < 1 || na < 1) return ctx->fail(HH_ERR_ARG, "hh_bk_chf: bad argument");
+  BkParams p;
+  int rc = make_params(ctx, m, tau, nullptr, p);
+  if (rc) return rc;
+  HH_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const size_t nv = sizeof(double) * (size_t)n, nm = sizeof(double) * (size_t)n * na;
+  HH_CUDA(ctx, ctx->d_misc.ensure(2 * nv + 3 * nm));
+  double *dV0 = ctx->d_misc.as<double>(), *dVT = dV0 + n, *da = dVT + n, *dre = da + (size_t)n * na, *dim_ = dre + (size_t)n * na;
+  HH_CUDA(ctx, cudaMemcpyAsync(dV0, V0, nv, cudaMemcpyHostToDevice, st));
+  HH_CUDA(ctx, cudaMemcpyAsync(dVT, VT, nv, cudaMemcpyHostToDevice, st));
+  HH_CUDA(ctx, cudaMemcpyAsync(da, a, nm, cudaMemcpyHostToDevice, st));
+  bk_chf_kernel<<<(n + 63) / 64, 64, 0, st>>>(p, dV0, dVT, n, da, na, dre, dim_);
+  HH_CUDA(ctx, cudaGetLastError());
+  HH_CUDA(ctx, cudaMemcpyAsync(out_re, dre, nm, cudaMemcpyDeviceToHost, st));
+  HH_CUDA(ctx, cudaMemcpyAsync(out_im, dim_, nm, cudaMemcpyDeviceToHost, st));
+  HH_CUDA(ctx, cudaStreamSynchronize(st));
+  return HH_OK;
+}
+
+int bk_log_besseli(hh_ctx *ctx, double nu, const double *zr, const double *zi, int n, double *out_re, double *out_im) {
+  if (!zr || !zi || !out_re || !out_im || n < 1) return ctx->fail(HH_ERR_ARG, "hh_bk_log_besseli: bad argument");
+  if (!(nu > -1.0)) return ctx->fail(HH_ERR_ARG, "order must be > -1 (got %g)", nu);
+  HH_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const size_t nv = sizeof(double) * (size_t)n;
+  HH_CUDA(ctx, ctx->d_misc.ensure(4 * nv));
+  double *dzr = ctx->d_misc.as<double>(), *dzi = dzr + n, *dre = dzi + n, *dim_ = dre + n;
+  HH_CUDA(ctx, cudaMemcpyAsync(dzr, zr, nv, cudaMemcpyHostToDevice, st));
+  HH_CUDA(ctx, cudaMemcpyAsync(dzi, zi, nv, cudaMemcpyHostToDevice, st));
+  bk_log_besseli_kernel<<<(n + 127) / 128, 128, 0, st>>>(make_bessel_order(nu), dzr, dzi, n, dre, dim_);
+  HH_CUDA(ctx, cudaGetLastError());
+  HH_CUDA(ctx, cudaMemcpyAsync(out_re, dre, nv, cudaMemcpyDeviceToHost, st));
+  HH_CUDA(ctx, cudaMemcpyAsync(out_im, dim_, nv, cudaMemcpyDeviceToHost, st));
+  HH_CUDA(ctx, cudaStreamSynchronize(st));
+  return HH_OK;
+}
+
+int bk_integral(hh_ctx *ctx, const hh_model *m, double tau, const hh_bk_config *cfg, const double *V0, const double *VT,
+                const double *U, int n, double *out8) {
+  if (!m || !V0 || !VT || !U || !out8 || n < 1) return ctx->fail(HH_ERR_ARG, "hh_bk_integral: bad argument");
+  BkParams p;
+  int rc = make_params(ctx, m, tau, cfg, p);
+  if (rc) return rc;
+  HH_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  rc = bk_set_smem(ctx);
+  if (rc) return rc;
+  const int nblocks = (n + kBkThreads - 1) / kBkThreads;
+  double *slab;
+  int64_t stride;
+  rc = ensure_slab(ctx, nblocks, p, &slab, &stride);
+  if (rc) return rc;
+  const size_t nv = sizeof(double) * (size_t)n;
+  HH_CUDA(ctx, ctx->d_misc.ensure(3 * nv + 8 * nv));
+  double *dV0 = ctx->d_misc.as<double>(), *dVT = dV0 + n, *dU = dVT + n, *dout = dU + n;
+  HH_CUDA(ctx, cudaMemcpyAsync(dV0, V0, nv, cudaMemcpyHostToDevice, st));
+  HH_CUDA(ctx, cudaMemcpyAsync(dVT, VT, nv, cudaMemcpyHostToDevice, st));
+  HH_CUDA(ctx, cudaMemcpyAsync(dU, U, nv, cudaMemcpyHostToDevice, st));
+  const int smem = kBkThreads * kBkTable * (int)sizeof(double);
+  bk_integral_kernel<<<nblocks, kBkThreads, smem, st>>>(p, dV0, dVT, dU, n, dout, slab, stride);
+  HH_CUDA(ctx, cudaGetLastError());
+  HH_CUDA(ctx, cudaMemcpyAsync(out8, dout, 8 * nv, cudaMemcpyDeviceToHost, st));
+  HH_CUDA(ctx, cudaStreamSynchronize(st));
+  return HH_OK;
+}
+
+int bk_variance(hh_ctx *ctx, const hh_model *m, double tau, const double *V0, int n, uint64_t seed, double *VT) {
+  if (!m || !V0 || !VT || n < 1) return ctx->fail(HH_ERR_ARG, "hh_bk_variance: bad argument");
+  BkParams p;
+  int rc = make_params(ctx, m, tau, nullptr, p);
+  if (rc) return rc;
+  HH_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const size_t nv = sizeof(double) * (size_t)n;
+  HH_CUDA(ctx, ctx->d_misc.ensure(2 * nv));
+  double *dV0 = ctx->d_misc.as<double>(), *dVT = dV0 + n;
+  HH_CUDA(ctx, cudaMemcpyAsync(dV0, V0, nv, cudaMemcpyHostToDevice, st));
+  bk_variance_kernel<<<(n + 127) / 128, 128, 0, st>>>(p, dV0, n, seed, dVT);
+  HH_CUDA(ctx, cudaGetLastError());
+  HH_CUDA(ctx, cudaMemcpyAsync(VT, dVT, nv, cudaMemcpyDeviceToHost, st));
+  HH_CUDA(ctx, cudaStreamSynchronize(st));
+  return HH_OK;
+}
+
+}  // namespace hh

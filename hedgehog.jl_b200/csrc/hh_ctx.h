@@ -43,6 +43,7 @@ struct PendingEuropean {
   int64_t n = 0;
   bool anti = false;
   bool want_terminal = false;
+  bool bk = false;  // Broadie-Kaya run: counters live in d_counters
 };
 
 }  // namespace hh
@@ -59,7 +60,8 @@ struct hh_ctx {
   std::string err;
 
   hh::DeviceBuffer d_payoffs, d_partials, d_final, d_terminal, d_seeds, d_normals, d_tangents;
-  hh::DeviceBuffer d_grid, d_cash, d_tau, d_lsm_partials, d_lsm_state, d_misc;
+  hh::DeviceBuffer d_grid, d_cash, d_tau, d_lsm_partials, d_lsm_state, d_misc, d_counters;
+  double bk_stats[5] = {0, 0, 0, 0, 0};
   void *h_pinned = nullptr;  // small pinned staging area for results
   size_t h_pinned_cap = 0;
   hh::PendingEuropean pend;

@@ -428,6 +428,54 @@ __global__ void __launch_bounds__(kThreads, MINB) heston_fast_kernel(const EuroA
   }
 }
 
+// Payoff sums from terminal spots that another kernel produced (Broadie-Kaya): the same payoff transpose as above.
+__global__ void __launch_bounds__(kThreads) terminal_payoff_kernel(const double *__restrict__ terminal, int64_t n,
+                                                                   const hh_payoff *__restrict__ payoffs, int npay,
+                                                                   int kp_log2, double *partials) {
+  constexpr int NACC = 3;
+  __shared__ double smem[NACC * kThreads];
+  const int tid = threadIdx.x;
+  const int KP = 1 << kp_log2;
+  const int k = tid & (KP - 1);
+  const int g = tid >> kp_log2;
+  const int G = kThreads >> kp_log2;
+  double strike = 0.0, cp = 0.0;
+  if (k < npay) {
+    strike = payoffs[k].strike;
+    cp = payoffs[k].cp;
+  }
+  double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0;
+  for (int64_t base = (int64_t)blockIdx.x * kThreads; base < n; base += (int64_t)gridDim.x * kThreads) {
+    const int64_t i = base + tid;
+    smem[tid] = i < n ? terminal[i] : 0.0;
+    __syncthreads();
+    const int64_t rem = n - base;
+    const int nvalid = rem < kThreads ? (int)rem : kThreads;
+    if (k < npay) {
+      for (int q = g; q < nvalid; q += G) {
+        const double sp = smem[q];
+        const double pay = fmax(cp * (sp - strike), 0.0);  // payoffs.jl:154-156
+        acc0 += pay;
+        acc1 = fma(pay, pay, acc1);
+        if (k == 0 && !isfinite(sp)) acc2 += 1.0;
+      }
+    }
+    __syncthreads();
+  }
+  smem[tid] = acc0;
+  smem[kThreads + tid] = acc1;
+  smem[2 * kThreads + tid] = acc2;
+  __syncthreads();
+  if (tid < npay) {
+    double *out = partials + ((size_t)blockIdx.x * npay + tid) * NACC;
+    for (int c = 0; c < NACC; ++c) {
+      double t = 0.0;
+      for (int gg = 0; gg < G; ++gg) t += smem[c * kThreads + (gg << kp_log2) + tid];
+      out[c] = t;
+    }
+  }
+}
+
 // Sum the per-block partials in a fixed order: one block per payoff.
 __global__ void __launch_bounds__(kThreads) finalize_kernel(const double *partials, int nblocks, int npay, int nacc,
                                                             double *out) {
@@ -726,6 +774,38 @@ int european_launch(hh_ctx *ctx, const hh_model *m, const hh_sim *s, const hh_pa
   ctx->pend.n = N;
   ctx->pend.anti = anti;
   ctx->pend.want_terminal = want_terminal != 0;
+  ctx->pend.bk = false;
+  return HH_OK;
+}
+
+// Enqueue the payoff reduction over terminal spots already on the device; ev0 was recorded by the caller before its
+// own kernels. Leaves the context in the same pending state as european_launch.
+int terminal_payoffs_launch(hh_ctx *ctx, const double *d_terminal, int64_t n, const hh_payoff *payoffs, int npay,
+                            int64_t) {
+  cudaStream_t st = ctx->stream;
+  int kp_log2 = 0;
+  while ((1 << kp_log2) < npay) kp_log2++;
+  HH_CUDA(ctx, ctx->d_payoffs.ensure(sizeof(hh_payoff) * (size_t)npay));
+  HH_CUDA(ctx, cudaMemcpyAsync(ctx->d_payoffs.ptr, payoffs, sizeof(hh_payoff) * (size_t)npay, cudaMemcpyHostToDevice, st));
+  constexpr int NACC = 3;
+  const int64_t batches = (n + kThreads - 1) / kThreads;
+  int64_t grid = (int64_t)ctx->sm_count * 4;
+  if (grid > batches) grid = batches;
+  HH_CUDA(ctx, ctx->d_partials.ensure(sizeof(double) * (size_t)grid * npay * NACC));
+  HH_CUDA(ctx, ctx->d_final.ensure(sizeof(double) * (size_t)npay * NACC));
+  terminal_payoff_kernel<<<(unsigned)grid, kThreads, 0, st>>>(d_terminal, n, ctx->d_payoffs.as<hh_payoff>(), npay, kp_log2,
+                                                              ctx->d_partials.as<double>());
+  HH_CUDA(ctx, cudaGetLastError());
+  finalize_kernel<<<npay, kThreads, 0, st>>>(ctx->d_partials.as<double>(), (int)grid, npay, NACC, ctx->d_final.as<double>());
+  HH_CUDA(ctx, cudaGetLastError());
+  HH_CUDA(ctx, cudaEventRecord(ctx->ev1, st));
+  ctx->pend.active = true;
+  ctx->pend.npay = npay;
+  ctx->pend.nblocks = (int)grid;
+  ctx->pend.n = n;
+  ctx->pend.anti = false;
+  ctx->pend.want_terminal = false;
+  ctx->pend.bk = false;
   return HH_OK;
 }
 
@@ -746,8 +826,13 @@ int european_collect(hh_ctx *ctx, double discount, hh_result *results, double *t
   HH_CUDA(ctx, cudaMemcpyAsync(fin.data(), ctx->d_final.ptr, sizeof(double) * fin.size(), cudaMemcpyDeviceToHost, st));
   if (terminal)
     HH_CUDA(ctx, cudaMemcpyAsync(terminal, ctx->d_terminal.ptr, sizeof(double) * tlen, cudaMemcpyDeviceToHost, st));
+  unsigned long long counters[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (ctx->pend.bk)
+    HH_CUDA(ctx, cudaMemcpyAsync(counters, ctx->d_counters.ptr, sizeof counters, cudaMemcpyDeviceToHost, st));
   HH_CUDA(ctx, cudaStreamSynchronize(st));
   ctx->pend.active = false;
+  if (ctx->pend.bk)
+    for (int i = 0; i < 5; ++i) ctx->bk_stats[i] = (double)counters[i];
   float ms = 0.f;
   HH_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
   for (int k = 0; k < npay; ++k) {
@@ -762,6 +847,7 @@ int european_collect(hh_ctx *ctx, double discount, hh_result *results, double *t
     if (var < 0) var = 0;
     r->std_error = discount * sqrt(var / (double)N);
     r->n_nonfinite = (int64_t)fin[2];
+    r->n_fallback = ctx->pend.bk ? (int64_t)counters[0] : 0;
     r->kernel_ms = ms;
   }
   return HH_OK;

@@ -114,6 +114,10 @@ struct LsmPassArgs {
   int t_next;
   int first;  // t+1 is the terminal date: z = payoff(S_M)
   int last;   // t = 0: no regression, accumulate sum / sumsq of D z
+  int reverse;             // walk the columns from the end (alternates per pass for L2 reuse)
+  unsigned int *done;      // arrival counter of the blocks of this pass
+  double *moments;         // [nacc] sums over all blocks, written by the last block
+  LsmFit *fit_out;         // nullable: where the last block writes the fit of date t (single-GPU form)
 };
 
 template <int DEG>
@@ -183,73 +187,35 @@ __device__ __forceinline__ void lsm_column(const LsmPassArgs &a, const double *f
   }
 }
 
-template <int DEG>
-__global__ void __launch_bounds__(kLsmThreads) lsm_pass_kernel(const LsmPassArgs a) {
-  constexpr int NACC = lsm_nacc<DEG>();
-  __shared__ double s_red[NACC][kLsmThreads / 32];
-  double fit[DEG + 1];
-  bool fit_active = false;
-  if (!a.first) {
-    fit_active = a.fit_next->active != 0.0;
+// Sum the per-block partials in a fixed order: moments[c] = sum_b partials[b][c]. One warp per accumulator
+// (lanes stride over the blocks, then a shuffle tree), so the dependent chain is nblocks / 32 long.
+__device__ __forceinline__ void lsm_reduce_partials(const double *partials, int nblocks, int nacc, double *moments) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  for (int c = warp; c < nacc; c += nwarps) {
+    double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;
+    int b = lane;
+    for (; b + 96 < nblocks; b += 128) {
+      t0 += partials[(size_t)b * nacc + c];
+      t1 += partials[(size_t)(b + 32) * nacc + c];
+      t2 += partials[(size_t)(b + 64) * nacc + c];
+      t3 += partials[(size_t)(b + 96) * nacc + c];
+    }
+    for (; b < nblocks; b += 32) t0 += partials[(size_t)b * nacc + c];
+    double t = (t0 + t1) + (t2 + t3);
 #pragma unroll
-    for (int k = 0; k <= DEG; ++k) fit[k] = a.fit_next->c[k];
-  }
-  double acc[NACC];
-#pragma unroll
-  for (int c = 0; c < NACC; ++c) acc[c] = 0.0;
-
-  // two columns per thread per iteration: 16 B loads and stores (the slices are 16 B aligned, stride is even)
-  const int64_t npairs = a.ncols >> 1;
-  const double2 *Sn2 = reinterpret_cast<const double2 *>(a.S_next);
-  const double2 *Sc2 = reinterpret_cast<const double2 *>(a.S_cur);
-  double2 *z2 = reinterpret_cast<double2 *>(a.z);
-  for (int64_t q = (int64_t)blockIdx.x * kLsmThreads + threadIdx.x; q < npairs; q += (int64_t)gridDim.x * kLsmThreads) {
-    const double2 sn = Sn2[q];
-    double2 sc = make_double2(0.0, 0.0), zi = make_double2(0.0, 0.0), zo;
-    if (!a.last) sc = Sc2[q];
-    if (!a.first) zi = z2[q];
-    lsm_column<DEG>(a, fit, fit_active, sn.x, sc.x, zi.x, 2 * q, zo.x, acc);
-    lsm_column<DEG>(a, fit, fit_active, sn.y, sc.y, zi.y, 2 * q + 1, zo.y, acc);
-    z2[q] = zo;
-  }
-  if ((a.ncols & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
-    const int64_t p = a.ncols - 1;
-    double zo;
-    lsm_column<DEG>(a, fit, fit_active, a.S_next[p], a.last ? 0.0 : a.S_cur[p], a.first ? 0.0 : a.z[p], p, zo, acc);
-    a.z[p] = zo;
-  }
-
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-  for (int c = 0; c < NACC; ++c) {
-    double v = acc[c];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-    if (lane == 0) s_red[c][warp] = v;
-  }
-  __syncthreads();
-  if (threadIdx.x < NACC) {
-    double t = 0.0;
-#pragma unroll
-    for (int w = 0; w < kLsmThreads / 32; ++w) t += s_red[threadIdx.x][w];
-    a.partials[(size_t)blockIdx.x * NACC + threadIdx.x] = t;
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_down_sync(0xffffffffu, t, o);
+    if (lane == 0) moments[c] = t;
   }
 }
 
-// Sum the per-block partials in a fixed order: moments[c] = sum_b partials[b][c].
-__global__ void lsm_reduce_kernel(const double *partials, int nblocks, int nacc, double *moments) {
-  const int c = threadIdx.x;
-  if (c >= nacc) return;
-  double t = 0.0;
-  for (int b = 0; b < nblocks; ++b) t += partials[(size_t)b * nacc + c];
-  moments[c] = t;
+__global__ void __launch_bounds__(256) lsm_reduce_kernel(const double *partials, int nblocks, int nacc, double *moments) {
+  lsm_reduce_partials(partials, nblocks, nacc, moments);
 }
 
 // Normal equations in the Chebyshev basis: G[i][j] = (m[i+j] + m[|i-j|]) / 2, rhs[i] = r[i]; Cholesky.
 // If the matrix is numerically singular at the requested degree (fewer distinct in-the-money spots than
 // coefficients), the leading block that factorises is used (a lower-degree fit in the same nested basis).
-__global__ void lsm_fit_kernel(const double *moments, int deg, LsmFit *out) {
-  if (threadIdx.x != 0) return;
+__device__ void lsm_fit(const double *moments, int deg, LsmFit *out) {
   const int nm = 2 * deg + 1;
   const double *m = moments, *r = moments + nm;
   const double count = moments[nm + deg + 1];
@@ -293,6 +259,100 @@ __global__ void lsm_fit_kernel(const double *moments, int deg, LsmFit *out) {
   *out = f;
 }
 
+__global__ void lsm_fit_kernel(const double *moments, int deg, LsmFit *out) {
+  if (threadIdx.x == 0) lsm_fit(moments, deg, out);
+}
+
+template <int DEG>
+__global__ void __launch_bounds__(kLsmThreads) lsm_pass_kernel(const LsmPassArgs a) {
+  constexpr int NACC = lsm_nacc<DEG>();
+  __shared__ double s_red[NACC][kLsmThreads / 32];
+  __shared__ bool s_last;
+  double fit[DEG + 1];
+  bool fit_active = false;
+  if (!a.first) {
+    fit_active = a.fit_next->active != 0.0;
+#pragma unroll
+    for (int k = 0; k <= DEG; ++k) fit[k] = a.fit_next->c[k];
+  }
+  double acc[NACC];
+#pragma unroll
+  for (int c = 0; c < NACC; ++c) acc[c] = 0.0;
+
+  // Two columns per thread per iteration (16 B loads and stores; the slices are 256 B aligned), and the loads of the
+  // next iteration are issued before the arithmetic of the current one so that every thread keeps 6 x 16 B in flight.
+  const int64_t npairs = a.ncols >> 1;
+  const double2 *Sn2 = reinterpret_cast<const double2 *>(a.S_next);
+  const double2 *Sc2 = reinterpret_cast<const double2 *>(a.S_cur);
+  double2 *z2 = reinterpret_cast<double2 *>(a.z);
+  const int64_t step = (int64_t)gridDim.x * kLsmThreads;
+  int64_t q = (int64_t)blockIdx.x * kLsmThreads + threadIdx.x;
+  // passes alternate their direction over the columns: what the previous pass touched last (z and the shared date
+  // slice) is what this pass touches first, while it is still in L2
+  const bool rev = a.reverse != 0;
+  auto at = [&](int64_t k) { return rev ? npairs - 1 - k : k; };
+  double2 sn = make_double2(0.0, 0.0), sc = sn, zi = sn;
+  if (q < npairs) {
+    sn = __ldcs(Sn2 + at(q));
+    if (!a.last) sc = __ldg(Sc2 + at(q));
+    if (!a.first) zi = z2[at(q)];
+  }
+  while (q < npairs) {
+    const int64_t qn = q + step;
+    double2 sn_n = make_double2(0.0, 0.0), sc_n = sn_n, zi_n = sn_n;
+    if (qn < npairs) {
+      sn_n = __ldcs(Sn2 + at(qn));
+      if (!a.last) sc_n = __ldg(Sc2 + at(qn));
+      if (!a.first) zi_n = z2[at(qn)];
+    }
+    double2 zo;
+    const int64_t col = 2 * at(q);
+    lsm_column<DEG>(a, fit, fit_active, sn.x, sc.x, zi.x, col, zo.x, acc);
+    lsm_column<DEG>(a, fit, fit_active, sn.y, sc.y, zi.y, col + 1, zo.y, acc);
+    z2[at(q)] = zo;
+    sn = sn_n;
+    sc = sc_n;
+    zi = zi_n;
+    q = qn;
+  }
+  if ((a.ncols & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+    const int64_t p = a.ncols - 1;
+    double zo;
+    lsm_column<DEG>(a, fit, fit_active, a.S_next[p], a.last ? 0.0 : a.S_cur[p], a.first ? 0.0 : a.z[p], p, zo, acc);
+    a.z[p] = zo;
+  }
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int c = 0; c < NACC; ++c) {
+    double v = acc[c];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if (lane == 0) s_red[c][warp] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < NACC) {
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < kLsmThreads / 32; ++w) t += s_red[threadIdx.x][w];
+    a.partials[(size_t)blockIdx.x * NACC + threadIdx.x] = t;
+  }
+  // the block that finishes last sums the partials of all blocks (fixed order) and fits the date's polynomial
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(a.done, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    lsm_reduce_partials(a.partials, (int)gridDim.x, NACC, a.moments);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      if (a.fit_out) lsm_fit(a.moments, DEG, a.fit_out);
+      *a.done = 0u;
+    }
+  }
+}
+
 // stopping_info values: v_p = payoff(G[tau_p][p])  (:112, :163-164)
 __global__ void lsm_stop_values_kernel(const double *grid, int64_t stride, int64_t ncols, const int32_t *tau, double strike,
                                        double cp, double *val) {
@@ -327,6 +387,27 @@ template <int DEG>
 static cudaError_t launch_pass(const LsmPassArgs &a, int grid, cudaStream_t st) {
   lsm_pass_kernel<DEG><<<grid, kLsmThreads, 0, st>>>(a);
   return cudaGetLastError();
+}
+
+template <int DEG>
+static int pass_occupancy() {
+  int occ = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, lsm_pass_kernel<DEG>, kLsmThreads, 0) != cudaSuccess || occ < 1) occ = 1;
+  return occ;
+}
+
+static int pass_occupancy_deg(int deg) {
+  switch (deg) {
+    case 0: return pass_occupancy<0>();
+    case 1: return pass_occupancy<1>();
+    case 2: return pass_occupancy<2>();
+    case 3: return pass_occupancy<3>();
+    case 4: return pass_occupancy<4>();
+    case 5: return pass_occupancy<5>();
+    case 6: return pass_occupancy<6>();
+    case 7: return pass_occupancy<7>();
+    default: return pass_occupancy<8>();
+  }
 }
 
 static cudaError_t launch_pass_deg(int deg, const LsmPassArgs &a, int grid, cudaStream_t st) {
@@ -402,16 +483,18 @@ int lsm_american(hh_ctx *ctx, const hh_model *m, const hh_sim *s, const hh_payof
   const int64_t path_blocks = (N + kLsmThreads - 1) / kLsmThreads;
   const int grid_paths = (int)(path_blocks < (int64_t)ctx->sm_count * 8 ? path_blocks : (int64_t)ctx->sm_count * 8);
   const int64_t pass_blocks = ((ncols >> 1) + kLsmThreads - 1) / kLsmThreads;
-  int grid_pass = (int)(pass_blocks < (int64_t)ctx->sm_count * 8 ? pass_blocks : (int64_t)ctx->sm_count * 8);
+  const int64_t resident = (int64_t)ctx->sm_count * pass_occupancy_deg(degree);  // one wave: every block is resident
+  int grid_pass = (int)(pass_blocks < resident ? pass_blocks : resident);
   if (grid_pass < 1) grid_pass = 1;
   const int nacc = 3 * degree + 3;
   HH_CUDA(ctx, ctx->d_lsm_partials.ensure(sizeof(double) * (size_t)grid_pass * nacc));
-  // state: [moments (nacc)] [fits (M+1)]
-  const size_t fit_off = ((size_t)nacc * sizeof(double) + 255) & ~(size_t)255;
+  // state: [moments (nacc)] [done counter] [fits (M+1)]
+  const size_t done_off = ((size_t)nacc * sizeof(double) + 255) & ~(size_t)255;
+  const size_t fit_off = done_off + 256;
   HH_CUDA(ctx, ctx->d_lsm_state.ensure(fit_off + sizeof(LsmFit) * (size_t)(M + 1)));
   double *d_moments = ctx->d_lsm_state.as<double>();
   LsmFit *d_fits = reinterpret_cast<LsmFit *>(static_cast<char *>(ctx->d_lsm_state.ptr) + fit_off);
-  HH_CUDA(ctx, cudaMemsetAsync(d_fits, 0, sizeof(LsmFit) * (size_t)(M + 1), st));
+  HH_CUDA(ctx, cudaMemsetAsync(ctx->d_lsm_state.ptr, 0, fit_off + sizeof(LsmFit) * (size_t)(M + 1), st));
 
   HH_CUDA(ctx, cudaEventRecord(ctx->ev0, st));
   if (anti) lsm_paths_kernel<true><<<grid_paths, kLsmThreads, 0, st>>>(pa);
@@ -447,6 +530,8 @@ int lsm_american(hh_ctx *ctx, const hh_model *m, const hh_sim *s, const hh_payof
   a.cp = payoff->cp;
   a.ua = ua;
   a.ub = ub;
+  a.done = reinterpret_cast<unsigned int *>(static_cast<char *>(ctx->d_lsm_state.ptr) + done_off);
+  a.moments = d_moments;
   const double *G = ctx->d_grid.as<double>();
   // pass(t), t = M-1 .. 0: decision at t+1 (with fit[t+1]), one-step discount, moments of date t (t >= 1)
   for (int t = M - 1; t >= 0; --t) {
@@ -456,14 +541,13 @@ int lsm_american(hh_ctx *ctx, const hh_model *m, const hh_sim *s, const hh_payof
     a.t_next = t + 1;
     a.first = (t + 1 == M);
     a.last = (t == 0);
+    const bool exchange = t >= 1 && comm && comm->world > 1;
+    a.fit_out = (t >= 1 && !exchange) ? d_fits + t : nullptr;
+    a.reverse = (M - 1 - t) & 1;
     HH_CUDA(ctx, launch_pass_deg(degree, a, grid_pass, st));
-    lsm_reduce_kernel<<<1, 32, 0, st>>>(a.partials, grid_pass, nacc, d_moments);
-    HH_CUDA(ctx, cudaGetLastError());
-    if (t >= 1) {
-      if (comm && comm->world > 1) {
-        if (comm->allreduce_sum_f64(comm->user, d_moments, (size_t)nacc, (void *)st) != 0)
-          return ctx->fail(HH_ERR_COMM, "allreduce callback failed at date %d", t);
-      }
+    if (exchange) {
+      if (comm->allreduce_sum_f64(comm->user, d_moments, (size_t)nacc, (void *)st) != 0)
+        return ctx->fail(HH_ERR_COMM, "allreduce callback failed at date %d", t);
       lsm_fit_kernel<<<1, 32, 0, st>>>(d_moments, degree, d_fits + t);
       HH_CUDA(ctx, cudaGetLastError());
     }

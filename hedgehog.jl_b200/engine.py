@@ -207,6 +207,32 @@ class CudaEngine:
         return re + 1j * im
 
 
+    def bk_integral(self, model, tau: float, V0, VT, U, cfg: Optional[abi.hh_bk_config] = None):
+        """sample_from_cf for given (V0, VT, u) triples -> dict of arrays (x, mean, var, h, J, status, resid, evals)."""
+        V0 = np.ascontiguousarray(V0, dtype=np.float64)
+        VT = np.ascontiguousarray(VT, dtype=np.float64)
+        U = np.ascontiguousarray(U, dtype=np.float64)
+        out = np.empty((V0.shape[0], 8))
+        self._check(self.lib.hh_bk_integral(self.h, C.byref(model), float(tau), C.byref(cfg) if cfg is not None else None,
+                                            _dp(V0), _dp(VT), _dp(U), V0.shape[0], _dp(out)), "hh_bk_integral")
+        names = ("x", "mean", "var", "h", "J", "status", "resid", "evals")
+        return {k: out[:, i] for i, k in enumerate(names)}
+
+    def bk_variance(self, model, tau: float, V0, seed: int):
+        V0 = np.ascontiguousarray(V0, dtype=np.float64)
+        VT = np.empty_like(V0)
+        self._check(self.lib.hh_bk_variance(self.h, C.byref(model), float(tau), _dp(V0), V0.shape[0],
+                                            int(seed) & 0xFFFFFFFFFFFFFFFF, _dp(VT)), "hh_bk_variance")
+        return VT
+
+    def bk_last_stats(self) -> dict:
+        out = np.zeros(5)
+        self._check(self.lib.hh_bk_last_stats(self.h, _dp(out)), "hh_bk_last_stats")
+        n = max(out[3], 1.0)
+        return {"n_fallback": int(out[0]), "mean_series_terms": out[1] / n, "mean_cdf_evaluations": out[2] / n,
+                "transitions": int(out[3]), "n_unbracketed": int(out[4])}
+
+
 _default_engines: dict = {}
 
 

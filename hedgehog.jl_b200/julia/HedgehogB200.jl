@@ -1,0 +1,278 @@
+# HedgehogB200.jl — Julia host layer of libhedgehog_mc.so (B200 / sm_100a Monte Carlo pricing path).
+#
+# Adds methods to Hedgehog.solve for two new method types, `B200MonteCarlo` and `B200LSM`, that carry the same fields
+# as Hedgehog's `MonteCarlo` (src/pricing_methods/montecarlo.jl:127-131) and `LSM`
+# (src/pricing_methods/least_squares_montecarlo.jl:31-34) and return the same solution types
+# (`MonteCarloSolution`, `LSMSolution`, src/solutions/pricing_solutions.jl:22-27, 78-84). Nothing numerical happens in
+# Julia: scalars are extracted exactly as the reference extracts them and handed to the C ABI (include/hedgehog_mc.h)
+# through `ccall`. There is no CUDA.jl and no CPU fallback: without the library or a B200 every call throws.
+#
+# NOTE: this image has no Julia toolchain, so this file has not been executed here; hedgehog.jl_b200/api.py is the
+# line-for-line Python (ctypes) twin that the test-suite runs against the same ABI. See INTEGRATION.md.
+module HedgehogB200
+
+using Hedgehog
+using Hedgehog: PricingProblem, VanillaOption, European, American, Spot, AbstractPricingMethod, AbstractMarketInputs,
+                BlackScholesInputs, HestonInputs, PriceDynamics, LognormalDynamics, HestonDynamics, SimulationStrategy,
+                SimulationConfig, EulerMaruyama, BlackScholesExact, HestonBroadieKaya, NoVarianceReduction, Antithetic,
+                MonteCarlo, LSM, MonteCarloSolution, LSMSolution, GreekProblem, BatchGreekProblem, ForwardAD,
+                SpotLens, VolLens, ZeroRateSpineLens, yearfrac, add_yearfrac, zero_rate, df, get_vol
+using Libdl
+
+export B200MonteCarlo, B200LSM, b200_library!
+
+# ---- library handle -----------------------------------------------------------------------------------------------
+const LIB = Ref{String}(get(ENV, "HEDGEHOG_MC_LIB", joinpath(@__DIR__, "..", "libhedgehog_mc.so")))
+b200_library!(path::AbstractString) = (LIB[] = path)
+
+const HH_OK = Cint(0)
+const HH_ERR_ARG = Cint(-1)
+const HH_ERR_UNSUPPORTED = Cint(-2)
+const HH_MODEL_GBM, HH_MODEL_HESTON = Cint(0), Cint(1)
+const HH_SCHEME_EM, HH_SCHEME_EXACT_TERMINAL, HH_SCHEME_EXACT_STEPS, HH_SCHEME_HESTON_BK = Cint(0), Cint(1), Cint(2), Cint(3)
+const HH_FLAG_SPLIT_STEP, HH_FLAG_Q1_SQRT_MEAN = UInt32(1), UInt32(2)
+
+# ---- POD mirrors of include/hedgehog_mc.h (field order and types are the ABI) -----------------------------------------
+struct HHModel
+    kind::Int32; flags::UInt32
+    S0::Float64; r::Float64; T::Float64; sigma::Float64
+    V0::Float64; kappa::Float64; theta::Float64; xi::Float64; rho::Float64
+    m11::Float64; m12::Float64; m21::Float64; m22::Float64
+end
+struct HHBkConfig
+    n_std::Int32; maxiter_newton::Int32; maxiter_bisection::Int32; max_terms::Int32
+    h_fd::Float64; cf_tol::Float64; atol::Float64
+end
+HHBkConfig() = HHBkConfig(5, 10, 100, 4096, 1e-2, 1e-3, 1e-4)  # sample_from_cf.jl:27,50,75,110-112
+struct HHSim
+    n_paths::Int64; path_offset::Int64
+    n_steps::Int32; scheme::Int32; vr::Int32; precision::Int32; rng_mode::Int32; reserved::Int32
+    base_seed::UInt64
+    seeds::Ptr{UInt64}; normals::Ptr{Float64}
+    bk::HHBkConfig
+end
+struct HHPayoff
+    strike::Float64; cp::Float64
+end
+struct HHResult
+    sum::Float64; sumsq::Float64; n::Int64; price::Float64; std_error::Float64
+    n_nonfinite::Int64; n_fallback::Int64; kernel_ms::Float64
+end
+struct HHTangent
+    dS0::Float64; dr::Float64; dsigma::Float64; dV0::Float64; dkappa::Float64; dtheta::Float64; dxi::Float64
+    dm11::Float64; dm12::Float64; dm21::Float64; dm22::Float64; ddiscount::Float64
+end
+struct HHLsmResult
+    sum::Float64; sumsq::Float64; n::Int64; price::Float64; std_error::Float64
+    n_dates_skipped::Int64; kernel_ms::Float64; path_ms::Float64; regress_ms::Float64
+end
+
+# ---- context ---------------------------------------------------------------------------------------------------------
+mutable struct Context
+    h::Ptr{Cvoid}
+end
+const CTX = Dict{Int,Context}()
+
+function context(device::Integer = parse(Int, get(ENV, "LOCAL_RANK", "0")))
+    get!(CTX, device) do
+        h = Ref{Ptr{Cvoid}}(C_NULL)
+        rc = ccall((:hh_create, LIB[]), Cint, (Ref{Ptr{Cvoid}}, Cint), h, device)
+        rc == HH_OK || error("hh_create(device=$device) failed ($rc): " *
+                             unsafe_string(ccall((:hh_last_error, LIB[]), Cstring, (Ptr{Cvoid},), C_NULL)))
+        ctx = Context(h[])
+        finalizer(c -> ccall((:hh_destroy, LIB[]), Cint, (Ptr{Cvoid},), c.h), ctx)
+        ctx
+    end
+end
+
+function check(ctx::Context, rc::Cint, what)
+    rc == HH_OK && return
+    msg = unsafe_string(ccall((:hh_last_error, LIB[]), Cstring, (Ptr{Cvoid},), ctx.h))
+    rc == HH_ERR_ARG && throw(ArgumentError("$what: $msg"))           # mirrors montecarlo.jl:65-66
+    rc == HH_ERR_UNSUPPORTED && throw(MethodError(Hedgehog.solve, (what, msg)))
+    error("$what failed ($rc): $msg")
+end
+
+# ---- method types: same three fields as Hedgehog.MonteCarlo ------------------------------------------------------------
+struct B200MonteCarlo{P<:PriceDynamics,S<:SimulationStrategy,C<:SimulationConfig} <: AbstractPricingMethod
+    dynamics::P
+    strategy::S
+    config::C
+    ensemble::Bool      # materialise MonteCarloSolution.ensemble on the host (8 B per trajectory D2H)
+    base_seed::Union{Nothing,UInt64}  # one Philox key + trajectory index in the counter, instead of config.seeds per path
+end
+B200MonteCarlo(d, s, c; ensemble = true, base_seed = nothing) = B200MonteCarlo(d, s, c, ensemble, base_seed)
+B200MonteCarlo(m::MonteCarlo; kw...) = B200MonteCarlo(m.dynamics, m.strategy, m.config; kw...)
+
+struct B200LSM{M<:B200MonteCarlo} <: AbstractPricingMethod
+    mc_method::M
+    degree::Int
+end
+B200LSM(d::PriceDynamics, s::SimulationStrategy, c::SimulationConfig, degree::Int; kw...) =
+    B200LSM(B200MonteCarlo(d, s, c; kw...), degree)
+B200LSM(m::LSM; kw...) = B200LSM(B200MonteCarlo(m.mc_method; kw...), m.degree)
+
+# ---- scalar extraction, exactly as the reference does it -----------------------------------------------------------------
+function corr_factor(rho)  # Cholesky factor of [1 rho; rho 1] (any factor gives the same law, heston.jl:18-20)
+    (1.0, 0.0, rho, sqrt(1 - rho^2))
+end
+
+function hh_model(prob::PricingProblem, ::LognormalDynamics)
+    m = prob.market_inputs
+    T = yearfrac(m.referenceDate, prob.payoff.expiry)            # montecarlo.jl:147
+    r = zero_rate(m.rate, 0.0)                                    # :150
+    sigma = get_vol(m.sigma, nothing, nothing)                    # :151
+    HHModel(HH_MODEL_GBM, HH_FLAG_SPLIT_STEP | HH_FLAG_Q1_SQRT_MEAN, m.spot, r, T, sigma, 0, 0, 0, 0, 0, 1, 0, 0, 1)
+end
+
+function hh_model(prob::PricingProblem, ::HestonDynamics)
+    m = prob.market_inputs
+    T = yearfrac(m.referenceDate, prob.payoff.expiry)            # montecarlo.jl:197
+    r = zero_rate(m.rate, 0.0)                                    # :200
+    m11, m12, m21, m22 = corr_factor(m.ρ)
+    HHModel(HH_MODEL_HESTON, HH_FLAG_SPLIT_STEP, m.spot, r, T, 0.0, m.V0, m.κ, m.θ, m.σ, m.ρ, m11, m12, m21, m22)  # :201
+end
+
+scheme_of(::EulerMaruyama, for_lsm) = HH_SCHEME_EM
+scheme_of(::BlackScholesExact, for_lsm) = for_lsm ? HH_SCHEME_EXACT_STEPS : HH_SCHEME_EXACT_TERMINAL
+scheme_of(::HestonBroadieKaya, for_lsm) = HH_SCHEME_HESTON_BK
+vr_of(::NoVarianceReduction) = Cint(0)
+vr_of(::Antithetic) = Cint(1)
+
+# `f(sim)` runs with the seed vector pinned for the duration of the ccall
+function with_sim(f, method::B200MonteCarlo, scheme::Cint)
+    cfg = method.config
+    exact = scheme == HH_SCHEME_EXACT_TERMINAL || scheme == HH_SCHEME_HESTON_BK
+    steps = exact ? 1 : cfg.steps                                 # exact strategies ignore `steps` (montecarlo.jl:454-459)
+    seeds = Vector{UInt64}(cfg.seeds)
+    if method.base_seed !== nothing || exact
+        key = method.base_seed === nothing ? seeds[1] : method.base_seed   # Xoshiro(seeds[1]) :456 -> ONE stream
+        sim = HHSim(cfg.trajectories, 0, steps, scheme, vr_of(cfg.variance_reduction), 0, 0, 0, key, C_NULL, C_NULL, HHBkConfig())
+        return f(sim)
+    end
+    GC.@preserve seeds begin
+        sim = HHSim(cfg.trajectories, 0, steps, scheme, vr_of(cfg.variance_reduction), 0, 0, 0, 0,
+                    pointer(seeds), C_NULL, HHBkConfig())           # remake(prob; seed = seeds[i]) :331
+        f(sim)
+    end
+end
+
+# ---- solve: European Monte Carlo (montecarlo.jl:478-493) ---------------------------------------------------------------
+function Hedgehog.solve(prob::PricingProblem{VanillaOption{TS,TE,European,C,Spot},I},
+                        method::B200MonteCarlo) where {TS,TE,C,I<:AbstractMarketInputs}
+    ctx = context()
+    model = hh_model(prob, method.dynamics)
+    scheme = scheme_of(method.strategy, false)
+    payoff = HHPayoff(prob.payoff.strike, prob.payoff.call_put())
+    discount = df(prob.market_inputs.rate, prob.payoff.expiry)    # :489
+    N = method.config.trajectories
+    anti = method.config.variance_reduction isa Antithetic
+    terminal = method.ensemble ? Vector{Float64}(undef, anti ? 2N : N) : Float64[]
+    res = Ref(HHResult(0, 0, 0, 0, 0, 0, 0, 0))
+    with_sim(method, scheme) do sim
+        GC.@preserve terminal begin
+            rc = ccall((:hh_mc_european, LIB[]), Cint,
+                       (Ptr{Cvoid}, Ref{HHModel}, Ref{HHSim}, Ref{HHPayoff}, Cint, Cdouble, Ref{HHResult}, Ptr{Float64}, Csize_t),
+                       ctx.h, model, sim, payoff, 1, discount, res,
+                       method.ensemble ? pointer(terminal) : Ptr{Float64}(C_NULL), length(terminal))
+            check(ctx, rc, "hh_mc_european")
+        end
+    end
+    ensemble = anti ? (terminal[1:N], terminal[N+1:end]) : terminal   # final_sample :398-402
+    return MonteCarloSolution(prob, method, res[].price, ensemble)    # :492
+end
+
+# ---- solve: American LSM (least_squares_montecarlo.jl:99-136) ------------------------------------------------------------
+function Hedgehog.solve(prob::PricingProblem{VanillaOption{TS,TE,American,C,S},I},
+                        method::B200LSM) where {TS,TE,C,S,I<:AbstractMarketInputs}
+    ctx = context()
+    mc = method.mc_method
+    model = hh_model(prob, mc.dynamics)
+    scheme = scheme_of(mc.strategy, true)
+    payoff = HHPayoff(prob.payoff.strike, prob.payoff.call_put())
+    m = prob.market_inputs
+    T = yearfrac(m.referenceDate, prob.payoff.expiry)                       # :104
+    nsteps = mc.config.steps
+    step_discount = df(m.rate, add_yearfrac(m.referenceDate, T / nsteps))   # :110
+    ncols = mc.config.trajectories * (mc.config.variance_reduction isa Antithetic ? 2 : 1)
+    stop_idx = Vector{Int32}(undef, ncols)
+    stop_val = Vector{Float64}(undef, ncols)
+    spot = Matrix{Float64}(undef, nsteps + 1, ncols)                        # column = trajectory, :50
+    out = Ref(HHLsmResult(0, 0, 0, 0, 0, 0, 0, 0, 0))
+    with_sim(mc, scheme) do sim
+        GC.@preserve stop_idx stop_val spot begin
+            rc = ccall((:hh_lsm_american, LIB[]), Cint,
+                       (Ptr{Cvoid}, Ref{HHModel}, Ref{HHSim}, Ref{HHPayoff}, Cint, Cdouble, Ptr{Cvoid}, Ref{HHLsmResult},
+                        Ptr{Int32}, Ptr{Float64}, Ptr{Float64}),
+                       ctx.h, model, sim, payoff, method.degree, step_discount, C_NULL, out,
+                       pointer(stop_idx), pointer(stop_val), pointer(spot))
+            check(ctx, rc, "hh_lsm_american")
+        end
+    end
+    stopping_info = [(Int(stop_idx[p]), stop_val[p]) for p in 1:ncols]      # :112, :163-164
+    return LSMSolution(prob, method, out[].price, stopping_info, spot)       # :135
+end
+
+# ---- Greeks: every ForwardAD lens is one tangent direction of the SAME simulation (greeks_problem.jl:249-262, 559-568) ---
+function tangent_of(prob::PricingProblem, lens)
+    m = prob.market_inputs
+    z = zeros(12)
+    if lens isa SpotLens
+        z[1] = 1.0
+    elseif lens isa ZeroRateSpineLens      # the rate moves the drift AND the discount factor
+        z[2] = 1.0
+        z[12] = -yearfrac(m.rate.reference_date, prob.payoff.expiry) * df(m.rate, prob.payoff.expiry)
+    elseif lens isa VolLens
+        z[3] = 1.0
+    else
+        name = string(lens)                # Accessors optics: (@optic _.market_inputs.κ) etc.
+        if occursin("V0", name); z[4] = 1.0
+        elseif occursin("κ", name); z[5] = 1.0
+        elseif occursin("θ", name); z[6] = 1.0
+        elseif occursin("σ", name); z[7] = 1.0
+        elseif occursin("ρ", name)          # d(Cholesky factor)/d rho
+            z[10] = 1.0; z[11] = -m.ρ / sqrt(1 - m.ρ^2)
+        elseif occursin("spot", name); z[1] = 1.0
+        else
+            throw(ArgumentError("no tangent rule for lens $lens"))
+        end
+    end
+    HHTangent(z...)
+end
+
+function forward_ad(prob::PricingProblem, lenses, method::B200MonteCarlo)
+    ctx = context()
+    model = hh_model(prob, method.dynamics)
+    scheme = scheme_of(method.strategy, false)
+    payoff = HHPayoff(prob.payoff.strike, prob.payoff.call_put())
+    discount = df(prob.market_inputs.rate, prob.payoff.expiry)
+    greeks = Vector{Float64}(undef, length(lenses))
+    for chunk in Iterators.partition(eachindex(lenses), 8)            # up to 8 directions per launch
+        tans = [tangent_of(prob, lenses[i]) for i in chunk]
+        res = Ref(HHResult(0, 0, 0, 0, 0, 0, 0, 0))
+        out = Vector{Float64}(undef, length(tans))
+        with_sim(method, scheme) do sim
+            GC.@preserve tans out begin
+                rc = ccall((:hh_mc_european_tangent, LIB[]), Cint,
+                           (Ptr{Cvoid}, Ref{HHModel}, Ptr{HHTangent}, Cint, Ref{HHSim}, Ref{HHPayoff}, Cint, Cdouble,
+                            Ref{HHResult}, Ptr{Float64}, Ptr{Float64}),
+                           ctx.h, model, pointer(tans), length(tans), sim, payoff, 1, discount, res, pointer(out), C_NULL)
+                check(ctx, rc, "hh_mc_european_tangent")
+            end
+        end
+        greeks[collect(chunk)] .= out
+    end
+    greeks
+end
+
+Hedgehog.solve(gprob::GreekProblem, ::ForwardAD, method::B200MonteCarlo) =
+    Hedgehog.GreekResult(forward_ad(gprob.pricing_problem, [gprob.wrt], method)[1])
+
+function Hedgehog.solve(gprob::BatchGreekProblem, ::ForwardAD, method::B200MonteCarlo)
+    g = forward_ad(gprob.pricing_problem, collect(gprob.lenses), method)
+    Dict(lens => g[i] for (i, lens) in enumerate(gprob.lenses))      # greeks_problem.jl:559-568
+end
+# FiniteDifference Greeks need no method here: Hedgehog's generic code re-solves with bumped inputs
+# (greeks_problem.jl:279-329), and the deterministic Philox stream gives it common random numbers.
+
+end # module

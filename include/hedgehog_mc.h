@@ -216,6 +216,18 @@ int hh_bk_chf(hh_ctx *ctx, const hh_model *model, double tau, const double *V0, 
 /* log I_nu(z) for complex z, real order nu > -1 (SpecialFunctions.besseli, heston.jl:173,207). */
 int hh_bk_log_besseli(hh_ctx *ctx, double nu, const double *z_re, const double *z_im, int n,
                       double *out_re, double *out_im);
+/* sample_from_cf (sample_from_cf.jl:27-41) for n independent (V0, VT, u) triples, u = the uniform the reference draws
+ * at :29. out8[i] = {x = sampled integral of V, mean, variance (moments_from_cf :50-64), h (:37), J = number of series
+ * terms (:84-93), status (0 root inside [0, max_guess], 1 secant accepted without a bracket, 2 fell back to max_guess),
+ * F(x) - u, number of CDF evaluations}. cfg NULL = reference defaults. */
+int hh_bk_integral(hh_ctx *ctx, const hh_model *model, double tau, const hh_bk_config *cfg, const double *V0,
+                   const double *VT, const double *u, int n, double *out8);
+/* sample_V_T (heston.jl:125-133): VT[i] = c * NoncentralChisq(d, lambda(V0[i])), one draw per i from Philox key `seed`. */
+int hh_bk_variance(hh_ctx *ctx, const hh_model *model, double tau, const double *V0, int n, uint64_t seed,
+                   double *VT);
+/* Statistics of the last Broadie-Kaya run on this context: out5 = {inversions that fell back to max_guess,
+ * sum of series lengths J, sum of CDF evaluations, transitions, inversions accepted without a bracket}. */
+int hh_bk_last_stats(hh_ctx *ctx, double *out5);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,170 @@
+"""GPU parity tests for the Broadie-Kaya exact Heston sampler (heston.jl:125-300, sample_from_cf.jl) through the C ABI.
+
+Protocol: the deterministic pieces — log I_nu(z), the characteristic function of the integrated variance,
+the finite-difference moments, the Fourier-series CDF — are compared with the scipy/AMOS oracle (oracle/bk_ref.py) at
+tight tolerance; the inversion must return a root that the reference's own acceptance test (|F(x) - u| <= 1e-4,
+sample_from_cf.jl:110,119) accepts; the samplers are checked in distribution (KS against scipy's noncentral chi-square)
+and the prices within 3 standard errors of Carr-Madan (the reference's own agreement tests, montecarlo_heston.jl:151-253)."""
+import datetime as dt
+import math
+
+import numpy as np
+import pytest
+from scipy import stats
+from scipy.special import ive
+
+import hedgehog_jl_b200 as hh
+from hedgehog_jl_b200 import _abi as abi
+from hedgehog_jl_b200.engine import SimSpec
+from helpers import heston_model
+from oracle import anchors as A
+from oracle import bk_ref as B
+
+pytestmark = pytest.mark.gpu
+
+C2 = dict(kappa=2.0, theta=0.04, xi=0.3, rho=-0.7, V0=0.04, r=0.03)
+Q8 = dict(kappa=0.04, theta=0.3, xi=-0.6, rho=0.04, V0=1.5, r=0.05)       # montecarlo_heston.jl:161-170 (Q8)
+BK1 = dict(kappa=6.21, theta=0.019, xi=0.61, rho=-0.7, V0=0.010201, r=0.0319)  # Broadie-Kaya (2006) case 1
+
+
+@pytest.mark.parametrize("nu", [-0.933, -0.5, -0.366, 0.0, 0.778, 2.5, 12.0])
+def test_log_besseli_matches_amos(cuda, nu):
+    rng = np.random.default_rng(3)
+    r = np.concatenate([rng.uniform(1e-3, 6, 3000), rng.uniform(4, 40, 3000), rng.uniform(30, 2000, 2000)])
+    th = rng.uniform(-np.pi, np.pi, r.size)
+    th[::50] = 0.0  # the real axis (z_kappa)
+    z = r * np.exp(1j * th)
+    z = z[np.abs(np.abs(th) - np.pi / 2) > 0.02]  # I_nu has its zeros on the imaginary axis: ill-conditioned there
+    got = cuda.bk_log_besseli(nu, z)
+    ref = np.log(ive(nu, z)) + np.abs(z.real)
+    assert np.max(np.abs(np.exp(got - ref) - 1.0)) < 2e-12
+
+
+@pytest.mark.parametrize("pars,tau", [(C2, 1.0), (C2, 1 / 12), (Q8, 364 / 365), (BK1, 1.0), (BK1, 0.25)])
+def test_characteristic_function_matches_oracle(cuda, pars, tau):
+    m = heston_model(S0=100.0, T=tau, **pars)
+    rng = np.random.default_rng(5)
+    n, na = 24, 120
+    V0 = pars["V0"] * rng.uniform(0.3, 2.0, n)
+    VT = pars["V0"] * rng.uniform(0.1, 3.0, n)
+    a = np.empty((n, na))
+    ref = np.empty((n, na), dtype=complex)
+    for i in range(n):
+        cf = B.HestonCF(pars["kappa"], pars["theta"], pars["xi"], V0[i], VT[i], tau)
+        mean, var = B.moments_from_cf(cf)
+        h = math.pi / (mean + 5 * math.sqrt(max(var, 1e-12)))
+        a[i] = h * np.arange(1, na + 1)
+        th = math.nan
+        for j in range(na):
+            ref[i, j], th = cf.evaluate(a[i, j], th)
+    got = cuda.bk_chf(m, tau, V0, VT, a)
+    assert np.max(np.abs(got - ref)) < 1e-12  # |phi| <= 1: absolute == relative to the series' scale
+
+
+@pytest.mark.parametrize("pars,tau", [(C2, 1.0), (C2, 1 / 12), (Q8, 364 / 365), (BK1, 1.0)])
+def test_integral_inversion_against_reference_algorithm(cuda, pars, tau):
+    m = heston_model(S0=100.0, T=tau, **pars)
+    rng = np.random.default_rng(11)
+    n = 96
+    d, lam_s, c = B.vt_params(pars["kappa"], pars["theta"], pars["xi"], 1.0, tau)
+    V0 = pars["V0"] * rng.uniform(0.5, 1.5, n)
+    VT = np.array([c * stats.ncx2.rvs(d, lam_s * v, random_state=rng) for v in V0])
+    U = rng.uniform(0.001, 0.999, n)
+    U[:4] = [1e-9, 0.5, 0.999999, 0.9999999999]
+    g = cuda.bk_integral(m, tau, V0, VT, U)
+    for i in range(n):
+        cf = B.HestonCF(pars["kappa"], pars["theta"], pars["xi"], V0[i], VT[i], tau)
+        o = B.sample_integral_V(cf, U[i])
+        # moments_from_cf differences Phi at +-1e-2: the SECOND difference cancels to ~1e-16 / h0^2 = 1e-12 absolute per
+        # rounding, so the reference's own variance (and the h derived from it) is only defined to about that noise
+        assert g["mean"][i] == pytest.approx(o["mean"], rel=1e-7)
+        assert g["var"][i] == pytest.approx(o["var"], rel=1e-6, abs=5e-10)
+        assert g["h"][i] == pytest.approx(o["h"], rel=5e-3)
+        assert abs(int(g["J"][i]) - o["J"]) <= 1
+        # with IDENTICAL h the series (truncation rule included) and its CDF must agree tightly
+        hg = g["h"][i]
+        phis = B.cf_series(cf, hg)
+        assert int(g["J"][i]) == len(phis)
+        F_same_h = lambda x: B.cdf_from_series(phis, x, hg)
+        if g["status"][i] == 2:  # fell back to max_guess (u ~ 1: the truncated series never reaches u), like the reference
+            assert F_same_h(g["x"][i]) < U[i]
+            assert g["x"][i] == pytest.approx(o["max_guess"], rel=1e-3)
+            continue
+        assert g["x"][i] >= 0.0
+        assert abs(F_same_h(g["x"][i]) - U[i]) <= 1e-10
+        assert abs(g["resid"][i]) <= 1e-12
+        # the GPU root passes the reference's acceptance test (sample_from_cf.jl:119) on the oracle's own CDF (own h)
+        assert abs(o["cdf"](g["x"][i]) - U[i]) <= 1e-4
+        if o["status"] != 2:
+            dx = g["x"][i] * 1e-3 + 1e-9
+            slope = max((o["cdf"](g["x"][i] + dx) - o["cdf"](g["x"][i])) / dx, 1e-12)
+            assert abs(g["x"][i] - o["x"]) <= 2.5e-4 / slope + 1e-12  # both within atol of the same root
+
+
+@pytest.mark.parametrize("pars,tau,v0", [(C2, 1.0, 0.04), (C2, 1 / 252, 0.09), (Q8, 364 / 365, 1.5), (BK1, 1.0, 0.010201),
+                                         (dict(C2, xi=0.05), 1 / 12, 0.04)])
+def test_variance_sampler_is_noncentral_chisquare(cuda, pars, tau, v0):
+    """d > 1 (chi2 + shifted normal), d < 1 (Poisson mixture, small and large means) against scipy's ncx2 law."""
+    m = heston_model(S0=100.0, T=tau, **pars)
+    n = 200_000
+    VT = cuda.bk_variance(m, tau, np.full(n, v0), seed=123)
+    d, lam, c = B.vt_params(pars["kappa"], pars["theta"], pars["xi"], v0, tau)
+    assert np.all(VT >= 0) and np.all(np.isfinite(VT))
+    ks = stats.kstest(VT / c, stats.ncx2(d, lam).cdf)
+    assert ks.pvalue > 1e-3, ks
+    assert VT.mean() == pytest.approx(c * (d + lam), rel=5 * math.sqrt(2 * (d + 2 * lam)) / (d + lam) / math.sqrt(n) + 1e-9)
+
+
+def _bk_problem(pars, T_days, n, steps=1, strike=100.0, seed=2024):
+    ref = dt.date(2020, 1, 1)
+    prob = hh.PricingProblem(hh.VanillaOption(strike, ref + dt.timedelta(days=T_days), hh.European(), hh.Call(), hh.Spot()),
+                             hh.HestonInputs(ref, pars["r"], 100.0, pars["V0"], pars["kappa"], pars["theta"], pars["xi"], pars["rho"]))
+    mc = hh.MonteCarlo(hh.HestonDynamics(), hh.HestonBroadieKaya(), hh.SimulationConfig(n, steps=steps, base_seed=seed),
+                       bk_steps_from_config=steps > 1)
+    return prob, mc
+
+
+@pytest.mark.parametrize("pars,days,tol", [(C2, 365, 2e-2), (Q8, 364, 5e-2), (BK1, 365, 2e-2)])
+def test_bk_price_vs_carr_madan(cuda, pars, days, tol):
+    """montecarlo_heston.jl:151-253: BK exact (NoVarianceReduction) vs Carr-Madan(1, 32), rtol 2e-2 / 5e-2 — and, being
+    an exact scheme, within 3 standard errors (+ the 1e-4 Carr-Madan truncation)."""
+    n = 400_000
+    prob, mc = _bk_problem(pars, days, n)
+    sol = hh.solve(prob, mc, engine=cuda)
+    T = days / 365
+    cm = A.heston_price(100.0, 100.0, pars["r"], T, pars["V0"], pars["kappa"], pars["theta"], pars["xi"], pars["rho"], bound=200.0)
+    assert sol.price == pytest.approx(cm, rel=tol)
+    assert abs(sol.price - cm) < 3.5 * sol.std_error + 2e-4 * cm, (sol.price, cm, sol.std_error)
+    assert sol.stats["n_nonfinite"] == 0
+    assert sol.stats["n_fallback"] <= 1e-4 * n
+    assert len(sol.ensemble) == n and np.all(sol.ensemble > 0)
+
+
+def test_bk_multi_date_is_consistent_with_one_transition(cuda):
+    """Config C4: 12 exact transitions compose to the same law as one (heston.jl:82-91 restarts from (S, V) each date)."""
+    n = 300_000
+    p1, m1 = _bk_problem(C2, 365, n, steps=1, seed=5)
+    p12, m12 = _bk_problem(C2, 365, n, steps=12, seed=6)
+    s1 = hh.solve(p1, m1, engine=cuda)
+    s12 = hh.solve(p12, m12, engine=cuda)
+    cm = A.heston_price(100.0, 100.0, 0.03, 1.0, 0.04, 2.0, 0.04, 0.3, -0.7, bound=200.0)
+    for s in (s1, s12):
+        assert abs(s.price - cm) < 3.5 * s.std_error + 2e-4 * cm, (s.price, cm, s.std_error)
+    assert stats.ks_2samp(s1.ensemble[:100_000], s12.ensemble[:100_000]).pvalue > 1e-3
+    st = cuda.bk_last_stats()
+    assert st["transitions"] == 12 * n and 3 < st["mean_series_terms"] < 500
+
+
+def test_bk_errors_and_shards(cuda):
+    m = heston_model()
+    with pytest.raises(NotImplementedError):  # Q5: Antithetic + BK is a MethodError in the reference
+        cuda.mc_european(m, SimSpec(n_paths=10, n_steps=1, scheme=abi.HH_SCHEME_HESTON_BK, vr=abi.HH_VR_ANTITHETIC), [(100.0, 1.0)], 1.0)
+    # shard invariance: the stream is keyed by the global trajectory index
+    sim = SimSpec(n_paths=4000, n_steps=2, scheme=abi.HH_SCHEME_HESTON_BK, base_seed=9)
+    _, full = cuda.mc_european(m, sim, [(100.0, 1.0)], 1.0, want_terminal=True)
+    parts = []
+    for g in range(4):
+        _, t = cuda.mc_european(m, SimSpec(n_paths=1000, path_offset=1000 * g, n_steps=2, scheme=abi.HH_SCHEME_HESTON_BK, base_seed=9),
+                                [(100.0, 1.0)], 1.0, want_terminal=True)
+        parts.append(t)
+    assert np.array_equal(np.concatenate(parts), full)
