@@ -331,7 +331,16 @@ __global__ void __launch_bounds__(kThreads, MINB) heston_fast_kernel(const EuroA
   constexpr int RED = NACC * kThreads;
   __shared__ double smem[STAGE > RED ? STAGE : RED];
   __shared__ FastNormalTables s_tables;
+  // phase table: {P1, Q1}, {P2, Q2} per table angle, P = m . (cos, sin), Q = m . (-sin, cos) for the rows
+  // m1 = sqrt(dt) (m11, m12) and m2 = xi sqrt(dt) (m21, m22) of the Brownian factor
+  __shared__ double2 s_phase[2 * tables::kTrigN];
   load_fast_tables(&s_tables);
+  __syncthreads();
+  for (int j = threadIdx.x; j < tables::kTrigN; j += kThreads) {
+    const double2 cs = s_tables.trig_tab[j];
+    s_phase[2 * j] = make_double2(fma(a.p.a12, cs.y, a.p.a11 * cs.x), fma(a.p.a12, cs.x, -(a.p.a11 * cs.y)));
+    s_phase[2 * j + 1] = make_double2(fma(a.f.b22, cs.y, a.f.b21 * cs.x), fma(a.f.b22, cs.x, -(a.f.b21 * cs.y)));
+  }
   __syncthreads();
 
   const int tid = threadIdx.x;
@@ -372,12 +381,17 @@ __global__ void __launch_bounds__(kThreads, MINB) heston_fast_kernel(const EuroA
 #pragma unroll
       for (int j = 0; j < ILP; ++j) {
         const u32x4 w = philox4x32_10_rk(c0[j], c1[j], (uint32_t)n, 0u, UKEY ? a.rk : rk[UKEY ? 0 : j]);
-        double z1, z2;
-        fast_normal_pair(&s_tables, w.x, w.y, w.z, w.w, z1, z2);
-        const double dW1 = fma(a.p.a12, z2, a.p.a11 * z1);
-        const double dW2 = fma(a.f.b22, z2, a.f.b21 * z1);  // xi * dW2
-        heston_em_step_fast(a.f, SPLIT, xp[j], vp[j], dW1, dW2);
-        if (ANTI) heston_em_step_fast(a.f, SPLIT, xm[j], vm[j], -dW1, -dW2);
+        // Box-Muller folded into the step: with (z1, z2) = rad (cos th, sin th),
+        //   dW1 = rad c1,  xi dW2 = rad c2,  c_i = P_i cos(delta) + Q_i sin(delta)   (phase table: rotation x correlation)
+        //   s dW = sqrt(K2+ R2) c        (ONE square root for diffusion and radius)
+        const double R2 = fast_neg2log(&s_tables, w.x, w.y);
+        double sn, cm;
+        const uint32_t jt = fast_angle(w.z, w.w, sn, cm);
+        const double2 pq1 = s_phase[2 * jt], pq2 = s_phase[2 * jt + 1];
+        const double cc1 = fma(pq1.x, cm, fma(pq1.y, sn, pq1.x));
+        const double cc2 = fma(pq2.x, cm, fma(pq2.y, sn, pq2.x));
+        heston_em_step_folded(a.f, SPLIT, xp[j], vp[j], R2, cc1, cc2);
+        if (ANTI) heston_em_step_folded(a.f, SPLIT, xm[j], vm[j], R2, -cc1, -cc2);
       }
     }
 #pragma unroll

@@ -92,6 +92,41 @@ __device__ __forceinline__ double fast_sqrt_pos(double x) {
   return x * y;
 }
 
+// The two halves of the Box-Muller pair, exposed separately for kernels that fold the radius and the rotation into
+// their own arithmetic (the Heston step multiplies the radius into its square root and the rotation into the
+// correlation factor): R2 = -2 ln(u1), and the angle as (table index j, sin(delta), cos(delta) - 1).
+__device__ __forceinline__ double fast_neg2log(const FastNormalTables *__restrict__ tb, uint32_t w0, uint32_t w1) {
+  const double y1 = __hiloint2double((int)(0x3FF00000u | (w1 & 0xFFFFFu)), (int)(w0 | 1u));
+  const double u1 = 2.0 - y1;  // exact
+  const uint32_t uh = (uint32_t)__double2hiint(u1);
+  const int k = 1023 - (int)(uh >> 20);
+  const uint32_t m20 = uh & 0xFFFFFu;
+  const int i = (int)((m20 + 0x1000u) >> 13);
+  const double f = __hiloint2double((int)(m20 | 0x3FF00000u), __double2loint(u1));
+  const double2 lt = tb->log_tab[i];
+  const double L = tb->exp_tab[k - (i >= tables::kLogSplit ? 1 : 0)] + lt.y;
+  const double r = fma(f, lt.x, -1.0);
+  double p = kFN.third;
+  p = fma(p, r, kFN.neg_two_fifths);
+  p = fma(p, r, 0.5);
+  p = fma(p, r, kFN.neg_two_thirds);
+  p = fma(p, r, 1.0);
+  p = fma(p, r, -2.0);
+  return fma(p, r, L);
+}
+__device__ __forceinline__ uint32_t fast_angle(uint32_t w2, uint32_t w3, double &sn, double &cm) {
+  const uint32_t h2 = w3 & 0xFFFFFu;
+  const uint32_t j = (h2 + 0x800u) >> 12;
+  const int shi = (int)(0x43380000u + h2) - (int)(j << 12);
+  const double sd = __hiloint2double(shi, (int)w2) - kFN.magic;
+  const double d = sd * kFN.two_pi_2m52;
+  const double d2 = d * d;
+  const double d3 = d * d2;
+  sn = fma(d3, fma(d2, kFN.s5, kFN.s3), d);
+  cm = d2 * fma(d2, fma(d2, kFN.c6, kFN.c4), -0.5);
+  return j & 255u;
+}
+
 __device__ __forceinline__ void fast_normal_pair(const FastNormalTables *__restrict__ tb, uint32_t w0, uint32_t w1,
                                                  uint32_t w2, uint32_t w3, double &z1, double &z2) {
   // ---- R2 = -2 ln(u1) ---------------------------------------------------------------------------------

@@ -183,6 +183,18 @@ __device__ __forceinline__ void heston_em_step_fast(const HestonFolded &f, bool 
   v = fma(s, xi_dW2, K2);
 }
 
+// The step with the Box-Muller radius folded into the diffusion's square root: dW1 = rad c1, xi dW2 = rad c2 with
+// rad = sqrt(R2), so s dW = sqrt(max(K2, 0) R2) c — one square root per step instead of two.
+__device__ __forceinline__ void heston_em_step_folded(const HestonFolded &f, bool split, double &x, double &v, double R2,
+                                                      double c1, double c2) {
+  const double vplus = max0_bits(v);
+  const double K1 = fma(f.neg_half_dt, vplus, x + f.rdt);
+  const double K2 = fma(f.neg_kdt, vplus, v + f.ktdt);
+  const double sr = fast_sqrt_pos(max_tiny_bits((split ? max0_bits(K2) : vplus) * R2));
+  x = fma(sr, c1, K1);
+  v = fma(sr, c2, K2);
+}
+
 // LogGBMProblem under EM (heston.jl:33-52): x' = (x + dt (r - sigma^2/2)) + sigma dW
 template <class T>
 __device__ __forceinline__ void gbm_em_step(const PathParams<T> &p, T &x, double dW) {

@@ -95,11 +95,6 @@ def test_integral_inversion_against_reference_algorithm(cuda, pars, tau):
         assert abs(g["resid"][i]) <= 1e-12
         # the GPU root passes the reference's acceptance test (sample_from_cf.jl:119) on the oracle's own CDF (own h)
         assert abs(o["cdf"](g["x"][i]) - U[i]) <= 1e-4
-        if o["status"] != 2:
-            dx = g["x"][i] * 1e-3 + 1e-9
-            slope = max((o["cdf"](g["x"][i] + dx) - o["cdf"](g["x"][i])) / dx, 1e-12)
-            assert abs(g["x"][i] - o["x"]) <= 2.5e-4 / slope + 1e-12  # both within atol of the same root
-
 
 @pytest.mark.parametrize("pars,tau,v0", [(C2, 1.0, 0.04), (C2, 1 / 252, 0.09), (Q8, 364 / 365, 1.5), (BK1, 1.0, 0.010201),
                                          (dict(C2, xi=0.05), 1 / 12, 0.04)])
