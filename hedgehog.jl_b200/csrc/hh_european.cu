@@ -46,6 +46,9 @@ struct EuroArgs {
   PathParams<double> p;
   HestonFolded f;
   PhiloxRoundKeys rk;  // round keys of base_seed (uniform across threads when seeds == NULL)
+  // bit patterns handed over as ARGUMENTS so that (x & mask) | pattern stays one LOP3 with a uniform-register operand
+  // (as literals the compiler splits it into an AND-immediate and an OR-immediate)
+  uint32_t one_hi, magic_hi;  // 0x3FF00000 (high word of 1.0), 0x43300000 (high word of 2^52)
 };
 
 // number of accumulators per (block, payoff): sum, sumsq, nonfinite, then per tangent: dsum, dsumsq
@@ -442,6 +445,152 @@ __global__ void __launch_bounds__(kThreads, MINB) heston_fast_kernel(const EuroA
   }
 }
 
+// ---- v2 of the headline kernel: lane-replicated tables in dynamic shared memory ---------------------------------
+// Same trajectory arithmetic as heston_fast_kernel up to rounding (the drift r dt is added once at expiry, the clamps
+// use one integer max each), but every table read of the step loop is bank-conflict free (hh_fastnormal.cuh, "v2").
+// Dynamic shared memory: [payoff staging / reduction | log table x8 | phase table x8 | exponent table].
+__host__ __device__ constexpr int fast2_stage_bytes(int threads) { return 3 * threads * 8; }
+__host__ __device__ constexpr int fast2_smem_bytes(int threads) { return fast2_stage_bytes(threads) + kLogRepBytes + kPhaseRepBytes + kExp2Bytes; }
+
+template <bool ANTI, bool SPLIT, bool UKEY, int ILP, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) heston_fast2_kernel(const EuroArgs a) {
+  constexpr int NACC = 3;
+  constexpr int kThreads = THREADS;  // shadows the file-scope block size
+  constexpr int kFast2StageBytes = fast2_stage_bytes(THREADS);
+  extern __shared__ __align__(16) unsigned char dsm[];
+  double *smem = reinterpret_cast<double *>(dsm);
+  char *s_log = reinterpret_cast<char *>(dsm) + kFast2StageBytes;
+  char *s_phase = s_log + kLogRepBytes;
+  double *s_exp = reinterpret_cast<double *>(s_phase + kPhaseRepBytes);
+  const int tid = threadIdx.x;
+  for (int e = tid; e < tables::kLog2Buckets * kRep; e += kThreads)
+    reinterpret_cast<double2 *>(s_log)[e] = g_fast_tables2.log_tab[e / kRep];
+  for (int e = tid; e < tables::kTrigN * kRep; e += kThreads) {
+    // phase table: {P1, Q1}, {P2, Q2} per table angle, P = m . (cos, sin), Q = m . (-sin, cos) for the rows
+    // m1 = sqrt(dt) (m11, m12) and m2 = xi sqrt(dt) (m21, m22) of the Brownian factor
+    const int j = e / kRep, q = e % kRep;
+    const double2 cs = g_fast_tables2.trig_tab[j];
+    double2 *dst = reinterpret_cast<double2 *>(s_phase) + (size_t)j * 2 * kRep + q;
+    dst[0] = make_double2(fma(a.p.a12, cs.y, a.p.a11 * cs.x), fma(a.p.a12, cs.x, -(a.p.a11 * cs.y)));
+    dst[kRep] = make_double2(fma(a.f.b22, cs.y, a.f.b21 * cs.x), fma(a.f.b22, cs.x, -(a.f.b21 * cs.y)));
+  }
+  for (int e = tid; e < tables::kExp2N; e += kThreads) s_exp[e] = g_fast_tables2.exp_tab[e];
+  __syncthreads();
+  const char *log_lane = s_log + (tid & (kRep - 1)) * 16;
+  const char *phase_lane = s_phase + (tid & (kRep - 1)) * 16;
+  const char *exp_biased = reinterpret_cast<const char *>(s_exp) - tables::kExp2Bias * 8;
+
+  const int KP = 1 << a.kp_log2;
+  const int k = tid & (KP - 1);
+  const int g = tid >> a.kp_log2;
+  const int G = kThreads >> a.kp_log2;
+  double strike = 0.0, cp = 0.0;
+  if (k < a.npay) {
+    strike = a.payoffs[k].strike;
+    cp = a.payoffs[k].cp;
+  }
+  double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0;
+  const int M = a.n_steps;
+  const double drift_total = (double)M * a.f.rdt;
+  constexpr int64_t kBatch = (int64_t)kThreads * ILP;
+
+  for (int64_t base = (int64_t)blockIdx.x * kBatch; base < a.n; base += (int64_t)gridDim.x * kBatch) {
+    double xp[ILP], vp[ILP], xm[ILP], vm[ILP];
+    uint32_t c0[ILP], c1[ILP];
+    PhiloxRoundKeys rk[UKEY ? 1 : ILP];
+#pragma unroll
+    for (int j = 0; j < ILP; ++j) {
+      const int64_t i = base + (int64_t)j * kThreads + tid;
+      const int64_t ic = i < a.n ? i : a.n - 1;  // tail lanes repeat the last trajectory; never accumulated
+      xp[j] = xm[j] = a.p.x0;
+      vp[j] = vm[j] = a.p.v0;
+      if (UKEY) {
+        const uint64_t idx = (uint64_t)(a.path_offset + ic);
+        c0[j] = (uint32_t)idx;
+        c1[j] = (uint32_t)(idx >> 32);
+      } else {
+        c0[j] = c1[j] = 0u;
+        rk[UKEY ? 0 : j] = philox_round_keys(a.seeds[ic]);
+      }
+    }
+#pragma unroll 1
+    for (int n = 0; n < M; ++n) {
+#pragma unroll
+      for (int j = 0; j < ILP; ++j) {
+        const u32x4 w = philox4x32_10_rk(c0[j], c1[j], (uint32_t)n, 0u, UKEY ? a.rk : rk[UKEY ? 0 : j]);
+        const double R2 = fast_neg2log_v2(log_lane, exp_biased, w.x, w.y, a.one_hi);
+        double sn, cs;
+        const uint32_t poff = fast_angle_v2(w.z, w.w, a.magic_hi, sn, cs);
+        const double2 pq1 = *reinterpret_cast<const double2 *>(phase_lane + poff);
+        const double2 pq2 = *reinterpret_cast<const double2 *>(phase_lane + poff + kRep * 16);
+        const double cc1 = fma(pq1.x, cs, pq1.y * sn);
+        const double cc2 = fma(pq2.x, cs, pq2.y * sn);
+        {
+          const double vplus = max0_hi(vp[j]);
+          const double K1 = fma(a.f.neg_half_dt, vplus, xp[j]);
+          const double K2 = fma(a.f.neg_kdt, vplus, vp[j] + a.f.ktdt);
+          const double sr = fast_sqrt_pos5(max_tiny_hi((SPLIT ? K2 : vplus) * R2));
+          xp[j] = fma(sr, cc1, K1);
+          vp[j] = fma(sr, cc2, K2);
+        }
+        if (ANTI) {
+          const double vplus = max0_hi(vm[j]);
+          const double K1 = fma(a.f.neg_half_dt, vplus, xm[j]);
+          const double K2 = fma(a.f.neg_kdt, vplus, vm[j] + a.f.ktdt);
+          const double sr = fast_sqrt_pos5(max_tiny_hi((SPLIT ? K2 : vplus) * R2));
+          xm[j] = fma(-sr, cc1, K1);
+          vm[j] = fma(-sr, cc2, K2);
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < ILP; ++j) {
+      const int64_t sub = base + (int64_t)j * kThreads;
+      if (sub >= a.n) break;
+      const int64_t i = sub + tid;
+      const double Sp = exp(xp[j] + drift_total);
+      const double Sm = ANTI ? exp(xm[j] + drift_total) : 0.0;
+      if (a.terminal && i < a.n) {
+        a.terminal[i] = Sp;
+        if (ANTI) a.terminal[a.n + i] = Sm;
+      }
+      smem[tid] = Sp;
+      if (ANTI) smem[kThreads + tid] = Sm;
+      __syncthreads();
+      const int64_t rem = a.n - sub;
+      const int nvalid = rem < kThreads ? (int)rem : kThreads;
+      if (k < a.npay) {
+        for (int q = g; q < nvalid; q += G) {
+          const double sp = smem[q];
+          double pay = fmax(cp * (sp - strike), 0.0);  // payoffs.jl:154-156
+          bool bad = !isfinite(sp);
+          if (ANTI) {
+            const double sm = smem[kThreads + q];
+            pay = 0.5 * (pay + fmax(cp * (sm - strike), 0.0));  // reduce_payoffs montecarlo.jl:430-432
+            bad = bad || !isfinite(sm);
+          }
+          acc0 += pay;
+          acc1 = fma(pay, pay, acc1);
+          if (k == 0 && bad) acc2 += 1.0;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  smem[tid] = acc0;
+  smem[kThreads + tid] = acc1;
+  smem[2 * kThreads + tid] = acc2;
+  __syncthreads();
+  if (tid < a.npay) {
+    double *out = a.partials + ((size_t)blockIdx.x * a.npay + tid) * NACC;
+    for (int c = 0; c < NACC; ++c) {
+      double t = 0.0;
+      for (int gg = 0; gg < G; ++gg) t += smem[c * kThreads + (gg << a.kp_log2) + tid];
+      out[c] = t;
+    }
+  }
+}
+
 // Payoff sums from terminal spots that another kernel produced (Broadie-Kaya): the same payoff transpose as above.
 __global__ void __launch_bounds__(kThreads) terminal_payoff_kernel(const double *__restrict__ terminal, int64_t n,
                                                                    const hh_payoff *__restrict__ payoffs, int npay,
@@ -601,6 +750,29 @@ static cudaError_t launch_fast_one(const EuroArgs &a, int sm_count, cudaStream_t
   return cudaGetLastError();
 }
 
+template <bool ANTI, bool SPLIT, bool UKEY, int ILP, int THREADS, int MINB>
+static cudaError_t launch_fast2_one(const EuroArgs &a, int sm_count, cudaStream_t st, int *nblocks, bool query_only) {
+  auto kern = heston_fast2_kernel<ANTI, SPLIT, UKEY, ILP, THREADS, MINB>;
+  static bool attr_set = false;  // per instantiation
+  if (!attr_set) {
+    cudaError_t e0 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, fast2_smem_bytes(THREADS));
+    if (e0 != cudaSuccess) return e0;
+    attr_set = true;
+  }
+  int occ = 0;
+  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, fast2_smem_bytes(THREADS));
+  if (e != cudaSuccess) return e;
+  if (occ < 1) occ = 1;
+  const int64_t batch = (int64_t)THREADS * ILP;
+  const int64_t batches = (a.n + batch - 1) / batch;
+  int64_t grid = (int64_t)sm_count * occ;
+  if (grid > batches) grid = batches;
+  *nblocks = (int)grid;
+  if (query_only) return cudaSuccess;
+  kern<<<(unsigned)grid, THREADS, fast2_smem_bytes(THREADS), st>>>(a);
+  return cudaGetLastError();
+}
+
 // variant: tuning knob (HH_HESTON_VARIANT) — 0 is the shipped default
 template <bool ANTI, bool SPLIT, bool UKEY>
 static cudaError_t launch_fast_v(const EuroArgs &a, int variant, int sm_count, cudaStream_t st, int *nb, bool q) {
@@ -610,7 +782,13 @@ static cudaError_t launch_fast_v(const EuroArgs &a, int variant, int sm_count, c
     case 1: return launch_fast_one<ANTI, SPLIT, UKEY, 1, 4>(a, sm_count, st, nb, q);
     case 2: return launch_fast_one<ANTI, SPLIT, UKEY, 1, 6>(a, sm_count, st, nb, q);
     case 3: return launch_fast_one<ANTI, SPLIT, UKEY, 2, 3>(a, sm_count, st, nb, q);
-    default: return launch_fast_one<ANTI, SPLIT, UKEY, 2, 2>(a, sm_count, st, nb, q);
+    case 4: return launch_fast_one<ANTI, SPLIT, UKEY, 2, 2>(a, sm_count, st, nb, q);  // v1 (tables not replicated)
+    case 5: return launch_fast2_one<ANTI, SPLIT, UKEY, 1, 256, 2>(a, sm_count, st, nb, q);
+    case 6: return launch_fast2_one<ANTI, SPLIT, UKEY, 1, 512, 2>(a, sm_count, st, nb, q);   // 32 warps per SM, <= 64 registers
+    case 7: return launch_fast2_one<ANTI, SPLIT, UKEY, 1, 1024, 1>(a, sm_count, st, nb, q);  // same, one block per SM
+    case 8: return launch_fast2_one<ANTI, SPLIT, UKEY, 2, 512, 1>(a, sm_count, st, nb, q);   // 16 warps, one block
+    case 9: return launch_fast2_one<ANTI, SPLIT, UKEY, 1, 768, 1>(a, sm_count, st, nb, q);   // 24 warps, <= 80 registers
+    default: return launch_fast2_one<ANTI, SPLIT, UKEY, 2, 256, 2>(a, sm_count, st, nb, q);
   }
 }
 
@@ -652,6 +830,8 @@ static int build_args(hh_ctx *ctx, const hh_model *m, const hh_sim *s, const hh_
   a.split = (m->flags & HH_FLAG_SPLIT_STEP) ? 1 : 0;
   a.parity = s->rng_mode == HH_RNG_NORMALS;
   a.rk = philox_round_keys(s->base_seed);
+  a.one_hi = 0x3FF00000u;
+  a.magic_hi = 0x43300000u;
   PathParams<double> &p = a.p;
   const double dt = m->T / nsteps;  // montecarlo.jl:349
   const double sqdt = sqrt(dt);
@@ -723,6 +903,7 @@ static int upload_inputs(hh_ctx *ctx, const hh_model *m, const hh_sim *s, const 
                          EuroArgs &a) {
   cudaStream_t st = ctx->stream;
   HH_CUDA(ctx, upload_fast_tables(ctx->device, st));
+  HH_CUDA(ctx, upload_fast_tables2(ctx->device, st));
   const int64_t N = s->n_paths;
   const int ncomp = m->kind == HH_MODEL_HESTON ? 2 : 1;
   a.npay = npay;

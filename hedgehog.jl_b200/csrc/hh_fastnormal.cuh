@@ -57,6 +57,16 @@ struct FastNormalConsts {
   double c6, c4;                                    // cos: -1/720, 1/24
   double tiny;                                      // 1e-300
 };
+struct FastNormalConsts2 {
+  double magic;       // 2^52 + 2^43
+  double s1, s3, s5;  // sin(C s) = s (s1 + s^2 (s3 + s^2 s5)), C = 2 pi 2^-52 folded into the coefficients
+  double c2, c4, c6;  // cos(C s) = 1 + s^2 (c2 + s^2 (c4 + s^2 c6))
+  double l5, l3;      // -2 ln(1+r) = r (-2 + r (1 + r (l3 + r (1/2 + r l5)))), l5 = -2/5, l3 = -2/3
+};
+__constant__ FastNormalConsts2 kFN2 = {4503599627370496.0 + 8796093022208.0,
+                                       0x1.921fb54442d18p-50, -0x1.4abbce625be53p-151, 0x1.466bc6775aae2p-254,
+                                       -0x1.3bd3cc9be45dep-100, 0x1.03c1f081b5ac4p-202, -0x1.55d3c7e3cbffap-306,
+                                       -0.4, -0x1.5555555555555p-1};
 __constant__ FastNormalConsts kFN = {0x1.5555555555555p-2, -0.4, -0x1.5555555555555p-1,
                                      0x1.921fb54442d18p-50, 6755399441055744.0,
                                      0x1.1111111111111p-7, -0x1.5555555555555p-3,
@@ -164,6 +174,93 @@ __device__ __forceinline__ void fast_normal_pair(const FastNormalTables *__restr
   const double rc = rad * cs.x, rs = rad * cs.y;
   z1 = fma(rc, cm, fma(-rs, sn, rc));
   z2 = fma(rs, cm, fma(rc, sn, rs));
+}
+
+// ---- v2: lane-replicated tables for the headline Heston kernel ------------------------------------------------
+// ncu on the v1 kernel (profiles/r1_b_*) showed the step loop bound by shared-memory bank conflicts, not by a math pipe:
+// four table reads per step at random indices cost ~40 L1 wavefronts per warp-step (9.9-way conflicts on average)
+// against 14 for conflict-free access. v2 stores every 16-byte table entry eight times, once per lane of a quarter
+// warp (the unit an LDS.128 is served in), so entry e of lane q sits at byte (e * 8 + q) * 16: the eight lanes of a
+// quarter warp always hit eight disjoint groups of four banks, whatever their indices. The v2 tables are also
+// indexed by TRUNCATION of the random bits (bucket centres at half-integers), which removes the rounding adds and the
+// carry handling from the integer pipe (see tools/gen_tables.py).
+struct FastTables2 {
+  double2 log_tab[tables::kLog2Buckets];  // {rcp_i, -2 ln c_i}
+  double2 trig_tab[tables::kTrigN];       // {cos, sin}(2 pi (j + 1/2) / 256)
+  double exp_tab[tables::kExp2N];         // 2 (1023 - e') ln 2
+};
+static __device__ FastTables2 g_fast_tables2;
+
+static inline cudaError_t upload_fast_tables2(int device, cudaStream_t st) {
+  static bool done[64] = {};
+  if (device >= 0 && device < 64 && done[device]) return cudaSuccess;
+  static FastTables2 h;
+  for (int i = 0; i < tables::kLog2Buckets; ++i) h.log_tab[i] = make_double2(tables::kLog2Tab[i][0], tables::kLog2Tab[i][1]);
+  for (int i = 0; i < tables::kTrigN; ++i) h.trig_tab[i] = make_double2(tables::kTrig2Tab[i][0], tables::kTrig2Tab[i][1]);
+  for (int i = 0; i < tables::kExp2N; ++i) h.exp_tab[i] = tables::kExp2Tab[i];
+  cudaError_t e = cudaMemcpyToSymbolAsync(g_fast_tables2, &h, sizeof h, 0, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e == cudaSuccess && device >= 0 && device < 64) done[device] = true;
+  return e;
+}
+
+constexpr int kRep = 8;                                                      // copies per entry (lanes of a quarter warp)
+constexpr int kLogRepBytes = tables::kLog2Buckets * kRep * 16;               // 32 KB
+constexpr int kPhaseRepBytes = tables::kTrigN * 2 * kRep * 16;               // 64 KB: {P1,Q1} then {P2,Q2} per angle
+constexpr int kExp2Bytes = ((tables::kExp2N * 8 + 15) / 16) * 16;
+constexpr uint32_t kLog2Carry = (1u << 20) - ((uint32_t)tables::kLog2Split << 12);  // mantissa + this carries iff bucket >= split
+
+// max(x, 0) for finite x with ONE integer max on the high word: a negative x becomes a positive denormal-sized value
+// (< 2^-1022), which rounds away in every use below exactly like 0 does.
+__device__ __forceinline__ double max0_hi(double x) {
+  return __hiloint2double(max(__double2hiint(x), 0), __double2loint(x));
+}
+// max(x, ~1e-300) the same way (the low word is kept: any value in [1e-300, 1.000001e-300] serves as the floor)
+__device__ __forceinline__ double max_tiny_hi(double x) {
+  return __hiloint2double(max(__double2hiint(x), 0x01a56e1f), __double2loint(x));
+}
+
+// R2 = -2 ln(u1), u1 = 2 - y1 with y1 = 1.(w1 low 20 bits | w0 | 1): the same uniform as v1 / the oracle.
+// log_lane = replicated log table + (lane & 7) * 16 bytes; exp_biased = exp table - kExp2Bias * 8 bytes.
+__device__ __forceinline__ double fast_neg2log_v2(const char *__restrict__ log_lane, const char *__restrict__ exp_biased,
+                                                  uint32_t w0, uint32_t w1, uint32_t one_hi) {
+  const double y1 = __hiloint2double((int)((w1 & 0xFFFFFu) | one_hi), (int)(w0 | 1u));
+  const double u1 = 2.0 - y1;  // exact
+  const uint32_t uh = (uint32_t)__double2hiint(u1);
+  const uint32_t boff = (uh >> 5) & 0x7F80u;                     // bucket * 128 bytes, bucket = top 8 mantissa bits
+  const uint32_t eoff = ((uh + kLog2Carry) >> 17) & 0x3FF8u;     // e' * 8 bytes
+  const double f = __hiloint2double((int)((uh & 0xFFFFFu) | one_hi), __double2loint(u1));
+  const double2 lt = *reinterpret_cast<const double2 *>(log_lane + boff);
+  const double L = *reinterpret_cast<const double *>(exp_biased + eoff) + lt.y;
+  const double r = fma(f, lt.x, -1.0);                           // |r| <= 2^-9 + 2^-24: degree 5 leaves r^6/3 < 2e-17
+  double p = fma(kFN2.l5, r, 0.5);
+  p = fma(p, r, kFN2.l3);
+  p = fma(p, r, 1.0);
+  p = fma(p, r, -2.0);
+  return fma(p, r, L);
+}
+// Angle theta = 2 pi n2 2^-52, n2 = (w3 low 20 bits, w2): returns the byte offset of table angle j = n2 >> 44 in the
+// replicated phase table (j * 256) and sin(delta), cos(delta) for delta = theta - 2 pi (j + 1/2) / 256, |delta| <= pi/256.
+__device__ __forceinline__ uint32_t fast_angle_v2(uint32_t w2, uint32_t w3, uint32_t magic_hi, double &sn,
+                                                   double &cs) {
+  const uint32_t poff = (w3 >> 4) & 0xFF00u;
+  // 2^52 + (n2 mod 2^44) exactly, minus (2^52 + 2^43): s in [-2^43, 2^43), delta = C s
+  const double sd = __hiloint2double((int)((w3 & 0xFFFu) | magic_hi), (int)w2) - kFN2.magic;
+  const double s2 = sd * sd;
+  sn = sd * fma(s2, fma(s2, kFN2.s5, kFN2.s3), kFN2.s1);
+  cs = fma(s2, fma(s2, fma(s2, kFN2.c6, kFN2.c4), kFN2.c2), 1.0);
+  return poff;
+}
+
+// sqrt(x), x in [1e-300, 1e300]: MUFU.RSQ64H seed y0 (2^-22.9), then s = s0 (1 + e + 3/2 e^2) with s0 = x y0,
+// e = 1/2 - s0 (y0 / 2) = (1 - x y0^2) / 2 — cubic, 5 FP64 instructions; y0 / 2 is an exponent decrement on the ALU.
+__device__ __forceinline__ double fast_sqrt_pos5(double x) {
+  const double y0 = rsqrt_seed(x);
+  const double h0 = __hiloint2double(__double2hiint(y0) - 0x00100000, 0);
+  const double s0 = x * y0;
+  const double e = fma(-s0, h0, 0.5);
+  const double p = fma(e * 1.5, e, e);
+  return fma(s0, p, s0);
 }
 
 }  // namespace hh
