@@ -155,6 +155,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-paths", type=int, default=400_000)
     ap.add_argument("--skip-ensemble", action="store_true")
+    ap.add_argument("--skip-f32", action="store_true")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -260,6 +261,30 @@ def main():
                                 "seconds": dt_e}
         del sol
 
+    # ---- Float32 fast mode of the same workload (config C2 "Float32 fast mode"): reported beside, not as `value` ------
+    f32 = None
+    if args.precision == "f64" and not args.skip_f32:
+        prob32, method32 = c2_problem(hh, total_paths, args.nsteps, "f32")
+        mdl32 = _model_of(prob32, method32)
+
+        def sim32(k):
+            s = _sim_of(method32, _scheme_of(method32), (rank, world))
+            s.base_seed = 7000 + k
+            return s
+        eng.mc_european_launch(mdl32, sim32(0), payoffs)
+        eng.mc_european_collect(D)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for k in range(K):
+            eng.mc_european_launch(mdl32, sim32(1 + k), payoffs)
+        e1.record(stream)
+        barrier()
+        ms32 = max_over_ranks(e0.elapsed_time(e1))
+        r32 = eng.mc_european_collect(D)[0]
+        f32 = {"value": path_steps_per_step * K / (ms32 * 1e-3), "unit": UNIT, "ms_per_step": ms32 / K, "price": r32.price,
+               "std_error": r32.std_error, "note": "f32 state and normals (32-bit uniforms, MUFU lg2/sin/cos/sqrt), f64 payoff sums"}
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
@@ -277,7 +302,7 @@ def main():
                                         "MEASURED_PEAKS.json has no FP64 entry",
                          "convention": "algorithmic 25 FLOP per path-step (log/sincos/sqrt expansions NOT counted); "
                                        "executed-FP64 fraction from ncu is in profiles/"},
-            "e2e": e2e, "gpu_launches": 2 * K, "clocks": clocks,
+            "e2e": e2e, "gpu_launches": 2 * K, "clocks": clocks, "f32_fast_mode": f32,
             "check": {"price": last.price, "std_error": last.std_error, "carr_madan": CARR_MADAN_C2,
                       "n_nonfinite": last.n_nonfinite, "e2e_price": e2e_price},
         }

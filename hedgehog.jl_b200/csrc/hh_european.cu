@@ -42,13 +42,14 @@ struct EuroArgs {
   double *terminal;
   const hh_payoff *payoffs;
   double *partials;  // [grid][npay][nacc]
-  int npay, kp_log2, n_steps, split, parity;
+  int npay, kp_log2, n_steps, split, parity, f32;
   PathParams<double> p;
   HestonFolded f;
   PhiloxRoundKeys rk;  // round keys of base_seed (uniform across threads when seeds == NULL)
   // bit patterns handed over as ARGUMENTS so that (x & mask) | pattern stays one LOP3 with a uniform-register operand
   // (as literals the compiler splits it into an AND-immediate and an OR-immediate)
   uint32_t one_hi, magic_hi;  // 0x3FF00000 (high word of 1.0), 0x43300000 (high word of 2^52)
+  uint32_t f32_one;           // 0x3F800000 (1.0f)
 };
 
 // number of accumulators per (block, payoff): sum, sumsq, nonfinite, then per tangent: dsum, dsumsq
@@ -591,6 +592,155 @@ __global__ void __launch_bounds__(THREADS, MINB) heston_fast2_kernel(const EuroA
   }
 }
 
+// ---- Float32 fast mode of the headline kernel (config C2, HH_PREC_F32) ----------------------------------------
+// FP32 state and normals, FP64 accumulation of the payoff sums. One Philox4x32-10 block feeds TWO steps (32-bit
+// uniforms): step n uses words (0, 1) of block n/2 when n is even and words (2, 3) when n is odd; the stream word of
+// the counter is 1, so the f32 mode never reuses the f64 mode's numbers. Mapping (restated in oracle/hh_oracle.c):
+//   u1 = 2 - float{0x3F800000 | (wa >> 9)}            in [2^-23, 1]      R2 = -2 ln(u1)            (MUFU.LG2)
+//   th = 2 pi (float{0x3F800000 | (wb >> 9)} - 1.5)   in [-pi, pi)       (cos, sin)(th)            (MUFU.COS/SIN)
+// The state is y = log(S / S0) - r t (starts at 0, so the FP32 rounding of the running sum stays ~1e-8 per step);
+// the drift and log S0 are added in FP64 at expiry. One square root per step, as in the FP64 kernel.
+struct HestonF32 {
+  float neg_half_dt, neg_kdt, ktdt, v0, a11, a12, b21, b22;
+};
+
+__device__ __forceinline__ float lg2_approx(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float sqrt_approx(float x) {
+  float y;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+template <bool SPLIT>
+__device__ __forceinline__ void heston_f32_step(const HestonF32 &h, uint32_t wa, uint32_t wb, uint32_t one_bits, float &yp,
+                                                float &vp, float &ym, float &vm, bool anti) {
+  const float fa = __uint_as_float((wa >> 9) | one_bits);
+  const float fb = __uint_as_float((wb >> 9) | one_bits);
+  const float R2 = -1.3862943611198906f * lg2_approx(2.0f - fa);  // -2 ln 2 * log2(u1)
+  const float th = fmaf(fb, 6.283185307179586f, -9.42477796076938f);
+  const float c = __cosf(th), s = __sinf(th);
+  const float cc1 = fmaf(h.a12, s, h.a11 * c);
+  const float cc2 = fmaf(h.b22, s, h.b21 * c);
+  {
+    const float vplus = fmaxf(vp, 0.0f);
+    const float K1 = fmaf(h.neg_half_dt, vplus, yp);
+    const float K2 = fmaf(h.neg_kdt, vplus, vp + h.ktdt);
+    const float sr = sqrt_approx((SPLIT ? fmaxf(K2, 0.0f) : vplus) * R2);
+    yp = fmaf(sr, cc1, K1);
+    vp = fmaf(sr, cc2, K2);
+  }
+  if (anti) {
+    const float vplus = fmaxf(vm, 0.0f);
+    const float K1 = fmaf(h.neg_half_dt, vplus, ym);
+    const float K2 = fmaf(h.neg_kdt, vplus, vm + h.ktdt);
+    const float sr = sqrt_approx((SPLIT ? fmaxf(K2, 0.0f) : vplus) * R2);
+    ym = fmaf(-sr, cc1, K1);
+    vm = fmaf(-sr, cc2, K2);
+  }
+}
+
+template <bool ANTI, bool SPLIT, bool UKEY, int ILP, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB) heston_f32_kernel(const EuroArgs a, const HestonF32 h) {
+  constexpr int NSIDE = ANTI ? 2 : 1;
+  constexpr int NACC = 3;
+  constexpr int STAGE = NSIDE * kThreads;
+  constexpr int RED = NACC * kThreads;
+  __shared__ double smem[STAGE > RED ? STAGE : RED];
+  const int tid = threadIdx.x;
+  const int KP = 1 << a.kp_log2;
+  const int k = tid & (KP - 1);
+  const int g = tid >> a.kp_log2;
+  const int G = kThreads >> a.kp_log2;
+  double strike = 0.0, cp = 0.0;
+  if (k < a.npay) {
+    strike = a.payoffs[k].strike;
+    cp = a.payoffs[k].cp;
+  }
+  double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0;
+  const int M = a.n_steps;
+  const double x_shift = a.p.x0 + (double)M * a.f.rdt;
+  constexpr int64_t kBatch = (int64_t)kThreads * ILP;
+
+  for (int64_t base = (int64_t)blockIdx.x * kBatch; base < a.n; base += (int64_t)gridDim.x * kBatch) {
+    float yp[ILP], vp[ILP], ym[ILP], vm[ILP];
+    uint32_t c0[ILP], c1[ILP];
+    PhiloxRoundKeys rk[UKEY ? 1 : ILP];
+#pragma unroll
+    for (int j = 0; j < ILP; ++j) {
+      const int64_t i = base + (int64_t)j * kThreads + tid;
+      const int64_t ic = i < a.n ? i : a.n - 1;
+      yp[j] = ym[j] = 0.0f;
+      vp[j] = vm[j] = h.v0;
+      if (UKEY) {
+        const uint64_t idx = (uint64_t)(a.path_offset + ic);
+        c0[j] = (uint32_t)idx;
+        c1[j] = (uint32_t)(idx >> 32);
+      } else {
+        c0[j] = c1[j] = 0u;
+        rk[UKEY ? 0 : j] = philox_round_keys(a.seeds[ic]);
+      }
+    }
+#pragma unroll 1
+    for (int n = 0; n < M; n += 2) {
+#pragma unroll
+      for (int j = 0; j < ILP; ++j) {
+        const u32x4 w = philox4x32_10_rk(c0[j], c1[j], (uint32_t)(n >> 1), 1u, UKEY ? a.rk : rk[UKEY ? 0 : j]);
+        heston_f32_step<SPLIT>(h, w.x, w.y, a.f32_one, yp[j], vp[j], ym[j], vm[j], ANTI);
+        if (n + 1 < M) heston_f32_step<SPLIT>(h, w.z, w.w, a.f32_one, yp[j], vp[j], ym[j], vm[j], ANTI);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < ILP; ++j) {
+      const int64_t sub = base + (int64_t)j * kThreads;
+      if (sub >= a.n) break;
+      const int64_t i = sub + tid;
+      const double Sp = exp((double)yp[j] + x_shift);
+      const double Sm = ANTI ? exp((double)ym[j] + x_shift) : 0.0;
+      if (a.terminal && i < a.n) {
+        a.terminal[i] = Sp;
+        if (ANTI) a.terminal[a.n + i] = Sm;
+      }
+      smem[tid] = Sp;
+      if (ANTI) smem[kThreads + tid] = Sm;
+      __syncthreads();
+      const int64_t rem = a.n - sub;
+      const int nvalid = rem < kThreads ? (int)rem : kThreads;
+      if (k < a.npay) {
+        for (int q = g; q < nvalid; q += G) {
+          const double sp = smem[q];
+          double pay = fmax(cp * (sp - strike), 0.0);  // payoffs.jl:154-156
+          bool bad = !isfinite(sp);
+          if (ANTI) {
+            const double sm = smem[kThreads + q];
+            pay = 0.5 * (pay + fmax(cp * (sm - strike), 0.0));  // reduce_payoffs montecarlo.jl:430-432
+            bad = bad || !isfinite(sm);
+          }
+          acc0 += pay;
+          acc1 = fma(pay, pay, acc1);
+          if (k == 0 && bad) acc2 += 1.0;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  smem[tid] = acc0;
+  smem[kThreads + tid] = acc1;
+  smem[2 * kThreads + tid] = acc2;
+  __syncthreads();
+  if (tid < a.npay) {
+    double *out = a.partials + ((size_t)blockIdx.x * a.npay + tid) * NACC;
+    for (int c = 0; c < NACC; ++c) {
+      double t = 0.0;
+      for (int gg = 0; gg < G; ++gg) t += smem[c * kThreads + (gg << a.kp_log2) + tid];
+      out[c] = t;
+    }
+  }
+}
+
 // Payoff sums from terminal spots that another kernel produced (Broadie-Kaya): the same payoff transpose as above.
 __global__ void __launch_bounds__(kThreads) terminal_payoff_kernel(const double *__restrict__ terminal, int64_t n,
                                                                    const hh_payoff *__restrict__ payoffs, int npay,
@@ -806,8 +956,56 @@ static cudaError_t launch_fast(const EuroArgs &a, bool anti, int sm_count, cudaS
 #undef HH_FAST
 }
 
+template <bool ANTI, bool SPLIT, bool UKEY, int ILP, int MINB>
+static cudaError_t launch_f32_one(const EuroArgs &a, const HestonF32 &h, int sm_count, cudaStream_t st, int *nblocks,
+                                  bool query_only) {
+  auto kern = heston_f32_kernel<ANTI, SPLIT, UKEY, ILP, MINB>;
+  int occ = 0;
+  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, 0);
+  if (e != cudaSuccess) return e;
+  if (occ < 1) occ = 1;
+  const int64_t batch = (int64_t)kThreads * ILP;
+  const int64_t batches = (a.n + batch - 1) / batch;
+  int64_t grid = (int64_t)sm_count * occ;
+  if (grid > batches) grid = batches;
+  *nblocks = (int)grid;
+  if (query_only) return cudaSuccess;
+  kern<<<(unsigned)grid, kThreads, 0, st>>>(a, h);
+  return cudaGetLastError();
+}
+
+static cudaError_t launch_f32(const EuroArgs &a, bool anti, int sm_count, cudaStream_t st, int *nb, bool q) {
+  HestonF32 h;
+  h.neg_half_dt = (float)a.f.neg_half_dt;
+  h.neg_kdt = (float)a.f.neg_kdt;
+  h.ktdt = (float)a.f.ktdt;
+  h.v0 = (float)a.p.v0;
+  h.a11 = (float)a.p.a11;
+  h.a12 = (float)a.p.a12;
+  h.b21 = (float)a.f.b21;
+  h.b22 = (float)a.f.b22;
+  const bool ukey = a.seeds == nullptr;
+  static const int variant = getenv("HH_F32_VARIANT") ? atoi(getenv("HH_F32_VARIANT")) : 0;
+#define HH_F32(A, S, U)                                                                   \
+  switch (variant) {                                                                      \
+    /* measured on B200, 5e7 x 252: ILP 4 / 3 blocks 23.3 ms, ILP 2 / 4 blocks 25.3 ms, ILP 1 / 8 blocks 25.1 ms */ \
+    case 1: return launch_f32_one<A, S, U, 2, 4>(a, h, sm_count, st, nb, q);             \
+    case 2: return launch_f32_one<A, S, U, 1, 8>(a, h, sm_count, st, nb, q);             \
+    default: return launch_f32_one<A, S, U, 4, 3>(a, h, sm_count, st, nb, q);            \
+  }
+  if (anti) {
+    if (a.split) { if (ukey) { HH_F32(true, true, true) } else { HH_F32(true, true, false) } }
+    else { if (ukey) { HH_F32(true, false, true) } else { HH_F32(true, false, false) } }
+  } else {
+    if (a.split) { if (ukey) { HH_F32(false, true, true) } else { HH_F32(false, true, false) } }
+    else { if (ukey) { HH_F32(false, false, true) } else { HH_F32(false, false, false) } }
+  }
+#undef HH_F32
+}
+
 static cudaError_t launch_any(int kind, const EuroArgs &a, const TangentPack *tp, int P, bool anti, int sm_count,
                               cudaStream_t st, int *nb, bool q) {
+  if (a.f32) return launch_f32(a, anti, sm_count, st, nb, q);
   if (kind == K_HESTON_EM && P == 0 && !a.parity) return launch_fast(a, anti, sm_count, st, nb, q);
   switch (kind) {
     case K_GBM_EM: return launch_kind<K_GBM_EM>(a, tp, P, anti, sm_count, st, nb, q);
@@ -829,9 +1027,11 @@ static int build_args(hh_ctx *ctx, const hh_model *m, const hh_sim *s, const hh_
   a.n_steps = nsteps;
   a.split = (m->flags & HH_FLAG_SPLIT_STEP) ? 1 : 0;
   a.parity = s->rng_mode == HH_RNG_NORMALS;
+  a.f32 = s->precision == HH_PREC_F32;
   a.rk = philox_round_keys(s->base_seed);
   a.one_hi = 0x3FF00000u;
   a.magic_hi = 0x43300000u;
+  a.f32_one = 0x3F800000u;
   PathParams<double> &p = a.p;
   const double dt = m->T / nsteps;  // montecarlo.jl:349
   const double sqdt = sqrt(dt);
@@ -933,7 +1133,9 @@ int european_launch(hh_ctx *ctx, const hh_model *m, const hh_sim *s, const hh_pa
   if (npay < 1 || npay > kThreads || !payoffs)
     return ctx->fail(HH_ERR_ARG, "npayoffs must be in [1, %d] (got %d)", kThreads, npay);
   if (s->scheme == HH_SCHEME_HESTON_BK) return ctx->fail(HH_ERR_UNSUPPORTED, "use the Broadie-Kaya driver");
-  if (s->precision != HH_PREC_F64) return ctx->fail(HH_ERR_UNSUPPORTED, "f32 fast mode is not built in this version");
+  if (s->precision == HH_PREC_F32 && (m->kind != HH_MODEL_HESTON || s->scheme != HH_SCHEME_EM || s->rng_mode != HH_RNG_PHILOX))
+    return ctx->fail(HH_ERR_UNSUPPORTED, "the f32 fast mode covers Heston Euler-Maruyama with the in-kernel RNG (config C2)");
+  if (s->precision != HH_PREC_F64 && s->precision != HH_PREC_F32) return ctx->fail(HH_ERR_ARG, "unknown precision %d", s->precision);
 
   const int64_t N = s->n_paths;
   const bool anti = s->vr == HH_VR_ANTITHETIC;

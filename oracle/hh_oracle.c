@@ -211,6 +211,53 @@ static terminal_t simulate_one(const hh_model *m, const hh_sim *sim, int64_t i, 
     return out;
   }
 
+  if (m->kind == HH_MODEL_HESTON && sim->scheme == HH_SCHEME_EM && sim->precision == HH_PREC_F32) {
+    /* Float32 fast mode (new-build convention, include/hedgehog_mc.h HH_PREC_F32): the same scheme as below in
+     * binary32, 32-bit uniforms, two steps per Philox block (stream word 1), state y = log(S/S0) - r t.
+     * The GPU uses MUFU approximations of lg2 / sin / cos / sqrt, so agreement is to ~1e-4 per path, not bitwise. */
+    const int split = (m->flags & HH_FLAG_SPLIT_STEP) != 0;
+    const float nhdt = (float)(-0.5 * dt), nkdt = (float)(-(m->kappa * dt)), ktdt = (float)(m->kappa * m->theta * dt);
+    const float a11 = (float)(sqdt * m->m11), a12 = (float)(sqdt * m->m12);
+    const float b21 = (float)(m->xi * (sqdt * m->m21)), b22 = (float)(m->xi * (sqdt * m->m22));
+    float yp = 0.0f, vp = (float)m->V0, ym = 0.0f, vm = vp;
+    uint32_t w[4] = {0, 0, 0, 0};
+    for (int n = 0; n < M; ++n) {
+      if ((n & 1) == 0) {
+        uint32_t ctr[4] = {(uint32_t)idx, (uint32_t)(idx >> 32), (uint32_t)(n >> 1), 1u};
+        uint32_t k2[2] = {(uint32_t)key, (uint32_t)(key >> 32)};
+        hho_philox4x32_10(ctr, k2, w);
+      }
+      const uint32_t wa = w[(n & 1) * 2], wb = w[(n & 1) * 2 + 1];
+      union { uint32_t u; float f; } fa, fb;
+      fa.u = (wa >> 9) | 0x3F800000u;
+      fb.u = (wb >> 9) | 0x3F800000u;
+      const float R2 = -1.3862943611198906f * log2f(2.0f - fa.f);
+      const float th = fmaf(fb.f, 6.283185307179586f, -9.42477796076938f);
+      const float c = cosf(th), sn = sinf(th);
+      const float cc1 = fmaf(a12, sn, a11 * c), cc2 = fmaf(b22, sn, b21 * c);
+      {
+        float vplus = fmaxf(vp, 0.0f);
+        float K1 = fmaf(nhdt, vplus, yp), K2 = fmaf(nkdt, vplus, vp + ktdt);
+        float sr = sqrtf((split ? fmaxf(K2, 0.0f) : vplus) * R2);
+        yp = fmaf(sr, cc1, K1);
+        vp = fmaf(sr, cc2, K2);
+      }
+      if (anti) {
+        float vplus = fmaxf(vm, 0.0f);
+        float K1 = fmaf(nhdt, vplus, ym), K2 = fmaf(nkdt, vplus, vm + ktdt);
+        float sr = sqrtf((split ? fmaxf(K2, 0.0f) : vplus) * R2);
+        ym = fmaf(-sr, cc1, K1);
+        vm = fmaf(-sr, cc2, K2);
+      }
+    }
+    const double shift = log(m->S0) + (double)M * (m->r * dt);
+    out.Sp = exp((double)yp + shift);
+    out.vp = vp;
+    out.Sm = anti ? exp((double)ym + shift) : 0.0;
+    out.vm = vm;
+    return out;
+  }
+
   if (m->kind == HH_MODEL_HESTON && sim->scheme == HH_SCHEME_EM) {
     /* LogHestonProblem heston.jl:7-31 : full truncation, diagonal noise, correlated Wiener;
      * EM{split=true} [upstream]: K = u + dt f(u); u' = K + g(K) .* dW. */

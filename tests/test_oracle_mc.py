@@ -143,3 +143,20 @@ def test_q1_sqrt_alpha_mean_switch(oracle):
     assert mk(one_year, True) == mk(one_year, False)
     two_years = REF + dt.timedelta(days=730)
     assert mk(two_years, True) != mk(two_years, False)
+
+
+def test_f32_restatement_agrees_with_f64_statistically(oracle):
+    """The binary32 restatement of Heston EM (the checker of the GPU's f32 fast mode) prices within 3 sigma of the
+    binary64 one and of Carr-Madan."""
+    from hedgehog_jl_b200 import _abi as abi
+    from hedgehog_jl_b200.engine import SimSpec
+    from helpers import heston_model
+    from oracle import anchors
+    m = heston_model()
+    D = math.exp(-m.r * m.T)
+    n = 200_000
+    r32, _ = oracle.mc_european(m, SimSpec(n_paths=n, n_steps=100, precision=abi.HH_PREC_F32, base_seed=8), [(100.0, 1.0)], D)
+    r64, _ = oracle.mc_european(m, SimSpec(n_paths=n, n_steps=100, base_seed=8), [(100.0, 1.0)], D)
+    cm = anchors.heston_price(100.0, 100.0, m.r, m.T, m.V0, m.kappa, m.theta, m.xi, m.rho)
+    assert abs(r32[0].price - r64[0].price) < 3 * math.hypot(r32[0].std_error, r64[0].std_error)
+    assert abs(r32[0].price - cm) < 3 * r32[0].std_error + 0.02
