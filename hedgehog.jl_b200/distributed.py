@@ -42,9 +42,10 @@ def make_comm(shard, group=None):
             if dist.get_backend(group) == "nccl":
                 ext = torch.cuda.ExternalStream(stream) if stream else torch.cuda.current_stream()
                 with torch.cuda.stream(ext):
+                    # stream-ordered: ProcessGroupNCCL makes `ext` wait for its collective, so the library's next kernel
+                    # (the fit) sees the reduced moments without a host round trip
                     t = torch.as_tensor(_DevArray(dev_ptr, count, stream), device="cuda")
                     dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
-                ext.synchronize()
             else:  # gloo (CPU tests with an injected engine): dev_ptr is a host pointer
                 buf = (C.c_double * count).from_address(dev_ptr)
                 t = torch.frombuffer(buf, dtype=torch.float64)
