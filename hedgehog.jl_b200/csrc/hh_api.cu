@@ -72,6 +72,9 @@ int hh_create(hh_ctx **out, int device) {
   ctx->cc_major = prop.major;
   ctx->cc_minor = prop.minor;
   ctx->total_mem = prop.totalGlobalMem;
+  ctx->l2_bytes = (size_t)prop.l2CacheSize;
+  ctx->l2_persist_max = (size_t)prop.persistingL2CacheMaxSize;
+  ctx->l2_window_max = (size_t)prop.accessPolicyMaxWindowSize;
   bool ok = cudaSetDevice(device) == cudaSuccess &&
             cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) == cudaSuccess &&
             cudaEventCreate(&ctx->ev0) == cudaSuccess && cudaEventCreate(&ctx->ev1) == cudaSuccess &&

@@ -53,6 +53,7 @@ struct hh_ctx {
   int sm_count = 0;
   int cc_major = 0, cc_minor = 0;
   size_t total_mem = 0;
+  size_t l2_bytes = 0, l2_persist_max = 0, l2_window_max = 0;  // L2 size, largest persisting carve-out, largest policy window
   cudaStream_t own_stream = nullptr;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;

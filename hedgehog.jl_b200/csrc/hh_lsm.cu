@@ -22,12 +22,14 @@
 // Multi-GPU: columns are sharded; the per-date moment vector (3 deg + 3 doubles) is sum-allreduced through the
 // caller's hh_comm callback between the pass and the fit, so every rank fits the same global polynomial.
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
 #include "hh_ctx.h"
 #include "hh_fastnormal.cuh"
 #include "hh_paths.cuh"
+#include "hh_tma.cuh"
 
 namespace hh {
 
@@ -44,13 +46,40 @@ struct LsmPathArgs {
   double S0, dt_drift, sig_sqdt;
 };
 
+// exp(y) - 1 for the per-step exponent of the GBM generator, |y| <= 1/2: y = j/64 + r, exp(y) - 1 =
+// (E_j - 1) + E_j (exp(r) - 1) with {E_j, E_j - 1} tabulated in shared memory (65 entries, filled with libm at kernel
+// start) and exp(r) - 1 by its series to r^6 (|r| <= 1/128: remainder 3.5e-19). 10 FP64 instructions against ~25 for
+// libm's exp; larger |y| (huge sigma sqrt(dt) Z) takes the libm path.
+constexpr int kExpJ = 32;
+struct ExpCoefs {
+  double magic, inv6, inv24, inv120, inv720;
+};
+__constant__ ExpCoefs kExpC = {6755399441055744.0, 1.0 / 6, 1.0 / 24, 1.0 / 120, 1.0 / 720};
+
+__device__ __forceinline__ double fast_expm1_small(const double2 *__restrict__ tab, double y) {
+  if (!(fabs(y) <= 0.5)) return exp(y) - 1.0;
+  const double t = fma(y, 64.0, kExpC.magic);  // nearest integer to 64 y in the low word
+  const int j = __double2loint(t);
+  const double r = fma(t - kExpC.magic, -0.015625, y);  // exact
+  const double2 e = tab[j + kExpJ];
+  double p = fma(r, kExpC.inv720, kExpC.inv120);
+  p = fma(p, r, kExpC.inv24);
+  p = fma(p, r, kExpC.inv6);
+  p = fma(p, r, 0.5);
+  p = fma(p, r, 1.0);
+  return fma(e.x, p * r, e.y);
+}
+
 template <bool ANTI>
 __global__ void __launch_bounds__(kLsmThreads) lsm_paths_kernel(const LsmPathArgs a) {
   __shared__ FastNormalTables s_tables;
-  if (!a.parity) {
-    load_fast_tables(&s_tables);
-    __syncthreads();
+  __shared__ double2 s_exp[2 * kExpJ + 1];
+  if (!a.parity) load_fast_tables(&s_tables);
+  if (threadIdx.x <= 2 * kExpJ) {
+    const double yj = (double)((int)threadIdx.x - kExpJ) * 0.015625;
+    s_exp[threadIdx.x] = make_double2(exp(yj), expm1(yj));
   }
+  __syncthreads();
   const int M = a.n_steps;
   for (int64_t i = (int64_t)blockIdx.x * kLsmThreads + threadIdx.x; i < a.n; i += (int64_t)gridDim.x * kLsmThreads) {
     uint64_t key = a.base_seed, idx = (uint64_t)(a.path_offset + i);
@@ -81,10 +110,10 @@ __global__ void __launch_bounds__(kLsmThreads) lsm_paths_kernel(const LsmPathArg
           const double zz = h ? zb : za;
           // GeometricBrownianMotionProcess increment [upstream]: S += S (exp((r - s^2/2) dt + s sqrt(dt) Z) - 1)
           const double e = a.sig_sqdt * zz;
-          Sp = fma(Sp, exp(a.dt_drift + e) - 1.0, Sp);
+          Sp = fma(Sp, fast_expm1_small(s_exp, a.dt_drift + e), Sp);
           gp[(size_t)(n + h + 1) * a.stride] = Sp;
           if (ANTI) {  // same normals, sigma -> -sigma (montecarlo.jl:270-284)
-            Sm = fma(Sm, exp(a.dt_drift - e) - 1.0, Sm);
+            Sm = fma(Sm, fast_expm1_small(s_exp, a.dt_drift - e), Sm);
             gm[(size_t)(n + h + 1) * a.stride] = Sm;
           }
         }
@@ -97,6 +126,7 @@ __global__ void __launch_bounds__(kLsmThreads) lsm_paths_kernel(const LsmPathArg
 // (no in-the-money column, least_squares_montecarlo.jl:122) or is the terminal date.
 struct LsmFit {
   double c[kLsmMaxDeg + 1];
+  double q[kLsmMaxDeg + 1];  // the same polynomial in powers of u (Horner form for the pass kernel); q[0] = +inf when inactive
   double active;
   double used_degree;
   double count;
@@ -138,42 +168,48 @@ __device__ __forceinline__ double clenshaw(const double *c, double u) {
 template <int DEG>
 __host__ __device__ constexpr int lsm_nacc() { return 3 * DEG + 3; }
 
-template <int DEG>
-__device__ __forceinline__ void lsm_column(const LsmPassArgs &a, const double *fit, bool fit_active, double sn, double sc,
-                                           double zin, int64_t p, double &zout, double *acc) {
+// One column of one pass, branch free. The pass kernel is bound by the SM's dispatch port, not by HBM, unless the
+// per-column instruction count is kept near the minimum (profiles/r1_c_ncu_lsm_pass_2e6.csv: DRAM 25 %, issue 57 %):
+//   decision at t+1:  e = cp S - cp K;  cont = Horner(q, ua S + ub);  exercise iff e > 0 and e > cont (strict, :163-164)
+//   moments at t:     g = 1{cp S_t - cp K > 0};  T_0 = g, T_1 = g u, T_k = 2 u T_{k-1} - T_{k-2}: the indicator rides
+//                     through the linear recurrence, so every sum is an unconditional add / fma.
+// Sign tests read the high word of the double on the integer pipe (x > 0 <=> hi(x) > 0 for the values that occur:
+// cp (S - K) is either 0 or at least one ulp of S).
+template <int DEG, bool FIRST, bool LAST, bool TAU>
+__device__ __forceinline__ void lsm_column(const LsmPassArgs &a, const double *q, double cpK, double sn, double sc,
+                                           double zin, int64_t p, double &zout, double *acc, int &cnt) {
   constexpr int NM = 2 * DEG + 1;
+  const double e = fma(a.cp, sn, -cpK);
   double zz;
-  if (a.first) {
-    zz = fmax(a.cp * (sn - a.strike), 0.0);  // stopping_info = (nsteps, payoff(S_T))  :112
+  if (FIRST) {
+    zz = __double2hiint(e) > 0 ? e : 0.0;  // stopping_info = (nsteps, payoff(S_T))  :112
   } else {
-    zz = zin;
-    const double e = fmax(a.cp * (sn - a.strike), 0.0);
-    if (fit_active && e > 0.0) {
-      const double cont = clenshaw<DEG>(fit, fma(a.ua, sn, a.ub));  // poly.(x)  :127
-      if (e > cont) {                                               // strict  :163-164
-        zz = e;
-        if (a.tau) a.tau[p] = a.t_next;
-      }
-    }
+    const double un = fma(a.ua, sn, a.ub);
+    double cont = q[DEG];  // poly.(x)  :127
+#pragma unroll
+    for (int k = DEG - 1; k >= 0; --k) cont = fma(cont, un, q[k]);
+    const bool ex = (__double2hiint(e) > 0) && (e > cont);
+    zz = ex ? e : zin;
+    if (TAU && ex) a.tau[p] = a.t_next;
   }
   zz *= a.D;  // discount^(tau - t) one date at a time  :117-118
   zout = zz;
-  if (a.last) {
+  if (LAST) {
     acc[0] += zz;
     acc[1] = fma(zz, zz, acc[1]);
-    acc[2] += 1.0;
+    cnt += 1;
   } else {
-    const double e0 = a.cp * (sc - a.strike);
-    if (e0 > 0.0) {  // in the money  :120-121
-      const double u = fma(a.ua, sc, a.ub);
-      const double u2 = 2.0 * u;
-      double t0 = 1.0, t1 = u;
-      acc[0] += 1.0;
-      acc[NM] += zz;
-      if (DEG >= 1) {
-        acc[1] += u;
-        acc[NM + 1] = fma(u, zz, acc[NM + 1]);
-      }
+    const double e0 = fma(a.cp, sc, -cpK);
+    const bool itm = __double2hiint(e0) > 0;  // in the money  :120-121
+    const double u = itm ? fma(a.ua, sc, a.ub) : 0.0;
+    const double g = itm ? 1.0 : 0.0;
+    cnt += itm ? 1 : 0;
+    acc[NM] = fma(g, zz, acc[NM]);
+    if (DEG >= 1 || NM > 1) {
+      const double u2 = u + u;
+      double t0 = g, t1 = u;
+      acc[1] += u;
+      if (DEG >= 1) acc[NM + 1] = fma(u, zz, acc[NM + 1]);
 #pragma unroll
       for (int k = 2; k < NM; ++k) {
         const double tk = fma(u2, t1, -t0);
@@ -182,144 +218,221 @@ __device__ __forceinline__ void lsm_column(const LsmPassArgs &a, const double *f
         acc[k] += tk;
         if (k <= DEG) acc[NM + k] = fma(tk, zz, acc[NM + k]);
       }
-      acc[NM + DEG + 1] += 1.0;
     }
   }
 }
 
-// Sum the per-block partials in a fixed order: moments[c] = sum_b partials[b][c]. One warp per accumulator
-// (lanes stride over the blocks, then a shuffle tree), so the dependent chain is nblocks / 32 long.
-__device__ __forceinline__ void lsm_reduce_partials(const double *partials, int nblocks, int nacc, double *moments) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  for (int c = warp; c < nacc; c += nwarps) {
-    double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;
-    int b = lane;
-    for (; b + 96 < nblocks; b += 128) {
-      t0 += partials[(size_t)b * nacc + c];
-      t1 += partials[(size_t)(b + 32) * nacc + c];
-      t2 += partials[(size_t)(b + 64) * nacc + c];
-      t3 += partials[(size_t)(b + 96) * nacc + c];
-    }
-    for (; b < nblocks; b += 32) t0 += partials[(size_t)b * nacc + c];
-    double t = (t0 + t1) + (t2 + t3);
+// Sum the per-block partials in a fixed order: moments[c] = sum_b partials[b][c]. The whole block takes part:
+// thread (c, g) sums blocks g, g + G, g + 2G, ... with eight independent accumulators (all loads in flight at once:
+// one L2 round trip instead of a dependent chain), then the G group sums of an accumulator are added in order.
+// scratch: >= 256 doubles of shared memory. Deterministic for a given grid size.
+__device__ __forceinline__ void lsm_reduce_partials(const double *partials, int nblocks, int nacc, double *moments,
+                                                    double *scratch) {
+  const int G = (int)blockDim.x / nacc;
+  const int c = (int)threadIdx.x % nacc, g = (int)threadIdx.x / nacc;
+  if (g < G) {
+    double t[8];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) t += __shfl_down_sync(0xffffffffu, t, o);
-    if (lane == 0) moments[c] = t;
+    for (int k = 0; k < 8; ++k) t[k] = 0.0;
+    int b = g;
+    for (; b + 7 * G < nblocks; b += 8 * G) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) t[k] += __ldcg(partials + (size_t)(b + k * G) * nacc + c);
+    }
+    for (int k = 0; b < nblocks; b += G, ++k) t[k & 7] += __ldcg(partials + (size_t)b * nacc + c);
+    scratch[g * nacc + c] = ((t[0] + t[1]) + (t[2] + t[3])) + ((t[4] + t[5]) + (t[6] + t[7]));
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < nacc) {
+    double v = 0.0;
+    for (int gg = 0; gg < G; ++gg) v += scratch[gg * nacc + threadIdx.x];
+    moments[threadIdx.x] = v;
   }
 }
 
 __global__ void __launch_bounds__(256) lsm_reduce_kernel(const double *partials, int nblocks, int nacc, double *moments) {
-  lsm_reduce_partials(partials, nblocks, nacc, moments);
+  __shared__ double scratch[256];
+  lsm_reduce_partials(partials, nblocks, nacc, moments, scratch);
+}
+
+// 1 / sqrt(d) to full double precision without the IEEE division/sqrt sequences (the fit is a serial chain on one
+// thread in the tail of every pass): MUFU.RSQ64H seed, two Newton steps.
+__device__ __forceinline__ double rsqrt_fast(double d) {
+  double y = rsqrt_seed(d);
+  double e = fma(-d * y, y, 1.0);
+  y = fma(y * e, fma(e, 0.375, 0.5), y);
+  e = fma(-d * y, y, 1.0);
+  return fma(y * e, 0.5, y);
 }
 
 // Normal equations in the Chebyshev basis: G[i][j] = (m[i+j] + m[|i-j|]) / 2, rhs[i] = r[i]; Cholesky.
 // If the matrix is numerically singular at the requested degree (fewer distinct in-the-money spots than
 // coefficients), the leading block that factorises is used (a lower-degree fit in the same nested basis).
-__device__ void lsm_fit(const double *moments, int deg, LsmFit *out) {
-  const int nm = 2 * deg + 1;
-  const double *m = moments, *r = moments + nm;
-  const double count = moments[nm + deg + 1];
-  LsmFit f;
-  for (int k = 0; k <= kLsmMaxDeg; ++k) f.c[k] = 0.0;
-  f.active = 0.0;
-  f.used_degree = -1.0;
-  f.count = count;
+// DEG is a compile-time constant so that every array lives in registers.
+template <int DEG>
+__device__ __forceinline__ void lsm_fit(const double *moments, LsmFit *out) {
+  constexpr int nm = 2 * DEG + 1;
+  double m[nm], r[DEG + 1];
+#pragma unroll
+  for (int k = 0; k < nm; ++k) m[k] = moments[k];
+#pragma unroll
+  for (int k = 0; k <= DEG; ++k) r[k] = moments[nm + k];
+  const double count = moments[nm + DEG + 1];
+  double c[DEG + 1];
+#pragma unroll
+  for (int k = 0; k <= DEG; ++k) c[k] = 0.0;
+  double active = 0.0, used = -1.0;
   if (count > 0.0) {
-    double L[kLsmMaxDeg + 1][kLsmMaxDeg + 1];
+    double L[DEG + 1][DEG + 1], inv[DEG + 1];
     int n = 0;  // size of the leading block that factorises
-    for (int j = 0; j <= deg; ++j) {
+    bool ok = true;
+#pragma unroll
+    for (int j = 0; j <= DEG; ++j) {
       double d = 0.5 * (m[2 * j] + m[0]);
-      for (int k = 0; k < j; ++k) d -= L[j][k] * L[j][k];
-      if (!(d > 1e-13 * m[0])) break;
-      const double ljj = sqrt(d);
-      L[j][j] = ljj;
-      for (int i = j + 1; i <= deg; ++i) {
+#pragma unroll
+      for (int k = 0; k < j; ++k) d = fma(-L[j][k], L[j][k], d);
+      ok = ok && (d > 1e-13 * m[0]);
+      const double rs = rsqrt_fast(ok ? d : 1.0);
+      inv[j] = rs;
+      L[j][j] = d * rs;
+#pragma unroll
+      for (int i = j + 1; i <= DEG; ++i) {
         double s = 0.5 * (m[i + j] + m[i - j]);
-        for (int k = 0; k < j; ++k) s -= L[i][k] * L[j][k];
-        L[i][j] = s / ljj;
+#pragma unroll
+        for (int k = 0; k < j; ++k) s = fma(-L[i][k], L[j][k], s);
+        L[i][j] = s * rs;
       }
-      n = j + 1;
+      if (ok) n = j + 1;
     }
     if (n > 0) {
-      double y[kLsmMaxDeg + 1];
-      for (int i = 0; i < n; ++i) {
+      double y[DEG + 1];
+#pragma unroll
+      for (int i = 0; i <= DEG; ++i) {
         double s = r[i];
-        for (int k = 0; k < i; ++k) s -= L[i][k] * y[k];
-        y[i] = s / L[i][i];
+#pragma unroll
+        for (int k = 0; k < i; ++k) s = fma(-L[i][k], y[k], s);
+        y[i] = i < n ? s * inv[i] : 0.0;
       }
-      for (int i = n - 1; i >= 0; --i) {
+#pragma unroll
+      for (int i = DEG; i >= 0; --i) {
         double s = y[i];
-        for (int k = i + 1; k < n; ++k) s -= L[k][i] * f.c[k];
-        f.c[i] = s / L[i][i];
+#pragma unroll
+        for (int k = i + 1; k <= DEG; ++k) s = fma(-L[k][i], c[k], s);  // c[k] = 0 for k >= n
+        c[i] = i < n ? s * inv[i] : 0.0;
       }
-      f.active = 1.0;
-      f.used_degree = (double)(n - 1);
+      active = 1.0;
+      used = (double)(n - 1);
     }
   }
-  *out = f;
-}
-
-__global__ void lsm_fit_kernel(const double *moments, int deg, LsmFit *out) {
-  if (threadIdx.x == 0) lsm_fit(moments, deg, out);
+  // powers of u: T_0 = 1, T_1 = u, T_{k+1} = 2 u T_k - T_{k-1}
+  double q[DEG + 1], ta[DEG + 1], tb[DEG + 1];
+#pragma unroll
+  for (int k = 0; k <= DEG; ++k) q[k] = ta[k] = tb[k] = 0.0;
+  ta[0] = 1.0;
+  q[0] = c[0];
+  if (DEG >= 1) {
+    tb[1] = 1.0;
+    q[1] = c[1];
+  }
+#pragma unroll
+  for (int k = 2; k <= DEG; ++k) {
+    double tc[DEG + 1];
+#pragma unroll
+    for (int j = 0; j <= DEG; ++j) tc[j] = (j > 0 ? 2.0 * tb[j - 1] : 0.0) - ta[j];
+#pragma unroll
+    for (int j = 0; j <= DEG; ++j) {
+      q[j] = fma(c[k], tc[j], q[j]);
+      ta[j] = tb[j];
+      tb[j] = tc[j];
+    }
+  }
+  if (active == 0.0) q[0] = __longlong_as_double(0x7ff0000000000000LL);  // never exercise against +inf
+#pragma unroll
+  for (int k = 0; k <= kLsmMaxDeg; ++k) {
+    out->c[k] = k <= DEG ? c[k < DEG ? k : DEG] : 0.0;
+    out->q[k] = k <= DEG ? q[k < DEG ? k : DEG] : 0.0;
+  }
+  out->active = active;
+  out->used_degree = used;
+  out->count = count;
 }
 
 template <int DEG>
+__global__ void lsm_fit_kernel(const double *moments, LsmFit *out) {
+  if (threadIdx.x == 0) lsm_fit<DEG>(moments, out);
+}
+
+template <int DEG, bool FIRST, bool LAST, bool TAU>
 __global__ void __launch_bounds__(kLsmThreads) lsm_pass_kernel(const LsmPassArgs a) {
   constexpr int NACC = lsm_nacc<DEG>();
+  constexpr int NM = 2 * DEG + 1;
   __shared__ double s_red[NACC][kLsmThreads / 32];
+  __shared__ double s_scratch[kLsmThreads];
   __shared__ bool s_last;
-  double fit[DEG + 1];
-  bool fit_active = false;
-  if (!a.first) {
-    fit_active = a.fit_next->active != 0.0;
+  double q[DEG + 1];
 #pragma unroll
-    for (int k = 0; k <= DEG; ++k) fit[k] = a.fit_next->c[k];
-  }
+  for (int k = 0; k <= DEG; ++k) q[k] = FIRST ? 0.0 : a.fit_next->q[k];
+  const double cpK = a.cp * a.strike;
   double acc[NACC];
 #pragma unroll
   for (int c = 0; c < NACC; ++c) acc[c] = 0.0;
+  int cnt = 0;
 
   // Two columns per thread per iteration (16 B loads and stores; the slices are 256 B aligned), and the loads of the
   // next iteration are issued before the arithmetic of the current one so that every thread keeps 6 x 16 B in flight.
   const int64_t npairs = a.ncols >> 1;
-  const double2 *Sn2 = reinterpret_cast<const double2 *>(a.S_next);
-  const double2 *Sc2 = reinterpret_cast<const double2 *>(a.S_cur);
-  double2 *z2 = reinterpret_cast<double2 *>(a.z);
   const int64_t step = (int64_t)gridDim.x * kLsmThreads;
-  int64_t q = (int64_t)blockIdx.x * kLsmThreads + threadIdx.x;
+  const int64_t first = (int64_t)blockIdx.x * kLsmThreads + threadIdx.x;
+  const int iters = first < npairs ? (int)((npairs - 1 - first) / step) + 1 : 0;
   // passes alternate their direction over the columns: what the previous pass touched last (z and the shared date
   // slice) is what this pass touches first, while it is still in L2
   const bool rev = a.reverse != 0;
-  auto at = [&](int64_t k) { return rev ? npairs - 1 - k : k; };
-  double2 sn = make_double2(0.0, 0.0), sc = sn, zi = sn;
-  if (q < npairs) {
-    sn = __ldcs(Sn2 + at(q));
-    if (!a.last) sc = __ldg(Sc2 + at(q));
-    if (!a.first) zi = z2[at(q)];
-  }
-  while (q < npairs) {
-    const int64_t qn = q + step;
-    double2 sn_n = make_double2(0.0, 0.0), sc_n = sn_n, zi_n = sn_n;
-    if (qn < npairs) {
-      sn_n = __ldcs(Sn2 + at(qn));
-      if (!a.last) sc_n = __ldg(Sc2 + at(qn));
-      if (!a.first) zi_n = z2[at(qn)];
-    }
+  int64_t idx = rev ? npairs - 1 - first : first;  // pair index of this thread's current iteration
+  const int64_t dstep = rev ? -step : step;
+  const double2 *pn = reinterpret_cast<const double2 *>(a.S_next) + idx;
+  const double2 *pc = reinterpret_cast<const double2 *>(a.S_cur) + idx;
+  double2 *pz = reinterpret_cast<double2 *>(a.z) + idx;
+  // software pipeline, unrolled by two with ping-pong register sets (no register moves): the loads of iteration
+  // i+1 are in flight while iteration i computes
+  double2 snA = make_double2(0.0, 0.0), scA = snA, ziA = snA, snB = snA, scB = snA, ziB = snA;
+  auto load = [&](double2 &sn, double2 &sc, double2 &zi) {
+    sn = __ldcs(pn);
+    if (!LAST) sc = __ldg(pc);
+    if (!FIRST) zi = *pz;
+  };
+  auto work = [&](const double2 &sn, const double2 &sc, const double2 &zi, double2 *zdst, int64_t col) {
     double2 zo;
-    const int64_t col = 2 * at(q);
-    lsm_column<DEG>(a, fit, fit_active, sn.x, sc.x, zi.x, col, zo.x, acc);
-    lsm_column<DEG>(a, fit, fit_active, sn.y, sc.y, zi.y, col + 1, zo.y, acc);
-    z2[at(q)] = zo;
-    sn = sn_n;
-    sc = sc_n;
-    zi = zi_n;
-    q = qn;
+    lsm_column<DEG, FIRST, LAST, TAU>(a, q, cpK, sn.x, sc.x, zi.x, col, zo.x, acc, cnt);
+    lsm_column<DEG, FIRST, LAST, TAU>(a, q, cpK, sn.y, sc.y, zi.y, col + 1, zo.y, acc, cnt);
+    *zdst = zo;
+  };
+  if (iters > 0) load(snA, scA, ziA);
+  int it = 0;
+  for (; it + 2 <= iters; it += 2) {
+    double2 *zA = pz;
+    const int64_t colA = 2 * idx;
+    pn += dstep; pc += dstep; pz += dstep; idx += dstep;
+    load(snB, scB, ziB);
+    work(snA, scA, ziA, zA, colA);
+    double2 *zB = pz;
+    const int64_t colB = 2 * idx;
+    pn += dstep; pc += dstep; pz += dstep; idx += dstep;
+    if (it + 2 < iters) load(snA, scA, ziA);
+    work(snB, scB, ziB, zB, colB);
   }
+  if (it < iters) work(snA, scA, ziA, pz, 2 * idx);
   if ((a.ncols & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
     const int64_t p = a.ncols - 1;
     double zo;
-    lsm_column<DEG>(a, fit, fit_active, a.S_next[p], a.last ? 0.0 : a.S_cur[p], a.first ? 0.0 : a.z[p], p, zo, acc);
+    lsm_column<DEG, FIRST, LAST, TAU>(a, q, cpK, a.S_next[p], LAST ? 0.0 : a.S_cur[p], FIRST ? 0.0 : a.z[p], p, zo, acc, cnt);
     a.z[p] = zo;
+  }
+  // the counts were kept on the integer pipe: m[0] = sum of the indicator, and the trailing count slot
+  if (LAST) {
+    acc[2] = (double)cnt;
+  } else {
+    acc[0] = (double)cnt;
+    acc[NM + DEG + 1] = (double)cnt;
   }
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -344,10 +457,134 @@ __global__ void __launch_bounds__(kLsmThreads) lsm_pass_kernel(const LsmPassArgs
   __syncthreads();
   if (s_last) {
     __threadfence();
-    lsm_reduce_partials(a.partials, (int)gridDim.x, NACC, a.moments);
+    lsm_reduce_partials(a.partials, (int)gridDim.x, NACC, a.moments, s_scratch);
     __syncthreads();
     if (threadIdx.x == 0) {
-      if (a.fit_out) lsm_fit(a.moments, DEG, a.fit_out);
+      if (a.fit_out) lsm_fit<DEG>(a.moments, a.fit_out);
+      *a.done = 0u;
+    }
+  }
+}
+
+// ---- the same pass with TMA-staged streaming ------------------------------------------------------------------
+// ncu on the register-prefetch version (profiles/r1_d_ncu_lsm_pass_1e7.csv): long-scoreboard stalls 11.8 per issue,
+// issue slots 35 % busy, DRAM at 70 % of peak — latency bound: one 16 B load per array per thread in flight is not
+// enough bytes in flight per SM. Here thread 0 of each block issues 1-D bulk copies (cp.async.bulk -> UBLKCP) of
+// whole 512-column chunks of G[t+1], G[t] and z into a kStages-deep ring in shared memory, tracked by one mbarrier per
+// stage; the block consumes chunk i while chunks i+1 .. i+kStages-1 are in flight (12 KB per chunk, 36 KB per block).
+constexpr int kLsmChunk = 2 * kLsmThreads;  // columns per chunk: one double2 per thread per array
+constexpr int kLsmStages = 3;
+
+template <int DEG, bool FIRST, bool LAST, bool TAU>
+__global__ void __launch_bounds__(kLsmThreads) lsm_pass_tma_kernel(const LsmPassArgs a) {
+  constexpr int NACC = lsm_nacc<DEG>();
+  constexpr int NM = 2 * DEG + 1;
+  __shared__ __align__(128) double s_next[kLsmStages][kLsmChunk];
+  __shared__ __align__(128) double s_cur[LAST ? 1 : kLsmStages][LAST ? 2 : kLsmChunk];
+  __shared__ __align__(128) double s_z[FIRST ? 1 : kLsmStages][FIRST ? 2 : kLsmChunk];
+  __shared__ __align__(8) uint64_t s_full[kLsmStages];
+  __shared__ double s_red[NACC][kLsmThreads / 32];
+  __shared__ bool s_last;
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < kLsmStages; ++s) mbar_init(&s_full[s], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  double q[DEG + 1];
+#pragma unroll
+  for (int k = 0; k <= DEG; ++k) q[k] = FIRST ? 0.0 : a.fit_next->q[k];
+  const double cpK = a.cp * a.strike;
+  double acc[NACC];
+#pragma unroll
+  for (int c = 0; c < NACC; ++c) acc[c] = 0.0;
+  int cnt = 0;
+
+  const int64_t neven = a.ncols & ~(int64_t)1;  // the odd last column is handled by one thread below
+  const int64_t nchunks = (neven + kLsmChunk - 1) / kLsmChunk;
+  const int my_chunks = (int64_t)blockIdx.x < nchunks ? (int)((nchunks - 1 - blockIdx.x) / gridDim.x) + 1 : 0;
+  const bool rev = a.reverse != 0;  // alternate direction: start where the previous pass ended (still in L2)
+  auto chunk_of = [&](int i) {
+    const int64_t c = (int64_t)blockIdx.x + (int64_t)i * gridDim.x;
+    return rev ? nchunks - 1 - c : c;
+  };
+  const uint64_t pol_first = l2_policy_evict_first();
+  auto issue = [&](int i) {  // thread 0 only
+    const int s = i % kLsmStages;
+    const int64_t c0 = chunk_of(i) * kLsmChunk;
+    const int64_t ncol = neven - c0 < kLsmChunk ? neven - c0 : kLsmChunk;
+    const uint32_t bytes = (uint32_t)ncol * 8u;
+    mbar_arrive_expect_tx(&s_full[s], bytes * (1u + (LAST ? 0u : 1u) + (FIRST ? 0u : 1u)));
+    bulk_load_hint(&s_next[s][0], a.S_next + c0, bytes, &s_full[s], pol_first);  // dead after this pass
+    if (!LAST) bulk_load(&s_cur[s][0], a.S_cur + c0, bytes, &s_full[s]);
+    if (!FIRST) bulk_load(&s_z[s][0], a.z + c0, bytes, &s_full[s]);
+  };
+  if (tid == 0) {
+    for (int i = 0; i < kLsmStages && i < my_chunks; ++i) issue(i);
+  }
+  for (int i = 0; i < my_chunks; ++i) {
+    const int s = i % kLsmStages;
+    const uint32_t parity = (uint32_t)(i / kLsmStages) & 1u;
+    const int64_t c0 = chunk_of(i) * kLsmChunk;
+    const int64_t ncol = neven - c0 < kLsmChunk ? neven - c0 : kLsmChunk;
+    const bool mine = 2 * tid < ncol;
+    mbar_wait(&s_full[s], parity);
+    double2 sn = make_double2(0.0, 0.0), sc = sn, zi = sn;
+    if (mine) {
+      sn = reinterpret_cast<const double2 *>(&s_next[s][0])[tid];
+      if (!LAST) sc = reinterpret_cast<const double2 *>(&s_cur[s][0])[tid];
+      if (!FIRST) zi = reinterpret_cast<const double2 *>(&s_z[s][0])[tid];
+    }
+    __syncthreads();  // every thread has taken its columns out of stage s
+    if (tid == 0 && i + kLsmStages < my_chunks) issue(i + kLsmStages);
+    if (mine) {
+      const int64_t col = c0 + 2 * tid;
+      double2 zo;
+      lsm_column<DEG, FIRST, LAST, TAU>(a, q, cpK, sn.x, sc.x, zi.x, col, zo.x, acc, cnt);
+      lsm_column<DEG, FIRST, LAST, TAU>(a, q, cpK, sn.y, sc.y, zi.y, col + 1, zo.y, acc, cnt);
+      *reinterpret_cast<double2 *>(a.z + col) = zo;
+    }
+  }
+  if ((a.ncols & 1) && blockIdx.x == 0 && tid == 0) {
+    const int64_t p = a.ncols - 1;
+    double zo;
+    lsm_column<DEG, FIRST, LAST, TAU>(a, q, cpK, a.S_next[p], LAST ? 0.0 : a.S_cur[p], FIRST ? 0.0 : a.z[p], p, zo, acc, cnt);
+    a.z[p] = zo;
+  }
+  if (LAST) {
+    acc[2] = (double)cnt;
+  } else {
+    acc[0] = (double)cnt;
+    acc[NM + DEG + 1] = (double)cnt;
+  }
+
+  const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+  for (int c = 0; c < NACC; ++c) {
+    double v = acc[c];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if (lane == 0) s_red[c][warp] = v;
+  }
+  __syncthreads();
+  if (tid < NACC) {
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < kLsmThreads / 32; ++w) t += s_red[tid][w];
+    a.partials[(size_t)blockIdx.x * NACC + tid] = t;
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = atomicAdd(a.done, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    lsm_reduce_partials(a.partials, (int)gridDim.x, NACC, a.moments, &s_next[0][0]);  // the ring is idle by now
+    __syncthreads();
+    if (tid == 0) {
+      if (a.fit_out) lsm_fit<DEG>(a.moments, a.fit_out);
       *a.done = 0u;
     }
   }
@@ -383,16 +620,35 @@ __global__ void lsm_transpose_kernel(const double *grid, int64_t stride, int64_t
   }
 }
 
+static const int g_lsm_tma = getenv("HH_LSM_TMA") ? atoi(getenv("HH_LSM_TMA")) : 1;
+
 template <int DEG>
 static cudaError_t launch_pass(const LsmPassArgs &a, int grid, cudaStream_t st) {
-  lsm_pass_kernel<DEG><<<grid, kLsmThreads, 0, st>>>(a);
+  if (g_lsm_tma) {
+    if (a.first && a.last) lsm_pass_tma_kernel<DEG, true, true, false><<<grid, kLsmThreads, 0, st>>>(a);
+    else if (a.first) lsm_pass_tma_kernel<DEG, true, false, false><<<grid, kLsmThreads, 0, st>>>(a);
+    else if (a.last && a.tau) lsm_pass_tma_kernel<DEG, false, true, true><<<grid, kLsmThreads, 0, st>>>(a);
+    else if (a.last) lsm_pass_tma_kernel<DEG, false, true, false><<<grid, kLsmThreads, 0, st>>>(a);
+    else if (a.tau) lsm_pass_tma_kernel<DEG, false, false, true><<<grid, kLsmThreads, 0, st>>>(a);
+    else lsm_pass_tma_kernel<DEG, false, false, false><<<grid, kLsmThreads, 0, st>>>(a);
+    return cudaGetLastError();
+  }
+  // the first pass never writes tau (lsm_fill_tau_kernel already set tau = M)
+  if (a.first && a.last) lsm_pass_kernel<DEG, true, true, false><<<grid, kLsmThreads, 0, st>>>(a);
+  else if (a.first) lsm_pass_kernel<DEG, true, false, false><<<grid, kLsmThreads, 0, st>>>(a);
+  else if (a.last && a.tau) lsm_pass_kernel<DEG, false, true, true><<<grid, kLsmThreads, 0, st>>>(a);
+  else if (a.last) lsm_pass_kernel<DEG, false, true, false><<<grid, kLsmThreads, 0, st>>>(a);
+  else if (a.tau) lsm_pass_kernel<DEG, false, false, true><<<grid, kLsmThreads, 0, st>>>(a);
+  else lsm_pass_kernel<DEG, false, false, false><<<grid, kLsmThreads, 0, st>>>(a);
   return cudaGetLastError();
 }
 
 template <int DEG>
 static int pass_occupancy() {
   int occ = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, lsm_pass_kernel<DEG>, kLsmThreads, 0) != cudaSuccess || occ < 1) occ = 1;
+  cudaError_t e = g_lsm_tma ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, lsm_pass_tma_kernel<DEG, false, false, true>, kLsmThreads, 0)
+                            : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, lsm_pass_kernel<DEG, false, false, true>, kLsmThreads, 0);
+  if (e != cudaSuccess || occ < 1) occ = 1;
   return occ;
 }
 
@@ -407,6 +663,20 @@ static int pass_occupancy_deg(int deg) {
     case 6: return pass_occupancy<6>();
     case 7: return pass_occupancy<7>();
     default: return pass_occupancy<8>();
+  }
+}
+
+static void launch_fit_deg(int deg, const double *moments, LsmFit *out, cudaStream_t st) {
+  switch (deg) {
+    case 0: lsm_fit_kernel<0><<<1, 32, 0, st>>>(moments, out); break;
+    case 1: lsm_fit_kernel<1><<<1, 32, 0, st>>>(moments, out); break;
+    case 2: lsm_fit_kernel<2><<<1, 32, 0, st>>>(moments, out); break;
+    case 3: lsm_fit_kernel<3><<<1, 32, 0, st>>>(moments, out); break;
+    case 4: lsm_fit_kernel<4><<<1, 32, 0, st>>>(moments, out); break;
+    case 5: lsm_fit_kernel<5><<<1, 32, 0, st>>>(moments, out); break;
+    case 6: lsm_fit_kernel<6><<<1, 32, 0, st>>>(moments, out); break;
+    case 7: lsm_fit_kernel<7><<<1, 32, 0, st>>>(moments, out); break;
+    default: lsm_fit_kernel<8><<<1, 32, 0, st>>>(moments, out); break;
   }
 }
 
@@ -533,6 +803,28 @@ int lsm_american(hh_ctx *ctx, const hh_model *m, const hh_sim *s, const hh_payof
   a.done = reinterpret_cast<unsigned int *>(static_cast<char *>(ctx->d_lsm_state.ptr) + done_off);
   a.moments = d_moments;
   const double *G = ctx->d_grid.as<double>();
+  // The cash-flow vector z is read and written by EVERY pass while each date slice is read twice and then dead:
+  // pin z in L2 (persisting access-policy window on the stream; misses and everything else stream through), so a
+  // pass moves 16 B per column through HBM (the two date slices) instead of 32 B.
+  static const int l2_mode = getenv("HH_LSM_L2") ? atoi(getenv("HH_LSM_L2")) : 1;
+  bool l2_window = false;
+  if (l2_mode && ctx->l2_persist_max > 0 && ctx->l2_window_max > 0) {
+    const size_t zbytes = sizeof(double) * (size_t)stride;
+    size_t carve = ctx->l2_persist_max;
+    if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve) == cudaSuccess) {
+      cudaStreamAttrValue attr;
+      memset(&attr, 0, sizeof attr);
+      const size_t win = zbytes < ctx->l2_window_max ? zbytes : ctx->l2_window_max;
+      attr.accessPolicyWindow.base_ptr = ctx->d_cash.ptr;
+      attr.accessPolicyWindow.num_bytes = win;
+      const double ratio = (double)carve / (double)win;
+      attr.accessPolicyWindow.hitRatio = (float)(ratio < 1.0 ? ratio : 1.0);
+      attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+      attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+      l2_window = cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr) == cudaSuccess;
+    }
+    (void)cudaGetLastError();
+  }
   // pass(t), t = M-1 .. 0: decision at t+1 (with fit[t+1]), one-step discount, moments of date t (t >= 1)
   for (int t = M - 1; t >= 0; --t) {
     a.S_next = G + (size_t)(t + 1) * stride;
@@ -548,11 +840,19 @@ int lsm_american(hh_ctx *ctx, const hh_model *m, const hh_sim *s, const hh_payof
     if (exchange) {
       if (comm->allreduce_sum_f64(comm->user, d_moments, (size_t)nacc, (void *)st) != 0)
         return ctx->fail(HH_ERR_COMM, "allreduce callback failed at date %d", t);
-      lsm_fit_kernel<<<1, 32, 0, st>>>(d_moments, degree, d_fits + t);
+      launch_fit_deg(degree, d_moments, d_fits + t, st);
       HH_CUDA(ctx, cudaGetLastError());
     }
   }
   HH_CUDA(ctx, cudaEventRecord(ctx->ev2, st));
+  if (l2_window) {
+    cudaStreamAttrValue attr;
+    memset(&attr, 0, sizeof attr);
+    attr.accessPolicyWindow.num_bytes = 0;  // disables the window
+    (void)cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr);
+    (void)cudaCtxResetPersistingL2Cache();
+    (void)cudaGetLastError();
+  }
 
   // results
   std::vector<double> mom((size_t)nacc);
