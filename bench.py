@@ -30,6 +30,12 @@ sys.path.insert(0, ROOT)
 METRIC = "heston_em_path_steps_per_sec"
 UNIT = "path-steps/s"
 FLOP_PER_PATH_STEP = 25.0  # 17 (SDE update) + 8 (Box-Muller scaling); transcendentals not counted
+# executed by heston_fast2_kernel per path-step, from ncu (profiles/r1_c_ncu_heston_fast_v2.csv): 31.1 FP64 instructions
+# = 51.2 FLOP (DFMA counted twice), 90.6 instructions in all
+EXEC_FLOP_PER_PATH_STEP = 51.16
+EXEC_FP64_INSTR_PER_PATH_STEP = 31.09
+EXEC_INSTR_PER_PATH_STEP = 90.6
+WORKLOAD = "C2 Heston EM European call: 1e8 paths x 252 steps per GPU, f64, NoVarianceReduction"
 CARR_MADAN_C2 = 9.242536279428904  # oracle/anchors.py heston_price(100,100,.03,1,.04,2,.04,.3,-.7), CarrMadan(1, 32)
 
 
@@ -131,8 +137,8 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt_s / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "C2 Heston EM European call, 252 steps, f64 (CPU, bounded sample)",
-                   "paths_per_step": sample_paths, "n_steps": args.nsteps},
+        "config": {"workload": WORKLOAD, "paths_per_gpu": args.paths, "n_steps": args.nsteps,
+                   "sample": f"each step prices {sample_paths} of the workload's trajectories x {args.nsteps} steps on the host cores"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{args.steps} x {sample_paths} paths x {args.nsteps} steps, OpenMP over all host threads; "
                                    "C restatement of the reference arithmetic (the Julia package cannot run here)"},
@@ -290,8 +296,8 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": per_launch_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": args.precision, "data": "synthetic",
-            "config": {"workload": "C2 Heston EM European call: 1e8 paths x 252 steps per GPU, f64, NoVarianceReduction"
-                       if args.paths == 100_000_000 and args.nsteps == 252 else
+            "config": {"workload": WORKLOAD
+                       if args.paths == 100_000_000 and args.nsteps == 252 and args.precision == "f64" else
                        f"Heston EM European call: {args.paths} paths x {args.nsteps} steps per GPU",
                        "paths_per_gpu": args.paths, "n_steps": args.nsteps, "rng": "Philox4x32-10 in-kernel, Box-Muller f64",
                        "l2": "not applicable: the kernel reads no HBM input (state in registers); every step uses a new seed",
@@ -300,8 +306,18 @@ def main():
                          "frac": achieved_tflops / fp64_peak, "traffic": None,
                          "peak_source": "DFMA-chain microbenchmark run by this bench (hh_bench_fp64_peak); "
                                         "MEASURED_PEAKS.json has no FP64 entry",
-                         "convention": "algorithmic 25 FLOP per path-step (log/sincos/sqrt expansions NOT counted); "
-                                       "executed-FP64 fraction from ncu is in profiles/"},
+                         "convention": "algorithmic 25 FLOP per path-step (log/sincos/sqrt expansions NOT counted)",
+                         "executed": {
+                             "tflops": EXEC_FLOP_PER_PATH_STEP * float(args.paths) * args.nsteps / (per_launch_ms * 1e-3) * 1e-12,
+                             "frac_of_fp64_peak": EXEC_FLOP_PER_PATH_STEP * float(args.paths) * args.nsteps
+                             / (per_launch_ms * 1e-3) * 1e-12 / fp64_peak,
+                             "flop_per_path_step": EXEC_FLOP_PER_PATH_STEP,
+                             "source": "ncu op_{dadd,dmul,dfma} counts of this kernel, profiles/r1_c_ncu_heston_fast_v2.csv"},
+                         "limiter": "SMSP dispatch port: an FP64 instruction holds it 2-3 cycles (profiles/"
+                                    "r1_b_ubench_issue_pipes.txt), so cycles per warp-step ~ 2.2 x 31 FP64 + 1.1 x 60 other; "
+                                    "measured 148 (DESIGN.md section 4)"} if args.precision == "f64" else
+            {"bound": "fp32+sfu", "achieved": achieved_tflops, "peak": None, "unit": "TFLOP/s", "frac": None, "traffic": None,
+             "convention": "algorithmic 25 FLOP per path-step; f32 fast mode (MUFU-bound), no FP32 peak measured"},
             "e2e": e2e, "gpu_launches": 2 * K, "clocks": clocks, "f32_fast_mode": f32,
             "check": {"price": last.price, "std_error": last.std_error, "carr_madan": CARR_MADAN_C2,
                       "n_nonfinite": last.n_nonfinite, "e2e_price": e2e_price},
