@@ -117,7 +117,13 @@ SYMBOLS = {
                                  C.c_int, _dp]),
     "hh_bk_variance": (C.c_int, [C.c_void_p, C.POINTER(hh_model), C.c_double, _dp, C.c_int, C.c_uint64, _dp]),
     "hh_bk_last_stats": (C.c_int, [C.c_void_p, _dp]),
+    "hh_peer_export": (C.c_int, [C.c_void_p, C.POINTER(C.c_ubyte)]),
+    "hh_peer_connect": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_ubyte)]),
+    "hh_peer_disconnect": (C.c_int, [C.c_void_p]),
 }
+HH_IPC_HANDLE_BYTES = 64
+HH_MAX_PEERS = 16
+HH_ERR_PEER_TIMEOUT = 4
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libhedgehog_mc.so")
 _lib = None

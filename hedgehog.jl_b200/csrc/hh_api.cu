@@ -98,12 +98,75 @@ int hh_destroy(hh_ctx *ctx) {
                               &ctx->d_cash,     &ctx->d_tau,      &ctx->d_lsm_partials, &ctx->d_lsm_state,
                               &ctx->d_misc,     &ctx->d_counters};
   for (auto *b : bufs) b->release();
+  for (int q = 0; q < ctx->peer_world; ++q)
+    if (q != ctx->peer_rank && ctx->peer_mail[q]) cudaIpcCloseMemHandle(ctx->peer_mail[q]);
+  if (ctx->mailbox) cudaFree(ctx->mailbox);
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
   cudaEventDestroy(ctx->ev0);
   cudaEventDestroy(ctx->ev1);
   cudaEventDestroy(ctx->ev2);
   cudaStreamDestroy(ctx->own_stream);
   delete ctx;
+  return HH_OK;
+}
+
+// mailbox layout (doubles): [parity 2][rank HH_MAX_PEERS][kMailSlot] payload, then flags [parity 2][rank] as uint64
+static constexpr size_t kMailSlot = 32;
+static constexpr size_t kMailBytes = 2 * HH_MAX_PEERS * kMailSlot * sizeof(double) + 2 * HH_MAX_PEERS * sizeof(unsigned long long);
+
+int hh_peer_export(hh_ctx *ctx, unsigned char handle[HH_IPC_HANDLE_BYTES]) {
+  if (!ctx || !handle) return HH_ERR_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  static_assert(sizeof(cudaIpcMemHandle_t) <= HH_IPC_HANDLE_BYTES, "IPC handle size");
+  HH_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (!ctx->mailbox) {
+    HH_CUDA(ctx, cudaMalloc(&ctx->mailbox, kMailBytes));
+    HH_CUDA(ctx, cudaMemset(ctx->mailbox, 0, kMailBytes));
+    HH_CUDA(ctx, cudaDeviceSynchronize());
+  }
+  cudaIpcMemHandle_t h;
+  HH_CUDA(ctx, cudaIpcGetMemHandle(&h, ctx->mailbox));
+  memset(handle, 0, HH_IPC_HANDLE_BYTES);
+  memcpy(handle, &h, sizeof h);
+  return HH_OK;
+}
+
+int hh_peer_connect(hh_ctx *ctx, int rank, int world, const unsigned char *handles) {
+  if (!ctx || !handles) return HH_ERR_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (world < 1 || world > HH_MAX_PEERS || rank < 0 || rank >= world)
+    return ctx->fail(HH_ERR_ARG, "peer connect: rank %d / world %d out of range (max %d)", rank, world, HH_MAX_PEERS);
+  if (!ctx->mailbox) return ctx->fail(HH_ERR_ARG, "peer connect: call hh_peer_export first");
+  HH_CUDA(ctx, cudaSetDevice(ctx->device));
+  for (int q = 0; q < world; ++q) {
+    if (q == rank) {
+      ctx->peer_mail[q] = ctx->mailbox;
+      continue;
+    }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handles + (size_t)q * HH_IPC_HANDLE_BYTES, sizeof h);
+    void *p = nullptr;
+    HH_CUDA(ctx, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    ctx->peer_mail[q] = p;
+  }
+  ctx->peer_rank = rank;
+  ctx->peer_world = world;
+  ctx->peer_epoch = 0;
+  return HH_OK;
+}
+
+int hh_peer_disconnect(hh_ctx *ctx) {
+  if (!ctx) return HH_ERR_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (int q = 0; q < ctx->peer_world; ++q) {
+    if (q != ctx->peer_rank && ctx->peer_mail[q]) cudaIpcCloseMemHandle(ctx->peer_mail[q]);
+    ctx->peer_mail[q] = nullptr;
+  }
+  ctx->peer_world = 1;
+  ctx->peer_rank = 0;
+  (void)cudaGetLastError();
   return HH_OK;
 }
 

@@ -62,6 +62,11 @@ struct hh_ctx {
 
   hh::DeviceBuffer d_payoffs, d_partials, d_final, d_terminal, d_seeds, d_normals, d_tangents;
   hh::DeviceBuffer d_grid, d_cash, d_tau, d_lsm_partials, d_lsm_state, d_misc, d_counters;
+  // peer mailboxes (hh_peer_*): own buffer + the peers' buffers mapped through CUDA IPC
+  void *mailbox = nullptr;
+  void *peer_mail[HH_MAX_PEERS] = {};
+  int peer_rank = 0, peer_world = 1;
+  unsigned long long peer_epoch = 0;  // advances identically on every rank (one per exchanged date)
   double bk_stats[5] = {0, 0, 0, 0, 0};
   void *h_pinned = nullptr;  // small pinned staging area for results
   size_t h_pinned_cap = 0;

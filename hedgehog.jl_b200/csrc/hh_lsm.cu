@@ -148,7 +148,20 @@ struct LsmPassArgs {
   unsigned int *done;      // arrival counter of the blocks of this pass
   double *moments;         // [nacc] sums over all blocks, written by the last block
   LsmFit *fit_out;         // nullable: where the last block writes the fit of date t (single-GPU form)
+  // peer exchange in the kernel tail (hh_peer_*): world > 1 switches it on
+  int px_world, px_rank;
+  unsigned long long px_epoch;  // unique per exchanged date, identical on every rank; parity selects the slot
+  double *px_mail[HH_MAX_PEERS];
+  int *px_error;                // set to 1 if a peer's contribution did not arrive in time
 };
+
+constexpr int kMailSlot = 32;  // doubles per (parity, rank) slot; flags follow the payload (see hh_api.cu)
+__device__ __forceinline__ double *mail_payload(double *mail, int parity, int rank) {
+  return mail + ((size_t)parity * HH_MAX_PEERS + rank) * kMailSlot;
+}
+__device__ __forceinline__ unsigned long long *mail_flag(double *mail, int parity, int rank) {
+  return reinterpret_cast<unsigned long long *>(mail + 2 * HH_MAX_PEERS * kMailSlot) + parity * HH_MAX_PEERS + rank;
+}
 
 template <int DEG>
 __device__ __forceinline__ double clenshaw(const double *c, double u) {
@@ -362,6 +375,90 @@ __global__ void lsm_fit_kernel(const double *moments, LsmFit *out) {
   if (threadIdx.x == 0) lsm_fit<DEG>(moments, out);
 }
 
+// Tail of a pass: block reduction -> per-block partials -> the block that arrives last sums all partials in a fixed
+// order, exchanges them with the peer GPUs if there are any, and fits the date's polynomial.
+// Peer exchange (one process per GPU, mailboxes mapped through CUDA IPC): the local sums go into slot [parity][my rank]
+// of EVERY rank's mailbox (plain stores to the mapped peer pointers, i.e. over NVLink), a system-scope fence, then
+// the release flag; the block waits for the flags of all ranks in its own mailbox and adds the slots in rank order,
+// so all ranks hold bit-identical global sums. Two parities alternate per date: a rank can only be one date ahead of
+// a peer (it needs the peer's sums to finish a date), so the slot written at date d+2 has been consumed.
+template <int DEG, bool LAST>
+__device__ __forceinline__ void lsm_pass_tail(const LsmPassArgs &a, double *acc, int cnt, double (*s_red)[kLsmThreads / 32],
+                                              double *scratch, bool *s_last) {
+  constexpr int NACC = lsm_nacc<DEG>();
+  constexpr int NM = 2 * DEG + 1;
+  const int tid = threadIdx.x;
+  // the counts were kept on the integer pipe: m[0] = sum of the indicator, and the trailing count slot
+  if (LAST) {
+    acc[2] = (double)cnt;
+  } else {
+    acc[0] = (double)cnt;
+    acc[NM + DEG + 1] = (double)cnt;
+  }
+  const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+  for (int c = 0; c < NACC; ++c) {
+    double v = acc[c];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if (lane == 0) s_red[c][warp] = v;
+  }
+  __syncthreads();
+  if (tid < NACC) {
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < kLsmThreads / 32; ++w) t += s_red[tid][w];
+    a.partials[(size_t)blockIdx.x * NACC + tid] = t;
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) *s_last = atomicAdd(a.done, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!*s_last) return;
+  __threadfence();
+  lsm_reduce_partials(a.partials, (int)gridDim.x, NACC, a.moments, scratch);
+  __syncthreads();
+  if (a.px_world > 1) {
+    const int parity = (int)(a.px_epoch & 1ull);
+    if (tid < NACC) {
+      const double v = a.moments[tid];
+      for (int qq = 0; qq < a.px_world; ++qq) mail_payload(a.px_mail[qq], parity, a.px_rank)[tid] = v;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid < a.px_world) {
+      unsigned long long *f = mail_flag(a.px_mail[tid], parity, a.px_rank);
+      asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(a.px_epoch) : "memory");
+      // wait for rank `tid`'s flag in MY mailbox (bounded: ~2 s at 2 GHz, then flag the error and go on)
+      const unsigned long long *mine = mail_flag(a.px_mail[a.px_rank], parity, tid);
+      const long long t0 = clock64();
+      unsigned long long seen = 0;
+      bool dead = *reinterpret_cast<volatile int *>(a.px_error) != 0;
+      while (!dead) {
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(mine) : "memory");
+        if (seen >= a.px_epoch) break;
+        if (clock64() - t0 > 4000000000ll) {
+          *a.px_error = 1;
+          dead = true;
+        }
+        __nanosleep(64);
+      }
+    }
+    __syncthreads();
+    if (tid < NACC) {
+      double v = 0.0;
+      for (int qq = 0; qq < a.px_world; ++qq)
+        v += *reinterpret_cast<volatile double *>(mail_payload(a.px_mail[a.px_rank], parity, qq) + tid);
+      a.moments[tid] = v;
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    if (a.fit_out) lsm_fit<DEG>(a.moments, a.fit_out);
+    *a.done = 0u;
+  }
+}
+
 template <int DEG, bool FIRST, bool LAST, bool TAU>
 __global__ void __launch_bounds__(kLsmThreads) lsm_pass_kernel(const LsmPassArgs a) {
   constexpr int NACC = lsm_nacc<DEG>();
@@ -427,43 +524,7 @@ __global__ void __launch_bounds__(kLsmThreads) lsm_pass_kernel(const LsmPassArgs
     lsm_column<DEG, FIRST, LAST, TAU>(a, q, cpK, a.S_next[p], LAST ? 0.0 : a.S_cur[p], FIRST ? 0.0 : a.z[p], p, zo, acc, cnt);
     a.z[p] = zo;
   }
-  // the counts were kept on the integer pipe: m[0] = sum of the indicator, and the trailing count slot
-  if (LAST) {
-    acc[2] = (double)cnt;
-  } else {
-    acc[0] = (double)cnt;
-    acc[NM + DEG + 1] = (double)cnt;
-  }
-
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-  for (int c = 0; c < NACC; ++c) {
-    double v = acc[c];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-    if (lane == 0) s_red[c][warp] = v;
-  }
-  __syncthreads();
-  if (threadIdx.x < NACC) {
-    double t = 0.0;
-#pragma unroll
-    for (int w = 0; w < kLsmThreads / 32; ++w) t += s_red[threadIdx.x][w];
-    a.partials[(size_t)blockIdx.x * NACC + threadIdx.x] = t;
-  }
-  // the block that finishes last sums the partials of all blocks (fixed order) and fits the date's polynomial
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) s_last = atomicAdd(a.done, 1u) == gridDim.x - 1;
-  __syncthreads();
-  if (s_last) {
-    __threadfence();
-    lsm_reduce_partials(a.partials, (int)gridDim.x, NACC, a.moments, s_scratch);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      if (a.fit_out) lsm_fit<DEG>(a.moments, a.fit_out);
-      *a.done = 0u;
-    }
-  }
+  lsm_pass_tail<DEG, LAST>(a, acc, cnt, s_red, s_scratch, &s_last);
 }
 
 // ---- the same pass with TMA-staged streaming ------------------------------------------------------------------
@@ -553,41 +614,7 @@ __global__ void __launch_bounds__(kLsmThreads) lsm_pass_tma_kernel(const LsmPass
     lsm_column<DEG, FIRST, LAST, TAU>(a, q, cpK, a.S_next[p], LAST ? 0.0 : a.S_cur[p], FIRST ? 0.0 : a.z[p], p, zo, acc, cnt);
     a.z[p] = zo;
   }
-  if (LAST) {
-    acc[2] = (double)cnt;
-  } else {
-    acc[0] = (double)cnt;
-    acc[NM + DEG + 1] = (double)cnt;
-  }
-
-  const int lane = tid & 31, warp = tid >> 5;
-#pragma unroll
-  for (int c = 0; c < NACC; ++c) {
-    double v = acc[c];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-    if (lane == 0) s_red[c][warp] = v;
-  }
-  __syncthreads();
-  if (tid < NACC) {
-    double t = 0.0;
-#pragma unroll
-    for (int w = 0; w < kLsmThreads / 32; ++w) t += s_red[tid][w];
-    a.partials[(size_t)blockIdx.x * NACC + tid] = t;
-  }
-  __threadfence();
-  __syncthreads();
-  if (tid == 0) s_last = atomicAdd(a.done, 1u) == gridDim.x - 1;
-  __syncthreads();
-  if (s_last) {
-    __threadfence();
-    lsm_reduce_partials(a.partials, (int)gridDim.x, NACC, a.moments, &s_next[0][0]);  // the ring is idle by now
-    __syncthreads();
-    if (tid == 0) {
-      if (a.fit_out) lsm_fit<DEG>(a.moments, a.fit_out);
-      *a.done = 0u;
-    }
-  }
+  lsm_pass_tail<DEG, LAST>(a, acc, cnt, s_red, &s_next[0][0] /* the ring is idle by now */, &s_last);
 }
 
 // stopping_info values: v_p = payoff(G[tau_p][p])  (:112, :163-164)
@@ -707,7 +734,11 @@ int lsm_american(hh_ctx *ctx, const hh_model *m, const hh_sim *s, const hh_payof
     return ctx->fail(HH_ERR_UNSUPPORTED, "LSM runs on LognormalDynamics + BlackScholesExact paths (SURVEY Q7)");
   if ((stop_idx == nullptr) != (stop_val == nullptr))
     return ctx->fail(HH_ERR_ARG, "stop_idx and stop_val must be both NULL or both non-NULL");
-  if (comm && !comm->allreduce_sum_f64) return ctx->fail(HH_ERR_ARG, "hh_comm without an allreduce callback");
+  const bool peer_mode = comm && comm->world > 1 && !comm->allreduce_sum_f64;  // in-kernel exchange over peer memory
+  if (comm && comm->world <= 1 && !comm->allreduce_sum_f64) comm = nullptr;
+  if (peer_mode && (ctx->peer_world != comm->world || ctx->peer_rank != comm->rank))
+    return ctx->fail(HH_ERR_ARG, "hh_comm asks for the peer exchange (rank %d of %d) but the context is connected as rank %d of %d "
+                     "(hh_peer_export / hh_peer_connect)", comm->rank, comm->world, ctx->peer_rank, ctx->peer_world);
 
   const int64_t N = s->n_paths;
   const bool anti = s->vr == HH_VR_ANTITHETIC;
@@ -802,6 +833,12 @@ int lsm_american(hh_ctx *ctx, const hh_model *m, const hh_sim *s, const hh_payof
   a.ub = ub;
   a.done = reinterpret_cast<unsigned int *>(static_cast<char *>(ctx->d_lsm_state.ptr) + done_off);
   a.moments = d_moments;
+  a.px_world = 1;
+  if (peer_mode) {
+    a.px_rank = ctx->peer_rank;
+    for (int qq = 0; qq < ctx->peer_world; ++qq) a.px_mail[qq] = static_cast<double *>(ctx->peer_mail[qq]);
+    a.px_error = reinterpret_cast<int *>(static_cast<char *>(ctx->d_lsm_state.ptr) + done_off + 128);  // zeroed above
+  }
   const double *G = ctx->d_grid.as<double>();
   // The cash-flow vector z is read and written by EVERY pass while each date slice is read twice and then dead:
   // pin z in L2 (persisting access-policy window on the stream; misses and everything else stream through), so a
@@ -833,8 +870,12 @@ int lsm_american(hh_ctx *ctx, const hh_model *m, const hh_sim *s, const hh_payof
     a.t_next = t + 1;
     a.first = (t + 1 == M);
     a.last = (t == 0);
-    const bool exchange = t >= 1 && comm && comm->world > 1;
+    const bool exchange = t >= 1 && comm && comm->world > 1 && !peer_mode;  // host-callback (NCCL) form
     a.fit_out = (t >= 1 && !exchange) ? d_fits + t : nullptr;
+    if (peer_mode) {
+      a.px_world = t >= 1 ? ctx->peer_world : 1;  // the last pass only sums prices; the host layer reduces those
+      a.px_epoch = t >= 1 ? ++ctx->peer_epoch : 0;
+    }
     a.reverse = (M - 1 - t) & 1;
     HH_CUDA(ctx, launch_pass_deg(degree, a, grid_pass, st));
     if (exchange) {
@@ -867,7 +908,12 @@ int lsm_american(hh_ctx *ctx, const hh_model *m, const hh_sim *s, const hh_payof
     HH_CUDA(ctx, cudaMemcpyAsync(stop_idx, ctx->d_tau.ptr, sizeof(int32_t) * (size_t)ncols, cudaMemcpyDeviceToHost, st));
     HH_CUDA(ctx, cudaMemcpyAsync(stop_val, ctx->d_misc.ptr, sizeof(double) * (size_t)ncols, cudaMemcpyDeviceToHost, st));
   }
+  int px_error = 0;
+  if (peer_mode)
+    HH_CUDA(ctx, cudaMemcpyAsync(&px_error, static_cast<char *>(ctx->d_lsm_state.ptr) + done_off + 128, sizeof(int),
+                                 cudaMemcpyDeviceToHost, st));
   HH_CUDA(ctx, cudaStreamSynchronize(st));
+  if (px_error) return ctx->fail(HH_ERR_PEER_TIMEOUT, "a peer's regression moments did not arrive within the in-kernel time limit");
   if (spot_paths) {
     // chunks of columns transposed on the device, then copied out (the staging buffer reuses d_terminal)
     const int nrows = M + 1;

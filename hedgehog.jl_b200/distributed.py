@@ -59,3 +59,25 @@ def make_comm(shard, group=None):
     cb = abi.hh_allreduce_fn(_cb)
     comm = abi.hh_comm(cb, None, rank, world)
     return comm, cb
+
+
+def connect_peers(engine, group=None):
+    """Map every rank's LSM mailbox into every other rank's process (CUDA IPC handles exchanged with all_gather_object).
+    After this, solve(::PricingProblem{American}, ::LSM) exchanges the per-date regression moments inside the pass
+    kernel's tail over NVLink instead of calling NCCL 49 times (include/hedgehog_mc.h, hh_peer_*)."""
+    import torch.distributed as dist
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    if world == 1:
+        return None
+    mine = engine.peer_export()
+    handles = [None] * world
+    dist.all_gather_object(handles, mine, group=group)
+    engine.peer_connect(rank, world, handles)
+    dist.barrier(group)  # nobody posts into a mailbox before everybody has mapped it
+    return rank, world
+
+
+def peer_comm(engine):
+    """hh_comm selecting the in-kernel peer exchange (no callback)."""
+    rank, world = engine.peers
+    return abi.hh_comm(abi.hh_allreduce_fn(), None, rank, world)

@@ -149,6 +149,25 @@ class CudaEngine:
         self._pending = None
         return list(res)
 
+    # -- peer mailboxes (multi-GPU LSM without a collective library) ------------------------------------------------
+    peers = None  # (rank, world) once connected
+
+    def peer_export(self) -> bytes:
+        buf = (C.c_ubyte * abi.HH_IPC_HANDLE_BYTES)()
+        self._check(self.lib.hh_peer_export(self.h, buf), "hh_peer_export")
+        return bytes(buf)
+
+    def peer_connect(self, rank: int, world: int, handles: Sequence[bytes]):
+        blob = b"".join(handles)
+        assert len(blob) == world * abi.HH_IPC_HANDLE_BYTES
+        arr = (C.c_ubyte * len(blob)).from_buffer_copy(blob)
+        self._check(self.lib.hh_peer_connect(self.h, int(rank), int(world), arr), "hh_peer_connect")
+        self.peers = (int(rank), int(world))
+
+    def peer_disconnect(self):
+        self._check(self.lib.hh_peer_disconnect(self.h), "hh_peer_disconnect")
+        self.peers = None
+
     # -- tangents --------------------------------------------------------------------------------
     def tangent_sums(self, model, tangents: Sequence[abi.hh_tangent], sim: SimSpec, payoffs):
         """Raw sums [npay, 2 + 2*ntan] and kernel ms."""

@@ -25,8 +25,11 @@ def solve_lsm(prob, method, *, engine=None, shard=None, group=None, stopping_inf
     comm = None
     keep = None
     if reduce is not None:
-        from .distributed import make_comm
-        comm, keep = make_comm(shard, group)
+        from .distributed import make_comm, peer_comm
+        if getattr(eng, "peers", None) == tuple(shard):
+            comm = peer_comm(eng)              # moments exchanged in the pass kernel's tail over peer memory
+        else:
+            comm, keep = make_comm(shard, group)  # NCCL all-reduce through the hh_comm callback
     out, tau, val, paths = eng.lsm_american(mdl, sim, (prob.payoff.strike, prob.payoff.call_put()), method.degree,
                                             step_discount, want_stopping=stopping_info, want_paths=spot_paths, comm=comm)
     del keep

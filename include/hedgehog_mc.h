@@ -70,6 +70,7 @@ extern "C" {
 #define HH_FLAG_Q1_SQRT_MEAN 2u /* marginal_law puts sqrt(alpha) in the mean (montecarlo.jl:302); off = alpha */
 
 typedef struct hh_ctx hh_ctx;
+#define HH_ERR_PEER_TIMEOUT 4   /* a peer's contribution did not arrive within the in-kernel time limit */
 
 /* Model scalars, extracted on the host exactly as the reference does
  * (T: montecarlo.jl:147; r = zero_rate(rate, 0.0): :150; sigma: :151; Heston fields: :201). */
@@ -158,6 +159,20 @@ typedef struct hh_comm {
   void *user;
   int32_t rank, world;
 } hh_comm;
+
+/* ---- peer mailboxes: the multi-GPU exchange of the LSM moments WITHOUT a collective library -------------
+ * One process per GPU. Each context owns a small device "mailbox"; hh_peer_export returns its CUDA IPC handle, the
+ * host exchanges the handles (any transport: MPI, torch.distributed, files) and hh_peer_connect maps every peer's
+ * mailbox into this process. hh_lsm_american then exchanges the per-date regression moments inside the tail of the
+ * pass kernel: the last block of each rank stores its 3*degree+3 sums into every peer's mailbox over NVLink
+ * (st.global to the mapped peer pointer, release flag), waits for the peers' flags and adds the contributions in
+ * rank order — so every rank fits the same polynomial, bit for bit, with no NCCL call and no host round trip.
+ * Select it by passing an hh_comm with allreduce_sum_f64 == NULL and world > 1. */
+#define HH_IPC_HANDLE_BYTES 64
+#define HH_MAX_PEERS 16
+int hh_peer_export(hh_ctx *ctx, unsigned char handle[HH_IPC_HANDLE_BYTES]);
+int hh_peer_connect(hh_ctx *ctx, int rank, int world, const unsigned char *handles /* world x HH_IPC_HANDLE_BYTES */);
+int hh_peer_disconnect(hh_ctx *ctx);
 
 /* ---- lifetime --------------------------------------------------------------------------- */
 int hh_version(void);

@@ -45,21 +45,40 @@ if rank == 0:
 
 put = hh.VanillaOption(100.0, dt.date(2020, 12, 31), hh.American(), hh.Put(), hh.Spot())
 bs = hh.BlackScholesInputs(dt.date(2020, 1, 1), 0.05, 100.0, 0.2)
-lsm = hh.LSM(hh.MonteCarlo(hh.LognormalDynamics(), hh.BlackScholesExact(), hh.SimulationConfig(4_000_000, steps=50, base_seed=12345)), 3)
-dist.barrier()
-torch.cuda.synchronize()
-t0 = time.perf_counter()
-sol = hh.solve(hh.PricingProblem(put, bs), lsm, engine=eng, stopping_info=False)
-torch.cuda.synchronize()
-t1 = time.perf_counter()
+NL = int(os.environ.get("HH_MGPU_LSM_PATHS", "4000000"))
+lsm = hh.LSM(hh.MonteCarlo(hh.LognormalDynamics(), hh.BlackScholesExact(), hh.SimulationConfig(NL, steps=50, base_seed=12345)), 3)
+
+
+def timed_lsm(label):
+    best = None
+    for rep in range(3):
+        dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        sol = hh.solve(hh.PricingProblem(put, bs), lsm, engine=eng, stopping_info=False)
+        torch.cuda.synchronize()
+        wall = (time.perf_counter() - t0) * 1e3
+        if best is None or wall < best[1]:
+            best = (sol, wall)
+    return best
+
+
+sol_nccl, wall_nccl = timed_lsm("nccl")          # hh_comm callback -> stream-ordered NCCL all-reduce, one per date
+from hedgehog_jl_b200 import distributed as hd
+hd.connect_peers(eng)                             # CUDA IPC mailboxes
+sol_peer, wall_peer = timed_lsm("peer")          # exchange inside the pass kernel's tail, no collective library
 if rank == 0:
     one = hh.solve(hh.PricingProblem(put, bs), lsm, engine=eng, shard=(0, 1), stopping_info=False)
-    out["lsm"] = {"sharded": sol.price, "single": one.price, "rel": abs(sol.price - one.price) / one.price,
-                  "sharded_wall_ms": (t1 - t0) * 1e3, "sharded_kernel_ms": sol.stats["kernel_ms"],
-                  "single_kernel_ms": one.stats["kernel_ms"], "n_cols_total": sol.stats["n_cols_total"]}
+    out["lsm"] = {"single": one.price, "single_kernel_ms": one.stats["kernel_ms"], "n_cols_total": sol_peer.stats["n_cols_total"],
+                  "nccl": {"price": sol_nccl.price, "rel": abs(sol_nccl.price - one.price) / one.price, "wall_ms": wall_nccl,
+                           "kernel_ms": sol_nccl.stats["kernel_ms"], "regress_ms": sol_nccl.stats["regress_ms"]},
+                  "peer": {"price": sol_peer.price, "rel": abs(sol_peer.price - one.price) / one.price, "wall_ms": wall_peer,
+                           "kernel_ms": sol_peer.stats["kernel_ms"], "regress_ms": sol_peer.stats["regress_ms"]}}
     print(json.dumps(out))
-    ok = (out["european_f64"]["rel"] < 1e-12 and out["european_f32"]["rel"] < 1e-12 and out["lsm"]["rel"] < 1e-6
+    ok = (out["european_f64"]["rel"] < 1e-12 and out["european_f32"]["rel"] < 1e-12 and out["lsm"]["nccl"]["rel"] < 1e-6
+          and out["lsm"]["peer"]["rel"] < 1e-6
           and all(abs(a - b) <= 1e-10 * max(1.0, abs(b)) for a, b in zip(out["greeks"]["sharded"], out["greeks"]["single"])))
     print("MGPU CHECK", "OK" if ok else "FAILED")
+eng.peer_disconnect()
 dist.barrier()
 dist.destroy_process_group()
