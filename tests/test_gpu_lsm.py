@@ -118,3 +118,25 @@ def test_lsm_edge_cases(cuda, oracle):
         cuda.lsm_american(m, SimSpec(n_paths=10, n_steps=5, scheme=abi.HH_SCHEME_EXACT_STEPS), (100.0, -1.0), 99, 0.99)
     with pytest.raises(NotImplementedError):  # Q7: only the S-space generator is meaningful
         cuda.lsm_american(m, SimSpec(n_paths=10, n_steps=5, scheme=abi.HH_SCHEME_EM), (100.0, -1.0), 3, 0.99)
+
+
+def test_peer_exchange_request_without_connection_is_an_argument_error(cuda):
+    """hh_comm with no callback and world > 1 selects the in-kernel peer exchange, which needs hh_peer_connect first."""
+    m = gbm_model()
+    sim = SimSpec(n_paths=1000, n_steps=5, scheme=abi.HH_SCHEME_EXACT_STEPS, base_seed=1)
+    comm = abi.hh_comm(abi.hh_allreduce_fn(), None, 0, 2)
+    with pytest.raises(ValueError):
+        cuda.lsm_american(m, sim, (100.0, -1.0), 2, 0.99, comm=comm)
+
+
+def test_peer_mailbox_loopback(cuda):
+    """A world of one: export, connect to itself, run (the exchange is skipped), disconnect."""
+    h = cuda.peer_export()
+    assert len(h) == abi.HH_IPC_HANDLE_BYTES and any(h)
+    cuda.peer_connect(0, 1, [h])
+    m = gbm_model()
+    sim = SimSpec(n_paths=2000, n_steps=5, scheme=abi.HH_SCHEME_EXACT_STEPS, base_seed=1)
+    a, *_ = cuda.lsm_american(m, sim, (100.0, -1.0), 2, 0.99, comm=abi.hh_comm(abi.hh_allreduce_fn(), None, 0, 1))
+    b, *_ = cuda.lsm_american(m, sim, (100.0, -1.0), 2, 0.99)
+    assert a.price == b.price
+    cuda.peer_disconnect()
