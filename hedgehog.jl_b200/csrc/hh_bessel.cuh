@@ -8,7 +8,10 @@
 // The LOG is returned directly, so arguments the reference overflows on (|Re z| > 709) stay finite here.
 //
 // Method (w = z reflected into Re w >= 0;  I_nu(z) = exp(+-i pi nu) I_nu(-z) otherwise):
-//   |w| <= 5             ascending series  (w/2)^nu sum_k (w^2/4)^k / (k! Gamma(nu+k+1))      (cancellation <= e^5)
+//   |w| <= 5, or |w| < r_asym and |w| - Re w <= 5
+//                        ascending series  (w/2)^nu sum_k (w^2/4)^k / (k! Gamma(nu+k+1)): the cancellation in the sum is
+//                        I_nu(|w|) / |I_nu(w)| ~ e^{|w| - Re w} <= e^5, whatever |w| (no cancellation at all on the real
+//                        axis), so arguments near the real axis never need the continued fractions (~50x dearer)
 //   |w| >= 20 + nu^2/2   Hankel expansion with BOTH exponentials (DLMF 10.40.5)
 //   otherwise            continued fractions: CF1 for I'/I (modified Lentz), Steed's CF2 for K_mu, K_mu+1, |mu| <= 1/2,
 //                        and the Wronskian I K' - I' K = -1/w (Temme 1975; Thompson & Barnett 1987 for complex w);
@@ -40,26 +43,45 @@ HH_HD cplx operator-(cplx a, double s) { return cplx{a.re - s, a.im}; }
 HH_HD cplx operator-(double s, cplx a) { return cplx{s - a.re, -a.im}; }
 HH_HD cplx conj(cplx a) { return cplx{a.re, -a.im}; }
 HH_HD double cabs2(cplx a) { return a.re * a.re + a.im * a.im; }
-HH_HD double cabs(cplx a) { return hypot(a.re, a.im); }
+HH_HD double cabs(cplx a) { return sqrt(a.re * a.re + a.im * a.im); }  // magnitudes here are far from over/underflow
 HH_HD double carg(cplx a) { return atan2(a.im, a.re); }
+// 1 / x to ~1 ulp for normal-range x: on the device MUFU.RCP64H + two Newton steps instead of the IEEE division
+// sequence (the Bessel series and the complex divisions below are dependent chains of them)
+HH_HD double rcp_fast(double x) {
+#ifdef __CUDA_ARCH__
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double e = fma(-x, y, 1.0);
+  y = fma(y, e, y);
+  e = fma(-x, y, 1.0);
+  return fma(y, e, y);
+#else
+  return 1.0 / x;
+#endif
+}
+
 HH_HD cplx operator/(cplx a, cplx b) {
-  // Smith's algorithm (no spurious overflow)
+  // Smith's algorithm (no spurious overflow), with reciprocals instead of divisions
   if (fabs(b.re) >= fabs(b.im)) {
-    const double r = b.im / b.re, d = b.re + b.im * r;
-    return cplx{(a.re + a.im * r) / d, (a.im - a.re * r) / d};
+    const double r = b.im * rcp_fast(b.re), id = rcp_fast(b.re + b.im * r);
+    return cplx{(a.re + a.im * r) * id, (a.im - a.re * r) * id};
   }
-  const double r = b.re / b.im, d = b.re * r + b.im;
-  return cplx{(a.re * r + a.im) / d, (a.im * r - a.re) / d};
+  const double r = b.re * rcp_fast(b.im), id = rcp_fast(b.re * r + b.im);
+  return cplx{(a.re * r + a.im) * id, (a.im * r - a.re) * id};
 }
 HH_HD cplx operator/(double s, cplx b) { return mk(s) / b; }
-HH_HD cplx operator/(cplx a, double s) { return cplx{a.re / s, a.im / s}; }
+HH_HD cplx operator/(cplx a, double s) {
+  const double is = rcp_fast(s);
+  return cplx{a.re * is, a.im * is};
+}
 HH_HD cplx cexp_(cplx a) {
   const double e = exp(a.re);
   double s, c;
   sincos(a.im, &s, &c);
   return cplx{e * c, e * s};
 }
-HH_HD cplx clog_(cplx a) { return cplx{log(cabs(a)), carg(a)}; }
+// log|a| = log(re^2 + im^2) / 2: no hypot, no sqrt (the arguments here are far from the over/underflow of the squares)
+HH_HD cplx clog_(cplx a) { return cplx{0.5 * log(cabs2(a)), carg(a)}; }
 HH_HD cplx csqrt_(cplx a) {
   // principal branch, Re >= 0
   const double m = cabs(a);
@@ -74,13 +96,13 @@ HH_HD cplx csqrt_(cplx a) {
 
 constexpr double kBesselPi = 3.14159265358979323846;
 
-// ---- ascending series: |w| <= 5 ------------------------------------------------------------------------
+// ---- ascending series: |w| - Re w <= 5, |w| <~ 25 ---------------------------------------------------------------
 HH_HD cplx log_besseli_series(double nu, double lgam_nu1, cplx w) {
   const cplx q = 0.25 * (w * w);
   cplx term = mk(1.0), sum = mk(1.0);
 #pragma unroll 1
-  for (int k = 1; k < 60; ++k) {
-    term = term * q / ((double)k * (nu + (double)k));
+  for (int k = 1; k < 100; ++k) {
+    term = (term * q) * rcp_fast((double)k * (nu + (double)k));
     sum = sum + term;
     if (cabs2(term) < 1e-34 * cabs2(sum)) break;
   }
@@ -93,17 +115,17 @@ HH_HD cplx log_besseli_asymptotic(double nu, cplx w) {
   const double mu4 = 4.0 * nu * nu;
   const cplx iw = 1.0 / w;
   cplx t = mk(1.0), s1 = mk(1.0), s2 = mk(1.0);
-  double last = 1.0;
+  double last = 1.0;  // |t|^2 of the previous term
 #pragma unroll 1
   for (int k = 1; k < 60; ++k) {
     const double odd = (double)(2 * k - 1);
-    t = t * iw * ((mu4 - odd * odd) / (8.0 * (double)k));  // a_k / w^k
-    const double m = cabs(t);
+    t = (t * iw) * ((mu4 - odd * odd) * rcp_fast(8.0 * (double)k));  // a_k / w^k
+    const double m = cabs2(t);
     if (m > last) break;  // the expansion has started to diverge
     last = m;
     s1 = (k & 1) ? s1 - t : s1 + t;
     s2 = s2 + t;
-    if (m < 1e-17) break;
+    if (m < 1e-34) break;
   }
   // I = e^w / sqrt(2 pi w) [ s1 + e^{-2w +- i pi (nu + 1/2)} s2 ],  + for Im w >= 0
   const double sgn = w.im >= 0.0 ? 1.0 : -1.0;
@@ -208,7 +230,7 @@ HH_HD cplx log_besseli(const BesselOrder &o, cplx z) {
   }
   const double aw = cabs(w);
   cplx r;
-  if (aw <= 5.0) {
+  if (aw <= 5.0 || (aw < o.r_asym && aw - w.re <= 5.0)) {
     r = log_besseli_series(nu, o.lgam_nu1, w);
   } else if (aw >= o.r_asym) {
     r = log_besseli_asymptotic(nu, w);
@@ -255,11 +277,12 @@ HH_HD BkCf bk_cf_init(const BkParams &p, double V0, double VT) {
 // Phi(a) with the unwrapped angle of z_gamma carried in theta_prev (NaN = first evaluation), heston.jl:184-212.
 HH_HD cplx bk_chf(const BkParams &p, const BkCf &it, double a, double &theta_prev) {
   const cplx g = csqrt_(cplx{p.kappa * p.kappa, -2.0 * p.xi2 * a});        // gamma            :190
-  const cplx eg = cexp_(-(p.tau * g));
+  const cplx egh = cexp_((-0.5 * p.tau) * g);  // e^{-g tau / 2}
+  const cplx eg = egh * egh;
   const cplx omeg = 1.0 - eg;
   const cplx zeta_g = omeg / g;                                              // :191
   const cplx eta_g = g * (1.0 + eg) / omeg;                                   // :192
-  const cplx zg = (it.sv * 4.0) * g * cexp_((-0.5 * p.tau) * g) / p.xi2 / omeg;  // nu_gamma         :193
+  const cplx zg = (it.sv * 4.0) * g * egh / p.xi2 / omeg;                       // nu_gamma         :193
   const double th = carg(zg);                                                 // :198
   double thu = th;
   if (!(theta_prev != theta_prev)) {                                          // :199-205

@@ -181,7 +181,7 @@ __device__ BkInversion bk_sample_integral(const BkParams &p, double V0, double V
     const cplx phi = bk_chf(p, it, h * (double)j, th);
     tb.set(j - 1, (2.0 / kBesselPi) * phi.re / (double)j);
     J = j;
-    if (cabs(phi) / (double)j < stop) break;
+    if (cabs2(phi) < (stop * (double)j) * (stop * (double)j)) break;  // |phi| / j < stop
   }
   r.J = J;
   // inverse_cdf :105-135
