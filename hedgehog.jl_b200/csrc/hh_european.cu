@@ -741,6 +741,173 @@ __global__ void __launch_bounds__(kThreads, MINB) heston_f32_kernel(const EuroAr
   }
 }
 
+// ---- Heston Euler-Maruyama with pathwise tangents, specialised (config C5) ---------------------------------------
+// european_kernel<K_HESTON_EM, Dual<8>> pushes a full dual number through every operation: 255 registers, 8 warps per
+// SM, and most of the arithmetic multiplies structural zeros. Here the tangent recursion of the step is written out:
+//     dK2_p = dv_p (1 - kappa dt 1{v>0}) + A_p - B_p v+          A_p = dt (dkappa_p theta + kappa dtheta_p), B_p = dt dkappa_p
+//     ds_p  = 1{arg>0} d(arg)_p / (2 s)                          arg = K2 (split step) or v
+//     dx_p' = dx_p - (dt/2) 1{v>0} dv_p + ds_p W1 + s (da11_p z1 + da12_p z2)        (+ dt dr_p, added once at expiry)
+//     dv_p' = dK2_p + ds_p W2 + s (db21_p z1 + db22_p z2)         W2 = xi dW2, db2x_p = dxi_p a2x + xi da2x_p
+// with the same rules as ForwardDiff (max(x,0) and sqrt pass a tangent iff their argument is positive): 10 FP64
+// instructions per direction and step, every per-direction constant a constant-bank operand. Directions that never touch
+// the variance (only dS0 and dr non-zero: delta, rho) are "trivial": dx_p is the constant dS0_p/S0 + T dr_p, no per-step
+// work. Kernel order of the directions: NF full ones first, then the trivial ones; the host permutes the sums back.
+struct HestonTanConsts {
+  double dx0[kMaxTan], dv0[kMaxTan], drift[kMaxTan];  // dS0/S0, dV0, T dr
+  double A[kMaxTan], B[kMaxTan], da11[kMaxTan], da12[kMaxTan], db21[kMaxTan], db22[kMaxTan];
+};
+
+// 1 / sqrt(d) to full double precision: MUFU.RSQ64H seed, two Newton steps
+__device__ __forceinline__ double rsqrt_full(double d) {
+  double y = rsqrt_seed(d);
+  double e = fma(-d * y, y, 1.0);
+  y = fma(y * e, fma(e, 0.375, 0.5), y);
+  e = fma(-d * y, y, 1.0);
+  return fma(y * e, 0.5, y);
+}
+
+template <bool SPLIT, int NF>
+__device__ __forceinline__ void heston_tangent_step(const HestonFolded &f, const HestonTanConsts &c, double one_m_kdt,
+                                                    double &x, double &v, double *dx, double *dv, double z1, double z2,
+                                                    double W1, double W2) {
+  const bool ind = __double2hiint(v) > 0;  // v > 0 (hi word test: exact unless v is a positive denormal)
+  const double vplus = max0_hi(v);
+  const double K1 = fma(f.neg_half_dt, vplus, x);
+  const double K2 = fma(f.neg_kdt, vplus, v + f.ktdt);
+  const double arg = SPLIT ? K2 : v;
+  const bool pos = __double2hiint(arg) > 0;
+  const double y = rsqrt_full(max_tiny_hi(arg));
+  const double s = pos ? arg * y : 0.0;     // sqrt(max(arg, 0))
+  const double hs = pos ? 0.5 * y : 0.0;    // d sqrt / d arg
+  const double cind = ind ? one_m_kdt : 1.0;
+  const double chalf = ind ? f.neg_half_dt : 0.0;
+  const double sz1 = s * z1, sz2 = s * z2;
+#pragma unroll
+  for (int p = 0; p < NF; ++p) {
+    const double aP = fma(dv[p], cind, fma(-c.B[p], vplus, c.A[p]));
+    const double g = (SPLIT ? aP : (ind ? dv[p] : 0.0)) * hs;
+    dx[p] = fma(c.da11[p], sz1, fma(c.da12[p], sz2, fma(g, W1, fma(dv[p], chalf, dx[p]))));
+    dv[p] = fma(c.db21[p], sz1, fma(c.db22[p], sz2, fma(g, W2, aP)));
+  }
+  x = fma(s, W1, K1);
+  v = fma(s, W2, K2);
+}
+
+template <bool ANTI, bool SPLIT, int NF, int P>
+__global__ void __launch_bounds__(kThreads) heston_tangent_kernel(const EuroArgs a, const HestonTanConsts c) {
+  constexpr int NACC = 3 + 2 * P;
+  constexpr int NV = 1 + P;
+  constexpr int NSIDE = ANTI ? 2 : 1;
+  constexpr int STAGE = NV * NSIDE * kThreads;
+  constexpr int RED = NACC * kThreads;
+  __shared__ double smem[STAGE > RED ? STAGE : RED];
+  __shared__ FastNormalTables s_tables;
+  load_fast_tables(&s_tables);
+  __syncthreads();
+  const int tid = threadIdx.x;
+  const int KP = 1 << a.kp_log2;
+  const int k = tid & (KP - 1);
+  const int g = tid >> a.kp_log2;
+  const int G = kThreads >> a.kp_log2;
+  double strike = 0.0, cp = 0.0;
+  if (k < a.npay) {
+    strike = a.payoffs[k].strike;
+    cp = a.payoffs[k].cp;
+  }
+  double acc[NACC];
+#pragma unroll
+  for (int q = 0; q < NACC; ++q) acc[q] = 0.0;
+  const int M = a.n_steps;
+  const double drift_total = (double)M * a.f.rdt;
+  const double one_m_kdt = 1.0 + a.f.neg_kdt;
+
+  for (int64_t base = (int64_t)blockIdx.x * kThreads; base < a.n; base += (int64_t)gridDim.x * kThreads) {
+    const int64_t i = base + tid;
+    const int64_t ic = i < a.n ? i : a.n - 1;
+    uint64_t key = a.base_seed, idx = (uint64_t)(a.path_offset + ic);
+    if (a.seeds) {
+      key = a.seeds[ic];
+      idx = 0;
+    }
+    double xp = a.p.x0, vp = a.p.v0, xm = a.p.x0, vm = a.p.v0;
+    double dxp[NF > 0 ? NF : 1], dvp[NF > 0 ? NF : 1], dxm[NF > 0 ? NF : 1], dvm[NF > 0 ? NF : 1];
+#pragma unroll
+    for (int p = 0; p < NF; ++p) {
+      dxp[p] = dxm[p] = c.dx0[p];
+      dvp[p] = dvm[p] = c.dv0[p];
+    }
+#pragma unroll 1
+    for (int n = 0; n < M; ++n) {
+      const u32x4 w = philox4x32_10((uint32_t)idx, (uint32_t)(idx >> 32), (uint32_t)n, 0u, (uint32_t)key, (uint32_t)(key >> 32));
+      double z1, z2;
+      fast_normal_pair(&s_tables, w.x, w.y, w.z, w.w, z1, z2);
+      const double W1 = fma(a.p.a12, z2, a.p.a11 * z1);
+      const double W2 = fma(a.f.b22, z2, a.f.b21 * z1);  // xi dW2
+      heston_tangent_step<SPLIT, NF>(a.f, c, one_m_kdt, xp, vp, dxp, dvp, z1, z2, W1, W2);
+      if (ANTI) heston_tangent_step<SPLIT, NF>(a.f, c, one_m_kdt, xm, vm, dxm, dvm, -z1, -z2, -W1, -W2);
+    }
+    const double Sp = exp(xp + drift_total);
+    const double Sm = ANTI ? exp(xm + drift_total) : 0.0;
+    if (a.terminal && i < a.n) {
+      a.terminal[i] = Sp;
+      if (ANTI) a.terminal[a.n + i] = Sm;
+    }
+    smem[tid] = Sp;
+    if (ANTI) smem[NV * kThreads + tid] = Sm;
+#pragma unroll
+    for (int q = 0; q < P; ++q) {  // dS_q = S d(log S)_q
+      const double tp_ = q < NF ? dxp[q < NF ? q : 0] + c.drift[q] : c.dx0[q] + c.drift[q];
+      smem[(1 + q) * kThreads + tid] = Sp * tp_;
+      if (ANTI) {
+        const double tm_ = q < NF ? dxm[q < NF ? q : 0] + c.drift[q] : c.dx0[q] + c.drift[q];
+        smem[(NV + 1 + q) * kThreads + tid] = Sm * tm_;
+      }
+    }
+    __syncthreads();
+    const int64_t rem = a.n - base;
+    const int nvalid = rem < kThreads ? (int)rem : kThreads;
+    if (k < a.npay) {
+      for (int j = g; j < nvalid; j += G) {
+        const double sp = smem[j];
+        const double ep = cp * (sp - strike);
+        double pay = fmax(ep, 0.0);  // payoffs.jl:154-156
+        const double ip = ep > 0.0 ? cp : 0.0;
+        bool bad = !isfinite(sp);
+        double im = 0.0;
+        if (ANTI) {
+          const double sm = smem[NV * kThreads + j];
+          const double em = cp * (sm - strike);
+          pay = 0.5 * (pay + fmax(em, 0.0));  // reduce_payoffs montecarlo.jl:430-432
+          im = em > 0.0 ? cp : 0.0;
+          bad = bad || !isfinite(sm);
+        }
+        acc[0] += pay;
+        acc[1] = fma(pay, pay, acc[1]);
+        if (k == 0 && bad) acc[2] += 1.0;
+#pragma unroll
+        for (int q = 0; q < P; ++q) {
+          double dpay = ip * smem[(1 + q) * kThreads + j];  // cp 1{cp(S-K)>0} dS
+          if (ANTI) dpay = 0.5 * (dpay + im * smem[(NV + 1 + q) * kThreads + j]);
+          acc[3 + q] += dpay;
+          acc[3 + P + q] = fma(dpay, dpay, acc[3 + P + q]);
+        }
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int q = 0; q < NACC; ++q) smem[q * kThreads + tid] = acc[q];
+  __syncthreads();
+  if (tid < a.npay) {
+    double *out = a.partials + ((size_t)blockIdx.x * a.npay + tid) * NACC;
+    for (int q = 0; q < NACC; ++q) {
+      double t = 0.0;
+      for (int gg = 0; gg < G; ++gg) t += smem[q * kThreads + (gg << a.kp_log2) + tid];
+      out[q] = t;
+    }
+  }
+}
+
 // Payoff sums from terminal spots that another kernel produced (Broadie-Kaya): the same payoff transpose as above.
 __global__ void __launch_bounds__(kThreads) terminal_payoff_kernel(const double *__restrict__ terminal, int64_t n,
                                                                    const hh_payoff *__restrict__ payoffs, int npay,
@@ -938,7 +1105,13 @@ static cudaError_t launch_fast_v(const EuroArgs &a, int variant, int sm_count, c
     case 7: return launch_fast2_one<ANTI, SPLIT, UKEY, 1, 1024, 1>(a, sm_count, st, nb, q);  // same, one block per SM
     case 8: return launch_fast2_one<ANTI, SPLIT, UKEY, 2, 512, 1>(a, sm_count, st, nb, q);   // 16 warps, one block
     case 9: return launch_fast2_one<ANTI, SPLIT, UKEY, 1, 768, 1>(a, sm_count, st, nb, q);   // 24 warps, <= 80 registers
-    default: return launch_fast2_one<ANTI, SPLIT, UKEY, 2, 256, 2>(a, sm_count, st, nb, q);
+    case 10: return launch_fast2_one<ANTI, SPLIT, UKEY, 2, 256, 2>(a, sm_count, st, nb, q);
+    default:
+      // measured on B200 at 1e8 x 252: 1024 threads x ILP 1 99.4 ms, 256 x ILP 2 100.9 ms, 512 x ILP 1 102.5 ms (all within
+      // 3 %: the kernel is dispatch-bound, occupancy hardly matters); small jobs keep the 256-thread blocks so that
+      // every SM gets work
+      if (a.n >= (int64_t)sm_count * 1024 * 4) return launch_fast2_one<ANTI, SPLIT, UKEY, 1, 1024, 1>(a, sm_count, st, nb, q);
+      return launch_fast2_one<ANTI, SPLIT, UKEY, 2, 256, 2>(a, sm_count, st, nb, q);
   }
 }
 
@@ -1001,6 +1174,45 @@ static cudaError_t launch_f32(const EuroArgs &a, bool anti, int sm_count, cudaSt
     else { if (ukey) { HH_F32(false, false, true) } else { HH_F32(false, false, false) } }
   }
 #undef HH_F32
+}
+
+template <bool ANTI, bool SPLIT, int NF, int P>
+static cudaError_t launch_tangent_one(const EuroArgs &a, const HestonTanConsts &c, int sm_count, cudaStream_t st, int *nblocks,
+                                      bool query_only) {
+  auto kern = heston_tangent_kernel<ANTI, SPLIT, NF, P>;
+  int occ = 0;
+  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, 0);
+  if (e != cudaSuccess) return e;
+  if (occ < 1) occ = 1;
+  const int64_t batches = (a.n + kThreads - 1) / kThreads;
+  int64_t grid = (int64_t)sm_count * occ;
+  if (grid > batches) grid = batches;
+  *nblocks = (int)grid;
+  if (query_only) return cudaSuccess;
+  kern<<<(unsigned)grid, kThreads, 0, st>>>(a, c);
+  return cudaGetLastError();
+}
+
+// nf: full directions (rounded up to an instantiated count), P: padded direction count (1, 2, 4, 8)
+template <bool ANTI, bool SPLIT>
+static cudaError_t launch_tangent_as(const EuroArgs &a, const HestonTanConsts &c, int nf, int P, int sm_count, cudaStream_t st,
+                                     int *nb, bool q) {
+#define HH_TAN(NF_, P_) return launch_tangent_one<ANTI, SPLIT, NF_, P_>(a, c, sm_count, st, nb, q)
+  switch (P) {
+    case 1: if (nf == 0) HH_TAN(0, 1); HH_TAN(1, 1);
+    case 2: if (nf == 0) HH_TAN(0, 2); if (nf == 1) HH_TAN(1, 2); HH_TAN(2, 2);
+    case 4: if (nf == 0) HH_TAN(0, 4); if (nf <= 2) HH_TAN(2, 4); HH_TAN(4, 4);
+    default: if (nf <= 2) HH_TAN(2, 8); if (nf <= 4) HH_TAN(4, 8); if (nf <= 6) HH_TAN(6, 8); HH_TAN(8, 8);
+  }
+#undef HH_TAN
+}
+
+static cudaError_t launch_tangent(const EuroArgs &a, const HestonTanConsts &c, int nf, int P, bool anti, int sm_count,
+                                  cudaStream_t st, int *nb, bool q) {
+  if (anti) return a.split ? launch_tangent_as<true, true>(a, c, nf, P, sm_count, st, nb, q)
+                           : launch_tangent_as<true, false>(a, c, nf, P, sm_count, st, nb, q);
+  return a.split ? launch_tangent_as<false, true>(a, c, nf, P, sm_count, st, nb, q)
+                 : launch_tangent_as<false, false>(a, c, nf, P, sm_count, st, nb, q);
 }
 
 static cudaError_t launch_any(int kind, const EuroArgs &a, const TangentPack *tp, int P, bool anti, int sm_count,
@@ -1277,14 +1489,49 @@ int tangent_sums(hh_ctx *ctx, const hh_model *m, const hh_tangent *tg, int ntan,
   HH_CUDA(ctx, cudaMemcpyAsync(ctx->d_tangents.ptr, &tp, sizeof tp, cudaMemcpyHostToDevice, st));
   const TangentPack *dtp = ctx->d_tangents.as<TangentPack>();
 
+  // Heston EM with the in-kernel RNG takes the specialised tangent kernel: directions in kernel order = full ones
+  // first (they need the per-step recursion), then the trivial ones (only dS0 / dr non-zero)
+  static const bool generic_tangent = getenv("HH_TANGENT_GENERIC") != nullptr;
+  const bool special = kind == K_HESTON_EM && !a.parity && !generic_tangent;
+  HestonTanConsts hc;
+  memset(&hc, 0, sizeof hc);
+  int order[kMaxTan], nfull = 0;  // order[kernel position] = caller's direction index
+  if (special) {
+    const PathParams<double> &pp = a.p;
+    bool full[kMaxTan];
+    for (int q = 0; q < ntan; ++q)
+      full[q] = tp.v0[q] != 0.0 || tp.kappa[q] != 0.0 || tp.theta[q] != 0.0 || tp.xi[q] != 0.0 || tp.a11[q] != 0.0 ||
+                tp.a12[q] != 0.0 || tp.a21[q] != 0.0 || tp.a22[q] != 0.0;
+    int pos = 0;
+    for (int q = 0; q < ntan; ++q) if (full[q]) order[pos++] = q;
+    nfull = pos;
+    for (int q = 0; q < ntan; ++q) if (!full[q]) order[pos++] = q;
+    for (int kq = 0; kq < ntan; ++kq) {
+      const int q = order[kq];
+      hc.dx0[kq] = tp.x0[q];
+      hc.dv0[kq] = tp.v0[q];
+      hc.drift[kq] = (double)a.n_steps * (pp.dt * tp.r[q]);
+      hc.A[kq] = pp.dt * (tp.kappa[q] * pp.theta + pp.kappa * tp.theta[q]);
+      hc.B[kq] = pp.dt * tp.kappa[q];
+      hc.da11[kq] = tp.a11[q];
+      hc.da12[kq] = tp.a12[q];
+      hc.db21[kq] = tp.xi[q] * pp.a21 + pp.xi * tp.a21[q];
+      hc.db22[kq] = tp.xi[q] * pp.a22 + pp.xi * tp.a22[q];
+    }
+  } else {
+    for (int q = 0; q < ntan; ++q) order[q] = q;
+  }
+
   int nblocks = 0;
-  HH_CUDA(ctx, launch_any(kind, a, dtp, P, anti, ctx->sm_count, st, &nblocks, true));
+  if (special) HH_CUDA(ctx, launch_tangent(a, hc, nfull, P, anti, ctx->sm_count, st, &nblocks, true));
+  else HH_CUDA(ctx, launch_any(kind, a, dtp, P, anti, ctx->sm_count, st, &nblocks, true));
   HH_CUDA(ctx, ctx->d_partials.ensure(sizeof(double) * (size_t)nblocks * npay * NACC));
   HH_CUDA(ctx, ctx->d_final.ensure(sizeof(double) * (size_t)npay * NACC));
   a.partials = ctx->d_partials.as<double>();
 
   HH_CUDA(ctx, cudaEventRecord(ctx->ev0, st));
-  HH_CUDA(ctx, launch_any(kind, a, dtp, P, anti, ctx->sm_count, st, &nblocks, false));
+  if (special) HH_CUDA(ctx, launch_tangent(a, hc, nfull, P, anti, ctx->sm_count, st, &nblocks, false));
+  else HH_CUDA(ctx, launch_any(kind, a, dtp, P, anti, ctx->sm_count, st, &nblocks, false));
   finalize_kernel<<<npay, kThreads, 0, st>>>(a.partials, nblocks, npay, NACC, ctx->d_final.as<double>());
   HH_CUDA(ctx, cudaGetLastError());
   HH_CUDA(ctx, cudaEventRecord(ctx->ev1, st));
@@ -1301,9 +1548,9 @@ int tangent_sums(hh_ctx *ctx, const hh_model *m, const hh_tangent *tg, int ntan,
     double *o = sums + (size_t)k * stride;
     o[0] = f[0];
     o[1] = f[1];
-    for (int q = 0; q < ntan; ++q) {
-      o[2 + q] = f[3 + q];
-      o[2 + ntan + q] = f[3 + P + q];
+    for (int kq = 0; kq < ntan; ++kq) {  // kernel order -> the caller's order
+      o[2 + order[kq]] = f[3 + kq];
+      o[2 + ntan + order[kq]] = f[3 + P + kq];
     }
   }
   return HH_OK;
