@@ -1,0 +1,93 @@
+"""Edge cases of the hot path through the C ABI: ragged sizes around the block and batch boundaries of every kernel,
+the maximum strike count, degenerate models, and the error behaviour that mirrors the reference."""
+import math
+
+import numpy as np
+import pytest
+
+import hedgehog_jl_b200 as hh
+from hedgehog_jl_b200 import _abi as abi
+from hedgehog_jl_b200.engine import SimSpec
+from helpers import gbm_model, heston_model, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("n", [1, 31, 255, 256, 257, 511, 513, 1023, 1025, 2049])
+@pytest.mark.parametrize("prec", [abi.HH_PREC_F64, abi.HH_PREC_F32])
+def test_ragged_path_counts_around_block_boundaries(cuda, oracle, n, prec):
+    m = heston_model()
+    sim = SimSpec(n_paths=n, n_steps=7, precision=prec, base_seed=11)
+    rg, tg = cuda.mc_european(m, sim, [(100.0, 1.0), (95.0, -1.0)], 0.97, want_terminal=True)
+    ro, to = oracle.mc_european(m, sim, [(100.0, 1.0), (95.0, -1.0)], 0.97, want_terminal=True)
+    assert tg.shape == to.shape == (n,)
+    assert rel_err(tg, to) < (1e-11 if prec == abi.HH_PREC_F64 else 5e-3)
+    for a, b in zip(rg, ro):
+        assert a.n == b.n == n
+        assert abs(a.price - b.price) <= (1e-11 if prec == abi.HH_PREC_F64 else 1e-3) * max(abs(b.price), 1.0)
+
+
+def test_large_job_takes_the_1024_thread_blocks_and_matches_the_small_block_sums(cuda):
+    """>= 4 x SMs x 1024 trajectories switch the headline kernel to 1024-thread blocks: same trajectories, the payoff sums
+    differ only by summation order."""
+    m = heston_model()
+    n = 148 * 1024 * 4 + 77
+    sim = SimSpec(n_paths=n, n_steps=10, base_seed=2)
+    big, tb = cuda.mc_european(m, sim, [(100.0, 1.0)], 1.0, want_terminal=True)
+    halves = [cuda.mc_european(m, SimSpec(n_paths=h, n_steps=10, base_seed=2, path_offset=o), [(100.0, 1.0)], 1.0, want_terminal=True)
+              for o, h in ((0, n // 2), (n // 2, n - n // 2))]
+    np.testing.assert_array_equal(np.concatenate([t for _, t in halves]), tb)
+    assert abs(sum(r[0].sum for r, _ in halves) - big[0].sum) <= 1e-12 * big[0].sum
+
+
+def test_maximum_strike_grid(cuda, oracle):
+    m = heston_model()
+    strikes = np.linspace(40.0, 200.0, 256)
+    pay = [(float(k), 1.0 if i % 2 else -1.0) for i, k in enumerate(strikes)]
+    sim = SimSpec(n_paths=3001, n_steps=9, vr=abi.HH_VR_ANTITHETIC, base_seed=4)
+    rg, _ = cuda.mc_european(m, sim, pay, 0.9)
+    ro, _ = oracle.mc_european(m, sim, pay, 0.9)
+    assert rel_err([r.sum + 1.0 for r in rg], [r.sum + 1.0 for r in ro]) < 1e-11
+    with pytest.raises(ValueError):
+        cuda.mc_european(m, sim, pay + [(100.0, 1.0)], 0.9)   # 257 payoffs
+    with pytest.raises(ValueError):
+        cuda.mc_european(m, sim, [], 0.9)                      # empty payoff list
+
+
+def test_degenerate_models(cuda, oracle):
+    # zero vol of vol and zero correlation: the variance is deterministic
+    m = heston_model(xi=0.0, rho=0.0)
+    sim = SimSpec(n_paths=500, n_steps=12, base_seed=1)
+    rg, tg = cuda.mc_european(m, sim, [(100.0, 1.0)], 1.0, want_terminal=True)
+    ro, to = oracle.mc_european(m, sim, [(100.0, 1.0)], 1.0, want_terminal=True)
+    assert rel_err(tg, to) < 1e-11
+    # variance started at zero with a violated Feller condition: full truncation keeps everything finite
+    m = heston_model(V0=0.0, kappa=0.5, theta=0.01, xi=1.0, rho=-0.9)
+    sim = SimSpec(n_paths=4000, n_steps=50, base_seed=1)
+    rg, tg = cuda.mc_european(m, sim, [(100.0, 1.0)], 1.0, want_terminal=True)
+    ro, to = oracle.mc_european(m, sim, [(100.0, 1.0)], 1.0, want_terminal=True)
+    assert np.all(np.isfinite(tg)) and rg[0].n_nonfinite == 0
+    assert rel_err(tg, to) < 1e-10
+    # zero volatility GBM: every path is the forward
+    g = gbm_model(sigma=0.0)
+    rg, tg = cuda.mc_european(g, SimSpec(n_paths=100, n_steps=4, scheme=abi.HH_SCHEME_EM, base_seed=1), [(100.0, 1.0)], 1.0,
+                              want_terminal=True)
+    assert rel_err(tg, np.full(100, 100.0 * math.exp(0.05))) < 1e-14
+
+
+@pytest.mark.parametrize("n,steps,deg", [(2, 2, 1), (3, 1, 2), (513, 3, 0), (1000, 4, 8)])
+def test_lsm_small_and_odd_shapes(cuda, oracle, n, steps, deg):
+    m = gbm_model()
+    z = np.random.Generator(np.random.Philox(n)).standard_normal((n, steps, 1))
+    sim = SimSpec(n_paths=n, n_steps=steps, scheme=abi.HH_SCHEME_EXACT_STEPS, rng_mode=abi.HH_RNG_NORMALS, normals=z)
+    D = math.exp(-m.r * m.T / steps)
+    og, tg, vg, pg = cuda.lsm_american(m, sim, (105.0, -1.0), deg, D, want_stopping=True, want_paths=True)
+    oo, to, vo, po = oracle.lsm_american(m, sim, (105.0, -1.0), min(deg, 5), D, want_stopping=True, want_paths=True)
+    assert rel_err(pg, po) < 1e-12
+    assert og.n == n and np.all((tg >= 1) & (tg <= steps))
+    if deg <= 2 and n > 100:
+        assert abs(og.price - oo.price) < 1e-6 * oo.price
+    with pytest.raises(ValueError):
+        cuda.lsm_american(m, sim, (105.0, -1.0), 9, D)     # degree above the built maximum
+    with pytest.raises(NotImplementedError):                # Q7: LSM on log-space schemes is rejected
+        cuda.lsm_american(m, SimSpec(n_paths=n, n_steps=steps, scheme=abi.HH_SCHEME_EM), (105.0, -1.0), 2, D)
