@@ -252,6 +252,23 @@ __device__ __forceinline__ uint32_t fast_angle_v2(uint32_t w2, uint32_t w3, uint
   return poff;
 }
 
+// The full Box-Muller pair from the lane-replicated v2 tables (kernels that need z1 and z2 themselves: the LSM path
+// generator). trig_lane = replicated {cos, sin}((j + 1/2) 2 pi / 256) table + (lane & 7) * 16 bytes, entry stride 128 B.
+__device__ __forceinline__ double fast_sqrt_pos5(double x);
+__device__ __forceinline__ void fast_normal_pair_v2(const char *__restrict__ log_lane, const char *__restrict__ exp_biased,
+                                                    const char *__restrict__ trig_lane, uint32_t w0, uint32_t w1, uint32_t w2,
+                                                    uint32_t w3, uint32_t one_hi, uint32_t magic_hi, double &z1, double &z2) {
+  const double R2 = fast_neg2log_v2(log_lane, exp_biased, w0, w1, one_hi);
+  double sn, cs;
+  const uint32_t poff = fast_angle_v2(w2, w3, magic_hi, sn, cs) >> 1;  // j * 128
+  const double2 t = *reinterpret_cast<const double2 *>(trig_lane + poff);
+  const double rad = fast_sqrt_pos5(max_tiny_hi(R2));
+  const double c = fma(t.x, cs, -(t.y * sn)), s_ = fma(t.y, cs, t.x * sn);
+  z1 = rad * c;
+  z2 = rad * s_;
+}
+constexpr int kTrigRepBytes = tables::kTrigN * kRep * 16;  // 32 KB
+
 // sqrt(x), x in [1e-300, 1e300]: MUFU.RSQ64H seed y0 (2^-22.9), then s = s0 (1 + e + 3/2 e^2) with s0 = x y0,
 // e = 1/2 - s0 (y0 / 2) = (1 - x y0^2) / 2 — cubic, 5 FP64 instructions; y0 / 2 is an exponent decrement on the ALU.
 __device__ __forceinline__ double fast_sqrt_pos5(double x) {

@@ -44,6 +44,8 @@ struct LsmPathArgs {
   double *grid;
   int n_steps, parity;
   double S0, dt_drift, sig_sqdt;
+  PhiloxRoundKeys rk;          // round keys of base_seed (uniform across threads when seeds == NULL)
+  uint32_t one_hi, magic_hi;   // 0x3FF00000, 0x43300000 as arguments (single-LOP3 bit assembly, see hh_european.cu)
 };
 
 // exp(y) - 1 for the per-step exponent of the GBM generator, |y| <= 1/2: y = j/64 + r, exp(y) - 1 =
@@ -56,8 +58,11 @@ struct ExpCoefs {
 };
 __constant__ ExpCoefs kExpC = {6755399441055744.0, 1.0 / 6, 1.0 / 24, 1.0 / 120, 1.0 / 720};
 
+__device__ __noinline__ double expm1_slow_path(double y) { return exp(y) - 1.0; }
+
 __device__ __forceinline__ double fast_expm1_small(const double2 *__restrict__ tab, double y) {
-  if (!(fabs(y) <= 0.5)) return exp(y) - 1.0;
+  // |y| <= 1/2 on the integer pipe (also false for NaN); the out-of-line libm path keeps the loop body small
+  if ((uint32_t)(__double2hiint(y) & 0x7fffffff) > 0x3fe00000u) return expm1_slow_path(y);
   const double t = fma(y, 64.0, kExpC.magic);  // nearest integer to 64 y in the low word
   const int j = __double2loint(t);
   const double r = fma(t - kExpC.magic, -0.015625, y);  // exact
@@ -70,24 +75,41 @@ __device__ __forceinline__ double fast_expm1_small(const double2 *__restrict__ t
   return fma(e.x, p * r, e.y);
 }
 
-template <bool ANTI>
+// Dynamic shared memory of the path generator: [log table x8 | trig table x8 | exponent table | expm1 table]
+constexpr int kLsmPathSmem = kLogRepBytes + kTrigRepBytes + kExp2Bytes + (2 * kExpJ + 1) * 16;
+
+template <bool ANTI, bool PARITY, bool UKEY>
 __global__ void __launch_bounds__(kLsmThreads) lsm_paths_kernel(const LsmPathArgs a) {
-  __shared__ FastNormalTables s_tables;
-  __shared__ double2 s_exp[2 * kExpJ + 1];
-  if (!a.parity) load_fast_tables(&s_tables);
-  if (threadIdx.x <= 2 * kExpJ) {
-    const double yj = (double)((int)threadIdx.x - kExpJ) * 0.015625;
-    s_exp[threadIdx.x] = make_double2(exp(yj), expm1(yj));
+  extern __shared__ __align__(16) unsigned char dsm[];
+  char *s_log = reinterpret_cast<char *>(dsm);
+  char *s_trig = s_log + kLogRepBytes;
+  double *s_e2 = reinterpret_cast<double *>(s_trig + kTrigRepBytes);
+  double2 *s_exp = reinterpret_cast<double2 *>(reinterpret_cast<char *>(s_e2) + kExp2Bytes);
+  const int tid = threadIdx.x;
+  if (!PARITY) {
+    for (int e = tid; e < tables::kLog2Buckets * kRep; e += kLsmThreads)
+      reinterpret_cast<double2 *>(s_log)[e] = g_fast_tables2.log_tab[e / kRep];
+    for (int e = tid; e < tables::kTrigN * kRep; e += kLsmThreads)
+      reinterpret_cast<double2 *>(s_trig)[e] = g_fast_tables2.trig_tab[e / kRep];
+    for (int e = tid; e < tables::kExp2N; e += kLsmThreads) s_e2[e] = g_fast_tables2.exp_tab[e];
+  }
+  if (tid <= 2 * kExpJ) {
+    const double yj = (double)(tid - kExpJ) * 0.015625;
+    s_exp[tid] = make_double2(exp(yj), expm1(yj));
   }
   __syncthreads();
+  const char *log_lane = s_log + (tid & (kRep - 1)) * 16;
+  const char *trig_lane = s_trig + (tid & (kRep - 1)) * 16;
+  const char *exp_biased = reinterpret_cast<const char *>(s_e2) - tables::kExp2Bias * 8;
   const int M = a.n_steps;
-  for (int64_t i = (int64_t)blockIdx.x * kLsmThreads + threadIdx.x; i < a.n; i += (int64_t)gridDim.x * kLsmThreads) {
-    uint64_t key = a.base_seed, idx = (uint64_t)(a.path_offset + i);
-    if (a.seeds) {
-      key = a.seeds[i];
+  for (int64_t i = (int64_t)blockIdx.x * kLsmThreads + tid; i < a.n; i += (int64_t)gridDim.x * kLsmThreads) {
+    uint64_t idx = (uint64_t)(a.path_offset + i);
+    PhiloxRoundKeys rk_own;
+    if (!UKEY && !PARITY) {
+      rk_own = philox_round_keys(a.seeds[i]);
       idx = 0;
     }
-    const double *z = a.parity ? a.normals + (size_t)i * (size_t)M : nullptr;
+    const double *z = PARITY ? a.normals + (size_t)i * (size_t)M : nullptr;
     double Sp = a.S0, Sm = a.S0;
     double *gp = a.grid + i;
     double *gm = a.grid + a.n + i;
@@ -96,25 +118,25 @@ __global__ void __launch_bounds__(kLsmThreads) lsm_paths_kernel(const LsmPathArg
 #pragma unroll 1
     for (int n = 0; n < M; n += 2) {
       double za, zb;
-      if (a.parity) {
+      if (PARITY) {
         za = z[n];
         zb = n + 1 < M ? z[n + 1] : 0.0;
       } else {
-        const u32x4 w = philox4x32_10((uint32_t)idx, (uint32_t)(idx >> 32), (uint32_t)(n >> 1), 0u, (uint32_t)key,
-                                      (uint32_t)(key >> 32));
-        fast_normal_pair(&s_tables, w.x, w.y, w.z, w.w, za, zb);
+        const u32x4 w = philox4x32_10_rk((uint32_t)idx, (uint32_t)(idx >> 32), (uint32_t)(n >> 1), 0u, UKEY ? a.rk : rk_own);
+        fast_normal_pair_v2(log_lane, exp_biased, trig_lane, w.x, w.y, w.z, w.w, a.one_hi, a.magic_hi, za, zb);
       }
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         if (n + h < M) {
           const double zz = h ? zb : za;
           // GeometricBrownianMotionProcess increment [upstream]: S += S (exp((r - s^2/2) dt + s sqrt(dt) Z) - 1)
-          const double e = a.sig_sqdt * zz;
-          Sp = fma(Sp, fast_expm1_small(s_exp, a.dt_drift + e), Sp);
-          gp[(size_t)(n + h + 1) * a.stride] = Sp;
+          Sp = fma(Sp, fast_expm1_small(s_exp, fma(a.sig_sqdt, zz, a.dt_drift)), Sp);
+          gp += a.stride;
+          *gp = Sp;
           if (ANTI) {  // same normals, sigma -> -sigma (montecarlo.jl:270-284)
-            Sm = fma(Sm, fast_expm1_small(s_exp, a.dt_drift - e), Sm);
-            gm[(size_t)(n + h + 1) * a.stride] = Sm;
+            Sm = fma(Sm, fast_expm1_small(s_exp, fma(-a.sig_sqdt, zz, a.dt_drift)), Sm);
+            gm += a.stride;
+            *gm = Sm;
           }
         }
       }
@@ -751,6 +773,7 @@ int lsm_american(hh_ctx *ctx, const hh_model *m, const hh_sim *s, const hh_payof
   HH_CUDA(ctx, cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
   HH_CUDA(ctx, upload_fast_tables(ctx->device, st));
+  HH_CUDA(ctx, upload_fast_tables2(ctx->device, st));
   HH_CUDA(ctx, ctx->d_grid.ensure(sizeof(double) * (size_t)stride * (size_t)(M + 1)));
   HH_CUDA(ctx, ctx->d_cash.ensure(sizeof(double) * (size_t)stride));
   if (want_stop) HH_CUDA(ctx, ctx->d_tau.ensure(sizeof(int32_t) * (size_t)stride));
@@ -765,6 +788,9 @@ int lsm_american(hh_ctx *ctx, const hh_model *m, const hh_sim *s, const hh_payof
   pa.n_steps = M;
   pa.parity = parity;
   const double dt = m->T / M;
+  pa.rk = philox_round_keys(s->base_seed);
+  pa.one_hi = 0x3FF00000u;
+  pa.magic_hi = 0x43300000u;
   pa.S0 = m->S0;
   pa.dt_drift = (m->r - 0.5 * (m->sigma * m->sigma)) * dt;
   pa.sig_sqdt = m->sigma * sqrt(dt);
@@ -782,7 +808,8 @@ int lsm_american(hh_ctx *ctx, const hh_model *m, const hh_sim *s, const hh_payof
 
   // grids: a multiple of the SM count, capped by the work
   const int64_t path_blocks = (N + kLsmThreads - 1) / kLsmThreads;
-  const int grid_paths = (int)(path_blocks < (int64_t)ctx->sm_count * 8 ? path_blocks : (int64_t)ctx->sm_count * 8);
+  // 64.9 KB of tables per block: 3 blocks per SM; one resident wave, grid-stride over the trajectories
+  const int grid_paths = (int)(path_blocks < (int64_t)ctx->sm_count * 3 ? path_blocks : (int64_t)ctx->sm_count * 3);
   const int64_t pass_blocks = ((ncols >> 1) + kLsmThreads - 1) / kLsmThreads;
   const int64_t resident = (int64_t)ctx->sm_count * pass_occupancy_deg(degree);  // one wave: every block is resident
   int grid_pass = (int)(pass_blocks < resident ? pass_blocks : resident);
@@ -798,8 +825,24 @@ int lsm_american(hh_ctx *ctx, const hh_model *m, const hh_sim *s, const hh_payof
   HH_CUDA(ctx, cudaMemsetAsync(ctx->d_lsm_state.ptr, 0, fit_off + sizeof(LsmFit) * (size_t)(M + 1), st));
 
   HH_CUDA(ctx, cudaEventRecord(ctx->ev0, st));
-  if (anti) lsm_paths_kernel<true><<<grid_paths, kLsmThreads, 0, st>>>(pa);
-  else lsm_paths_kernel<false><<<grid_paths, kLsmThreads, 0, st>>>(pa);
+  {
+    const bool ukey = pa.seeds == nullptr;
+    cudaError_t le = cudaSuccess;
+#define HH_LSM_PATHS(A, P, U)                                                                                           \
+  do {                                                                                                                  \
+    static bool attr_set = false;                                                                                       \
+    if (!attr_set) {                                                                                                    \
+      le = cudaFuncSetAttribute(lsm_paths_kernel<A, P, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLsmPathSmem); \
+      attr_set = le == cudaSuccess;                                                                                     \
+    }                                                                                                                   \
+    if (le == cudaSuccess) lsm_paths_kernel<A, P, U><<<grid_paths, kLsmThreads, kLsmPathSmem, st>>>(pa);                \
+  } while (0)
+    if (parity) { if (anti) HH_LSM_PATHS(true, true, true); else HH_LSM_PATHS(false, true, true); }
+    else if (ukey) { if (anti) HH_LSM_PATHS(true, false, true); else HH_LSM_PATHS(false, false, true); }
+    else { if (anti) HH_LSM_PATHS(true, false, false); else HH_LSM_PATHS(false, false, false); }
+#undef HH_LSM_PATHS
+    HH_CUDA(ctx, le);
+  }
   HH_CUDA(ctx, cudaGetLastError());
   HH_CUDA(ctx, cudaEventRecord(ctx->ev1, st));
 
