@@ -24,6 +24,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <type_traits>
 #include <vector>
 
 #include "hh_ctx.h"
@@ -78,8 +79,13 @@ __device__ __forceinline__ double fast_expm1_small(const double2 *__restrict__ t
 // Dynamic shared memory of the path generator: [log table x8 | trig table x8 | exponent table | expm1 table]
 constexpr int kLsmPathSmem = kLogRepBytes + kTrigRepBytes + kExp2Bytes + (2 * kExpJ + 1) * 16;
 
+// 64.9 KB of tables per block allow 3 blocks per SM: 512-thread blocks give 48 warps per SM to hide the dependent
+// chains (Philox rounds -> log -> sqrt -> exp), 32 registers per thread (ncu at 24 warps: issue slots 59 % busy, "wait"
+// the top stall)
+constexpr int kLsmPathThreads = 512;
+
 template <bool ANTI, bool PARITY, bool UKEY>
-__global__ void __launch_bounds__(kLsmThreads) lsm_paths_kernel(const LsmPathArgs a) {
+__global__ void __launch_bounds__(kLsmPathThreads) lsm_paths_kernel(const LsmPathArgs a) {
   extern __shared__ __align__(16) unsigned char dsm[];
   char *s_log = reinterpret_cast<char *>(dsm);
   char *s_trig = s_log + kLogRepBytes;
@@ -87,11 +93,11 @@ __global__ void __launch_bounds__(kLsmThreads) lsm_paths_kernel(const LsmPathArg
   double2 *s_exp = reinterpret_cast<double2 *>(reinterpret_cast<char *>(s_e2) + kExp2Bytes);
   const int tid = threadIdx.x;
   if (!PARITY) {
-    for (int e = tid; e < tables::kLog2Buckets * kRep; e += kLsmThreads)
+    for (int e = tid; e < tables::kLog2Buckets * kRep; e += kLsmPathThreads)
       reinterpret_cast<double2 *>(s_log)[e] = g_fast_tables2.log_tab[e / kRep];
-    for (int e = tid; e < tables::kTrigN * kRep; e += kLsmThreads)
+    for (int e = tid; e < tables::kTrigN * kRep; e += kLsmPathThreads)
       reinterpret_cast<double2 *>(s_trig)[e] = g_fast_tables2.trig_tab[e / kRep];
-    for (int e = tid; e < tables::kExp2N; e += kLsmThreads) s_e2[e] = g_fast_tables2.exp_tab[e];
+    for (int e = tid; e < tables::kExp2N; e += kLsmPathThreads) s_e2[e] = g_fast_tables2.exp_tab[e];
   }
   if (tid <= 2 * kExpJ) {
     const double yj = (double)(tid - kExpJ) * 0.015625;
@@ -102,7 +108,7 @@ __global__ void __launch_bounds__(kLsmThreads) lsm_paths_kernel(const LsmPathArg
   const char *trig_lane = s_trig + (tid & (kRep - 1)) * 16;
   const char *exp_biased = reinterpret_cast<const char *>(s_e2) - tables::kExp2Bias * 8;
   const int M = a.n_steps;
-  for (int64_t i = (int64_t)blockIdx.x * kLsmThreads + tid; i < a.n; i += (int64_t)gridDim.x * kLsmThreads) {
+  for (int64_t i = (int64_t)blockIdx.x * kLsmPathThreads + tid; i < a.n; i += (int64_t)gridDim.x * kLsmPathThreads) {
     uint64_t idx = (uint64_t)(a.path_offset + i);
     PhiloxRoundKeys rk_own;
     if (!UKEY && !PARITY) {
@@ -154,6 +160,14 @@ struct LsmFit {
   double count;
 };
 
+// Exchange of the regression moments with the peer GPUs (mailboxes mapped through CUDA IPC, see lsm_peer_exchange)
+struct PeerX {
+  int world, rank;
+  unsigned long long epoch;  // unique per exchanged date, identical on every rank; its parity selects the slot
+  double *mail[HH_MAX_PEERS];
+  int *error;                // set to 1 if a peer's contribution did not arrive in time
+};
+
 struct LsmPassArgs {
   int64_t ncols;
   const double *S_next;  // G[t+1]
@@ -170,11 +184,7 @@ struct LsmPassArgs {
   unsigned int *done;      // arrival counter of the blocks of this pass
   double *moments;         // [nacc] sums over all blocks, written by the last block
   LsmFit *fit_out;         // nullable: where the last block writes the fit of date t (single-GPU form)
-  // peer exchange in the kernel tail (hh_peer_*): world > 1 switches it on
-  int px_world, px_rank;
-  unsigned long long px_epoch;  // unique per exchanged date, identical on every rank; parity selects the slot
-  double *px_mail[HH_MAX_PEERS];
-  int *px_error;                // set to 1 if a peer's contribution did not arrive in time
+  PeerX px;                // peer exchange in the kernel tail (hh_peer_*): world > 1 switches it on
 };
 
 constexpr int kMailSlot = 32;  // doubles per (parity, rank) slot; flags follow the payload (see hh_api.cu)
@@ -210,8 +220,8 @@ __host__ __device__ constexpr int lsm_nacc() { return 3 * DEG + 3; }
 //                     through the linear recurrence, so every sum is an unconditional add / fma.
 // Sign tests read the high word of the double on the integer pipe (x > 0 <=> hi(x) > 0 for the values that occur:
 // cp (S - K) is either 0 or at least one ulp of S).
-template <int DEG, bool FIRST, bool LAST, bool TAU>
-__device__ __forceinline__ void lsm_column(const LsmPassArgs &a, const double *q, double cpK, double sn, double sc,
+template <int DEG, bool FIRST, bool LAST, bool TAU, class A>
+__device__ __forceinline__ void lsm_column(const A &a, const double *q, double cpK, double sn, double sc,
                                            double zin, int64_t p, double &zout, double *acc, int &cnt) {
   constexpr int NM = 2 * DEG + 1;
   const double e = fma(a.cp, sn, -cpK);
@@ -397,13 +407,51 @@ __global__ void lsm_fit_kernel(const double *moments, LsmFit *out) {
   if (threadIdx.x == 0) lsm_fit<DEG>(moments, out);
 }
 
+// Peer exchange, called by ONE block per rank with all its threads (one process per GPU, mailboxes mapped through CUDA
+// IPC): the local sums mom[0..nacc) go into slot [parity][my rank] of EVERY rank's mailbox (plain stores to the mapped peer
+// pointers, i.e. over NVLink), a system-scope fence, then the release flag; the block waits for the flags of all ranks
+// in its own mailbox and adds the slots in rank order, so all ranks hold bit-identical global sums in mom[]. Two
+// parities alternate per date: a rank can only be one date ahead of a peer (it needs the peer's sums to finish a
+// date), so the slot written at date d+2 has been consumed.
+__device__ __forceinline__ void lsm_peer_exchange(const PeerX &px, unsigned long long epoch, double *mom, int nacc) {
+  const int tid = threadIdx.x;
+  const int parity = (int)(epoch & 1ull);
+  if (tid < nacc) {
+    const double v = mom[tid];
+    for (int qq = 0; qq < px.world; ++qq) mail_payload(px.mail[qq], parity, px.rank)[tid] = v;
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (tid < px.world) {
+    unsigned long long *f = mail_flag(px.mail[tid], parity, px.rank);
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(epoch) : "memory");
+    // wait for rank `tid`'s flag in MY mailbox (bounded: ~2 s at 2 GHz, then flag the error and go on)
+    const unsigned long long *mine = mail_flag(px.mail[px.rank], parity, tid);
+    const long long t0 = clock64();
+    unsigned long long seen = 0;
+    bool dead = *reinterpret_cast<volatile int *>(px.error) != 0;
+    while (!dead) {
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(mine) : "memory");
+      if (seen >= epoch) break;
+      if (clock64() - t0 > 4000000000ll) {
+        *px.error = 1;
+        dead = true;
+      }
+      __nanosleep(64);
+    }
+  }
+  __syncthreads();
+  if (tid < nacc) {
+    double v = 0.0;
+    for (int qq = 0; qq < px.world; ++qq)
+      v += *reinterpret_cast<volatile double *>(mail_payload(px.mail[px.rank], parity, qq) + tid);
+    mom[tid] = v;
+  }
+  __syncthreads();
+}
+
 // Tail of a pass: block reduction -> per-block partials -> the block that arrives last sums all partials in a fixed
-// order, exchanges them with the peer GPUs if there are any, and fits the date's polynomial.
-// Peer exchange (one process per GPU, mailboxes mapped through CUDA IPC): the local sums go into slot [parity][my rank]
-// of EVERY rank's mailbox (plain stores to the mapped peer pointers, i.e. over NVLink), a system-scope fence, then
-// the release flag; the block waits for the flags of all ranks in its own mailbox and adds the slots in rank order,
-// so all ranks hold bit-identical global sums. Two parities alternate per date: a rank can only be one date ahead of
-// a peer (it needs the peer's sums to finish a date), so the slot written at date d+2 has been consumed.
+// order, exchanges them with the peer GPUs if there are any (lsm_peer_exchange), and fits the date's polynomial.
 template <int DEG, bool LAST>
 __device__ __forceinline__ void lsm_pass_tail(const LsmPassArgs &a, double *acc, int cnt, double (*s_red)[kLsmThreads / 32],
                                               double *scratch, bool *s_last) {
@@ -440,41 +488,7 @@ __device__ __forceinline__ void lsm_pass_tail(const LsmPassArgs &a, double *acc,
   __threadfence();
   lsm_reduce_partials(a.partials, (int)gridDim.x, NACC, a.moments, scratch);
   __syncthreads();
-  if (a.px_world > 1) {
-    const int parity = (int)(a.px_epoch & 1ull);
-    if (tid < NACC) {
-      const double v = a.moments[tid];
-      for (int qq = 0; qq < a.px_world; ++qq) mail_payload(a.px_mail[qq], parity, a.px_rank)[tid] = v;
-    }
-    __threadfence_system();
-    __syncthreads();
-    if (tid < a.px_world) {
-      unsigned long long *f = mail_flag(a.px_mail[tid], parity, a.px_rank);
-      asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(a.px_epoch) : "memory");
-      // wait for rank `tid`'s flag in MY mailbox (bounded: ~2 s at 2 GHz, then flag the error and go on)
-      const unsigned long long *mine = mail_flag(a.px_mail[a.px_rank], parity, tid);
-      const long long t0 = clock64();
-      unsigned long long seen = 0;
-      bool dead = *reinterpret_cast<volatile int *>(a.px_error) != 0;
-      while (!dead) {
-        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(mine) : "memory");
-        if (seen >= a.px_epoch) break;
-        if (clock64() - t0 > 4000000000ll) {
-          *a.px_error = 1;
-          dead = true;
-        }
-        __nanosleep(64);
-      }
-    }
-    __syncthreads();
-    if (tid < NACC) {
-      double v = 0.0;
-      for (int qq = 0; qq < a.px_world; ++qq)
-        v += *reinterpret_cast<volatile double *>(mail_payload(a.px_mail[a.px_rank], parity, qq) + tid);
-      a.moments[tid] = v;
-    }
-    __syncthreads();
-  }
+  if (a.px.world > 1) lsm_peer_exchange(a.px, a.px.epoch, a.moments, NACC);
   if (tid == 0) {
     if (a.fit_out) lsm_fit<DEG>(a.moments, a.fit_out);
     *a.done = 0u;
@@ -639,6 +653,220 @@ __global__ void __launch_bounds__(kLsmThreads) lsm_pass_tma_kernel(const LsmPass
   lsm_pass_tail<DEG, LAST>(a, acc, cnt, s_red, &s_next[0][0] /* the ring is idle by now */, &s_last);
 }
 
+// ---- the whole backward induction in ONE persistent cooperative kernel ---------------------------------------------
+// One launch per date costs ~9.5 us of fixed time at C3 (drain, last-block reduction, launch, ramp): 0.47 ms of 2.4.
+// Here every block stays resident for all dates (cooperative launch guarantees co-residency), owns a fixed set of
+// 512-column chunks, and the dates are separated by one grid barrier: after it EVERY block sums the per-block partials of
+// the date in the same fixed order and fits the polynomial itself (0.5 us of serial work, done redundantly instead of
+// broadcast). Partials are double-buffered by date parity, so a block that races ahead writes the other buffer.
+// With peers, block 0 exchanges the local sums (lsm_peer_exchange) and publishes the global sums through a flag.
+struct LsmBackArgs {
+  int64_t ncols, stride;
+  const double *G;         // [M+1][stride]
+  double *z;
+  int32_t *tau;            // nullable
+  double *partials;        // [2][grid][nacc]
+  unsigned int *barrier;   // grid barrier counter, zeroed before the launch
+  double *gmom;            // [2][32] global sums published by block 0 (peer mode)
+  unsigned int *gflag;     // generation of gmom
+  double *moments_out;     // final [sum, sumsq, count]
+  LsmFit *fits;            // [M+1], written by block 0 (statistics for the host)
+  double D, strike, cp, ua, ub;
+  int M;
+  PeerX px;                // px.epoch = epoch of the first exchanged date minus one
+};
+struct LsmColArgs {
+  double cp, ua, ub, D;
+  int32_t *tau;
+  int t_next;
+};
+
+__device__ __forceinline__ void lsm_grid_barrier(unsigned int *counter, unsigned int target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(counter, 1u);
+    unsigned int seen;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+    } while (seen < target);
+  }
+  __syncthreads();
+}
+
+template <int DEG, bool TAU>
+__global__ void __launch_bounds__(kLsmThreads) lsm_backward_kernel(const LsmBackArgs a) {
+  constexpr int NACC = lsm_nacc<DEG>();
+  constexpr int NM = 2 * DEG + 1;
+  __shared__ __align__(128) double s_next[kLsmStages][kLsmChunk];
+  __shared__ __align__(128) double s_cur[kLsmStages][kLsmChunk];
+  __shared__ __align__(128) double s_z[kLsmStages][kLsmChunk];
+  __shared__ __align__(8) uint64_t s_full[kLsmStages];
+  __shared__ double s_red[NACC][kLsmThreads / 32];
+  __shared__ double s_mom[32];
+  __shared__ double s_scratch[kLsmThreads];  // the ring is never idle here (next date primed before the barrier)
+  __shared__ LsmFit s_fit;
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < kLsmStages; ++s) mbar_init(&s_full[s], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  const double cpK = a.cp * a.strike;
+  const int64_t neven = a.ncols & ~(int64_t)1;
+  const int64_t nchunks = (neven + kLsmChunk - 1) / kLsmChunk;
+  const int my_chunks = (int64_t)blockIdx.x < nchunks ? (int)((nchunks - 1 - blockIdx.x) / gridDim.x) + 1 : 0;
+  const uint64_t pol_first = l2_policy_evict_first();
+  unsigned int seq = 0;  // chunks consumed so far by this block, over all dates: ring stage and mbarrier parity
+  LsmColArgs ca;
+  ca.cp = a.cp;
+  ca.ua = a.ua;
+  ca.ub = a.ub;
+  ca.D = a.D;
+  ca.tau = a.tau;
+
+  for (int t = a.M - 1; t >= 0; --t) {
+    const int date = a.M - 1 - t;  // 0, 1, ...
+    const bool first = (t + 1 == a.M), last = (t == 0);
+    const double *S_next = a.G + (size_t)(t + 1) * a.stride;
+    const double *S_cur = a.G + (size_t)t * a.stride;
+    ca.t_next = t + 1;
+    double q[DEG + 1];
+#pragma unroll
+    for (int k = 0; k <= DEG; ++k) q[k] = first ? 0.0 : s_fit.q[k];
+    double acc[NACC];
+#pragma unroll
+    for (int c = 0; c < NACC; ++c) acc[c] = 0.0;
+    int cnt = 0;
+
+    // thread 0 only: chunk i of date `td` (its S_next = G[td+1]) into ring position `at`
+    auto issue_date = [&](int td, int i, unsigned int at) {
+      const bool f = (td + 1 == a.M), l = (td == 0);
+      const int s = (int)(at % kLsmStages);
+      const int64_t c0 = ((int64_t)blockIdx.x + (int64_t)i * gridDim.x) * kLsmChunk;
+      const int64_t ncol = neven - c0 < kLsmChunk ? neven - c0 : kLsmChunk;
+      const uint32_t bytes = (uint32_t)ncol * 8u;
+      mbar_arrive_expect_tx(&s_full[s], bytes * (1u + (l ? 0u : 1u) + (f ? 0u : 1u)));
+      bulk_load_hint(&s_next[s][0], a.G + (size_t)(td + 1) * a.stride + c0, bytes, &s_full[s], pol_first);  // dead after date td
+      if (!l) bulk_load(&s_cur[s][0], a.G + (size_t)td * a.stride + c0, bytes, &s_full[s]);
+      if (!f) bulk_load(&s_z[s][0], a.z + c0, bytes, &s_full[s]);
+    };
+    auto issue = [&](int i, unsigned int at) { issue_date(t, i, at); };
+    if (tid == 0 && first) {  // later dates were primed before the previous grid barrier
+      for (int i = 0; i < kLsmStages && i < my_chunks; ++i) issue(i, seq + (unsigned)i);
+    }
+    auto chunks = [&](auto first_c, auto last_c) {
+      constexpr bool F = decltype(first_c)::value, L = decltype(last_c)::value;
+      for (int i = 0; i < my_chunks; ++i, ++seq) {
+        const int s = (int)(seq % kLsmStages);
+        const uint32_t parity = (seq / kLsmStages) & 1u;
+        const int64_t c0 = ((int64_t)blockIdx.x + (int64_t)i * gridDim.x) * kLsmChunk;
+        const int64_t ncol = neven - c0 < kLsmChunk ? neven - c0 : kLsmChunk;
+        const bool mine = 2 * tid < ncol;
+        mbar_wait(&s_full[s], parity);
+        double2 sn = make_double2(0.0, 0.0), sc = sn, zi = sn;
+        if (mine) {
+          sn = reinterpret_cast<const double2 *>(&s_next[s][0])[tid];
+          if (!L) sc = reinterpret_cast<const double2 *>(&s_cur[s][0])[tid];
+          if (!F) zi = reinterpret_cast<const double2 *>(&s_z[s][0])[tid];
+        }
+        __syncthreads();  // every thread has taken its columns out of stage s
+        if (tid == 0 && i + kLsmStages < my_chunks) issue(i + kLsmStages, seq + kLsmStages);
+        if (mine) {
+          const int64_t col = c0 + 2 * tid;
+          double2 zo;
+          lsm_column<DEG, F, L, TAU>(ca, q, cpK, sn.x, sc.x, zi.x, col, zo.x, acc, cnt);
+          lsm_column<DEG, F, L, TAU>(ca, q, cpK, sn.y, sc.y, zi.y, col + 1, zo.y, acc, cnt);
+          *reinterpret_cast<double2 *>(a.z + col) = zo;
+        }
+      }
+      if ((a.ncols & 1) && blockIdx.x == 0 && tid == 0) {
+        const int64_t p = a.ncols - 1;
+        double zo;
+        lsm_column<DEG, F, L, TAU>(ca, q, cpK, S_next[p], L ? 0.0 : S_cur[p], F ? 0.0 : a.z[p], p, zo, acc, cnt);
+        a.z[p] = zo;
+      }
+      if (L) {
+        acc[2] = (double)cnt;
+      } else {
+        acc[0] = (double)cnt;
+        acc[NM + DEG + 1] = (double)cnt;
+      }
+    };
+    using T_ = std::true_type;
+    using F_ = std::false_type;
+    if (first && last) chunks(T_{}, T_{});
+    else if (first) chunks(T_{}, F_{});
+    else if (last) chunks(F_{}, T_{});
+    else chunks(F_{}, F_{});
+
+    // block reduction -> partials[date parity][block]
+    double *part = a.partials + (size_t)(date & 1) * gridDim.x * NACC;
+    const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+    for (int c = 0; c < NACC; ++c) {
+      double v = acc[c];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+      if (lane == 0) s_red[c][warp] = v;
+    }
+    __syncthreads();
+    if (tid < NACC) {
+      double v = 0.0;
+#pragma unroll
+      for (int w = 0; w < kLsmThreads / 32; ++w) v += s_red[tid][w];
+      part[(size_t)blockIdx.x * NACC + tid] = v;
+    }
+    // prime the ring with the first chunks of the NEXT date while this block waits at the barrier and fits: the
+    // chunks are this block's own (fixed ownership), so its z stores of this date only need to be ordered before the
+    // bulk copies of the async proxy (fence.proxy.async by every writer, then the block barrier)
+    asm volatile("fence.proxy.async;" ::: "memory");
+    __syncthreads();
+    if (tid == 0 && !last) {
+      for (int i = 0; i < kLsmStages && i < my_chunks; ++i) issue_date(t - 1, i, seq + (unsigned)i);
+    }
+    lsm_grid_barrier(a.barrier, (unsigned)(date + 1) * gridDim.x);
+
+    if (last) {
+      if (blockIdx.x == 0) {
+        lsm_reduce_partials(part, (int)gridDim.x, NACC, s_mom, s_scratch);
+        __syncthreads();
+        if (tid < 3) a.moments_out[tid] = s_mom[tid];
+      }
+      break;
+    }
+    // every block: the same fixed-order sum of all partials, then the same fit
+    lsm_reduce_partials(part, (int)gridDim.x, NACC, s_mom, s_scratch);
+    __syncthreads();
+    if (a.px.world > 1) {
+      double *gm = a.gmom + (size_t)(date & 1) * 32;
+      if (blockIdx.x == 0) {
+        lsm_peer_exchange(a.px, a.px.epoch + (unsigned long long)(date + 1), s_mom, NACC);
+        if (tid < NACC) gm[tid] = s_mom[tid];
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(a.gflag), "r"((unsigned)(date + 1)) : "memory");
+      } else {
+        if (tid == 0) {
+          unsigned int seen;
+          do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(a.gflag) : "memory");
+          } while (seen < (unsigned)(date + 1));
+        }
+        __syncthreads();
+        if (tid < NACC) s_mom[tid] = __ldcg(gm + tid);
+        __syncthreads();
+      }
+    }
+    if (tid == 0) {
+      lsm_fit<DEG>(s_mom, &s_fit);
+      if (blockIdx.x == 0) a.fits[t] = s_fit;
+    }
+    __syncthreads();
+  }
+}
+
 // stopping_info values: v_p = payoff(G[tau_p][p])  (:112, :163-164)
 __global__ void lsm_stop_values_kernel(const double *grid, int64_t stride, int64_t ncols, const int32_t *tau, double strike,
                                        double cp, double *val) {
@@ -743,6 +971,49 @@ static cudaError_t launch_pass_deg(int deg, const LsmPassArgs &a, int grid, cuda
   }
 }
 
+template <int DEG, bool TAU>
+static cudaError_t launch_backward(const LsmBackArgs &b, int sm_count, int64_t nchunks, cudaStream_t st, bool query_only, int *grid_out) {
+  auto kern = lsm_backward_kernel<DEG, TAU>;
+  int occ = 0;
+  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kLsmThreads, 0);
+  if (e != cudaSuccess) return e;
+  if (occ < 1) return cudaErrorLaunchOutOfResources;
+  static const int cap = getenv("HH_LSM_BLOCKS_PER_SM") ? atoi(getenv("HH_LSM_BLOCKS_PER_SM")) : 2;
+  // measured at C3 (1e7 x 50, degree 3): 1 block per SM 2.79 ms, 2: 2.07 ms, 3: 2.29 ms, 4: 2.42 ms — barrier and partial-sum
+  // costs grow with the grid, and two 8-warp blocks per SM already keep enough bulk copies in flight
+  if (occ > cap) occ = cap;
+  int64_t grid = (int64_t)sm_count * occ;
+  if (grid > nchunks) grid = nchunks;
+  if (grid < 1) grid = 1;
+  *grid_out = (int)grid;
+  if (query_only) return cudaSuccess;
+  LsmBackArgs copy = b;
+  void *args[] = {&copy};
+  return cudaLaunchCooperativeKernel(reinterpret_cast<void *>(kern), dim3((unsigned)grid), dim3(kLsmThreads), args, 0, st);
+}
+
+static cudaError_t launch_backward_deg(int deg, bool tau, const LsmBackArgs &b, int sm_count, int64_t nchunks, cudaStream_t st,
+                                       bool query_only, int *grid_out) {
+#define HH_BACK(D)                                                                                   \
+  case D:                                                                                            \
+    return tau ? launch_backward<D, true>(b, sm_count, nchunks, st, query_only, grid_out)          \
+               : launch_backward<D, false>(b, sm_count, nchunks, st, query_only, grid_out)
+  switch (deg) {
+    HH_BACK(0);
+    HH_BACK(1);
+    HH_BACK(2);
+    HH_BACK(3);
+    HH_BACK(4);
+    HH_BACK(5);
+    HH_BACK(6);
+    HH_BACK(7);
+    default:
+      return tau ? launch_backward<8, true>(b, sm_count, nchunks, st, query_only, grid_out)
+                 : launch_backward<8, false>(b, sm_count, nchunks, st, query_only, grid_out);
+  }
+#undef HH_BACK
+}
+
 int lsm_american(hh_ctx *ctx, const hh_model *m, const hh_sim *s, const hh_payoff *payoff, int degree,
                  double step_discount, const hh_comm *comm, hh_lsm_result *out, int32_t *stop_idx, double *stop_val,
                  double *spot_paths) {
@@ -807,7 +1078,7 @@ int lsm_american(hh_ctx *ctx, const hh_model *m, const hh_sim *s, const hh_payof
   }
 
   // grids: a multiple of the SM count, capped by the work
-  const int64_t path_blocks = (N + kLsmThreads - 1) / kLsmThreads;
+  const int64_t path_blocks = (N + kLsmPathThreads - 1) / kLsmPathThreads;
   // 64.9 KB of tables per block: 3 blocks per SM; one resident wave, grid-stride over the trajectories
   const int grid_paths = (int)(path_blocks < (int64_t)ctx->sm_count * 3 ? path_blocks : (int64_t)ctx->sm_count * 3);
   const int64_t pass_blocks = ((ncols >> 1) + kLsmThreads - 1) / kLsmThreads;
@@ -815,10 +1086,27 @@ int lsm_american(hh_ctx *ctx, const hh_model *m, const hh_sim *s, const hh_payof
   int grid_pass = (int)(pass_blocks < resident ? pass_blocks : resident);
   if (grid_pass < 1) grid_pass = 1;
   const int nacc = 3 * degree + 3;
-  HH_CUDA(ctx, ctx->d_lsm_partials.ensure(sizeof(double) * (size_t)grid_pass * nacc));
+  static const int persistent_env = getenv("HH_LSM_PERSISTENT") ? atoi(getenv("HH_LSM_PERSISTENT")) : 1;
+  const int64_t neven = ncols & ~(int64_t)1;
+  const int64_t nchunks = (neven + kLsmChunk - 1) / kLsmChunk;
+  const bool host_exchange = comm && comm->world > 1 && !peer_mode;  // NCCL through the callback needs a launch per date
+  int grid_back = 0;
+  bool persistent = persistent_env && !host_exchange && nchunks >= 1;
+  if (persistent) {
+    LsmBackArgs probe;
+    memset(&probe, 0, sizeof probe);
+    if (launch_backward_deg(degree, want_stop, probe, ctx->sm_count, nchunks, st, true, &grid_back) != cudaSuccess) {
+      (void)cudaGetLastError();
+      persistent = false;
+    }
+  }
+  {
+    const size_t need = (size_t)(persistent && 2 * grid_back > grid_pass ? 2 * grid_back : grid_pass) * nacc;
+    HH_CUDA(ctx, ctx->d_lsm_partials.ensure(sizeof(double) * need));
+  }
   // state: [moments (nacc)] [done counter] [fits (M+1)]
   const size_t done_off = ((size_t)nacc * sizeof(double) + 255) & ~(size_t)255;
-  const size_t fit_off = done_off + 256;
+  const size_t fit_off = done_off + 1024;  // +0 done, +64 grid barrier, +128 peer error, +192 gmom flag, +256 gmom[2][32]
   HH_CUDA(ctx, ctx->d_lsm_state.ensure(fit_off + sizeof(LsmFit) * (size_t)(M + 1)));
   double *d_moments = ctx->d_lsm_state.as<double>();
   LsmFit *d_fits = reinterpret_cast<LsmFit *>(static_cast<char *>(ctx->d_lsm_state.ptr) + fit_off);
@@ -835,7 +1123,7 @@ int lsm_american(hh_ctx *ctx, const hh_model *m, const hh_sim *s, const hh_payof
       le = cudaFuncSetAttribute(lsm_paths_kernel<A, P, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLsmPathSmem); \
       attr_set = le == cudaSuccess;                                                                                     \
     }                                                                                                                   \
-    if (le == cudaSuccess) lsm_paths_kernel<A, P, U><<<grid_paths, kLsmThreads, kLsmPathSmem, st>>>(pa);                \
+    if (le == cudaSuccess) lsm_paths_kernel<A, P, U><<<grid_paths, kLsmPathThreads, kLsmPathSmem, st>>>(pa);                \
   } while (0)
     if (parity) { if (anti) HH_LSM_PATHS(true, true, true); else HH_LSM_PATHS(false, true, true); }
     else if (ukey) { if (anti) HH_LSM_PATHS(true, false, true); else HH_LSM_PATHS(false, false, true); }
@@ -876,11 +1164,11 @@ int lsm_american(hh_ctx *ctx, const hh_model *m, const hh_sim *s, const hh_payof
   a.ub = ub;
   a.done = reinterpret_cast<unsigned int *>(static_cast<char *>(ctx->d_lsm_state.ptr) + done_off);
   a.moments = d_moments;
-  a.px_world = 1;
+  a.px.world = 1;
   if (peer_mode) {
-    a.px_rank = ctx->peer_rank;
-    for (int qq = 0; qq < ctx->peer_world; ++qq) a.px_mail[qq] = static_cast<double *>(ctx->peer_mail[qq]);
-    a.px_error = reinterpret_cast<int *>(static_cast<char *>(ctx->d_lsm_state.ptr) + done_off + 128);  // zeroed above
+    a.px.rank = ctx->peer_rank;
+    for (int qq = 0; qq < ctx->peer_world; ++qq) a.px.mail[qq] = static_cast<double *>(ctx->peer_mail[qq]);
+    a.px.error = reinterpret_cast<int *>(static_cast<char *>(ctx->d_lsm_state.ptr) + done_off + 128);  // zeroed above
   }
   const double *G = ctx->d_grid.as<double>();
   // The cash-flow vector z is read and written by EVERY pass while each date slice is read twice and then dead:
@@ -905,6 +1193,36 @@ int lsm_american(hh_ctx *ctx, const hh_model *m, const hh_sim *s, const hh_payof
     }
     (void)cudaGetLastError();
   }
+  if (persistent) {
+    LsmBackArgs bk;
+    memset(&bk, 0, sizeof bk);
+    char *state = static_cast<char *>(ctx->d_lsm_state.ptr);
+    bk.ncols = ncols;
+    bk.stride = stride;
+    bk.G = G;
+    bk.z = ctx->d_cash.as<double>();
+    bk.tau = want_stop ? ctx->d_tau.as<int32_t>() : nullptr;
+    bk.partials = ctx->d_lsm_partials.as<double>();
+    bk.barrier = reinterpret_cast<unsigned int *>(state + done_off + 64);
+    bk.gflag = reinterpret_cast<unsigned int *>(state + done_off + 192);
+    bk.gmom = reinterpret_cast<double *>(state + done_off + 256);
+    bk.moments_out = d_moments;
+    bk.fits = d_fits;
+    bk.D = step_discount;
+    bk.strike = payoff->strike;
+    bk.cp = payoff->cp;
+    bk.ua = ua;
+    bk.ub = ub;
+    bk.M = M;
+    bk.px.world = 1;
+    if (peer_mode) {
+      bk.px = a.px;
+      bk.px.world = ctx->peer_world;
+      bk.px.epoch = ctx->peer_epoch;         // date d (0-based) uses epoch base + d + 1
+      ctx->peer_epoch += (unsigned long long)(M > 1 ? M - 1 : 0);
+    }
+    HH_CUDA(ctx, launch_backward_deg(degree, want_stop, bk, ctx->sm_count, nchunks, st, false, &grid_back));
+  } else {
   // pass(t), t = M-1 .. 0: decision at t+1 (with fit[t+1]), one-step discount, moments of date t (t >= 1)
   for (int t = M - 1; t >= 0; --t) {
     a.S_next = G + (size_t)(t + 1) * stride;
@@ -916,8 +1234,8 @@ int lsm_american(hh_ctx *ctx, const hh_model *m, const hh_sim *s, const hh_payof
     const bool exchange = t >= 1 && comm && comm->world > 1 && !peer_mode;  // host-callback (NCCL) form
     a.fit_out = (t >= 1 && !exchange) ? d_fits + t : nullptr;
     if (peer_mode) {
-      a.px_world = t >= 1 ? ctx->peer_world : 1;  // the last pass only sums prices; the host layer reduces those
-      a.px_epoch = t >= 1 ? ++ctx->peer_epoch : 0;
+      a.px.world = t >= 1 ? ctx->peer_world : 1;  // the last pass only sums prices; the host layer reduces those
+      a.px.epoch = t >= 1 ? ++ctx->peer_epoch : 0;
     }
     a.reverse = (M - 1 - t) & 1;
     HH_CUDA(ctx, launch_pass_deg(degree, a, grid_pass, st));
@@ -927,6 +1245,7 @@ int lsm_american(hh_ctx *ctx, const hh_model *m, const hh_sim *s, const hh_payof
       launch_fit_deg(degree, d_moments, d_fits + t, st);
       HH_CUDA(ctx, cudaGetLastError());
     }
+  }
   }
   HH_CUDA(ctx, cudaEventRecord(ctx->ev2, st));
   if (l2_window) {
