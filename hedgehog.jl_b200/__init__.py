@@ -12,3 +12,4 @@ from .greeks import (BatchGreekProblem, FDBackward, FDCentral, FDForward, FieldL
                      GreekProblem, GreekResult, SecondOrderGreekProblem, SpotLens, VolLens, ZeroRateSpineLens, optic,
                      strike_grid_greeks)
 from .greeks import set as set_lens  # noqa: F401
+from .calibration import CalibrationProblem, CalibrationResult, OptimizerAlgo, RootFinderAlgo, basket_prices_and_jacobian  # noqa: F401,E402

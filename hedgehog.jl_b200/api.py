@@ -370,6 +370,9 @@ def solve(prob, method, *args, engine=None, shard=None, group=None, **kw):
     """Hedgehog.solve for the Monte Carlo path. Dispatches like the reference:
     PricingProblem × MonteCarlo (European), PricingProblem × LSM (American), and the Greek problems."""
     from . import greeks as _g
+    from . import calibration as _c
+    if isinstance(prob, _c.CalibrationProblem):
+        return _c.solve_calibration(prob, method, *args, engine=engine, shard=shard, group=group, **kw)
     if isinstance(prob, (_g.GreekProblem, _g.BatchGreekProblem, _g.SecondOrderGreekProblem)):
         return _g.solve_greek(prob, method, *args, engine=engine, shard=shard, group=group, **kw)
     if isinstance(prob, BasketPricingProblem):
