@@ -96,6 +96,48 @@ HH_HD cplx csqrt_(cplx a) {
 
 constexpr double kBesselPi = 3.14159265358979323846;
 
+// I_nu = exp(E) F: the series and the Hankel expansion produce an algebraic factor F (the sum) next to an exponent that
+// only needs log|w| and arg w, which the caller often has already (bk_chf unwraps arg z_gamma anyway). Returning
+// (E, F) instead of log I avoids a complex logarithm of F per evaluation, and the caller exponentiates once.
+struct BesselEF {
+  cplx E, F;
+};
+
+HH_HD BesselEF besseli_series_ef(double nu, double lgam_nu1, cplx w, double log_aw, double arg_w) {
+  const cplx q = 0.25 * (w * w);
+  cplx term = mk(1.0), sum = mk(1.0);
+#pragma unroll 1
+  for (int k = 1; k < 100; ++k) {
+    term = (term * q) * rcp_fast((double)k * (nu + (double)k));
+    sum = sum + term;
+    if (cabs2(term) < 1e-34 * cabs2(sum)) break;
+  }
+  // (w/2)^nu / Gamma(nu+1) * sum
+  return BesselEF{cplx{nu * (log_aw - 0.6931471805599453) - lgam_nu1, nu * arg_w}, sum};
+}
+
+HH_HD BesselEF besseli_asymptotic_ef(double nu, cplx w, double log_aw, double arg_w) {
+  const double mu4 = 4.0 * nu * nu;
+  const cplx iw = 1.0 / w;
+  cplx t = mk(1.0), s1 = mk(1.0), s2 = mk(1.0);
+  double last = 1.0;  // |t|^2 of the previous term
+#pragma unroll 1
+  for (int k = 1; k < 60; ++k) {
+    const double odd = (double)(2 * k - 1);
+    t = (t * iw) * ((mu4 - odd * odd) * rcp_fast(8.0 * (double)k));  // a_k / w^k
+    const double m = cabs2(t);
+    if (m > last) break;  // the expansion has started to diverge
+    last = m;
+    s1 = (k & 1) ? s1 - t : s1 + t;
+    s2 = s2 + t;
+    if (m < 1e-34) break;
+  }
+  // I = e^w / sqrt(2 pi w) [ s1 + e^{-2w +- i pi (nu + 1/2)} s2 ],  + for Im w >= 0
+  const double sgn = w.im >= 0.0 ? 1.0 : -1.0;
+  const cplx e2 = cexp_(cplx{-2.0 * w.re, -2.0 * w.im + sgn * kBesselPi * (nu + 0.5)});
+  return BesselEF{cplx{w.re - 0.5 * (1.8378770664093453 + log_aw), w.im - 0.5 * arg_w}, s1 + e2 * s2};  // log(2 pi)
+}
+
 // ---- ascending series: |w| - Re w <= 5, |w| <~ 25 ---------------------------------------------------------------
 HH_HD cplx log_besseli_series(double nu, double lgam_nu1, cplx w) {
   const cplx q = 0.25 * (w * w);
@@ -246,6 +288,31 @@ HH_HD cplx log_besseli(const BesselOrder &o, cplx z) {
   return r;
 }
 
+// I_nu(z) = exp(E) F for z != 0 with log|z| and arg z supplied by the caller (arg z in (-pi, pi]).
+HH_HD BesselEF besseli_ef(const BesselOrder &o, cplx z, double log_az, double arg_z) {
+  const double nu = o.nu;
+  cplx w = z;
+  double rot = 0.0, arg_w = arg_z;
+  if (z.re < 0.0) {
+    w = -z;
+    const double sg = z.im >= 0.0 ? 1.0 : -1.0;
+    rot = sg * kBesselPi * nu;
+    arg_w = arg_z - sg * kBesselPi;  // arg(-z) in (-pi/2, pi/2)
+  }
+  const double aw = cabs(w);
+  BesselEF r;
+  if (aw <= 5.0 || (aw < o.r_asym && aw - w.re <= 5.0)) {
+    r = besseli_series_ef(nu, o.lgam_nu1, w, log_az, arg_w);
+  } else if (aw >= o.r_asym) {
+    r = besseli_asymptotic_ef(nu, w, log_az, arg_w);
+  } else {
+    r.E = log_besseli(o, w);  // continued fractions (rare: strongly rotated arguments of moderate size)
+    r.F = mk(1.0);
+  }
+  r.E.im += rot;
+  return r;
+}
+
 // ---- Broadie-Kaya: characteristic function of int_0^tau V ds given (V0, VT) ------------------------------------------
 // HestonCFIterator + evaluate_chf, src/distributions/heston.jl:150-212.
 struct BkParams {
@@ -291,11 +358,12 @@ HH_HD cplx bk_chf(const BkParams &p, const BkCf &it, double a, double &theta_pre
     thu = theta_prev + dlt;
   }
   theta_prev = thu;
-  cplx logIg = log_besseli(p.ord, zg);                                        // :206-207
-  logIg.im += p.ord.nu * (thu - th);
+  // I_nu(z_gamma) = exp(E) F with log|z_gamma| and the angle already in hand                       :206-207
+  BesselEF ig = besseli_ef(p.ord, zg, 0.5 * log(cabs2(zg)), th);
+  ig.E.im += p.ord.nu * (thu - th);
   // phi = exp(-(g - k) tau / 2) (zeta_k / zeta_g) exp((V0+VT)/s^2 (eta_k - eta_g)) exp(logIg - logIk)   :195-211
-  const cplx ex = (-0.5 * p.tau) * (g - p.kappa) + it.vsum_s * (p.eta_k - eta_g) + (logIg - it.logIk);
-  return (p.zeta_k / zeta_g) * cexp_(ex);
+  const cplx ex = (-0.5 * p.tau) * (g - p.kappa) + it.vsum_s * (p.eta_k - eta_g) + (ig.E - it.logIk);
+  return ((p.zeta_k / zeta_g) * ig.F) * cexp_(ex);
 }
 
 }  // namespace hh
