@@ -30,7 +30,7 @@
 namespace hh {
 
 constexpr int kBkThreads = 128;
-constexpr int kBkTable = 96;  // table entries per thread in shared memory (kBkThreads * kBkTable * 8 B = 96 KB)
+constexpr int kBkTable = 32;  // table entries per thread in shared memory (32 KB per block); longer series (mean 12.3 at C4) spill to the HBM slab
 
 // terminal spots -> payoff sums (hh_european.cu)
 int terminal_payoffs_launch(hh_ctx *ctx, const double *d_terminal, int64_t n, const hh_payoff *payoffs, int npay,
@@ -257,7 +257,7 @@ struct BkArgs {
   unsigned long long *counters;  // [0] fallbacks, [1] sum J, [2] sum root-finder evaluations, [3] transitions, [4] unbracketed accepted
 };
 
-__global__ void __launch_bounds__(kBkThreads) bk_paths_kernel(const BkArgs a) {
+__global__ void __launch_bounds__(kBkThreads, 3) bk_paths_kernel(const BkArgs a) {
   extern __shared__ double s_tab[];
   BkTable tb;
   tb.sh = s_tab + threadIdx.x;
