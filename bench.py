@@ -36,6 +36,7 @@ EXEC_FLOP_PER_PATH_STEP = 51.16
 EXEC_FP64_INSTR_PER_PATH_STEP = 31.09
 EXEC_INSTR_PER_PATH_STEP = 90.6
 WORKLOAD = "C2 Heston EM European call: 1e8 paths x 252 steps per GPU, f64, NoVarianceReduction"
+EULER_BIAS_252 = 0.005651  # price(252 steps) - Carr-Madan, 2e8 paths, std error 0.0005 (tools/euler_bias.py)
 CARR_MADAN_C2 = 9.242536279428904  # oracle/anchors.py heston_price(100,100,.03,1,.04,2,.04,.3,-.7), CarrMadan(1, 32)
 
 
@@ -320,7 +321,12 @@ def main():
              "convention": "algorithmic 25 FLOP per path-step; f32 fast mode (MUFU-bound), no FP32 peak measured"},
             "e2e": e2e, "gpu_launches": 2 * K, "clocks": clocks, "f32_fast_mode": f32,
             "check": {"price": last.price, "std_error": last.std_error, "carr_madan": CARR_MADAN_C2,
-                      "n_nonfinite": last.n_nonfinite, "e2e_price": e2e_price},
+                      "n_nonfinite": last.n_nonfinite, "e2e_price": e2e_price,
+                      "euler_bias_at_252_steps": EULER_BIAS_252,
+                      "z_vs_carr_madan_plus_bias": (last.price - CARR_MADAN_C2 - EULER_BIAS_252) / last.std_error
+                      if args.nsteps == 252 and last.std_error > 0 else None,
+                      "note": "the scheme's O(dt) discretisation bias, measured with 2e8 paths per step count "
+                              "(profiles/r1_i_euler_bias_c2.json: +0.0217, +0.0112, +0.0057, +0.0023, +0.0004 at 63..1008 steps)"},
         }
         if world == 1 and not args.no_cpu_baseline:
             v, info = cpu_sample(100_000, args.nsteps, seconds=args.cpu_seconds)
