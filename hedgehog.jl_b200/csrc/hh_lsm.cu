@@ -1221,8 +1221,15 @@ int lsm_american(hh_ctx *ctx, const hh_model *m, const hh_sim *s, const hh_payof
       bk.px.epoch = ctx->peer_epoch;         // date d (0-based) uses epoch base + d + 1
       ctx->peer_epoch += (unsigned long long)(M > 1 ? M - 1 : 0);
     }
-    HH_CUDA(ctx, launch_backward_deg(degree, want_stop, bk, ctx->sm_count, nchunks, st, false, &grid_back));
-  } else {
+    const cudaError_t le = launch_backward_deg(degree, want_stop, bk, ctx->sm_count, nchunks, st, false, &grid_back);
+    if (le != cudaSuccess && !peer_mode) {
+      (void)cudaGetLastError();  // no cooperative launch here (e.g. a partitioned device): one launch per date instead
+      persistent = false;
+    } else {
+      HH_CUDA(ctx, le);
+    }
+  }
+  if (!persistent) {
   // pass(t), t = M-1 .. 0: decision at t+1 (with fit[t+1]), one-step discount, moments of date t (t >= 1)
   for (int t = M - 1; t >= 0; --t) {
     a.S_next = G + (size_t)(t + 1) * stride;

@@ -100,8 +100,10 @@ struct B200MonteCarlo{P<:PriceDynamics,S<:SimulationStrategy,C<:SimulationConfig
     config::C
     ensemble::Bool      # materialise MonteCarloSolution.ensemble on the host (8 B per trajectory D2H)
     base_seed::Union{Nothing,UInt64}  # one Philox key + trajectory index in the counter, instead of config.seeds per path
+    precision::Symbol   # :f64, or :f32 = the Float32 fast mode (Heston Euler-Maruyama only, HH_PREC_F32)
 end
-B200MonteCarlo(d, s, c; ensemble = true, base_seed = nothing) = B200MonteCarlo(d, s, c, ensemble, base_seed)
+B200MonteCarlo(d, s, c; ensemble = true, base_seed = nothing, precision = :f64) =
+    B200MonteCarlo(d, s, c, ensemble, base_seed, precision)
 B200MonteCarlo(m::MonteCarlo; kw...) = B200MonteCarlo(m.dynamics, m.strategy, m.config; kw...)
 
 struct B200LSM{M<:B200MonteCarlo} <: AbstractPricingMethod
@@ -145,13 +147,14 @@ function with_sim(f, method::B200MonteCarlo, scheme::Cint)
     exact = scheme == HH_SCHEME_EXACT_TERMINAL || scheme == HH_SCHEME_HESTON_BK
     steps = exact ? 1 : cfg.steps                                 # exact strategies ignore `steps` (montecarlo.jl:454-459)
     seeds = Vector{UInt64}(cfg.seeds)
+    prec = method.precision === :f32 ? Cint(1) : Cint(0)          # HH_PREC_F32 / HH_PREC_F64
     if method.base_seed !== nothing || exact
         key = method.base_seed === nothing ? seeds[1] : method.base_seed   # Xoshiro(seeds[1]) :456 -> ONE stream
-        sim = HHSim(cfg.trajectories, 0, steps, scheme, vr_of(cfg.variance_reduction), 0, 0, 0, key, C_NULL, C_NULL, HHBkConfig())
+        sim = HHSim(cfg.trajectories, 0, steps, scheme, vr_of(cfg.variance_reduction), prec, 0, 0, key, C_NULL, C_NULL, HHBkConfig())
         return f(sim)
     end
     GC.@preserve seeds begin
-        sim = HHSim(cfg.trajectories, 0, steps, scheme, vr_of(cfg.variance_reduction), 0, 0, 0, 0,
+        sim = HHSim(cfg.trajectories, 0, steps, scheme, vr_of(cfg.variance_reduction), prec, 0, 0, 0,
                     pointer(seeds), C_NULL, HHBkConfig())           # remake(prob; seed = seeds[i]) :331
         f(sim)
     end
@@ -272,6 +275,21 @@ function Hedgehog.solve(gprob::BatchGreekProblem, ::ForwardAD, method::B200Monte
     g = forward_ad(gprob.pricing_problem, collect(gprob.lenses), method)
     Dict(lens => g[i] for (i, lens) in enumerate(gprob.lenses))      # greeks_problem.jl:559-568
 end
+# Multi-GPU (one Julia process per GPU, e.g. MPI.jl): after `h = peer_export()` on every rank and an Allgather of the 64-byte
+# handles, `peer_connect(rank, world, handles)` maps the peers' mailboxes; B200LSM solves then pass
+# hh_comm(C_NULL, C_NULL, rank, world) and the regression moments are exchanged inside the kernel over NVLink.
+function peer_export()
+    h = zeros(UInt8, 64)
+    ctx = context()
+    check(ctx, ccall((:hh_peer_export, LIB[]), Cint, (Ptr{Cvoid}, Ptr{UInt8}), ctx.h, h), "hh_peer_export")
+    h
+end
+function peer_connect(rank::Integer, world::Integer, handles::Vector{UInt8})
+    ctx = context()
+    check(ctx, ccall((:hh_peer_connect, LIB[]), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{UInt8}), ctx.h, rank, world, handles),
+          "hh_peer_connect")
+end
+
 # FiniteDifference Greeks need no method here: Hedgehog's generic code re-solves with bumped inputs
 # (greeks_problem.jl:279-329), and the deterministic Philox stream gives it common random numbers.
 
