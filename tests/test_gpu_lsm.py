@@ -140,3 +140,43 @@ def test_peer_mailbox_loopback(cuda):
     b, *_ = cuda.lsm_american(m, sim, (100.0, -1.0), 2, 0.99)
     assert a.price == b.price
     cuda.peer_disconnect()
+
+
+def test_persistent_and_per_date_kernels_agree(cuda):
+    """The persistent cooperative kernel (default) and the one-launch-per-date form (HH_LSM_PERSISTENT=0, also the path the
+    NCCL callback takes) run the same column arithmetic; block partitions differ, so sums agree to rounding and the
+    stopping decisions exactly (up to ties)."""
+    import json
+    import os
+    import subprocess
+    import sys
+    code = r'''
+import json, math, sys
+sys.path.insert(0, %r)
+import numpy as np
+import hedgehog_jl_b200 as hh
+from hedgehog_jl_b200 import _abi as abi
+from hedgehog_jl_b200.engine import SimSpec
+sys.path.insert(0, %r)
+from helpers import gbm_model
+eng = hh.default_engine(0)
+m = gbm_model()
+out = {}
+for anti in (0, 1):
+    sim = SimSpec(n_paths=300_001, n_steps=25, scheme=abi.HH_SCHEME_EXACT_STEPS, vr=anti, base_seed=9)
+    o, tau, val, _ = eng.lsm_american(m, sim, (100.0, -1.0), 3, math.exp(-m.r * m.T / 25), want_stopping=True)
+    out[str(anti)] = [o.price, o.std_error, int(tau.sum()), float(val.sum())]
+print(json.dumps(out))
+'''
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = {}
+    for mode in ("1", "0"):
+        env = dict(os.environ, HH_LSM_PERSISTENT=mode)
+        p = subprocess.run([sys.executable, "-c", code % (root, os.path.join(root, "tests"))], env=env, capture_output=True,
+                           text=True, timeout=300)
+        assert p.returncode == 0, p.stderr[-2000:]
+        res[mode] = json.loads(p.stdout.strip().splitlines()[-1])
+    for anti in ("0", "1"):
+        a, b = res["1"][anti], res["0"][anti]
+        assert abs(a[0] - b[0]) <= 1e-9 * abs(b[0]), (a, b)
+        assert abs(a[2] - b[2]) <= 25 * 3  # at most a few tie flips
