@@ -91,3 +91,21 @@ def test_lsm_small_and_odd_shapes(cuda, oracle, n, steps, deg):
         cuda.lsm_american(m, sim, (105.0, -1.0), 9, D)     # degree above the built maximum
     with pytest.raises(NotImplementedError):                # Q7: LSM on log-space schemes is rejected
         cuda.lsm_american(m, SimSpec(n_paths=n, n_steps=steps, scheme=abi.HH_SCHEME_EM), (105.0, -1.0), 2, D)
+
+
+def test_global_trajectory_index_beyond_32_bits(cuda, oracle):
+    """Shards deep into a huge job: the trajectory index fills both counter words of Philox (idx >> 32 != 0)."""
+    m = heston_model()
+    for prec, tol in ((abi.HH_PREC_F64, 1e-11), (abi.HH_PREC_F32, 5e-3)):
+        sim = SimSpec(n_paths=700, n_steps=9, precision=prec, base_seed=77, path_offset=(1 << 33) + 12345)
+        rg, tg = cuda.mc_european(m, sim, [(100.0, 1.0)], 1.0, want_terminal=True)
+        ro, to = oracle.mc_european(m, sim, [(100.0, 1.0)], 1.0, want_terminal=True)
+        assert rel_err(tg, to) < tol
+        near = SimSpec(n_paths=700, n_steps=9, precision=prec, base_seed=77, path_offset=12345)
+        _, t0 = cuda.mc_european(m, near, [(100.0, 1.0)], 1.0, want_terminal=True)
+        assert not np.allclose(t0, tg)  # a different part of the stream
+    g = gbm_model()
+    sim = SimSpec(n_paths=300, n_steps=6, scheme=abi.HH_SCHEME_EXACT_STEPS, base_seed=5, path_offset=(1 << 40) + 3)
+    og, _, _, pg = cuda.lsm_american(g, sim, (100.0, -1.0), 2, 0.99, want_paths=True)
+    oo, _, _, po = oracle.lsm_american(g, sim, (100.0, -1.0), 2, 0.99, want_paths=True)
+    assert rel_err(pg, po) < 1e-12
