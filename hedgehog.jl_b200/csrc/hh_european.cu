@@ -800,11 +800,23 @@ __global__ void __launch_bounds__(kThreads) heston_tangent_kernel(const EuroArgs
   constexpr int NSIDE = ANTI ? 2 : 1;
   constexpr int STAGE = NV * NSIDE * kThreads;
   constexpr int RED = NACC * kThreads;
-  __shared__ double smem[STAGE > RED ? STAGE : RED];
-  __shared__ FastNormalTables s_tables;
-  load_fast_tables(&s_tables);
-  __syncthreads();
+  constexpr int STAGE_DOUBLES = STAGE > RED ? STAGE : RED;
+  // dynamic shared memory: [payoff staging / reduction | log table x8 | trig table x8 | exponent table]
+  extern __shared__ __align__(16) unsigned char dsm[];
+  double *smem = reinterpret_cast<double *>(dsm);
+  char *s_log = reinterpret_cast<char *>(dsm) + STAGE_DOUBLES * 8;
+  char *s_trig = s_log + kLogRepBytes;
+  double *s_e2 = reinterpret_cast<double *>(s_trig + kTrigRepBytes);
   const int tid = threadIdx.x;
+  for (int e = tid; e < tables::kLog2Buckets * kRep; e += kThreads)
+    reinterpret_cast<double2 *>(s_log)[e] = g_fast_tables2.log_tab[e / kRep];
+  for (int e = tid; e < tables::kTrigN * kRep; e += kThreads)
+    reinterpret_cast<double2 *>(s_trig)[e] = g_fast_tables2.trig_tab[e / kRep];
+  for (int e = tid; e < tables::kExp2N; e += kThreads) s_e2[e] = g_fast_tables2.exp_tab[e];
+  __syncthreads();
+  const char *log_lane = s_log + (tid & (kRep - 1)) * 16;
+  const char *trig_lane = s_trig + (tid & (kRep - 1)) * 16;
+  const char *exp_biased = reinterpret_cast<const char *>(s_e2) - tables::kExp2Bias * 8;
   const int KP = 1 << a.kp_log2;
   const int k = tid & (KP - 1);
   const int g = tid >> a.kp_log2;
@@ -840,7 +852,7 @@ __global__ void __launch_bounds__(kThreads) heston_tangent_kernel(const EuroArgs
     for (int n = 0; n < M; ++n) {
       const u32x4 w = philox4x32_10((uint32_t)idx, (uint32_t)(idx >> 32), (uint32_t)n, 0u, (uint32_t)key, (uint32_t)(key >> 32));
       double z1, z2;
-      fast_normal_pair(&s_tables, w.x, w.y, w.z, w.w, z1, z2);
+      fast_normal_pair_v2(log_lane, exp_biased, trig_lane, w.x, w.y, w.z, w.w, a.one_hi, a.magic_hi, z1, z2);
       const double W1 = fma(a.p.a12, z2, a.p.a11 * z1);
       const double W2 = fma(a.f.b22, z2, a.f.b21 * z1);  // xi dW2
       heston_tangent_step<SPLIT, NF>(a.f, c, one_m_kdt, xp, vp, dxp, dvp, z1, z2, W1, W2);
@@ -1180,8 +1192,16 @@ template <bool ANTI, bool SPLIT, int NF, int P>
 static cudaError_t launch_tangent_one(const EuroArgs &a, const HestonTanConsts &c, int sm_count, cudaStream_t st, int *nblocks,
                                       bool query_only) {
   auto kern = heston_tangent_kernel<ANTI, SPLIT, NF, P>;
+  constexpr int NACC = 3 + 2 * P, STAGE = (1 + P) * (ANTI ? 2 : 1) * kThreads, RED = NACC * kThreads;
+  constexpr int smem = (STAGE > RED ? STAGE : RED) * 8 + kLogRepBytes + kTrigRepBytes + kExp2Bytes;
+  static bool attr_set = false;  // per instantiation
+  if (!attr_set) {
+    cudaError_t e0 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e0 != cudaSuccess) return e0;
+    attr_set = true;
+  }
   int occ = 0;
-  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, 0);
+  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, smem);
   if (e != cudaSuccess) return e;
   if (occ < 1) occ = 1;
   const int64_t batches = (a.n + kThreads - 1) / kThreads;
@@ -1189,7 +1209,7 @@ static cudaError_t launch_tangent_one(const EuroArgs &a, const HestonTanConsts &
   if (grid > batches) grid = batches;
   *nblocks = (int)grid;
   if (query_only) return cudaSuccess;
-  kern<<<(unsigned)grid, kThreads, 0, st>>>(a, c);
+  kern<<<(unsigned)grid, kThreads, smem, st>>>(a, c);
   return cudaGetLastError();
 }
 
@@ -1201,8 +1221,14 @@ static cudaError_t launch_tangent_as(const EuroArgs &a, const HestonTanConsts &c
   switch (P) {
     case 1: if (nf == 0) HH_TAN(0, 1); HH_TAN(1, 1);
     case 2: if (nf == 0) HH_TAN(0, 2); if (nf == 1) HH_TAN(1, 2); HH_TAN(2, 2);
-    case 4: if (nf == 0) HH_TAN(0, 4); if (nf <= 2) HH_TAN(2, 4); HH_TAN(4, 4);
-    default: if (nf <= 2) HH_TAN(2, 8); if (nf <= 4) HH_TAN(4, 8); if (nf <= 6) HH_TAN(6, 8); HH_TAN(8, 8);
+    case 4: if (nf == 0) HH_TAN(0, 4); if (nf <= 2) HH_TAN(2, 4); if (nf == 3) HH_TAN(3, 4); HH_TAN(4, 4);
+    default:
+      if (nf <= 2) HH_TAN(2, 8);
+      if (nf <= 4) HH_TAN(4, 8);
+      if (nf == 5) HH_TAN(5, 8);  // C5: V0, kappa, theta, xi, rho (+ the trivial S0, r)
+      if (nf == 6) HH_TAN(6, 8);
+      if (nf == 7) HH_TAN(7, 8);
+      HH_TAN(8, 8);
   }
 #undef HH_TAN
 }
