@@ -258,15 +258,19 @@ def main():
            "note": "hedgehog_jl_b200.solve(problem, method): scalars + payoff array in, [sum, sumsq, nonfinite] out, "
                    "allreduce of the partial sums across ranks; MonteCarloSolution.ensemble not requested"}
     if world == 1 and not args.skip_ensemble:
-        # the reference also returns the terminal price vector (MonteCarloSolution.ensemble): 8 B per trajectory D2H
+        # the reference also returns the terminal price vector (MonteCarloSolution.ensemble): 8 B per trajectory D2H,
+        # staged through a pinned double buffer into the caller's pageable array (one untimed call sizes the buffers)
+        sol = hh.solve(*c2_problem(hh, total_paths, args.nsteps, args.precision, ensemble=True, base_seed=3999), engine=eng)
+        del sol
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        sol = hh.solve(*c2_problem(hh, total_paths, args.nsteps, args.precision, ensemble=True, base_seed=4000), engine=eng)
+        for k in range(2):
+            sol = hh.solve(*c2_problem(hh, total_paths, args.nsteps, args.precision, ensemble=True, base_seed=4000 + k), engine=eng)
+            del sol
         torch.cuda.synchronize()
-        dt_e = time.perf_counter() - t0
+        dt_e = (time.perf_counter() - t0) / 2
         e2e["with_ensemble"] = {"value": path_steps_per_step / dt_e, "unit": UNIT, "d2h_bytes_per_step": 8 * total_paths,
                                 "seconds": dt_e}
-        del sol
 
     # ---- Float32 fast mode of the same workload (config C2 "Float32 fast mode"): reported beside, not as `value` ------
     f32 = None

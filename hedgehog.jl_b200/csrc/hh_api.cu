@@ -102,6 +102,10 @@ int hh_destroy(hh_ctx *ctx) {
     if (q != ctx->peer_rank && ctx->peer_mail[q]) cudaIpcCloseMemHandle(ctx->peer_mail[q]);
   if (ctx->mailbox) cudaFree(ctx->mailbox);
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+  for (int b = 0; b < 2; ++b) {
+    if (ctx->h_stage[b]) cudaFreeHost(ctx->h_stage[b]);
+    if (ctx->ev_stage[b]) cudaEventDestroy(ctx->ev_stage[b]);
+  }
   cudaEventDestroy(ctx->ev0);
   cudaEventDestroy(ctx->ev1);
   cudaEventDestroy(ctx->ev2);

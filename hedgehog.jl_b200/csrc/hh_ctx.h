@@ -70,6 +70,8 @@ struct hh_ctx {
   double bk_stats[5] = {0, 0, 0, 0, 0};
   void *h_pinned = nullptr;  // small pinned staging area for results
   size_t h_pinned_cap = 0;
+  void *h_stage[2] = {nullptr, nullptr};  // pinned double buffer for large device -> pageable-host copies
+  cudaEvent_t ev_stage[2] = {nullptr, nullptr};
   hh::PendingEuropean pend;
 
   int fail(int code, const char *fmt, ...) {

@@ -15,6 +15,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <thread>
 #include <vector>
 
 #include "hh_ctx.h"
@@ -1444,6 +1445,51 @@ int terminal_payoffs_launch(hh_ctx *ctx, const double *d_terminal, int64_t n, co
   return HH_OK;
 }
 
+// Large device -> host copies into the CALLER's pageable buffer (MonteCarloSolution.ensemble: 800 MB at config C2).
+// A plain cudaMemcpy to pageable memory runs at ~4 GB/s here (the driver stages it and the fresh pages fault in one by
+// one). Instead: 32 MB chunks DMA into a pinned double buffer on the stream while a few host threads copy the previous
+// chunk into the caller's buffer (first-touch page faults in parallel).
+static int copy_to_pageable_host(hh_ctx *ctx, void *dst, const void *src_dev, size_t bytes, cudaStream_t st) {
+  constexpr size_t kChunk = (size_t)32 << 20;
+  if (bytes < 2 * kChunk) {
+    HH_CUDA(ctx, cudaMemcpyAsync(dst, src_dev, bytes, cudaMemcpyDeviceToHost, st));
+    return HH_OK;
+  }
+  for (int b = 0; b < 2; ++b) {
+    if (!ctx->h_stage[b]) HH_CUDA(ctx, cudaHostAlloc(&ctx->h_stage[b], kChunk, cudaHostAllocDefault));
+    if (!ctx->ev_stage[b]) HH_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_stage[b], cudaEventDisableTiming));
+  }
+  const size_t nchunks = (bytes + kChunk - 1) / kChunk;
+  auto chunk_bytes = [&](size_t i) { return i + 1 < nchunks ? kChunk : bytes - i * kChunk; };
+  auto issue = [&](size_t i) -> cudaError_t {
+    cudaError_t e = cudaMemcpyAsync(ctx->h_stage[i & 1], static_cast<const char *>(src_dev) + i * kChunk, chunk_bytes(i),
+                                    cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaEventRecord(ctx->ev_stage[i & 1], st);
+    return e;
+  };
+  unsigned hw = std::thread::hardware_concurrency();
+  const int nthreads = (int)(hw == 0 ? 4 : hw > 8 ? 8 : hw);
+  HH_CUDA(ctx, issue(0));
+  if (nchunks > 1) HH_CUDA(ctx, issue(1));
+  for (size_t i = 0; i < nchunks; ++i) {
+    HH_CUDA(ctx, cudaEventSynchronize(ctx->ev_stage[i & 1]));
+    const size_t nb = chunk_bytes(i);
+    char *d = static_cast<char *>(dst) + i * kChunk;
+    const char *sp = static_cast<const char *>(ctx->h_stage[i & 1]);
+    std::vector<std::thread> pool;
+    const size_t per = ((nb / nthreads) + 4095) & ~(size_t)4095;
+    for (int t = 0; t < nthreads; ++t) {
+      const size_t o = (size_t)t * per;
+      if (o >= nb) break;
+      const size_t len = o + per < nb ? per : nb - o;
+      pool.emplace_back([=] { memcpy(d + o, sp + o, len); });
+    }
+    for (auto &th : pool) th.join();
+    if (i + 2 < nchunks) HH_CUDA(ctx, issue(i + 2));  // the buffer just drained
+  }
+  return HH_OK;
+}
+
 int european_collect(hh_ctx *ctx, double discount, hh_result *results, double *terminal, size_t terminal_len) {
   if (!ctx->pend.active) return ctx->fail(HH_ERR_ARG, "collect without a pending launch");
   const int npay = ctx->pend.npay;
@@ -1459,8 +1505,10 @@ int european_collect(hh_ctx *ctx, double discount, hh_result *results, double *t
   cudaStream_t st = ctx->stream;
   std::vector<double> fin((size_t)npay * NACC);
   HH_CUDA(ctx, cudaMemcpyAsync(fin.data(), ctx->d_final.ptr, sizeof(double) * fin.size(), cudaMemcpyDeviceToHost, st));
-  if (terminal)
-    HH_CUDA(ctx, cudaMemcpyAsync(terminal, ctx->d_terminal.ptr, sizeof(double) * tlen, cudaMemcpyDeviceToHost, st));
+  if (terminal) {
+    const int rc = copy_to_pageable_host(ctx, terminal, ctx->d_terminal.ptr, sizeof(double) * tlen, st);
+    if (rc) return rc;
+  }
   unsigned long long counters[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   if (ctx->pend.bk)
     HH_CUDA(ctx, cudaMemcpyAsync(counters, ctx->d_counters.ptr, sizeof counters, cudaMemcpyDeviceToHost, st));
