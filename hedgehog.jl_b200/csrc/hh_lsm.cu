@@ -175,7 +175,7 @@ struct LsmPassArgs {
   int32_t *tau;          // nullable
   const LsmFit *fit_next;
   double *partials;      // [grid][nacc]
-  double D, strike, cp, ua, ub;
+  double Dp, rscale, strike, cp, ua, ub;  // Dp = D^(t+1); rscale = D^-t turns the time-0 sums into date-t money for the fit
   int t_next;
   int first;  // t+1 is the terminal date: z = payoff(S_M)
   int last;   // t = 0: no regression, accumulate sum / sumsq of D z
@@ -219,24 +219,30 @@ __host__ __device__ constexpr int lsm_nacc() { return 3 * DEG + 3; }
 //                     through the linear recurrence, so every sum is an unconditional add / fma.
 // Sign tests read the high word of the double on the integer pipe (x > 0 <=> hi(x) > 0 for the values that occur:
 // cp (S - K) is either 0 or at least one ulp of S).
+// Cash flows are kept in TIME-0 money, z = D^tau v (what the reference averages at the end, :132-133): a column's z only
+// changes when it is exercised, so most columns are never rewritten (the pass is L2-throughput bound and z stores were a
+// sixth of its L2 traffic), and the regression target of date t, D^(tau-t) v (:117-118), is z D^-t — a factor common to
+// all columns that is applied to the right-hand-side sums in the fit instead of per column.
 template <int DEG, bool FIRST, bool LAST, bool TAU, class A>
 __device__ __forceinline__ void lsm_column(const A &a, const double *q, double cpK, double sn, double sc,
-                                           double zin, int64_t p, double &zout, double *acc, int &cnt) {
+                                           double zin, int64_t p, double &zout, bool &changed, double *acc, int &cnt) {
   constexpr int NM = 2 * DEG + 1;
   const double e = fma(a.cp, sn, -cpK);
+  const double e_now = e * a.Dp;  // exercise value at date t+1 in time-0 money, Dp = D^(t+1)
   double zz;
   if (FIRST) {
-    zz = __double2hiint(e) > 0 ? e : 0.0;  // stopping_info = (nsteps, payoff(S_T))  :112
+    zz = __double2hiint(e) > 0 ? e_now : 0.0;  // stopping_info = (nsteps, payoff(S_T))  :112
+    changed = true;
   } else {
     const double un = fma(a.ua, sn, a.ub);
-    double cont = q[DEG];  // poly.(x)  :127
+    double cont = q[DEG];  // poly.(x)  :127  (in date-(t+1) money, like e)
 #pragma unroll
     for (int k = DEG - 1; k >= 0; --k) cont = fma(cont, un, q[k]);
     const bool ex = (__double2hiint(e) > 0) && (e > cont);
-    zz = ex ? e : zin;
+    zz = ex ? e_now : zin;
+    changed = ex;
     if (TAU && ex) a.tau[p] = a.t_next;
   }
-  zz *= a.D;  // discount^(tau - t) one date at a time  :117-118
   zout = zz;
   if (LAST) {
     acc[0] += zz;
@@ -314,13 +320,13 @@ __device__ __forceinline__ double rsqrt_fast(double d) {
 // coefficients), the leading block that factorises is used (a lower-degree fit in the same nested basis).
 // DEG is a compile-time constant so that every array lives in registers.
 template <int DEG>
-__device__ __forceinline__ void lsm_fit(const double *moments, LsmFit *out) {
+__device__ __forceinline__ void lsm_fit(const double *moments, double rscale, LsmFit *out) {
   constexpr int nm = 2 * DEG + 1;
   double m[nm], r[DEG + 1];
 #pragma unroll
   for (int k = 0; k < nm; ++k) m[k] = moments[k];
 #pragma unroll
-  for (int k = 0; k <= DEG; ++k) r[k] = moments[nm + k];
+  for (int k = 0; k <= DEG; ++k) r[k] = moments[nm + k] * rscale;  // time-0 money -> date-t money
   const double count = moments[nm + DEG + 1];
   double c[DEG + 1];
 #pragma unroll
@@ -402,8 +408,8 @@ __device__ __forceinline__ void lsm_fit(const double *moments, LsmFit *out) {
 }
 
 template <int DEG>
-__global__ void lsm_fit_kernel(const double *moments, LsmFit *out) {
-  if (threadIdx.x == 0) lsm_fit<DEG>(moments, out);
+__global__ void lsm_fit_kernel(const double *moments, double rscale, LsmFit *out) {
+  if (threadIdx.x == 0) lsm_fit<DEG>(moments, rscale, out);
 }
 
 // Peer exchange, called by ONE block per rank with all its threads (one process per GPU, mailboxes mapped through CUDA
@@ -489,7 +495,7 @@ __device__ __forceinline__ void lsm_pass_tail(const LsmPassArgs &a, double *acc,
   __syncthreads();
   if (a.px.world > 1) lsm_peer_exchange(a.px, a.px.epoch, a.moments, NACC);
   if (tid == 0) {
-    if (a.fit_out) lsm_fit<DEG>(a.moments, a.fit_out);
+    if (a.fit_out) lsm_fit<DEG>(a.moments, a.rscale, a.fit_out);
     *a.done = 0u;
   }
 }
@@ -534,9 +540,10 @@ __global__ void __launch_bounds__(kLsmThreads) lsm_pass_kernel(const LsmPassArgs
   };
   auto work = [&](const double2 &sn, const double2 &sc, const double2 &zi, double2 *zdst, int64_t col) {
     double2 zo;
-    lsm_column<DEG, FIRST, LAST, TAU>(a, q, cpK, sn.x, sc.x, zi.x, col, zo.x, acc, cnt);
-    lsm_column<DEG, FIRST, LAST, TAU>(a, q, cpK, sn.y, sc.y, zi.y, col + 1, zo.y, acc, cnt);
-    *zdst = zo;
+    bool cx, cy;
+    lsm_column<DEG, FIRST, LAST, TAU>(a, q, cpK, sn.x, sc.x, zi.x, col, zo.x, cx, acc, cnt);
+    lsm_column<DEG, FIRST, LAST, TAU>(a, q, cpK, sn.y, sc.y, zi.y, col + 1, zo.y, cy, acc, cnt);
+    if (cx || cy) *zdst = zo;
   };
   if (iters > 0) load(snA, scA, ziA);
   int it = 0;
@@ -556,8 +563,9 @@ __global__ void __launch_bounds__(kLsmThreads) lsm_pass_kernel(const LsmPassArgs
   if ((a.ncols & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
     const int64_t p = a.ncols - 1;
     double zo;
-    lsm_column<DEG, FIRST, LAST, TAU>(a, q, cpK, a.S_next[p], LAST ? 0.0 : a.S_cur[p], FIRST ? 0.0 : a.z[p], p, zo, acc, cnt);
-    a.z[p] = zo;
+    bool ch;
+    lsm_column<DEG, FIRST, LAST, TAU>(a, q, cpK, a.S_next[p], LAST ? 0.0 : a.S_cur[p], FIRST ? 0.0 : a.z[p], p, zo, ch, acc, cnt);
+    if (ch) a.z[p] = zo;
   }
   lsm_pass_tail<DEG, LAST>(a, acc, cnt, s_red, s_scratch, &s_last);
 }
@@ -638,16 +646,18 @@ __global__ void __launch_bounds__(kLsmThreads) lsm_pass_tma_kernel(const LsmPass
     if (mine) {
       const int64_t col = c0 + 2 * tid;
       double2 zo;
-      lsm_column<DEG, FIRST, LAST, TAU>(a, q, cpK, sn.x, sc.x, zi.x, col, zo.x, acc, cnt);
-      lsm_column<DEG, FIRST, LAST, TAU>(a, q, cpK, sn.y, sc.y, zi.y, col + 1, zo.y, acc, cnt);
-      *reinterpret_cast<double2 *>(a.z + col) = zo;
+      bool cx, cy;
+      lsm_column<DEG, FIRST, LAST, TAU>(a, q, cpK, sn.x, sc.x, zi.x, col, zo.x, cx, acc, cnt);
+      lsm_column<DEG, FIRST, LAST, TAU>(a, q, cpK, sn.y, sc.y, zi.y, col + 1, zo.y, cy, acc, cnt);
+      if (cx || cy) *reinterpret_cast<double2 *>(a.z + col) = zo;
     }
   }
   if ((a.ncols & 1) && blockIdx.x == 0 && tid == 0) {
     const int64_t p = a.ncols - 1;
     double zo;
-    lsm_column<DEG, FIRST, LAST, TAU>(a, q, cpK, a.S_next[p], LAST ? 0.0 : a.S_cur[p], FIRST ? 0.0 : a.z[p], p, zo, acc, cnt);
-    a.z[p] = zo;
+    bool ch;
+    lsm_column<DEG, FIRST, LAST, TAU>(a, q, cpK, a.S_next[p], LAST ? 0.0 : a.S_cur[p], FIRST ? 0.0 : a.z[p], p, zo, ch, acc, cnt);
+    if (ch) a.z[p] = zo;
   }
   lsm_pass_tail<DEG, LAST>(a, acc, cnt, s_red, &s_next[0][0] /* the ring is idle by now */, &s_last);
 }
@@ -670,12 +680,13 @@ struct LsmBackArgs {
   unsigned int *gflag;     // generation of gmom
   double *moments_out;     // final [sum, sumsq, count]
   LsmFit *fits;            // [M+1], written by block 0 (statistics for the host)
-  double D, strike, cp, ua, ub;
+  double logD, strike, cp, ua, ub;  // logD = log of the one-step discount factor
   int M;
   PeerX px;                // px.epoch = epoch of the first exchanged date minus one
+  int z_policy, cur_policy;  // L2 hints of the bulk loads: 0 none, 1 evict_last, 2 evict_first
 };
 struct LsmColArgs {
-  double cp, ua, ub, D;
+  double cp, ua, ub, Dp;
   int32_t *tau;
   int t_next;
 };
@@ -693,37 +704,86 @@ __device__ __forceinline__ void lsm_grid_barrier(unsigned int *counter, unsigned
   __syncthreads();
 }
 
+constexpr int kBackCpt = 2;                            // columns per consumer thread and chunk (4: 2.24 ms, 2: 2.07 ms at C3)
+constexpr int kBackChunk = kBackCpt * kLsmThreads;     // 512 columns: 4 KB per array, 12 KB per stage
+constexpr int kBackStages = 4;
+constexpr int kBackSmem = kBackStages * 3 * kBackChunk * 8;
+constexpr int kBackThreads = kLsmThreads + 32;         // 8 consumer warps + 1 producer warp
+
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
+}
+
+// Warp-specialised: warp 8 is the producer (one lane issues the bulk copies as ring slots drain), warps 0-7 consume.
+// ncu on the version whose consumers met at a __syncthreads per chunk (profiles/r1_j_ncu_lsm_backward.csv): "barrier" was the
+// top stall (2.4 cycles per issue), issue slots 49 % busy, DRAM 49 %. Here a consumer warp announces that it has taken
+// its columns out of a stage by arriving on the stage's `empty` mbarrier and goes on computing; only the producer waits.
 template <int DEG, bool TAU>
-__global__ void __launch_bounds__(kLsmThreads) lsm_backward_kernel(const LsmBackArgs a) {
+__global__ void __launch_bounds__(kBackThreads) lsm_backward_kernel(const LsmBackArgs a) {
   constexpr int NACC = lsm_nacc<DEG>();
   constexpr int NM = 2 * DEG + 1;
-  __shared__ __align__(128) double s_next[kLsmStages][kLsmChunk];
-  __shared__ __align__(128) double s_cur[kLsmStages][kLsmChunk];
-  __shared__ __align__(128) double s_z[kLsmStages][kLsmChunk];
-  __shared__ __align__(8) uint64_t s_full[kLsmStages];
-  __shared__ double s_red[NACC][kLsmThreads / 32];
+  constexpr int NCW = kLsmThreads / 32;  // consumer warps
+  // ring in dynamic shared memory: [stage][array (next, cur, z)][kBackChunk doubles]
+  extern __shared__ __align__(128) unsigned char dsm_back[];
+  double *ring = reinterpret_cast<double *>(dsm_back);
+  auto s_next = [&](int s) { return ring + ((size_t)s * 3 + 0) * kBackChunk; };
+  auto s_cur = [&](int s) { return ring + ((size_t)s * 3 + 1) * kBackChunk; };
+  auto s_z = [&](int s) { return ring + ((size_t)s * 3 + 2) * kBackChunk; };
+  __shared__ __align__(8) uint64_t s_full[kBackStages], s_empty[kBackStages];
+  __shared__ double s_red[NACC][NCW];
   __shared__ double s_mom[32];
-  __shared__ double s_scratch[kLsmThreads];  // the ring is never idle here (next date primed before the barrier)
+  __shared__ double s_scratch[kBackThreads + 32];
   __shared__ LsmFit s_fit;
   const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const bool producer = warp == NCW;
   if (tid == 0) {
 #pragma unroll
-    for (int s = 0; s < kLsmStages; ++s) mbar_init(&s_full[s], 1);
+    for (int s = 0; s < kBackStages; ++s) {
+      mbar_init(&s_full[s], 1);
+      mbar_init(&s_empty[s], NCW);
+    }
     mbar_fence_init();
   }
   __syncthreads();
   const double cpK = a.cp * a.strike;
   const int64_t neven = a.ncols & ~(int64_t)1;
-  const int64_t nchunks = (neven + kLsmChunk - 1) / kLsmChunk;
+  const int64_t nchunks = (neven + kBackChunk - 1) / kBackChunk;
+  const int64_t cstep = (int64_t)gridDim.x * kBackChunk;
   const int my_chunks = (int64_t)blockIdx.x < nchunks ? (int)((nchunks - 1 - blockIdx.x) / gridDim.x) + 1 : 0;
   const uint64_t pol_first = l2_policy_evict_first();
-  unsigned int seq = 0;  // chunks consumed so far by this block, over all dates: ring stage and mbarrier parity
+  const uint64_t pol_last = l2_policy_evict_last();
+  unsigned int seq = 0;  // chunks of this block so far, over all dates (same count on both sides): ring slot and phase
   LsmColArgs ca;
   ca.cp = a.cp;
   ca.ua = a.ua;
   ca.ub = a.ub;
-  ca.D = a.D;
   ca.tau = a.tau;
+
+  // one lane of the producer warp: chunk i of date `td` (its S_next = G[td+1]) into ring position `at`, after the
+  // consumers have drained what was there
+  auto issue_date = [&](int td, int i, unsigned int at) {
+    const bool f = (td + 1 == a.M), l = (td == 0);
+    const int s = (int)(at % kBackStages);
+    mbar_wait(&s_empty[s], ((at / kBackStages) & 1u) ^ 1u);  // passes at once the first time round the ring
+    const int64_t c0 = (int64_t)blockIdx.x * kBackChunk + (int64_t)i * cstep;
+    const int64_t ncol = neven - c0 < kBackChunk ? neven - c0 : kBackChunk;
+    const uint32_t bytes = (uint32_t)ncol * 8u;
+    mbar_arrive_expect_tx(&s_full[s], bytes * (1u + (l ? 0u : 1u) + (f ? 0u : 1u)));
+    bulk_load_hint(s_next(s), a.G + (size_t)(td + 1) * a.stride + c0, bytes, &s_full[s], pol_first);  // dead after date td
+    if (!l) {
+      if (a.cur_policy == 0) bulk_load(s_cur(s), a.G + (size_t)td * a.stride + c0, bytes, &s_full[s]);
+      else bulk_load_hint(s_cur(s), a.G + (size_t)td * a.stride + c0, bytes, &s_full[s], a.cur_policy == 1 ? pol_last : pol_first);
+    }
+    if (!f) {
+      if (a.z_policy == 0) bulk_load(s_z(s), a.z + c0, bytes, &s_full[s]);
+      else bulk_load_hint(s_z(s), a.z + c0, bytes, &s_full[s], a.z_policy == 1 ? pol_last : pol_first);
+    }
+  };
+  const int nprime = my_chunks < kBackStages ? my_chunks : kBackStages;  // chunks of a date issued ahead of its start
+  if (producer && lane == 0) {
+    for (int i = 0; i < nprime; ++i) issue_date(a.M - 1, i, (unsigned)i);
+  }
 
   for (int t = a.M - 1; t >= 0; --t) {
     const int date = a.M - 1 - t;  // 0, 1, ...
@@ -731,6 +791,7 @@ __global__ void __launch_bounds__(kLsmThreads) lsm_backward_kernel(const LsmBack
     const double *S_next = a.G + (size_t)(t + 1) * a.stride;
     const double *S_cur = a.G + (size_t)t * a.stride;
     ca.t_next = t + 1;
+    ca.Dp = exp((double)(t + 1) * a.logD);
     double q[DEG + 1];
 #pragma unroll
     for (int k = 0; k <= DEG; ++k) q[k] = first ? 0.0 : s_fit.q[k];
@@ -739,91 +800,92 @@ __global__ void __launch_bounds__(kLsmThreads) lsm_backward_kernel(const LsmBack
     for (int c = 0; c < NACC; ++c) acc[c] = 0.0;
     int cnt = 0;
 
-    // thread 0 only: chunk i of date `td` (its S_next = G[td+1]) into ring position `at`
-    auto issue_date = [&](int td, int i, unsigned int at) {
-      const bool f = (td + 1 == a.M), l = (td == 0);
-      const int s = (int)(at % kLsmStages);
-      const int64_t c0 = ((int64_t)blockIdx.x + (int64_t)i * gridDim.x) * kLsmChunk;
-      const int64_t ncol = neven - c0 < kLsmChunk ? neven - c0 : kLsmChunk;
-      const uint32_t bytes = (uint32_t)ncol * 8u;
-      mbar_arrive_expect_tx(&s_full[s], bytes * (1u + (l ? 0u : 1u) + (f ? 0u : 1u)));
-      bulk_load_hint(&s_next[s][0], a.G + (size_t)(td + 1) * a.stride + c0, bytes, &s_full[s], pol_first);  // dead after date td
-      if (!l) bulk_load(&s_cur[s][0], a.G + (size_t)td * a.stride + c0, bytes, &s_full[s]);
-      if (!f) bulk_load(&s_z[s][0], a.z + c0, bytes, &s_full[s]);
-    };
-    auto issue = [&](int i, unsigned int at) { issue_date(t, i, at); };
-    if (tid == 0 && first) {  // later dates were primed before the previous grid barrier
-      for (int i = 0; i < kLsmStages && i < my_chunks; ++i) issue(i, seq + (unsigned)i);
+    if (producer) {
+      // the first nprime chunks of this date are already in flight (issued before the previous grid barrier)
+      if (lane == 0)
+        for (int i = nprime; i < my_chunks; ++i) issue_date(t, i, seq + (unsigned)i);
+      seq += (unsigned)my_chunks;
+    } else {
+      auto chunks = [&](auto first_c, auto last_c) {
+        constexpr bool F = decltype(first_c)::value, L = decltype(last_c)::value;
+        int64_t c0 = (int64_t)blockIdx.x * kBackChunk;
+        for (int i = 0; i < my_chunks; ++i, ++seq, c0 += cstep) {
+          const int s = (int)(seq % kBackStages);
+          const uint32_t parity = (seq / kBackStages) & 1u;
+          const int ncol = (int)(neven - c0 < kBackChunk ? neven - c0 : kBackChunk);
+          mbar_wait(&s_full[s], parity);
+          // kBackCpt / 2 column pairs per thread, a block-wide stride apart (conflict-free 16 B shared loads)
+          double2 sn[kBackCpt / 2], sc[kBackCpt / 2], zi[kBackCpt / 2];
+#pragma unroll
+          for (int h = 0; h < kBackCpt / 2; ++h) {
+            const int pr = tid + h * kLsmThreads;
+            sn[h] = sc[h] = zi[h] = make_double2(0.0, 0.0);
+            if (2 * pr < ncol) {
+              sn[h] = reinterpret_cast<const double2 *>(s_next(s))[pr];
+              if (!L) sc[h] = reinterpret_cast<const double2 *>(s_cur(s))[pr];
+              if (!F) zi[h] = reinterpret_cast<const double2 *>(s_z(s))[pr];
+            }
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&s_empty[s]);  // this warp has taken its columns out of stage s
+#pragma unroll
+          for (int h = 0; h < kBackCpt / 2; ++h) {
+            const int pr = tid + h * kLsmThreads;
+            if (2 * pr < ncol) {
+              const int64_t col = c0 + 2 * pr;
+              double2 zo;
+              bool cx, cy;
+              lsm_column<DEG, F, L, TAU>(ca, q, cpK, sn[h].x, sc[h].x, zi[h].x, col, zo.x, cx, acc, cnt);
+              lsm_column<DEG, F, L, TAU>(ca, q, cpK, sn[h].y, sc[h].y, zi[h].y, col + 1, zo.y, cy, acc, cnt);
+              if (cx || cy) *reinterpret_cast<double2 *>(a.z + col) = zo;
+            }
+          }
+        }
+        if ((a.ncols & 1) && blockIdx.x == 0 && tid == 0) {
+          const int64_t p = a.ncols - 1;
+          double zo;
+          bool ch;
+          lsm_column<DEG, F, L, TAU>(ca, q, cpK, S_next[p], L ? 0.0 : S_cur[p], F ? 0.0 : a.z[p], p, zo, ch, acc, cnt);
+          if (ch) a.z[p] = zo;
+        }
+        if (L) {
+          acc[2] = (double)cnt;
+        } else {
+          acc[0] = (double)cnt;
+          acc[NM + DEG + 1] = (double)cnt;
+        }
+      };
+      using T_ = std::true_type;
+      using F_ = std::false_type;
+      if (first && last) chunks(T_{}, T_{});
+      else if (first) chunks(T_{}, F_{});
+      else if (last) chunks(F_{}, T_{});
+      else chunks(F_{}, F_{});
     }
-    auto chunks = [&](auto first_c, auto last_c) {
-      constexpr bool F = decltype(first_c)::value, L = decltype(last_c)::value;
-      for (int i = 0; i < my_chunks; ++i, ++seq) {
-        const int s = (int)(seq % kLsmStages);
-        const uint32_t parity = (seq / kLsmStages) & 1u;
-        const int64_t c0 = ((int64_t)blockIdx.x + (int64_t)i * gridDim.x) * kLsmChunk;
-        const int64_t ncol = neven - c0 < kLsmChunk ? neven - c0 : kLsmChunk;
-        const bool mine = 2 * tid < ncol;
-        mbar_wait(&s_full[s], parity);
-        double2 sn = make_double2(0.0, 0.0), sc = sn, zi = sn;
-        if (mine) {
-          sn = reinterpret_cast<const double2 *>(&s_next[s][0])[tid];
-          if (!L) sc = reinterpret_cast<const double2 *>(&s_cur[s][0])[tid];
-          if (!F) zi = reinterpret_cast<const double2 *>(&s_z[s][0])[tid];
-        }
-        __syncthreads();  // every thread has taken its columns out of stage s
-        if (tid == 0 && i + kLsmStages < my_chunks) issue(i + kLsmStages, seq + kLsmStages);
-        if (mine) {
-          const int64_t col = c0 + 2 * tid;
-          double2 zo;
-          lsm_column<DEG, F, L, TAU>(ca, q, cpK, sn.x, sc.x, zi.x, col, zo.x, acc, cnt);
-          lsm_column<DEG, F, L, TAU>(ca, q, cpK, sn.y, sc.y, zi.y, col + 1, zo.y, acc, cnt);
-          *reinterpret_cast<double2 *>(a.z + col) = zo;
-        }
-      }
-      if ((a.ncols & 1) && blockIdx.x == 0 && tid == 0) {
-        const int64_t p = a.ncols - 1;
-        double zo;
-        lsm_column<DEG, F, L, TAU>(ca, q, cpK, S_next[p], L ? 0.0 : S_cur[p], F ? 0.0 : a.z[p], p, zo, acc, cnt);
-        a.z[p] = zo;
-      }
-      if (L) {
-        acc[2] = (double)cnt;
-      } else {
-        acc[0] = (double)cnt;
-        acc[NM + DEG + 1] = (double)cnt;
-      }
-    };
-    using T_ = std::true_type;
-    using F_ = std::false_type;
-    if (first && last) chunks(T_{}, T_{});
-    else if (first) chunks(T_{}, F_{});
-    else if (last) chunks(F_{}, T_{});
-    else chunks(F_{}, F_{});
 
-    // block reduction -> partials[date parity][block]
+    // block reduction -> partials[date parity][block] (the producer warp holds zeros and stays out)
     double *part = a.partials + (size_t)(date & 1) * gridDim.x * NACC;
-    const int lane = tid & 31, warp = tid >> 5;
+    if (!producer) {
 #pragma unroll
-    for (int c = 0; c < NACC; ++c) {
-      double v = acc[c];
+      for (int c = 0; c < NACC; ++c) {
+        double v = acc[c];
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-      if (lane == 0) s_red[c][warp] = v;
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if (lane == 0) s_red[c][warp] = v;
+      }
     }
+    // this block's z stores of the date must be ordered before the bulk copies (async proxy) that re-read them
+    asm volatile("fence.proxy.async;" ::: "memory");
     __syncthreads();
     if (tid < NACC) {
       double v = 0.0;
 #pragma unroll
-      for (int w = 0; w < kLsmThreads / 32; ++w) v += s_red[tid][w];
+      for (int w = 0; w < NCW; ++w) v += s_red[tid][w];
       part[(size_t)blockIdx.x * NACC + tid] = v;
     }
-    // prime the ring with the first chunks of the NEXT date while this block waits at the barrier and fits: the
-    // chunks are this block's own (fixed ownership), so its z stores of this date only need to be ordered before the
-    // bulk copies of the async proxy (fence.proxy.async by every writer, then the block barrier)
-    asm volatile("fence.proxy.async;" ::: "memory");
-    __syncthreads();
-    if (tid == 0 && !last) {
-      for (int i = 0; i < kLsmStages && i < my_chunks; ++i) issue_date(t - 1, i, seq + (unsigned)i);
+    // prime the ring with the first chunks of the NEXT date while the block waits at the grid barrier and fits
+    if (producer && lane == 0 && !last) {
+      for (int i = 0; i < nprime; ++i) issue_date(t - 1, i, seq + (unsigned)i);
     }
     lsm_grid_barrier(a.barrier, (unsigned)(date + 1) * gridDim.x);
 
@@ -859,7 +921,7 @@ __global__ void __launch_bounds__(kLsmThreads) lsm_backward_kernel(const LsmBack
       }
     }
     if (tid == 0) {
-      lsm_fit<DEG>(s_mom, &s_fit);
+      lsm_fit<DEG>(s_mom, exp(-(double)t * a.logD), &s_fit);
       if (blockIdx.x == 0) a.fits[t] = s_fit;
     }
     __syncthreads();
@@ -942,17 +1004,17 @@ static int pass_occupancy_deg(int deg) {
   }
 }
 
-static void launch_fit_deg(int deg, const double *moments, LsmFit *out, cudaStream_t st) {
+static void launch_fit_deg(int deg, const double *moments, double rscale, LsmFit *out, cudaStream_t st) {
   switch (deg) {
-    case 0: lsm_fit_kernel<0><<<1, 32, 0, st>>>(moments, out); break;
-    case 1: lsm_fit_kernel<1><<<1, 32, 0, st>>>(moments, out); break;
-    case 2: lsm_fit_kernel<2><<<1, 32, 0, st>>>(moments, out); break;
-    case 3: lsm_fit_kernel<3><<<1, 32, 0, st>>>(moments, out); break;
-    case 4: lsm_fit_kernel<4><<<1, 32, 0, st>>>(moments, out); break;
-    case 5: lsm_fit_kernel<5><<<1, 32, 0, st>>>(moments, out); break;
-    case 6: lsm_fit_kernel<6><<<1, 32, 0, st>>>(moments, out); break;
-    case 7: lsm_fit_kernel<7><<<1, 32, 0, st>>>(moments, out); break;
-    default: lsm_fit_kernel<8><<<1, 32, 0, st>>>(moments, out); break;
+    case 0: lsm_fit_kernel<0><<<1, 32, 0, st>>>(moments, rscale, out); break;
+    case 1: lsm_fit_kernel<1><<<1, 32, 0, st>>>(moments, rscale, out); break;
+    case 2: lsm_fit_kernel<2><<<1, 32, 0, st>>>(moments, rscale, out); break;
+    case 3: lsm_fit_kernel<3><<<1, 32, 0, st>>>(moments, rscale, out); break;
+    case 4: lsm_fit_kernel<4><<<1, 32, 0, st>>>(moments, rscale, out); break;
+    case 5: lsm_fit_kernel<5><<<1, 32, 0, st>>>(moments, rscale, out); break;
+    case 6: lsm_fit_kernel<6><<<1, 32, 0, st>>>(moments, rscale, out); break;
+    case 7: lsm_fit_kernel<7><<<1, 32, 0, st>>>(moments, rscale, out); break;
+    default: lsm_fit_kernel<8><<<1, 32, 0, st>>>(moments, rscale, out); break;
   }
 }
 
@@ -973,8 +1035,14 @@ static cudaError_t launch_pass_deg(int deg, const LsmPassArgs &a, int grid, cuda
 template <int DEG, bool TAU>
 static cudaError_t launch_backward(const LsmBackArgs &b, int sm_count, int64_t nchunks, cudaStream_t st, bool query_only, int *grid_out) {
   auto kern = lsm_backward_kernel<DEG, TAU>;
+  static bool attr_set = false;  // per instantiation
+  if (!attr_set) {
+    cudaError_t e0 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kBackSmem);
+    if (e0 != cudaSuccess) return e0;
+    attr_set = true;
+  }
   int occ = 0;
-  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kLsmThreads, 0);
+  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kBackThreads, kBackSmem);
   if (e != cudaSuccess) return e;
   if (occ < 1) return cudaErrorLaunchOutOfResources;
   static const int cap = getenv("HH_LSM_BLOCKS_PER_SM") ? atoi(getenv("HH_LSM_BLOCKS_PER_SM")) : 2;
@@ -988,7 +1056,7 @@ static cudaError_t launch_backward(const LsmBackArgs &b, int sm_count, int64_t n
   if (query_only) return cudaSuccess;
   LsmBackArgs copy = b;
   void *args[] = {&copy};
-  return cudaLaunchCooperativeKernel(reinterpret_cast<void *>(kern), dim3((unsigned)grid), dim3(kLsmThreads), args, 0, st);
+  return cudaLaunchCooperativeKernel(reinterpret_cast<void *>(kern), dim3((unsigned)grid), dim3(kBackThreads), args, kBackSmem, st);
 }
 
 static cudaError_t launch_backward_deg(int deg, bool tau, const LsmBackArgs &b, int sm_count, int64_t nchunks, cudaStream_t st,
@@ -1087,7 +1155,7 @@ int lsm_american(hh_ctx *ctx, const hh_model *m, const hh_sim *s, const hh_payof
   const int nacc = 3 * degree + 3;
   static const int persistent_env = getenv("HH_LSM_PERSISTENT") ? atoi(getenv("HH_LSM_PERSISTENT")) : 1;
   const int64_t neven = ncols & ~(int64_t)1;
-  const int64_t nchunks = (neven + kLsmChunk - 1) / kLsmChunk;
+  const int64_t nchunks = (neven + kBackChunk - 1) / kBackChunk;  // chunks of the persistent kernel
   const bool host_exchange = comm && comm->world > 1 && !peer_mode;  // NCCL through the callback needs a launch per date
   int grid_back = 0;
   bool persistent = persistent_env && !host_exchange && nchunks >= 1;
@@ -1156,7 +1224,6 @@ int lsm_american(hh_ctx *ctx, const hh_model *m, const hh_sim *s, const hh_payof
   a.z = ctx->d_cash.as<double>();
   a.tau = want_stop ? ctx->d_tau.as<int32_t>() : nullptr;
   a.partials = ctx->d_lsm_partials.as<double>();
-  a.D = step_discount;
   a.strike = payoff->strike;
   a.cp = payoff->cp;
   a.ua = ua;
@@ -1207,12 +1274,16 @@ int lsm_american(hh_ctx *ctx, const hh_model *m, const hh_sim *s, const hh_payof
     bk.gmom = reinterpret_cast<double *>(state + done_off + 256);
     bk.moments_out = d_moments;
     bk.fits = d_fits;
-    bk.D = step_discount;
+    bk.logD = log(step_discount);
     bk.strike = payoff->strike;
     bk.cp = payoff->cp;
     bk.ua = ua;
     bk.ub = ub;
     bk.M = M;
+    static const int zpol = getenv("HH_LSM_ZPOL") ? atoi(getenv("HH_LSM_ZPOL")) : 0;
+    static const int cpol = getenv("HH_LSM_CPOL") ? atoi(getenv("HH_LSM_CPOL")) : 0;
+    bk.z_policy = zpol;
+    bk.cur_policy = cpol;
     bk.px.world = 1;
     if (peer_mode) {
       bk.px = a.px;
@@ -1235,6 +1306,8 @@ int lsm_american(hh_ctx *ctx, const hh_model *m, const hh_sim *s, const hh_payof
     a.S_cur = G + (size_t)t * stride;
     a.fit_next = d_fits + (t + 1);
     a.t_next = t + 1;
+    a.Dp = pow(step_discount, (double)(t + 1));
+    a.rscale = pow(step_discount, -(double)t);
     a.first = (t + 1 == M);
     a.last = (t == 0);
     const bool exchange = t >= 1 && comm && comm->world > 1 && !peer_mode;  // host-callback (NCCL) form
@@ -1248,7 +1321,7 @@ int lsm_american(hh_ctx *ctx, const hh_model *m, const hh_sim *s, const hh_payof
     if (exchange) {
       if (comm->allreduce_sum_f64(comm->user, d_moments, (size_t)nacc, (void *)st) != 0)
         return ctx->fail(HH_ERR_COMM, "allreduce callback failed at date %d", t);
-      launch_fit_deg(degree, d_moments, d_fits + t, st);
+      launch_fit_deg(degree, d_moments, a.rscale, d_fits + t, st);
       HH_CUDA(ctx, cudaGetLastError());
     }
   }
