@@ -142,6 +142,10 @@ int hh_peer_connect(hh_ctx *ctx, int rank, int world, const unsigned char *handl
     return ctx->fail(HH_ERR_ARG, "peer connect: rank %d / world %d out of range (max %d)", rank, world, HH_MAX_PEERS);
   if (!ctx->mailbox) return ctx->fail(HH_ERR_ARG, "peer connect: call hh_peer_export first");
   HH_CUDA(ctx, cudaSetDevice(ctx->device));
+  // epochs restart at zero with every connection: clear flags left by an earlier one. The caller synchronises the ranks
+  // between connect and the first exchange (nobody posts into a mailbox before everybody has connected).
+  HH_CUDA(ctx, cudaMemset(ctx->mailbox, 0, kMailBytes));
+  HH_CUDA(ctx, cudaDeviceSynchronize());
   for (int q = 0; q < world; ++q) {
     if (q == rank) {
       ctx->peer_mail[q] = ctx->mailbox;
