@@ -102,6 +102,9 @@ int hh_destroy(hh_ctx *ctx) {
     if (q != ctx->peer_rank && ctx->peer_mail[q]) cudaIpcCloseMemHandle(ctx->peer_mail[q]);
   if (ctx->mailbox) cudaFree(ctx->mailbox);
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+  for (int i = 0; i < 16; ++i)
+    if (ctx->ev_seg[i]) cudaEventDestroy(ctx->ev_seg[i]);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   for (int b = 0; b < 2; ++b) {
     if (ctx->h_stage[b]) cudaFreeHost(ctx->h_stage[b]);
     if (ctx->ev_stage[b]) cudaEventDestroy(ctx->ev_stage[b]);

@@ -479,6 +479,7 @@ int bk_european_launch(hh_ctx *ctx, const hh_model *m, const hh_sim *s, const hh
   if (rc) return rc;
   ctx->pend.want_terminal = want_terminal != 0;
   ctx->pend.bk = true;
+  ctx->pend.nseg = 0;
   return HH_OK;
 }
 

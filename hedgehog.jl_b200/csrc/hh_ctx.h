@@ -44,6 +44,10 @@ struct PendingEuropean {
   bool anti = false;
   bool want_terminal = false;
   bool bk = false;  // Broadie-Kaya run: counters live in d_counters
+  // the simulation was launched in `nseg` segments of trajectories so that the copy of a segment's terminal values to the
+  // host overlaps the kernel of the next one; seg_end[i] = first trajectory after segment i
+  int nseg = 0;
+  int64_t seg_end[16] = {};
 };
 
 }  // namespace hh
@@ -72,6 +76,8 @@ struct hh_ctx {
   size_t h_pinned_cap = 0;
   void *h_stage[2] = {nullptr, nullptr};  // pinned double buffer for large device -> pageable-host copies
   cudaEvent_t ev_stage[2] = {nullptr, nullptr};
+  cudaStream_t copy_stream = nullptr;     // device -> host copies that overlap the kernels on `stream`
+  cudaEvent_t ev_seg[16] = {};            // segment i of a segmented launch has finished
   hh::PendingEuropean pend;
 
   int fail(int code, const char *fmt, ...) {

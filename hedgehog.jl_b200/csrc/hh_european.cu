@@ -1398,8 +1398,50 @@ int european_launch(hh_ctx *ctx, const hh_model *m, const hh_sim *s, const hh_pa
   HH_CUDA(ctx, ctx->d_final.ensure(sizeof(double) * (size_t)npay * NACC));
   a.partials = ctx->d_partials.as<double>();
 
+  // MonteCarloSolution.ensemble of a large job: launch the trajectories in segments, so that collect() can copy the
+  // terminal values of segment i to the host while segment i+1 is being simulated (the kernels are grid-stride over
+  // a.n with the global trajectory index in the Philox counter, so a segment is just a shard)
+  static const int64_t seg_min = getenv("HH_SEGMENT_MIN") ? atoll(getenv("HH_SEGMENT_MIN")) : ((int64_t)4 << 20);
+  int nseg = 1;
+  if (want_terminal && !anti && !a.parity && !s->seeds && N >= 2 * seg_min) {
+    nseg = (int)(N / seg_min);
+    if (nseg > 8) nseg = 8;
+  }
+  ctx->pend.nseg = 0;
   HH_CUDA(ctx, cudaEventRecord(ctx->ev0, st));
-  HH_CUDA(ctx, launch_any(kind, a, nullptr, 0, anti, ctx->sm_count, st, &nblocks, false));
+  if (nseg == 1) {
+    HH_CUDA(ctx, launch_any(kind, a, nullptr, 0, anti, ctx->sm_count, st, &nblocks, false));
+  } else {
+    // every segment runs a full grid: its own slice of the partial sums
+    int64_t per = ((N / nseg) + 1023) & ~(int64_t)1023;
+    int total_blocks = 0, nb = 0;
+    std::vector<EuroArgs> segs;
+    for (int64_t lo = 0; lo < N; lo += per) {
+      EuroArgs b = a;
+      b.n = N - lo < per ? N - lo : per;
+      b.path_offset = a.path_offset + lo;
+      b.terminal = a.terminal + lo;
+      HH_CUDA(ctx, launch_any(kind, b, nullptr, 0, anti, ctx->sm_count, st, &nb, true));
+      total_blocks += nb;
+      segs.push_back(b);
+    }
+    HH_CUDA(ctx, ctx->d_partials.ensure(sizeof(double) * (size_t)total_blocks * npay * NACC));
+    a.partials = ctx->d_partials.as<double>();
+    int done = 0, i = 0;
+    int64_t end = 0;
+    for (EuroArgs &b : segs) {
+      b.partials = a.partials + (size_t)done * npay * NACC;
+      HH_CUDA(ctx, launch_any(kind, b, nullptr, 0, anti, ctx->sm_count, st, &nb, false));
+      done += nb;
+      end += b.n;
+      if (!ctx->ev_seg[i]) HH_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_seg[i], cudaEventDisableTiming));
+      HH_CUDA(ctx, cudaEventRecord(ctx->ev_seg[i], st));
+      ctx->pend.seg_end[i] = end;
+      ++i;
+    }
+    ctx->pend.nseg = i;
+    nblocks = total_blocks;
+  }
   finalize_kernel<<<npay, kThreads, 0, st>>>(a.partials, nblocks, npay, NACC, ctx->d_final.as<double>());
   HH_CUDA(ctx, cudaGetLastError());
   HH_CUDA(ctx, cudaEventRecord(ctx->ev1, st));
@@ -1504,16 +1546,31 @@ int european_collect(hh_ctx *ctx, double discount, hh_result *results, double *t
   HH_CUDA(ctx, cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
   std::vector<double> fin((size_t)npay * NACC);
-  HH_CUDA(ctx, cudaMemcpyAsync(fin.data(), ctx->d_final.ptr, sizeof(double) * fin.size(), cudaMemcpyDeviceToHost, st));
-  if (terminal) {
+  // (the copy of the sums into pageable memory blocks the host until the stream has drained: it comes AFTER the
+  // segment copies, which must run while the later segments are still being simulated)
+  if (terminal && ctx->pend.nseg > 1) {
+    if (!ctx->copy_stream) HH_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    int64_t lo = 0;
+    for (int i = 0; i < ctx->pend.nseg; ++i) {  // segment i travels while segments i+1.. are still being simulated
+      const int64_t hi = ctx->pend.seg_end[i];
+      HH_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_seg[i], 0));
+      const int rc = copy_to_pageable_host(ctx, terminal + lo, ctx->d_terminal.as<double>() + lo, sizeof(double) * (size_t)(hi - lo),
+                                           ctx->copy_stream);
+      if (rc) return rc;
+      HH_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
+      lo = hi;
+    }
+  } else if (terminal) {
     const int rc = copy_to_pageable_host(ctx, terminal, ctx->d_terminal.ptr, sizeof(double) * tlen, st);
     if (rc) return rc;
   }
+  HH_CUDA(ctx, cudaMemcpyAsync(fin.data(), ctx->d_final.ptr, sizeof(double) * fin.size(), cudaMemcpyDeviceToHost, st));
   unsigned long long counters[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   if (ctx->pend.bk)
     HH_CUDA(ctx, cudaMemcpyAsync(counters, ctx->d_counters.ptr, sizeof counters, cudaMemcpyDeviceToHost, st));
   HH_CUDA(ctx, cudaStreamSynchronize(st));
   ctx->pend.active = false;
+  ctx->pend.nseg = 0;
   if (ctx->pend.bk)
     for (int i = 0; i < 5; ++i) ctx->bk_stats[i] = (double)counters[i];
   float ms = 0.f;

@@ -109,3 +109,22 @@ def test_global_trajectory_index_beyond_32_bits(cuda, oracle):
     og, _, _, pg = cuda.lsm_american(g, sim, (100.0, -1.0), 2, 0.99, want_paths=True)
     oo, _, _, po = oracle.lsm_american(g, sim, (100.0, -1.0), 2, 0.99, want_paths=True)
     assert rel_err(pg, po) < 1e-12
+
+
+@pytest.mark.parametrize("prec", [abi.HH_PREC_F64, abi.HH_PREC_F32])
+def test_segmented_launch_for_the_ensemble_is_invisible(cuda, prec):
+    """A large job that returns the terminal vector is launched in segments (the copy of one overlaps the simulation of the
+    next): same trajectories as two explicit shards, sums equal up to summation order."""
+    m = heston_model()
+    n = (8 << 20) + 4321  # >= 2 x the segment minimum
+    sim = SimSpec(n_paths=n, n_steps=5, precision=prec, base_seed=21)
+    res, term = cuda.mc_european(m, sim, [(100.0, 1.0), (90.0, -1.0)], 1.0, want_terminal=True)
+    res0, _ = cuda.mc_european(m, sim, [(100.0, 1.0), (90.0, -1.0)], 1.0)               # one launch, no terminal vector
+    parts = [cuda.mc_european(m, SimSpec(n_paths=h, n_steps=5, precision=prec, base_seed=21, path_offset=o), [(100.0, 1.0)], 1.0,
+                              want_terminal=True)[1] for o, h in ((0, 3_000_000), (3_000_000, n - 3_000_000))]
+    np.testing.assert_array_equal(np.concatenate(parts), term)
+    for a, b in zip(res, res0):
+        assert a.n == b.n == n
+        assert abs(a.sum - b.sum) <= 1e-12 * abs(b.sum) and abs(a.sumsq - b.sumsq) <= 1e-12 * abs(b.sumsq)
+    pay = np.maximum(term - 100.0, 0.0)
+    assert abs(res[0].sum - pay.sum()) <= 1e-10 * pay.sum()
