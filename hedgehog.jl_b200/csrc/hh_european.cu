@@ -1491,7 +1491,7 @@ int terminal_payoffs_launch(hh_ctx *ctx, const double *d_terminal, int64_t n, co
 // A plain cudaMemcpy to pageable memory runs at ~4 GB/s here (the driver stages it and the fresh pages fault in one by
 // one). Instead: 32 MB chunks DMA into a pinned double buffer on the stream while a few host threads copy the previous
 // chunk into the caller's buffer (first-touch page faults in parallel).
-static int copy_to_pageable_host(hh_ctx *ctx, void *dst, const void *src_dev, size_t bytes, cudaStream_t st) {
+int copy_to_pageable_host(hh_ctx *ctx, void *dst, const void *src_dev, size_t bytes, cudaStream_t st) {
   constexpr size_t kChunk = (size_t)32 << 20;
   if (bytes < 2 * kChunk) {
     HH_CUDA(ctx, cudaMemcpyAsync(dst, src_dev, bytes, cudaMemcpyDeviceToHost, st));

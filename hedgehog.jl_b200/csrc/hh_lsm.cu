@@ -1346,8 +1346,8 @@ int lsm_american(hh_ctx *ctx, const hh_model *m, const hh_sim *s, const hh_payof
     lsm_stop_values_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(G, stride, ncols, ctx->d_tau.as<int32_t>(), payoff->strike,
                                                              payoff->cp, ctx->d_misc.as<double>());
     HH_CUDA(ctx, cudaGetLastError());
-    HH_CUDA(ctx, cudaMemcpyAsync(stop_idx, ctx->d_tau.ptr, sizeof(int32_t) * (size_t)ncols, cudaMemcpyDeviceToHost, st));
-    HH_CUDA(ctx, cudaMemcpyAsync(stop_val, ctx->d_misc.ptr, sizeof(double) * (size_t)ncols, cudaMemcpyDeviceToHost, st));
+    if (int rc2 = copy_to_pageable_host(ctx, stop_idx, ctx->d_tau.ptr, sizeof(int32_t) * (size_t)ncols, st)) return rc2;
+    if (int rc2 = copy_to_pageable_host(ctx, stop_val, ctx->d_misc.ptr, sizeof(double) * (size_t)ncols, st)) return rc2;
   }
   int px_error = 0;
   if (peer_mode)
@@ -1365,8 +1365,8 @@ int lsm_american(hh_ctx *ctx, const hh_model *m, const hh_sim *s, const hh_payof
       dim3 g((unsigned)((np + 31) / 32), (unsigned)((nrows + 31) / 32));
       lsm_transpose_kernel<<<g, dim3(32, 8), 0, st>>>(G, stride, p0, np, nrows, ctx->d_terminal.as<double>());
       HH_CUDA(ctx, cudaGetLastError());
-      HH_CUDA(ctx, cudaMemcpyAsync(spot_paths + (size_t)p0 * nrows, ctx->d_terminal.ptr, sizeof(double) * (size_t)np * nrows,
-                                   cudaMemcpyDeviceToHost, st));
+      if (int rc2 = copy_to_pageable_host(ctx, spot_paths + (size_t)p0 * nrows, ctx->d_terminal.ptr, sizeof(double) * (size_t)np * nrows, st))
+        return rc2;
       HH_CUDA(ctx, cudaStreamSynchronize(st));
     }
   }

@@ -39,7 +39,12 @@ def solve_lsm(prob, method, *, engine=None, shard=None, group=None, stopping_inf
     n = s[2]
     mean = s[0] / n
     var = max((s[1] - n * mean * mean) / (n - 1), 0.0) if n > 1 else 0.0
-    info = list(zip(tau.tolist(), val.tolist())) if stopping_info else None
+    # the reference's Vector{Tuple{Int,S}} (:112); "arrays" keeps the two numpy arrays (a Python list of 1e7 tuples costs
+    # seconds to build and is only useful for small cases)
+    if stopping_info == "arrays":
+        info = (tau, val)
+    else:
+        info = list(zip(tau.tolist(), val.tolist())) if stopping_info else None
     stats = {"kernel_ms": out.kernel_ms, "path_ms": out.path_ms, "regress_ms": out.regress_ms,
              "n_dates_skipped": out.n_dates_skipped, "n_cols_local": int(out.n), "n_cols_total": int(n)}
     return api.LSMSolution(prob, method, float(mean), info, None if paths is None else paths.T,
