@@ -593,6 +593,140 @@ __global__ void __launch_bounds__(THREADS, MINB) heston_fast2_kernel(const EuroA
   }
 }
 
+// ---- LognormalDynamics pricing kernels (configs C1-like at scale): GBM Euler-Maruyama and exact steps ---------------
+// The generic european_kernel carries the number-type template and the v1 tables; for plain prices with the in-kernel
+// RNG this kernel uses the lane-replicated v2 tables, the uniform round keys, one Philox block per TWO steps (a GBM step
+// needs one normal), the table-driven exp(y) - 1 for the exact step, and ILP 2. Same trajectories as the generic
+// kernel and the oracle up to rounding (the log-space drift is added once at expiry).
+constexpr int gbm_fast_smem(bool anti) {
+  return 3 * kThreads * 8 * (anti ? 2 : 1) + kLogRepBytes + kTrigRepBytes + kExp2Bytes + kExpm1TabBytes;
+}
+
+template <int KIND, bool ANTI, bool UKEY, int ILP>
+__global__ void __launch_bounds__(kThreads) gbm_fast_kernel(const EuroArgs a) {
+  static_assert(KIND == K_GBM_EM || KIND == K_GBM_STEPS, "terminal sampling stays in the generic kernel");
+  constexpr int NACC = 3;
+  constexpr int NSIDE = ANTI ? 2 : 1;
+  extern __shared__ __align__(16) unsigned char dsm[];
+  double *smem = reinterpret_cast<double *>(dsm);  // 3 * kThreads * NSIDE doubles: staging, then the final reduction
+  char *s_log = reinterpret_cast<char *>(dsm) + 3 * kThreads * 8 * NSIDE;
+  char *s_trig = s_log + kLogRepBytes;
+  double *s_e2 = reinterpret_cast<double *>(s_trig + kTrigRepBytes);
+  double2 *s_exp = reinterpret_cast<double2 *>(reinterpret_cast<char *>(s_e2) + kExp2Bytes);
+  const int tid = threadIdx.x;
+  for (int e = tid; e < tables::kLog2Buckets * kRep; e += kThreads)
+    reinterpret_cast<double2 *>(s_log)[e] = g_fast_tables2.log_tab[e / kRep];
+  for (int e = tid; e < tables::kTrigN * kRep; e += kThreads)
+    reinterpret_cast<double2 *>(s_trig)[e] = g_fast_tables2.trig_tab[e / kRep];
+  for (int e = tid; e < tables::kExp2N; e += kThreads) s_e2[e] = g_fast_tables2.exp_tab[e];
+  if (KIND == K_GBM_STEPS) fill_expm1_table(s_exp);
+  __syncthreads();
+  const char *log_lane = s_log + (tid & (kRep - 1)) * 16;
+  const char *trig_lane = s_trig + (tid & (kRep - 1)) * 16;
+  const char *exp_biased = reinterpret_cast<const char *>(s_e2) - tables::kExp2Bias * 8;
+  const int KP = 1 << a.kp_log2;
+  const int k = tid & (KP - 1);
+  const int g = tid >> a.kp_log2;
+  const int G = kThreads >> a.kp_log2;
+  double strike = 0.0, cp = 0.0;
+  if (k < a.npay) {
+    strike = a.payoffs[k].strike;
+    cp = a.payoffs[k].cp;
+  }
+  double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0;
+  const int M = a.n_steps;
+  const double sig = a.p.sig_sqdt, drift = a.p.dt_drift;
+  const double drift_total = (double)M * drift;
+  constexpr int64_t kBatch = (int64_t)kThreads * ILP;
+
+  for (int64_t base = (int64_t)blockIdx.x * kBatch; base < a.n; base += (int64_t)gridDim.x * kBatch) {
+    double sp[ILP], sm[ILP];
+    uint32_t c0[ILP], c1[ILP];
+    PhiloxRoundKeys rk[UKEY ? 1 : ILP];
+#pragma unroll
+    for (int j = 0; j < ILP; ++j) {
+      const int64_t i = base + (int64_t)j * kThreads + tid;
+      const int64_t ic = i < a.n ? i : a.n - 1;
+      sp[j] = sm[j] = KIND == K_GBM_EM ? a.p.x0 : a.p.S0;
+      if (UKEY) {
+        const uint64_t idx = (uint64_t)(a.path_offset + ic);
+        c0[j] = (uint32_t)idx;
+        c1[j] = (uint32_t)(idx >> 32);
+      } else {
+        c0[j] = c1[j] = 0u;
+        rk[UKEY ? 0 : j] = philox_round_keys(a.seeds[ic]);
+      }
+    }
+#pragma unroll 1
+    for (int n = 0; n < M; n += 2) {
+#pragma unroll
+      for (int j = 0; j < ILP; ++j) {
+        const u32x4 w = philox4x32_10_rk(c0[j], c1[j], (uint32_t)(n >> 1), 0u, UKEY ? a.rk : rk[UKEY ? 0 : j]);
+        double za, zb;
+        fast_normal_pair_v2(log_lane, exp_biased, trig_lane, w.x, w.y, w.z, w.w, a.one_hi, a.magic_hi, za, zb);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          if (n + h < M) {
+            const double z = h ? zb : za;
+            if (KIND == K_GBM_EM) {  // heston.jl:33-52 under EM; the drift is added at expiry
+              sp[j] = fma(sig, z, sp[j]);
+              if (ANTI) sm[j] = fma(-sig, z, sm[j]);  // NoiseGrid(t, -W) montecarlo.jl:258
+            } else {  // S += S (exp((r - s^2/2) dt + s sqrt(dt) Z) - 1), antithetic: sigma -> -sigma (montecarlo.jl:270-284)
+              sp[j] = fma(sp[j], fast_expm1_small(s_exp, fma(sig, z, drift)), sp[j]);
+              if (ANTI) sm[j] = fma(sm[j], fast_expm1_small(s_exp, fma(-sig, z, drift)), sm[j]);
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < ILP; ++j) {
+      const int64_t sub = base + (int64_t)j * kThreads;
+      if (sub >= a.n) break;
+      const int64_t i = sub + tid;
+      const double Sp = KIND == K_GBM_EM ? exp(sp[j] + drift_total) : sp[j];  // final_sample montecarlo.jl:398
+      const double Sm = ANTI ? (KIND == K_GBM_EM ? exp(sm[j] + drift_total) : sm[j]) : 0.0;
+      if (a.terminal && i < a.n) {
+        a.terminal[i] = Sp;
+        if (ANTI) a.terminal[a.n + i] = Sm;
+      }
+      smem[tid] = Sp;
+      if (ANTI) smem[kThreads + tid] = Sm;
+      __syncthreads();
+      const int64_t rem = a.n - sub;
+      const int nvalid = rem < kThreads ? (int)rem : kThreads;
+      if (k < a.npay) {
+        for (int q = g; q < nvalid; q += G) {
+          const double s_ = smem[q];
+          double pay = fmax(cp * (s_ - strike), 0.0);  // payoffs.jl:154-156
+          bool bad = !isfinite(s_);
+          if (ANTI) {
+            const double t_ = smem[kThreads + q];
+            pay = 0.5 * (pay + fmax(cp * (t_ - strike), 0.0));  // reduce_payoffs montecarlo.jl:430-432
+            bad = bad || !isfinite(t_);
+          }
+          acc0 += pay;
+          acc1 = fma(pay, pay, acc1);
+          if (k == 0 && bad) acc2 += 1.0;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  smem[tid] = acc0;
+  smem[kThreads + tid] = acc1;
+  smem[2 * kThreads + tid] = acc2;
+  __syncthreads();
+  if (tid < a.npay) {
+    double *out = a.partials + ((size_t)blockIdx.x * a.npay + tid) * NACC;
+    for (int c = 0; c < NACC; ++c) {
+      double t = 0.0;
+      for (int gg = 0; gg < G; ++gg) t += smem[c * kThreads + (gg << a.kp_log2) + tid];
+      out[c] = t;
+    }
+  }
+}
+
 // ---- Float32 fast mode of the headline kernel (config C2, HH_PREC_F32) ----------------------------------------
 // FP32 state and normals, FP64 accumulation of the payoff sums. One Philox4x32-10 block feeds TWO steps (32-bit
 // uniforms): step n uses words (0, 1) of block n/2 when n is even and words (2, 3) when n is odd; the stream word of
@@ -1242,10 +1376,49 @@ static cudaError_t launch_tangent(const EuroArgs &a, const HestonTanConsts &c, i
                  : launch_tangent_as<false, false>(a, c, nf, P, sm_count, st, nb, q);
 }
 
+template <int KIND, bool ANTI, bool UKEY>
+static cudaError_t launch_gbm_fast_one(const EuroArgs &a, int sm_count, cudaStream_t st, int *nblocks, bool query_only) {
+  constexpr int ILP = 2;
+  auto kern = gbm_fast_kernel<KIND, ANTI, UKEY, ILP>;
+  constexpr int smem = gbm_fast_smem(ANTI);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e0 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e0 != cudaSuccess) return e0;
+    attr_set = true;
+  }
+  int occ = 0;
+  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, smem);
+  if (e != cudaSuccess) return e;
+  if (occ < 1) occ = 1;
+  const int64_t batch = (int64_t)kThreads * ILP;
+  const int64_t batches = (a.n + batch - 1) / batch;
+  int64_t grid = (int64_t)sm_count * occ;
+  if (grid > batches) grid = batches;
+  *nblocks = (int)grid;
+  if (query_only) return cudaSuccess;
+  kern<<<(unsigned)grid, kThreads, smem, st>>>(a);
+  return cudaGetLastError();
+}
+
+template <int KIND>
+static cudaError_t launch_gbm_fast(const EuroArgs &a, bool anti, int sm_count, cudaStream_t st, int *nb, bool q) {
+  const bool ukey = a.seeds == nullptr;
+  if (anti) return ukey ? launch_gbm_fast_one<KIND, true, true>(a, sm_count, st, nb, q)
+                        : launch_gbm_fast_one<KIND, true, false>(a, sm_count, st, nb, q);
+  return ukey ? launch_gbm_fast_one<KIND, false, true>(a, sm_count, st, nb, q)
+              : launch_gbm_fast_one<KIND, false, false>(a, sm_count, st, nb, q);
+}
+
 static cudaError_t launch_any(int kind, const EuroArgs &a, const TangentPack *tp, int P, bool anti, int sm_count,
                               cudaStream_t st, int *nb, bool q) {
   if (a.f32) return launch_f32(a, anti, sm_count, st, nb, q);
   if (kind == K_HESTON_EM && P == 0 && !a.parity) return launch_fast(a, anti, sm_count, st, nb, q);
+  static const bool gbm_generic = getenv("HH_GBM_GENERIC") != nullptr;
+  if (P == 0 && !a.parity && !gbm_generic) {
+    if (kind == K_GBM_EM) return launch_gbm_fast<K_GBM_EM>(a, anti, sm_count, st, nb, q);
+    if (kind == K_GBM_STEPS) return launch_gbm_fast<K_GBM_STEPS>(a, anti, sm_count, st, nb, q);
+  }
   switch (kind) {
     case K_GBM_EM: return launch_kind<K_GBM_EM>(a, tp, P, anti, sm_count, st, nb, q);
     case K_GBM_TERMINAL: return launch_kind<K_GBM_TERMINAL>(a, tp, P, anti, sm_count, st, nb, q);

@@ -280,4 +280,39 @@ __device__ __forceinline__ double fast_sqrt_pos5(double x) {
   return fma(s0, p, s0);
 }
 
+// exp(y) - 1 for the per-step exponent of the GBM generator, |y| <= 1/2: y = j/512 + r, exp(y) - 1 =
+// (E_j - 1) + E_j (exp(r) - 1) with {E_j, E_j - 1} tabulated in shared memory (513 entries, filled with libm at kernel
+// start) and exp(r) - 1 by its series to r^4 (|r| <= 1/1024: remainder r^5/120 < 7.4e-18). 8 FP64 instructions against ~25 for
+// libm's exp; larger |y| (huge sigma sqrt(dt) Z) takes the libm path.
+constexpr int kExpJ = 256;
+constexpr double kExpScale = 512.0, kExpInvScale = 1.0 / 512.0;
+struct ExpCoefs {
+  double magic, inv6, inv24, inv120, inv720;
+};
+__constant__ ExpCoefs kExpC = {6755399441055744.0, 1.0 / 6, 1.0 / 24, 1.0 / 120, 1.0 / 720};
+
+static __device__ __noinline__ double expm1_slow_path(double y) { return exp(y) - 1.0; }
+
+__device__ __forceinline__ double fast_expm1_small(const double2 *__restrict__ tab, double y) {
+  // |y| <= 1/2 on the integer pipe (also false for NaN); the out-of-line libm path keeps the loop body small
+  if ((uint32_t)(__double2hiint(y) & 0x7fffffff) > 0x3fe00000u) return expm1_slow_path(y);
+  const double t = fma(y, kExpScale, kExpC.magic);  // nearest integer to 512 y in the low word
+  const int j = __double2loint(t);
+  const double r = fma(t - kExpC.magic, -kExpInvScale, y);  // exact
+  const double2 e = tab[j + kExpJ];
+  double p = fma(r, kExpC.inv24, kExpC.inv6);  // r^5/120 <= 7.4e-18 is dropped: below half an ulp of exp(y)
+  p = fma(p, r, 0.5);
+  p = fma(p, r, 1.0);
+  return fma(e.x, p * r, e.y);
+}
+
+constexpr int kExpm1TabBytes = (2 * kExpJ + 1) * 16;
+// fills the {E_j, E_j - 1} table with libm (all threads of the block; the caller synchronises)
+__device__ __forceinline__ void fill_expm1_table(double2 *tab) {
+  for (int e = threadIdx.x; e <= 2 * kExpJ; e += blockDim.x) {
+    const double yj = (double)(e - kExpJ) * kExpInvScale;
+    tab[e] = make_double2(exp(yj), expm1(yj));
+  }
+}
+
 }  // namespace hh

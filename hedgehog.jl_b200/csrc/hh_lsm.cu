@@ -49,34 +49,8 @@ struct LsmPathArgs {
   uint32_t one_hi, magic_hi;   // 0x3FF00000, 0x43300000 as arguments (single-LOP3 bit assembly, see hh_european.cu)
 };
 
-// exp(y) - 1 for the per-step exponent of the GBM generator, |y| <= 1/2: y = j/512 + r, exp(y) - 1 =
-// (E_j - 1) + E_j (exp(r) - 1) with {E_j, E_j - 1} tabulated in shared memory (513 entries, filled with libm at kernel
-// start) and exp(r) - 1 by its series to r^4 (|r| <= 1/1024: remainder r^5/120 < 7.4e-18). 8 FP64 instructions against ~25 for
-// libm's exp; larger |y| (huge sigma sqrt(dt) Z) takes the libm path.
-constexpr int kExpJ = 256;
-constexpr double kExpScale = 512.0, kExpInvScale = 1.0 / 512.0;
-struct ExpCoefs {
-  double magic, inv6, inv24, inv120, inv720;
-};
-__constant__ ExpCoefs kExpC = {6755399441055744.0, 1.0 / 6, 1.0 / 24, 1.0 / 120, 1.0 / 720};
-
-__device__ __noinline__ double expm1_slow_path(double y) { return exp(y) - 1.0; }
-
-__device__ __forceinline__ double fast_expm1_small(const double2 *__restrict__ tab, double y) {
-  // |y| <= 1/2 on the integer pipe (also false for NaN); the out-of-line libm path keeps the loop body small
-  if ((uint32_t)(__double2hiint(y) & 0x7fffffff) > 0x3fe00000u) return expm1_slow_path(y);
-  const double t = fma(y, kExpScale, kExpC.magic);  // nearest integer to 512 y in the low word
-  const int j = __double2loint(t);
-  const double r = fma(t - kExpC.magic, -kExpInvScale, y);  // exact
-  const double2 e = tab[j + kExpJ];
-  double p = fma(r, kExpC.inv24, kExpC.inv6);  // r^5/120 <= 7.4e-18 is dropped: below half an ulp of exp(y)
-  p = fma(p, r, 0.5);
-  p = fma(p, r, 1.0);
-  return fma(e.x, p * r, e.y);
-}
-
 // Dynamic shared memory of the path generator: [log table x8 | trig table x8 | exponent table | expm1 table]
-constexpr int kLsmPathSmem = kLogRepBytes + kTrigRepBytes + kExp2Bytes + (2 * kExpJ + 1) * 16;
+constexpr int kLsmPathSmem = kLogRepBytes + kTrigRepBytes + kExp2Bytes + kExpm1TabBytes;
 
 // 64.9 KB of tables per block allow 3 blocks per SM: 512-thread blocks give 48 warps per SM to hide the dependent
 // chains (Philox rounds -> log -> sqrt -> exp), 32 registers per thread (ncu at 24 warps: issue slots 59 % busy, "wait"
@@ -98,10 +72,7 @@ __global__ void __launch_bounds__(kLsmPathThreads) lsm_paths_kernel(const LsmPat
       reinterpret_cast<double2 *>(s_trig)[e] = g_fast_tables2.trig_tab[e / kRep];
     for (int e = tid; e < tables::kExp2N; e += kLsmPathThreads) s_e2[e] = g_fast_tables2.exp_tab[e];
   }
-  for (int e = tid; e <= 2 * kExpJ; e += kLsmPathThreads) {
-    const double yj = (double)(e - kExpJ) * kExpInvScale;
-    s_exp[e] = make_double2(exp(yj), expm1(yj));
-  }
+  fill_expm1_table(s_exp);
   __syncthreads();
   const char *log_lane = s_log + (tid & (kRep - 1)) * 16;
   const char *trig_lane = s_trig + (tid & (kRep - 1)) * 16;
