@@ -308,7 +308,8 @@ def main():
                        "l2": "not applicable: the kernel reads no HBM input (state in registers); every step uses a new seed",
                        "sharding": "contiguous global path index blocks per rank, no data-path collective"},
             "roofline": {"bound": "fp64", "achieved": achieved_tflops, "peak": fp64_peak, "unit": "TFLOP/s",
-                         "frac": achieved_tflops / fp64_peak, "traffic": None,
+                         "frac": achieved_tflops / fp64_peak,
+                         "traffic": 25088.0,  # dram bytes per launch (ncu, profiles/r1_g_ncu_heston_v3.csv): tables only, no data stream
                          "peak_source": "DFMA-chain microbenchmark run by this bench (hh_bench_fp64_peak); "
                                         "MEASURED_PEAKS.json has no FP64 entry",
                          "convention": "algorithmic 25 FLOP per path-step (log/sincos/sqrt expansions NOT counted)",
