@@ -598,13 +598,14 @@ __global__ void __launch_bounds__(THREADS, MINB) heston_fast2_kernel(const EuroA
 // RNG this kernel uses the lane-replicated v2 tables, the uniform round keys, one Philox block per TWO steps (a GBM step
 // needs one normal), the table-driven exp(y) - 1 for the exact step, and ILP 2. Same trajectories as the generic
 // kernel and the oracle up to rounding (the log-space drift is added once at expiry).
-constexpr int gbm_fast_smem(bool anti) {
-  return 3 * kThreads * 8 * (anti ? 2 : 1) + kLogRepBytes + kTrigRepBytes + kExp2Bytes + kExpm1TabBytes;
+__host__ __device__ constexpr int gbm_fast_smem(bool anti, int threads, bool steps) {
+  return 3 * threads * 8 * (anti ? 2 : 1) + kLogRepBytes + kTrigRepBytes + kExp2Bytes + (steps ? kExpm1TabBytes : 0);
 }
 
-template <int KIND, bool ANTI, bool UKEY, int ILP>
-__global__ void __launch_bounds__(kThreads) gbm_fast_kernel(const EuroArgs a) {
+template <int KIND, bool ANTI, bool UKEY, int ILP, int THREADS>
+__global__ void __launch_bounds__(THREADS) gbm_fast_kernel(const EuroArgs a) {
   static_assert(KIND == K_GBM_EM || KIND == K_GBM_STEPS, "terminal sampling stays in the generic kernel");
+  constexpr int kThreads = THREADS;  // shadows the file-scope block size
   constexpr int NACC = 3;
   constexpr int NSIDE = ANTI ? 2 : 1;
   extern __shared__ __align__(16) unsigned char dsm[];
@@ -1376,11 +1377,11 @@ static cudaError_t launch_tangent(const EuroArgs &a, const HestonTanConsts &c, i
                  : launch_tangent_as<false, false>(a, c, nf, P, sm_count, st, nb, q);
 }
 
-template <int KIND, bool ANTI, bool UKEY>
-static cudaError_t launch_gbm_fast_one(const EuroArgs &a, int sm_count, cudaStream_t st, int *nblocks, bool query_only) {
-  constexpr int ILP = 2;
-  auto kern = gbm_fast_kernel<KIND, ANTI, UKEY, ILP>;
-  constexpr int smem = gbm_fast_smem(ANTI);
+template <int KIND, bool ANTI, bool UKEY, int ILP, int THREADS>
+static cudaError_t launch_gbm_fast_cfg(const EuroArgs &a, int sm_count, cudaStream_t st, int *nblocks, bool query_only) {
+  constexpr int kThreads = THREADS;
+  auto kern = gbm_fast_kernel<KIND, ANTI, UKEY, ILP, THREADS>;
+  constexpr int smem = gbm_fast_smem(ANTI, THREADS, KIND == K_GBM_STEPS);
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e0 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -1399,6 +1400,18 @@ static cudaError_t launch_gbm_fast_one(const EuroArgs &a, int sm_count, cudaStre
   if (query_only) return cudaSuccess;
   kern<<<(unsigned)grid, kThreads, smem, st>>>(a);
   return cudaGetLastError();
+}
+
+// measured at 2e7 x 252 (EM / exact steps, 1e11 path-steps/s): 256 x ILP 2: 4.36 / 2.90, 512 x ILP 2: 4.80 / 3.28,
+// 1024 x ILP 1: 4.67 / 3.29 — large jobs take 512-thread blocks (more warps share one copy of the tables)
+template <int KIND, bool ANTI, bool UKEY>
+static cudaError_t launch_gbm_fast_one(const EuroArgs &a, int sm_count, cudaStream_t st, int *nblocks, bool query_only) {
+  static const int variant = getenv("HH_GBM_VARIANT") ? atoi(getenv("HH_GBM_VARIANT")) : 0;
+  if (variant == 1) return launch_gbm_fast_cfg<KIND, ANTI, UKEY, 2, 256>(a, sm_count, st, nblocks, query_only);
+  if (variant == 2) return launch_gbm_fast_cfg<KIND, ANTI, UKEY, 2, 512>(a, sm_count, st, nblocks, query_only);
+  if (variant == 3) return launch_gbm_fast_cfg<KIND, ANTI, UKEY, 1, 1024>(a, sm_count, st, nblocks, query_only);
+  if (a.n >= (int64_t)sm_count * 1024 * 4) return launch_gbm_fast_cfg<KIND, ANTI, UKEY, 2, 512>(a, sm_count, st, nblocks, query_only);
+  return launch_gbm_fast_cfg<KIND, ANTI, UKEY, 2, 256>(a, sm_count, st, nblocks, query_only);
 }
 
 template <int KIND>
