@@ -1298,12 +1298,11 @@ int lsm_american(hh_ctx *ctx, const hh_model *m, const hh_sim *s, const hh_payof
   }
   }
   HH_CUDA(ctx, cudaEventRecord(ctx->ev2, st));
-  if (l2_window) {
+  if (l2_window) {  // later launches on this stream must not inherit the window (the kernels above already have it)
     cudaStreamAttrValue attr;
     memset(&attr, 0, sizeof attr);
-    attr.accessPolicyWindow.num_bytes = 0;  // disables the window
+    attr.accessPolicyWindow.num_bytes = 0;
     (void)cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr);
-    (void)cudaCtxResetPersistingL2Cache();
     (void)cudaGetLastError();
   }
 
@@ -1325,6 +1324,11 @@ int lsm_american(hh_ctx *ctx, const hh_model *m, const hh_sim *s, const hh_payof
     HH_CUDA(ctx, cudaMemcpyAsync(&px_error, static_cast<char *>(ctx->d_lsm_state.ptr) + done_off + 128, sizeof(int),
                                  cudaMemcpyDeviceToHost, st));
   HH_CUDA(ctx, cudaStreamSynchronize(st));
+  if (l2_window) {  // the induction has finished: give the persisting lines and the carve-out back
+    (void)cudaCtxResetPersistingL2Cache();
+    (void)cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 0);
+    (void)cudaGetLastError();
+  }
   if (px_error) return ctx->fail(HH_ERR_PEER_TIMEOUT, "a peer's regression moments did not arrive within the in-kernel time limit");
   if (spot_paths) {
     // chunks of columns transposed on the device, then copied out (the staging buffer reuses d_terminal)
