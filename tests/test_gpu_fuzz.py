@@ -1,0 +1,96 @@
+"""Randomised differential test of the specialised kernels against the oracle: 60 random models (including harsh ones:
+Feller condition violated, vol of vol up to 2, correlation near +-1, few large steps, tiny and huge spots, negative rates).
+The specialised kernels replace libm by tables, integer clamps and seeded square roots, so this is where a range or
+sign assumption would show."""
+import math
+
+import numpy as np
+import pytest
+
+import hedgehog_jl_b200 as hh
+from hedgehog_jl_b200 import _abi as abi
+from hedgehog_jl_b200.engine import SimSpec
+from helpers import gbm_model, heston_model, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _random_heston(rng):
+    corr = rng.choice(["cholesky", "sym_sqrt", "svd"])
+    return heston_model(S0=float(10 ** rng.uniform(-3, 5)), r=float(rng.uniform(-0.05, 0.2)), T=float(rng.uniform(0.02, 10.0)),
+                        V0=float(10 ** rng.uniform(-4, 0)), kappa=float(10 ** rng.uniform(-2, 1.2)), theta=float(10 ** rng.uniform(-4, 0)),
+                        xi=float(rng.uniform(0.0, 2.0)), rho=float(rng.uniform(-0.999, 0.999)), corr=corr,
+                        split=bool(rng.integers(0, 2)))
+
+
+@pytest.mark.parametrize("seed", range(30))
+def test_heston_fast_kernels_on_random_models(cuda, oracle, seed):
+    rng = np.random.default_rng(1000 + seed)
+    m = _random_heston(rng)
+    steps = int(rng.integers(1, 60))
+    anti = int(rng.integers(0, 2))
+    n = int(rng.integers(1, 3000))
+    pay = [(m.S0 * float(k), float(cp)) for k, cp in ((0.8, 1.0), (1.0, -1.0), (1.3, 1.0))]
+    D = math.exp(-m.r * m.T)
+    sim = SimSpec(n_paths=n, n_steps=steps, vr=anti, base_seed=int(rng.integers(0, 2 ** 62)), path_offset=int(rng.integers(0, 2 ** 40)))
+    rg, tg = cuda.mc_european(m, sim, pay, D, want_terminal=True)
+    ro, to = oracle.mc_european(m, sim, pay, D, want_terminal=True)
+    fin = np.isfinite(to)
+    assert np.array_equal(np.isfinite(tg), fin)
+    # log-space comparison: x = log S carries the 1e-16-per-step differences. A path whose variance lands within rounding
+    # of the truncation kink sees them amplified by d sqrt(K2)/dK2 -> infinity (ill-conditioned in the scheme itself, for
+    # the oracle as for the GPU), hence a quantile bound plus a looser bound on the worst path.
+    dlog = np.abs(np.log(tg[fin]) - np.log(to[fin]))
+    assert np.quantile(dlog, 0.99) < 1e-10, np.quantile(dlog, 0.99)
+    assert dlog.max() < 1e-6, dlog.max()
+    # f32 fast mode stays finite and close on the same model (loose: MUFU approximations, binary32 state)
+    sim32 = SimSpec(n_paths=n, n_steps=steps, vr=anti, precision=abi.HH_PREC_F32, base_seed=sim.base_seed)
+    r32, t32 = cuda.mc_european(m, sim32, pay, D, want_terminal=True)
+    o32, u32 = oracle.mc_european(m, sim32, pay, D, want_terminal=True)
+    ok = np.isfinite(u32) & (u32 > 0)
+    assert np.all(np.isfinite(t32[ok]))
+    assert np.median(np.abs(np.log(t32[ok]) - np.log(u32[ok]))) < 1e-3
+
+
+@pytest.mark.parametrize("seed", range(15))
+def test_gbm_fast_kernels_on_random_models(cuda, oracle, seed):
+    rng = np.random.default_rng(2000 + seed)
+    m = gbm_model(S0=float(10 ** rng.uniform(-3, 5)), r=float(rng.uniform(-0.05, 0.3)), sigma=float(rng.uniform(0.0, 3.0)),
+                  T=float(rng.uniform(0.02, 10.0)))
+    # the reference's exact step S += S (exp(y) - 1) cancels catastrophically once exp(y) << 1; keep sigma sqrt(dt) <= 0.6 so
+    # that the comparison measures the kernels, not that formula (|y| > 1/2 still occurs: the libm path is exercised)
+    steps = max(int(rng.integers(1, 40)), int(math.ceil(m.T * (m.sigma / 0.6) ** 2)))
+    anti = int(rng.integers(0, 2))
+    n = int(rng.integers(1, 3000))
+    pay = [(m.S0, 1.0), (m.S0 * 1.2, -1.0)]
+    for scheme in (abi.HH_SCHEME_EM, abi.HH_SCHEME_EXACT_STEPS):  # sigma sqrt(dt) up to 3: the exp(y) - 1 slow path too
+        sim = SimSpec(n_paths=n, n_steps=steps, scheme=scheme, vr=anti, base_seed=int(rng.integers(0, 2 ** 62)))
+        rg, tg = cuda.mc_european(m, sim, pay, 0.9, want_terminal=True)
+        ro, to = oracle.mc_european(m, sim, pay, 0.9, want_terminal=True)
+        good = np.isfinite(to) & (to > 0)
+        dlog = np.abs(np.log(tg[good]) - np.log(to[good]))
+        assert np.quantile(dlog, 0.99) < 1e-10 and dlog.max() < 1e-7, (np.quantile(dlog, 0.99), dlog.max())
+
+
+@pytest.mark.parametrize("seed", range(15))
+def test_heston_tangent_kernel_on_random_models(cuda, oracle, seed):
+    rng = np.random.default_rng(3000 + seed)
+    m = _random_heston(rng)
+    m.T = float(rng.uniform(0.05, 2.0))
+    m.xi = float(rng.uniform(0.05, 0.8))
+    steps = int(rng.integers(2, 40))
+    anti = int(rng.integers(0, 2))
+    n = 1500
+    _, dM = hh.corr_factor(m.rho, "cholesky")
+    (m.m11, m.m12, m.m21, m.m22), _ = hh.corr_factor(m.rho, "cholesky")
+    tans = [abi.hh_tangent(dS0=1.0), abi.hh_tangent(dV0=1.0), abi.hh_tangent(dr=1.0), abi.hh_tangent(dkappa=1.0),
+            abi.hh_tangent(dtheta=1.0), abi.hh_tangent(dxi=1.0), abi.hh_tangent(dm11=dM[0], dm12=dM[1], dm21=dM[2], dm22=dM[3])]
+    nt = int(rng.integers(1, 8))
+    pay = [(m.S0 * 0.9, 1.0), (m.S0 * 1.1, -1.0)]
+    sim = SimSpec(n_paths=n, n_steps=steps, vr=anti, base_seed=int(rng.integers(0, 2 ** 62)))
+    sg, _ = cuda.tangent_sums(m, tans[:nt], sim, pay)
+    so, _ = oracle.tangent_sums(m, tans[:nt], sim, pay)
+    # sums of squares of tangents can be huge when the variance sits at zero (d sqrt -> infinity); compare the first moments
+    cols = [0, 1] + [2 + q for q in range(nt)]
+    scale = np.maximum(np.abs(so[:, cols]), 1e-8 * np.abs(so[:, cols]).max() + 1e-300)
+    assert np.max(np.abs(sg[:, cols] - so[:, cols]) / scale) < 1e-6
