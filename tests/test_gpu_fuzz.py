@@ -94,3 +94,27 @@ def test_heston_tangent_kernel_on_random_models(cuda, oracle, seed):
     cols = [0, 1] + [2 + q for q in range(nt)]
     scale = np.maximum(np.abs(so[:, cols]), 1e-8 * np.abs(so[:, cols]).max() + 1e-300)
     assert np.max(np.abs(sg[:, cols] - so[:, cols]) / scale) < 1e-6
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_lsm_on_random_contracts(cuda, oracle, seed):
+    """Random American contracts: stored paths 1e-12, stopping decisions equal to the QR oracle's except for a handful of
+    ties, price within 1e-6 (persistent kernel, Chebyshev normal equations, time-0 money vs the oracle's literal form)."""
+    rng = np.random.default_rng(4000 + seed)
+    m = gbm_model(S0=float(rng.uniform(20, 200)), r=float(rng.uniform(0.0, 0.12)), sigma=float(rng.uniform(0.05, 0.6)),
+                  T=float(rng.uniform(0.1, 3.0)))
+    steps = int(rng.integers(2, 30))
+    deg = int(rng.integers(1, 5))
+    anti = int(rng.integers(0, 2))
+    cp = float(rng.choice([-1.0, -1.0, 1.0]))
+    K = m.S0 * float(rng.uniform(0.85, 1.15))
+    n = int(rng.integers(5000, 30000))
+    sim = SimSpec(n_paths=n, n_steps=steps, scheme=abi.HH_SCHEME_EXACT_STEPS, vr=anti, base_seed=int(rng.integers(0, 2 ** 62)))
+    D = math.exp(-m.r * m.T / steps)
+    og, tg, vg, pg = cuda.lsm_american(m, sim, (K, cp), deg, D, want_stopping=True, want_paths=True)
+    oo, to, vo, po = oracle.lsm_american(m, sim, (K, cp), deg, D, want_stopping=True, want_paths=True)
+    assert rel_err(pg, po) < 1e-12
+    flips = int(np.sum(tg != to))
+    assert flips <= max(3, 3e-4 * len(to)), (flips, len(to))
+    assert abs(og.price - oo.price) <= (1e-9 if flips == 0 else 2e-5) * max(abs(oo.price), 1e-3), (og.price, oo.price, flips)
+    assert og.n_dates_skipped == oo.n_dates_skipped
