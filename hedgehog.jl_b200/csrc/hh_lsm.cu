@@ -120,6 +120,108 @@ __global__ void __launch_bounds__(kLsmPathThreads) lsm_paths_kernel(const LsmPat
   }
 }
 
+// ---- log-space generators --------------------------------------------------------------------------
+// The reference's extract_spot_grid takes component 1 of the saved state raw (least_squares_montecarlo.jl:53), which
+// under EulerMaruyama / HestonNoise is log S, not S: it only tests BlackScholesExact. This generator is the
+// corrected extraction for those schemes — the state is advanced in log space exactly as the pricing kernels do
+// (LogGBMProblem / LogHestonProblem, heston.jl:7-52) and every date stores S = exp(x), so the backward induction
+// below sees spots whatever the scheme.
+struct LsmLogArgs {
+  LsmPathArgs b;
+  PathParams<double> p;
+  int split;
+};
+
+constexpr int kLsmLogSmem = kLogRepBytes + kTrigRepBytes + kExp2Bytes;
+
+template <bool HESTON, bool ANTI, bool PARITY, bool UKEY>
+__global__ void __launch_bounds__(kLsmPathThreads) lsm_logspace_paths_kernel(const LsmLogArgs a) {
+  extern __shared__ __align__(16) unsigned char dsm[];
+  char *s_log = reinterpret_cast<char *>(dsm);
+  char *s_trig = s_log + kLogRepBytes;
+  double *s_e2 = reinterpret_cast<double *>(s_trig + kTrigRepBytes);
+  const int tid = threadIdx.x;
+  if (!PARITY) {
+    for (int e = tid; e < tables::kLog2Buckets * kRep; e += kLsmPathThreads)
+      reinterpret_cast<double2 *>(s_log)[e] = g_fast_tables2.log_tab[e / kRep];
+    for (int e = tid; e < tables::kTrigN * kRep; e += kLsmPathThreads)
+      reinterpret_cast<double2 *>(s_trig)[e] = g_fast_tables2.trig_tab[e / kRep];
+    for (int e = tid; e < tables::kExp2N; e += kLsmPathThreads) s_e2[e] = g_fast_tables2.exp_tab[e];
+  }
+  __syncthreads();
+  const char *log_lane = s_log + (tid & (kRep - 1)) * 16;
+  const char *trig_lane = s_trig + (tid & (kRep - 1)) * 16;
+  const char *exp_biased = reinterpret_cast<const char *>(s_e2) - tables::kExp2Bias * 8;
+  const LsmPathArgs &b = a.b;
+  const PathParams<double> &p = a.p;
+  const bool split = a.split != 0;
+  const int M = b.n_steps;
+  constexpr int NC = HESTON ? 2 : 1;
+  for (int64_t i = (int64_t)blockIdx.x * kLsmPathThreads + tid; i < b.n; i += (int64_t)gridDim.x * kLsmPathThreads) {
+    uint64_t idx = (uint64_t)(b.path_offset + i);
+    PhiloxRoundKeys rk_own;
+    if (!UKEY && !PARITY) {
+      rk_own = philox_round_keys(b.seeds[i]);
+      idx = 0;
+    }
+    const double *z = PARITY ? b.normals + (size_t)i * (size_t)M * NC : nullptr;
+    double xp = p.x0, xm = p.x0, vp = p.v0, vm = p.v0;
+    double *gp = b.grid + i;
+    double *gm = b.grid + b.n + i;
+    gp[0] = b.S0;
+    if (ANTI) gm[0] = b.S0;
+    if (HESTON) {
+#pragma unroll 1
+      for (int n = 0; n < M; ++n) {
+        double z1, z2;
+        if (PARITY) {
+          z1 = z[2 * n];
+          z2 = z[2 * n + 1];
+        } else {
+          const u32x4 w = philox4x32_10_rk((uint32_t)idx, (uint32_t)(idx >> 32), (uint32_t)n, 0u, UKEY ? b.rk : rk_own);
+          fast_normal_pair_v2(log_lane, exp_biased, trig_lane, w.x, w.y, w.z, w.w, b.one_hi, b.magic_hi, z1, z2);
+        }
+        const double dW1 = fma(p.a12, z2, p.a11 * z1);
+        const double dW2 = fma(p.a22, z2, p.a21 * z1);
+        heston_em_step<double>(p, split, xp, vp, dW1, dW2);
+        gp += b.stride;
+        *gp = exp(xp);
+        if (ANTI) {  // NoiseGrid(t, -W), montecarlo.jl:258
+          heston_em_step<double>(p, split, xm, vm, -dW1, -dW2);
+          gm += b.stride;
+          *gm = exp(xm);
+        }
+      }
+    } else {
+#pragma unroll 1
+      for (int n = 0; n < M; n += 2) {
+        double za, zb;
+        if (PARITY) {
+          za = z[n];
+          zb = n + 1 < M ? z[n + 1] : 0.0;
+        } else {
+          const u32x4 w = philox4x32_10_rk((uint32_t)idx, (uint32_t)(idx >> 32), (uint32_t)(n >> 1), 0u, UKEY ? b.rk : rk_own);
+          fast_normal_pair_v2(log_lane, exp_biased, trig_lane, w.x, w.y, w.z, w.w, b.one_hi, b.magic_hi, za, zb);
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          if (n + h < M) {
+            const double dW = p.sqdt * (h ? zb : za);
+            gbm_em_step<double>(p, xp, dW);
+            gp += b.stride;
+            *gp = exp(xp);
+            if (ANTI) {
+              gbm_em_step<double>(p, xm, -dW);
+              gm += b.stride;
+              *gm = exp(xm);
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
 // Fitted polynomial of one date, in the Chebyshev basis of u = a S + b. active = 0: the date was skipped
 // (no in-the-money column, least_squares_montecarlo.jl:122) or is the terminal date.
 struct LsmFit {
@@ -1061,8 +1163,12 @@ int lsm_american(hh_ctx *ctx, const hh_model *m, const hh_sim *s, const hh_payof
   if (degree < 0 || degree > kLsmMaxDeg) return ctx->fail(HH_ERR_ARG, "degree must be in [0, %d] (got %d)", kLsmMaxDeg, degree);
   // Q7: the reference reads component 1 of the saved state as the spot (least_squares_montecarlo.jl:53), which is
   // only true for the S-space BlackScholesExact generator — the only LSM configuration it tests.
-  if (m->kind != HH_MODEL_GBM || s->scheme != HH_SCHEME_EXACT_STEPS)
-    return ctx->fail(HH_ERR_UNSUPPORTED, "LSM runs on LognormalDynamics + BlackScholesExact paths (SURVEY Q7)");
+  // BlackScholesExact is the drop-in configuration; the log-space EulerMaruyama / HestonNoise generators are accepted
+  // too, with the corrected extraction S = exp(x) (lsm_logspace_paths_kernel).
+  const bool logspace = s->scheme == HH_SCHEME_EM;
+  if (!(m->kind == HH_MODEL_GBM && s->scheme == HH_SCHEME_EXACT_STEPS) && !logspace)
+    return ctx->fail(HH_ERR_UNSUPPORTED, "LSM runs on BlackScholesExact, EulerMaruyama or HestonNoise paths (SURVEY Q7)");
+  if (s->precision != HH_PREC_F64) return ctx->fail(HH_ERR_UNSUPPORTED, "LSM paths are generated in binary64");
   if ((stop_idx == nullptr) != (stop_val == nullptr))
     return ctx->fail(HH_ERR_ARG, "stop_idx and stop_val must be both NULL or both non-NULL");
   const bool peer_mode = comm && comm->world > 1 && !comm->allreduce_sum_f64;  // in-kernel exchange over peer memory
@@ -1104,7 +1210,7 @@ int lsm_american(hh_ctx *ctx, const hh_model *m, const hh_sim *s, const hh_payof
   pa.dt_drift = (m->r - 0.5 * (m->sigma * m->sigma)) * dt;
   pa.sig_sqdt = m->sigma * sqrt(dt);
   if (parity) {
-    const size_t bytes = sizeof(double) * (size_t)N * (size_t)M;
+    const size_t bytes = sizeof(double) * (size_t)N * (size_t)M * (m->kind == HH_MODEL_HESTON ? 2 : 1);
     HH_CUDA(ctx, ctx->d_normals.ensure(bytes));
     HH_CUDA(ctx, cudaMemcpyAsync(ctx->d_normals.ptr, s->normals, bytes, cudaMemcpyHostToDevice, st));
     pa.normals = ctx->d_normals.as<double>();
@@ -1151,7 +1257,55 @@ int lsm_american(hh_ctx *ctx, const hh_model *m, const hh_sim *s, const hh_payof
   HH_CUDA(ctx, cudaMemsetAsync(ctx->d_lsm_state.ptr, 0, fit_off + sizeof(LsmFit) * (size_t)(M + 1), st));
 
   HH_CUDA(ctx, cudaEventRecord(ctx->ev0, st));
-  {
+  if (logspace) {
+    LsmLogArgs la;
+    memset(&la, 0, sizeof la);
+    la.b = pa;
+    la.split = (m->flags & HH_FLAG_SPLIT_STEP) != 0;
+    PathParams<double> &p = la.p;
+    const double sqdt = sqrt(dt);
+    p.dt = dt;
+    p.sqdt = sqdt;
+    p.x0 = log(m->S0);
+    p.S0 = m->S0;
+    p.r = m->r;
+    const bool heston = m->kind == HH_MODEL_HESTON;
+    if (heston) {
+      p.v0 = m->V0;
+      p.kappa = m->kappa;
+      p.theta = m->theta;
+      p.xi = m->xi;
+      p.a11 = sqdt * m->m11;
+      p.a12 = sqdt * m->m12;
+      p.a21 = sqdt * m->m21;
+      p.a22 = sqdt * m->m22;
+    } else {
+      p.sigma = m->sigma;
+      p.dt_drift = dt * (m->r - 0.5 * (m->sigma * m->sigma));
+    }
+    const bool ukey = pa.seeds == nullptr;
+    cudaError_t le = cudaSuccess;
+#define HH_LSM_LOG(H, A, P, U)                                                                                            \
+  do {                                                                                                                  \
+    static bool attr_set = false;                                                                                       \
+    if (!attr_set) {                                                                                                    \
+      le = cudaFuncSetAttribute(lsm_logspace_paths_kernel<H, A, P, U>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+                                kLsmLogSmem);                                                                           \
+      attr_set = le == cudaSuccess;                                                                                     \
+    }                                                                                                                   \
+    if (le == cudaSuccess) lsm_logspace_paths_kernel<H, A, P, U><<<grid_paths, kLsmPathThreads, kLsmLogSmem, st>>>(la); \
+  } while (0)
+#define HH_LSM_LOG_H(H)                                                                                    \
+  do {                                                                                                     \
+    if (parity) { if (anti) HH_LSM_LOG(H, true, true, true); else HH_LSM_LOG(H, false, true, true); }     \
+    else if (ukey) { if (anti) HH_LSM_LOG(H, true, false, true); else HH_LSM_LOG(H, false, false, true); } \
+    else { if (anti) HH_LSM_LOG(H, true, false, false); else HH_LSM_LOG(H, false, false, false); }        \
+  } while (0)
+    if (heston) HH_LSM_LOG_H(true); else HH_LSM_LOG_H(false);
+#undef HH_LSM_LOG_H
+#undef HH_LSM_LOG
+    HH_CUDA(ctx, le);
+  } else {
     const bool ukey = pa.seeds == nullptr;
     cudaError_t le = cudaSuccess;
 #define HH_LSM_PATHS(A, P, U)                                                                                           \
@@ -1183,8 +1337,10 @@ int lsm_american(hh_ctx *ctx, const hh_model *m, const hh_sim *s, const hh_payof
     ua = 2.0 / payoff->strike;
     ub = -1.0;
   } else {  // call: S in (K, Smax), Smax = a 6-sigma excursion of the terminal spot
-    const double drift = fmax((m->r - 0.5 * m->sigma * m->sigma) * m->T, 0.0);
-    const double smax = fmax(m->S0, payoff->strike) * exp(drift + 6.0 * fabs(m->sigma) * sqrt(m->T));
+    // Heston: the larger of the initial and the long-run volatility stands in for sigma (the map only conditions the basis)
+    const double sg = m->kind == HH_MODEL_HESTON ? sqrt(fmax(fmax(m->V0, m->theta), 0.0)) : fabs(m->sigma);
+    const double drift = fmax((m->r - 0.5 * sg * sg) * m->T, 0.0);
+    const double smax = fmax(m->S0, payoff->strike) * exp(drift + 6.0 * sg * sqrt(m->T));
     ua = 2.0 / (smax - payoff->strike);
     ub = -1.0 - ua * payoff->strike;
   }

@@ -177,11 +177,19 @@ static terminal_t simulate_one(const hh_model *m, const hh_sim *sim, int64_t i, 
     /* LogGBMProblem heston.jl:33-52 ; EM: K = x + dt f ; x' = K + g dW [upstream] */
     double drift = m->r - 0.5 * (m->sigma * m->sigma);
     double xp = log(m->S0), xm = xp;
+    /* grid (LSM): the corrected S-space extraction exp(x) of the log state, not the raw component the
+     * reference takes (least_squares_montecarlo.jl:53, Q7) */
+    if (grid_p) grid_p[0] = m->S0;
+    if (grid_m) grid_m[0] = m->S0;
     for (int n = 0; n < M; ++n) {
       draw(m, sim, i, n, key, idx, &z1, &z2);
       double dW = sqdt * z1;
       xp = (xp + dt * drift) + m->sigma * dW;
-      if (anti) xm = (xm + dt * drift) + m->sigma * (-dW); /* NoiseGrid(t, -W) montecarlo.jl:258 */
+      if (grid_p) grid_p[(size_t)(n + 1) * gstride] = exp(xp);
+      if (anti) {
+        xm = (xm + dt * drift) + m->sigma * (-dW); /* NoiseGrid(t, -W) montecarlo.jl:258 */
+        if (grid_m) grid_m[(size_t)(n + 1) * gstride] = exp(xm);
+      }
     }
     out.Sp = exp(xp); /* final_sample montecarlo.jl:398 */
     out.Sm = anti ? exp(xm) : 0.0;
@@ -264,7 +272,11 @@ static terminal_t simulate_one(const hh_model *m, const hh_sim *sim, int64_t i, 
     const int split = (m->flags & HH_FLAG_SPLIT_STEP) != 0;
     const double a11 = sqdt * m->m11, a12 = sqdt * m->m12, a21 = sqdt * m->m21, a22 = sqdt * m->m22;
     double xp = log(m->S0), vp = m->V0, xm = xp, vm = vp;
+    if (grid_p) grid_p[0] = m->S0; /* LSM grid: S = exp(x), see the GBM EM branch */
+    if (grid_m) grid_m[0] = m->S0;
     for (int n = 0; n < M; ++n) {
+      if (n > 0 && grid_p) grid_p[(size_t)n * gstride] = exp(xp);
+      if (n > 0 && grid_m) grid_m[(size_t)n * gstride] = exp(xm);
       draw(m, sim, i, n, key, idx, &z1, &z2);
       double dW1 = a11 * z1 + a12 * z2;
       double dW2 = a21 * z1 + a22 * z2;
@@ -289,6 +301,8 @@ static terminal_t simulate_one(const hh_model *m, const hh_sim *sim, int64_t i, 
     out.vp = vp;
     out.Sm = anti ? exp(xm) : 0.0;
     out.vm = vm;
+    if (grid_p) grid_p[(size_t)M * gstride] = out.Sp;
+    if (grid_m) grid_m[(size_t)M * gstride] = out.Sm;
     return out;
   }
   out.Sp = NAN;
@@ -626,8 +640,11 @@ int hho_lsm_american(const hh_model *model, const hh_sim *sim, const hh_payoff *
   int rc = check_args(model, sim);
   if (rc) return rc;
   /* Q7: LSM reads component 1 of the saved state as the spot (lsm.jl:53) — only the S-space
-   * BlackScholesExact generator is meaningful. */
-  if (model->kind != HH_MODEL_GBM || sim->scheme != HH_SCHEME_EXACT_STEPS) return HH_ERR_UNSUPPORTED;
+   * BlackScholesExact generator is meaningful in the reference. The log-space Euler-Maruyama schemes are
+   * accepted here with the corrected extraction S = exp(x), binary64 only. */
+  if (!(model->kind == HH_MODEL_GBM && sim->scheme == HH_SCHEME_EXACT_STEPS) && sim->scheme != HH_SCHEME_EM)
+    return HH_ERR_UNSUPPORTED;
+  if (sim->precision != HH_PREC_F64) return HH_ERR_UNSUPPORTED;
   const int64_t N = sim->n_paths;
   const int anti = sim->vr == HH_VR_ANTITHETIC;
   const int64_t ncols = anti ? 2 * N : N;

@@ -89,8 +89,8 @@ def test_lsm_small_and_odd_shapes(cuda, oracle, n, steps, deg):
         assert abs(og.price - oo.price) < 1e-6 * oo.price
     with pytest.raises(ValueError):
         cuda.lsm_american(m, sim, (105.0, -1.0), 9, D)     # degree above the built maximum
-    with pytest.raises(NotImplementedError):                # Q7: LSM on log-space schemes is rejected
-        cuda.lsm_american(m, SimSpec(n_paths=n, n_steps=steps, scheme=abi.HH_SCHEME_EM), (105.0, -1.0), 2, D)
+    with pytest.raises(NotImplementedError):                # the terminal-law sampler saves no dates
+        cuda.lsm_american(m, SimSpec(n_paths=n, n_steps=steps, scheme=abi.HH_SCHEME_EXACT_TERMINAL), (105.0, -1.0), 2, D)
 
 
 def test_global_trajectory_index_beyond_32_bits(cuda, oracle):

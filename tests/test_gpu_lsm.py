@@ -13,7 +13,7 @@ import pytest
 import hedgehog_jl_b200 as hh
 from hedgehog_jl_b200 import _abi as abi
 from hedgehog_jl_b200.engine import SimSpec
-from helpers import gbm_model, rel_err
+from helpers import gbm_model, heston_model, rel_err
 
 pytestmark = pytest.mark.gpu
 
@@ -24,14 +24,14 @@ def _run_both(cuda, oracle, m, sim, payoff, degree, D):
     return (og, tg, vg, pg), (oo, to, vo, po)
 
 
-def _check(g, o, max_flip_frac=2e-4):
+def _check(g, o, max_flip_frac=2e-4, path_tol=1e-12):
     (og, tg, vg, pg), (oo, to, vo, po) = g, o
-    assert rel_err(pg, po) < 1e-12
+    assert rel_err(pg, po) < path_tol
     assert og.n == oo.n
     flips = int(np.sum(tg != to))
     assert flips <= max(2, max_flip_frac * len(to)), flips
     same = tg == to
-    assert rel_err(vg[same] + 1.0, vo[same] + 1.0) < 1e-12
+    assert rel_err(vg[same] + 1.0, vo[same] + 1.0) < path_tol
     if flips == 0:
         assert abs(og.price - oo.price) <= 1e-9 * abs(oo.price)
         assert abs(og.std_error - oo.std_error) <= 1e-7 * abs(oo.std_error)
@@ -116,8 +116,13 @@ def test_lsm_edge_cases(cuda, oracle):
     # argument errors
     with pytest.raises(ValueError):
         cuda.lsm_american(m, SimSpec(n_paths=10, n_steps=5, scheme=abi.HH_SCHEME_EXACT_STEPS), (100.0, -1.0), 99, 0.99)
-    with pytest.raises(NotImplementedError):  # Q7: only the S-space generator is meaningful
-        cuda.lsm_american(m, SimSpec(n_paths=10, n_steps=5, scheme=abi.HH_SCHEME_EM), (100.0, -1.0), 3, 0.99)
+    with pytest.raises(NotImplementedError):  # the terminal-law sampler saves no dates: nothing to regress on
+        cuda.lsm_american(m, SimSpec(n_paths=10, n_steps=5, scheme=abi.HH_SCHEME_EXACT_TERMINAL), (100.0, -1.0), 3, 0.99)
+    with pytest.raises(NotImplementedError):  # nor does Broadie-Kaya
+        cuda.lsm_american(heston_model(), SimSpec(n_paths=10, n_steps=5, scheme=abi.HH_SCHEME_HESTON_BK), (100.0, -1.0), 3, 0.99)
+    with pytest.raises(NotImplementedError):  # LSM grids are binary64
+        cuda.lsm_american(heston_model(), SimSpec(n_paths=10, n_steps=5, scheme=abi.HH_SCHEME_EM, precision=abi.HH_PREC_F32),
+                          (100.0, -1.0), 3, 0.99)
 
 
 def test_peer_exchange_request_without_connection_is_an_argument_error(cuda):
@@ -180,3 +185,86 @@ print(json.dumps(out))
         a, b = res["1"][anti], res["0"][anti]
         assert abs(a[0] - b[0]) <= 1e-9 * abs(b[0]), (a, b)
         assert abs(a[2] - b[2]) <= 25 * 3  # at most a few tie flips
+
+
+# ---- log-space generators with the corrected S-space extraction ------------------------------------
+# The oracle restates the same extension (oracle/hh_oracle.c simulate_one, grid stores exp(x)); the reference itself
+# would regress on log S here (least_squares_montecarlo.jl:53), so there is no reference behaviour to match beyond
+# the schemes themselves, which the European parity tests pin.
+
+def _normals(n, steps, nc, seed=5):
+    return np.random.default_rng(seed).standard_normal((n, steps, nc)) if nc > 1 else np.random.default_rng(seed).standard_normal((n, steps))
+
+
+@pytest.mark.parametrize("anti", [False, True])
+@pytest.mark.parametrize("model", ["gbm", "heston", "heston_nosplit"])
+def test_lsm_logspace_parity_mode(cuda, oracle, model, anti):
+    n, steps = 4099, 24
+    m = gbm_model() if model == "gbm" else heston_model(split=model == "heston")
+    z = np.ascontiguousarray(_normals(n, steps, 1 if model == "gbm" else 2))
+    sim = SimSpec(n_paths=n, n_steps=steps, scheme=abi.HH_SCHEME_EM, vr=int(anti), rng_mode=abi.HH_RNG_NORMALS, normals=z)
+    D = math.exp(-m.r * m.T / steps)
+    g, o = _run_both(cuda, oracle, m, sim, (100.0, -1.0), 3, D)
+    _check(g, o, max_flip_frac=5e-4, path_tol=1e-11)
+    assert np.all(g[3][:, 0] == m.S0) and np.all(g[3] > 0.0)  # spots, not log-spots
+
+
+@pytest.mark.parametrize("model", ["gbm", "heston"])
+@pytest.mark.parametrize("seeded", [False, True])
+def test_lsm_logspace_native_rng(cuda, oracle, model, seeded):
+    n, steps = 30_001, 40
+    m = gbm_model(sigma=0.3) if model == "gbm" else heston_model(xi=0.5, rho=-0.5)
+    kw = dict(seeds=np.random.Generator(np.random.Philox(3)).integers(0, 2**64, size=n, dtype=np.uint64)) if seeded \
+        else dict(base_seed=99, path_offset=12345)
+    sim = SimSpec(n_paths=n, n_steps=steps, scheme=abi.HH_SCHEME_EM, vr=abi.HH_VR_ANTITHETIC, **kw)
+    D = math.exp(-m.r * m.T / steps)
+    _check(*_run_both(cuda, oracle, m, sim, (105.0, -1.0), 4, D), max_flip_frac=5e-4, path_tol=1e-10)
+
+
+def test_lsm_gbm_em_equals_exact_steps_on_the_same_normals(cuda):
+    """x' = x + (r - s^2/2) dt + s sqrt(dt) Z and S' = S exp(the same) are one law: with the same normals the two
+    generators give the same spots to rounding and hence the same price."""
+    n, steps = 20_000, 30
+    m = gbm_model()
+    z = np.random.default_rng(8).standard_normal((n, steps))
+    D = math.exp(-m.r * m.T / steps)
+    res = {}
+    for scheme in (abi.HH_SCHEME_EM, abi.HH_SCHEME_EXACT_STEPS):
+        sim = SimSpec(n_paths=n, n_steps=steps, scheme=scheme, vr=abi.HH_VR_ANTITHETIC, rng_mode=abi.HH_RNG_NORMALS, normals=z)
+        res[scheme] = cuda.lsm_american(m, sim, (100.0, -1.0), 3, D, want_stopping=True, want_paths=True)
+    a, b = res[abi.HH_SCHEME_EM], res[abi.HH_SCHEME_EXACT_STEPS]
+    assert rel_err(a[3], b[3]) < 1e-12
+    assert np.mean(a[1] != b[1]) < 5e-4
+    assert abs(a[0].price - b[0].price) < 1e-5 * b[0].price
+
+
+def test_lsm_heston_degenerate_to_gbm(cuda):
+    """xi = 0, V0 = theta: the variance stays at theta and the log-Heston step is the log-GBM step with sigma = sqrt(theta)."""
+    n, steps = 20_000, 30
+    z2 = np.random.default_rng(9).standard_normal((n, steps, 2))
+    mg = gbm_model(r=0.03, sigma=0.2)
+    mh = heston_model(r=0.03, V0=0.04, theta=0.04, xi=0.0, rho=0.0)
+    D = math.exp(-0.03 / steps)
+    sg = SimSpec(n_paths=n, n_steps=steps, scheme=abi.HH_SCHEME_EM, rng_mode=abi.HH_RNG_NORMALS, normals=np.ascontiguousarray(z2[:, :, 0]))
+    sh = SimSpec(n_paths=n, n_steps=steps, scheme=abi.HH_SCHEME_EM, rng_mode=abi.HH_RNG_NORMALS, normals=z2)
+    a = cuda.lsm_american(mg, sg, (100.0, -1.0), 3, D, want_stopping=True, want_paths=True)
+    b = cuda.lsm_american(mh, sh, (100.0, -1.0), 3, D, want_stopping=True, want_paths=True)
+    assert rel_err(a[3], b[3]) < 1e-12
+    assert abs(a[0].price - b[0].price) < 1e-5 * b[0].price
+
+
+def test_lsm_heston_american_put_through_solve(cuda):
+    """solve(PricingProblem{American}, LSM(HestonDynamics, EulerMaruyama)): American >= European (Carr-Madan) and the
+    early-exercise premium is of the Black-Scholes order of magnitude at the same volatility level."""
+    from oracle import anchors as A
+    ref, exp = dt.date(2020, 1, 1), dt.date(2021, 1, 1)
+    prob = hh.PricingProblem(hh.VanillaOption(100.0, exp, hh.American(), hh.Put(), hh.Spot()),
+                             hh.HestonInputs(ref, 0.05, 100.0, 0.04, 2.0, 0.04, 0.3, -0.7))
+    cfg = hh.SimulationConfig(400_000, steps=100, base_seed=2024, variance_reduction=hh.Antithetic())
+    sol = hh.solve(prob, hh.LSM(hh.HestonDynamics(), hh.EulerMaruyama(), cfg, 3), engine=cuda, stopping_info=False)
+    T = 366 / 365
+    call = A.heston_price(100.0, 100.0, 0.05, T, 0.04, 2.0, 0.04, 0.3, -0.7)
+    euro_put = call - 100.0 + 100.0 * math.exp(-0.05 * T)
+    assert sol.price > euro_put + 3 * sol.std_error
+    bs_premium = A.crr_price(100.0, 100.0, 0.05, 0.2, T, 1000, cp=-1, american=True) - A.bs_price(100.0, 100.0, 0.05, 0.2, T, cp=-1)
+    assert 0.4 * bs_premium < sol.price - euro_put < 2.0 * bs_premium

@@ -160,3 +160,50 @@ def test_f32_restatement_agrees_with_f64_statistically(oracle):
     cm = anchors.heston_price(100.0, 100.0, m.r, m.T, m.V0, m.kappa, m.theta, m.xi, m.rho)
     assert abs(r32[0].price - r64[0].price) < 3 * math.hypot(r32[0].std_error, r64[0].std_error)
     assert abs(r32[0].price - cm) < 3 * r32[0].std_error + 0.02
+
+
+# ---- LSM on the log-space schemes (extraction S = exp(x)) ---------------------------------------------
+
+def test_lsm_logspace_extraction_is_consistent_across_schemes(oracle):
+    """The same normals through BlackScholesExact (S-space), log-GBM Euler-Maruyama and a degenerate log-Heston
+    (xi = 0, V0 = theta = sigma^2) are one law: equal spot grids (to rounding) and equal LSM prices."""
+    from hedgehog_jl_b200 import _abi as abi
+    from hedgehog_jl_b200.engine import SimSpec
+    from helpers import gbm_model, heston_model, rel_err
+    n, steps = 5000, 20
+    z2 = np.random.default_rng(3).standard_normal((n, steps, 2))
+    z1 = np.ascontiguousarray(z2[:, :, 0])
+    mg, mh = gbm_model(r=0.03, sigma=0.2), heston_model(r=0.03, V0=0.04, theta=0.04, xi=0.0, rho=0.0)
+    D = math.exp(-0.03 / steps)
+    runs = []
+    for m, scheme, z in ((mg, abi.HH_SCHEME_EXACT_STEPS, z1), (mg, abi.HH_SCHEME_EM, z1), (mh, abi.HH_SCHEME_EM, z2)):
+        sim = SimSpec(n_paths=n, n_steps=steps, scheme=scheme, vr=abi.HH_VR_ANTITHETIC, rng_mode=abi.HH_RNG_NORMALS, normals=z)
+        runs.append(oracle.lsm_american(m, sim, (100.0, -1.0), 3, D, want_stopping=True, want_paths=True))
+    base = runs[0]
+    for r in runs[1:]:
+        assert rel_err(r[3], base[3]) < 1e-12
+        assert np.mean(r[1] != base[1]) < 1e-3
+        assert r[0].price == pytest.approx(base[0].price, rel=1e-4)
+    assert np.all(base[3][:, 0] == 100.0)
+
+
+def test_lsm_heston_american_put_premium(oracle):
+    """LSM(HestonDynamics, EulerMaruyama): American >= European (Carr-Madan by put-call parity), with a premium of
+    the Black-Scholes order at the same volatility level."""
+    prob = hh.PricingProblem(hh.VanillaOption(100.0, EXP, hh.American(), hh.Put(), hh.Spot()),
+                             hh.HestonInputs(REF, 0.05, 100.0, 0.04, 2.0, 0.04, 0.3, -0.7))
+    cfg = hh.SimulationConfig(40_000, steps=50, base_seed=11, variance_reduction=hh.Antithetic())
+    sol = hh.solve(prob, hh.LSM(hh.HestonDynamics(), hh.EulerMaruyama(), cfg, 3), engine=oracle, stopping_info=False)
+    T = 366 / 365
+    euro_put = A.heston_price(100.0, 100.0, 0.05, T, 0.04, 2.0, 0.04, 0.3, -0.7) - 100.0 + 100.0 * math.exp(-0.05 * T)
+    bs_premium = A.crr_price(100.0, 100.0, 0.05, 0.2, T, 1000, cp=-1, american=True) - A.bs_price(100.0, 100.0, 0.05, 0.2, T, cp=-1)
+    assert sol.price > euro_put
+    assert 0.4 * bs_premium < sol.price - euro_put < 2.0 * bs_premium
+
+
+def test_lsm_rejects_schemes_without_saved_dates(oracle):
+    from hedgehog_jl_b200 import _abi as abi
+    from hedgehog_jl_b200.engine import SimSpec
+    from helpers import gbm_model
+    with pytest.raises(NotImplementedError):
+        oracle.lsm_american(gbm_model(), SimSpec(n_paths=10, n_steps=5, scheme=abi.HH_SCHEME_EXACT_TERMINAL), (100.0, -1.0), 2, 0.99)

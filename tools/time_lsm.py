@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""Times config C3 (American put LSM under GBM): usage python tools/time_lsm.py [paths] [dates] [degree]"""
+"""Times config C3 (American put LSM under GBM): usage python tools/time_lsm.py [paths] [dates] [degree]
+HH_LSM_MODEL = gbm (BlackScholesExact, default) | gbm_em | heston_em picks the path generator."""
 import math
 import os
 import sys
@@ -16,13 +17,19 @@ eng = hh.default_engine(0)
 m = abi.hh_model()
 m.kind, m.flags = abi.HH_MODEL_GBM, abi.HH_FLAG_SPLIT_STEP
 m.S0, m.r, m.T, m.sigma = 100.0, 0.05, 1.0, 0.2
+which = os.environ.get("HH_LSM_MODEL", "gbm")
+scheme = abi.HH_SCHEME_EXACT_STEPS if which == "gbm" else abi.HH_SCHEME_EM
+if which == "heston_em":
+    m.kind = abi.HH_MODEL_HESTON
+    m.V0, m.kappa, m.theta, m.xi, m.rho = 0.04, 2.0, 0.04, 0.3, -0.7
+    (m.m11, m.m12, m.m21, m.m22), _ = hh.corr_factor(m.rho, "cholesky")
 best = None
 for rep in range(4):
-    sim = SimSpec(n_paths=n, n_steps=steps, scheme=abi.HH_SCHEME_EXACT_STEPS, base_seed=12345 + rep)
+    sim = SimSpec(n_paths=n, n_steps=steps, scheme=scheme, base_seed=12345 + rep)
     out, *_ = eng.lsm_american(m, sim, (100.0, -1.0), deg, math.exp(-m.r * m.T / steps))
     if best is None or out.kernel_ms < best.kernel_ms:
         best = out
 gb = n * steps * 32 / 1e9
-print(f"paths={n} dates={steps} degree={deg} price={best.price:.5f} se={best.std_error:.5f} path_ms={best.path_ms:.3f} "
+print(f"model={which} paths={n} dates={steps} degree={deg} price={best.price:.5f} se={best.std_error:.5f} path_ms={best.path_ms:.3f} "
       f"regress_ms={best.regress_ms:.3f} total_ms={best.kernel_ms:.3f} algorithmic_GBps={gb / (best.kernel_ms * 1e-3):.1f} "
       f"regress_GBps(24B/col-date)={n * (steps) * 24 / 1e9 / (best.regress_ms * 1e-3):.1f}")
