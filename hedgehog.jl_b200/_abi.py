@@ -57,6 +57,18 @@ class hh_payoff(C.Structure):
     _fields_ = [("strike", C.c_double), ("cp", C.c_double)]
 
 
+# hh_mc_path_dependent (include/hedgehog_mc.h): payoff kinds and per-column statistics
+(HH_PD_VANILLA, HH_PD_ASIAN_ARITH, HH_PD_ASIAN_GEOM, HH_PD_UP_OUT, HH_PD_UP_IN, HH_PD_DOWN_OUT, HH_PD_DOWN_IN,
+ HH_PD_DIGITAL_CASH, HH_PD_DIGITAL_ASSET) = range(9)
+HH_PD_NKINDS = 9
+HH_PD_NSTATS = 5
+
+
+class hh_path_payoff(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("reserved", C.c_int32), ("strike", C.c_double), ("cp", C.c_double),
+                ("barrier", C.c_double), ("amount", C.c_double)]
+
+
 class hh_result(C.Structure):
     _fields_ = [
         ("sum", C.c_double), ("sumsq", C.c_double), ("n", C.c_int64), ("price", C.c_double),
@@ -111,6 +123,8 @@ SYMBOLS = {
     "hh_lsm_american": (C.c_int, [C.c_void_p, C.POINTER(hh_model), C.POINTER(hh_sim), C.POINTER(hh_payoff), C.c_int,
                                   C.c_double, C.POINTER(hh_comm), C.POINTER(hh_lsm_result), C.POINTER(C.c_int32),
                                   _dp, _dp]),
+    "hh_mc_path_dependent": (C.c_int, [C.c_void_p, C.POINTER(hh_model), C.POINTER(hh_sim), C.c_int,
+                                       C.POINTER(hh_path_payoff), C.c_int, C.c_double, C.POINTER(hh_result), _dp, C.c_size_t]),
     "hh_bk_chf": (C.c_int, [C.c_void_p, C.POINTER(hh_model), C.c_double, _dp, _dp, C.c_int, _dp, C.c_int, _dp, _dp]),
     "hh_bk_log_besseli": (C.c_int, [C.c_void_p, C.c_double, _dp, _dp, C.c_int, _dp, _dp]),
     "hh_bk_integral": (C.c_int, [C.c_void_p, C.POINTER(hh_model), C.c_double, C.POINTER(hh_bk_config), _dp, _dp, _dp,

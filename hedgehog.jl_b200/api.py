@@ -375,8 +375,16 @@ def solve(prob, method, *args, engine=None, shard=None, group=None, **kw):
         return _c.solve_calibration(prob, method, *args, engine=engine, shard=shard, group=group, **kw)
     if isinstance(prob, (_g.GreekProblem, _g.BatchGreekProblem, _g.SecondOrderGreekProblem)):
         return _g.solve_greek(prob, method, *args, engine=engine, shard=shard, group=group, **kw)
+    from . import pathdep as _pd
     if isinstance(prob, BasketPricingProblem):
+        if isinstance(method, MonteCarlo) and any(_pd.is_path_payoff(p) for p in prob.payoffs):
+            res, stats = _pd.solve_path_dependent(prob.payoffs, prob.market_inputs, method, engine=engine, shard=shard, group=group)
+            return [MonteCarloSolution(PricingProblem(p, prob.market_inputs), method, price, None, se, stats)
+                    for p, (price, se) in zip(prob.payoffs, res)]
         return _solve_basket(prob, method, engine, shard, group)
+    if isinstance(method, MonteCarlo) and _pd.is_path_payoff(prob.payoff):
+        ((price, se),), stats = _pd.solve_path_dependent([prob.payoff], prob.market_inputs, method, engine=engine, shard=shard, group=group)
+        return MonteCarloSolution(prob, method, price, None, se, stats)
     if isinstance(method, LSM):
         from .lsm import solve_lsm
         return solve_lsm(prob, method, engine=engine, shard=shard, group=group, **kw)

@@ -230,6 +230,14 @@ int hh_mc_european(hh_ctx *ctx, const hh_model *model, const hh_sim *sim, const 
   return hh_mc_european_collect(ctx, discount, results, terminal, terminal_len);
 }
 
+int hh_mc_path_dependent(hh_ctx *ctx, const hh_model *model, const hh_sim *sim, int monitor_every,
+                         const hh_path_payoff *payoffs, int npayoffs, double discount, hh_result *results,
+                         double *path_stats, size_t path_stats_len) {
+  if (!ctx) return HH_ERR_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  return hh::path_dependent(ctx, model, sim, monitor_every, payoffs, npayoffs, discount, results, path_stats, path_stats_len);
+}
+
 int hh_mc_european_tangent_sums(hh_ctx *ctx, const hh_model *model, const hh_tangent *tangents, int ntangents,
                                 const hh_sim *sim, const hh_payoff *payoffs, int npayoffs, double *sums,
                                 double *kernel_ms) {

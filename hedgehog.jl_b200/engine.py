@@ -53,6 +53,13 @@ class SimSpec:
         return s, keep
 
 
+def path_payoff_array(payoffs):
+    arr = (abi.hh_path_payoff * len(payoffs))()
+    for i, (kind, strike, cp, barrier, amount) in enumerate(payoffs):
+        arr[i].kind, arr[i].strike, arr[i].cp, arr[i].barrier, arr[i].amount = int(kind), float(strike), float(cp), float(barrier), float(amount)
+    return arr
+
+
 def _payoff_array(payoffs: Sequence[tuple]):
     arr = (abi.hh_payoff * len(payoffs))()
     for i, (k, cp) in enumerate(payoffs):
@@ -205,6 +212,23 @@ class CudaEngine:
         self._check(rc, "hh_lsm_american")
         del keep
         return out, stop_idx, stop_val, paths
+
+    # -- path-dependent payoffs (hh_mc_path_dependent) -------------------------------------------------------
+    def mc_path_dependent(self, model, sim: SimSpec, payoffs, discount: float, monitor_every: int = 1,
+                          want_stats: bool = False):
+        """payoffs: sequence of (kind, strike, cp, barrier, amount). Returns (results, stats) with stats the
+        HH_PD_NSTATS x ncols array [S_T, A, G, max S, min S] or None."""
+        s, keep = sim.to_c(self.lib)
+        pa = path_payoff_array(payoffs)
+        res = (abi.hh_result * len(payoffs))()
+        ncols = sim.n_paths * (2 if sim.vr == abi.HH_VR_ANTITHETIC else 1)
+        stats = np.empty((abi.HH_PD_NSTATS, ncols), dtype=np.float64) if want_stats else None
+        rc = self.lib.hh_mc_path_dependent(self.h, C.byref(model), C.byref(s), int(monitor_every), pa, len(payoffs),
+                                           float(discount), res, _dp(stats) if want_stats else None,
+                                           stats.size if want_stats else 0)
+        self._check(rc, "hh_mc_path_dependent")
+        del keep
+        return list(res), stats
 
     # -- Broadie-Kaya probes ---------------------------------------------------------------------------
     def bk_chf(self, model, tau: float, V0: np.ndarray, VT: np.ndarray, a: np.ndarray):

@@ -19,7 +19,7 @@ using Hedgehog: PricingProblem, VanillaOption, European, American, Spot, Abstrac
                 SpotLens, VolLens, ZeroRateSpineLens, yearfrac, add_yearfrac, zero_rate, df, get_vol
 using Libdl
 
-export B200MonteCarlo, B200LSM, b200_library!
+export B200MonteCarlo, B200LSM, b200_library!, AsianOption, BarrierOption, DigitalOption
 
 # ---- library handle -----------------------------------------------------------------------------------------------
 const LIB = Ref{String}(get(ENV, "HEDGEHOG_MC_LIB", joinpath(@__DIR__, "..", "libhedgehog_mc.so")))
@@ -214,6 +214,45 @@ function Hedgehog.solve(prob::PricingProblem{VanillaOption{TS,TE,American,C,S},I
     end
     stopping_info = [(Int(stop_idx[p]), stop_val[p]) for p in 1:ncols]      # :112, :163-164
     return LSMSolution(prob, method, out[].price, stopping_info, spot)       # :135
+end
+
+# ---- path-dependent payoffs (roadmap Phase 5, derivatives_pricing_roadmap.md:73-80; hh_mc_path_dependent) -------------
+# Hedgehog has no Asian / barrier / digital payoff types yet. These follow VanillaOption's conventions (payoffs.jl:101-140:
+# strike, expiry in ticks, call_put functor) so that solve(PricingProblem(payoff, inputs), B200MonteCarlo(...)) reads
+# like the European solve. `monitor_every`: monitoring dates are every k-th step of config.steps, expiry included.
+struct HHPathPayoff
+    kind::Int32; reserved::Int32; strike::Float64; cp::Float64; barrier::Float64; amount::Float64
+end
+abstract type PathDependentPayoff <: Hedgehog.AbstractPayoff end
+struct AsianOption{TS,TE,C<:Hedgehog.AbstractCallPut} <: PathDependentPayoff
+    strike::TS; expiry::TE; call_put::C; geometric::Bool; monitor_every::Int
+end
+struct BarrierOption{TS,TE,C<:Hedgehog.AbstractCallPut} <: PathDependentPayoff
+    strike::TS; barrier::TS; expiry::TE; call_put::C; up::Bool; knock_out::Bool; rebate::TS; monitor_every::Int
+end
+struct DigitalOption{TS,TE,C<:Hedgehog.AbstractCallPut} <: PathDependentPayoff
+    strike::TS; expiry::TE; call_put::C; cash::Union{Nothing,TS}; monitor_every::Int   # cash === nothing: asset-or-nothing
+end
+hh_path_payoff(p::AsianOption) = HHPathPayoff(p.geometric ? 2 : 1, 0, p.strike, p.call_put(), 0.0, 0.0)
+hh_path_payoff(p::BarrierOption) =
+    HHPathPayoff(p.up ? (p.knock_out ? 3 : 4) : (p.knock_out ? 5 : 6), 0, p.strike, p.call_put(), p.barrier, p.rebate)
+hh_path_payoff(p::DigitalOption) =
+    p.cash === nothing ? HHPathPayoff(8, 0, p.strike, p.call_put(), 0.0, 0.0) : HHPathPayoff(7, 0, p.strike, p.call_put(), 0.0, p.cash)
+
+function Hedgehog.solve(prob::PricingProblem{P,I}, method::B200MonteCarlo) where {P<:PathDependentPayoff,I<:AbstractMarketInputs}
+    ctx = context()
+    model = hh_model(prob, method.dynamics)
+    scheme = scheme_of(method.strategy, true)                     # BlackScholesExact in its stepping form
+    payoff = hh_path_payoff(prob.payoff)
+    discount = df(prob.market_inputs.rate, prob.payoff.expiry)    # montecarlo.jl:489
+    res = Ref(HHResult(0, 0, 0, 0, 0, 0, 0, 0))
+    with_sim(method, scheme) do sim
+        rc = ccall((:hh_mc_path_dependent, LIB[]), Cint,
+                   (Ptr{Cvoid}, Ref{HHModel}, Ref{HHSim}, Cint, Ref{HHPathPayoff}, Cint, Cdouble, Ref{HHResult}, Ptr{Float64}, Csize_t),
+                   ctx.h, model, sim, prob.payoff.monitor_every, payoff, 1, discount, res, Ptr{Float64}(C_NULL), 0)
+        check(ctx, rc, "hh_mc_path_dependent")
+    end
+    return MonteCarloSolution(prob, method, res[].price, Float64[])
 end
 
 # ---- Greeks: every ForwardAD lens is one tangent direction of the SAME simulation (greeks_problem.jl:249-262, 559-568) ---

@@ -1,0 +1,156 @@
+"""Path-dependent payoffs priced on the Monte Carlo path — SURVEY §8(f) N4.
+
+The reference has none of these yet; its roadmap lists them as Phase 5 (derivatives_pricing_roadmap.md:73-80:
+arithmetic / geometric Asians, digitals, discretely monitored barriers, "Monitoring / Averaging modifiers"). The types
+below follow the conventions of `VanillaOption` (payoffs.jl:101-140: strike, expiry, call_put) so that
+`solve(PricingProblem(payoff, market_inputs), MonteCarlo(dynamics, strategy, config))` reads like the reference's
+European solve; all numerics run in `hh_mc_path_dependent` (csrc/hh_pathdep.cu)."""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Any, Sequence
+
+import numpy as np
+
+from . import _abi as abi
+from . import api
+
+
+# ---- modifiers ----------------------------------------------------------------------------------------------------------
+class ArithmeticAverage: pass
+class GeometricAverage: pass
+class Up: pass
+class Down: pass
+class KnockIn: pass
+class KnockOut: pass
+class AssetOrNothing: pass
+
+
+@dataclass(frozen=True)
+class CashOrNothing:
+    amount: float = 1.0
+
+
+@dataclass(frozen=True)
+class Monitoring:
+    """Monitoring dates = every `every`-th step of SimulationConfig.steps (t = 0 excluded, expiry included)."""
+    every: int = 1
+
+
+class _PathPayoff:
+    exercise_style = api.European()
+    underlying = api.Spot()
+
+    def _base(self, strike, expiry_date, call_put, monitoring):
+        object.__setattr__(self, "strike", strike)
+        object.__setattr__(self, "expiry", api.to_ticks(expiry_date))
+        object.__setattr__(self, "call_put", call_put)
+        object.__setattr__(self, "monitoring", monitoring or Monitoring())
+
+
+@dataclass(frozen=True, init=False)
+class AsianOption(_PathPayoff):
+    """max(cp (avg S - K), 0), fixed strike, average over the monitoring dates."""
+    strike: float
+    expiry: int
+    call_put: Any
+    averaging: Any
+    monitoring: Monitoring
+
+    def __init__(self, strike, expiry_date, call_put, averaging=None, monitoring=None):
+        self._base(strike, expiry_date, call_put, monitoring)
+        object.__setattr__(self, "averaging", averaging or ArithmeticAverage())
+
+    def abi_tuple(self):
+        kind = abi.HH_PD_ASIAN_GEOM if isinstance(self.averaging, GeometricAverage) else abi.HH_PD_ASIAN_ARITH
+        return (kind, self.strike, self.call_put(), 0.0, 0.0)
+
+
+@dataclass(frozen=True, init=False)
+class BarrierOption(_PathPayoff):
+    """Vanilla payoff at expiry, switched on (KnockIn) or off (KnockOut) when the spot is at or beyond `barrier` on a
+    monitoring date; otherwise `rebate`, paid at expiry."""
+    strike: float
+    barrier: float
+    expiry: int
+    call_put: Any
+    direction: Any
+    knock: Any
+    rebate: float
+    monitoring: Monitoring
+
+    def __init__(self, strike, barrier, expiry_date, call_put, direction, knock, rebate=0.0, monitoring=None):
+        self._base(strike, expiry_date, call_put, monitoring)
+        object.__setattr__(self, "barrier", barrier)
+        object.__setattr__(self, "direction", direction)
+        object.__setattr__(self, "knock", knock)
+        object.__setattr__(self, "rebate", rebate)
+
+    def abi_tuple(self):
+        up, out = isinstance(self.direction, Up), isinstance(self.knock, KnockOut)
+        kind = {(True, True): abi.HH_PD_UP_OUT, (True, False): abi.HH_PD_UP_IN,
+                (False, True): abi.HH_PD_DOWN_OUT, (False, False): abi.HH_PD_DOWN_IN}[(up, out)]
+        return (kind, self.strike, self.call_put(), self.barrier, self.rebate)
+
+
+@dataclass(frozen=True, init=False)
+class DigitalOption(_PathPayoff):
+    """CashOrNothing(amount) or AssetOrNothing() if cp (S_T - K) > 0."""
+    strike: float
+    expiry: int
+    call_put: Any
+    payout: Any
+    monitoring: Monitoring
+
+    def __init__(self, strike, expiry_date, call_put, payout=None, monitoring=None):
+        self._base(strike, expiry_date, call_put, monitoring)
+        object.__setattr__(self, "payout", payout or CashOrNothing(1.0))
+
+    def abi_tuple(self):
+        if isinstance(self.payout, AssetOrNothing):
+            return (abi.HH_PD_DIGITAL_ASSET, self.strike, self.call_put(), 0.0, 0.0)
+        return (abi.HH_PD_DIGITAL_CASH, self.strike, self.call_put(), 0.0, self.payout.amount)
+
+
+def _abi_tuple(p):
+    if isinstance(p, api.VanillaOption):
+        if not isinstance(p.exercise_style, api.European) or not isinstance(p.underlying, api.Spot):
+            raise TypeError("path-dependent baskets take European options on the Spot underlying")
+        return (abi.HH_PD_VANILLA, p.strike, p.call_put(), 0.0, 0.0)
+    return p.abi_tuple()
+
+
+def is_path_payoff(p) -> bool:
+    return isinstance(p, _PathPayoff)
+
+
+def solve_path_dependent(payoffs: Sequence, market_inputs, method, *, engine=None, shard=None, group=None):
+    """Prices `payoffs` (same expiry, same monitoring) on ONE set of trajectories; returns (price, std_error) per
+    payoff and the launch statistics. Multi-GPU: each rank simulates its block of trajectories and the (sum, sumsq, n)
+    triples are sum-reduced, as in the European solve."""
+    p0 = payoffs[0]
+    every = getattr(p0, "monitoring", Monitoring()).every
+    for p in payoffs:
+        if p.expiry != p0.expiry:
+            raise ValueError("payoffs priced on common trajectories must share the expiry")
+        if getattr(p, "monitoring", Monitoring(every)).every != every:
+            raise ValueError("payoffs priced on common trajectories must share the monitoring dates")
+    eng = engine or api.default_engine()
+    shard, reduce = api._shard_and_reduce(shard, group)
+    prob0 = api.PricingProblem(p0, market_inputs)
+    mdl = api._model_of(prob0, method)
+    sim = api._sim_of(method, api._scheme_of(method, for_lsm=True), shard)  # stepping form of BlackScholesExact
+    discount = api.df(market_inputs.rate, p0.expiry)
+    results, _ = eng.mc_path_dependent(mdl, sim, [_abi_tuple(p) for p in payoffs], discount, every)
+    sums = np.array([[r.sum, r.sumsq, float(r.n)] for r in results], dtype=np.float64)
+    if reduce is not None:
+        sums = reduce(sums)
+    out = []
+    for s, q, n in sums:
+        mean = s / n
+        var = max((q - n * mean * mean) / (n - 1), 0.0) if n > 1 else 0.0
+        out.append((discount * mean, discount * math.sqrt(var / n)))
+    stats = {"kernel_ms": results[0].kernel_ms, "n_nonfinite": results[0].n_nonfinite, "n_local": sim.n_paths,
+             "n_total": int(sums[0][2])}
+    return out, stats

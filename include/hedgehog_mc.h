@@ -216,6 +216,41 @@ int hh_mc_european_tangent_sums(hh_ctx *ctx, const hh_model *model, const hh_tan
                                 int ntangents, const hh_sim *sim, const hh_payoff *payoffs,
                                 int npayoffs, double *sums, double *kernel_ms);
 
+/* ---- Path-dependent payoffs on the simulation grid ------------------------------
+ * Not in the reference yet: its roadmap lists them as Phase 5 (derivatives_pricing_roadmap.md:73-80: arithmetic /
+ * geometric Asian, cash- and asset-or-nothing digitals, discretely monitored up/down knock-in/out barriers, "Monitoring /
+ * Averaging modifiers"). The trajectories are those of hh_mc_european (same schemes, RNG streams, antithetic pairing
+ * and reduce_payoffs averaging, montecarlo.jl:430-432); the kernel keeps running statistics per trajectory in registers.
+ * Monitoring dates: steps monitor_every, 2 monitor_every, ..., n_steps (t = 0 excluded, expiry included); n_steps must
+ * be a multiple of monitor_every. */
+#define HH_PD_VANILLA 0        /* max(cp (S_T - K), 0) */
+#define HH_PD_ASIAN_ARITH 1    /* max(cp (A - K), 0), A = mean of S over the monitoring dates */
+#define HH_PD_ASIAN_GEOM 2     /* max(cp (G - K), 0), G = exp(mean of log S) */
+#define HH_PD_UP_OUT 3         /* vanilla unless max S >= barrier on a monitoring date, then `amount` (rebate at expiry) */
+#define HH_PD_UP_IN 4          /* vanilla if max S >= barrier on a monitoring date, else `amount` */
+#define HH_PD_DOWN_OUT 5       /* vanilla unless min S <= barrier, then `amount` */
+#define HH_PD_DOWN_IN 6        /* vanilla if min S <= barrier, else `amount` */
+#define HH_PD_DIGITAL_CASH 7   /* `amount` if cp (S_T - K) > 0 */
+#define HH_PD_DIGITAL_ASSET 8  /* S_T if cp (S_T - K) > 0 */
+#define HH_PD_NKINDS 9
+#define HH_PD_NSTATS 5         /* per column: S_T, A, G, max S, min S over the monitoring dates */
+typedef struct hh_path_payoff {
+  int32_t kind; /* HH_PD_* */
+  int32_t reserved;
+  double strike;
+  double cp;      /* +1 call, -1 put */
+  double barrier; /* barriers only */
+  double amount;  /* barrier rebate (paid at expiry) or digital cash amount */
+} hh_path_payoff;
+
+/* model/sim as in hh_mc_european; schemes HH_SCHEME_EM (both models) and HH_SCHEME_EXACT_STEPS (GBM, advanced in log
+ * space: the same law and the same values to rounding). npayoffs in [1, 256].
+ * path_stats: nullable host buffer, HH_PD_NSTATS x ncols row-major (ncols = n_paths, doubled [plus | minus] when
+ * antithetic), path_stats_len its length in doubles. */
+int hh_mc_path_dependent(hh_ctx *ctx, const hh_model *model, const hh_sim *sim, int monitor_every,
+                         const hh_path_payoff *payoffs, int npayoffs, double discount, hh_result *results,
+                         double *path_stats, size_t path_stats_len);
+
 /* ---- American LSM: solve(::PricingProblem{American}, ::LSM), least_squares_montecarlo.jl:99-136 --
  * stop_idx/stop_val: nullable, stopping_info[(tau, value)] per column (:112,:163-164);
  * spot_paths: nullable, (n_steps+1) x ncols, column-major like the reference Matrix (:50);

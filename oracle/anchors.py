@@ -99,3 +99,45 @@ def carr_madan_price(cf, S0, K, r, T, alpha=1.0, bound=32.0, cp=1.0):
 
 def heston_price(S0, K, r, T, V0, kappa, theta, sigma, rho, alpha=1.0, bound=32.0, cp=1.0):
     return carr_madan_price(lambda u: heston_cf(u, S0, V0, kappa, theta, sigma, rho, r, T), S0, K, r, T, alpha, bound, cp)
+
+
+# ---- closed forms for the path-dependent payoffs (roadmap Phase 5, derivatives_pricing_roadmap.md:73-80) --------------
+def geometric_asian_price(S, K, r, sigma, T, m, cp=1.0):
+    """Discretely monitored geometric-average option under Black-Scholes, dates t_i = i T / m, i = 1..m:
+    log G is normal with mean log S + (r - sigma^2/2) T (m+1)/(2m) and variance sigma^2 T (m+1)(2m+1)/(6 m^2)."""
+    mu = math.log(S) + (r - 0.5 * sigma ** 2) * T * (m + 1) / (2 * m)
+    v = sigma ** 2 * T * (m + 1) * (2 * m + 1) / (6 * m * m)
+    sv = math.sqrt(v)
+    d2 = (mu - math.log(K)) / sv
+    d1 = d2 + sv
+    return math.exp(-r * T) * cp * (math.exp(mu + 0.5 * v) * norm.cdf(cp * d1) - K * norm.cdf(cp * d2))
+
+
+def digital_price(S, K, r, sigma, T, cp=1.0, cash=None):
+    """cash-or-nothing (cash = amount) or asset-or-nothing (cash = None) under Black-Scholes."""
+    sq = sigma * math.sqrt(T)
+    d1 = (math.log(S / K) + (r + 0.5 * sigma ** 2) * T) / sq
+    d2 = d1 - sq
+    if cash is None:
+        return S * norm.cdf(cp * d1)
+    return cash * math.exp(-r * T) * norm.cdf(cp * d2)
+
+
+def up_and_in_call_price(S, K, H, r, sigma, T):
+    """Continuously monitored up-and-in call, H > max(S, K) (reflection principle; Hull, Options Futures and Other
+    Derivatives, 'Barrier options'), no rebate."""
+    sq = sigma * math.sqrt(T)
+    lam = (r + 0.5 * sigma ** 2) / sigma ** 2
+    x1 = math.log(S / H) / sq + lam * sq
+    y = math.log(H * H / (S * K)) / sq + lam * sq
+    y1 = math.log(H / S) / sq + lam * sq
+    D = math.exp(-r * T)
+    return (S * norm.cdf(x1) - K * D * norm.cdf(x1 - sq)
+            - S * (H / S) ** (2 * lam) * (norm.cdf(-y) - norm.cdf(-y1))
+            + K * D * (H / S) ** (2 * lam - 2) * (norm.cdf(-y + sq) - norm.cdf(-y1 + sq)))
+
+
+def discrete_barrier_shift(H, sigma, T, m, up=True):
+    """Broadie-Glasserman-Kou continuity correction: a barrier monitored at m dates prices like a continuous one
+    moved away from the spot by exp(+-0.5826 sigma sqrt(T/m))."""
+    return H * math.exp((1.0 if up else -1.0) * 0.5826 * sigma * math.sqrt(T / m))

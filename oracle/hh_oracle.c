@@ -382,6 +382,115 @@ int hho_mc_european(const hh_model *model, const hh_sim *sim, const hh_payoff *p
   return HH_OK;
 }
 
+/* ------------------------------------------------------------------------------------------
+ * Path-dependent payoffs on the simulation grid (include/hedgehog_mc.h hh_mc_path_dependent; the reference's
+ * roadmap Phase 5, derivatives_pricing_roadmap.md:73-80 — not implemented there yet). The statistics are taken in
+ * S-SPACE from the saved spots of each trajectory (the grid the LSM extension fills), independently of the
+ * kernel's log-space bookkeeping: A = mean S, G = exp(mean log S), max S, min S over the monitoring dates.
+ * ---------------------------------------------------------------------------------------- */
+static double pd_payoff_of(const hh_path_payoff *c, const double *st) {
+  const double ST = st[0], A = st[1], G = st[2], mx = st[3], mn = st[4];
+  const double vanilla = fmax(c->cp * (ST - c->strike), 0.0);
+  switch (c->kind) {
+    case HH_PD_ASIAN_ARITH: return fmax(c->cp * (A - c->strike), 0.0);
+    case HH_PD_ASIAN_GEOM: return fmax(c->cp * (G - c->strike), 0.0);
+    case HH_PD_UP_OUT: return mx >= c->barrier ? c->amount : vanilla;
+    case HH_PD_UP_IN: return mx >= c->barrier ? vanilla : c->amount;
+    case HH_PD_DOWN_OUT: return mn <= c->barrier ? c->amount : vanilla;
+    case HH_PD_DOWN_IN: return mn <= c->barrier ? vanilla : c->amount;
+    case HH_PD_DIGITAL_CASH: return c->cp * (ST - c->strike) > 0.0 ? c->amount : 0.0;
+    case HH_PD_DIGITAL_ASSET: return c->cp * (ST - c->strike) > 0.0 ? ST : 0.0;
+    default: return vanilla;
+  }
+}
+
+static void pd_stats_of(const double *spots, int M, int every, double *st) {
+  double sum = 0.0, sumlog = 0.0, mx = -INFINITY, mn = INFINITY;
+  int m = 0;
+  for (int t = every; t <= M; t += every, ++m) {
+    sum += spots[t];
+    sumlog += log(spots[t]);
+    mx = fmax(mx, spots[t]);
+    mn = fmin(mn, spots[t]);
+  }
+  st[0] = spots[M];
+  st[1] = sum / m;
+  st[2] = exp(sumlog / m);
+  st[3] = mx;
+  st[4] = mn;
+}
+
+int hho_mc_path_dependent(const hh_model *model, const hh_sim *sim, int monitor_every, const hh_path_payoff *payoffs,
+                          int npayoffs, double discount, hh_result *results, double *path_stats) {
+  int rc = check_args(model, sim);
+  if (rc) return rc;
+  if (npayoffs < 1 || !payoffs || !results) return HH_ERR_ARG;
+  if (!(sim->scheme == HH_SCHEME_EM || (model->kind == HH_MODEL_GBM && sim->scheme == HH_SCHEME_EXACT_STEPS)))
+    return HH_ERR_UNSUPPORTED;
+  if (sim->precision != HH_PREC_F64) return HH_ERR_UNSUPPORTED;
+  const int M = sim->n_steps;
+  if (monitor_every < 1 || M % monitor_every != 0) return HH_ERR_ARG;
+  for (int k = 0; k < npayoffs; ++k)
+    if (payoffs[k].kind < 0 || payoffs[k].kind >= HH_PD_NKINDS) return HH_ERR_ARG;
+  const int64_t N = sim->n_paths;
+  const int anti = sim->vr == HH_VR_ANTITHETIC;
+  const int64_t ncols = anti ? 2 * N : N;
+  long double *sum = calloc((size_t)npayoffs, sizeof(long double));
+  long double *sumsq = calloc((size_t)npayoffs, sizeof(long double));
+  int64_t nonfinite = 0;
+#pragma omp parallel
+  {
+    long double *ls = calloc((size_t)npayoffs, sizeof(long double));
+    long double *lq = calloc((size_t)npayoffs, sizeof(long double));
+    double *gp = malloc(sizeof(double) * (size_t)(M + 1) * 2);
+    double *gm = gp + (M + 1);
+    int64_t lnf = 0;
+#pragma omp for schedule(static)
+    for (int64_t i = 0; i < N; ++i) {
+      simulate_one(model, sim, i, gp, anti ? gm : NULL, 1);
+      double sp[HH_PD_NSTATS], sm[HH_PD_NSTATS];
+      pd_stats_of(gp, M, monitor_every, sp);
+      if (anti) pd_stats_of(gm, M, monitor_every, sm);
+      if (!isfinite(sp[0]) || (anti && !isfinite(sm[0]))) lnf++;
+      if (path_stats)
+        for (int q = 0; q < HH_PD_NSTATS; ++q) {
+          path_stats[(size_t)q * ncols + i] = sp[q];
+          if (anti) path_stats[(size_t)q * ncols + N + i] = sm[q];
+        }
+      for (int k = 0; k < npayoffs; ++k) {
+        double p = pd_payoff_of(&payoffs[k], sp);
+        if (anti) p = (p + pd_payoff_of(&payoffs[k], sm)) / 2; /* reduce_payoffs montecarlo.jl:430-432 */
+        ls[k] += p;
+        lq[k] += (long double)p * p;
+      }
+    }
+#pragma omp critical
+    {
+      for (int k = 0; k < npayoffs; ++k) { sum[k] += ls[k]; sumsq[k] += lq[k]; }
+      nonfinite += lnf;
+    }
+    free(ls);
+    free(lq);
+    free(gp);
+  }
+  for (int k = 0; k < npayoffs; ++k) {
+    hh_result *r = &results[k];
+    memset(r, 0, sizeof(*r));
+    r->sum = (double)sum[k];
+    r->sumsq = (double)sumsq[k];
+    r->n = N;
+    long double mean = sum[k] / N;
+    r->price = (double)(discount * mean);
+    long double var = N > 1 ? (sumsq[k] - N * mean * mean) / (N - 1) : 0;
+    if (var < 0) var = 0;
+    r->std_error = (double)(discount * sqrtl(var / N));
+    r->n_nonfinite = nonfinite;
+  }
+  free(sum);
+  free(sumsq);
+  return HH_OK;
+}
+
 int hho_heston_em_terminal_v(const hh_model *model, const hh_sim *sim, double *v_terminal) {
   int rc = check_args(model, sim);
   if (rc) return rc;

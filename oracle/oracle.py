@@ -46,6 +46,8 @@ def lib():
         L.hho_set_threads.argtypes = [C.c_int]
         L.hho_mc_european.argtypes = [C.POINTER(abi.hh_model), C.POINTER(abi.hh_sim), C.POINTER(abi.hh_payoff), C.c_int,
                                       C.c_double, C.POINTER(abi.hh_result), dp, C.c_size_t]
+        L.hho_mc_path_dependent.argtypes = [C.POINTER(abi.hh_model), C.POINTER(abi.hh_sim), C.c_int,
+                                            C.POINTER(abi.hh_path_payoff), C.c_int, C.c_double, C.POINTER(abi.hh_result), dp]
         L.hho_heston_em_terminal_v.argtypes = [C.POINTER(abi.hh_model), C.POINTER(abi.hh_sim), dp]
         L.hho_mc_european_tangent_sums.argtypes = [C.POINTER(abi.hh_model), C.POINTER(abi.hh_tangent), C.c_int,
                                                    C.POINTER(abi.hh_sim), C.POINTER(abi.hh_payoff), C.c_int, dp]
@@ -114,6 +116,17 @@ class OracleEngine:
         _raise(self.lib.hho_mc_european(C.byref(model), C.byref(s), pa, len(payoffs), float(discount), res, tptr, tlen),
                "mc_european")
         return list(res), terminal
+
+    def mc_path_dependent(self, model, sim: SimSpec, payoffs, discount, monitor_every=1, want_stats=False):
+        from hedgehog_jl_b200.engine import path_payoff_array
+        s, keep = sim.to_c(hh.load_library())
+        pa = path_payoff_array(payoffs)
+        res = (abi.hh_result * len(payoffs))()
+        ncols = sim.n_paths * (2 if sim.vr == abi.HH_VR_ANTITHETIC else 1)
+        stats = np.empty((abi.HH_PD_NSTATS, ncols)) if want_stats else None
+        _raise(self.lib.hho_mc_path_dependent(C.byref(model), C.byref(s), int(monitor_every), pa, len(payoffs),
+                                              float(discount), res, _dp(stats) if want_stats else None), "mc_path_dependent")
+        return list(res), stats
 
     def heston_terminal_v(self, model, sim: SimSpec):
         s, keep = sim.to_c(hh.load_library())

@@ -37,7 +37,7 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layout_matches_the_c_compiler(tmp_path):
     structs = {"hh_model": abi.hh_model, "hh_bk_config": abi.hh_bk_config, "hh_sim": abi.hh_sim,
                "hh_payoff": abi.hh_payoff, "hh_result": abi.hh_result, "hh_tangent": abi.hh_tangent,
-               "hh_lsm_result": abi.hh_lsm_result, "hh_comm": abi.hh_comm}
+               "hh_lsm_result": abi.hh_lsm_result, "hh_comm": abi.hh_comm, "hh_path_payoff": abi.hh_path_payoff}
     lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{HEADER}"', "int main(void){"]
     for name, st in structs.items():
         lines.append(f'printf("{name} %zu\\n", sizeof({name}));')
