@@ -55,6 +55,14 @@ def main():
     g1 = hh.solve(hh.BatchGreekProblem(prob, lenses), hh.ForwardAD(), method, engine=eng, shard=(0, 1))
     res["greeks"] = {"sharded": [float(g[l]) for l in lenses], "single": [float(g1[l]) for l in lenses]}
 
+    # path-dependent payoffs on common trajectories: the same shard + [sum, sumsq, n] reduction
+    exp = dt.date(2020, 12, 31)
+    pd_basket = hh.BasketPricingProblem([hh.AsianOption(100.0, exp, hh.Call(), monitoring=hh.Monitoring(4)),
+                                         hh.BarrierOption(100.0, 120.0, exp, hh.Call(), hh.Up(), hh.KnockOut(), monitoring=hh.Monitoring(4)),
+                                         hh.DigitalOption(95.0, exp, hh.Put(), monitoring=hh.Monitoring(4))], market)
+    res["pathdep"] = {"sharded": [[s.price, s.std_error] for s in hh.solve(pd_basket, method, engine=eng)],
+                      "single": [[s.price, s.std_error] for s in hh.solve(pd_basket, method, engine=eng, shard=(0, 1))]}
+
     # the hh_comm callback the LSM driver calls between pass and fit: in-place sum-allreduce of a buffer
     comm, keep = hd.make_comm((rank, world))
     buf = np.arange(12, dtype=np.float64) * (rank + 1)

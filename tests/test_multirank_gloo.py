@@ -57,3 +57,9 @@ def test_lsm_comm_callback_sums_in_place(ranks):
     for i, r in enumerate(ranks):
         assert r["comm"] == {"rc": 0, "buf": want, "rank": i, "world": 2}
         assert r["allreduce"] == [[3.0, 4.0], [6.0, 4.0]]
+
+
+def test_path_dependent_payoffs_reduce_across_ranks(ranks):
+    assert ranks[0]["pathdep"]["sharded"] == ranks[1]["pathdep"]["sharded"]
+    for r in ranks:
+        np.testing.assert_allclose(r["pathdep"]["sharded"], r["pathdep"]["single"], rtol=1e-10)
