@@ -129,17 +129,19 @@ __global__ void __launch_bounds__(kLsmPathThreads) lsm_paths_kernel(const LsmPat
 struct LsmLogArgs {
   LsmPathArgs b;
   PathParams<double> p;
+  HestonFolded f;  // host-folded step constants (native-RNG mode)
   int split;
 };
 
-constexpr int kLsmLogSmem = kLogRepBytes + kTrigRepBytes + kExp2Bytes;
+constexpr int kLsmLogSmem = kLogRepBytes + kTrigRepBytes + kExpFullBytes + kExp2Bytes;
 
 template <bool HESTON, bool ANTI, bool PARITY, bool UKEY>
 __global__ void __launch_bounds__(kLsmPathThreads) lsm_logspace_paths_kernel(const LsmLogArgs a) {
   extern __shared__ __align__(16) unsigned char dsm[];
   char *s_log = reinterpret_cast<char *>(dsm);
   char *s_trig = s_log + kLogRepBytes;
-  double *s_e2 = reinterpret_cast<double *>(s_trig + kTrigRepBytes);
+  double *s_expf = reinterpret_cast<double *>(s_trig + kTrigRepBytes);
+  double *s_e2 = s_expf + kExpFullN;
   const int tid = threadIdx.x;
   if (!PARITY) {
     for (int e = tid; e < tables::kLog2Buckets * kRep; e += kLsmPathThreads)
@@ -147,11 +149,14 @@ __global__ void __launch_bounds__(kLsmPathThreads) lsm_logspace_paths_kernel(con
     for (int e = tid; e < tables::kTrigN * kRep; e += kLsmPathThreads)
       reinterpret_cast<double2 *>(s_trig)[e] = g_fast_tables2.trig_tab[e / kRep];
     for (int e = tid; e < tables::kExp2N; e += kLsmPathThreads) s_e2[e] = g_fast_tables2.exp_tab[e];
+    fill_exp_full_table(s_expf);
   }
   __syncthreads();
   const char *log_lane = s_log + (tid & (kRep - 1)) * 16;
   const char *trig_lane = s_trig + (tid & (kRep - 1)) * 16;
   const char *exp_biased = reinterpret_cast<const char *>(s_e2) - tables::kExp2Bias * 8;
+  // spots from log-spots: the table-driven exp with the in-kernel RNG, libm's in parity mode
+  auto spot_of = [&](double x) { return PARITY ? exp(x) : fast_exp_full(s_expf, x); };
   const LsmPathArgs &b = a.b;
   const PathParams<double> &p = a.p;
   const bool split = a.split != 0;
@@ -182,14 +187,20 @@ __global__ void __launch_bounds__(kLsmPathThreads) lsm_logspace_paths_kernel(con
           fast_normal_pair_v2(log_lane, exp_biased, trig_lane, w.x, w.y, w.z, w.w, b.one_hi, b.magic_hi, z1, z2);
         }
         const double dW1 = fma(p.a12, z2, p.a11 * z1);
-        const double dW2 = fma(p.a22, z2, p.a21 * z1);
-        heston_em_step<double>(p, split, xp, vp, dW1, dW2);
+        if (PARITY) {
+          const double dW2 = fma(p.a22, z2, p.a21 * z1);
+          heston_em_step<double>(p, split, xp, vp, dW1, dW2);
+          if (ANTI) heston_em_step<double>(p, split, xm, vm, -dW1, -dW2);  // NoiseGrid(t, -W), montecarlo.jl:258
+        } else {  // host-folded constants, xi folded into dW2, branch-free clamps and sqrt (hh_paths.cuh)
+          const double xdW2 = fma(a.f.b22, z2, a.f.b21 * z1);
+          heston_em_step_fast(a.f, split, xp, vp, dW1, xdW2);
+          if (ANTI) heston_em_step_fast(a.f, split, xm, vm, -dW1, -xdW2);
+        }
         gp += b.stride;
-        *gp = exp(xp);
-        if (ANTI) {  // NoiseGrid(t, -W), montecarlo.jl:258
-          heston_em_step<double>(p, split, xm, vm, -dW1, -dW2);
+        *gp = spot_of(xp);
+        if (ANTI) {
           gm += b.stride;
-          *gm = exp(xm);
+          *gm = spot_of(xm);
         }
       }
     } else {
@@ -209,11 +220,11 @@ __global__ void __launch_bounds__(kLsmPathThreads) lsm_logspace_paths_kernel(con
             const double dW = p.sqdt * (h ? zb : za);
             gbm_em_step<double>(p, xp, dW);
             gp += b.stride;
-            *gp = exp(xp);
+            *gp = spot_of(xp);
             if (ANTI) {
               gbm_em_step<double>(p, xm, -dW);
               gm += b.stride;
-              *gm = exp(xm);
+              *gm = spot_of(xm);
             }
           }
         }
@@ -1279,6 +1290,12 @@ int lsm_american(hh_ctx *ctx, const hh_model *m, const hh_sim *s, const hh_payof
       p.a12 = sqdt * m->m12;
       p.a21 = sqdt * m->m21;
       p.a22 = sqdt * m->m22;
+      la.f.rdt = m->r * dt;
+      la.f.neg_half_dt = -0.5 * dt;
+      la.f.neg_kdt = -(m->kappa * dt);
+      la.f.ktdt = m->kappa * m->theta * dt;
+      la.f.b21 = m->xi * p.a21;
+      la.f.b22 = m->xi * p.a22;
     } else {
       p.sigma = m->sigma;
       p.dt_drift = dt * (m->r - 0.5 * (m->sigma * m->sigma));

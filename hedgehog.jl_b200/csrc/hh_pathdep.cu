@@ -13,6 +13,7 @@
 // Cost: the log-space step plus 4 FP64 per monitoring date (sum, max, min) and one exp per monitoring date when an
 // arithmetic average is requested (template switch ARITH: barriers, digitals and geometric Asians never leave log space).
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -42,6 +43,7 @@ struct PdArgs {
   int npay, kp_log2, n_steps, monitor_every, split;
   double inv_m;      // 1 / number of monitoring dates
   PathParams<double> p;
+  HestonFolded f;  // folded step constants of the native-RNG Heston kernel
   PhiloxRoundKeys rk;
   uint32_t one_hi, magic_hi;
 };
@@ -54,12 +56,13 @@ struct PdRunning {
     max_x = -INFINITY;
     min_x = INFINITY;
   }
-  template <bool ARITH>
-  __device__ __forceinline__ void monitor(double x) {
+  // FASTEXP: table-driven exp (hh_fastnormal.cuh fast_exp_full); the parity mode keeps libm's
+  template <bool ARITH, bool FASTEXP>
+  __device__ __forceinline__ void monitor(double x, const double *exp_tab) {
     sum_x += x;
     max_x = fmax(max_x, x);
     min_x = fmin(min_x, x);
-    if (ARITH) sum_s += exp(x);
+    if (ARITH) sum_s += FASTEXP ? fast_exp_full(exp_tab, x) : exp(x);
   }
 };
 
@@ -78,7 +81,81 @@ __device__ __forceinline__ double pd_payoff(const PdPayoff &c, double ST, double
   }
 }
 
-constexpr int kPdTableBytes = kLogRepBytes + kTrigRepBytes + kExp2Bytes;
+// Stages the five statistics of each thread's column(s) as [stat][side][thread], writes them out when requested, and
+// evaluates every contract on the staged columns: thread (k, g) = (contract, path group), as european_kernel does for a
+// strike grid. Called by all threads of the block (it synchronises).
+template <bool ANTI, bool ARITH, int THREADS>
+__device__ __forceinline__ void pd_stage_and_pay(const PdArgs &a, double *stage, int tid, int64_t i, int64_t base, double xp,
+                                                 double xm, const PdRunning &rp, const PdRunning &rm, const PdPayoff &mine,
+                                                 int k, int g, int G, double *acc) {
+  constexpr int NSIDE = ANTI ? 2 : 1;
+  const double ST = exp(xp);  // final_sample, montecarlo.jl:398
+  stage[(0 * NSIDE + 0) * THREADS + tid] = ST;
+  stage[(1 * NSIDE + 0) * THREADS + tid] = ARITH ? rp.sum_s * a.inv_m : 0.0;
+  stage[(2 * NSIDE + 0) * THREADS + tid] = exp(rp.sum_x * a.inv_m);
+  stage[(3 * NSIDE + 0) * THREADS + tid] = rp.max_x;
+  stage[(4 * NSIDE + 0) * THREADS + tid] = rp.min_x;
+  if (ANTI) {
+    const double STm = exp(xm);
+    stage[(0 * NSIDE + 1) * THREADS + tid] = STm;
+    stage[(1 * NSIDE + 1) * THREADS + tid] = ARITH ? rm.sum_s * a.inv_m : 0.0;
+    stage[(2 * NSIDE + 1) * THREADS + tid] = exp(rm.sum_x * a.inv_m);
+    stage[(3 * NSIDE + 1) * THREADS + tid] = rm.max_x;
+    stage[(4 * NSIDE + 1) * THREADS + tid] = rm.min_x;
+  }
+  if (a.stats && i < a.n) {  // S_T, A, G, max S, min S
+    const int64_t ncols = a.n * NSIDE;
+#pragma unroll
+    for (int side = 0; side < NSIDE; ++side) {
+      const int64_t col = i + side * a.n;
+#pragma unroll
+      for (int s = 0; s < kPdStats; ++s) {
+        const double v = stage[(s * NSIDE + side) * THREADS + tid];
+        a.stats[(int64_t)s * ncols + col] = s >= 3 ? exp(v) : v;
+      }
+    }
+  }
+  __syncthreads();
+  const int64_t rem = a.n - base;
+  const int nvalid = rem < THREADS ? (int)rem : THREADS;
+  if (k < a.npay) {
+    for (int j = g; j < nvalid; j += G) {
+      const double sT = stage[(0 * NSIDE + 0) * THREADS + j];
+      double pay = pd_payoff(mine, sT, stage[(1 * NSIDE + 0) * THREADS + j], stage[(2 * NSIDE + 0) * THREADS + j],
+                             stage[(3 * NSIDE + 0) * THREADS + j], stage[(4 * NSIDE + 0) * THREADS + j]);
+      bool bad = !isfinite(sT);
+      if (ANTI) {
+        const double sTm = stage[(0 * NSIDE + 1) * THREADS + j];
+        const double paym = pd_payoff(mine, sTm, stage[(1 * NSIDE + 1) * THREADS + j], stage[(2 * NSIDE + 1) * THREADS + j],
+                                      stage[(3 * NSIDE + 1) * THREADS + j], stage[(4 * NSIDE + 1) * THREADS + j]);
+        pay = 0.5 * (pay + paym);  // reduce_payoffs, montecarlo.jl:430-432
+        bad = bad || !isfinite(sTm);
+      }
+      acc[0] += pay;
+      acc[1] = fma(pay, pay, acc[1]);
+      if (k == 0 && bad) acc[2] += 1.0;
+    }
+  }
+  __syncthreads();
+}
+
+// fixed-order reduction over the path groups that share a contract (stage holds at least kPdAcc * THREADS doubles)
+template <int THREADS>
+__device__ __forceinline__ void pd_block_reduce(const PdArgs &a, double *stage, int tid, int G, const double *acc) {
+#pragma unroll
+  for (int c = 0; c < kPdAcc; ++c) stage[c * THREADS + tid] = acc[c];
+  __syncthreads();
+  if (tid < a.npay) {
+    double *out = a.partials + ((size_t)blockIdx.x * a.npay + tid) * kPdAcc;
+    for (int c = 0; c < kPdAcc; ++c) {
+      double t = 0.0;
+      for (int gg = 0; gg < G; ++gg) t += stage[c * THREADS + (gg << a.kp_log2) + tid];
+      out[c] = t;
+    }
+  }
+}
+
+constexpr int kPdTableBytes = kLogRepBytes + kTrigRepBytes + kExpFullBytes + kExp2Bytes;
 constexpr int kPdStageDoubles = kPdStats * 2 * kPdThreads;  // also holds the kPdAcc * kPdThreads of the final reduction
 constexpr int kPdSmem = ((kPdTableBytes + 15) & ~15) + kPdStageDoubles * 8;
 
@@ -87,9 +164,11 @@ __global__ void __launch_bounds__(kPdThreads, 2) pathdep_kernel(const PdArgs a) 
   extern __shared__ __align__(16) unsigned char dsm[];
   char *s_log = reinterpret_cast<char *>(dsm);
   char *s_trig = s_log + kLogRepBytes;
-  double *s_e2 = reinterpret_cast<double *>(s_trig + kTrigRepBytes);
+  double *s_expf = reinterpret_cast<double *>(s_trig + kTrigRepBytes);
+  double *s_e2 = s_expf + kExpFullN;
   double *stage = reinterpret_cast<double *>(dsm + ((kPdTableBytes + 15) & ~15));
   const int tid = threadIdx.x;
+  fill_exp_full_table(s_expf);
   if (!PARITY) {
     for (int e = tid; e < tables::kLog2Buckets * kRep; e += kPdThreads)
       reinterpret_cast<double2 *>(s_log)[e] = g_fast_tables2.log_tab[e / kRep];
@@ -150,8 +229,8 @@ __global__ void __launch_bounds__(kPdThreads, 2) pathdep_kernel(const PdArgs a) 
           if (ANTI) heston_em_step<double>(p, split, xm, vm, -dW1, -dW2);  // NoiseGrid(t, -W), montecarlo.jl:258
           if (--due == 0) {
             due = every;
-            rp.monitor<ARITH>(xp);
-            if (ANTI) rm.monitor<ARITH>(xm);
+            rp.monitor<ARITH, !PARITY>(xp, s_expf);
+            if (ANTI) rm.monitor<ARITH, !PARITY>(xm, s_expf);
           }
         }
       } else {
@@ -173,79 +252,122 @@ __global__ void __launch_bounds__(kPdThreads, 2) pathdep_kernel(const PdArgs a) 
               if (ANTI) gbm_em_step<double>(p, xm, -dW);
               if (--due == 0) {
                 due = every;
-                rp.monitor<ARITH>(xp);
-                if (ANTI) rm.monitor<ARITH>(xm);
+                rp.monitor<ARITH, !PARITY>(xp, s_expf);
+                if (ANTI) rm.monitor<ARITH, !PARITY>(xm, s_expf);
               }
             }
           }
         }
       }
     }
-    // stage the statistics of my column(s): [stat][side][thread]
-    {
-      const double ST = exp(xp);  // final_sample, montecarlo.jl:398
-      stage[(0 * 2 + 0) * kPdThreads + tid] = ST;
-      stage[(1 * 2 + 0) * kPdThreads + tid] = ARITH ? rp.sum_s * a.inv_m : 0.0;
-      stage[(2 * 2 + 0) * kPdThreads + tid] = exp(rp.sum_x * a.inv_m);
-      stage[(3 * 2 + 0) * kPdThreads + tid] = rp.max_x;
-      stage[(4 * 2 + 0) * kPdThreads + tid] = rp.min_x;
-      if (ANTI) {
-        const double STm = exp(xm);
-        stage[(0 * 2 + 1) * kPdThreads + tid] = STm;
-        stage[(1 * 2 + 1) * kPdThreads + tid] = ARITH ? rm.sum_s * a.inv_m : 0.0;
-        stage[(2 * 2 + 1) * kPdThreads + tid] = exp(rm.sum_x * a.inv_m);
-        stage[(3 * 2 + 1) * kPdThreads + tid] = rm.max_x;
-        stage[(4 * 2 + 1) * kPdThreads + tid] = rm.min_x;
-      }
-      if (a.stats && i < a.n) {  // S_T, A, G, max S, min S
-        const int64_t ncols = a.n * NSIDE;
-#pragma unroll
-        for (int side = 0; side < NSIDE; ++side) {
-          const int64_t col = i + side * a.n;
-#pragma unroll
-          for (int s = 0; s < kPdStats; ++s) {
-            const double v = stage[(s * 2 + side) * kPdThreads + tid];
-            a.stats[(int64_t)s * ncols + col] = s >= 3 ? exp(v) : v;
-          }
-        }
-      }
-    }
-    __syncthreads();
-    const int64_t rem = a.n - base;
-    const int nvalid = rem < kPdThreads ? (int)rem : kPdThreads;
-    if (k < a.npay) {
-      for (int j = g; j < nvalid; j += G) {
-        const double ST = stage[(0 * 2 + 0) * kPdThreads + j];
-        double pay = pd_payoff(mine, ST, stage[(1 * 2 + 0) * kPdThreads + j], stage[(2 * 2 + 0) * kPdThreads + j],
-                               stage[(3 * 2 + 0) * kPdThreads + j], stage[(4 * 2 + 0) * kPdThreads + j]);
-        bool bad = !isfinite(ST);
-        if (ANTI) {
-          const double STm = stage[(0 * 2 + 1) * kPdThreads + j];
-          const double paym = pd_payoff(mine, STm, stage[(1 * 2 + 1) * kPdThreads + j], stage[(2 * 2 + 1) * kPdThreads + j],
-                                        stage[(3 * 2 + 1) * kPdThreads + j], stage[(4 * 2 + 1) * kPdThreads + j]);
-          pay = 0.5 * (pay + paym);  // reduce_payoffs, montecarlo.jl:430-432
-          bad = bad || !isfinite(STm);
-        }
-        acc[0] += pay;
-        acc[1] = fma(pay, pay, acc[1]);
-        if (k == 0 && bad) acc[2] += 1.0;
-      }
-    }
-    __syncthreads();
+    pd_stage_and_pay<ANTI, ARITH, kPdThreads>(a, stage, tid, i, base, xp, xm, rp, rm, mine, k, g, G, acc);
   }
+  pd_block_reduce<kPdThreads>(a, stage, tid, G, acc);
+}
 
-  // fixed-order reduction over the path groups that share a contract
-#pragma unroll
-  for (int c = 0; c < kPdAcc; ++c) stage[c * kPdThreads + tid] = acc[c];
-  __syncthreads();
-  if (tid < a.npay) {
-    double *out = a.partials + ((size_t)blockIdx.x * a.npay + tid) * kPdAcc;
-    for (int c = 0; c < kPdAcc; ++c) {
-      double t = 0.0;
-      for (int gg = 0; gg < G; ++gg) t += stage[c * kPdThreads + (gg << a.kp_log2) + tid];
-      out[c] = t;
-    }
+// ---- LogHestonProblem with the in-kernel RNG: the step of the headline kernel (heston_fast2_kernel, hh_european.cu) ----
+// Box-Muller radius folded into the diffusion's square root, rotation folded into the Brownian factor through the phase
+// table, integer clamps, branch-free sqrt; the drift r dt stays inside the step so that the state is log S on every
+// monitoring date. Same trajectories as pathdep_kernel<true, ...> and the oracle up to rounding.
+// Shared memory: [staging | log table x8 | phase table x8 | T_j | exponent table]; THREADS = 1024 for plain runs with the
+// uniform key (<= 64 registers), 512 otherwise (antithetic pairs / per-trajectory keys need the registers).
+template <bool ANTI, int THREADS>
+__host__ __device__ constexpr int pd_fast_stage_bytes() { return kPdStats * (ANTI ? 2 : 1) * THREADS * 8; }
+template <bool ANTI, int THREADS>
+__host__ __device__ constexpr int pd_fast_smem() {
+  return pd_fast_stage_bytes<ANTI, THREADS>() + kLogRepBytes + kPhaseRepBytes + kExpFullBytes + kExp2Bytes;
+}
+
+template <bool ANTI, bool SPLIT, bool UKEY, bool ARITH, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1) pathdep_heston_fast_kernel(const PdArgs a) {
+  extern __shared__ __align__(16) unsigned char dsm[];
+  double *stage = reinterpret_cast<double *>(dsm);
+  char *s_log = reinterpret_cast<char *>(dsm) + pd_fast_stage_bytes<ANTI, THREADS>();
+  char *s_phase = s_log + kLogRepBytes;
+  double *s_expf = reinterpret_cast<double *>(s_phase + kPhaseRepBytes);
+  double *s_e2 = s_expf + kExpFullN;
+  const int tid = threadIdx.x;
+  for (int e = tid; e < tables::kLog2Buckets * kRep; e += THREADS)
+    reinterpret_cast<double2 *>(s_log)[e] = g_fast_tables2.log_tab[e / kRep];
+  for (int e = tid; e < tables::kTrigN * kRep; e += THREADS) {
+    // phase table: {P1, Q1}, {P2, Q2} per table angle (see heston_fast2_kernel)
+    const int j = e / kRep, q = e % kRep;
+    const double2 cs = g_fast_tables2.trig_tab[j];
+    double2 *dst = reinterpret_cast<double2 *>(s_phase) + (size_t)j * 2 * kRep + q;
+    dst[0] = make_double2(fma(a.p.a12, cs.y, a.p.a11 * cs.x), fma(a.p.a12, cs.x, -(a.p.a11 * cs.y)));
+    dst[kRep] = make_double2(fma(a.f.b22, cs.y, a.f.b21 * cs.x), fma(a.f.b22, cs.x, -(a.f.b21 * cs.y)));
   }
+  for (int e = tid; e < tables::kExp2N; e += THREADS) s_e2[e] = g_fast_tables2.exp_tab[e];
+  fill_exp_full_table(s_expf);
+  __syncthreads();
+  const char *log_lane = s_log + (tid & (kRep - 1)) * 16;
+  const char *phase_lane = s_phase + (tid & (kRep - 1)) * 16;
+  const char *exp_biased = reinterpret_cast<const char *>(s_e2) - tables::kExp2Bias * 8;
+
+  const int KP = 1 << a.kp_log2;
+  const int k = tid & (KP - 1);
+  const int g = tid >> a.kp_log2;
+  const int G = THREADS >> a.kp_log2;
+  PdPayoff mine;
+  mine.kind = HH_PD_VANILLA;
+  mine.strike = mine.cp = mine.log_barrier = mine.amount = 0.0;
+  if (k < a.npay) mine = a.payoffs[k];
+  double acc[kPdAcc] = {0.0, 0.0, 0.0};
+  const int M = a.n_steps;
+  const int every = a.monitor_every;
+
+  for (int64_t base = (int64_t)blockIdx.x * THREADS; base < a.n; base += (int64_t)gridDim.x * THREADS) {
+    const int64_t i = base + tid;
+    const int64_t ic = i < a.n ? i : a.n - 1;  // tail lanes repeat the last trajectory; never accumulated
+    double xp = a.p.x0, xm = a.p.x0, vp = a.p.v0, vm = a.p.v0;
+    PdRunning rp, rm;
+    rp.reset();
+    rm.reset();
+    uint32_t c0 = 0u, c1 = 0u;
+    PhiloxRoundKeys rk_own;
+    if (UKEY) {
+      const uint64_t idx = (uint64_t)(a.path_offset + ic);
+      c0 = (uint32_t)idx;
+      c1 = (uint32_t)(idx >> 32);
+    } else {
+      rk_own = philox_round_keys(a.seeds[ic]);
+    }
+    int due = every;
+#pragma unroll 1
+    for (int n = 0; n < M; ++n) {
+      const u32x4 w = philox4x32_10_rk(c0, c1, (uint32_t)n, 0u, UKEY ? a.rk : rk_own);
+      const double R2 = fast_neg2log_v2(log_lane, exp_biased, w.x, w.y, a.one_hi);
+      double sn, cs;
+      const uint32_t poff = fast_angle_v2(w.z, w.w, a.magic_hi, sn, cs);
+      const double2 pq1 = *reinterpret_cast<const double2 *>(phase_lane + poff);
+      const double2 pq2 = *reinterpret_cast<const double2 *>(phase_lane + poff + kRep * 16);
+      const double cc1 = fma(pq1.x, cs, pq1.y * sn);
+      const double cc2 = fma(pq2.x, cs, pq2.y * sn);
+      {
+        const double vplus = max0_hi(vp);
+        const double K1 = fma(a.f.neg_half_dt, vplus, xp + a.f.rdt);
+        const double K2 = fma(a.f.neg_kdt, vplus, vp + a.f.ktdt);
+        const double sr = fast_sqrt_pos5(max_tiny_hi((SPLIT ? K2 : vplus) * R2));
+        xp = fma(sr, cc1, K1);
+        vp = fma(sr, cc2, K2);
+      }
+      if (ANTI) {
+        const double vplus = max0_hi(vm);
+        const double K1 = fma(a.f.neg_half_dt, vplus, xm + a.f.rdt);
+        const double K2 = fma(a.f.neg_kdt, vplus, vm + a.f.ktdt);
+        const double sr = fast_sqrt_pos5(max_tiny_hi((SPLIT ? K2 : vplus) * R2));
+        xm = fma(-sr, cc1, K1);
+        vm = fma(-sr, cc2, K2);
+      }
+      if (--due == 0) {
+        due = every;
+        rp.monitor<ARITH, true>(xp, s_expf);
+        if (ANTI) rm.monitor<ARITH, true>(xm, s_expf);
+      }
+    }
+    pd_stage_and_pay<ANTI, ARITH, THREADS>(a, stage, tid, i, base, xp, xm, rp, rm, mine, k, g, G, acc);
+  }
+  pd_block_reduce<THREADS>(a, stage, tid, G, acc);
 }
 
 // Sum the per-block partials in a fixed order: one block per contract.
@@ -282,6 +404,41 @@ template <bool H>
 static cudaError_t pd_launch_model(const PdArgs &a, bool anti, bool arith, bool parity, bool ukey, int grid, cudaStream_t st) {
   if (anti) return arith ? pd_launch_rng<H, true, true>(a, parity, ukey, grid, st) : pd_launch_rng<H, true, false>(a, parity, ukey, grid, st);
   return arith ? pd_launch_rng<H, false, true>(a, parity, ukey, grid, st) : pd_launch_rng<H, false, false>(a, parity, ukey, grid, st);
+}
+
+template <bool A, bool SP, bool U, bool AR, int T>
+static cudaError_t pd_fast_one(const PdArgs &a, int sm_count, cudaStream_t st, int *grid_out) {
+  constexpr int smem = pd_fast_smem<A, T>();
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(pathdep_heston_fast_kernel<A, SP, U, AR, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  const int64_t batches = (a.n + T - 1) / T;
+  const int grid = (int)(batches < (int64_t)sm_count ? batches : (int64_t)sm_count);  // one block per SM
+  *grid_out = grid;
+  if (!a.partials) return cudaSuccess;  // sizing query
+  pathdep_heston_fast_kernel<A, SP, U, AR, T><<<grid, T, smem, st>>>(a);
+  return cudaGetLastError();
+}
+
+template <bool A, bool SP, bool AR>
+static cudaError_t pd_fast_key(const PdArgs &a, bool ukey, int sm_count, cudaStream_t st, int *grid_out) {
+  if (!ukey) return pd_fast_one<A, SP, false, AR, 512>(a, sm_count, st, grid_out);
+  // uniform key: 1024 threads once the job fills them, as the headline kernel does (HH_PD_THREADS=512 forces the small block)
+  static const int force_threads = getenv("HH_PD_THREADS") ? atoi(getenv("HH_PD_THREADS")) : 0;
+  return a.n >= (int64_t)sm_count * 1024 && force_threads != 512 ? pd_fast_one<A, SP, true, AR, 1024>(a, sm_count, st, grid_out)
+                                                                 : pd_fast_one<A, SP, true, AR, 512>(a, sm_count, st, grid_out);
+}
+
+static cudaError_t pd_fast(const PdArgs &a, bool anti, bool arith, bool ukey, int sm_count, cudaStream_t st, int *grid_out) {
+  const bool split = a.split != 0;
+#define HH_PD_FAST(A, SP)                                                                        \
+  (arith ? pd_fast_key<A, SP, true>(a, ukey, sm_count, st, grid_out) : pd_fast_key<A, SP, false>(a, ukey, sm_count, st, grid_out))
+  if (anti) return split ? HH_PD_FAST(true, true) : HH_PD_FAST(true, false);
+  return split ? HH_PD_FAST(false, true) : HH_PD_FAST(false, false);
+#undef HH_PD_FAST
 }
 
 int path_dependent(hh_ctx *ctx, const hh_model *m, const hh_sim *s, int monitor_every, const hh_path_payoff *payoffs,
@@ -355,6 +512,12 @@ int path_dependent(hh_ctx *ctx, const hh_model *m, const hh_sim *s, int monitor_
     p.a12 = sqdt * m->m12;
     p.a21 = sqdt * m->m21;
     p.a22 = sqdt * m->m22;
+    a.f.rdt = m->r * dt;
+    a.f.neg_half_dt = -0.5 * dt;
+    a.f.neg_kdt = -(m->kappa * dt);
+    a.f.ktdt = m->kappa * m->theta * dt;
+    a.f.b21 = m->xi * p.a21;
+    a.f.b22 = m->xi * p.a22;
   } else {
     p.sigma = m->sigma;
     p.dt_drift = dt * (m->r - 0.5 * (m->sigma * m->sigma));
@@ -378,17 +541,28 @@ int path_dependent(hh_ctx *ctx, const hh_model *m, const hh_sim *s, int monitor_
     HH_CUDA(ctx, ctx->d_terminal.ensure(sizeof(double) * (size_t)ncols * kPdStats));
     a.stats = ctx->d_terminal.as<double>();
   }
-  // one resident wave (2 blocks of 512 threads per SM with 105 KB of tables + staging each), grid-stride over batches
-  const int64_t batches = (N + kPdThreads - 1) / kPdThreads;
-  const int grid = (int)(batches < (int64_t)ctx->sm_count * 2 ? batches : (int64_t)ctx->sm_count * 2);
+  // Heston with the in-kernel RNG takes the specialised kernel (HH_PD_GENERIC=1 forces the generic one); everything else
+  // the generic kernel: one resident wave (2 blocks of 512 threads per SM), grid-stride over batches
+  static const bool force_generic = getenv("HH_PD_GENERIC") && atoi(getenv("HH_PD_GENERIC")) != 0;
+  const bool fast = heston && !parity && !force_generic;
+  const bool ukey = a.seeds == nullptr;
+  int grid = 0;
+  if (fast) {
+    HH_CUDA(ctx, pd_fast(a, anti, arith, ukey, ctx->sm_count, st, &grid));  // partials == NULL: sizing only
+  } else {
+    const int64_t batches = (N + kPdThreads - 1) / kPdThreads;
+    grid = (int)(batches < (int64_t)ctx->sm_count * 2 ? batches : (int64_t)ctx->sm_count * 2);
+  }
   HH_CUDA(ctx, ctx->d_partials.ensure(sizeof(double) * (size_t)grid * npay * kPdAcc));
   HH_CUDA(ctx, ctx->d_final.ensure(sizeof(double) * (size_t)npay * kPdAcc));
   a.partials = ctx->d_partials.as<double>();
 
   HH_CUDA(ctx, cudaEventRecord(ctx->ev0, st));
-  const bool ukey = a.seeds == nullptr;
-  HH_CUDA(ctx, heston ? pd_launch_model<true>(a, anti, arith, parity, ukey, grid, st)
-                      : pd_launch_model<false>(a, anti, arith, parity, ukey, grid, st));
+  if (fast)
+    HH_CUDA(ctx, pd_fast(a, anti, arith, ukey, ctx->sm_count, st, &grid));
+  else
+    HH_CUDA(ctx, heston ? pd_launch_model<true>(a, anti, arith, parity, ukey, grid, st)
+                        : pd_launch_model<false>(a, anti, arith, parity, ukey, grid, st));
   pathdep_finalize_kernel<<<npay, 256, 0, st>>>(a.partials, grid, npay, ctx->d_final.as<double>());
   HH_CUDA(ctx, cudaGetLastError());
   HH_CUDA(ctx, cudaEventRecord(ctx->ev1, st));
