@@ -319,8 +319,8 @@ __device__ __forceinline__ void fill_expm1_table(double2 *tab) {
 // exp(x) = 2^k T_j exp(r) with T_j = 2^(j/256) in shared memory (2 KB, filled at kernel start), |r| <= ln2/512 and
 // exp(r) by its series to r^4 (remainder r^5/120 < 3.8e-17 relative); the argument reduction uses a two-word ln2/256
 // under FMA (exact product), and 2^k is an integer add on the exponent field (T_j exp(r) is in [0.99, 2.01) and
-// |k| <= 1010, so the result stays normal). 9 FP64 instructions against ~25 for libm's exp; error <= 1.1 ulp
-// (tools/gen_tables.py --check-exp emulates it). |x| >= 700, NaN and Inf take the libm path.
+// |k| <= 1010, so the result stays normal). 9 FP64 instructions against ~25 for libm's exp; error <= 1.5 ulp
+// (tests/test_fast_exp_emulation.py emulates it). |x| >= 700, NaN and Inf take the libm path.
 constexpr int kExpFullN = 256;
 constexpr int kExpFullBytes = kExpFullN * 8;
 struct ExpFullCoefs {
