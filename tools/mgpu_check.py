@@ -3,7 +3,8 @@
    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29555 tools/mgpu_check.py
 Each rank prices its shard; rank 0 also prices the whole job alone and compares:
   European (Heston EM, f64 and f32), strike grid, batch Greeks: reduced sums equal the single-GPU sums to ~1e-13;
-  LSM (American put, GBM): the per-date regression moments are all-reduced through the hh_comm callback (NCCL on the
+  path-dependent payoffs (Asian / barrier / digital basket under Heston): the same reduction;
+  LSM (American put, GBM; and under Heston with the log-space generator): the per-date regression moments are all-reduced through the hh_comm callback (NCCL on the
   library's stream), so every rank fits the same polynomial; price equals the single-GPU price up to tie flips."""
 import datetime as dt
 import json
@@ -43,6 +44,21 @@ if rank == 0:
     g1 = hh.solve(hh.BatchGreekProblem(prob, lenses), hh.ForwardAD(), method, engine=eng, shard=(0, 1))
     out["greeks"] = {"sharded": [float(g[l]) for l in lenses], "single": [float(g1[l]) for l in lenses]}
 
+# path-dependent payoffs on common trajectories (hh_mc_path_dependent): the same shard + sum reduction as the European solve
+exp_ = dt.date(2020, 12, 31)
+mon = hh.Monitoring(4)
+pd_basket = hh.BasketPricingProblem([hh.AsianOption(100.0, exp_, hh.Call(), monitoring=mon),
+                                     hh.AsianOption(100.0, exp_, hh.Put(), hh.GeometricAverage(), mon),
+                                     hh.BarrierOption(100.0, 125.0, exp_, hh.Call(), hh.Up(), hh.KnockOut(), monitoring=mon),
+                                     hh.BarrierOption(100.0, 80.0, exp_, hh.Put(), hh.Down(), hh.KnockIn(), monitoring=mon),
+                                     hh.DigitalOption(100.0, exp_, hh.Call(), monitoring=mon)], market)
+method = hh.MonteCarlo(hh.HestonDynamics(), hh.EulerMaruyama(),
+                       hh.SimulationConfig(2_000_001, steps=64, base_seed=23, variance_reduction=hh.Antithetic()), ensemble=False)
+pd = hh.solve(pd_basket, method, engine=eng)
+if rank == 0:
+    pd1 = hh.solve(pd_basket, method, engine=eng, shard=(0, 1))
+    out["path_dependent"] = {"sharded": [s.price for s in pd], "single": [s.price for s in pd1]}
+
 put = hh.VanillaOption(100.0, dt.date(2020, 12, 31), hh.American(), hh.Put(), hh.Spot())
 bs = hh.BlackScholesInputs(dt.date(2020, 1, 1), 0.05, 100.0, 0.2)
 NL = int(os.environ.get("HH_MGPU_LSM_PATHS", "4000000"))
@@ -67,6 +83,13 @@ sol_nccl, wall_nccl = timed_lsm("nccl")          # hh_comm callback -> stream-or
 from hedgehog_jl_b200 import distributed as hd
 hd.connect_peers(eng)                             # CUDA IPC mailboxes
 sol_peer, wall_peer = timed_lsm("peer")          # exchange inside the pass kernel's tail, no collective library
+# American put under Heston (log-space generator, spots = exp(x)) with the in-kernel peer exchange
+lsm_h = hh.LSM(hh.MonteCarlo(hh.HestonDynamics(), hh.EulerMaruyama(), hh.SimulationConfig(NL, steps=50, base_seed=777)), 3)
+sol_h = hh.solve(hh.PricingProblem(put, market), lsm_h, engine=eng, stopping_info=False)
+if rank == 0:
+    one_h = hh.solve(hh.PricingProblem(put, market), lsm_h, engine=eng, shard=(0, 1), stopping_info=False)
+    out["lsm_heston"] = {"single": one_h.price, "peer": sol_h.price, "rel": abs(sol_h.price - one_h.price) / one_h.price,
+                         "kernel_ms": sol_h.stats["kernel_ms"], "single_kernel_ms": one_h.stats["kernel_ms"]}
 if rank == 0:
     one = hh.solve(hh.PricingProblem(put, bs), lsm, engine=eng, shard=(0, 1), stopping_info=False)
     out["lsm"] = {"single": one.price, "single_kernel_ms": one.stats["kernel_ms"], "n_cols_total": sol_peer.stats["n_cols_total"],
@@ -76,7 +99,8 @@ if rank == 0:
                            "kernel_ms": sol_peer.stats["kernel_ms"], "regress_ms": sol_peer.stats["regress_ms"]}}
     print(json.dumps(out))
     ok = (out["european_f64"]["rel"] < 1e-12 and out["european_f32"]["rel"] < 1e-12 and out["lsm"]["nccl"]["rel"] < 1e-6
-          and out["lsm"]["peer"]["rel"] < 1e-6
+          and out["lsm"]["peer"]["rel"] < 1e-6 and out["lsm_heston"]["rel"] < 1e-6
+          and all(abs(a - b) <= 1e-11 * max(1.0, abs(b)) for a, b in zip(out["path_dependent"]["sharded"], out["path_dependent"]["single"]))
           and all(abs(a - b) <= 1e-10 * max(1.0, abs(b)) for a, b in zip(out["greeks"]["sharded"], out["greeks"]["single"])))
     print("MGPU CHECK", "OK" if ok else "FAILED")
 eng.peer_disconnect()
