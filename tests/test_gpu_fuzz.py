@@ -118,3 +118,35 @@ def test_lsm_on_random_contracts(cuda, oracle, seed):
     assert flips <= max(3, 3e-4 * len(to)), (flips, len(to))
     assert abs(og.price - oo.price) <= (1e-9 if flips == 0 else 2e-5) * max(abs(oo.price), 1e-3), (og.price, oo.price, flips)
     assert og.n_dates_skipped == oo.n_dates_skipped
+
+
+@pytest.mark.parametrize("seed", range(20))
+def test_path_dependent_kernels_on_random_models(cuda, oracle, seed):
+    """The specialised path-dependent Heston kernel (folded step, table-driven exp) and the generic one (log-GBM) on
+    harsh random models: per-column statistics agree in log space (quantile bound + looser worst-path bound, as above),
+    non-finite columns coincide, and the sums of the continuous payoffs agree."""
+    rng = np.random.default_rng(3000 + seed)
+    heston = bool(seed % 2 == 0)
+    m = _random_heston(rng) if heston else gbm_model(S0=float(10 ** rng.uniform(-3, 5)), r=float(rng.uniform(-0.05, 0.3)),
+                                                     sigma=float(rng.uniform(0.0, 2.0)), T=float(rng.uniform(0.02, 10.0)))
+    every = int(rng.choice([1, 2, 5]))
+    steps = every * int(rng.integers(1, 20))
+    anti = int(rng.integers(0, 2))
+    n = int(rng.integers(1, 3000))
+    kw = dict(base_seed=int(rng.integers(0, 2 ** 62)), path_offset=int(rng.integers(0, 2 ** 40)))
+    if seed % 5 == 0:
+        kw = dict(seeds=rng.integers(0, 2 ** 63, size=n, dtype=np.uint64))
+    sim = SimSpec(n_paths=n, n_steps=steps, scheme=abi.HH_SCHEME_EM, vr=anti, **kw)
+    pays = [(abi.HH_PD_ASIAN_ARITH, m.S0, 1.0, 0.0, 0.0), (abi.HH_PD_ASIAN_GEOM, m.S0 * 1.1, -1.0, 0.0, 0.0),
+            (abi.HH_PD_UP_OUT, m.S0, 1.0, m.S0 * 1.5, 0.0), (abi.HH_PD_DOWN_IN, m.S0, -1.0, m.S0 * 0.7, 0.0)]
+    rg, sg = cuda.mc_path_dependent(m, sim, pays, 1.0, every, want_stats=True)
+    ro, so = oracle.mc_path_dependent(m, sim, pays, 1.0, every, want_stats=True)
+    fin = np.isfinite(so) & (so > 0)
+    assert np.array_equal(np.isfinite(sg) & (sg > 0), fin)
+    dlog = np.abs(np.log(sg[fin]) - np.log(so[fin]))
+    assert np.quantile(dlog, 0.99) < 1e-10, np.quantile(dlog, 0.99)
+    assert dlog.max() < 1e-6, dlog.max()
+    if fin.all():
+        for g, o in zip(rg[:2], ro[:2]):   # continuous payoffs: no decision to flip
+            assert g.sum == pytest.approx(o.sum, rel=1e-6, abs=1e-6 * m.S0)
+        assert rg[0].n_nonfinite == 0
