@@ -21,8 +21,12 @@
 
 #ifdef __CUDACC__
 #define HH_HD __host__ __device__ __forceinline__
+// One copy per kernel instead of one per call site: the Broadie-Kaya kernel inlined to 16 000 instructions (256 KB), and
+// ncu showed instruction fetch ("no_instruction") as its first stall reason, ahead of every data dependency.
+#define HH_HD_OUTLINE inline __host__ __device__ __noinline__
 #else
 #define HH_HD inline
+#define HH_HD_OUTLINE inline
 #endif
 
 namespace hh {
@@ -44,7 +48,7 @@ HH_HD cplx operator-(double s, cplx a) { return cplx{s - a.re, -a.im}; }
 HH_HD cplx conj(cplx a) { return cplx{a.re, -a.im}; }
 HH_HD double cabs2(cplx a) { return a.re * a.re + a.im * a.im; }
 HH_HD double cabs(cplx a) { return sqrt(a.re * a.re + a.im * a.im); }  // magnitudes here are far from over/underflow
-HH_HD double carg(cplx a) { return atan2(a.im, a.re); }
+HH_HD_OUTLINE double carg(cplx a) { return atan2(a.im, a.re); }
 // 1 / x to ~1 ulp for normal-range x: on the device MUFU.RCP64H + two Newton steps instead of the IEEE division
 // sequence (the Bessel series and the complex divisions below are dependent chains of them)
 HH_HD double rcp_fast(double x) {
@@ -74,7 +78,7 @@ HH_HD cplx operator/(cplx a, double s) {
   const double is = rcp_fast(s);
   return cplx{a.re * is, a.im * is};
 }
-HH_HD cplx cexp_(cplx a) {
+HH_HD_OUTLINE cplx cexp_(cplx a) {
   const double e = exp(a.re);
   double s, c;
   sincos(a.im, &s, &c);
@@ -177,7 +181,7 @@ HH_HD cplx log_besseli_asymptotic(double nu, cplx w) {
 
 // ---- continued fractions + Wronskian: 2 <= |w|, Re w >= 0, order xnu >= 0 ------------------------------------------
 // Returns log I_xnu(w); if dlog is non-null also I'_xnu / I_xnu.
-HH_HD cplx log_besseli_cf(double xnu, cplx x, cplx *ratio_deriv) {
+HH_HD_OUTLINE cplx log_besseli_cf(double xnu, cplx x, cplx *ratio_deriv) {
   const double EPS = 1e-16, FPMIN = 1e-200;
   const int nl = (int)(xnu + 0.5);
   const double xmu = xnu - (double)nl, xmu2 = xmu * xmu;
@@ -262,7 +266,7 @@ inline BesselOrder make_bessel_order(double nu) {
 }
 
 // log I_nu(z), any complex z != 0. The imaginary part is a valid argument of I_nu(z) (branch unspecified).
-HH_HD cplx log_besseli(const BesselOrder &o, cplx z) {
+HH_HD_OUTLINE cplx log_besseli(const BesselOrder &o, cplx z) {
   const double nu = o.nu;
   cplx w = z;
   double rot = 0.0;  // I_nu(z) = e^{i rot} I_nu(w)
@@ -342,7 +346,7 @@ HH_HD BkCf bk_cf_init(const BkParams &p, double V0, double VT) {
 }
 
 // Phi(a) with the unwrapped angle of z_gamma carried in theta_prev (NaN = first evaluation), heston.jl:184-212.
-HH_HD cplx bk_chf(const BkParams &p, const BkCf &it, double a, double &theta_prev) {
+HH_HD_OUTLINE cplx bk_chf(const BkParams &p, const BkCf &it, double a, double &theta_prev) {
   const cplx g = csqrt_(cplx{p.kappa * p.kappa, -2.0 * p.xi2 * a});        // gamma            :190
   const cplx egh = cexp_((-0.5 * p.tau) * g);  // e^{-g tau / 2}
   const cplx eg = egh * egh;

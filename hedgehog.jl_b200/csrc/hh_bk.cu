@@ -20,6 +20,7 @@
 //   5. draws log S'.
 // Payoffs are then reduced from the terminal spots by hh_european.cu's terminal_payoff kernel.
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -30,6 +31,7 @@
 namespace hh {
 
 constexpr int kBkThreads = 128;
+constexpr int kBkDefaultMinb = 3;
 constexpr int kBkTable = 32;  // table entries per thread in shared memory (32 KB per block); longer series (mean 12.3 at C4) spill to the HBM slab
 
 // terminal spots -> payoff sums (hh_european.cu)
@@ -133,7 +135,7 @@ struct BkTable {
 };
 
 // F(x) - u and F'(x) for F(x) = h x / pi + sum_j c_j sin(j h x)   (cdf_from_cf, sample_from_cf.jl:75-96)
-__device__ __forceinline__ void bk_cdf(const BkTable &tb, int J, double h, double x, double &F, double &dF) {
+__device__ __noinline__ void bk_cdf(const BkTable &tb, int J, double h, double x, double &F, double &dF) {
   const double th = h * x;
   double s1, c1;
   sincos(th, &s1, &c1);
@@ -257,7 +259,10 @@ struct BkArgs {
   unsigned long long *counters;  // [0] fallbacks, [1] sum J, [2] sum root-finder evaluations, [3] transitions, [4] unbracketed accepted
 };
 
-__global__ void __launch_bounds__(kBkThreads, 3) bk_paths_kernel(const BkArgs a) {
+// MINB = resident blocks per SM the register allocation is bounded for (3: 168 registers; 6: 85). The kernel is
+// latency-bound (issue slots 30 % busy at 12 warps per SM, ncu), so the bound is chosen by measurement: HH_BK_MINB.
+template <int MINB>
+__global__ void __launch_bounds__(kBkThreads, MINB) bk_paths_kernel(const BkArgs a) {
   extern __shared__ double s_tab[];
   BkTable tb;
   tb.sh = s_tab + threadIdx.x;
@@ -423,7 +428,10 @@ static int bk_set_smem(hh_ctx *ctx) {
   static bool done[64] = {};
   if (ctx->device < 64 && done[ctx->device]) return HH_OK;
   const int bytes = kBkThreads * kBkTable * (int)sizeof(double);
-  HH_CUDA(ctx, cudaFuncSetAttribute(bk_paths_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  HH_CUDA(ctx, cudaFuncSetAttribute(bk_paths_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  HH_CUDA(ctx, cudaFuncSetAttribute(bk_paths_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  HH_CUDA(ctx, cudaFuncSetAttribute(bk_paths_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  HH_CUDA(ctx, cudaFuncSetAttribute(bk_paths_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   HH_CUDA(ctx, cudaFuncSetAttribute(bk_integral_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   if (ctx->device < 64) done[ctx->device] = true;
   return HH_OK;
@@ -447,8 +455,12 @@ int bk_european_launch(hh_ctx *ctx, const hh_model *m, const hh_sim *s, const hh
   rc = bk_set_smem(ctx);
   if (rc) return rc;
   const int smem = kBkThreads * kBkTable * (int)sizeof(double);
+  static const int minb_env = getenv("HH_BK_MINB") ? atoi(getenv("HH_BK_MINB")) : kBkDefaultMinb;
+  const int minb = minb_env < 3 ? 3 : (minb_env > 6 ? 6 : minb_env);
+  void (*kern)(const BkArgs) = minb == 3 ? bk_paths_kernel<3> : minb == 4 ? bk_paths_kernel<4> : minb == 5 ? bk_paths_kernel<5>
+                                                                                                             : bk_paths_kernel<6>;
   int occ = 1;
-  HH_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bk_paths_kernel, kBkThreads, smem));
+  HH_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kBkThreads, smem));
   if (occ < 1) occ = 1;
   const int64_t want_blocks = (N + kBkThreads - 1) / kBkThreads;
   int64_t grid = (int64_t)ctx->sm_count * occ;
@@ -473,7 +485,7 @@ int bk_european_launch(hh_ctx *ctx, const hh_model *m, const hh_sim *s, const hh
   a.terminal = ctx->d_terminal.as<double>();
   a.counters = ctx->d_counters.as<unsigned long long>();
   HH_CUDA(ctx, cudaEventRecord(ctx->ev0, st));
-  bk_paths_kernel<<<(unsigned)grid, kBkThreads, smem, st>>>(a);
+  kern<<<(unsigned)grid, kBkThreads, smem, st>>>(a);
   HH_CUDA(ctx, cudaGetLastError());
   rc = terminal_payoffs_launch(ctx, a.terminal, N, payoffs, npay, 0);
   if (rc) return rc;
