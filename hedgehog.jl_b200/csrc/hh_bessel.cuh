@@ -107,28 +107,40 @@ struct BesselEF {
   cplx E, F;
 };
 
-HH_HD BesselEF besseli_series_ef(double nu, double lgam_nu1, cplx w, double log_aw, double arg_w) {
+constexpr int kSeriesMaxTerms = 100, kHankelMaxTerms = 60;
+
+// sum_k (w^2/4)^k / (k! (nu+1)_k): the ascending series without its prefactor. `rk` (nullable) tabulates
+// 1 / (k (nu + k)); the convergence test runs on every second term (one extra term at most).
+HH_HD cplx bessel_series_sum(double nu, cplx w, const double *rk) {
   const cplx q = 0.25 * (w * w);
   cplx term = mk(1.0), sum = mk(1.0);
 #pragma unroll 1
-  for (int k = 1; k < 100; ++k) {
-    term = (term * q) * rcp_fast((double)k * (nu + (double)k));
+  for (int k = 1; k + 1 < kSeriesMaxTerms; k += 2) {
+    const double r1 = rk ? rk[k] : rcp_fast((double)k * (nu + (double)k));
+    const double r2 = rk ? rk[k + 1] : rcp_fast((double)(k + 1) * (nu + (double)(k + 1)));
+    term = (term * q) * r1;
+    sum = sum + term;
+    term = (term * q) * r2;
     sum = sum + term;
     if (cabs2(term) < 1e-34 * cabs2(sum)) break;
   }
-  // (w/2)^nu / Gamma(nu+1) * sum
-  return BesselEF{cplx{nu * (log_aw - 0.6931471805599453) - lgam_nu1, nu * arg_w}, sum};
+  return sum;
 }
 
-HH_HD BesselEF besseli_asymptotic_ef(double nu, cplx w, double log_aw, double arg_w) {
+// Hankel sums s1 = sum (-1)^k a_k / w^k, s2 = sum a_k / w^k, a_k = prod (4 nu^2 - (2j-1)^2) / (8 j), stopped at the
+// smallest term. `bk` (nullable) tabulates (4 nu^2 - (2k-1)^2) / (8 k).
+HH_HD void bessel_hankel_sums(double nu, cplx w, const double *bk, cplx &s1, cplx &s2) {
   const double mu4 = 4.0 * nu * nu;
   const cplx iw = 1.0 / w;
-  cplx t = mk(1.0), s1 = mk(1.0), s2 = mk(1.0);
+  cplx t = mk(1.0);
+  s1 = mk(1.0);
+  s2 = mk(1.0);
   double last = 1.0;  // |t|^2 of the previous term
 #pragma unroll 1
-  for (int k = 1; k < 60; ++k) {
+  for (int k = 1; k < kHankelMaxTerms; ++k) {
     const double odd = (double)(2 * k - 1);
-    t = (t * iw) * ((mu4 - odd * odd) * rcp_fast(8.0 * (double)k));  // a_k / w^k
+    const double b = bk ? bk[k] : (mu4 - odd * odd) * rcp_fast(8.0 * (double)k);
+    t = (t * iw) * b;  // a_k / w^k
     const double m = cabs2(t);
     if (m > last) break;  // the expansion has started to diverge
     last = m;
@@ -136,6 +148,17 @@ HH_HD BesselEF besseli_asymptotic_ef(double nu, cplx w, double log_aw, double ar
     s2 = s2 + t;
     if (m < 1e-34) break;
   }
+}
+
+HH_HD BesselEF besseli_series_ef(double nu, double lgam_nu1, cplx w, double log_aw, double arg_w, const double *rk) {
+  const cplx sum = bessel_series_sum(nu, w, rk);
+  // (w/2)^nu / Gamma(nu+1) * sum
+  return BesselEF{cplx{nu * (log_aw - 0.6931471805599453) - lgam_nu1, nu * arg_w}, sum};
+}
+
+HH_HD BesselEF besseli_asymptotic_ef(double nu, cplx w, double log_aw, double arg_w, const double *bk) {
+  cplx s1, s2;
+  bessel_hankel_sums(nu, w, bk, s1, s2);
   // I = e^w / sqrt(2 pi w) [ s1 + e^{-2w +- i pi (nu + 1/2)} s2 ],  + for Im w >= 0
   const double sgn = w.im >= 0.0 ? 1.0 : -1.0;
   const cplx e2 = cexp_(cplx{-2.0 * w.re, -2.0 * w.im + sgn * kBesselPi * (nu + 0.5)});
@@ -143,36 +166,16 @@ HH_HD BesselEF besseli_asymptotic_ef(double nu, cplx w, double log_aw, double ar
 }
 
 // ---- ascending series: |w| - Re w <= 5, |w| <~ 25 ---------------------------------------------------------------
-HH_HD cplx log_besseli_series(double nu, double lgam_nu1, cplx w) {
-  const cplx q = 0.25 * (w * w);
-  cplx term = mk(1.0), sum = mk(1.0);
-#pragma unroll 1
-  for (int k = 1; k < 100; ++k) {
-    term = (term * q) * rcp_fast((double)k * (nu + (double)k));
-    sum = sum + term;
-    if (cabs2(term) < 1e-34 * cabs2(sum)) break;
-  }
+HH_HD cplx log_besseli_series(double nu, double lgam_nu1, cplx w, const double *rk) {
+  const cplx sum = bessel_series_sum(nu, w, rk);
   // (w/2)^nu / Gamma(nu+1) * sum
   return nu * clog_(0.5 * w) - lgam_nu1 + clog_(sum);
 }
 
 // ---- Hankel expansion: |w| large, Re w >= 0 -----------------------------------------------------------------
-HH_HD cplx log_besseli_asymptotic(double nu, cplx w) {
-  const double mu4 = 4.0 * nu * nu;
-  const cplx iw = 1.0 / w;
-  cplx t = mk(1.0), s1 = mk(1.0), s2 = mk(1.0);
-  double last = 1.0;  // |t|^2 of the previous term
-#pragma unroll 1
-  for (int k = 1; k < 60; ++k) {
-    const double odd = (double)(2 * k - 1);
-    t = (t * iw) * ((mu4 - odd * odd) * rcp_fast(8.0 * (double)k));  // a_k / w^k
-    const double m = cabs2(t);
-    if (m > last) break;  // the expansion has started to diverge
-    last = m;
-    s1 = (k & 1) ? s1 - t : s1 + t;
-    s2 = s2 + t;
-    if (m < 1e-34) break;
-  }
+HH_HD cplx log_besseli_asymptotic(double nu, cplx w, const double *bk) {
+  cplx s1, s2;
+  bessel_hankel_sums(nu, w, bk, s1, s2);
   // I = e^w / sqrt(2 pi w) [ s1 + e^{-2w +- i pi (nu + 1/2)} s2 ],  + for Im w >= 0
   const double sgn = w.im >= 0.0 ? 1.0 : -1.0;
   const cplx e2 = cexp_(cplx{-2.0 * w.re, -2.0 * w.im + sgn * kBesselPi * (nu + 0.5)});
@@ -256,12 +259,18 @@ struct BesselOrder {
   double nu;        // order, > -1
   double lgam_nu1;  // lgamma(nu + 1)
   double r_asym;    // |w| from which the Hankel expansion is used
+  // optional coefficient tables (the order is fixed per launch; the Broadie-Kaya kernel fills them in shared memory):
+  // series_rk[k] = 1 / (k (nu + k)), hankel_bk[k] = (4 nu^2 - (2k - 1)^2) / (8 k). NULL: computed on the fly.
+  const double *series_rk;
+  const double *hankel_bk;
 };
 inline BesselOrder make_bessel_order(double nu) {
   BesselOrder o;
   o.nu = nu;
   o.lgam_nu1 = lgamma(nu + 1.0);
   o.r_asym = 20.0 + 0.5 * nu * nu;
+  o.series_rk = nullptr;
+  o.hankel_bk = nullptr;
   return o;
 }
 
@@ -277,9 +286,9 @@ HH_HD_OUTLINE cplx log_besseli(const BesselOrder &o, cplx z) {
   const double aw = cabs(w);
   cplx r;
   if (aw <= 5.0 || (aw < o.r_asym && aw - w.re <= 5.0)) {
-    r = log_besseli_series(nu, o.lgam_nu1, w);
+    r = log_besseli_series(nu, o.lgam_nu1, w, o.series_rk);
   } else if (aw >= o.r_asym) {
-    r = log_besseli_asymptotic(nu, w);
+    r = log_besseli_asymptotic(nu, w, o.hankel_bk);
   } else if (nu >= 0.0) {
     r = log_besseli_cf(nu, w, nullptr);
   } else {
@@ -306,9 +315,9 @@ HH_HD BesselEF besseli_ef(const BesselOrder &o, cplx z, double log_az, double ar
   const double aw = cabs(w);
   BesselEF r;
   if (aw <= 5.0 || (aw < o.r_asym && aw - w.re <= 5.0)) {
-    r = besseli_series_ef(nu, o.lgam_nu1, w, log_az, arg_w);
+    r = besseli_series_ef(nu, o.lgam_nu1, w, log_az, arg_w, o.series_rk);
   } else if (aw >= o.r_asym) {
-    r = besseli_asymptotic_ef(nu, w, log_az, arg_w);
+    r = besseli_asymptotic_ef(nu, w, log_az, arg_w, o.hankel_bk);
   } else {
     r.E = log_besseli(o, w);  // continued fractions (rare: strongly rotated arguments of moderate size)
     r.F = mk(1.0);

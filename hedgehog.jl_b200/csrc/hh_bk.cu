@@ -31,7 +31,7 @@
 namespace hh {
 
 constexpr int kBkThreads = 128;
-constexpr int kBkDefaultMinb = 3;
+constexpr int kBkDefaultMinb = 4;
 constexpr int kBkTable = 32;  // table entries per thread in shared memory (32 KB per block); longer series (mean 12.3 at C4) spill to the HBM slab
 
 // terminal spots -> payoff sums (hh_european.cu)
@@ -259,6 +259,15 @@ struct BkArgs {
   unsigned long long *counters;  // [0] fallbacks, [1] sum J, [2] sum root-finder evaluations, [3] transitions, [4] unbracketed accepted
 };
 
+// series_rk[k] = 1 / (k (nu + k)), hankel_bk[k] = (4 nu^2 - (2k-1)^2) / (8 k), by all threads of the block (IEEE division: once)
+__device__ __forceinline__ void bk_fill_order_tables(double nu, double *rk, double *bk) {
+  for (int k = threadIdx.x; k < kSeriesMaxTerms; k += blockDim.x) rk[k] = k ? 1.0 / ((double)k * (nu + (double)k)) : 0.0;
+  for (int k = threadIdx.x; k < kHankelMaxTerms; k += blockDim.x) {
+    const double odd = (double)(2 * k - 1);
+    bk[k] = k ? (4.0 * nu * nu - odd * odd) / (8.0 * (double)k) : 0.0;
+  }
+}
+
 // MINB = resident blocks per SM the register allocation is bounded for (3: 168 registers; 6: 85). The kernel is
 // latency-bound (issue slots 30 % busy at 12 warps per SM, ncu), so the bound is chosen by measurement: HH_BK_MINB.
 template <int MINB>
@@ -270,7 +279,18 @@ __global__ void __launch_bounds__(kBkThreads, MINB) bk_paths_kernel(const BkArgs
   tb.cap = kBkTable;
   tb.slab = a.slab + ((int64_t)blockIdx.x * kBkThreads + threadIdx.x);
   tb.slab_stride = a.slab_stride;
-  const BkParams &p = a.p;
+  // The parameters live in shared memory (the outlined functions take them by reference: a reference to the kernel
+  // arguments would be copied to every thread's local memory), next to the coefficient tables of the fixed order nu.
+  __shared__ BkParams s_p;
+  __shared__ double s_rk[kSeriesMaxTerms], s_bk[kHankelMaxTerms];
+  bk_fill_order_tables(a.p.ord.nu, s_rk, s_bk);
+  if (threadIdx.x == 0) {
+    s_p = a.p;
+    s_p.ord.series_rk = s_rk;
+    s_p.ord.hankel_bk = s_bk;
+  }
+  __syncthreads();
+  const BkParams &p = s_p;
   unsigned long long nfall = 0, sumJ = 0, sumIt = 0, ntr = 0, nsec = 0;
   for (int64_t i = (int64_t)blockIdx.x * kBkThreads + threadIdx.x; i < a.n; i += (int64_t)gridDim.x * kBkThreads) {
     BkRng rng;
