@@ -139,7 +139,8 @@ HH_IPC_HANDLE_BYTES = 64
 HH_MAX_PEERS = 16
 HH_ERR_PEER_TIMEOUT = 4
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libhedgehog_mc.so")
+# HH_LIB_PATH: another build of the same library (A/B timing of two builds on one box); the default is the in-tree one
+LIB_PATH = os.environ.get("HH_LIB_PATH") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libhedgehog_mc.so")
 _lib = None
 
 
