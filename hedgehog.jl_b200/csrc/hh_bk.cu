@@ -254,6 +254,9 @@ struct BkArgs {
   double x0, v0;
   double *terminal;  // S_T per trajectory
   double *vterm;     // nullable: V_T per trajectory
+  double *stats;     // nullable: HH_PD_NSTATS x n path statistics over the monitoring dates (hh_mc_path_dependent)
+  int monitor_every; // every k-th date is a monitoring date
+  double inv_m;      // 1 / number of monitoring dates
   double *slab;
   int64_t slab_stride;
   unsigned long long *counters;  // [0] fallbacks, [1] sum J, [2] sum root-finder evaluations, [3] transitions, [4] unbracketed accepted
@@ -304,6 +307,8 @@ __global__ void __launch_bounds__(kBkThreads, MINB) bk_paths_kernel(const BkArgs
     rng.k0 = (uint32_t)key;
     rng.k1 = (uint32_t)(key >> 32);
     double x = a.x0, v = a.v0;
+    double sum_s = 0.0, sum_x = 0.0, max_x = -INFINITY, min_x = INFINITY;  // running statistics (a.stats only)
+    int due = a.monitor_every;
     for (int n = 0; n < a.n_dates; ++n) {
       rng.c2 = (uint32_t)n;
       rng.draw = 0;
@@ -323,9 +328,23 @@ __global__ void __launch_bounds__(kBkThreads, MINB) bk_paths_kernel(const BkArgs
       sumJ += (unsigned)inv.J;
       sumIt += (unsigned)inv.iters;
       ++ntr;
+      if (a.stats && --due == 0) {  // a monitoring date: the transition is exact, so the statistics carry no time-stepping bias
+        due = a.monitor_every;
+        sum_x += x;
+        max_x = fmax(max_x, x);
+        min_x = fmin(min_x, x);
+        sum_s += exp(x);
+      }
     }
     a.terminal[i] = exp(x);
     if (a.vterm) a.vterm[i] = v;
+    if (a.stats) {  // S_T, A, G, max S, min S
+      a.stats[i] = exp(x);
+      a.stats[a.n + i] = sum_s * a.inv_m;
+      a.stats[2 * a.n + i] = exp(sum_x * a.inv_m);
+      a.stats[3 * a.n + i] = exp(max_x);
+      a.stats[4 * a.n + i] = exp(min_x);
+    }
   }
   // warp-aggregate the statistics
 #pragma unroll
@@ -457,15 +476,14 @@ static int bk_set_smem(hh_ctx *ctx) {
   return HH_OK;
 }
 
-int bk_european_launch(hh_ctx *ctx, const hh_model *m, const hh_sim *s, const hh_payoff *payoffs, int npay,
-                       int want_terminal) {
-  if (npay < 1 || npay > 256 || !payoffs) return ctx->fail(HH_ERR_ARG, "npayoffs must be in [1, 256] (got %d)", npay);
+// Launches the path kernel for `s` (validated by the caller); terminal spots land in ctx->d_terminal, path statistics in
+// `d_stats` when non-null. Records ev0 before the kernel.
+static int bk_paths_launch(hh_ctx *ctx, const hh_model *m, const hh_sim *s, double *d_stats, int monitor_every, BkArgs &a) {
   if (s->rng_mode != HH_RNG_PHILOX)
     return ctx->fail(HH_ERR_UNSUPPORTED, "Broadie-Kaya draws from the in-kernel Philox stream only; the deterministic "
                                          "pieces have their own parity probes (hh_bk_chf, hh_bk_integral)");
   if (s->precision != HH_PREC_F64) return ctx->fail(HH_ERR_UNSUPPORTED, "Broadie-Kaya runs in f64 only");
   const int ndates = s->n_steps > 0 ? s->n_steps : 1;
-  BkArgs a;
   memset(&a, 0, sizeof a);
   int rc = make_params(ctx, m, m->T / ndates, &s->bk, a.p);
   if (rc) return rc;
@@ -504,14 +522,42 @@ int bk_european_launch(hh_ctx *ctx, const hh_model *m, const hh_sim *s, const hh
   a.v0 = m->V0;
   a.terminal = ctx->d_terminal.as<double>();
   a.counters = ctx->d_counters.as<unsigned long long>();
+  a.stats = d_stats;
+  a.monitor_every = monitor_every > 0 ? monitor_every : 1;
+  a.inv_m = 1.0 / (double)(ndates / a.monitor_every > 0 ? ndates / a.monitor_every : 1);
   HH_CUDA(ctx, cudaEventRecord(ctx->ev0, st));
   kern<<<(unsigned)grid, kBkThreads, smem, st>>>(a);
   HH_CUDA(ctx, cudaGetLastError());
-  rc = terminal_payoffs_launch(ctx, a.terminal, N, payoffs, npay, 0);
+  return HH_OK;
+}
+
+int bk_european_launch(hh_ctx *ctx, const hh_model *m, const hh_sim *s, const hh_payoff *payoffs, int npay,
+                       int want_terminal) {
+  if (npay < 1 || npay > 256 || !payoffs) return ctx->fail(HH_ERR_ARG, "npayoffs must be in [1, 256] (got %d)", npay);
+  BkArgs a;
+  int rc = bk_paths_launch(ctx, m, s, nullptr, 1, a);
+  if (rc) return rc;
+  rc = terminal_payoffs_launch(ctx, a.terminal, s->n_paths, payoffs, npay, 0);
   if (rc) return rc;
   ctx->pend.want_terminal = want_terminal != 0;
   ctx->pend.bk = true;
   ctx->pend.nseg = 0;
+  return HH_OK;
+}
+
+// Path statistics under exact Broadie-Kaya transitions for hh_mc_path_dependent (hh_pathdep.cu): HH_PD_NSTATS x n_paths
+// into `d_stats` (device), the inversion counters into ctx->bk_stats after the caller has synchronised and called
+// bk_read_counters.
+int bk_path_stats_launch(hh_ctx *ctx, const hh_model *m, const hh_sim *s, int monitor_every, double *d_stats) {
+  BkArgs a;
+  return bk_paths_launch(ctx, m, s, d_stats, monitor_every, a);
+}
+
+int bk_read_counters(hh_ctx *ctx, int64_t *n_fallback) {  // after the stream has been synchronised
+  unsigned long long counters[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  HH_CUDA(ctx, cudaMemcpy(counters, ctx->d_counters.ptr, sizeof counters, cudaMemcpyDeviceToHost));
+  for (int i = 0; i < 5; ++i) ctx->bk_stats[i] = (double)counters[i];
+  if (n_fallback) *n_fallback = (int64_t)counters[0];
   return HH_OK;
 }
 

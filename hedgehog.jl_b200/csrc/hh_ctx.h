@@ -110,6 +110,9 @@ int validate_model_sim(hh_ctx *ctx, const hh_model *model, const hh_sim *sim);
 // implemented in hh_pathdep.cu
 int path_dependent(hh_ctx *ctx, const hh_model *model, const hh_sim *sim, int monitor_every, const hh_path_payoff *payoffs,
                    int npayoffs, double discount, hh_result *results, double *path_stats, size_t path_stats_len);
+// implemented in hh_bk.cu
+int bk_path_stats_launch(hh_ctx *ctx, const hh_model *model, const hh_sim *sim, int monitor_every, double *d_stats);
+int bk_read_counters(hh_ctx *ctx, int64_t *n_fallback);
 // device -> the caller's pageable buffer through a pinned double buffer with parallel host copies (large outputs)
 int copy_to_pageable_host(hh_ctx *ctx, void *dst, const void *src_dev, size_t bytes, cudaStream_t st);
 }  // namespace hh

@@ -28,9 +28,9 @@ constexpr int kPdThreads = 512;
 constexpr int kPdStats = HH_PD_NSTATS;
 constexpr int kPdAcc = 3;  // sum, sumsq, nonfinite
 
-struct PdPayoff {  // device form of hh_path_payoff: the barrier in log space
+struct PdPayoff {  // device form of hh_path_payoff: the barrier in log space (stepping kernels) and as given
   int kind;
-  double strike, cp, log_barrier, amount;
+  double strike, cp, log_barrier, amount, barrier;
 };
 
 struct PdArgs {
@@ -193,7 +193,7 @@ __global__ void __launch_bounds__(kPdThreads, 2) pathdep_kernel(const PdArgs a) 
   const int G = kPdThreads >> a.kp_log2;  // number of path groups
   PdPayoff mine;
   mine.kind = HH_PD_VANILLA;
-  mine.strike = mine.cp = mine.log_barrier = mine.amount = 0.0;
+  mine.strike = mine.cp = mine.log_barrier = mine.amount = mine.barrier = 0.0;
   if (k < a.npay) mine = a.payoffs[k];
   double acc[kPdAcc] = {0.0, 0.0, 0.0};
 
@@ -310,7 +310,7 @@ __global__ void __launch_bounds__(THREADS, 1) pathdep_heston_fast_kernel(const P
   const int G = THREADS >> a.kp_log2;
   PdPayoff mine;
   mine.kind = HH_PD_VANILLA;
-  mine.strike = mine.cp = mine.log_barrier = mine.amount = 0.0;
+  mine.strike = mine.cp = mine.log_barrier = mine.amount = mine.barrier = 0.0;
   if (k < a.npay) mine = a.payoffs[k];
   double acc[kPdAcc] = {0.0, 0.0, 0.0};
   const int M = a.n_steps;
@@ -368,6 +368,45 @@ __global__ void __launch_bounds__(THREADS, 1) pathdep_heston_fast_kernel(const P
     pd_stage_and_pay<ANTI, ARITH, THREADS>(a, stage, tid, i, base, xp, xm, rp, rm, mine, k, g, G, acc);
   }
   pd_block_reduce<THREADS>(a, stage, tid, G, acc);
+}
+
+// Contracts evaluated from a statistics buffer [HH_PD_NSTATS][n] in S-space (the Broadie-Kaya path kernel writes it:
+// exact transitions between the monitoring dates, hh_bk.cu). Same (contract, path group) transpose, no antithetic side.
+__global__ void __launch_bounds__(256) pathdep_from_stats_kernel(const double *__restrict__ stats, int64_t n,
+                                                                 const PdPayoff *__restrict__ payoffs, int npay, int kp_log2,
+                                                                 double *partials) {
+  __shared__ double red[kPdAcc * 256];
+  const int tid = threadIdx.x;
+  const int KP = 1 << kp_log2;
+  const int k = tid & (KP - 1);
+  const int g = tid >> kp_log2;
+  const int G = 256 >> kp_log2;
+  PdPayoff mine;
+  mine.kind = HH_PD_VANILLA;
+  mine.strike = mine.cp = mine.log_barrier = mine.amount = mine.barrier = 0.0;
+  if (k < npay) mine = payoffs[k];
+  mine.log_barrier = mine.barrier;  // pd_payoff compares its max / min arguments with log_barrier: spots against the barrier here
+  double acc[kPdAcc] = {0.0, 0.0, 0.0};
+  if (k < npay) {
+    for (int64_t j = (int64_t)blockIdx.x * G + g; j < n; j += (int64_t)gridDim.x * G) {
+      const double ST = stats[j];
+      const double pay = pd_payoff(mine, ST, stats[n + j], stats[2 * n + j], stats[3 * n + j], stats[4 * n + j]);
+      acc[0] += pay;
+      acc[1] = fma(pay, pay, acc[1]);
+      if (k == 0 && !isfinite(ST)) acc[2] += 1.0;
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < kPdAcc; ++c) red[c * 256 + tid] = acc[c];
+  __syncthreads();
+  if (tid < npay) {
+    double *out = partials + ((size_t)blockIdx.x * npay + tid) * kPdAcc;
+    for (int c = 0; c < kPdAcc; ++c) {
+      double t = 0.0;
+      for (int gg = 0; gg < G; ++gg) t += red[c * 256 + (gg << kp_log2) + tid];
+      out[c] = t;
+    }
+  }
 }
 
 // Sum the per-block partials in a fixed order: one block per contract.
@@ -441,6 +480,25 @@ static cudaError_t pd_fast(const PdArgs &a, bool anti, bool arith, bool ukey, in
 #undef HH_PD_FAST
 }
 
+static void fill_results(hh_result *results, const std::vector<double> &fin, int npay, int64_t N, double discount, float ms,
+                         int64_t n_fallback) {
+  for (int k = 0; k < npay; ++k) {
+    hh_result *r = &results[k];
+    memset(r, 0, sizeof *r);
+    r->sum = fin[(size_t)k * kPdAcc + 0];
+    r->sumsq = fin[(size_t)k * kPdAcc + 1];
+    r->n = N;
+    const double mean = r->sum / (double)N;
+    r->price = discount * mean;  // montecarlo.jl:489-490
+    double var = N > 1 ? (r->sumsq - (double)N * mean * mean) / (double)(N - 1) : 0.0;
+    if (var < 0) var = 0;
+    r->std_error = discount * sqrt(var / (double)N);
+    r->n_nonfinite = (int64_t)fin[2];
+    r->n_fallback = n_fallback;
+    r->kernel_ms = ms;
+  }
+}
+
 int path_dependent(hh_ctx *ctx, const hh_model *m, const hh_sim *s, int monitor_every, const hh_path_payoff *payoffs,
                    int npay, double discount, hh_result *results, double *path_stats, size_t path_stats_len) {
   int rc = validate_model_sim(ctx, m, s);
@@ -449,9 +507,11 @@ int path_dependent(hh_ctx *ctx, const hh_model *m, const hh_sim *s, int monitor_
   if (!payoffs || !results) return ctx->fail(HH_ERR_ARG, "payoffs/results is NULL");
   if (npay < 1 || npay > 256) return ctx->fail(HH_ERR_ARG, "npayoffs must be in [1, 256] (got %d)", npay);
   const bool heston = m->kind == HH_MODEL_HESTON;
-  if (!(s->scheme == HH_SCHEME_EM || (!heston && s->scheme == HH_SCHEME_EXACT_STEPS)))
+  const bool bk = heston && s->scheme == HH_SCHEME_HESTON_BK;  // exact transitions between the dates (n_steps of them)
+  if (!(s->scheme == HH_SCHEME_EM || (!heston && s->scheme == HH_SCHEME_EXACT_STEPS) || bk))
     return ctx->fail(HH_ERR_UNSUPPORTED, "path-dependent payoffs run on the stepping schemes (EulerMaruyama; BlackScholesExact "
-                     "increments for LognormalDynamics); scheme %d saves no intermediate dates", s->scheme);
+                     "increments for LognormalDynamics; HestonBroadieKaya transitions); scheme %d saves no intermediate dates",
+                     s->scheme);
   if (s->precision != HH_PREC_F64) return ctx->fail(HH_ERR_UNSUPPORTED, "path-dependent payoffs are computed in binary64");
   const int M = s->n_steps;
   if (monitor_every < 1 || M % monitor_every != 0)
@@ -469,6 +529,7 @@ int path_dependent(hh_ctx *ctx, const hh_model *m, const hh_sim *s, int monitor_
     host[k].cp = q.cp;
     host[k].log_barrier = barrier ? log(q.barrier) : 0.0;
     host[k].amount = q.amount;
+    host[k].barrier = q.barrier;
     arith = arith || q.kind == HH_PD_ASIAN_ARITH;
   }
   const int64_t N = s->n_paths;
@@ -480,6 +541,42 @@ int path_dependent(hh_ctx *ctx, const hh_model *m, const hh_sim *s, int monitor_
 
   HH_CUDA(ctx, cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
+  if (bk) {
+    // The Broadie-Kaya path kernel writes the statistics of every trajectory (S-space); the contracts are evaluated from
+    // that buffer. d_misc holds the statistics (d_terminal and d_grid belong to the path kernel).
+    HH_CUDA(ctx, ctx->d_misc.ensure(sizeof(double) * (size_t)N * kPdStats));
+    HH_CUDA(ctx, ctx->d_payoffs.ensure(sizeof(PdPayoff) * (size_t)npay));
+    HH_CUDA(ctx, cudaMemcpyAsync(ctx->d_payoffs.ptr, host.data(), sizeof(PdPayoff) * (size_t)npay, cudaMemcpyHostToDevice, st));
+    rc = bk_path_stats_launch(ctx, m, s, monitor_every, ctx->d_misc.as<double>());  // records ev0
+    if (rc) return rc;
+    int kp_log2 = 0;
+    while ((1 << kp_log2) < npay) kp_log2++;
+    const int G = 256 >> kp_log2;
+    const int64_t want = (N + G - 1) / G;
+    const int grid = (int)(want < (int64_t)ctx->sm_count * 8 ? want : (int64_t)ctx->sm_count * 8);
+    HH_CUDA(ctx, ctx->d_partials.ensure(sizeof(double) * (size_t)grid * npay * kPdAcc));
+    HH_CUDA(ctx, ctx->d_final.ensure(sizeof(double) * (size_t)npay * kPdAcc));
+    pathdep_from_stats_kernel<<<grid, 256, 0, st>>>(ctx->d_misc.as<double>(), N, ctx->d_payoffs.as<PdPayoff>(), npay, kp_log2,
+                                                   ctx->d_partials.as<double>());
+    HH_CUDA(ctx, cudaGetLastError());
+    pathdep_finalize_kernel<<<npay, 256, 0, st>>>(ctx->d_partials.as<double>(), grid, npay, ctx->d_final.as<double>());
+    HH_CUDA(ctx, cudaGetLastError());
+    HH_CUDA(ctx, cudaEventRecord(ctx->ev1, st));
+    std::vector<double> fin((size_t)npay * kPdAcc);
+    if (path_stats) {
+      rc = copy_to_pageable_host(ctx, path_stats, ctx->d_misc.ptr, sizeof(double) * (size_t)N * kPdStats, st);
+      if (rc) return rc;
+    }
+    HH_CUDA(ctx, cudaMemcpyAsync(fin.data(), ctx->d_final.ptr, sizeof(double) * fin.size(), cudaMemcpyDeviceToHost, st));
+    HH_CUDA(ctx, cudaStreamSynchronize(st));
+    int64_t n_fallback = 0;
+    rc = bk_read_counters(ctx, &n_fallback);
+    if (rc) return rc;
+    float ms = 0.f;
+    HH_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    fill_results(results, fin, npay, N, discount, ms, n_fallback);
+    return HH_OK;
+  }
   HH_CUDA(ctx, upload_fast_tables2(ctx->device, st));
 
   PdArgs a;
@@ -576,20 +673,7 @@ int path_dependent(hh_ctx *ctx, const hh_model *m, const hh_sim *s, int monitor_
   HH_CUDA(ctx, cudaStreamSynchronize(st));
   float ms = 0.f;
   HH_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
-  for (int k = 0; k < npay; ++k) {
-    hh_result *r = &results[k];
-    memset(r, 0, sizeof *r);
-    r->sum = fin[(size_t)k * kPdAcc + 0];
-    r->sumsq = fin[(size_t)k * kPdAcc + 1];
-    r->n = N;
-    const double mean = r->sum / (double)N;
-    r->price = discount * mean;  // montecarlo.jl:489-490
-    double var = N > 1 ? (r->sumsq - (double)N * mean * mean) / (double)(N - 1) : 0.0;
-    if (var < 0) var = 0;
-    r->std_error = discount * sqrt(var / (double)N);
-    r->n_nonfinite = (int64_t)fin[2];
-    r->kernel_ms = ms;
-  }
+  fill_results(results, fin, npay, N, discount, ms, 0);
   return HH_OK;
 }
 

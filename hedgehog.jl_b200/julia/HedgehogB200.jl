@@ -142,10 +142,12 @@ vr_of(::NoVarianceReduction) = Cint(0)
 vr_of(::Antithetic) = Cint(1)
 
 # `f(sim)` runs with the seed vector pinned for the duration of the ccall
-function with_sim(f, method::B200MonteCarlo, scheme::Cint)
+function with_sim(f, method::B200MonteCarlo, scheme::Cint; dates_from_config::Bool=false)
     cfg = method.config
     exact = scheme == HH_SCHEME_EXACT_TERMINAL || scheme == HH_SCHEME_HESTON_BK
-    steps = exact ? 1 : cfg.steps                                 # exact strategies ignore `steps` (montecarlo.jl:454-459)
+    # exact strategies ignore `steps` (montecarlo.jl:454-459); path-dependent payoffs under HestonBroadieKaya use them as
+    # the number of exactly simulated dates
+    steps = (exact && !dates_from_config) ? 1 : cfg.steps
     seeds = Vector{UInt64}(cfg.seeds)
     prec = method.precision === :f32 ? Cint(1) : Cint(0)          # HH_PREC_F32 / HH_PREC_F64
     if method.base_seed !== nothing || exact
@@ -246,7 +248,7 @@ function Hedgehog.solve(prob::PricingProblem{P,I}, method::B200MonteCarlo) where
     payoff = hh_path_payoff(prob.payoff)
     discount = df(prob.market_inputs.rate, prob.payoff.expiry)    # montecarlo.jl:489
     res = Ref(HHResult(0, 0, 0, 0, 0, 0, 0, 0))
-    with_sim(method, scheme) do sim
+    with_sim(method, scheme; dates_from_config = scheme == HH_SCHEME_HESTON_BK) do sim
         rc = ccall((:hh_mc_path_dependent, LIB[]), Cint,
                    (Ptr{Cvoid}, Ref{HHModel}, Ref{HHSim}, Cint, Ref{HHPathPayoff}, Cint, Cdouble, Ref{HHResult}, Ptr{Float64}, Csize_t),
                    ctx.h, model, sim, prob.payoff.monitor_every, payoff, 1, discount, res, Ptr{Float64}(C_NULL), 0)

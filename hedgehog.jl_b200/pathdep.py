@@ -140,7 +140,11 @@ def solve_path_dependent(payoffs: Sequence, market_inputs, method, *, engine=Non
     shard, reduce = api._shard_and_reduce(shard, group)
     prob0 = api.PricingProblem(p0, market_inputs)
     mdl = api._model_of(prob0, method)
-    sim = api._sim_of(method, api._scheme_of(method, for_lsm=True), shard)  # stepping form of BlackScholesExact
+    scheme = api._scheme_of(method, for_lsm=True)                             # stepping form of BlackScholesExact
+    if scheme == abi.HH_SCHEME_HESTON_BK:                                       # exact transitions between config.steps dates
+        from dataclasses import replace
+        method = replace(method, bk_steps_from_config=True)
+    sim = api._sim_of(method, scheme, shard)
     discount = api.df(market_inputs.rate, p0.expiry)
     results, _ = eng.mc_path_dependent(mdl, sim, [_abi_tuple(p) for p in payoffs], discount, every)
     sums = np.array([[r.sum, r.sumsq, float(r.n)] for r in results], dtype=np.float64)

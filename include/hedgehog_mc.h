@@ -243,8 +243,10 @@ typedef struct hh_path_payoff {
   double amount;  /* barrier rebate (paid at expiry) or digital cash amount */
 } hh_path_payoff;
 
-/* model/sim as in hh_mc_european; schemes HH_SCHEME_EM (both models) and HH_SCHEME_EXACT_STEPS (GBM, advanced in log
- * space: the same law and the same values to rounding). npayoffs in [1, 256].
+/* model/sim as in hh_mc_european; schemes HH_SCHEME_EM (both models), HH_SCHEME_EXACT_STEPS (GBM, advanced in log
+ * space: the same law and the same values to rounding) and HH_SCHEME_HESTON_BK (exact Broadie-Kaya transitions between
+ * n_steps dates: no time-stepping bias at the monitoring dates; in-kernel RNG, no antithetic, like hh_mc_european).
+ * npayoffs in [1, 256].
  * path_stats: nullable host buffer, HH_PD_NSTATS x ncols row-major (ncols = n_paths, doubled [plus | minus] when
  * antithetic), path_stats_len its length in doubles. */
 int hh_mc_path_dependent(hh_ctx *ctx, const hh_model *model, const hh_sim *sim, int monitor_every,

@@ -106,8 +106,8 @@ def test_argument_errors(cuda):
         cuda.mc_path_dependent(m, sim, [ALL_KINDS[0]] * 257, 1.0, 1)
     with pytest.raises(NotImplementedError):
         cuda.mc_path_dependent(m, SimSpec(n_paths=100, n_steps=8, scheme=abi.HH_SCHEME_EXACT_TERMINAL), ALL_KINDS, 1.0, 1)
-    with pytest.raises(NotImplementedError):
-        cuda.mc_path_dependent(heston_model(), SimSpec(n_paths=100, n_steps=8, scheme=abi.HH_SCHEME_HESTON_BK), ALL_KINDS, 1.0, 1)
+    with pytest.raises(ValueError):            # HestonBroadieKaya is not defined for LognormalDynamics
+        cuda.mc_path_dependent(m, SimSpec(n_paths=100, n_steps=8, scheme=abi.HH_SCHEME_HESTON_BK), ALL_KINDS, 1.0, 1)
     with pytest.raises(NotImplementedError):
         cuda.mc_path_dependent(heston_model(), SimSpec(n_paths=100, n_steps=8, scheme=abi.HH_SCHEME_EM, precision=abi.HH_PREC_F32),
                                ALL_KINDS, 1.0, 1)
@@ -152,3 +152,46 @@ def test_heston_asian_put_call_parity_of_the_average(cuda):
     EA = 100.0 * np.mean([math.exp(0.03 * T * i / 12) for i in range(1, 13)])
     # Euler-Maruyama in log space carries a small martingale bias (E[S] is off by O(dt)); allow 2e-4 relative on E[A]
     assert abs((call.price - put.price) - math.exp(-0.03 * T) * (EA - 100.0)) < 3.5 * math.hypot(call.std_error, put.std_error) + 2e-2
+
+
+# ---- exact Broadie-Kaya transitions between the monitoring dates -------------------------------------------------------
+
+def test_broadie_kaya_statistics_match_the_european_path(cuda):
+    """The statistics come out of the same path kernel as hh_mc_european under HestonBroadieKaya: S_T is bit-identical, a
+    VANILLA contract reproduces the European price, knock-in + knock-out = vanilla, min <= G <= A <= max."""
+    m = heston_model()
+    n, dates = 20_000, 6
+    sim = SimSpec(n_paths=n, n_steps=dates, scheme=abi.HH_SCHEME_HESTON_BK, base_seed=31)
+    pays = [(abi.HH_PD_VANILLA, 100.0, 1.0, 0.0, 0.0), (abi.HH_PD_UP_OUT, 100.0, 1.0, 125.0, 0.0), (abi.HH_PD_UP_IN, 100.0, 1.0, 125.0, 0.0),
+            (abi.HH_PD_ASIAN_ARITH, 100.0, 1.0, 0.0, 0.0), (abi.HH_PD_ASIAN_GEOM, 100.0, 1.0, 0.0, 0.0), (abi.HH_PD_DOWN_IN, 100.0, -1.0, 85.0, 0.0)]
+    res, st = cuda.mc_path_dependent(m, sim, pays, 0.97, 1, want_stats=True)
+    eur, term = cuda.mc_european(m, sim, [(100.0, 1.0)], 0.97, want_terminal=True)
+    assert np.array_equal(st[0], term)
+    assert res[0].sum == pytest.approx(eur[0].sum, rel=1e-13)
+    assert res[1].sum + res[2].sum == pytest.approx(res[0].sum, rel=1e-12)
+    assert np.all(st[4] <= st[2] * (1 + 1e-14)) and np.all(st[2] <= st[1] * (1 + 1e-14)) and np.all(st[1] <= st[3] * (1 + 1e-14))
+    for c, r in zip(pays, res):
+        assert r.sum == pytest.approx(numpy_payoff(c, st).sum(), rel=1e-12)
+        assert r.n_fallback == 0
+    # monitoring every second date: the statistics of dates 2, 4, 6 only
+    res2, st2 = cuda.mc_path_dependent(m, sim, pays, 0.97, 2, want_stats=True)
+    assert np.array_equal(st2[0], st[0]) and np.all(st2[3] <= st[3]) and np.all(st2[4] >= st[4])
+    with pytest.raises(NotImplementedError):   # Q5: Antithetic + HestonBroadieKaya
+        cuda.mc_path_dependent(m, SimSpec(n_paths=n, n_steps=dates, scheme=abi.HH_SCHEME_HESTON_BK, vr=abi.HH_VR_ANTITHETIC), pays, 1.0, 1)
+
+
+def test_broadie_kaya_asian_agrees_with_fine_euler_maruyama(cuda):
+    """Monthly-monitored Asian and barrier options: exact transitions (12 dates) against Euler-Maruyama on 40 steps per
+    month, through solve(); agreement within 4 combined standard errors plus the scheme's O(dt) bias."""
+    ref, exp = dt.date(2020, 1, 1), dt.date(2021, 1, 1)
+    mk = hh.HestonInputs(ref, 0.03, 100.0, 0.04, 2.0, 0.04, 0.3, -0.7)
+    def basket(mon):
+        return hh.BasketPricingProblem([hh.AsianOption(100.0, exp, hh.Call(), monitoring=mon),
+                                        hh.AsianOption(100.0, exp, hh.Put(), hh.GeometricAverage(), mon),
+                                        hh.BarrierOption(100.0, 120.0, exp, hh.Call(), hh.Up(), hh.KnockOut(), monitoring=mon)], mk)
+    bk = hh.solve(basket(hh.Monitoring(1)), hh.MonteCarlo(hh.HestonDynamics(), hh.HestonBroadieKaya(),
+                                                         hh.SimulationConfig(400_000, steps=12, base_seed=5), ensemble=False), engine=cuda)
+    em = hh.solve(basket(hh.Monitoring(40)), hh.MonteCarlo(hh.HestonDynamics(), hh.EulerMaruyama(),
+                                                          hh.SimulationConfig(2_000_000, steps=480, base_seed=6), ensemble=False), engine=cuda)
+    for a, b in zip(bk, em):
+        assert abs(a.price - b.price) < 4.0 * math.hypot(a.std_error, b.std_error) + 5e-3 * b.price, (a.price, b.price, a.std_error, b.std_error)
