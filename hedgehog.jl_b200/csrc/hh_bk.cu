@@ -251,9 +251,11 @@ struct BkArgs {
   const uint64_t *seeds;
   int n_dates;
   BkParams p;
-  double x0, v0;
+  double x0, v0, s0;
   double *terminal;  // S_T per trajectory
   double *vterm;     // nullable: V_T per trajectory
+  double *grid;      // nullable: spots at dates 0..n_dates, date-major with `grid_stride` columns per date (LSM)
+  int64_t grid_stride;
   double *stats;     // nullable: HH_PD_NSTATS x n path statistics over the monitoring dates (hh_mc_path_dependent)
   int monitor_every; // every k-th date is a monitoring date
   double inv_m;      // 1 / number of monitoring dates
@@ -307,6 +309,7 @@ __global__ void __launch_bounds__(kBkThreads, MINB) bk_paths_kernel(const BkArgs
     rng.k0 = (uint32_t)key;
     rng.k1 = (uint32_t)(key >> 32);
     double x = a.x0, v = a.v0;
+    if (a.grid) a.grid[i] = a.s0;
     double sum_s = 0.0, sum_x = 0.0, max_x = -INFINITY, min_x = INFINITY;  // running statistics (a.stats only)
     int due = a.monitor_every;
     for (int n = 0; n < a.n_dates; ++n) {
@@ -328,6 +331,7 @@ __global__ void __launch_bounds__(kBkThreads, MINB) bk_paths_kernel(const BkArgs
       sumJ += (unsigned)inv.J;
       sumIt += (unsigned)inv.iters;
       ++ntr;
+      if (a.grid) a.grid[(int64_t)(n + 1) * a.grid_stride + i] = exp(x);
       if (a.stats && --due == 0) {  // a monitoring date: the transition is exact, so the statistics carry no time-stepping bias
         due = a.monitor_every;
         sum_x += x;
@@ -457,8 +461,8 @@ static int make_params(hh_ctx *ctx, const hh_model *m, double tau, const hh_bk_c
 static int ensure_slab(hh_ctx *ctx, int nblocks, const BkParams &p, double **slab, int64_t *stride) {
   const int64_t threads = (int64_t)nblocks * kBkThreads;
   const int64_t extra = p.max_terms > kBkTable ? p.max_terms - kBkTable : 0;
-  HH_CUDA(ctx, ctx->d_grid.ensure(sizeof(double) * (size_t)(threads * extra + 1)));
-  *slab = ctx->d_grid.as<double>();
+  HH_CUDA(ctx, ctx->d_bk_slab.ensure(sizeof(double) * (size_t)(threads * extra + 1)));
+  *slab = ctx->d_bk_slab.as<double>();
   *stride = threads;
   return HH_OK;
 }
@@ -478,7 +482,8 @@ static int bk_set_smem(hh_ctx *ctx) {
 
 // Launches the path kernel for `s` (validated by the caller); terminal spots land in ctx->d_terminal, path statistics in
 // `d_stats` when non-null. Records ev0 before the kernel.
-static int bk_paths_launch(hh_ctx *ctx, const hh_model *m, const hh_sim *s, double *d_stats, int monitor_every, BkArgs &a) {
+static int bk_paths_launch(hh_ctx *ctx, const hh_model *m, const hh_sim *s, double *d_stats, int monitor_every, BkArgs &a,
+                           double *d_grid = nullptr, int64_t grid_stride = 0) {
   if (s->rng_mode != HH_RNG_PHILOX)
     return ctx->fail(HH_ERR_UNSUPPORTED, "Broadie-Kaya draws from the in-kernel Philox stream only; the deterministic "
                                          "pieces have their own parity probes (hh_bk_chf, hh_bk_integral)");
@@ -520,6 +525,9 @@ static int bk_paths_launch(hh_ctx *ctx, const hh_model *m, const hh_sim *s, doub
   a.n_dates = ndates;
   a.x0 = log(m->S0);
   a.v0 = m->V0;
+  a.s0 = m->S0;
+  a.grid = d_grid;
+  a.grid_stride = grid_stride;
   a.terminal = ctx->d_terminal.as<double>();
   a.counters = ctx->d_counters.as<unsigned long long>();
   a.stats = d_stats;
@@ -551,6 +559,11 @@ int bk_european_launch(hh_ctx *ctx, const hh_model *m, const hh_sim *s, const hh
 int bk_path_stats_launch(hh_ctx *ctx, const hh_model *m, const hh_sim *s, int monitor_every, double *d_stats) {
   BkArgs a;
   return bk_paths_launch(ctx, m, s, d_stats, monitor_every, a);
+}
+
+int bk_path_grid_launch(hh_ctx *ctx, const hh_model *m, const hh_sim *s, double *d_grid, int64_t grid_stride) {
+  BkArgs a;
+  return bk_paths_launch(ctx, m, s, nullptr, 1, a, d_grid, grid_stride);
 }
 
 int bk_read_counters(hh_ctx *ctx, int64_t *n_fallback) {  // after the stream has been synchronised

@@ -65,7 +65,7 @@ struct hh_ctx {
   std::string err;
 
   hh::DeviceBuffer d_payoffs, d_partials, d_final, d_terminal, d_seeds, d_normals, d_tangents;
-  hh::DeviceBuffer d_grid, d_cash, d_tau, d_lsm_partials, d_lsm_state, d_misc, d_counters;
+  hh::DeviceBuffer d_grid, d_cash, d_tau, d_lsm_partials, d_lsm_state, d_misc, d_counters, d_bk_slab;
   // peer mailboxes (hh_peer_*): own buffer + the peers' buffers mapped through CUDA IPC
   void *mailbox = nullptr;
   void *peer_mail[HH_MAX_PEERS] = {};
@@ -113,6 +113,8 @@ int path_dependent(hh_ctx *ctx, const hh_model *model, const hh_sim *sim, int mo
 // implemented in hh_bk.cu
 int bk_path_stats_launch(hh_ctx *ctx, const hh_model *model, const hh_sim *sim, int monitor_every, double *d_stats);
 int bk_read_counters(hh_ctx *ctx, int64_t *n_fallback);
+// spots of every trajectory at dates 0..n_steps into the date-major grid of the LSM driver (hh_lsm.cu)
+int bk_path_grid_launch(hh_ctx *ctx, const hh_model *model, const hh_sim *sim, double *d_grid, int64_t grid_stride);
 // device -> the caller's pageable buffer through a pinned double buffer with parallel host copies (large outputs)
 int copy_to_pageable_host(hh_ctx *ctx, void *dst, const void *src_dev, size_t bytes, cudaStream_t st);
 }  // namespace hh

@@ -1176,9 +1176,12 @@ int lsm_american(hh_ctx *ctx, const hh_model *m, const hh_sim *s, const hh_payof
   // only true for the S-space BlackScholesExact generator — the only LSM configuration it tests.
   // BlackScholesExact is the drop-in configuration; the log-space EulerMaruyama / HestonNoise generators are accepted
   // too, with the corrected extraction S = exp(x) (lsm_logspace_paths_kernel).
+  // HestonBroadieKaya: the exact sampler writes the spots of its n_steps dates (bk_path_grid_launch, hh_bk.cu).
   const bool logspace = s->scheme == HH_SCHEME_EM;
-  if (!(m->kind == HH_MODEL_GBM && s->scheme == HH_SCHEME_EXACT_STEPS) && !logspace)
-    return ctx->fail(HH_ERR_UNSUPPORTED, "LSM runs on BlackScholesExact, EulerMaruyama or HestonNoise paths (SURVEY Q7)");
+  const bool bk = m->kind == HH_MODEL_HESTON && s->scheme == HH_SCHEME_HESTON_BK;
+  if (!(m->kind == HH_MODEL_GBM && s->scheme == HH_SCHEME_EXACT_STEPS) && !logspace && !bk)
+    return ctx->fail(HH_ERR_UNSUPPORTED, "LSM runs on BlackScholesExact, EulerMaruyama, HestonNoise or HestonBroadieKaya paths "
+                     "(SURVEY Q7)");
   if (s->precision != HH_PREC_F64) return ctx->fail(HH_ERR_UNSUPPORTED, "LSM paths are generated in binary64");
   if ((stop_idx == nullptr) != (stop_val == nullptr))
     return ctx->fail(HH_ERR_ARG, "stop_idx and stop_val must be both NULL or both non-NULL");
@@ -1268,7 +1271,10 @@ int lsm_american(hh_ctx *ctx, const hh_model *m, const hh_sim *s, const hh_payof
   HH_CUDA(ctx, cudaMemsetAsync(ctx->d_lsm_state.ptr, 0, fit_off + sizeof(LsmFit) * (size_t)(M + 1), st));
 
   HH_CUDA(ctx, cudaEventRecord(ctx->ev0, st));
-  if (logspace) {
+  if (bk) {
+    rc = bk_path_grid_launch(ctx, m, s, ctx->d_grid.as<double>(), stride);
+    if (rc) return rc;
+  } else if (logspace) {
     LsmLogArgs la;
     memset(&la, 0, sizeof la);
     la.b = pa;

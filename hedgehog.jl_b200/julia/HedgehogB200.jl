@@ -204,7 +204,7 @@ function Hedgehog.solve(prob::PricingProblem{VanillaOption{TS,TE,American,C,S},I
     stop_val = Vector{Float64}(undef, ncols)
     spot = Matrix{Float64}(undef, nsteps + 1, ncols)                        # column = trajectory, :50
     out = Ref(HHLsmResult(0, 0, 0, 0, 0, 0, 0, 0, 0))
-    with_sim(mc, scheme) do sim
+    with_sim(mc, scheme; dates_from_config = scheme == HH_SCHEME_HESTON_BK) do sim
         GC.@preserve stop_idx stop_val spot begin
             rc = ccall((:hh_lsm_american, LIB[]), Cint,
                        (Ptr{Cvoid}, Ref{HHModel}, Ref{HHSim}, Ref{HHPayoff}, Cint, Cdouble, Ptr{Cvoid}, Ref{HHLsmResult},

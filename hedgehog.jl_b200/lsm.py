@@ -18,7 +18,11 @@ def solve_lsm(prob, method, *, engine=None, shard=None, group=None, stopping_inf
     eng = engine or api.default_engine()
     shard, reduce = api._shard_and_reduce(shard, group)
     mdl = api._model_of(prob, mc)
-    sim = api._sim_of(mc, api._scheme_of(mc, for_lsm=True), shard)
+    scheme = api._scheme_of(mc, for_lsm=True)
+    if scheme == abi.HH_SCHEME_HESTON_BK:   # exact transitions between config.steps exercise dates
+        from dataclasses import replace
+        mc = replace(mc, bk_steps_from_config=True)
+    sim = api._sim_of(mc, scheme, shard)
     m = prob.market_inputs
     T = api.yearfrac(m.referenceDate, prob.payoff.expiry)                                 # lsm.jl:104
     step_discount = api.df(m.rate, api.add_yearfrac(m.referenceDate, T / sim.n_steps))   # lsm.jl:110

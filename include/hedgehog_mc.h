@@ -258,8 +258,10 @@ int hh_mc_path_dependent(hh_ctx *ctx, const hh_model *model, const hh_sim *sim, 
  * spot_paths: nullable, (n_steps+1) x ncols, column-major like the reference Matrix (:50);
  * comm: nullable; when set, the per-date regression moments are sum-allreduced across ranks.
  * sim->scheme: HH_SCHEME_EXACT_STEPS (LognormalDynamics + BlackScholesExact, the configuration the reference tests),
- * or HH_SCHEME_EM (log-GBM / log-Heston Euler-Maruyama) where every saved date holds S = exp(x): the reference takes
- * the saved component raw there (:53) and regresses on log-prices. Other schemes save no dates: HH_ERR_UNSUPPORTED. */
+ * HH_SCHEME_EM (log-GBM / log-Heston Euler-Maruyama) where every saved date holds S = exp(x): the reference takes
+ * the saved component raw there (:53) and regresses on log-prices; or HH_SCHEME_HESTON_BK: n_steps exercise dates
+ * simulated exactly (Bermudan exercise without time-stepping bias). HH_SCHEME_EXACT_TERMINAL saves no dates:
+ * HH_ERR_UNSUPPORTED. */
 int hh_lsm_american(hh_ctx *ctx, const hh_model *model, const hh_sim *sim, const hh_payoff *payoff,
                     int degree, double step_discount, const hh_comm *comm, hh_lsm_result *out,
                     int32_t *stop_idx, double *stop_val, double *spot_paths);

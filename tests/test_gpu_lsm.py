@@ -118,8 +118,9 @@ def test_lsm_edge_cases(cuda, oracle):
         cuda.lsm_american(m, SimSpec(n_paths=10, n_steps=5, scheme=abi.HH_SCHEME_EXACT_STEPS), (100.0, -1.0), 99, 0.99)
     with pytest.raises(NotImplementedError):  # the terminal-law sampler saves no dates: nothing to regress on
         cuda.lsm_american(m, SimSpec(n_paths=10, n_steps=5, scheme=abi.HH_SCHEME_EXACT_TERMINAL), (100.0, -1.0), 3, 0.99)
-    with pytest.raises(NotImplementedError):  # nor does Broadie-Kaya
-        cuda.lsm_american(heston_model(), SimSpec(n_paths=10, n_steps=5, scheme=abi.HH_SCHEME_HESTON_BK), (100.0, -1.0), 3, 0.99)
+    with pytest.raises(NotImplementedError):  # Q5: Antithetic + HestonBroadieKaya
+        cuda.lsm_american(heston_model(), SimSpec(n_paths=10, n_steps=5, scheme=abi.HH_SCHEME_HESTON_BK, vr=abi.HH_VR_ANTITHETIC),
+                          (100.0, -1.0), 3, 0.99)
     with pytest.raises(NotImplementedError):  # LSM grids are binary64
         cuda.lsm_american(heston_model(), SimSpec(n_paths=10, n_steps=5, scheme=abi.HH_SCHEME_EM, precision=abi.HH_PREC_F32),
                           (100.0, -1.0), 3, 0.99)
@@ -268,3 +269,39 @@ def test_lsm_heston_american_put_through_solve(cuda):
     assert sol.price > euro_put + 3 * sol.std_error
     bs_premium = A.crr_price(100.0, 100.0, 0.05, 0.2, T, 1000, cp=-1, american=True) - A.bs_price(100.0, 100.0, 0.05, 0.2, T, cp=-1)
     assert 0.4 * bs_premium < sol.price - euro_put < 2.0 * bs_premium
+
+
+# ---- exercise dates simulated exactly (HestonBroadieKaya) --------------------------------------------------------------
+
+def test_lsm_broadie_kaya_grid_is_the_european_path(cuda):
+    """The grid comes out of the same path kernel as hh_mc_european under HestonBroadieKaya: date 0 = S0, the last date is
+    bit-identical to the European terminal spots; tau in 1..dates."""
+    m = heston_model()
+    n, dates = 20_000, 6
+    sim = SimSpec(n_paths=n, n_steps=dates, scheme=abi.HH_SCHEME_HESTON_BK, base_seed=31)
+    out, tau, val, paths = cuda.lsm_american(m, sim, (100.0, -1.0), 3, math.exp(-m.r * m.T / dates), want_stopping=True, want_paths=True)
+    _, term = cuda.mc_european(m, sim, [(100.0, 1.0)], 1.0, want_terminal=True)
+    assert paths.shape == (n, dates + 1)
+    assert np.all(paths[:, 0] == m.S0) and np.array_equal(paths[:, -1], term) and np.all(paths > 0)
+    assert tau.min() >= 1 and tau.max() == dates and out.n == n
+    with pytest.raises(NotImplementedError):  # Broadie-Kaya draws in-kernel only
+        cuda.lsm_american(m, SimSpec(n_paths=10, n_steps=3, scheme=abi.HH_SCHEME_HESTON_BK, rng_mode=abi.HH_RNG_NORMALS,
+                                     normals=np.zeros((10, 3, 2))), (100.0, -1.0), 2, 0.99)
+
+
+def test_lsm_broadie_kaya_bermudan_put_through_solve(cuda):
+    """Monthly-exercisable put under Heston: exact transitions between the 12 exercise dates against Euler-Maruyama with
+    the same 12 dates (coarse steps, so only loosely equal), and above the European put (Carr-Madan)."""
+    from oracle import anchors as A
+    ref, exp = dt.date(2020, 1, 1), dt.date(2021, 1, 1)
+    T = 366 / 365
+    mk = hh.HestonInputs(ref, 0.05, 100.0, 0.04, 2.0, 0.04, 0.3, -0.7)
+    put = hh.PricingProblem(hh.VanillaOption(100.0, exp, hh.American(), hh.Put(), hh.Spot()), mk)
+    bk = hh.solve(put, hh.LSM(hh.HestonDynamics(), hh.HestonBroadieKaya(), hh.SimulationConfig(400_000, steps=12, base_seed=3), 3),
+                  engine=cuda, stopping_info=False)
+    em = hh.solve(put, hh.LSM(hh.HestonDynamics(), hh.EulerMaruyama(), hh.SimulationConfig(400_000, steps=12, base_seed=4), 3),
+                  engine=cuda, stopping_info=False)
+    euro_put = A.heston_price(100.0, 100.0, 0.05, T, 0.04, 2.0, 0.04, 0.3, -0.7) - 100.0 + 100.0 * math.exp(-0.05 * T)
+    assert bk.price > euro_put + 3 * bk.std_error
+    assert abs(bk.price - em.price) < 0.02 * bk.price
+    assert bk.stats["n_cols_total"] == 400_000
