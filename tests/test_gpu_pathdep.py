@@ -195,3 +195,21 @@ def test_broadie_kaya_asian_agrees_with_fine_euler_maruyama(cuda):
                                                           hh.SimulationConfig(2_000_000, steps=480, base_seed=6), ensemble=False), engine=cuda)
     for a, b in zip(bk, em):
         assert abs(a.price - b.price) < 4.0 * math.hypot(a.std_error, b.std_error) + 5e-3 * b.price, (a.price, b.price, a.std_error, b.std_error)
+
+
+def test_results_are_reproducible_and_shard_additive(cuda):
+    """Fixed-order reductions: the same call twice gives bit-identical sums; two shards of the global trajectory index
+    (path_offset) add up to the whole job's sums to rounding, statistics concatenate exactly."""
+    m = heston_model()
+    pays = [c for c in ALL_KINDS]
+    whole = SimSpec(n_paths=30_000, n_steps=20, scheme=abi.HH_SCHEME_EM, base_seed=77)
+    r1, s1 = cuda.mc_path_dependent(m, whole, pays, 1.0, 4, want_stats=True)
+    r2, s2 = cuda.mc_path_dependent(m, whole, pays, 1.0, 4, want_stats=True)
+    assert all(a.sum == b.sum and a.sumsq == b.sumsq for a, b in zip(r1, r2)) and np.array_equal(s1, s2)
+    lo = SimSpec(n_paths=12_345, n_steps=20, scheme=abi.HH_SCHEME_EM, base_seed=77, path_offset=0)
+    hi = SimSpec(n_paths=30_000 - 12_345, n_steps=20, scheme=abi.HH_SCHEME_EM, base_seed=77, path_offset=12_345)
+    ra, sa = cuda.mc_path_dependent(m, lo, pays, 1.0, 4, want_stats=True)
+    rb, sb = cuda.mc_path_dependent(m, hi, pays, 1.0, 4, want_stats=True)
+    assert np.array_equal(np.concatenate([sa, sb], axis=1), s1)
+    for a, b, w in zip(ra, rb, r1):
+        assert a.sum + b.sum == pytest.approx(w.sum, rel=1e-13)
