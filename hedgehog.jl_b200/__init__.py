@@ -14,4 +14,4 @@ from .greeks import (BatchGreekProblem, FDBackward, FDCentral, FDForward, FieldL
 from .greeks import set as set_lens  # noqa: F401
 from .calibration import CalibrationProblem, CalibrationResult, OptimizerAlgo, RootFinderAlgo, basket_prices_and_jacobian  # noqa: F401,E402
 from .pathdep import (ArithmeticAverage, AsianOption, AssetOrNothing, BarrierOption, CashOrNothing, DigitalOption, Down,  # noqa: F401,E402
-                      GeometricAverage, KnockIn, KnockOut, Monitoring, Up)
+                      GeometricAverage, GeometricControlVariate, KnockIn, KnockOut, Monitoring, Up)

@@ -71,6 +71,7 @@ __device__ __forceinline__ double pd_payoff(const PdPayoff &c, double ST, double
   switch (c.kind) {
     case HH_PD_ASIAN_ARITH: return fmax(c.cp * (A - c.strike), 0.0);
     case HH_PD_ASIAN_GEOM: return fmax(c.cp * (G - c.strike), 0.0);
+    case HH_PD_ASIAN_ARITH_MINUS_GEOM: return fmax(c.cp * (A - c.strike), 0.0) - fmax(c.cp * (G - c.strike), 0.0);
     case HH_PD_UP_OUT: return mx >= c.log_barrier ? c.amount : vanilla;
     case HH_PD_UP_IN: return mx >= c.log_barrier ? vanilla : c.amount;
     case HH_PD_DOWN_OUT: return mn <= c.log_barrier ? c.amount : vanilla;
@@ -530,7 +531,7 @@ int path_dependent(hh_ctx *ctx, const hh_model *m, const hh_sim *s, int monitor_
     host[k].log_barrier = barrier ? log(q.barrier) : 0.0;
     host[k].amount = q.amount;
     host[k].barrier = q.barrier;
-    arith = arith || q.kind == HH_PD_ASIAN_ARITH;
+    arith = arith || q.kind == HH_PD_ASIAN_ARITH || q.kind == HH_PD_ASIAN_ARITH_MINUS_GEOM;
   }
   const int64_t N = s->n_paths;
   const bool anti = s->vr == HH_VR_ANTITHETIC;

@@ -235,7 +235,7 @@ end
 struct DigitalOption{TS,TE,C<:Hedgehog.AbstractCallPut} <: PathDependentPayoff
     strike::TS; expiry::TE; call_put::C; cash::Union{Nothing,TS}; monitor_every::Int   # cash === nothing: asset-or-nothing
 end
-hh_path_payoff(p::AsianOption) = HHPathPayoff(p.geometric ? 2 : 1, 0, p.strike, p.call_put(), 0.0, 0.0)
+hh_path_payoff(p::AsianOption) = HHPathPayoff(p.geometric ? 2 : 1, 0, p.strike, p.call_put(), 0.0, 0.0)   # kind 9: arithmetic - geometric (control variate)
 hh_path_payoff(p::BarrierOption) =
     HHPathPayoff(p.up ? (p.knock_out ? 3 : 4) : (p.knock_out ? 5 : 6), 0, p.strike, p.call_put(), p.barrier, p.rebate)
 hh_path_payoff(p::DigitalOption) =

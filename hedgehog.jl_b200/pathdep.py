@@ -19,6 +19,12 @@ from . import api
 
 # ---- modifiers ----------------------------------------------------------------------------------------------------------
 class ArithmeticAverage: pass
+
+
+class GeometricControlVariate:
+    """Control variate for the arithmetic Asian under Black-Scholes (roadmap "control variates"): the kernel
+    accumulates the payoff DIFFERENCE arithmetic - geometric on the same trajectories (correlation ~0.999) and the host
+    adds the closed-form price of the discretely monitored geometric Asian."""
 class GeometricAverage: pass
 class Up: pass
 class Down: pass
@@ -58,12 +64,19 @@ class AsianOption(_PathPayoff):
     averaging: Any
     monitoring: Monitoring
 
-    def __init__(self, strike, expiry_date, call_put, averaging=None, monitoring=None):
+    control_variate: Any
+
+    def __init__(self, strike, expiry_date, call_put, averaging=None, monitoring=None, control_variate=None):
         self._base(strike, expiry_date, call_put, monitoring)
         object.__setattr__(self, "averaging", averaging or ArithmeticAverage())
+        object.__setattr__(self, "control_variate", control_variate)
+        if control_variate is not None and isinstance(self.averaging, GeometricAverage):
+            raise ValueError("the geometric Asian has a closed form; the control variate applies to the arithmetic average")
 
     def abi_tuple(self):
         kind = abi.HH_PD_ASIAN_GEOM if isinstance(self.averaging, GeometricAverage) else abi.HH_PD_ASIAN_ARITH
+        if self.control_variate is not None:
+            kind = abi.HH_PD_ASIAN_ARITH_MINUS_GEOM
         return (kind, self.strike, self.call_put(), 0.0, 0.0)
 
 
@@ -113,6 +126,19 @@ class DigitalOption(_PathPayoff):
         return (abi.HH_PD_DIGITAL_CASH, self.strike, self.call_put(), 0.0, self.payout.amount)
 
 
+def geometric_asian_closed_form(S, K, r, sigma, T, m, cp):
+    """Discretely monitored geometric-average option under Black-Scholes, dates i T / m, i = 1..m: log G is normal with
+    mean log S + (r - sigma^2/2) T (m+1)/(2m) and variance sigma^2 T (m+1)(2m+1)/(6 m^2)."""
+    from statistics import NormalDist
+    N = NormalDist().cdf
+    mu = math.log(S) + (r - 0.5 * sigma * sigma) * T * (m + 1) / (2 * m)
+    v = sigma * sigma * T * (m + 1) * (2 * m + 1) / (6 * m * m)
+    sv = math.sqrt(v)
+    d2 = (mu - math.log(K)) / sv
+    d1 = d2 + sv
+    return math.exp(-r * T) * cp * (math.exp(mu + 0.5 * v) * N(cp * d1) - K * N(cp * d2))
+
+
 def _abi_tuple(p):
     if isinstance(p, api.VanillaOption):
         if not isinstance(p.exercise_style, api.European) or not isinstance(p.underlying, api.Spot):
@@ -151,10 +177,17 @@ def solve_path_dependent(payoffs: Sequence, market_inputs, method, *, engine=Non
     if reduce is not None:
         sums = reduce(sums)
     out = []
-    for s, q, n in sums:
+    for p, (s, q, n) in zip(payoffs, sums):
         mean = s / n
         var = max((q - n * mean * mean) / (n - 1), 0.0) if n > 1 else 0.0
-        out.append((discount * mean, discount * math.sqrt(var / n)))
+        price = discount * mean
+        if getattr(p, "control_variate", None) is not None:
+            if not isinstance(market_inputs, api.BlackScholesInputs):
+                raise TypeError("GeometricControlVariate needs the closed-form geometric Asian: BlackScholesInputs only")
+            T = api.yearfrac(market_inputs.referenceDate, p.expiry)
+            price += geometric_asian_closed_form(market_inputs.spot, p.strike, api.zero_rate(market_inputs.rate, 0.0),
+                                                 api.get_vol(market_inputs.sigma), T, sim.n_steps // every, p.call_put())
+        out.append((price, discount * math.sqrt(var / n)))
     stats = {"kernel_ms": results[0].kernel_ms, "n_nonfinite": results[0].n_nonfinite, "n_local": sim.n_paths,
              "n_total": int(sums[0][2])}
     return out, stats

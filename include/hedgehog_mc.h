@@ -232,7 +232,10 @@ int hh_mc_european_tangent_sums(hh_ctx *ctx, const hh_model *model, const hh_tan
 #define HH_PD_DOWN_IN 6        /* vanilla if min S <= barrier, else `amount` */
 #define HH_PD_DIGITAL_CASH 7   /* `amount` if cp (S_T - K) > 0 */
 #define HH_PD_DIGITAL_ASSET 8  /* S_T if cp (S_T - K) > 0 */
-#define HH_PD_NKINDS 9
+#define HH_PD_ASIAN_ARITH_MINUS_GEOM 9 /* max(cp (A - K), 0) - max(cp (G - K), 0): the arithmetic Asian with the geometric one \
+                                          as a control variate (roadmap "control variates"): the host adds the \
+                                          closed-form geometric price under Black-Scholes */
+#define HH_PD_NKINDS 10
 #define HH_PD_NSTATS 5         /* per column: S_T, A, G, max S, min S over the monitoring dates */
 typedef struct hh_path_payoff {
   int32_t kind; /* HH_PD_* */

@@ -394,6 +394,7 @@ static double pd_payoff_of(const hh_path_payoff *c, const double *st) {
   switch (c->kind) {
     case HH_PD_ASIAN_ARITH: return fmax(c->cp * (A - c->strike), 0.0);
     case HH_PD_ASIAN_GEOM: return fmax(c->cp * (G - c->strike), 0.0);
+    case HH_PD_ASIAN_ARITH_MINUS_GEOM: return fmax(c->cp * (A - c->strike), 0.0) - fmax(c->cp * (G - c->strike), 0.0);
     case HH_PD_UP_OUT: return mx >= c->barrier ? c->amount : vanilla;
     case HH_PD_UP_IN: return mx >= c->barrier ? vanilla : c->amount;
     case HH_PD_DOWN_OUT: return mn <= c->barrier ? c->amount : vanilla;

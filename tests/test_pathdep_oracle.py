@@ -20,7 +20,7 @@ ALL_KINDS = [(abi.HH_PD_VANILLA, 100.0, 1.0, 0.0, 0.0), (abi.HH_PD_ASIAN_ARITH, 
              (abi.HH_PD_ASIAN_GEOM, 95.0, -1.0, 0.0, 0.0), (abi.HH_PD_UP_OUT, 100.0, 1.0, 120.0, 1.5),
              (abi.HH_PD_UP_IN, 100.0, 1.0, 120.0, 0.0), (abi.HH_PD_DOWN_OUT, 100.0, -1.0, 85.0, 0.0),
              (abi.HH_PD_DOWN_IN, 100.0, -1.0, 85.0, 0.5), (abi.HH_PD_DIGITAL_CASH, 105.0, 1.0, 0.0, 10.0),
-             (abi.HH_PD_DIGITAL_ASSET, 105.0, -1.0, 0.0, 0.0)]
+             (abi.HH_PD_DIGITAL_ASSET, 105.0, -1.0, 0.0, 0.0), (abi.HH_PD_ASIAN_ARITH_MINUS_GEOM, 100.0, 1.0, 0.0, 0.0)]
 
 
 def numpy_stats(m, z, every, heston):
@@ -54,7 +54,8 @@ def numpy_payoff(c, st):
             abi.HH_PD_ASIAN_GEOM: np.maximum(cp * (G - K), 0.0), abi.HH_PD_UP_OUT: np.where(mx >= B, amt, van),
             abi.HH_PD_UP_IN: np.where(mx >= B, van, amt), abi.HH_PD_DOWN_OUT: np.where(mn <= B, amt, van),
             abi.HH_PD_DOWN_IN: np.where(mn <= B, van, amt), abi.HH_PD_DIGITAL_CASH: np.where(cp * (ST - K) > 0, amt, 0.0),
-            abi.HH_PD_DIGITAL_ASSET: np.where(cp * (ST - K) > 0, ST, 0.0)}[kind]
+            abi.HH_PD_DIGITAL_ASSET: np.where(cp * (ST - K) > 0, ST, 0.0),
+            abi.HH_PD_ASIAN_ARITH_MINUS_GEOM: np.maximum(cp * (Am - K), 0.0) - np.maximum(cp * (G - K), 0.0)}[kind]
 
 
 @pytest.mark.parametrize("model", ["gbm", "heston"])
@@ -134,3 +135,25 @@ def test_monitoring_edge_cases(oracle):
         hh.solve(hh.BasketPricingProblem([hh.AsianOption(100.0, EXP, hh.Call()), hh.AsianOption(100.0, EXP, hh.Call(), monitoring=hh.Monitoring(2))],
                                          hh.BlackScholesInputs(REF, 0.05, 100.0, 0.2)),
                  hh.MonteCarlo(hh.LognormalDynamics(), hh.EulerMaruyama(), hh.SimulationConfig(100, steps=4)), engine=oracle)
+
+
+def test_geometric_control_variate_for_the_arithmetic_asian(oracle):
+    """Roadmap "control variates" (SURVEY N3): arithmetic - geometric on common trajectories plus the closed-form geometric
+    price. Same expectation as the plain estimator (3.5 sigma), standard error more than 10x smaller; the closed form on
+    the product side equals the oracle's anchor."""
+    from hedgehog_jl_b200.pathdep import geometric_asian_closed_form
+    mk = hh.BlackScholesInputs(REF, 0.05, 100.0, 0.2)
+    mc = hh.MonteCarlo(hh.LognormalDynamics(), hh.EulerMaruyama(), hh.SimulationConfig(100_000, steps=50, base_seed=3))
+    ps = [hh.AsianOption(100.0, EXP, hh.Call()), hh.AsianOption(100.0, EXP, hh.Call(), control_variate=hh.GeometricControlVariate()),
+          hh.AsianOption(95.0, EXP, hh.Put()), hh.AsianOption(95.0, EXP, hh.Put(), control_variate=hh.GeometricControlVariate())]
+    plain_c, cv_c, plain_p, cv_p = hh.solve(hh.BasketPricingProblem(ps, mk), mc, engine=oracle)
+    for plain, cv in ((plain_c, cv_c), (plain_p, cv_p)):
+        assert abs(plain.price - cv.price) < 3.5 * plain.std_error
+        assert cv.std_error < 0.1 * plain.std_error
+    assert geometric_asian_closed_form(100.0, 95.0, 0.05, 0.2, T, 50, -1.0) == pytest.approx(
+        A.geometric_asian_price(100.0, 95.0, 0.05, 0.2, T, 50, cp=-1.0), rel=1e-13)
+    with pytest.raises(TypeError):   # no closed form under Heston
+        hh.solve(hh.PricingProblem(ps[1], hh.HestonInputs(REF, 0.03, 100.0, 0.04, 2.0, 0.04, 0.3, -0.7)),
+                 hh.MonteCarlo(hh.HestonDynamics(), hh.EulerMaruyama(), hh.SimulationConfig(1000, steps=10)), engine=oracle)
+    with pytest.raises(ValueError):
+        hh.AsianOption(100.0, EXP, hh.Call(), hh.GeometricAverage(), control_variate=hh.GeometricControlVariate())
