@@ -31,7 +31,7 @@
 namespace hh {
 
 constexpr int kBkThreads = 128;
-constexpr int kBkDefaultMinb = 4;
+constexpr int kBkDefaultMinb = 3;
 constexpr int kBkTable = 32;  // table entries per thread in shared memory (32 KB per block); longer series (mean 12.3 at C4) spill to the HBM slab
 
 // terminal spots -> payoff sums (hh_european.cu)
