@@ -13,5 +13,5 @@ from .greeks import (BatchGreekProblem, FDBackward, FDCentral, FDForward, FieldL
                      strike_grid_greeks)
 from .greeks import set as set_lens  # noqa: F401
 from .calibration import CalibrationProblem, CalibrationResult, OptimizerAlgo, RootFinderAlgo, basket_prices_and_jacobian  # noqa: F401,E402
-from .pathdep import (ArithmeticAverage, AsianOption, AssetOrNothing, BarrierOption, CashOrNothing, DigitalOption, Down,  # noqa: F401,E402
+from .pathdep import (ArithmeticAverage, AsianOption, BlackScholesControlVariate, AssetOrNothing, BarrierOption, CashOrNothing, DigitalOption, Down,  # noqa: F401,E402
                       GeometricAverage, GeometricControlVariate, KnockIn, KnockOut, Monitoring, Up)

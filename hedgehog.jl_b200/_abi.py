@@ -59,8 +59,8 @@ class hh_payoff(C.Structure):
 
 # hh_mc_path_dependent (include/hedgehog_mc.h): payoff kinds and per-column statistics
 (HH_PD_VANILLA, HH_PD_ASIAN_ARITH, HH_PD_ASIAN_GEOM, HH_PD_UP_OUT, HH_PD_UP_IN, HH_PD_DOWN_OUT, HH_PD_DOWN_IN,
- HH_PD_DIGITAL_CASH, HH_PD_DIGITAL_ASSET, HH_PD_ASIAN_ARITH_MINUS_GEOM) = range(10)
-HH_PD_NKINDS = 10
+ HH_PD_DIGITAL_CASH, HH_PD_DIGITAL_ASSET, HH_PD_ASIAN_ARITH_MINUS_GEOM, HH_PD_BS_CONTROL, HH_PD_VANILLA_MINUS_BS) = range(12)
+HH_PD_NKINDS = 12
 HH_PD_NSTATS = 5
 
 

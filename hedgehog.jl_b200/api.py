@@ -197,6 +197,7 @@ class MonteCarlo:  # montecarlo.jl:127-131
     ensemble: bool = True             # materialise MonteCarloSolution.ensemble (terminal prices) on the host
     normals: Optional[np.ndarray] = None  # parity mode: pre-generated standard normals [path, step, comp]
     bk_steps_from_config: bool = False    # False: exact strategies ignore `steps` like the reference (Q6)
+    control_variate: Any = None           # pathdep.BlackScholesControlVariate(): Heston + EulerMaruyama vanilla prices
 
 
 B200MonteCarlo = MonteCarlo
@@ -391,6 +392,8 @@ def solve(prob, method, *args, engine=None, shard=None, group=None, **kw):
     if isinstance(method, MonteCarlo):
         if not isinstance(prob.payoff.exercise_style, European):
             raise TypeError("solve(::PricingProblem, ::MonteCarlo) is defined for European exercise; use LSM")
+        if method.control_variate is not None:
+            return _pd.solve_bs_control(prob, method, engine=engine, shard=shard, group=group)
         (price_se,), ens, stats = _solve_european(prob, method, engine, shard, group)
         return MonteCarloSolution(prob, method, price_se[0], ens, price_se[1], stats)
     raise TypeError(f"no B200 solve for method {type(method).__name__}")

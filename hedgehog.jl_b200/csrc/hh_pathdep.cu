@@ -26,6 +26,7 @@ namespace hh {
 
 constexpr int kPdThreads = 512;
 constexpr int kPdStats = HH_PD_NSTATS;
+constexpr int kPdStage = HH_PD_NSTATS + 1;  // staged per column: the statistics and the control's terminal spot
 constexpr int kPdAcc = 3;  // sum, sumsq, nonfinite
 
 struct PdPayoff {  // device form of hh_path_payoff: the barrier in log space (stepping kernels) and as given
@@ -42,6 +43,8 @@ struct PdArgs {
   double *stats;     // nullable: [kPdStats][ncols]
   int npay, kp_log2, n_steps, monitor_every, split;
   double inv_m;      // 1 / number of monitoring dates
+  int cv_on;         // advance the Black-Scholes control trajectory (HH_PD_BS_CONTROL / HH_PD_VANILLA_MINUS_BS requested)
+  double cv_sigma, cv_drift;  // its volatility and (r - sigma_cv^2 / 2) dt
   PathParams<double> p;
   HestonFolded f;  // folded step constants of the native-RNG Heston kernel
   PhiloxRoundKeys rk;
@@ -66,7 +69,7 @@ struct PdRunning {
   }
 };
 
-__device__ __forceinline__ double pd_payoff(const PdPayoff &c, double ST, double A, double G, double mx, double mn) {
+__device__ __forceinline__ double pd_payoff(const PdPayoff &c, double ST, double A, double G, double mx, double mn, double Scv) {
   const double vanilla = fmax(c.cp * (ST - c.strike), 0.0);  // payoffs.jl:154-156
   switch (c.kind) {
     case HH_PD_ASIAN_ARITH: return fmax(c.cp * (A - c.strike), 0.0);
@@ -78,6 +81,8 @@ __device__ __forceinline__ double pd_payoff(const PdPayoff &c, double ST, double
     case HH_PD_DOWN_IN: return mn <= c.log_barrier ? vanilla : c.amount;
     case HH_PD_DIGITAL_CASH: return c.cp * (ST - c.strike) > 0.0 ? c.amount : 0.0;
     case HH_PD_DIGITAL_ASSET: return c.cp * (ST - c.strike) > 0.0 ? ST : 0.0;
+    case HH_PD_BS_CONTROL: return fmax(c.cp * (Scv - c.strike), 0.0);
+    case HH_PD_VANILLA_MINUS_BS: return vanilla - c.amount * fmax(c.cp * (Scv - c.strike), 0.0);
     default: return vanilla;
   }
 }
@@ -87,8 +92,8 @@ __device__ __forceinline__ double pd_payoff(const PdPayoff &c, double ST, double
 // strike grid. Called by all threads of the block (it synchronises).
 template <bool ANTI, bool ARITH, int THREADS>
 __device__ __forceinline__ void pd_stage_and_pay(const PdArgs &a, double *stage, int tid, int64_t i, int64_t base, double xp,
-                                                 double xm, const PdRunning &rp, const PdRunning &rm, const PdPayoff &mine,
-                                                 int k, int g, int G, double *acc) {
+                                                 double xm, double xbp, double xbm, const PdRunning &rp, const PdRunning &rm,
+                                                 const PdPayoff &mine, int k, int g, int G, double *acc) {
   constexpr int NSIDE = ANTI ? 2 : 1;
   const double ST = exp(xp);  // final_sample, montecarlo.jl:398
   stage[(0 * NSIDE + 0) * THREADS + tid] = ST;
@@ -96,6 +101,7 @@ __device__ __forceinline__ void pd_stage_and_pay(const PdArgs &a, double *stage,
   stage[(2 * NSIDE + 0) * THREADS + tid] = exp(rp.sum_x * a.inv_m);
   stage[(3 * NSIDE + 0) * THREADS + tid] = rp.max_x;
   stage[(4 * NSIDE + 0) * THREADS + tid] = rp.min_x;
+  stage[(5 * NSIDE + 0) * THREADS + tid] = a.cv_on ? exp(xbp) : 0.0;
   if (ANTI) {
     const double STm = exp(xm);
     stage[(0 * NSIDE + 1) * THREADS + tid] = STm;
@@ -103,6 +109,7 @@ __device__ __forceinline__ void pd_stage_and_pay(const PdArgs &a, double *stage,
     stage[(2 * NSIDE + 1) * THREADS + tid] = exp(rm.sum_x * a.inv_m);
     stage[(3 * NSIDE + 1) * THREADS + tid] = rm.max_x;
     stage[(4 * NSIDE + 1) * THREADS + tid] = rm.min_x;
+    stage[(5 * NSIDE + 1) * THREADS + tid] = a.cv_on ? exp(xbm) : 0.0;
   }
   if (a.stats && i < a.n) {  // S_T, A, G, max S, min S
     const int64_t ncols = a.n * NSIDE;
@@ -123,12 +130,14 @@ __device__ __forceinline__ void pd_stage_and_pay(const PdArgs &a, double *stage,
     for (int j = g; j < nvalid; j += G) {
       const double sT = stage[(0 * NSIDE + 0) * THREADS + j];
       double pay = pd_payoff(mine, sT, stage[(1 * NSIDE + 0) * THREADS + j], stage[(2 * NSIDE + 0) * THREADS + j],
-                             stage[(3 * NSIDE + 0) * THREADS + j], stage[(4 * NSIDE + 0) * THREADS + j]);
+                             stage[(3 * NSIDE + 0) * THREADS + j], stage[(4 * NSIDE + 0) * THREADS + j],
+                             stage[(5 * NSIDE + 0) * THREADS + j]);
       bool bad = !isfinite(sT);
       if (ANTI) {
         const double sTm = stage[(0 * NSIDE + 1) * THREADS + j];
         const double paym = pd_payoff(mine, sTm, stage[(1 * NSIDE + 1) * THREADS + j], stage[(2 * NSIDE + 1) * THREADS + j],
-                                      stage[(3 * NSIDE + 1) * THREADS + j], stage[(4 * NSIDE + 1) * THREADS + j]);
+                                      stage[(3 * NSIDE + 1) * THREADS + j], stage[(4 * NSIDE + 1) * THREADS + j],
+                                      stage[(5 * NSIDE + 1) * THREADS + j]);
         pay = 0.5 * (pay + paym);  // reduce_payoffs, montecarlo.jl:430-432
         bad = bad || !isfinite(sTm);
       }
@@ -157,7 +166,7 @@ __device__ __forceinline__ void pd_block_reduce(const PdArgs &a, double *stage, 
 }
 
 constexpr int kPdTableBytes = kLogRepBytes + kTrigRepBytes + kExpFullBytes + kExp2Bytes;
-constexpr int kPdStageDoubles = kPdStats * 2 * kPdThreads;  // also holds the kPdAcc * kPdThreads of the final reduction
+constexpr int kPdStageDoubles = kPdStage * 2 * kPdThreads;  // also holds the kPdAcc * kPdThreads of the final reduction
 constexpr int kPdSmem = ((kPdTableBytes + 15) & ~15) + kPdStageDoubles * 8;
 
 template <bool HESTON, bool ANTI, bool PARITY, bool UKEY, bool ARITH>
@@ -201,6 +210,7 @@ __global__ void __launch_bounds__(kPdThreads, 2) pathdep_kernel(const PdArgs a) 
   for (int64_t base = (int64_t)blockIdx.x * kPdThreads; base < a.n; base += (int64_t)gridDim.x * kPdThreads) {
     const int64_t i = base + tid;
     double xp = p.x0, xm = p.x0, vp = p.v0, vm = p.v0;
+    double xbp = p.x0, xbm = p.x0;  // Black-Scholes control on the same dW1 (a.cv_on)
     PdRunning rp, rm;
     rp.reset();
     rm.reset();
@@ -228,6 +238,10 @@ __global__ void __launch_bounds__(kPdThreads, 2) pathdep_kernel(const PdArgs a) 
           const double dW2 = fma(p.a22, z2, p.a21 * z1);
           heston_em_step<double>(p, split, xp, vp, dW1, dW2);
           if (ANTI) heston_em_step<double>(p, split, xm, vm, -dW1, -dW2);  // NoiseGrid(t, -W), montecarlo.jl:258
+          if (a.cv_on) {
+            xbp = fma(a.cv_sigma, dW1, xbp + a.cv_drift);
+            if (ANTI) xbm = fma(a.cv_sigma, -dW1, xbm + a.cv_drift);
+          }
           if (--due == 0) {
             due = every;
             rp.monitor<ARITH, !PARITY>(xp, s_expf);
@@ -261,7 +275,7 @@ __global__ void __launch_bounds__(kPdThreads, 2) pathdep_kernel(const PdArgs a) 
         }
       }
     }
-    pd_stage_and_pay<ANTI, ARITH, kPdThreads>(a, stage, tid, i, base, xp, xm, rp, rm, mine, k, g, G, acc);
+    pd_stage_and_pay<ANTI, ARITH, kPdThreads>(a, stage, tid, i, base, xp, xm, xbp, xbm, rp, rm, mine, k, g, G, acc);
   }
   pd_block_reduce<kPdThreads>(a, stage, tid, G, acc);
 }
@@ -273,7 +287,7 @@ __global__ void __launch_bounds__(kPdThreads, 2) pathdep_kernel(const PdArgs a) 
 // Shared memory: [staging | log table x8 | phase table x8 | T_j | exponent table]; THREADS = 1024 for plain runs with the
 // uniform key (<= 64 registers), 512 otherwise (antithetic pairs / per-trajectory keys need the registers).
 template <bool ANTI, int THREADS>
-__host__ __device__ constexpr int pd_fast_stage_bytes() { return kPdStats * (ANTI ? 2 : 1) * THREADS * 8; }
+__host__ __device__ constexpr int pd_fast_stage_bytes() { return kPdStage * (ANTI ? 2 : 1) * THREADS * 8; }
 template <bool ANTI, int THREADS>
 __host__ __device__ constexpr int pd_fast_smem() {
   return pd_fast_stage_bytes<ANTI, THREADS>() + kLogRepBytes + kPhaseRepBytes + kExpFullBytes + kExp2Bytes;
@@ -321,6 +335,7 @@ __global__ void __launch_bounds__(THREADS, 1) pathdep_heston_fast_kernel(const P
     const int64_t i = base + tid;
     const int64_t ic = i < a.n ? i : a.n - 1;  // tail lanes repeat the last trajectory; never accumulated
     double xp = a.p.x0, xm = a.p.x0, vp = a.p.v0, vm = a.p.v0;
+    double xbp = a.p.x0, xbm = a.p.x0;  // Black-Scholes control on the same dW1 (a.cv_on)
     PdRunning rp, rm;
     rp.reset();
     rm.reset();
@@ -360,13 +375,18 @@ __global__ void __launch_bounds__(THREADS, 1) pathdep_heston_fast_kernel(const P
         xm = fma(-sr, cc1, K1);
         vm = fma(-sr, cc2, K2);
       }
+      if (a.cv_on) {  // dW1 = rad cc1 with the Box-Muller radius, which the Heston step itself never forms
+        const double dW1 = fast_sqrt_pos5(max_tiny_hi(R2)) * cc1;
+        xbp = fma(a.cv_sigma, dW1, xbp + a.cv_drift);
+        if (ANTI) xbm = fma(a.cv_sigma, -dW1, xbm + a.cv_drift);
+      }
       if (--due == 0) {
         due = every;
         rp.monitor<ARITH, true>(xp, s_expf);
         if (ANTI) rm.monitor<ARITH, true>(xm, s_expf);
       }
     }
-    pd_stage_and_pay<ANTI, ARITH, THREADS>(a, stage, tid, i, base, xp, xm, rp, rm, mine, k, g, G, acc);
+    pd_stage_and_pay<ANTI, ARITH, THREADS>(a, stage, tid, i, base, xp, xm, xbp, xbm, rp, rm, mine, k, g, G, acc);
   }
   pd_block_reduce<THREADS>(a, stage, tid, G, acc);
 }
@@ -391,7 +411,7 @@ __global__ void __launch_bounds__(256) pathdep_from_stats_kernel(const double *_
   if (k < npay) {
     for (int64_t j = (int64_t)blockIdx.x * G + g; j < n; j += (int64_t)gridDim.x * G) {
       const double ST = stats[j];
-      const double pay = pd_payoff(mine, ST, stats[n + j], stats[2 * n + j], stats[3 * n + j], stats[4 * n + j]);
+      const double pay = pd_payoff(mine, ST, stats[n + j], stats[2 * n + j], stats[3 * n + j], stats[4 * n + j], 0.0);
       acc[0] += pay;
       acc[1] = fma(pay, pay, acc[1]);
       if (k == 0 && !isfinite(ST)) acc[2] += 1.0;
@@ -481,6 +501,14 @@ static cudaError_t pd_fast(const PdArgs &a, bool anti, bool arith, bool ukey, in
 #undef HH_PD_FAST
 }
 
+// sigma_cv^2 of the Black-Scholes control: the mean of E[V_t] = theta + (V0 - theta) e^(-kappa t) over [0, T]
+static double bs_control_variance(const hh_model *m) {
+  const double kT = m->kappa * m->T;
+  const double w = fabs(kT) > 1e-8 ? -expm1(-kT) / kT : 1.0 - 0.5 * kT;
+  const double v = m->theta + (m->V0 - m->theta) * w;
+  return v > 1e-12 ? v : 1e-12;
+}
+
 static void fill_results(hh_result *results, const std::vector<double> &fin, int npay, int64_t N, double discount, float ms,
                          int64_t n_fallback) {
   for (int k = 0; k < npay; ++k) {
@@ -517,7 +545,7 @@ int path_dependent(hh_ctx *ctx, const hh_model *m, const hh_sim *s, int monitor_
   const int M = s->n_steps;
   if (monitor_every < 1 || M % monitor_every != 0)
     return ctx->fail(HH_ERR_ARG, "n_steps (%d) must be a positive multiple of monitor_every (%d)", M, monitor_every);
-  bool arith = path_stats != nullptr;
+  bool arith = path_stats != nullptr, cv = false;
   std::vector<PdPayoff> host((size_t)npay);
   for (int k = 0; k < npay; ++k) {
     const hh_path_payoff &q = payoffs[k];
@@ -532,6 +560,11 @@ int path_dependent(hh_ctx *ctx, const hh_model *m, const hh_sim *s, int monitor_
     host[k].amount = q.amount;
     host[k].barrier = q.barrier;
     arith = arith || q.kind == HH_PD_ASIAN_ARITH || q.kind == HH_PD_ASIAN_ARITH_MINUS_GEOM;
+    if (q.kind == HH_PD_BS_CONTROL || q.kind == HH_PD_VANILLA_MINUS_BS) {
+      if (!heston || s->scheme != HH_SCHEME_EM)
+        return ctx->fail(HH_ERR_ARG, "payoff %d: the Black-Scholes control variate runs next to HestonDynamics + EulerMaruyama", k);
+      cv = true;
+    }
   }
   const int64_t N = s->n_paths;
   const bool anti = s->vr == HH_VR_ANTITHETIC;
@@ -590,6 +623,11 @@ int path_dependent(hh_ctx *ctx, const hh_model *m, const hh_sim *s, int monitor_
   a.monitor_every = monitor_every;
   a.inv_m = 1.0 / (double)(M / monitor_every);
   a.split = (m->flags & HH_FLAG_SPLIT_STEP) != 0;
+  a.cv_on = cv;
+  if (cv) {
+    a.cv_sigma = sqrt(bs_control_variance(m));
+    a.cv_drift = (m->r - 0.5 * a.cv_sigma * a.cv_sigma) * (m->T / s->n_steps);
+  }
   a.rk = philox_round_keys(s->base_seed);
   a.one_hi = 0x3FF00000u;
   a.magic_hi = 0x43300000u;

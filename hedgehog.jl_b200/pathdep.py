@@ -9,7 +9,7 @@ from __future__ import annotations
 
 import math
 from dataclasses import dataclass
-from typing import Any, Sequence
+from typing import Any, Optional, Sequence
 
 import numpy as np
 
@@ -191,3 +191,72 @@ def solve_path_dependent(payoffs: Sequence, market_inputs, method, *, engine=Non
     stats = {"kernel_ms": results[0].kernel_ms, "n_nonfinite": results[0].n_nonfinite, "n_local": sim.n_paths,
              "n_total": int(sums[0][2])}
     return out, stats
+
+
+# ---- Black-Scholes control variate for Heston vanilla prices (roadmap "Control variates using Black-Scholes", N3) -----
+@dataclass(frozen=True)
+class BlackScholesControlVariate:
+    """MonteCarlo(HestonDynamics(), EulerMaruyama(), config, control_variate=BlackScholesControlVariate()).
+    The kernel advances a log-GBM trajectory on the same Brownian increments next to every Heston trajectory
+    (HH_PD_VANILLA_MINUS_BS); price = D mean(X - beta Y) + beta BS(sigma_cv). beta = None: estimated from a pilot run of
+    `pilot` trajectories on a separate seed (the same on every rank), so that the main estimator stays unbiased."""
+    beta: Optional[float] = None
+    pilot: int = 50_000
+
+
+def bs_control_sigma(V0, kappa, theta, T):
+    """sigma_cv of the control: sqrt of the mean of E[V_t] = theta + (V0 - theta) e^(-kappa t) over [0, T]
+    (the same formula as bs_control_variance in csrc/hh_pathdep.cu)."""
+    kT = kappa * T
+    w = -math.expm1(-kT) / kT if abs(kT) > 1e-8 else 1.0 - 0.5 * kT
+    return math.sqrt(max(theta + (V0 - theta) * w, 1e-12))
+
+
+def black_scholes_closed_form(S, K, r, sigma, T, cp):
+    from statistics import NormalDist
+    N = NormalDist().cdf
+    sq = sigma * math.sqrt(T)
+    d1 = (math.log(S / K) + (r + 0.5 * sigma * sigma) * T) / sq
+    return cp * (S * N(cp * d1) - K * math.exp(-r * T) * N(cp * (d1 - sq)))
+
+
+def _var(r):
+    n = float(r.n)
+    mean = r.sum / n
+    return max((r.sumsq - n * mean * mean) / (n - 1), 0.0)
+
+
+def solve_bs_control(prob, method, *, engine=None, shard=None, group=None):
+    from .engine import SimSpec
+    cv = method.control_variate
+    if not (isinstance(method.dynamics, api.HestonDynamics) and isinstance(method.strategy, api.EulerMaruyama)):
+        raise TypeError("BlackScholesControlVariate runs next to HestonDynamics + EulerMaruyama")
+    if not isinstance(prob.payoff, api.VanillaOption) or not isinstance(prob.payoff.underlying, api.Spot):
+        raise TypeError("BlackScholesControlVariate prices European vanilla options on the Spot underlying")
+    eng = engine or api.default_engine()
+    shard, reduce = api._shard_and_reduce(shard, group)
+    mdl = api._model_of(prob, method)
+    sim = api._sim_of(method, abi.HH_SCHEME_EM, shard)
+    K, cp = prob.payoff.strike, prob.payoff.call_put()
+    discount = api.df(prob.market_inputs.rate, prob.payoff.expiry)
+    sigma_cv = bs_control_sigma(mdl.V0, mdl.kappa, mdl.theta, mdl.T)
+    bs = black_scholes_closed_form(mdl.S0, K, mdl.r, sigma_cv, mdl.T, cp)
+    beta = cv.beta
+    if beta is None:  # Cov(X, Y) = (Var X + Var Y - Var(X - Y)) / 2 from three sums of ONE pilot launch
+        seed = (int(method.config.base_seed) ^ 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
+        pilot = SimSpec(n_paths=max(2, min(cv.pilot, method.config.trajectories)), n_steps=sim.n_steps, scheme=abi.HH_SCHEME_EM,
+                        vr=sim.vr, base_seed=seed)
+        px, py, pd = eng.mc_path_dependent(mdl, pilot, [(abi.HH_PD_VANILLA, K, cp, 0.0, 0.0), (abi.HH_PD_BS_CONTROL, K, cp, 0.0, 0.0),
+                                                        (abi.HH_PD_VANILLA_MINUS_BS, K, cp, 0.0, 1.0)], discount, 1)[0]
+        vy = _var(py)
+        beta = 0.5 * (_var(px) + vy - _var(pd)) / vy if vy > 0.0 else 0.0
+    (res,), _ = eng.mc_path_dependent(mdl, sim, [(abi.HH_PD_VANILLA_MINUS_BS, K, cp, 0.0, beta)], discount, 1)
+    sums = np.array([res.sum, res.sumsq, float(res.n)])
+    if reduce is not None:
+        sums = reduce(sums)
+    s, q, n = sums
+    mean = s / n
+    var = max((q - n * mean * mean) / (n - 1), 0.0) if n > 1 else 0.0
+    stats = {"kernel_ms": res.kernel_ms, "n_nonfinite": res.n_nonfinite, "n_local": sim.n_paths, "n_total": int(n),
+             "beta": beta, "sigma_cv": sigma_cv, "control_price": bs}
+    return api.MonteCarloSolution(prob, method, discount * mean + beta * bs, None, discount * math.sqrt(var / n), stats)

@@ -235,7 +235,13 @@ int hh_mc_european_tangent_sums(hh_ctx *ctx, const hh_model *model, const hh_tan
 #define HH_PD_ASIAN_ARITH_MINUS_GEOM 9 /* max(cp (A - K), 0) - max(cp (G - K), 0): the arithmetic Asian with the geometric one \
                                           as a control variate (roadmap "control variates"): the host adds the \
                                           closed-form geometric price under Black-Scholes */
-#define HH_PD_NKINDS 10
+/* Black-Scholes control variate for HestonDynamics + Euler-Maruyama (roadmap "Control variates using Black-Scholes",
+ * SURVEY N3): next to every Heston trajectory the kernel advances a log-GBM trajectory on the SAME Brownian increments
+ * dW1, with the constant variance sigma_cv^2 = theta + (V0 - theta)(1 - e^(-kappa T))/(kappa T) (the mean of E[V_t]
+ * over [0, T]); its terminal spot S_cv has the closed-form Black-Scholes expectation, which the host adds back. */
+#define HH_PD_BS_CONTROL 10        /* max(cp (S_cv - K), 0): the control alone (pilot runs estimate its covariance) */
+#define HH_PD_VANILLA_MINUS_BS 11  /* max(cp (S_T - K), 0) - amount * max(cp (S_cv - K), 0), amount = beta */
+#define HH_PD_NKINDS 12
 #define HH_PD_NSTATS 5         /* per column: S_T, A, G, max S, min S over the monitoring dates */
 typedef struct hh_path_payoff {
   int32_t kind; /* HH_PD_* */

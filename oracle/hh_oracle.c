@@ -146,11 +146,19 @@ void hho_fill_normals(const hh_model *model, const hh_sim *sim, double *Z) {
  * One trajectory -> terminal spot (plus, minus). `grid`, when non-null, receives every saved
  * state of the S-space generator (LSM), stride `gstride` between dates.
  * ---------------------------------------------------------------------------------------- */
-typedef struct { double Sp, Sm, vp, vm; } terminal_t;
+typedef struct { double Sp, Sm, vp, vm, cvp, cvm; } terminal_t; /* cv*: terminal spot of the Black-Scholes control (Heston EM f64) */
+
+/* sigma_cv^2 of the Black-Scholes control variate (include/hedgehog_mc.h HH_PD_BS_CONTROL): mean of E[V_t] over [0, T] */
+static double bs_control_variance(const hh_model *m) {
+  double kT = m->kappa * m->T;
+  double w = fabs(kT) > 1e-8 ? -expm1(-kT) / kT : 1.0 - 0.5 * kT;
+  double v = m->theta + (m->V0 - m->theta) * w;
+  return v > 1e-12 ? v : 1e-12;
+}
 
 static terminal_t simulate_one(const hh_model *m, const hh_sim *sim, int64_t i, double *grid_p, double *grid_m,
                                size_t gstride) {
-  terminal_t out = {0, 0, 0, 0};
+  terminal_t out = {0, 0, 0, 0, 0, 0};
   uint64_t key, idx;
   path_stream(sim, i, &key, &idx);
   const int anti = sim->vr == HH_VR_ANTITHETIC;
@@ -272,6 +280,8 @@ static terminal_t simulate_one(const hh_model *m, const hh_sim *sim, int64_t i, 
     const int split = (m->flags & HH_FLAG_SPLIT_STEP) != 0;
     const double a11 = sqdt * m->m11, a12 = sqdt * m->m12, a21 = sqdt * m->m21, a22 = sqdt * m->m22;
     double xp = log(m->S0), vp = m->V0, xm = xp, vm = vp;
+    const double cv_sigma = sqrt(bs_control_variance(m)), cv_drift = (m->r - 0.5 * cv_sigma * cv_sigma) * dt;
+    double xbp = xp, xbm = xp; /* log-GBM control on the same dW1 */
     if (grid_p) grid_p[0] = m->S0; /* LSM grid: S = exp(x), see the GBM EM branch */
     if (grid_m) grid_m[0] = m->S0;
     for (int n = 0; n < M; ++n) {
@@ -296,7 +306,11 @@ static terminal_t simulate_one(const hh_model *m, const hh_sim *sim, int64_t i, 
         xm = K1 + s * (-dW1);
         vm = K2 + (m->xi * s) * (-dW2);
       }
+      xbp = (xbp + cv_drift) + cv_sigma * dW1;
+      xbm = (xbm + cv_drift) + cv_sigma * (-dW1);
     }
+    out.cvp = exp(xbp);
+    out.cvm = exp(xbm);
     out.Sp = exp(xp);
     out.vp = vp;
     out.Sm = anti ? exp(xm) : 0.0;
@@ -388,7 +402,7 @@ int hho_mc_european(const hh_model *model, const hh_sim *sim, const hh_payoff *p
  * S-SPACE from the saved spots of each trajectory (the grid the LSM extension fills), independently of the
  * kernel's log-space bookkeeping: A = mean S, G = exp(mean log S), max S, min S over the monitoring dates.
  * ---------------------------------------------------------------------------------------- */
-static double pd_payoff_of(const hh_path_payoff *c, const double *st) {
+static double pd_payoff_of(const hh_path_payoff *c, const double *st, double Scv) {
   const double ST = st[0], A = st[1], G = st[2], mx = st[3], mn = st[4];
   const double vanilla = fmax(c->cp * (ST - c->strike), 0.0);
   switch (c->kind) {
@@ -401,6 +415,8 @@ static double pd_payoff_of(const hh_path_payoff *c, const double *st) {
     case HH_PD_DOWN_IN: return mn <= c->barrier ? vanilla : c->amount;
     case HH_PD_DIGITAL_CASH: return c->cp * (ST - c->strike) > 0.0 ? c->amount : 0.0;
     case HH_PD_DIGITAL_ASSET: return c->cp * (ST - c->strike) > 0.0 ? ST : 0.0;
+    case HH_PD_BS_CONTROL: return fmax(c->cp * (Scv - c->strike), 0.0);
+    case HH_PD_VANILLA_MINUS_BS: return vanilla - c->amount * fmax(c->cp * (Scv - c->strike), 0.0);
     default: return vanilla;
   }
 }
@@ -431,8 +447,12 @@ int hho_mc_path_dependent(const hh_model *model, const hh_sim *sim, int monitor_
   if (sim->precision != HH_PREC_F64) return HH_ERR_UNSUPPORTED;
   const int M = sim->n_steps;
   if (monitor_every < 1 || M % monitor_every != 0) return HH_ERR_ARG;
-  for (int k = 0; k < npayoffs; ++k)
+  for (int k = 0; k < npayoffs; ++k) {
     if (payoffs[k].kind < 0 || payoffs[k].kind >= HH_PD_NKINDS) return HH_ERR_ARG;
+    if ((payoffs[k].kind == HH_PD_BS_CONTROL || payoffs[k].kind == HH_PD_VANILLA_MINUS_BS) &&
+        !(model->kind == HH_MODEL_HESTON && sim->scheme == HH_SCHEME_EM))
+      return HH_ERR_ARG;
+  }
   const int64_t N = sim->n_paths;
   const int anti = sim->vr == HH_VR_ANTITHETIC;
   const int64_t ncols = anti ? 2 * N : N;
@@ -448,7 +468,7 @@ int hho_mc_path_dependent(const hh_model *model, const hh_sim *sim, int monitor_
     int64_t lnf = 0;
 #pragma omp for schedule(static)
     for (int64_t i = 0; i < N; ++i) {
-      simulate_one(model, sim, i, gp, anti ? gm : NULL, 1);
+      terminal_t tt = simulate_one(model, sim, i, gp, anti ? gm : NULL, 1);
       double sp[HH_PD_NSTATS], sm[HH_PD_NSTATS];
       pd_stats_of(gp, M, monitor_every, sp);
       if (anti) pd_stats_of(gm, M, monitor_every, sm);
@@ -459,8 +479,8 @@ int hho_mc_path_dependent(const hh_model *model, const hh_sim *sim, int monitor_
           if (anti) path_stats[(size_t)q * ncols + N + i] = sm[q];
         }
       for (int k = 0; k < npayoffs; ++k) {
-        double p = pd_payoff_of(&payoffs[k], sp);
-        if (anti) p = (p + pd_payoff_of(&payoffs[k], sm)) / 2; /* reduce_payoffs montecarlo.jl:430-432 */
+        double p = pd_payoff_of(&payoffs[k], sp, tt.cvp);
+        if (anti) p = (p + pd_payoff_of(&payoffs[k], sm, tt.cvm)) / 2; /* reduce_payoffs montecarlo.jl:430-432 */
         ls[k] += p;
         lq[k] += (long double)p * p;
       }

@@ -21,14 +21,18 @@ from test_pathdep_oracle import ALL_KINDS, numpy_payoff
 pytestmark = pytest.mark.gpu
 
 
+HESTON_KINDS = ALL_KINDS + [(abi.HH_PD_BS_CONTROL, 100.0, 1.0, 0.0, 0.0), (abi.HH_PD_VANILLA_MINUS_BS, 95.0, -1.0, 0.0, 0.8)]
+
+
 def _compare(cuda, oracle, m, sim, payoffs, every, stat_tol=1e-11):
     rg, sg = cuda.mc_path_dependent(m, sim, payoffs, 0.97, every, want_stats=True)
     ro, so = oracle.mc_path_dependent(m, sim, payoffs, 0.97, every, want_stats=True)
     assert rel_err(sg, so) < stat_tol
     n = sim.n_paths
     for c, g, o in zip(payoffs, rg, ro):
-        pg, po = numpy_payoff(c, sg), numpy_payoff(c, so)
-        assert np.count_nonzero(np.abs(pg - po) > 1e-9 * (1.0 + np.abs(po))) == 0  # no decision flipped
+        if c[0] < abi.HH_PD_BS_CONTROL:  # (the control's terminal spot is not among the exported statistics)
+            pg, po = numpy_payoff(c, sg), numpy_payoff(c, so)
+            assert np.count_nonzero(np.abs(pg - po) > 1e-9 * (1.0 + np.abs(po))) == 0  # no decision flipped
         assert g.n == o.n == n
         assert g.sum == pytest.approx(o.sum, rel=1e-10, abs=1e-9)
         assert g.sumsq == pytest.approx(o.sumsq, rel=1e-10, abs=1e-9)
@@ -53,7 +57,7 @@ def test_parity_mode_all_payoffs(cuda, oracle, model, anti):
     scheme = abi.HH_SCHEME_EXACT_STEPS if model == "gbm_steps" else abi.HH_SCHEME_EM
     sim = SimSpec(n_paths=n, n_steps=M, scheme=scheme, vr=int(anti), rng_mode=abi.HH_RNG_NORMALS, normals=z)
     for every in (1, 6):
-        _compare(cuda, oracle, m, sim, ALL_KINDS, every)
+        _compare(cuda, oracle, m, sim, HESTON_KINDS if heston else ALL_KINDS, every)
 
 
 @pytest.mark.parametrize("model", ["gbm", "heston"])
@@ -64,7 +68,10 @@ def test_native_rng_all_payoffs(cuda, oracle, model, seeded):
     kw = dict(seeds=np.random.Generator(np.random.Philox(2)).integers(0, 2**64, size=n, dtype=np.uint64)) if seeded \
         else dict(base_seed=4242, path_offset=(1 << 33) + 5)
     sim = SimSpec(n_paths=n, n_steps=M, scheme=abi.HH_SCHEME_EM, vr=abi.HH_VR_ANTITHETIC, **kw)
-    _compare(cuda, oracle, m, sim, ALL_KINDS, 5, stat_tol=1e-10)
+    _compare(cuda, oracle, m, sim, HESTON_KINDS if model == "heston" else ALL_KINDS, 5, stat_tol=1e-10)
+    if model == "heston":   # and without the antithetic side (the 1024-thread instantiation when the key is uniform)
+        _compare(cuda, oracle, m, SimSpec(n_paths=200_003 if not seeded else n, n_steps=20, scheme=abi.HH_SCHEME_EM, **(kw if seeded else dict(base_seed=6))),
+                 HESTON_KINDS, 4, stat_tol=1e-10)
 
 
 def test_without_arithmetic_average_the_kernel_stays_in_log_space(cuda, oracle):
@@ -81,7 +88,7 @@ def test_without_arithmetic_average_the_kernel_stays_in_log_space(cuda, oracle):
 def test_many_contracts_and_odd_shapes(cuda, oracle):
     m = gbm_model()
     rng = np.random.default_rng(3)
-    pays = [(int(rng.integers(0, abi.HH_PD_NKINDS)), float(rng.uniform(80, 120)), float(rng.choice([-1.0, 1.0])),
+    pays = [(int(rng.integers(0, abi.HH_PD_BS_CONTROL)), float(rng.uniform(80, 120)), float(rng.choice([-1.0, 1.0])),
              float(rng.uniform(70, 140)), float(rng.uniform(0, 2))) for _ in range(256)]
     for n, M, every in ((1, 1, 1), (513, 7, 7), (1025, 9, 3)):
         sim = SimSpec(n_paths=n, n_steps=M, scheme=abi.HH_SCHEME_EM, base_seed=n)
@@ -213,3 +220,27 @@ def test_results_are_reproducible_and_shard_additive(cuda):
     assert np.array_equal(np.concatenate([sa, sb], axis=1), s1)
     for a, b, w in zip(ra, rb, r1):
         assert a.sum + b.sum == pytest.approx(w.sum, rel=1e-13)
+
+
+def test_black_scholes_control_variate_through_solve(cuda):
+    """MonteCarlo(HestonDynamics(), EulerMaruyama(), config, control_variate=BlackScholesControlVariate()): same
+    expectation as the plain estimator, standard error more than halved (variance / 6 at these parameters), agreement
+    with Carr-Madan up to the Euler bias; the control variate is rejected where its closed form does not apply."""
+    from oracle import anchors as A
+    ref, exp = dt.date(2020, 1, 1), dt.date(2021, 1, 1)
+    mk = hh.HestonInputs(ref, 0.03, 100.0, 0.04, 2.0, 0.04, 0.3, -0.7)
+    prob = hh.PricingProblem(hh.VanillaOption(100.0, exp, hh.European(), hh.Call(), hh.Spot()), mk)
+    cfg = hh.SimulationConfig(4_000_000, steps=252, base_seed=9)
+    plain = hh.solve(prob, hh.MonteCarlo(hh.HestonDynamics(), hh.EulerMaruyama(), cfg, ensemble=False), engine=cuda)
+    cv = hh.solve(prob, hh.MonteCarlo(hh.HestonDynamics(), hh.EulerMaruyama(), cfg, ensemble=False,
+                                      control_variate=hh.BlackScholesControlVariate()), engine=cuda)
+    assert cv.std_error < 0.5 * plain.std_error and 0.5 < cv.stats["beta"] < 1.0
+    assert abs(cv.price - plain.price) < 3.5 * plain.std_error
+    cm = A.heston_price(100.0, 100.0, 0.03, 366 / 365, 0.04, 2.0, 0.04, 0.3, -0.7)
+    assert abs(cv.price - cm) < 3.5 * cv.std_error + 0.008   # Euler bias at 252 steps: +0.0057
+    with pytest.raises(TypeError):
+        hh.solve(hh.PricingProblem(prob.payoff, hh.BlackScholesInputs(ref, 0.03, 100.0, 0.2)),
+                 hh.MonteCarlo(hh.LognormalDynamics(), hh.EulerMaruyama(), cfg, control_variate=hh.BlackScholesControlVariate()), engine=cuda)
+    with pytest.raises(ValueError):   # C ABI: the control kinds need HestonDynamics + EulerMaruyama
+        cuda.mc_path_dependent(gbm_model(), SimSpec(n_paths=10, n_steps=5, scheme=abi.HH_SCHEME_EM),
+                               [(abi.HH_PD_VANILLA_MINUS_BS, 100.0, 1.0, 0.0, 1.0)], 1.0, 1)

@@ -157,3 +157,30 @@ def test_geometric_control_variate_for_the_arithmetic_asian(oracle):
                  hh.MonteCarlo(hh.HestonDynamics(), hh.EulerMaruyama(), hh.SimulationConfig(1000, steps=10)), engine=oracle)
     with pytest.raises(ValueError):
         hh.AsianOption(100.0, EXP, hh.Call(), hh.GeometricAverage(), control_variate=hh.GeometricControlVariate())
+
+
+def test_black_scholes_control_variate_for_heston(oracle):
+    """Roadmap "Control variates using Black-Scholes" (SURVEY N3): the control's sample mean matches its closed form, the
+    controlled estimator has the plain estimator's expectation and a much smaller standard error, and it agrees with
+    Carr-Madan up to the scheme's O(dt) bias."""
+    from hedgehog_jl_b200.pathdep import bs_control_sigma, black_scholes_closed_form
+    mk = hh.HestonInputs(REF, 0.03, 100.0, 0.04, 2.0, 0.04, 0.3, -0.7)
+    prob = hh.PricingProblem(hh.VanillaOption(100.0, EXP, hh.European(), hh.Call(), hh.Spot()), mk)
+    cfg = hh.SimulationConfig(100_000, steps=100, base_seed=9)
+    plain = hh.solve(prob, hh.MonteCarlo(hh.HestonDynamics(), hh.EulerMaruyama(), cfg, ensemble=False), engine=oracle)
+    cv = hh.solve(prob, hh.MonteCarlo(hh.HestonDynamics(), hh.EulerMaruyama(), cfg, ensemble=False,
+                                      control_variate=hh.BlackScholesControlVariate()), engine=oracle)
+    assert cv.std_error < 0.5 * plain.std_error and 0.5 < cv.stats["beta"] < 1.0
+    assert abs(cv.price - plain.price) < 3.5 * plain.std_error
+    cm = A.heston_price(100.0, 100.0, 0.03, T, 0.04, 2.0, 0.04, 0.3, -0.7)
+    assert abs(cv.price - cm) < 3.5 * cv.std_error + 0.02   # + the Euler bias at 100 steps (profiles/r1_i_euler_bias_c2.json)
+    # the control alone: a log-GBM trajectory with sigma_cv, whose mean is the Black-Scholes price
+    sig = bs_control_sigma(0.09, 1.5, 0.04, T)
+    assert sig == pytest.approx(math.sqrt(0.04 + 0.05 * (1 - math.exp(-1.5 * T)) / (1.5 * T)), rel=1e-14)
+    m = heston_model(r=0.03, T=T, V0=0.09, kappa=1.5, theta=0.04, xi=0.4, rho=-0.5)
+    sim = SimSpec(n_paths=200_000, n_steps=50, scheme=abi.HH_SCHEME_EM, vr=abi.HH_VR_ANTITHETIC, base_seed=2)
+    (ctrl,), _ = oracle.mc_path_dependent(m, sim, [(abi.HH_PD_BS_CONTROL, 105.0, -1.0, 0.0, 0.0)], math.exp(-0.03 * T), 1)
+    assert abs(ctrl.price - black_scholes_closed_form(100.0, 105.0, 0.03, sig, T, -1.0)) < 3.5 * ctrl.std_error
+    assert black_scholes_closed_form(100.0, 105.0, 0.03, sig, T, -1.0) == pytest.approx(A.bs_price(100.0, 105.0, 0.03, sig, T, cp=-1.0), rel=1e-12)
+    with pytest.raises(ValueError):   # the control needs HestonDynamics + EulerMaruyama
+        oracle.mc_path_dependent(gbm_model(), SimSpec(n_paths=10, n_steps=5, scheme=abi.HH_SCHEME_EM), [(abi.HH_PD_BS_CONTROL, 100.0, 1.0, 0.0, 0.0)], 1.0, 1)
