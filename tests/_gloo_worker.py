@@ -63,6 +63,12 @@ def main():
     res["pathdep"] = {"sharded": [[s.price, s.std_error] for s in hh.solve(pd_basket, method, engine=eng)],
                       "single": [[s.price, s.std_error] for s in hh.solve(pd_basket, method, engine=eng, shard=(0, 1))]}
 
+    # Black-Scholes control variate: the pilot (beta) is the same launch on every rank, the controlled sums are sharded
+    cvm = hh.MonteCarlo(hh.HestonDynamics(), hh.EulerMaruyama(), hh.SimulationConfig(N, steps=16, base_seed=11), ensemble=False,
+                        control_variate=hh.BlackScholesControlVariate(pilot=4000))
+    a, b = hh.solve(prob, cvm, engine=eng), hh.solve(prob, cvm, engine=eng, shard=(0, 1))
+    res["bs_control"] = {"sharded": [a.price, a.std_error, a.stats["beta"]], "single": [b.price, b.std_error, b.stats["beta"]]}
+
     # the hh_comm callback the LSM driver calls between pass and fit: in-place sum-allreduce of a buffer
     comm, keep = hd.make_comm((rank, world))
     buf = np.arange(12, dtype=np.float64) * (rank + 1)

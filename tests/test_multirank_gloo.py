@@ -63,3 +63,9 @@ def test_path_dependent_payoffs_reduce_across_ranks(ranks):
     assert ranks[0]["pathdep"]["sharded"] == ranks[1]["pathdep"]["sharded"]
     for r in ranks:
         np.testing.assert_allclose(r["pathdep"]["sharded"], r["pathdep"]["single"], rtol=1e-10)
+
+
+def test_black_scholes_control_variate_reduces_across_ranks(ranks):
+    assert ranks[0]["bs_control"]["sharded"] == ranks[1]["bs_control"]["sharded"]
+    for r in ranks:
+        np.testing.assert_allclose(r["bs_control"]["sharded"], r["bs_control"]["single"], rtol=1e-10)
