@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Times hh_mc_path_dependent: usage python tools/time_pathdep.py [paths] [steps] [every]
-HH_PD_MODEL = heston (default) | gbm; HH_PD_SET = all | logspace (no arithmetic average: the kernel never calls exp)."""
+HH_PD_MODEL = heston (default) | gbm; HH_PD_SET = all | logspace (no arithmetic average: the kernel never calls exp) | vanilla | cv (Black-Scholes control)."""
 import math
 import os
 import sys
@@ -24,8 +24,13 @@ if which == "heston":
     (m.m11, m.m12, m.m21, m.m22), _ = hh.corr_factor(m.rho, "cholesky")
 pays = [(abi.HH_PD_ASIAN_GEOM, 100.0, 1.0, 0.0, 0.0), (abi.HH_PD_UP_OUT, 100.0, 1.0, 130.0, 0.0),
         (abi.HH_PD_DOWN_IN, 100.0, -1.0, 80.0, 0.0), (abi.HH_PD_DIGITAL_CASH, 100.0, 1.0, 0.0, 1.0)]
-if os.environ.get("HH_PD_SET", "all") == "all":
+which_set = os.environ.get("HH_PD_SET", "all")
+if which_set == "all":
     pays.append((abi.HH_PD_ASIAN_ARITH, 100.0, 1.0, 0.0, 0.0))
+elif which_set == "vanilla":      # the European payoff through this kernel (baseline of the control-variate cost)
+    pays = [(abi.HH_PD_VANILLA, 100.0, 1.0, 0.0, 0.0)]
+elif which_set == "cv":           # Black-Scholes control variate (Heston only): the control trajectory is advanced too
+    pays = [(abi.HH_PD_VANILLA_MINUS_BS, 100.0, 1.0, 0.0, 0.77)]
 for anti in (0, 1):
     best = None
     for rep in range(4):
