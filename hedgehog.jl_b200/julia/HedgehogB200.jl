@@ -19,7 +19,7 @@ using Hedgehog: PricingProblem, VanillaOption, European, American, Spot, Abstrac
                 SpotLens, VolLens, ZeroRateSpineLens, yearfrac, add_yearfrac, zero_rate, df, get_vol
 using Libdl
 
-export B200MonteCarlo, B200LSM, b200_library!, AsianOption, BarrierOption, DigitalOption
+export B200MonteCarlo, B200LSM, b200_library!, AsianOption, BarrierOption, DigitalOption, solve_with_bs_control
 
 # ---- library handle -----------------------------------------------------------------------------------------------
 const LIB = Ref{String}(get(ENV, "HEDGEHOG_MC_LIB", joinpath(@__DIR__, "..", "libhedgehog_mc.so")))
@@ -255,6 +255,51 @@ function Hedgehog.solve(prob::PricingProblem{P,I}, method::B200MonteCarlo) where
         check(ctx, rc, "hh_mc_path_dependent")
     end
     return MonteCarloSolution(prob, method, res[].price, Float64[])
+end
+
+# ---- Black-Scholes control variate for Heston vanilla prices (roadmap "Control variates using Black-Scholes") ---------------
+# The kernel advances a log-GBM trajectory on the same Brownian increments next to every Heston trajectory
+# (HH_PD_BS_CONTROL = 10, HH_PD_VANILLA_MINUS_BS = 11 in include/hedgehog_mc.h); the expectation of the control is
+# Hedgehog's own BlackScholesAnalytic price at sigma_cv. beta === nothing: estimated from one pilot launch on another seed.
+function path_dependent_results(ctx, model::HHModel, sim::HHSim, payoffs::Vector{HHPathPayoff}, discount, every::Integer)
+    res = Vector{HHResult}(undef, length(payoffs))
+    GC.@preserve payoffs res begin
+        rc = ccall((:hh_mc_path_dependent, LIB[]), Cint,
+                   (Ptr{Cvoid}, Ref{HHModel}, Ref{HHSim}, Cint, Ptr{HHPathPayoff}, Cint, Cdouble, Ptr{HHResult}, Ptr{Float64}, Csize_t),
+                   ctx.h, model, sim, every, pointer(payoffs), length(payoffs), discount, pointer(res), Ptr{Float64}(C_NULL), 0)
+        check(ctx, rc, "hh_mc_path_dependent")
+    end
+    return res
+end
+sample_var(r::HHResult) = max((r.sumsq - r.n * (r.sum / r.n)^2) / (r.n - 1), 0.0)
+
+function solve_with_bs_control(prob::PricingProblem{VanillaOption{TS,TE,European,C,Spot},I}, method::B200MonteCarlo;
+                               beta = nothing, pilot::Int = 50_000) where {TS,TE,C,I<:AbstractMarketInputs}
+    method.dynamics isa HestonDynamics && method.strategy isa EulerMaruyama ||
+        throw(ArgumentError("the Black-Scholes control variate runs next to HestonDynamics + EulerMaruyama"))
+    ctx = context()
+    model = hh_model(prob, method.dynamics)
+    K, cp = prob.payoff.strike, prob.payoff.call_put()
+    m = prob.market_inputs
+    discount = df(m.rate, prob.payoff.expiry)
+    kT = model.kappa * model.T
+    w = abs(kT) > 1e-8 ? -expm1(-kT) / kT : 1 - kT / 2
+    sigma_cv = sqrt(max(model.theta + (model.V0 - model.theta) * w, 1e-12))     # mean of E[V_t] over [0, T]
+    control = Hedgehog.solve(PricingProblem(prob.payoff, Hedgehog.BlackScholesInputs(m.referenceDate, m.rate, m.spot, sigma_cv)),
+                             Hedgehog.BlackScholesAnalytic()).price
+    with_sim(method, HH_SCHEME_EM) do sim
+        b = beta
+        if b === nothing    # Cov(X, Y) = (Var X + Var Y - Var(X - Y)) / 2 from the three sums of one pilot launch
+            ps = HHSim(min(pilot, sim.n_paths), 0, sim.n_steps, sim.scheme, sim.vr, sim.precision, 0, 0,
+                       sim.base_seed ⊻ 0x9E3779B97F4A7C15, C_NULL, C_NULL, HHBkConfig())
+            px, py, pd = path_dependent_results(ctx, model, ps, [HHPathPayoff(0, 0, K, cp, 0.0, 0.0), HHPathPayoff(10, 0, K, cp, 0.0, 0.0),
+                                                                 HHPathPayoff(11, 0, K, cp, 0.0, 1.0)], discount, 1)
+            vy = sample_var(py)
+            b = vy > 0 ? (sample_var(px) + vy - sample_var(pd)) / (2vy) : 0.0
+        end
+        r = path_dependent_results(ctx, model, sim, [HHPathPayoff(11, 0, K, cp, 0.0, b)], discount, 1)[1]
+        MonteCarloSolution(prob, method, r.price + b * control, Float64[])
+    end
 end
 
 # ---- Greeks: every ForwardAD lens is one tangent direction of the SAME simulation (greeks_problem.jl:249-262, 559-568) ---
