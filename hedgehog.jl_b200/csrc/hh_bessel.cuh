@@ -92,10 +92,10 @@ HH_HD cplx csqrt_(cplx a) {
   if (m == 0.0) return cplx{0.0, 0.0};
   if (a.re >= 0.0) {
     const double t = sqrt(0.5 * (m + a.re));
-    return cplx{t, 0.5 * a.im / t};
+    return cplx{t, 0.5 * a.im * rcp_fast(t)};
   }
   const double t = sqrt(0.5 * (m - a.re));
-  return cplx{0.5 * fabs(a.im) / t, a.im >= 0.0 ? t : -t};
+  return cplx{0.5 * fabs(a.im) * rcp_fast(t), a.im >= 0.0 ? t : -t};
 }
 
 constexpr double kBesselPi = 3.14159265358979323846;
@@ -312,11 +312,12 @@ HH_HD BesselEF besseli_ef(const BesselOrder &o, cplx z, double log_az, double ar
     rot = sg * kBesselPi * nu;
     arg_w = arg_z - sg * kBesselPi;  // arg(-z) in (-pi/2, pi/2)
   }
-  const double aw = cabs(w);
+  // region tests on |w|^2 (Re w >= 0 here: |w| - Re w <= 5  <=>  |w|^2 <= (5 + Re w)^2): no square root
+  const double aw2 = cabs2(w), ra2 = o.r_asym * o.r_asym, edge = 5.0 + w.re;
   BesselEF r;
-  if (aw <= 5.0 || (aw < o.r_asym && aw - w.re <= 5.0)) {
+  if (aw2 <= 25.0 || (aw2 < ra2 && aw2 <= edge * edge)) {
     r = besseli_series_ef(nu, o.lgam_nu1, w, log_az, arg_w, o.series_rk);
-  } else if (aw >= o.r_asym) {
+  } else if (aw2 >= ra2) {
     r = besseli_asymptotic_ef(nu, w, log_az, arg_w, o.hankel_bk);
   } else {
     r.E = log_besseli(o, w);  // continued fractions (rare: strongly rotated arguments of moderate size)
@@ -343,6 +344,7 @@ struct BkParams {
 struct BkCf {       // per (V0, VT) pair: HestonCFIterator
   double sv;        // sqrt(V0 VT)
   double vsum_s;    // (V0 + VT) / sigma^2
+  double sv4_xi2;   // 4 sqrt(V0 VT) / sigma^2
   cplx logIk;       // log I_nu(z_kappa)
 };
 
@@ -350,6 +352,7 @@ HH_HD BkCf bk_cf_init(const BkParams &p, double V0, double VT) {
   BkCf it;
   it.sv = sqrt(V0 * VT);
   it.vsum_s = (V0 + VT) / p.xi2;
+  it.sv4_xi2 = it.sv * 4.0 / p.xi2;
   it.logIk = log_besseli(p.ord, mk(it.sv * p.wk));
   return it;
 }
@@ -360,14 +363,15 @@ HH_HD_OUTLINE cplx bk_chf(const BkParams &p, const BkCf &it, double a, double &t
   const cplx egh = cexp_((-0.5 * p.tau) * g);  // e^{-g tau / 2}
   const cplx eg = egh * egh;
   const cplx omeg = 1.0 - eg;
-  const cplx zeta_g = omeg / g;                                              // :191
-  const cplx eta_g = g * (1.0 + eg) / omeg;                                   // :192
-  const cplx zg = (it.sv * 4.0) * g * egh / p.xi2 / omeg;                       // nu_gamma         :193
+  // one complex reciprocal serves the three quotients of :191-193 (1 / zeta_g = g / (1 - e^{-g tau}))
+  const cplx g_io = g * (1.0 / omeg);
+  const cplx eta_g = g_io * (1.0 + eg);                                       // :192
+  const cplx zg = it.sv4_xi2 * (g_io * egh);                                  // nu_gamma         :193
   const double th = carg(zg);                                                 // :198
   double thu = th;
   if (!(theta_prev != theta_prev)) {                                          // :199-205
     double dlt = th - theta_prev;
-    dlt -= 2.0 * kBesselPi * nearbyint(dlt / (2.0 * kBesselPi));
+    dlt -= 2.0 * kBesselPi * nearbyint(dlt * (0.5 / kBesselPi));
     thu = theta_prev + dlt;
   }
   theta_prev = thu;
@@ -376,7 +380,7 @@ HH_HD_OUTLINE cplx bk_chf(const BkParams &p, const BkCf &it, double a, double &t
   ig.E.im += p.ord.nu * (thu - th);
   // phi = exp(-(g - k) tau / 2) (zeta_k / zeta_g) exp((V0+VT)/s^2 (eta_k - eta_g)) exp(logIg - logIk)   :195-211
   const cplx ex = (-0.5 * p.tau) * (g - p.kappa) + it.vsum_s * (p.eta_k - eta_g) + (ig.E - it.logIk);
-  return ((p.zeta_k / zeta_g) * ig.F) * cexp_(ex);
+  return ((p.zeta_k * g_io) * ig.F) * cexp_(ex);  // zeta_k / zeta_g (:191)
 }
 
 }  // namespace hh
