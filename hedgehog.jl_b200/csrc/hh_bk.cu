@@ -151,8 +151,9 @@ __device__ __noinline__ void bk_cdf(const BkTable &tb, int J, double h, double x
     sp = s; s = sn;
     cp = c; c = cn;
   }
-  F = h * x / kBesselPi + acc;
-  dF = h / kBesselPi + h * dacc;
+  constexpr double kInvPi = 1.0 / kBesselPi;
+  F = fma(h * x, kInvPi, acc);
+  dF = fma(h, kInvPi, h * dacc);
 }
 
 // sample_from_cf (sample_from_cf.jl:27-41) for a given uniform u.
@@ -181,7 +182,7 @@ __device__ BkInversion bk_sample_integral(const BkParams &p, double V0, double V
   const double stop = kBesselPi * p.cf_tol / 2.0;
   for (int j = 1; j <= p.max_terms; ++j) {
     const cplx phi = bk_chf(p, it, h * (double)j, th);
-    tb.set(j - 1, (2.0 / kBesselPi) * phi.re / (double)j);
+    tb.set(j - 1, (2.0 / kBesselPi) * phi.re * rcp_fast((double)j));
     J = j;
     if (cabs2(phi) < (stop * (double)j) * (stop * (double)j)) break;  // |phi| / j < stop
   }
