@@ -146,7 +146,8 @@ HH_HD cplx bessel_series_sum(double nu, cplx w, const double *rk) {
     sum = sum + term;
     term = (term * q) * r2;
     sum = sum + term;
-    if (cabs2(term) < 1e-34 * cabs2(sum)) break;
+    // |term| <= 1e-17 |sum| in the 1-norm (within sqrt 2 of the 2-norm test; two instructions fewer per pair of terms)
+    if (fabs(term.re) + fabs(term.im) < 1e-17 * (fabs(sum.re) + fabs(sum.im))) break;
   }
   return sum;
 }
