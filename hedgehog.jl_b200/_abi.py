@@ -9,7 +9,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-HH_VERSION = 100
+HH_VERSION = 200
 
 HH_OK = 0
 HH_ERR_ARG = -1
@@ -22,7 +22,7 @@ HH_MODEL_GBM, HH_MODEL_HESTON = 0, 1
 HH_SCHEME_EM, HH_SCHEME_EXACT_TERMINAL, HH_SCHEME_EXACT_STEPS, HH_SCHEME_HESTON_BK = 0, 1, 2, 3
 HH_VR_NONE, HH_VR_ANTITHETIC = 0, 1
 HH_PREC_F64, HH_PREC_F32 = 0, 1
-HH_RNG_PHILOX, HH_RNG_NORMALS = 0, 1
+HH_RNG_PHILOX, HH_RNG_NORMALS, HH_RNG_PHILOX_64 = 0, 1, 2
 HH_FLAG_SPLIT_STEP, HH_FLAG_Q1_SQRT_MEAN = 1, 2
 
 
@@ -49,6 +49,7 @@ class hh_sim(C.Structure):
         ("rng_mode", C.c_int32), ("reserved", C.c_int32),
         ("base_seed", C.c_uint64),
         ("seeds", C.POINTER(C.c_uint64)), ("normals", C.POINTER(C.c_double)),
+        ("seeds_len", C.c_uint64), ("normals_len", C.c_uint64),
         ("bk", hh_bk_config),
     ]
 
@@ -110,6 +111,7 @@ SYMBOLS = {
                                  C.POINTER(C.c_size_t)]),
     "hh_default_bk_config": (None, [C.POINTER(hh_bk_config)]),
     "hh_bench_fp64_peak": (C.c_int, [C.c_void_p, _dp, _dp]),
+    "hh_bench_heston_ablation": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, _dp]),
     "hh_mc_european": (C.c_int, [C.c_void_p, C.POINTER(hh_model), C.POINTER(hh_sim), C.POINTER(hh_payoff), C.c_int,
                                  C.c_double, C.POINTER(hh_result), _dp, C.c_size_t]),
     "hh_mc_european_launch": (C.c_int, [C.c_void_p, C.POINTER(hh_model), C.POINTER(hh_sim), C.POINTER(hh_payoff),
@@ -134,6 +136,7 @@ SYMBOLS = {
     "hh_peer_export": (C.c_int, [C.c_void_p, C.POINTER(C.c_ubyte)]),
     "hh_peer_connect": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_ubyte)]),
     "hh_peer_disconnect": (C.c_int, [C.c_void_p]),
+    "hh_peer_set_timeout": (C.c_int, [C.c_void_p, C.c_double]),
 }
 HH_IPC_HANDLE_BYTES = 64
 HH_MAX_PEERS = 16

@@ -1,5 +1,6 @@
 // hh_api.cu — extern "C" surface of libhedgehog_mc.so: context lifetime and the thin wrappers
 // that lock the context and forward to the kernels' host drivers. See include/hedgehog_mc.h.
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -23,6 +24,7 @@ int bk_integral(hh_ctx *ctx, const hh_model *m, double tau, const hh_bk_config *
                 const double *U, int n, double *out8);
 int bk_variance(hh_ctx *ctx, const hh_model *m, double tau, const double *V0, int n, uint64_t seed, double *VT);
 int fp64_peak(hh_ctx *ctx, double *tflops, double *ms);
+int heston_ablation(hh_ctx *ctx, int64_t n_paths, int n_steps, int rng_mode, int part, double *ms);
 }  // namespace hh
 
 extern "C" {
@@ -75,6 +77,12 @@ int hh_create(hh_ctx **out, int device) {
   ctx->l2_bytes = (size_t)prop.l2CacheSize;
   ctx->l2_persist_max = (size_t)prop.persistingL2CacheMaxSize;
   ctx->l2_window_max = (size_t)prop.accessPolicyMaxWindowSize;
+  int khz = 0;
+  if (cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device) == cudaSuccess && khz > 0) ctx->sm_clock_hz = 1e3 * (double)khz;
+  if (const char *ts = getenv("HH_PEER_TIMEOUT_S")) {
+    const double t = atof(ts);
+    if (t > 0.0) ctx->peer_timeout_s = t;
+  }
   bool ok = cudaSetDevice(device) == cudaSuccess &&
             cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) == cudaSuccess &&
             cudaEventCreate(&ctx->ev0) == cudaSuccess && cudaEventCreate(&ctx->ev1) == cudaSuccess &&
@@ -119,7 +127,9 @@ int hh_destroy(hh_ctx *ctx) {
 
 // mailbox layout (doubles): [parity 2][rank HH_MAX_PEERS][kMailSlot] payload, then flags [parity 2][rank] as uint64
 static constexpr size_t kMailSlot = 32;
-static constexpr size_t kMailBytes = 2 * HH_MAX_PEERS * kMailSlot * sizeof(double) + 2 * HH_MAX_PEERS * sizeof(unsigned long long);
+// ... and one "abort" word behind the flags (hh_lsm.cu: mail_abort), padded to 16 bytes
+static constexpr size_t kMailBytes =
+    2 * HH_MAX_PEERS * kMailSlot * sizeof(double) + 2 * HH_MAX_PEERS * sizeof(unsigned long long) + 16;
 
 int hh_peer_export(hh_ctx *ctx, unsigned char handle[HH_IPC_HANDLE_BYTES]) {
   if (!ctx || !handle) return HH_ERR_ARG;
@@ -166,6 +176,14 @@ int hh_peer_connect(hh_ctx *ctx, int rank, int world, const unsigned char *handl
   return HH_OK;
 }
 
+int hh_peer_set_timeout(hh_ctx *ctx, double seconds) {
+  if (!ctx) return HH_ERR_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (!(seconds > 0.0) || seconds > 3600.0) return ctx->fail(HH_ERR_ARG, "peer timeout must be in (0, 3600] seconds (got %g)", seconds);
+  ctx->peer_timeout_s = seconds;
+  return HH_OK;
+}
+
 int hh_peer_disconnect(hh_ctx *ctx) {
   if (!ctx) return HH_ERR_ARG;
   std::lock_guard<std::mutex> lk(ctx->mu);
@@ -202,13 +220,12 @@ int hh_device_info(hh_ctx *ctx, int32_t *sm_count, int32_t *cc_major, int32_t *c
 int hh_bench_fp64_peak(hh_ctx *ctx, double *tflops, double *ms) {
   if (!ctx) return HH_ERR_ARG;
   std::lock_guard<std::mutex> lk(ctx->mu);
+  NvtxRange nv("hh_bench_fp64_peak");
   return hh::fp64_peak(ctx, tflops, ms);
 }
 
-int hh_mc_european_launch(hh_ctx *ctx, const hh_model *model, const hh_sim *sim, const hh_payoff *payoffs, int npayoffs,
-                          int want_terminal) {
-  if (!ctx) return HH_ERR_ARG;
-  std::lock_guard<std::mutex> lk(ctx->mu);
+static int european_launch_locked(hh_ctx *ctx, const hh_model *model, const hh_sim *sim, const hh_payoff *payoffs,
+                                  int npayoffs, int want_terminal) {
   if (sim && sim->scheme == HH_SCHEME_HESTON_BK) {
     int rc = hh::validate_model_sim(ctx, model, sim);
     if (rc) return rc;
@@ -217,17 +234,38 @@ int hh_mc_european_launch(hh_ctx *ctx, const hh_model *model, const hh_sim *sim,
   return hh::european_launch(ctx, model, sim, payoffs, npayoffs, want_terminal);
 }
 
+int hh_bench_heston_ablation(hh_ctx *ctx, int64_t n_paths, int n_steps, int rng_mode, int part, double *ms) {
+  if (!ctx) return HH_ERR_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  NvtxRange nv("hh_bench_heston_ablation");
+  return hh::heston_ablation(ctx, n_paths, n_steps, rng_mode, part, ms);
+}
+
+int hh_mc_european_launch(hh_ctx *ctx, const hh_model *model, const hh_sim *sim, const hh_payoff *payoffs, int npayoffs,
+                          int want_terminal) {
+  if (!ctx) return HH_ERR_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  NvtxRange nv("hh_mc_european_launch");
+  return european_launch_locked(ctx, model, sim, payoffs, npayoffs, want_terminal);
+}
+
 int hh_mc_european_collect(hh_ctx *ctx, double discount, hh_result *results, double *terminal, size_t terminal_len) {
   if (!ctx) return HH_ERR_ARG;
   std::lock_guard<std::mutex> lk(ctx->mu);
+  NvtxRange nv("hh_mc_european_collect");
   return hh::european_collect(ctx, discount, results, terminal, terminal_len);
 }
 
+// The blocking form holds the context mutex across launch AND collect: two threads sharing a context can never collect
+// each other's results (the header promises serialised calls).
 int hh_mc_european(hh_ctx *ctx, const hh_model *model, const hh_sim *sim, const hh_payoff *payoffs, int npayoffs,
                    double discount, hh_result *results, double *terminal, size_t terminal_len) {
-  int rc = hh_mc_european_launch(ctx, model, sim, payoffs, npayoffs, terminal != nullptr);
+  if (!ctx) return HH_ERR_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  NvtxRange nv("hh_mc_european");
+  int rc = european_launch_locked(ctx, model, sim, payoffs, npayoffs, terminal != nullptr);
   if (rc) return rc;
-  return hh_mc_european_collect(ctx, discount, results, terminal, terminal_len);
+  return hh::european_collect(ctx, discount, results, terminal, terminal_len);
 }
 
 int hh_mc_path_dependent(hh_ctx *ctx, const hh_model *model, const hh_sim *sim, int monitor_every,
@@ -235,6 +273,7 @@ int hh_mc_path_dependent(hh_ctx *ctx, const hh_model *model, const hh_sim *sim, 
                          double *path_stats, size_t path_stats_len) {
   if (!ctx) return HH_ERR_ARG;
   std::lock_guard<std::mutex> lk(ctx->mu);
+  NvtxRange nv("hh_mc_path_dependent");
   return hh::path_dependent(ctx, model, sim, monitor_every, payoffs, npayoffs, discount, results, path_stats, path_stats_len);
 }
 
@@ -243,6 +282,7 @@ int hh_mc_european_tangent_sums(hh_ctx *ctx, const hh_model *model, const hh_tan
                                 double *kernel_ms) {
   if (!ctx) return HH_ERR_ARG;
   std::lock_guard<std::mutex> lk(ctx->mu);
+  NvtxRange nv("hh_mc_european_tangent_sums");
   return hh::tangent_sums(ctx, model, tangents, ntangents, sim, payoffs, npayoffs, sums, kernel_ms);
 }
 
@@ -293,6 +333,7 @@ int hh_lsm_american(hh_ctx *ctx, const hh_model *model, const hh_sim *sim, const
                     double *spot_paths) {
   if (!ctx) return HH_ERR_ARG;
   std::lock_guard<std::mutex> lk(ctx->mu);
+  NvtxRange nv("hh_lsm_american");
   return hh::lsm_american(ctx, model, sim, payoff, degree, step_discount, comm, out, stop_idx, stop_val, spot_paths);
 }
 
@@ -300,6 +341,7 @@ int hh_bk_chf(hh_ctx *ctx, const hh_model *model, double tau, const double *V0, 
               int na, double *out_re, double *out_im) {
   if (!ctx) return HH_ERR_ARG;
   std::lock_guard<std::mutex> lk(ctx->mu);
+  NvtxRange nv("hh_bk_chf");
   return hh::bk_chf(ctx, model, tau, V0, VT, n, a, na, out_re, out_im);
 }
 
@@ -307,6 +349,7 @@ int hh_bk_log_besseli(hh_ctx *ctx, double nu, const double *z_re, const double *
                       double *out_im) {
   if (!ctx) return HH_ERR_ARG;
   std::lock_guard<std::mutex> lk(ctx->mu);
+  NvtxRange nv("hh_bk_log_besseli");
   return hh::bk_log_besseli(ctx, nu, z_re, z_im, n, out_re, out_im);
 }
 
@@ -314,12 +357,14 @@ int hh_bk_integral(hh_ctx *ctx, const hh_model *model, double tau, const hh_bk_c
                    const double *VT, const double *u, int n, double *out8) {
   if (!ctx) return HH_ERR_ARG;
   std::lock_guard<std::mutex> lk(ctx->mu);
+  NvtxRange nv("hh_bk_integral");
   return hh::bk_integral(ctx, model, tau, cfg, V0, VT, u, n, out8);
 }
 
 int hh_bk_variance(hh_ctx *ctx, const hh_model *model, double tau, const double *V0, int n, uint64_t seed, double *VT) {
   if (!ctx) return HH_ERR_ARG;
   std::lock_guard<std::mutex> lk(ctx->mu);
+  NvtxRange nv("hh_bk_variance");
   return hh::bk_variance(ctx, model, tau, V0, n, seed, VT);
 }
 

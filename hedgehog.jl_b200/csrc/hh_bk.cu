@@ -469,15 +469,15 @@ static int ensure_slab(hh_ctx *ctx, int nblocks, const BkParams &p, double **sla
 }
 
 static int bk_set_smem(hh_ctx *ctx) {
-  static bool done[64] = {};
-  if (ctx->device < 64 && done[ctx->device]) return HH_OK;
+  static PerDeviceOnce done;
+  if (done.done(ctx->device)) return HH_OK;
   const int bytes = kBkThreads * kBkTable * (int)sizeof(double);
   HH_CUDA(ctx, cudaFuncSetAttribute(bk_paths_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   HH_CUDA(ctx, cudaFuncSetAttribute(bk_paths_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   HH_CUDA(ctx, cudaFuncSetAttribute(bk_paths_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   HH_CUDA(ctx, cudaFuncSetAttribute(bk_paths_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   HH_CUDA(ctx, cudaFuncSetAttribute(bk_integral_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-  if (ctx->device < 64) done[ctx->device] = true;
+  done.set(ctx->device);
   return HH_OK;
 }
 

@@ -2,7 +2,9 @@
 // scratch, last-error text. Host-side only.
 #pragma once
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <mutex>
@@ -35,6 +37,28 @@ struct DeviceBuffer {
     return static_cast<T *>(ptr);
   }
 };
+
+// "Done once PER DEVICE": the opt-in above 48 KB of dynamic shared memory and the constant-table uploads are per device,
+// and contexts on different GPUs may reach the same call site from different threads (each context has its own mutex).
+struct PerDeviceOnce {
+  std::atomic<unsigned long long> mask{0};
+  bool done(int dev) const { return dev >= 0 && dev < 64 && ((mask.load(std::memory_order_acquire) >> dev) & 1ull); }
+  void set(int dev) {
+    if (dev >= 0 && dev < 64) mask.fetch_or(1ull << dev, std::memory_order_release);
+  }
+};
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize for `kern` on the CURRENT device, once per device.
+template <class K>
+inline cudaError_t smem_opt_in(PerDeviceOnce &once, K kern, int bytes) {
+  int dev = -1;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (once.done(dev)) return cudaSuccess;
+  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) once.set(dev);
+  return e;
+}
 
 struct PendingEuropean {
   bool active = false;
@@ -71,6 +95,8 @@ struct hh_ctx {
   void *peer_mail[HH_MAX_PEERS] = {};
   int peer_rank = 0, peer_world = 1;
   unsigned long long peer_epoch = 0;  // advances identically on every rank (one per exchanged date)
+  double peer_timeout_s = 30.0;       // in-kernel limit on one peer wait (hh_peer_set_timeout)
+  double sm_clock_hz = 1.965e9;       // clock64() rate used to turn that limit into cycles
   double bk_stats[5] = {0, 0, 0, 0, 0};
   void *h_pinned = nullptr;  // small pinned staging area for results
   size_t h_pinned_cap = 0;
@@ -93,6 +119,14 @@ struct hh_ctx {
     int code = (e == cudaErrorMemoryAllocation) ? HH_ERR_NOMEM : HH_ERR_CUDA;
     return fail(code, "CUDA error %d (%s) in %s at %s:%d", (int)e, cudaGetErrorString(e), what, file, line);
   }
+};
+
+// NVTX range around a C-ABI call (visible in nsys / ncu --nvtx; a no-op costing a few ns when no tool is attached).
+struct NvtxRange {
+  explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+  NvtxRange(const NvtxRange &) = delete;
+  NvtxRange &operator=(const NvtxRange &) = delete;
 };
 
 #define HH_CUDA(ctx, call)                                                   \

@@ -51,6 +51,8 @@ struct EuroArgs {
   // (as literals the compiler splits it into an AND-immediate and an OR-immediate)
   uint32_t one_hi, magic_hi;  // 0x3FF00000 (high word of 1.0), 0x43300000 (high word of 2^52)
   uint32_t f32_one;           // 0x3F800000 (1.0f)
+  uint32_t lo_fill;           // 0x00080000: the half-ulp bit behind the 32 random mantissa bits (HH_RNG_PHILOX_64)
+  int rng64;                  // HH_RNG_PHILOX_64
 };
 
 // number of accumulators per (block, payoff): sum, sumsq, nonfinite, then per tangent: dsum, dsumsq
@@ -323,6 +325,7 @@ __global__ void __launch_bounds__(kThreads) european_kernel(const EuroArgs a, co
   }
 }
 
+#ifdef HH_TUNING  // the first version of the headline kernel (tables not replicated): kept for A/B timing only
 // ---- the headline kernel: Heston Euler-Maruyama, Float64, native RNG (config C2) -----------------------------
 // Same trajectory arithmetic and payoff transpose as european_kernel, specialised for throughput:
 //   UKEY  the Philox round keys are uniform (base_seed mode) and come from the kernel arguments (constant bank),
@@ -447,6 +450,8 @@ __global__ void __launch_bounds__(kThreads, MINB) heston_fast_kernel(const EuroA
   }
 }
 
+#endif  // HH_TUNING
+
 // ---- v2 of the headline kernel: lane-replicated tables in dynamic shared memory ---------------------------------
 // Same trajectory arithmetic as heston_fast_kernel up to rounding (the drift r dt is added once at expiry, the clamps
 // use one integer max each), but every table read of the step loop is bank-conflict free (hh_fastnormal.cuh, "v2").
@@ -454,7 +459,43 @@ __global__ void __launch_bounds__(kThreads, MINB) heston_fast_kernel(const EuroA
 __host__ __device__ constexpr int fast2_stage_bytes(int threads) { return 3 * threads * 8; }
 __host__ __device__ constexpr int fast2_smem_bytes(int threads) { return fast2_stage_bytes(threads) + kLogRepBytes + kPhaseRepBytes + kExp2Bytes; }
 
-template <bool ANTI, bool SPLIT, bool UKEY, int ILP, int THREADS, int MINB>
+// One Euler-Maruyama step of one trajectory (and its antithetic partner) from the random words of the step:
+// (w0..w3) = one Philox block under HH_RNG_PHILOX, (w0, w1) = half a block under HH_RNG_PHILOX_64 (R64).
+template <bool ANTI, bool SPLIT, bool R64>
+__device__ __forceinline__ void fast2_step(const EuroArgs &a, const char *__restrict__ log_lane,
+                                           const char *__restrict__ exp_biased, const char *__restrict__ phase_lane,
+                                           uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, double &xp, double &vp,
+                                           double &xm, double &vm) {
+  double sn, cs;
+  const double R2 = R64 ? fast_neg2log_32(log_lane, exp_biased, w1, a.one_hi, a.lo_fill)
+                        : fast_neg2log_v2(log_lane, exp_biased, w0, w1, a.one_hi);
+  const uint32_t poff = R64 ? fast_angle_v2(w0, w0, a.magic_hi, sn, cs) : fast_angle_v2(w2, w3, a.magic_hi, sn, cs);
+  const double2 pq1 = *reinterpret_cast<const double2 *>(phase_lane + poff);
+  const double2 pq2 = *reinterpret_cast<const double2 *>(phase_lane + poff + kRep * 16);
+  const double cc1 = fma(pq1.x, cs, pq1.y * sn);
+  const double cc2 = fma(pq2.x, cs, pq2.y * sn);
+  {
+    const double vplus = max0_hi(vp);
+    const double K1 = fma(a.f.neg_half_dt, vplus, xp);
+    const double K2 = fma(a.f.neg_kdt, vplus, vp + a.f.ktdt);
+    const double sr = fast_sqrt_pos5(max_tiny_hi((SPLIT ? K2 : vplus) * R2));
+    xp = fma(sr, cc1, K1);
+    vp = fma(sr, cc2, K2);
+  }
+  if (ANTI) {
+    const double vplus = max0_hi(vm);
+    const double K1 = fma(a.f.neg_half_dt, vplus, xm);
+    const double K2 = fma(a.f.neg_kdt, vplus, vm + a.f.ktdt);
+    const double sr = fast_sqrt_pos5(max_tiny_hi((SPLIT ? K2 : vplus) * R2));
+    xm = fma(-sr, cc1, K1);
+    vm = fma(-sr, cc2, K2);
+  }
+}
+
+// R64: the HH_RNG_PHILOX_64 stream (one Philox block per two steps, hh_fastnormal.cuh).
+// ABL: ablation for hh_bench_heston_ablation — 0 the product kernel; 1 Philox replaced by a counter hash (what the
+// table-driven Box-Muller and the step cost alone); 2 Philox only (its words XOR-folded into the state, no FP64 work).
+template <bool ANTI, bool SPLIT, bool UKEY, int ILP, int THREADS, int MINB, bool R64 = false, int ABL = 0>
 __global__ void __launch_bounds__(THREADS, MINB) heston_fast2_kernel(const EuroArgs a) {
   constexpr int NACC = 3;
   constexpr int kThreads = THREADS;  // shadows the file-scope block size
@@ -515,35 +556,40 @@ __global__ void __launch_bounds__(THREADS, MINB) heston_fast2_kernel(const EuroA
         rk[UKEY ? 0 : j] = philox_round_keys(a.seeds[ic]);
       }
     }
+    uint32_t fold[ILP];  // ABL == 2 only
+#pragma unroll
+    for (int j = 0; j < ILP; ++j) fold[j] = 0u;
+    constexpr int kStepsPerBlock = R64 ? 2 : 1;
+    constexpr uint32_t kStreamWord = R64 ? 2u : 0u;  // f32 fast mode: 1
 #pragma unroll 1
-    for (int n = 0; n < M; ++n) {
+    for (int n = 0; n < M; n += kStepsPerBlock) {
 #pragma unroll
       for (int j = 0; j < ILP; ++j) {
-        const u32x4 w = philox4x32_10_rk(c0[j], c1[j], (uint32_t)n, 0u, UKEY ? a.rk : rk[UKEY ? 0 : j]);
-        const double R2 = fast_neg2log_v2(log_lane, exp_biased, w.x, w.y, a.one_hi);
-        double sn, cs;
-        const uint32_t poff = fast_angle_v2(w.z, w.w, a.magic_hi, sn, cs);
-        const double2 pq1 = *reinterpret_cast<const double2 *>(phase_lane + poff);
-        const double2 pq2 = *reinterpret_cast<const double2 *>(phase_lane + poff + kRep * 16);
-        const double cc1 = fma(pq1.x, cs, pq1.y * sn);
-        const double cc2 = fma(pq2.x, cs, pq2.y * sn);
-        {
-          const double vplus = max0_hi(vp[j]);
-          const double K1 = fma(a.f.neg_half_dt, vplus, xp[j]);
-          const double K2 = fma(a.f.neg_kdt, vplus, vp[j] + a.f.ktdt);
-          const double sr = fast_sqrt_pos5(max_tiny_hi((SPLIT ? K2 : vplus) * R2));
-          xp[j] = fma(sr, cc1, K1);
-          vp[j] = fma(sr, cc2, K2);
+        u32x4 w;
+        if (ABL == 1) {  // no Philox: a counter hash, so that the table indices still vary
+          const uint32_t t = (c0[j] + (uint32_t)n) * 0x9E3779B9u;
+          w.x = t;
+          w.y = (t >> 7) ^ (uint32_t)n;
+          w.z = t ^ 0x5555AAAAu;
+          w.w = ~t;
+        } else {
+          w = philox4x32_10_rk(c0[j], c1[j], (uint32_t)(R64 ? n >> 1 : n), kStreamWord, UKEY ? a.rk : rk[UKEY ? 0 : j]);
         }
-        if (ANTI) {
-          const double vplus = max0_hi(vm[j]);
-          const double K1 = fma(a.f.neg_half_dt, vplus, xm[j]);
-          const double K2 = fma(a.f.neg_kdt, vplus, vm[j] + a.f.ktdt);
-          const double sr = fast_sqrt_pos5(max_tiny_hi((SPLIT ? K2 : vplus) * R2));
-          xm[j] = fma(-sr, cc1, K1);
-          vm[j] = fma(-sr, cc2, K2);
+        if (ABL == 2) {
+          fold[j] ^= w.x ^ w.y ^ w.z ^ w.w;
+          continue;
         }
+        // Box-Muller folded into the step: with (z1, z2) = rad (cos th, sin th),
+        //   dW1 = rad c1,  xi dW2 = rad c2,  c_i = P_i cos(delta) + Q_i sin(delta)   (phase table: rotation x correlation)
+        //   s dW = sqrt(K2+ R2) c        (ONE square root for diffusion and radius)
+        fast2_step<ANTI, SPLIT, R64>(a, log_lane, exp_biased, phase_lane, w.x, w.y, w.z, w.w, xp[j], vp[j], xm[j], vm[j]);
+        if (R64 && n + 1 < M)
+          fast2_step<ANTI, SPLIT, true>(a, log_lane, exp_biased, phase_lane, w.z, w.w, 0u, 0u, xp[j], vp[j], xm[j], vm[j]);
       }
+    }
+    if (ABL == 2) {
+#pragma unroll
+      for (int j = 0; j < ILP; ++j) xp[j] = __hiloint2double((int)(fold[j] & 0x000FFFFFu) | 0x3FF00000, (int)fold[j]);
     }
 #pragma unroll
     for (int j = 0; j < ILP; ++j) {
@@ -1126,10 +1172,25 @@ int validate_model_sim(hh_ctx *ctx, const hh_model *m, const hh_sim *s) {
     return ctx->fail(HH_ERR_ARG, "n_steps must be positive (got %d)", s->n_steps);
   if (s->vr != HH_VR_NONE && s->vr != HH_VR_ANTITHETIC)
     return ctx->fail(HH_ERR_ARG, "unknown variance reduction %d", s->vr);
-  if (s->rng_mode != HH_RNG_NORMALS && s->rng_mode != HH_RNG_PHILOX)
+  if (s->rng_mode != HH_RNG_NORMALS && s->rng_mode != HH_RNG_PHILOX && s->rng_mode != HH_RNG_PHILOX_64)
     return ctx->fail(HH_ERR_ARG, "unknown rng_mode %d", s->rng_mode);
   if (s->rng_mode == HH_RNG_NORMALS && !s->normals)
     return ctx->fail(HH_ERR_ARG, "rng_mode = HH_RNG_NORMALS needs a normals buffer");
+  if (s->rng_mode == HH_RNG_PHILOX_64 &&
+      !(m->kind == HH_MODEL_HESTON && s->scheme == HH_SCHEME_EM && s->precision == HH_PREC_F64))
+    return ctx->fail(HH_ERR_UNSUPPORTED, "HH_RNG_PHILOX_64 is defined for HestonDynamics + EulerMaruyama in f64");
+  // the lengths behind the caller's pointers (the copies below read exactly this many elements)
+  if (s->rng_mode == HH_RNG_NORMALS) {
+    const uint64_t ncomp = m->kind == HH_MODEL_HESTON ? 2 : 1;
+    const uint64_t nst = s->scheme == HH_SCHEME_EXACT_TERMINAL ? 1 : (uint64_t)(s->n_steps > 0 ? s->n_steps : 0);
+    const uint64_t need = (uint64_t)s->n_paths * nst * ncomp;
+    if (s->normals_len < need)
+      return ctx->fail(HH_ERR_ARG, "normals buffer too short: %llu elements for n_paths x n_steps x components = %llu",
+                       (unsigned long long)s->normals_len, (unsigned long long)need);
+  } else if (s->seeds && s->seeds_len < (uint64_t)s->n_paths) {  // montecarlo.jl:65-66
+    return ctx->fail(HH_ERR_ARG, "Number of seeds (%llu) must be >= number of trajectories (%lld).",
+                     (unsigned long long)s->seeds_len, (long long)s->n_paths);
+  }
   if (m->kind == HH_MODEL_GBM) {
     if (s->scheme != HH_SCHEME_EM && s->scheme != HH_SCHEME_EXACT_TERMINAL && s->scheme != HH_SCHEME_EXACT_STEPS)
       return ctx->fail(HH_ERR_ARG, "scheme %d is not defined for LognormalDynamics", s->scheme);
@@ -1198,6 +1259,7 @@ static cudaError_t launch_kind(const EuroArgs &a, const TangentPack *tp, int P, 
   }
 }
 
+#ifdef HH_TUNING
 template <bool ANTI, bool SPLIT, bool UKEY, int ILP, int MINB>
 static cudaError_t launch_fast_one(const EuroArgs &a, int sm_count, cudaStream_t st, int *nblocks, bool query_only) {
   auto kern = heston_fast_kernel<ANTI, SPLIT, UKEY, ILP, MINB>;
@@ -1214,16 +1276,13 @@ static cudaError_t launch_fast_one(const EuroArgs &a, int sm_count, cudaStream_t
   kern<<<(unsigned)grid, kThreads, 0, st>>>(a);
   return cudaGetLastError();
 }
+#endif
 
-template <bool ANTI, bool SPLIT, bool UKEY, int ILP, int THREADS, int MINB>
+template <bool ANTI, bool SPLIT, bool UKEY, int ILP, int THREADS, int MINB, bool R64 = false, int ABL = 0>
 static cudaError_t launch_fast2_one(const EuroArgs &a, int sm_count, cudaStream_t st, int *nblocks, bool query_only) {
-  auto kern = heston_fast2_kernel<ANTI, SPLIT, UKEY, ILP, THREADS, MINB>;
-  static bool attr_set = false;  // per instantiation
-  if (!attr_set) {
-    cudaError_t e0 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, fast2_smem_bytes(THREADS));
-    if (e0 != cudaSuccess) return e0;
-    attr_set = true;
-  }
+  auto kern = heston_fast2_kernel<ANTI, SPLIT, UKEY, ILP, THREADS, MINB, R64, ABL>;
+  static PerDeviceOnce opted;  // per instantiation and device
+  if (cudaError_t e0 = smem_opt_in(opted, kern, fast2_smem_bytes(THREADS)); e0 != cudaSuccess) return e0;
   int occ = 0;
   cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, fast2_smem_bytes(THREADS));
   if (e != cudaSuccess) return e;
@@ -1238,35 +1297,42 @@ static cudaError_t launch_fast2_one(const EuroArgs &a, int sm_count, cudaStream_
   return cudaGetLastError();
 }
 
-// variant: tuning knob (HH_HESTON_VARIANT) — 0 is the shipped default
-template <bool ANTI, bool SPLIT, bool UKEY>
+// Block shape of the headline kernel, measured on B200 at 1e8 x 252: 1024 threads x ILP 1 99.4 ms, 256 x ILP 2 100.9 ms,
+// 512 x ILP 1 102.5 ms (all within 3 %: the kernel is dispatch-bound, occupancy hardly matters); small jobs keep the
+// 256-thread blocks so that every SM gets work. The other shapes that were tried (HH_HESTON_VARIANT) are compiled only
+// with -DHH_TUNING.
+template <bool ANTI, bool SPLIT, bool UKEY, bool R64>
 static cudaError_t launch_fast_v(const EuroArgs &a, int variant, int sm_count, cudaStream_t st, int *nb, bool q) {
-  switch (variant) {
-    // measured on B200, 1e7 x 252 (tools/time_heston.py): ILP 2 / 2 blocks per SM 12.75 ms, ILP 1 / 4 blocks 13.42 ms,
-    // ILP 1 / 6 blocks 13.83 ms — the kernel is issue-bound, occupancy hardly matters
-    case 1: return launch_fast_one<ANTI, SPLIT, UKEY, 1, 4>(a, sm_count, st, nb, q);
-    case 2: return launch_fast_one<ANTI, SPLIT, UKEY, 1, 6>(a, sm_count, st, nb, q);
-    case 3: return launch_fast_one<ANTI, SPLIT, UKEY, 2, 3>(a, sm_count, st, nb, q);
-    case 4: return launch_fast_one<ANTI, SPLIT, UKEY, 2, 2>(a, sm_count, st, nb, q);  // v1 (tables not replicated)
-    case 5: return launch_fast2_one<ANTI, SPLIT, UKEY, 1, 256, 2>(a, sm_count, st, nb, q);
-    case 6: return launch_fast2_one<ANTI, SPLIT, UKEY, 1, 512, 2>(a, sm_count, st, nb, q);   // 32 warps per SM, <= 64 registers
-    case 7: return launch_fast2_one<ANTI, SPLIT, UKEY, 1, 1024, 1>(a, sm_count, st, nb, q);  // same, one block per SM
-    case 8: return launch_fast2_one<ANTI, SPLIT, UKEY, 2, 512, 1>(a, sm_count, st, nb, q);   // 16 warps, one block
-    case 9: return launch_fast2_one<ANTI, SPLIT, UKEY, 1, 768, 1>(a, sm_count, st, nb, q);   // 24 warps, <= 80 registers
-    case 10: return launch_fast2_one<ANTI, SPLIT, UKEY, 2, 256, 2>(a, sm_count, st, nb, q);
-    default:
-      // measured on B200 at 1e8 x 252: 1024 threads x ILP 1 99.4 ms, 256 x ILP 2 100.9 ms, 512 x ILP 1 102.5 ms (all within
-      // 3 %: the kernel is dispatch-bound, occupancy hardly matters); small jobs keep the 256-thread blocks so that
-      // every SM gets work
-      if (a.n >= (int64_t)sm_count * 1024 * 4) return launch_fast2_one<ANTI, SPLIT, UKEY, 1, 1024, 1>(a, sm_count, st, nb, q);
-      return launch_fast2_one<ANTI, SPLIT, UKEY, 2, 256, 2>(a, sm_count, st, nb, q);
+#ifdef HH_TUNING
+  if (!R64) {
+    switch (variant) {
+      // measured on B200, 1e7 x 252 (tools/time_heston.py): ILP 2 / 2 blocks per SM 12.75 ms, ILP 1 / 4 blocks 13.42 ms,
+      // ILP 1 / 6 blocks 13.83 ms — the kernel is issue-bound, occupancy hardly matters
+      case 1: return launch_fast_one<ANTI, SPLIT, UKEY, 1, 4>(a, sm_count, st, nb, q);
+      case 2: return launch_fast_one<ANTI, SPLIT, UKEY, 1, 6>(a, sm_count, st, nb, q);
+      case 3: return launch_fast_one<ANTI, SPLIT, UKEY, 2, 3>(a, sm_count, st, nb, q);
+      case 4: return launch_fast_one<ANTI, SPLIT, UKEY, 2, 2>(a, sm_count, st, nb, q);  // v1 (tables not replicated)
+      case 5: return launch_fast2_one<ANTI, SPLIT, UKEY, 1, 256, 2>(a, sm_count, st, nb, q);
+      case 6: return launch_fast2_one<ANTI, SPLIT, UKEY, 1, 512, 2>(a, sm_count, st, nb, q);   // 32 warps per SM, <= 64 registers
+      case 8: return launch_fast2_one<ANTI, SPLIT, UKEY, 2, 512, 1>(a, sm_count, st, nb, q);   // 16 warps, one block
+      case 9: return launch_fast2_one<ANTI, SPLIT, UKEY, 1, 768, 1>(a, sm_count, st, nb, q);   // 24 warps, <= 80 registers
+      default: break;
+    }
   }
+#endif
+  (void)variant;
+  if (a.n >= (int64_t)sm_count * 1024 * 4) return launch_fast2_one<ANTI, SPLIT, UKEY, 1, 1024, 1, R64>(a, sm_count, st, nb, q);
+  return launch_fast2_one<ANTI, SPLIT, UKEY, 2, 256, 2, R64>(a, sm_count, st, nb, q);
 }
 
 static cudaError_t launch_fast(const EuroArgs &a, bool anti, int sm_count, cudaStream_t st, int *nb, bool q) {
   static const int variant = getenv("HH_HESTON_VARIANT") ? atoi(getenv("HH_HESTON_VARIANT")) : 0;
   const bool ukey = a.seeds == nullptr;
-#define HH_FAST(A, S, U) return launch_fast_v<A, S, U>(a, variant, sm_count, st, nb, q)
+#define HH_FAST(A, S, U)                                                                    \
+  do {                                                                                      \
+    if (a.rng64) return launch_fast_v<A, S, U, true>(a, variant, sm_count, st, nb, q);      \
+    return launch_fast_v<A, S, U, false>(a, variant, sm_count, st, nb, q);                  \
+  } while (0)
   if (anti) {
     if (a.split) { if (ukey) HH_FAST(true, true, true); else HH_FAST(true, true, false); }
     else { if (ukey) HH_FAST(true, false, true); else HH_FAST(true, false, false); }
@@ -1330,12 +1396,8 @@ static cudaError_t launch_tangent_one(const EuroArgs &a, const HestonTanConsts &
   auto kern = heston_tangent_kernel<ANTI, SPLIT, NF, P>;
   constexpr int NACC = 3 + 2 * P, STAGE = (1 + P) * (ANTI ? 2 : 1) * kThreads, RED = NACC * kThreads;
   constexpr int smem = (STAGE > RED ? STAGE : RED) * 8 + kLogRepBytes + kTrigRepBytes + kExp2Bytes;
-  static bool attr_set = false;  // per instantiation
-  if (!attr_set) {
-    cudaError_t e0 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e0 != cudaSuccess) return e0;
-    attr_set = true;
-  }
+  static PerDeviceOnce opted;  // per instantiation and device
+  if (cudaError_t e0 = smem_opt_in(opted, kern, smem); e0 != cudaSuccess) return e0;
   int occ = 0;
   cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, smem);
   if (e != cudaSuccess) return e;
@@ -1382,12 +1444,8 @@ static cudaError_t launch_gbm_fast_cfg(const EuroArgs &a, int sm_count, cudaStre
   constexpr int kThreads = THREADS;
   auto kern = gbm_fast_kernel<KIND, ANTI, UKEY, ILP, THREADS>;
   constexpr int smem = gbm_fast_smem(ANTI, THREADS, KIND == K_GBM_STEPS);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e0 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e0 != cudaSuccess) return e0;
-    attr_set = true;
-  }
+  static PerDeviceOnce opted;  // per instantiation and device
+  if (cudaError_t e0 = smem_opt_in(opted, kern, smem); e0 != cudaSuccess) return e0;
   int occ = 0;
   cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, smem);
   if (e != cudaSuccess) return e;
@@ -1457,6 +1515,8 @@ static int build_args(hh_ctx *ctx, const hh_model *m, const hh_sim *s, const hh_
   a.one_hi = 0x3FF00000u;
   a.magic_hi = 0x43300000u;
   a.f32_one = 0x3F800000u;
+  a.lo_fill = 0x00080000u;
+  a.rng64 = s->rng_mode == HH_RNG_PHILOX_64;
   PathParams<double> &p = a.p;
   const double dt = m->T / nsteps;  // montecarlo.jl:349
   const double sqdt = sqrt(dt);
@@ -1789,6 +1849,9 @@ int tangent_sums(hh_ctx *ctx, const hh_model *m, const hh_tangent *tg, int ntan,
   if (s->scheme == HH_SCHEME_HESTON_BK)
     return ctx->fail(HH_ERR_UNSUPPORTED, "pathwise tangents are not defined through the Broadie-Kaya sampler");
   if (s->precision != HH_PREC_F64) return ctx->fail(HH_ERR_UNSUPPORTED, "tangents run in f64 only");
+  if (s->rng_mode == HH_RNG_PHILOX_64) return ctx->fail(HH_ERR_UNSUPPORTED, "HH_RNG_PHILOX_64 prices only; tangents run on HH_RNG_PHILOX");
+  // d_partials / d_final are shared with a pending hh_mc_european_launch
+  if (ctx->pend.active) return ctx->fail(HH_ERR_ARG, "a European launch is pending on this context: collect it first");
 
   const bool anti = s->vr == HH_VR_ANTITHETIC;
   const int P = ntan <= 1 ? 1 : ntan <= 2 ? 2 : ntan <= 4 ? 4 : 8;
@@ -1870,6 +1933,53 @@ int tangent_sums(hh_ctx *ctx, const hh_model *m, const hh_tangent *tg, int ntan,
       o[2 + ntan + order[kq]] = f[3 + P + kq];
     }
   }
+  return HH_OK;
+}
+
+// hh_bench_heston_ablation: the headline instantiation (no antithetic, split step, base-seed keys, 1024 threads) with one
+// part of its step removed, on the C2 model. One launch, timed with events on the context stream.
+int heston_ablation(hh_ctx *ctx, int64_t n_paths, int n_steps, int rng_mode, int part, double *ms_out) {
+  if (!ms_out || n_paths < 1 || n_steps < 1) return ctx->fail(HH_ERR_ARG, "ablation: n_paths, n_steps >= 1 and ms non-NULL");
+  if (rng_mode != HH_RNG_PHILOX && rng_mode != HH_RNG_PHILOX_64) return ctx->fail(HH_ERR_ARG, "ablation: rng_mode must be a Philox stream");
+  if (part < 0 || part > 2) return ctx->fail(HH_ERR_ARG, "ablation: part must be 0, 1 or 2");
+  if (ctx->pend.active) return ctx->fail(HH_ERR_ARG, "a European launch is pending on this context: collect it first");
+  hh_model m;
+  memset(&m, 0, sizeof m);
+  m.kind = HH_MODEL_HESTON;
+  m.flags = HH_FLAG_SPLIT_STEP;
+  m.S0 = 100.0, m.r = 0.03, m.T = 1.0, m.V0 = 0.04, m.kappa = 2.0, m.theta = 0.04, m.xi = 0.3, m.rho = -0.7;
+  m.m11 = 1.0, m.m12 = 0.0, m.m21 = m.rho, m.m22 = sqrt(1.0 - m.rho * m.rho);
+  hh_sim s;
+  memset(&s, 0, sizeof s);
+  s.n_paths = n_paths, s.n_steps = n_steps, s.scheme = HH_SCHEME_EM, s.rng_mode = rng_mode, s.base_seed = 42;
+  const hh_payoff pay = {100.0, 1.0};
+  EuroArgs a;
+  TangentPack tp;
+  int kind = 0;
+  build_args(ctx, &m, &s, nullptr, 0, a, tp, kind);
+  HH_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  int rc = upload_inputs(ctx, &m, &s, &pay, 1, a);
+  if (rc) return rc;
+  int nb = 0;
+  HH_CUDA(ctx, (launch_fast2_one<false, true, true, 1, 1024, 1>(a, ctx->sm_count, st, &nb, true)));
+  HH_CUDA(ctx, ctx->d_partials.ensure(sizeof(double) * (size_t)nb * 3));
+  a.partials = ctx->d_partials.as<double>();
+  HH_CUDA(ctx, cudaEventRecord(ctx->ev0, st));
+  cudaError_t e = cudaErrorInvalidValue;
+  const bool r64 = rng_mode == HH_RNG_PHILOX_64;
+  if (part == 0) e = r64 ? launch_fast2_one<false, true, true, 1, 1024, 1, true, 0>(a, ctx->sm_count, st, &nb, false)
+                         : launch_fast2_one<false, true, true, 1, 1024, 1, false, 0>(a, ctx->sm_count, st, &nb, false);
+  if (part == 1) e = r64 ? launch_fast2_one<false, true, true, 1, 1024, 1, true, 1>(a, ctx->sm_count, st, &nb, false)
+                         : launch_fast2_one<false, true, true, 1, 1024, 1, false, 1>(a, ctx->sm_count, st, &nb, false);
+  if (part == 2) e = r64 ? launch_fast2_one<false, true, true, 1, 1024, 1, true, 2>(a, ctx->sm_count, st, &nb, false)
+                         : launch_fast2_one<false, true, true, 1, 1024, 1, false, 2>(a, ctx->sm_count, st, &nb, false);
+  HH_CUDA(ctx, e);
+  HH_CUDA(ctx, cudaEventRecord(ctx->ev1, st));
+  HH_CUDA(ctx, cudaStreamSynchronize(st));
+  float ms = 0.f;
+  HH_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+  *ms_out = ms;
   return HH_OK;
 }
 

@@ -14,6 +14,9 @@
 // Accuracy: each normal is within ~4e-16 (absolute) of the libm evaluation of the same formulas, checked
 // per path against the oracle by tests/test_gpu_european.py.
 #pragma once
+#include <mutex>
+
+#include "hh_ctx.h"
 #include "hh_device.cuh"
 #include "hh_tables.h"
 
@@ -29,15 +32,18 @@ struct FastNormalTables {
 static __device__ FastNormalTables g_fast_tables;
 
 static inline cudaError_t upload_fast_tables(int device, cudaStream_t st) {
-  static bool done[64] = {};
-  if (device >= 0 && device < 64 && done[device]) return cudaSuccess;
+  static PerDeviceOnce done;   // per device; contexts on different GPUs may arrive here from different threads
+  static std::mutex mu;        // guards the static host image below
+  if (done.done(device)) return cudaSuccess;
+  std::lock_guard<std::mutex> lk(mu);
+  if (done.done(device)) return cudaSuccess;
   static FastNormalTables h;  // static: must outlive the async copy
   for (int i = 0; i < tables::kLogBuckets; ++i) h.log_tab[i] = make_double2(tables::kLogTab[i][0], tables::kLogTab[i][1]);
   for (int i = 0; i < tables::kTrigN; ++i) h.trig_tab[i] = make_double2(tables::kTrigTab[i][0], tables::kTrigTab[i][1]);
   for (int i = 0; i < tables::kExpN; ++i) h.exp_tab[i] = tables::kExpTab[i];
   cudaError_t e = cudaMemcpyToSymbolAsync(g_fast_tables, &h, sizeof h, 0, cudaMemcpyHostToDevice, st);
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-  if (e == cudaSuccess && device >= 0 && device < 64) done[device] = true;
+  if (e == cudaSuccess) done.set(device);
   return e;
 }
 
@@ -192,15 +198,18 @@ struct FastTables2 {
 static __device__ FastTables2 g_fast_tables2;
 
 static inline cudaError_t upload_fast_tables2(int device, cudaStream_t st) {
-  static bool done[64] = {};
-  if (device >= 0 && device < 64 && done[device]) return cudaSuccess;
+  static PerDeviceOnce done;
+  static std::mutex mu;
+  if (done.done(device)) return cudaSuccess;
+  std::lock_guard<std::mutex> lk(mu);
+  if (done.done(device)) return cudaSuccess;
   static FastTables2 h;
   for (int i = 0; i < tables::kLog2Buckets; ++i) h.log_tab[i] = make_double2(tables::kLog2Tab[i][0], tables::kLog2Tab[i][1]);
   for (int i = 0; i < tables::kTrigN; ++i) h.trig_tab[i] = make_double2(tables::kTrig2Tab[i][0], tables::kTrig2Tab[i][1]);
   for (int i = 0; i < tables::kExp2N; ++i) h.exp_tab[i] = tables::kExp2Tab[i];
   cudaError_t e = cudaMemcpyToSymbolAsync(g_fast_tables2, &h, sizeof h, 0, cudaMemcpyHostToDevice, st);
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-  if (e == cudaSuccess && device >= 0 && device < 64) done[device] = true;
+  if (e == cudaSuccess) done.set(device);
   return e;
 }
 
@@ -252,6 +261,39 @@ __device__ __forceinline__ uint32_t fast_angle_v2(uint32_t w2, uint32_t w3, uint
   return poff;
 }
 
+// ---- HH_RNG_PHILOX_64: 64 random bits per Heston step (one Philox4x32-10 block per TWO steps) -------------------------
+// Philox is the largest single cost of the headline kernel (18 IMAD.WIDE + 20 LOP3 of its 93 instructions per step), and
+// the 52-bit construction above uses 104 of the 128 bits of a block. The opt-in stream halves that cost: step n takes
+// words (wa, wb) = (0, 1) of block n/2 when n is even and words (2, 3) when n is odd (counter stream word 2), as
+//   angle   the 52-bit construction fed with wa twice: n2 = (wa & 0xFFFFF) << 32 | wa, theta = 2 pi n2 2^-52
+//           = 2 pi (rotl(wa, 12) + d) 2^-32 with a sub-grid dither d = (wa & 0xFFFFF) 2^-20 in [0, 1): 2^32 equally likely
+//           angles, one per cell of the 2^32 grid (the angle is periodic: no edge cell) — the same instructions as above;
+//   radius  y1 = double{hi = 0x3FF00000 | (wb & 0xFFFFF), lo = (wb & 0xFFF00000) | 0x80000},  u1 = 2 - y1
+//           = 1 - (rotl(wb, 12) + 1/2) 2^-32: the midpoints of the 2^32 grid, u1 in [2^-33, 1 - 2^-33], |z| <= 6.77.
+// Everything after the bits is the same f64 arithmetic (restated in oracle/hh_oracle.c: hho_normal_pair64).
+
+// R2 = -2 ln(u1) from the two words of y1 (see fast_neg2log_v2 for the table layout)
+__device__ __forceinline__ double fast_neg2log_words(const char *__restrict__ log_lane, const char *__restrict__ exp_biased,
+                                                     uint32_t y_lo, uint32_t y_hi, uint32_t one_hi) {
+  const double y1 = __hiloint2double((int)y_hi, (int)y_lo);
+  const double u1 = 2.0 - y1;  // exact
+  const uint32_t uh = (uint32_t)__double2hiint(u1);
+  const uint32_t boff = (uh >> 5) & 0x7F80u;
+  const uint32_t eoff = ((uh + kLog2Carry) >> 17) & 0x3FF8u;
+  const double f = __hiloint2double((int)((uh & 0xFFFFFu) | one_hi), __double2loint(u1));
+  const double2 lt = *reinterpret_cast<const double2 *>(log_lane + boff);
+  const double L = *reinterpret_cast<const double *>(exp_biased + eoff) + lt.y;
+  const double r = fma(f, lt.x, -1.0);
+  double p = fma(kFN2.l5, r, 0.5);
+  p = fma(p, r, kFN2.l3);
+  p = fma(p, r, 1.0);
+  p = fma(p, r, -2.0);
+  return fma(p, r, L);
+}
+__device__ __forceinline__ double fast_neg2log_32(const char *__restrict__ log_lane, const char *__restrict__ exp_biased,
+                                                  uint32_t wb, uint32_t one_hi, uint32_t lo_fill) {
+  return fast_neg2log_words(log_lane, exp_biased, (wb & 0xFFF00000u) | lo_fill, (wb & 0xFFFFFu) | one_hi, one_hi);
+}
 // The full Box-Muller pair from the lane-replicated v2 tables (kernels that need z1 and z2 themselves: the LSM path
 // generator). trig_lane = replicated {cos, sin}((j + 1/2) 2 pi / 256) table + (lane & 7) * 16 bytes, entry stride 128 B.
 __device__ __forceinline__ double fast_sqrt_pos5(double x);

@@ -249,6 +249,7 @@ struct PeerX {
   unsigned long long epoch;  // unique per exchanged date, identical on every rank; its parity selects the slot
   double *mail[HH_MAX_PEERS];
   int *error;                // set to 1 if a peer's contribution did not arrive in time
+  long long timeout_cycles;  // in-kernel limit on one wait (hh_peer_set_timeout; SM clock cycles)
 };
 
 struct LsmPassArgs {
@@ -276,6 +277,11 @@ __device__ __forceinline__ double *mail_payload(double *mail, int parity, int ra
 }
 __device__ __forceinline__ unsigned long long *mail_flag(double *mail, int parity, int rank) {
   return reinterpret_cast<unsigned long long *>(mail + 2 * HH_MAX_PEERS * kMailSlot) + parity * HH_MAX_PEERS + rank;
+}
+// "abort" word behind the flags: a rank that gives up waiting sets it in EVERY rank's mailbox, so that all ranks leave
+// the exchange with the same error instead of one raising while the others finish (and later hang in a host collective)
+__device__ __forceinline__ unsigned long long *mail_abort(double *mail) {
+  return reinterpret_cast<unsigned long long *>(mail + 2 * HH_MAX_PEERS * kMailSlot) + 2 * HH_MAX_PEERS;
 }
 
 template <int DEG>
@@ -514,17 +520,28 @@ __device__ __forceinline__ void lsm_peer_exchange(const PeerX &px, unsigned long
   if (tid < px.world) {
     unsigned long long *f = mail_flag(px.mail[tid], parity, px.rank);
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(epoch) : "memory");
-    // wait for rank `tid`'s flag in MY mailbox (bounded: ~2 s at 2 GHz, then flag the error and go on)
+    // wait for rank `tid`'s flag in MY mailbox, bounded by px.timeout_cycles (hh_peer_set_timeout). Giving up poisons
+    // every rank's mailbox, and a poisoned mailbox ends every wait: all ranks return HH_ERR_PEER_TIMEOUT together.
     const unsigned long long *mine = mail_flag(px.mail[px.rank], parity, tid);
+    const unsigned long long *poison = mail_abort(px.mail[px.rank]);
     const long long t0 = clock64();
-    unsigned long long seen = 0;
+    unsigned long long seen = 0, ab = 0;
     bool dead = *reinterpret_cast<volatile int *>(px.error) != 0;
+    unsigned spins = 0;
     while (!dead) {
       asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(mine) : "memory");
       if (seen >= epoch) break;
-      if (clock64() - t0 > 4000000000ll) {
-        *px.error = 1;
-        dead = true;
+      if ((++spins & 63u) == 0u) {
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(ab) : "l"(poison) : "memory");
+        if (ab != 0ull) {
+          *px.error = 1;
+          dead = true;
+        } else if (clock64() - t0 > px.timeout_cycles) {
+          for (int qq = 0; qq < px.world; ++qq)
+            asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(mail_abort(px.mail[qq])), "l"(1ull) : "memory");
+          *px.error = 1;
+          dead = true;
+        }
       }
       __nanosleep(64);
     }
@@ -1119,12 +1136,8 @@ static cudaError_t launch_pass_deg(int deg, const LsmPassArgs &a, int grid, cuda
 template <int DEG, bool TAU>
 static cudaError_t launch_backward(const LsmBackArgs &b, int sm_count, int64_t nchunks, cudaStream_t st, bool query_only, int *grid_out) {
   auto kern = lsm_backward_kernel<DEG, TAU>;
-  static bool attr_set = false;  // per instantiation
-  if (!attr_set) {
-    cudaError_t e0 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kBackSmem);
-    if (e0 != cudaSuccess) return e0;
-    attr_set = true;
-  }
+  static PerDeviceOnce opted;  // per instantiation and device
+  if (cudaError_t e0 = smem_opt_in(opted, kern, kBackSmem); e0 != cudaSuccess) return e0;
   int occ = 0;
   cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kBackThreads, kBackSmem);
   if (e != cudaSuccess) return e;
@@ -1171,6 +1184,8 @@ int lsm_american(hh_ctx *ctx, const hh_model *m, const hh_sim *s, const hh_payof
   int rc = validate_model_sim(ctx, m, s);
   if (rc) return rc;
   if (!payoff || !out) return ctx->fail(HH_ERR_ARG, "payoff/out is NULL");
+  if (ctx->pend.active) return ctx->fail(HH_ERR_ARG, "a European launch is pending on this context: collect it first");
+  if (s->rng_mode == HH_RNG_PHILOX_64) return ctx->fail(HH_ERR_UNSUPPORTED, "HH_RNG_PHILOX_64 covers European pricing only");
   if (degree < 0 || degree > kLsmMaxDeg) return ctx->fail(HH_ERR_ARG, "degree must be in [0, %d] (got %d)", kLsmMaxDeg, degree);
   // Q7: the reference reads component 1 of the saved state as the spot (least_squares_montecarlo.jl:53), which is
   // only true for the S-space BlackScholesExact generator — the only LSM configuration it tests.
@@ -1310,12 +1325,8 @@ int lsm_american(hh_ctx *ctx, const hh_model *m, const hh_sim *s, const hh_payof
     cudaError_t le = cudaSuccess;
 #define HH_LSM_LOG(H, A, P, U)                                                                                            \
   do {                                                                                                                  \
-    static bool attr_set = false;                                                                                       \
-    if (!attr_set) {                                                                                                    \
-      le = cudaFuncSetAttribute(lsm_logspace_paths_kernel<H, A, P, U>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
-                                kLsmLogSmem);                                                                           \
-      attr_set = le == cudaSuccess;                                                                                     \
-    }                                                                                                                   \
+    static PerDeviceOnce opted;                                                                                         \
+    le = smem_opt_in(opted, lsm_logspace_paths_kernel<H, A, P, U>, kLsmLogSmem);                                        \
     if (le == cudaSuccess) lsm_logspace_paths_kernel<H, A, P, U><<<grid_paths, kLsmPathThreads, kLsmLogSmem, st>>>(la); \
   } while (0)
 #define HH_LSM_LOG_H(H)                                                                                    \
@@ -1333,11 +1344,8 @@ int lsm_american(hh_ctx *ctx, const hh_model *m, const hh_sim *s, const hh_payof
     cudaError_t le = cudaSuccess;
 #define HH_LSM_PATHS(A, P, U)                                                                                           \
   do {                                                                                                                  \
-    static bool attr_set = false;                                                                                       \
-    if (!attr_set) {                                                                                                    \
-      le = cudaFuncSetAttribute(lsm_paths_kernel<A, P, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLsmPathSmem); \
-      attr_set = le == cudaSuccess;                                                                                     \
-    }                                                                                                                   \
+    static PerDeviceOnce opted;                                                                                         \
+    le = smem_opt_in(opted, lsm_paths_kernel<A, P, U>, kLsmPathSmem);                                                   \
     if (le == cudaSuccess) lsm_paths_kernel<A, P, U><<<grid_paths, kLsmPathThreads, kLsmPathSmem, st>>>(pa);                \
   } while (0)
     if (parity) { if (anti) HH_LSM_PATHS(true, true, true); else HH_LSM_PATHS(false, true, true); }
@@ -1385,6 +1393,7 @@ int lsm_american(hh_ctx *ctx, const hh_model *m, const hh_sim *s, const hh_payof
     a.px.rank = ctx->peer_rank;
     for (int qq = 0; qq < ctx->peer_world; ++qq) a.px.mail[qq] = static_cast<double *>(ctx->peer_mail[qq]);
     a.px.error = reinterpret_cast<int *>(static_cast<char *>(ctx->d_lsm_state.ptr) + done_off + 128);  // zeroed above
+    a.px.timeout_cycles = (long long)(ctx->peer_timeout_s * ctx->sm_clock_hz);
   }
   const double *G = ctx->d_grid.as<double>();
   // The cash-flow vector z is read and written by EVERY pass while each date slice is read twice and then dead:
@@ -1508,7 +1517,10 @@ int lsm_american(hh_ctx *ctx, const hh_model *m, const hh_sim *s, const hh_payof
     (void)cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 0);
     (void)cudaGetLastError();
   }
-  if (px_error) return ctx->fail(HH_ERR_PEER_TIMEOUT, "a peer's regression moments did not arrive within the in-kernel time limit");
+  if (px_error)
+    return ctx->fail(HH_ERR_PEER_TIMEOUT, "a peer's regression moments did not arrive within the in-kernel time limit (%.1f s, "
+                     "hh_peer_set_timeout) or a peer gave up; every rank fails together: reconnect with hh_peer_connect",
+                     ctx->peer_timeout_s);
   if (spot_paths) {
     // chunks of columns transposed on the device, then copied out (the staging buffer reuses d_terminal)
     const int nrows = M + 1;

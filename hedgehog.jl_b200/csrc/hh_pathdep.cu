@@ -444,12 +444,8 @@ __global__ void __launch_bounds__(256) pathdep_finalize_kernel(const double *par
 
 template <bool H, bool A, bool P, bool U, bool AR>
 static cudaError_t pd_launch_one(const PdArgs &a, int grid, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(pathdep_kernel<H, A, P, U, AR>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPdSmem);
-    if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
+  static PerDeviceOnce opted;  // per instantiation and device
+  if (cudaError_t e = smem_opt_in(opted, pathdep_kernel<H, A, P, U, AR>, kPdSmem); e != cudaSuccess) return e;
   pathdep_kernel<H, A, P, U, AR><<<grid, kPdThreads, kPdSmem, st>>>(a);
   return cudaGetLastError();
 }
@@ -469,12 +465,8 @@ static cudaError_t pd_launch_model(const PdArgs &a, bool anti, bool arith, bool 
 template <bool A, bool SP, bool U, bool AR, int T>
 static cudaError_t pd_fast_one(const PdArgs &a, int sm_count, cudaStream_t st, int *grid_out) {
   constexpr int smem = pd_fast_smem<A, T>();
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(pathdep_heston_fast_kernel<A, SP, U, AR, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
+  static PerDeviceOnce opted;  // per instantiation and device
+  if (cudaError_t e = smem_opt_in(opted, pathdep_heston_fast_kernel<A, SP, U, AR, T>, smem); e != cudaSuccess) return e;
   const int64_t batches = (a.n + T - 1) / T;
   const int grid = (int)(batches < (int64_t)sm_count ? batches : (int64_t)sm_count);  // one block per SM
   *grid_out = grid;
@@ -534,6 +526,7 @@ int path_dependent(hh_ctx *ctx, const hh_model *m, const hh_sim *s, int monitor_
   if (rc) return rc;
   if (ctx->pend.active) return ctx->fail(HH_ERR_ARG, "a European launch is pending on this context: collect it first");
   if (!payoffs || !results) return ctx->fail(HH_ERR_ARG, "payoffs/results is NULL");
+  if (s->rng_mode == HH_RNG_PHILOX_64) return ctx->fail(HH_ERR_UNSUPPORTED, "HH_RNG_PHILOX_64 covers European pricing only");
   if (npay < 1 || npay > 256) return ctx->fail(HH_ERR_ARG, "npayoffs must be in [1, 256] (got %d)", npay);
   const bool heston = m->kind == HH_MODEL_HESTON;
   const bool bk = heston && s->scheme == HH_SCHEME_HESTON_BK;  // exact transitions between the dates (n_steps of them)

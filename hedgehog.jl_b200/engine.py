@@ -42,10 +42,13 @@ class SimSpec:
                 raise ValueError(f"Number of seeds ({seeds.shape[0]}) must be ≥ number of trajectories ({self.n_paths}).")
             keep.append(seeds)
             s.seeds = seeds.ctypes.data_as(C.POINTER(C.c_uint64))
+            s.seeds_len = int(seeds.size)
         if self.normals is not None:
             z = np.ascontiguousarray(self.normals, dtype=np.float64)
+            # the C side reads n_paths * n_steps * components doubles behind this pointer and checks normals_len
             keep.append(z)
             s.normals = z.ctypes.data_as(C.POINTER(C.c_double))
+            s.normals_len = int(z.size)
         if self.bk is not None:
             s.bk = self.bk
         else:
@@ -115,6 +118,16 @@ class CudaEngine:
         sm, ma, mi, mem = C.c_int32(), C.c_int32(), C.c_int32(), C.c_size_t()
         self._check(self.lib.hh_device_info(self.h, C.byref(sm), C.byref(ma), C.byref(mi), C.byref(mem)), "hh_device_info")
         return {"sm_count": sm.value, "cc": (ma.value, mi.value), "total_mem": mem.value}
+
+    def heston_ablation(self, n_paths: int, n_steps: int, rng_mode: int, part: int) -> float:
+        """Device ms of the headline kernel with one part of its step removed (hh_bench_heston_ablation)."""
+        ms = C.c_double()
+        self._check(self.lib.hh_bench_heston_ablation(self.h, int(n_paths), int(n_steps), int(rng_mode), int(part),
+                                                      C.byref(ms)), "hh_bench_heston_ablation")
+        return ms.value
+
+    def peer_set_timeout(self, seconds: float):
+        self._check(self.lib.hh_peer_set_timeout(self.h, float(seconds)), "hh_peer_set_timeout")
 
     def fp64_peak(self):
         """(TFLOP/s, ms) of the in-library DFMA-chain microbenchmark."""

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define HH_VERSION 100 /* 0.1.0 */
+#define HH_VERSION 200 /* 0.2.0: hh_sim carries seeds_len / normals_len; HH_RNG_PHILOX_64; hh_peer_set_timeout */
 
 /* ---- error codes ------------------------------------------------------------------- */
 #define HH_OK 0
@@ -42,6 +42,7 @@ extern "C" {
 #define HH_ERR_CUDA 1           /* CUDA runtime failure, see hh_last_error */
 #define HH_ERR_NOMEM 2          /* device allocation failed */
 #define HH_ERR_COMM 3           /* the caller-supplied allreduce callback failed */
+#define HH_ERR_PEER_TIMEOUT 4   /* a peer's contribution did not arrive within the in-kernel time limit */
 
 /* ---- enums (int32 in the structs) ---------------------------------------------------- */
 /* dynamics: LognormalDynamics / HestonDynamics                montecarlo.jl:15,22 */
@@ -62,15 +63,19 @@ extern "C" {
 #define HH_PREC_F32 1 /* fast mode (Heston Euler-Maruyama, in-kernel RNG): f32 state and normals from 32-bit uniforms, \
                          two steps per Philox block, f64 payoff accumulation; agrees with f64 statistically (3 sigma) */
 
-#define HH_RNG_PHILOX 0  /* in-kernel Philox4x32-10 + Box-Muller */
+#define HH_RNG_PHILOX 0  /* in-kernel Philox4x32-10 + Box-Muller, 52-bit uniforms: one Philox block per Heston step */
 #define HH_RNG_NORMALS 1 /* parity mode: consume caller-supplied standard normals */
+#define HH_RNG_PHILOX_64 2 /* opt-in fast stream (Heston Euler-Maruyama, f64, European pricing): one Philox4x32-10 block \
+                              feeds TWO steps, each step taking 64 random bits — a 32-bit radius uniform \
+                              u1 = 1 - (k + 1/2) 2^-32 and a 32-bit angle theta = 2 pi w 2^-32 — evaluated in f64 by the \
+                              same table-driven Box-Muller. Counter stream word 2: never reuses HH_RNG_PHILOX numbers. \
+                              Same law up to the 2^-32 grid (|z| <= 6.7); restated bit for bit in the oracle. */
 
 /* hh_model.flags */
 #define HH_FLAG_SPLIT_STEP 1u   /* EM{split=true}: diffusion evaluated at K = u + dt f(u) [StochasticDiffEq default] */
 #define HH_FLAG_Q1_SQRT_MEAN 2u /* marginal_law puts sqrt(alpha) in the mean (montecarlo.jl:302); off = alpha */
 
 typedef struct hh_ctx hh_ctx;
-#define HH_ERR_PEER_TIMEOUT 4   /* a peer's contribution did not arrive within the in-kernel time limit */
 
 /* Model scalars, extracted on the host exactly as the reference does
  * (T: montecarlo.jl:147; r = zero_rate(rate, 0.0): :150; sigma: :151; Heston fields: :201). */
@@ -113,6 +118,9 @@ typedef struct hh_sim {
   uint64_t base_seed;  /* Philox key when seeds == NULL; counter carries the global path index */
   const uint64_t *seeds;  /* host, nullable: one key per local trajectory (config.seeds), len >= n_paths */
   const double *normals;  /* host, parity mode only: Z[path][step][component] contiguous */
+  uint64_t seeds_len;     /* elements behind `seeds`; checked: >= n_paths (montecarlo.jl:65-66 ArgumentError) */
+  uint64_t normals_len;   /* elements behind `normals`; checked: >= n_paths * n_steps * components (1 GBM, 2 Heston; \
+                             n_steps counts as 1 for HH_SCHEME_EXACT_TERMINAL) */
   hh_bk_config bk;
 } hh_sim;
 
@@ -173,6 +181,11 @@ typedef struct hh_comm {
 int hh_peer_export(hh_ctx *ctx, unsigned char handle[HH_IPC_HANDLE_BYTES]);
 int hh_peer_connect(hh_ctx *ctx, int rank, int world, const unsigned char *handles /* world x HH_IPC_HANDLE_BYTES */);
 int hh_peer_disconnect(hh_ctx *ctx);
+/* In-kernel limit on one wait for a peer's moments (default 30 s, or the environment variable HH_PEER_TIMEOUT_S at
+ * hh_create). A rank that gives up marks every rank's mailbox, so ALL ranks return HH_ERR_PEER_TIMEOUT from the same
+ * hh_lsm_american call; the connection is dead afterwards (hh_peer_connect again). Hosts should still open a solve with
+ * a barrier: ranks must not be further apart than this limit when they enter hh_lsm_american. */
+int hh_peer_set_timeout(hh_ctx *ctx, double seconds);
 
 /* ---- lifetime --------------------------------------------------------------------------- */
 int hh_version(void);
@@ -186,6 +199,13 @@ void hh_default_bk_config(hh_bk_config *out);
 /* Measured FP64 peak of this GPU: a register-resident DFMA-chain microbenchmark (2 FLOP per DFMA).
  * MEASURED_PEAKS.json holds no FP64 figure, so bench.py's roofline denominator comes from here. */
 int hh_bench_fp64_peak(hh_ctx *ctx, double *tflops, double *ms);
+/* Ablation of the headline kernel (heston_fast2_kernel, the instantiation hh_mc_european launches for a large
+ * base-seed job): the SAME kernel with one part of the step removed, timed on n_paths x n_steps.
+ *   part 0: the full step (both streams: rng_mode HH_RNG_PHILOX or HH_RNG_PHILOX_64)
+ *   part 1: no Philox (the random words are replaced by a two-instruction counter hash): table-driven Box-Muller + SDE step
+ *   part 2: Philox only (the words are XOR-folded into the state; no FP64 work)
+ * Results are not prices; `ms` is the device time of the one launch. bench.py reports the split. */
+int hh_bench_heston_ablation(hh_ctx *ctx, int64_t n_paths, int n_steps, int rng_mode, int part, double *ms);
 
 /* ---- European Monte Carlo: solve(::PricingProblem, ::MonteCarlo), montecarlo.jl:478-493 ------
  * One simulation prices `npayoffs` vanilla payoffs on the same paths (npayoffs = 1 is the

@@ -91,6 +91,28 @@ void hho_normal_pair(uint64_t key, uint64_t idx, uint32_t block, uint32_t stream
   *z2 = r * s;
 }
 
+/* HH_RNG_PHILOX_64 (include/hedgehog_mc.h; hedgehog.jl_b200/csrc/hh_fastnormal.cuh): the Box-Muller pair of Heston
+ * step `step` from 64 random bits — words (0, 1) of Philox block step/2 (counter stream word 2) when step is even, words
+ * (2, 3) when it is odd:
+ *   angle   n2 = (wa & 0xFFFFF) << 32 | wa                          theta = 2 pi n2 2^-52
+ *   radius  n1 = (wb & 0xFFFFF) << 32 | (wb & 0xFFF00000) | 0x80000  u1 = 1 - n1 2^-52 = 1 - (rotl(wb, 12) + 1/2) 2^-32 */
+void hho_normal_pair64(uint64_t key, uint64_t idx, uint32_t step, double *z1, double *z2) {
+  uint32_t ctr[4] = {(uint32_t)idx, (uint32_t)(idx >> 32), step >> 1, 2u};
+  uint32_t k[2] = {(uint32_t)key, (uint32_t)(key >> 32)};
+  uint32_t w[4];
+  hho_philox4x32_10(ctr, k, w);
+  const uint32_t wa = w[(step & 1u) * 2], wb = w[(step & 1u) * 2 + 1];
+  uint64_t n1 = ((uint64_t)(wb & 0xFFFFFu) << 32) | (uint64_t)((wb & 0xFFF00000u) | 0x80000u);
+  uint64_t n2 = ((uint64_t)(wa & 0xFFFFFu) << 32) | wa;
+  double u1 = 1.0 - (double)n1 * 0x1.0p-52; /* exact */
+  double u2 = (double)n2 * 0x1.0p-52;       /* exact */
+  double r = sqrt(-2.0 * log(u1));
+  double s, c;
+  sincospi_ref(2.0 * u2, &s, &c);
+  *z1 = r * c;
+  *z2 = r * s;
+}
+
 /* key / counter-index of local trajectory i (hedgehog_mc.h: hh_sim.seeds / base_seed) */
 static inline void path_stream(const hh_sim *sim, int64_t i, uint64_t *key, uint64_t *idx) {
   if (sim->seeds) { *key = sim->seeds[i]; *idx = 0; }
@@ -114,7 +136,9 @@ static inline void draw(const hh_model *m, const hh_sim *sim, int64_t i, int n, 
     *z2 = nc == 2 ? z[1] : 0.0;
     return;
   }
-  if (nc == 2) {
+  if (nc == 2 && sim->rng_mode == HH_RNG_PHILOX_64) {
+    hho_normal_pair64(key, idx, (uint32_t)n, z1, z2);
+  } else if (nc == 2) {
     hho_normal_pair(key, idx, (uint32_t)n, 0u, z1, z2);
   } else {
     double a, b;
@@ -127,7 +151,7 @@ static inline void draw(const hh_model *m, const hh_sim *sim, int64_t i, int n, 
 void hho_fill_normals(const hh_model *model, const hh_sim *sim, double *Z) {
   int nc = ncomp_of(model, sim), ns = nsteps_of(sim);
   hh_sim s = *sim;
-  s.rng_mode = HH_RNG_PHILOX;
+  if (s.rng_mode == HH_RNG_NORMALS) s.rng_mode = HH_RNG_PHILOX;
 #pragma omp parallel for schedule(static)
   for (int64_t i = 0; i < sim->n_paths; ++i) {
     uint64_t key, idx;
@@ -327,6 +351,9 @@ static int check_args(const hh_model *m, const hh_sim *sim) {
   if (!m || !sim || sim->n_paths <= 0) return HH_ERR_ARG;
   if (sim->scheme != HH_SCHEME_EXACT_TERMINAL && sim->n_steps <= 0) return HH_ERR_ARG;
   if (sim->rng_mode == HH_RNG_NORMALS && !sim->normals) return HH_ERR_ARG;
+  if (sim->rng_mode == HH_RNG_PHILOX_64 &&
+      !(m->kind == HH_MODEL_HESTON && sim->scheme == HH_SCHEME_EM && sim->precision == HH_PREC_F64))
+    return HH_ERR_UNSUPPORTED;
   if (sim->scheme == HH_SCHEME_HESTON_BK) return HH_ERR_UNSUPPORTED; /* BK oracle lives in oracle/bk_ref.py (scipy AMOS) */
   if (m->kind == HH_MODEL_HESTON && sim->scheme != HH_SCHEME_EM) return HH_ERR_ARG;
   if (m->kind == HH_MODEL_GBM && sim->scheme == HH_SCHEME_HESTON_BK) return HH_ERR_ARG;

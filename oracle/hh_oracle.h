@@ -30,6 +30,8 @@ extern "C" {
 void hho_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 /* The library's native-RNG convention: one Philox block -> one Box-Muller pair. */
 void hho_normal_pair(uint64_t key, uint64_t idx, uint32_t block, uint32_t stream, double *z1, double *z2);
+/* HH_RNG_PHILOX_64: the pair of Heston step `step` from half a Philox block (32-bit radius uniform, 32-bit angle). */
+void hho_normal_pair64(uint64_t key, uint64_t idx, uint32_t step, double *z1, double *z2);
 /* Fill Z[path][step][comp] with the native stream's normals (so parity mode can replay it). */
 void hho_fill_normals(const hh_model *model, const hh_sim *sim, double *Z);
 

@@ -128,3 +128,76 @@ def test_segmented_launch_for_the_ensemble_is_invisible(cuda, prec):
         assert abs(a.sum - b.sum) <= 1e-12 * abs(b.sum) and abs(a.sumsq - b.sumsq) <= 1e-12 * abs(b.sumsq)
     pay = np.maximum(term - 100.0, 0.0)
     assert abs(res[0].sum - pay.sum()) <= 1e-10 * pay.sum()
+
+
+def test_buffer_lengths_are_checked(cuda):
+    """hh_sim carries the element counts behind `seeds` and `normals`; a short buffer is HH_ERR_ARG, never an
+    out-of-bounds host read (wrong shapes are easy to produce: exact schemes force one step, Heston needs 2 components)."""
+    m = heston_model()
+    z = np.zeros((100, 8, 1))                      # Heston needs [path, step, 2]
+    with pytest.raises(ValueError, match="normals buffer too short"):
+        cuda.mc_european(m, SimSpec(n_paths=100, n_steps=8, rng_mode=abi.HH_RNG_NORMALS, normals=z), [(100.0, 1.0)], 1.0)
+    with pytest.raises(ValueError, match="normals buffer too short"):
+        cuda.lsm_american(gbm_model(), SimSpec(n_paths=100, n_steps=9, scheme=abi.HH_SCHEME_EXACT_STEPS,
+                                               rng_mode=abi.HH_RNG_NORMALS, normals=z), (100.0, -1.0), 2, 0.99)
+    # the C side checks seeds_len itself (the Python mirror also raises before the call: bypass it with a raw struct)
+    import ctypes as C
+    s, keep = SimSpec(n_paths=50, n_steps=4, seeds=np.arange(50, dtype=np.uint64)).to_c(cuda.lib)
+    s.n_paths = 60
+    res = (abi.hh_result * 1)()
+    pa = (abi.hh_payoff * 1)()
+    pa[0].strike, pa[0].cp = 100.0, 1.0
+    rc = cuda.lib.hh_mc_european(cuda.h, C.byref(m), C.byref(s), pa, 1, 1.0, res, None, 0)
+    assert rc == abi.HH_ERR_ARG and b"Number of seeds (50)" in cuda.lib.hh_last_error(cuda.h)
+
+
+def test_two_contexts_and_two_threads_in_one_process(cuda, oracle):
+    """(i) A second context (on a second GPU when the box has one) launches every kernel family that opts in to more than
+    48 KB of dynamic shared memory: the opt-in is tracked per device, not per process. (ii) Two threads sharing ONE
+    context: hh_mc_european holds the context mutex across launch and collect, so each thread gets its own results."""
+    import threading
+    import torch
+    dev = 1 if torch.cuda.device_count() > 1 else 0
+    other = hh.CudaEngine(dev)
+    try:
+        m, g = heston_model(), gbm_model()
+        sim = SimSpec(n_paths=5000, n_steps=12, base_seed=9)
+        ra, ta = cuda.mc_european(m, sim, [(100.0, 1.0)], 1.0, want_terminal=True)
+        rb, tb = other.mc_european(m, sim, [(100.0, 1.0)], 1.0, want_terminal=True)
+        np.testing.assert_array_equal(ta, tb)
+        t = abi.hh_tangent()
+        t.dV0 = 1.0
+        sa, _ = cuda.tangent_sums(m, [t], sim, [(100.0, 1.0)])
+        sb, _ = other.tangent_sums(m, [t], sim, [(100.0, 1.0)])
+        np.testing.assert_array_equal(sa, sb)
+        lsim = SimSpec(n_paths=4000, n_steps=10, scheme=abi.HH_SCHEME_EXACT_STEPS, base_seed=3)
+        la = cuda.lsm_american(g, lsim, (100.0, -1.0), 3, 0.995)[0]
+        lb = other.lsm_american(g, lsim, (100.0, -1.0), 3, 0.995)[0]
+        assert la.price == lb.price
+        pd = [(abi.HH_PD_ASIAN_ARITH, 100.0, 1.0, 0.0, 0.0)]
+        pa, _ = cuda.mc_path_dependent(m, sim, pd, 1.0)
+        pb, _ = other.mc_path_dependent(m, sim, pd, 1.0)
+        assert pa[0].sum == pb[0].sum
+    finally:
+        other.close()
+
+    expect = {}
+    for seed in range(8):
+        expect[seed] = cuda.mc_european(heston_model(), SimSpec(n_paths=20_000, n_steps=20, base_seed=seed), [(100.0, 1.0)], 1.0)[0][0].sum
+    got, errs = {}, []
+
+    def work(seeds):
+        try:
+            for _ in range(5):
+                for seed in seeds:
+                    r = cuda.mc_european(heston_model(), SimSpec(n_paths=20_000, n_steps=20, base_seed=seed), [(100.0, 1.0)], 1.0)
+                    if r[0][0].sum != expect[seed]:
+                        errs.append((seed, r[0][0].sum))
+                    got[seed] = r[0][0].sum
+        except Exception as e:  # noqa: BLE001
+            errs.append(repr(e))
+    th = [threading.Thread(target=work, args=(range(0, 4),)), threading.Thread(target=work, args=(range(4, 8),))]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not errs, errs[:3]
+    assert got == expect
