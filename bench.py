@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""bench.py — BASELINE.json's headline metric: Heston Euler-Maruyama path-steps/sec (config C2).
+"""bench.py — BASELINE.json's headline metric: Heston Euler-Maruyama path-steps/sec (config C2), with the other four
+BASELINE configurations, the Philox ablation and (under torchrun) the strong-scaling and multi-GPU LSM lines beside it.
 
     python bench.py --gpus N --steps K --warmup W            # our arm (CUDA, one rank per GPU under torchrun)
     python bench.py --impl reference --gpus N --steps K ...  # the reference arm: CPU implementation of the same path
@@ -8,12 +9,22 @@ A "step" is one pass of the hot path over one batch of synthetic input: pricing 
 (S0=K=100, r=0.03, V0=0.04, kappa=2, theta=0.04, xi=0.3, rho=-0.7, T=1, call) with `--paths` trajectories
 x 252 Euler-Maruyama steps per GPU in Float64 (weak scaling: per-GPU work fixed, disjoint Philox streams).
 
-Keys (see the task contract):
-  value     whole-job path-steps/s, kernels only (inputs are a few scalars, already on the device)
-  e2e       the same through the public API hedgehog_jl_b200.solve(problem, method) with host buffers
-  roofline  ALGORITHMIC FP64 work (25 FLOP per path-step) / average kernel time, against the FP64
-            DFMA peak measured in this run (MEASURED_PEAKS.json has no FP64 figure)
+Keys of the JSON line (see the task contract):
+  value         whole-job path-steps/s, kernels only (inputs are a few scalars, already on the device), default stream
+  e2e           the same through the public API hedgehog_jl_b200.solve(problem, method) with host buffers
+  roofline      ALGORITHMIC FP64 work (25 FLOP per path-step) / average kernel time, against the FP64 DFMA
+                peak measured in this run (MEASURED_PEAKS.json has no FP64 figure); `executed` and `traffic` come from the
+                ncu capture of the SAME kernel instantiation, recorded in profiles/ncu_constants.json
+  ablation      the headline kernel with Philox removed / with only Philox (hh_bench_heston_ablation), both streams
+  philox64      the opt-in HH_RNG_PHILOX_64 stream (one Philox block per two steps) — reported beside, never as `value`
+  f32_fast_mode config C2's Float32 fast mode — reported beside
+  configs       C1, C3, C4, C5 (N = 1): value + unit, kernel_ms, e2e_ms, roofline, check against the closed-form /
+                Carr-Madan / CRR anchors of tests/golden/config_anchors.json (written by tools/gen_anchors.py)
+  multi_gpu     N > 1: c2_strong (1e8 TOTAL trajectories through solve) and c3_lsm_peer (1e7 total columns, moments
+                exchanged inside the kernel over peer memory)
   cpu_baseline  the CPU oracle (a C restatement of the reference's arithmetic, "port") on a bounded sample
+
+The reference arm imports nothing from the product package and loads only oracle/_build/libhh_oracle.so.
 """
 import argparse
 import json
@@ -29,24 +40,45 @@ sys.path.insert(0, ROOT)
 
 METRIC = "heston_em_path_steps_per_sec"
 UNIT = "path-steps/s"
-FLOP_PER_PATH_STEP = 25.0  # SURVEY.md §8d: 17 (SDE update) + 8 (Box-Muller scaling); transcendentals not counted
-# executed by heston_fast2_kernel per path-step, from ncu (profiles/r1_c_ncu_heston_fast_v2.csv): 31.1 FP64 instructions
-# = 51.2 FLOP (DFMA counted twice), 90.6 instructions in all
-EXEC_FLOP_PER_PATH_STEP = 51.16
-EXEC_FP64_INSTR_PER_PATH_STEP = 31.09
-EXEC_INSTR_PER_PATH_STEP = 90.6
+FLOP_PER_PATH_STEP = 25.0  # SURVEY.md 8d: 17 (SDE update) + 8 (Box-Muller scaling); transcendentals not counted
+FLOP_PER_PATH_STEP_C5 = 263.0  # 25 + 17 * 2P with P = 7 tangent directions
+LSM_BYTES_PER_PATH_DATE = 32.0  # 8 (store) + 8 (read S_t) + 16 (read/write cash flow)
 WORKLOAD = "C2 Heston EM European call: 1e8 paths x 252 steps per GPU, f64, NoVarianceReduction"
 EULER_BIAS_252 = 0.005651  # price(252 steps) - Carr-Madan, 2e8 paths, std error 0.0005 (tools/euler_bias.py)
-CARR_MADAN_C2 = 9.242536279428904  # oracle/anchors.py heston_price(100,100,.03,1,.04,2,.04,.3,-.7), CarrMadan(1, 32)
+HEADLINE_KERNEL = "heston_fast2_kernel<0, 1, 1, 1, 1024, 1, 0, 0>"  # what hh_mc_european launches for C2 (hh_european.cu)
 
 
-def c2_problem(hh, total_paths, nsteps, precision="f64", ensemble=False, base_seed=42):
+def load_json(*rel):
+    try:
+        with open(os.path.join(ROOT, *rel)) as f:
+            return json.load(f)
+    except Exception:
+        return None
+
+
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def config_dict(args):
+    """The `config` object: identical in both arms (the reference arm's sample is described in cpu_baseline.sample)."""
+    headline = args.paths == 100_000_000 and args.nsteps == 252 and args.precision == "f64"
+    return {"workload": WORKLOAD if headline else f"Heston EM European call: {args.paths} paths x {args.nsteps} steps per GPU",
+            "paths_per_gpu": args.paths, "n_steps": args.nsteps, "rng": "Philox4x32-10 in-kernel, Box-Muller f64",
+            "l2": "not applicable: the kernel reads no HBM input (state in registers); every step uses a new seed",
+            "sharding": "contiguous global path index blocks per rank, no data-path collective"}
+
+
+def c2_problem(hh, total_paths, nsteps, precision="f64", ensemble=False, base_seed=42, rng="philox"):
     import datetime as dt
     payoff = hh.VanillaOption(100.0, dt.date(2020, 12, 31), hh.European(), hh.Call(), hh.Spot())  # 365 days: T = 1
     market = hh.HestonInputs(dt.date(2020, 1, 1), 0.03, 100.0, 0.04, 2.0, 0.04, 0.3, -0.7)
     prob = hh.PricingProblem(payoff, market)
     cfg = hh.SimulationConfig(total_paths, steps=nsteps, base_seed=base_seed)
-    method = hh.MonteCarlo(hh.HestonDynamics(), hh.EulerMaruyama(), cfg, precision=precision, ensemble=ensemble)
+    method = hh.MonteCarlo(hh.HestonDynamics(), hh.EulerMaruyama(), cfg, precision=precision, ensemble=ensemble, rng=rng)
     return prob, method
 
 
@@ -86,23 +118,18 @@ class ClockSampler:
                 "reasons": reasons}
 
 
+# ---- the reference arm and the cpu_baseline leg: the ONLY code here that touches oracle/ ---------------------------------
 def cpu_sample(paths, nsteps, seconds=None, reps=1):
-    """Time the CPU oracle on `paths` x `nsteps` of the C2 workload, all host threads. Returns (path-steps/s, info)."""
-    import hedgehog_jl_b200 as hh
-    from hedgehog_jl_b200 import _abi as abi
-    from hedgehog_jl_b200.engine import SimSpec
+    """Time the CPU oracle on `paths` x `nsteps` of the C2 workload with every host thread this process may use.
+    Returns (path-steps/s, info). Imports nothing from the product package."""
     from oracle import oracle as O
-    eng = O.OracleEngine()
-    m = abi.hh_model()
-    m.kind, m.flags = abi.HH_MODEL_HESTON, abi.HH_FLAG_SPLIT_STEP
-    m.S0, m.r, m.T = 100.0, 0.03, 1.0
-    m.V0, m.kappa, m.theta, m.xi, m.rho = 0.04, 2.0, 0.04, 0.3, -0.7
-    (m.m11, m.m12, m.m21, m.m22), _ = hh.corr_factor(m.rho, "cholesky")
+    want = host_threads()
+    eng = O.OracleEngine(threads=want)  # omp_set_num_threads: overrides the OMP_NUM_THREADS=1 that torchrun exports
+    m = O.heston_model(100.0, 0.03, 1.0, 0.04, 2.0, 0.04, 0.3, -0.7)
     D = math.exp(-0.03)
-    done, t_used, price = 0, 0.0, None
-    rep = 0
+    done, t_used, price, rep = 0, 0.0, None, 0
     while True:
-        sim = SimSpec(n_paths=paths, n_steps=nsteps, scheme=abi.HH_SCHEME_EM, base_seed=42 + rep, path_offset=rep * paths)
+        sim = O.OSim(n_paths=paths, n_steps=nsteps, scheme=O.HH_SCHEME_EM, base_seed=42 + rep, path_offset=rep * paths)
         t0 = time.perf_counter()
         res, _ = eng.mc_european(m, sim, [(100.0, 1.0)], D)
         t_used += time.perf_counter() - t0
@@ -114,41 +141,42 @@ def cpu_sample(paths, nsteps, seconds=None, reps=1):
                 break
         elif t_used >= seconds:
             break
-    return done / t_used, {"cores": eng.threads, "paths": paths * rep, "seconds": t_used, "price": price}
+    return done / t_used, {"cores": eng.threads_used, "cores_requested": want, "paths": paths * rep, "seconds": t_used,
+                           "price": price}
 
 
 def run_reference(args, rank, world):
     """Reference arm: the reference's CPU path. The Julia package cannot run in this image (no julia), so this is
-    the C restatement (oracle/, OpenMP over all host cores); see BASELINE.md §3."""
+    the C restatement (oracle/, OpenMP over all host cores); see BASELINE.md section 3."""
     if rank != 0:
         return
     sample_paths = args.ref_paths
     for _ in range(args.warmup):
         cpu_sample(max(sample_paths // 10, 1000), args.nsteps)
     t0 = time.perf_counter()
-    total = 0
-    cores = 1
+    total, info = 0, {}
     for k in range(args.steps):
         v, info = cpu_sample(sample_paths, args.nsteps)
         total += sample_paths * args.nsteps
-        cores = info["cores"]
     dt_s = time.perf_counter() - t0
     value = total / dt_s
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt_s / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "paths_per_gpu": args.paths, "n_steps": args.nsteps,
-                   "sample": f"each step prices {sample_paths} of the workload's trajectories x {args.nsteps} steps on the host cores"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{args.steps} x {sample_paths} paths x {args.nsteps} steps, OpenMP over all host threads; "
-                                   "C restatement of the reference arithmetic (the Julia package cannot run here)"},
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config_dict(args),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": info.get("cores"), "cores_requested": info.get("cores_requested"),
+                         "kind": "port",
+                         "sample": f"{args.steps} x {sample_paths} trajectories x {args.nsteps} steps of the workload, OpenMP over "
+                                   "all host threads of this process; C restatement of the reference arithmetic (oracle/; "
+                                   "the Julia package cannot run here)"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "loaded_product_modules": sorted(k for k in sys.modules if k.startswith("hedgehog")),
     }
     print(json.dumps(line), flush=True)
 
 
+# ---- our arm --------------------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -163,6 +191,10 @@ def main():
     ap.add_argument("--ref-paths", type=int, default=400_000)
     ap.add_argument("--skip-ensemble", action="store_true")
     ap.add_argument("--skip-f32", action="store_true")
+    ap.add_argument("--skip-configs", action="store_true", help="leave C1/C3/C4/C5 (N = 1) and the multi-GPU lines (N > 1) out")
+    ap.add_argument("--skip-ablation", action="store_true")
+    ap.add_argument("--ablate", action="store_true", help="only the Philox ablation of the headline kernel, as JSON")
+    ap.add_argument("--config-scale", type=float, default=1.0, help="shrinks the path counts of the configs block (smoke runs)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -173,7 +205,6 @@ def main():
         run_reference(args, rank, world)
         return
 
-    import numpy as np
     import torch
     import torch.distributed as dist
 
@@ -205,6 +236,37 @@ def main():
         return float(t.item())
 
     fp64_peak, _ = eng.fp64_peak()
+    peaks = load_json("MEASURED_PEAKS.json") or {}
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    hbm_peak_source = "MEASURED_PEAKS.json (of measured)" if "hbm_gbs" in peaks else "B200_PROFILING.md fallback 6650 GB/s (of fallback)"
+    anchors = load_json("tests", "golden", "config_anchors.json") or {}
+    ncu_consts = (load_json("profiles", "ncu_constants.json") or {})
+    carr_madan_c2 = anchors.get("c2_carr_madan_call", 9.242536279428904)
+
+    def ablation(paths):
+        """hh_bench_heston_ablation for both streams: ms and cycles per warp-step (SM clock taken from nvidia-smi's max)."""
+        out = {}
+        smsp = eng.device_info()["sm_count"] * 4
+        for name, rng in (("philox_52bit", abi.HH_RNG_PHILOX), ("philox_64", abi.HH_RNG_PHILOX_64)):
+            parts = {}
+            for part, label in ((0, "full"), (1, "no_philox"), (2, "philox_only")):
+                eng.heston_ablation(paths, args.nsteps, rng, part)
+                ms = min(eng.heston_ablation(paths, args.nsteps, rng, part) for _ in range(2))
+                parts[label] = {"ms": ms, "cycles_per_warp_step": ms * 1e-3 * 1.965e9 / (paths * args.nsteps / 32 / smsp)}
+            f, a, b = (parts[k]["ms"] for k in ("full", "no_philox", "philox_only"))
+            parts["philox_marginal_share"] = (f - a) / f   # what removing Philox saves
+            parts["philox_standalone_share"] = b / f       # what Philox costs alone (the two overlap partly)
+            out[name] = parts
+        out["note"] = ("the same kernel instantiation with one part of the step removed (include/hedgehog_mc.h, "
+                       "hh_bench_heston_ablation); cycles at 1965 MHz per warp-step per SM sub-partition")
+        return out
+
+    if args.ablate:
+        if rank == 0:
+            print(json.dumps({"ablation": ablation(args.paths)}), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     K, W = args.steps, args.warmup
     total_paths = args.paths * world
@@ -213,28 +275,33 @@ def main():
     payoffs = [(100.0, 1.0)]
     D = hh.df(prob.market_inputs.rate, prob.payoff.expiry)
 
-    def sim_for(k):
-        s = _sim_of(method, _scheme_of(method), (rank, world))
-        s.base_seed = 42 + k  # every step simulates fresh trajectories
-        return s
+    def timed_launches(meth, seed0):
+        """W warm-up + K timed launches of the C2 step on this rank's shard; returns (ms over K launches, last result)."""
+        mm = _model_of(prob, meth)
+
+        def sim_for(k):
+            s = _sim_of(meth, _scheme_of(meth), (rank, world))
+            s.base_seed = seed0 + k  # every step simulates fresh trajectories
+            return s
+        for k in range(W):
+            eng.mc_european_launch(mm, sim_for(1000 + k), payoffs)
+            eng.mc_european_collect(D)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for k in range(K):
+            eng.mc_european_launch(mm, sim_for(k), payoffs)
+        e1.record(stream)
+        barrier()
+        ms_ = max_over_ranks(e0.elapsed_time(e1))
+        return ms_, eng.mc_european_collect(D)[0]
 
     # ---- kernels only ("value") --------------------------------------------------------------------------------
-    for k in range(W):
-        eng.mc_european_launch(mdl, sim_for(1000 + k), payoffs)
-        eng.mc_european_collect(D)
     sampler = ClockSampler(local_rank)
     time.sleep(0.3)
-    barrier()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_wall0 = time.time()
-    ev0.record(stream)
-    for k in range(K):
-        eng.mc_european_launch(mdl, sim_for(k), payoffs)
-    ev1.record(stream)
-    barrier()
+    ms, last = timed_launches(method, 42)
     t_wall1 = time.time()
-    ms = max_over_ranks(ev0.elapsed_time(ev1))
-    last = eng.mc_european_collect(D)[0]
     clocks = sampler.stop(t_wall0, t_wall1)
     path_steps_per_step = float(total_paths) * args.nsteps
     value = path_steps_per_step * K / (ms * 1e-3)
@@ -272,67 +339,72 @@ def main():
         e2e["with_ensemble"] = {"value": path_steps_per_step / dt_e, "unit": UNIT, "d2h_bytes_per_step": 8 * total_paths,
                                 "seconds": dt_e}
 
-    # ---- Float32 fast mode of the same workload (config C2 "Float32 fast mode"): reported beside, not as `value` ------
-    f32 = None
+    # ---- beside the headline: the Float32 fast mode and the opt-in Philox stream of the same workload ------------------
+    f32 = p64 = None
     if args.precision == "f64" and not args.skip_f32:
-        prob32, method32 = c2_problem(hh, total_paths, args.nsteps, "f32")
-        mdl32 = _model_of(prob32, method32)
-
-        def sim32(k):
-            s = _sim_of(method32, _scheme_of(method32), (rank, world))
-            s.base_seed = 7000 + k
-            return s
-        eng.mc_european_launch(mdl32, sim32(0), payoffs)
-        eng.mc_european_collect(D)
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        for k in range(K):
-            eng.mc_european_launch(mdl32, sim32(1 + k), payoffs)
-        e1.record(stream)
-        barrier()
-        ms32 = max_over_ranks(e0.elapsed_time(e1))
-        r32 = eng.mc_european_collect(D)[0]
+        ms32, r32 = timed_launches(c2_problem(hh, total_paths, args.nsteps, "f32")[1], 7000)
         f32 = {"value": path_steps_per_step * K / (ms32 * 1e-3), "unit": UNIT, "ms_per_step": ms32 / K, "price": r32.price,
                "std_error": r32.std_error, "note": "f32 state and normals (32-bit uniforms, MUFU lg2/sin/cos/sqrt), f64 payoff sums"}
+    if args.precision == "f64":
+        ms64, r64 = timed_launches(c2_problem(hh, total_paths, args.nsteps, "f64", rng="philox64")[1], 9000)
+        a64 = FLOP_PER_PATH_STEP * float(args.paths) * args.nsteps / (ms64 / K * 1e-3) * 1e-12
+        p64 = {"value": path_steps_per_step * K / (ms64 * 1e-3), "unit": UNIT, "ms_per_step": ms64 / K, "price": r64.price,
+               "std_error": r64.std_error, "roofline_frac_algorithmic": a64 / fp64_peak,
+               "z_vs_carr_madan_plus_bias": (r64.price - carr_madan_c2 - EULER_BIAS_252) / r64.std_error if args.nsteps == 252 else None,
+               "note": "HH_RNG_PHILOX_64 (opt-in): one Philox4x32-10 block per TWO steps, 32-bit radius uniform + 32-bit angle per "
+                       "step, same f64 arithmetic; restated in the oracle and compared per path (tests/test_gpu_philox64.py)"}
+
+    abl = None
+    if world == 1 and not args.skip_ablation and args.precision == "f64":
+        abl = ablation(args.paths)
+
+    configs = multi = None
+    if not args.skip_configs:
+        if world == 1:
+            configs = run_configs(hh, eng, args.config_scale, fp64_peak, hbm_peak, hbm_peak_source, anchors, ncu_consts)
+        else:
+            multi = run_multi_gpu(hh, eng, rank, world, args, barrier, max_over_ranks, anchors)
 
     if rank == 0:
+        kc = ncu_consts.get(HEADLINE_KERNEL) or {}
+        executed = None
+        if kc.get("flop_per_path_step"):
+            tf = kc["flop_per_path_step"] * float(args.paths) * args.nsteps / (per_launch_ms * 1e-3) * 1e-12
+            executed = {"tflops": tf, "frac_of_fp64_peak": tf / fp64_peak, "flop_per_path_step": kc["flop_per_path_step"],
+                        "fp64_instr_per_path_step": kc.get("fp64_instr_per_path_step"),
+                        "instr_per_path_step": kc.get("instr_per_path_step"), "kernel": HEADLINE_KERNEL,
+                        "source": kc.get("source")}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": per_launch_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": args.precision, "data": "synthetic",
-            "config": {"workload": WORKLOAD
-                       if args.paths == 100_000_000 and args.nsteps == 252 and args.precision == "f64" else
-                       f"Heston EM European call: {args.paths} paths x {args.nsteps} steps per GPU",
-                       "paths_per_gpu": args.paths, "n_steps": args.nsteps, "rng": "Philox4x32-10 in-kernel, Box-Muller f64",
-                       "l2": "not applicable: the kernel reads no HBM input (state in registers); every step uses a new seed",
-                       "sharding": "contiguous global path index blocks per rank, no data-path collective"},
+            "dtype": args.precision, "data": "synthetic", "config": config_dict(args),
             "roofline": {"bound": "fp64", "achieved": achieved_tflops, "peak": fp64_peak, "unit": "TFLOP/s",
                          "frac": achieved_tflops / fp64_peak,
-                         "traffic": 25088.0,  # dram bytes per launch (ncu, profiles/r1_g_ncu_heston_v3.csv): tables only, no data stream
+                         "traffic": kc.get("dram_bytes_per_launch"),  # ncu dram__bytes_read + write of this kernel (tables only)
+                         "traffic_source": kc.get("source"),
                          "peak_source": "DFMA-chain microbenchmark run by this bench (hh_bench_fp64_peak); "
                                         "MEASURED_PEAKS.json has no FP64 entry",
                          "convention": "algorithmic 25 FLOP per path-step (log/sincos/sqrt expansions NOT counted)",
-                         "executed": {
-                             "tflops": EXEC_FLOP_PER_PATH_STEP * float(args.paths) * args.nsteps / (per_launch_ms * 1e-3) * 1e-12,
-                             "frac_of_fp64_peak": EXEC_FLOP_PER_PATH_STEP * float(args.paths) * args.nsteps
-                             / (per_launch_ms * 1e-3) * 1e-12 / fp64_peak,
-                             "flop_per_path_step": EXEC_FLOP_PER_PATH_STEP,
-                             "source": "ncu op_{dadd,dmul,dfma} counts of this kernel, profiles/r1_c_ncu_heston_fast_v2.csv"},
-                         "limiter": "SMSP dispatch port: an FP64 instruction holds it 2-3 cycles (profiles/"
-                                    "r1_b_ubench_issue_pipes.txt), so cycles per warp-step ~ 2.2 x 31 FP64 + 1.1 x 60 other; "
-                                    "measured 148 (DESIGN.md section 4)"} if args.precision == "f64" else
+                         "executed": executed,
+                         "limiter": "SMSP dispatch port: an FP64 instruction holds it 2 cycles, so a step costs >= 2 x 31 FP64 + "
+                                    "58 other = 120 cycles per warp; the FP64 + table part alone runs at that bound, Philox "
+                                    "(17 IMAD.WIDE at ~4 cycles of the FMA pipe) overlaps it only partly: see `ablation` "
+                                    "(DESIGN.md section 4.1)"} if args.precision == "f64" else
             {"bound": "fp32+sfu", "achieved": achieved_tflops, "peak": None, "unit": "TFLOP/s", "frac": None, "traffic": None,
              "convention": "algorithmic 25 FLOP per path-step; f32 fast mode (MUFU-bound), no FP32 peak measured"},
-            "e2e": e2e, "gpu_launches": 2 * K, "clocks": clocks, "f32_fast_mode": f32,
-            "check": {"price": last.price, "std_error": last.std_error, "carr_madan": CARR_MADAN_C2,
+            "e2e": e2e, "gpu_launches": 2 * K, "clocks": clocks, "f32_fast_mode": f32, "philox64": p64, "ablation": abl,
+            "check": {"price": last.price, "std_error": last.std_error, "carr_madan": carr_madan_c2,
                       "n_nonfinite": last.n_nonfinite, "e2e_price": e2e_price,
                       "euler_bias_at_252_steps": EULER_BIAS_252,
-                      "z_vs_carr_madan_plus_bias": (last.price - CARR_MADAN_C2 - EULER_BIAS_252) / last.std_error
+                      "z_vs_carr_madan_plus_bias": (last.price - carr_madan_c2 - EULER_BIAS_252) / last.std_error
                       if args.nsteps == 252 and last.std_error > 0 else None,
                       "note": "the scheme's O(dt) discretisation bias, measured with 2e8 paths per step count "
                               "(profiles/r1_i_euler_bias_c2.json: +0.0217, +0.0112, +0.0057, +0.0023, +0.0004 at 63..1008 steps)"},
         }
+        if configs is not None:
+            line["configs"] = configs
+        if multi is not None:
+            line["multi_gpu"] = multi
         if world == 1 and not args.no_cpu_baseline:
             v, info = cpu_sample(100_000, args.nsteps, seconds=args.cpu_seconds)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": info["cores"], "kind": "port",
@@ -341,6 +413,213 @@ def main():
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def _wall(f, reps):
+    best, res = None, None
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        res = f()
+        t = (time.perf_counter() - t0) * 1e3
+        best = t if best is None or t < best else best
+    return res, best
+
+
+def run_configs(hh, eng, scale, fp64_peak, hbm_peak, hbm_peak_source, anchors, ncu_consts):
+    """C1, C3, C4, C5 of BASELINE.json on one GPU through hh.solve: one warm-up solve, then the best of 3 (kernel ms from the
+    library's CUDA events, e2e ms = wall clock around solve with host buffers)."""
+    import datetime as dt
+
+    import numpy as np
+    out = {}
+    call = lambda K=100.0, ex=None, cp=None: hh.VanillaOption(K, dt.date(2020, 12, 31), ex or hh.European(), cp or hh.Call(), hh.Spot())
+    bs = hh.BlackScholesInputs(dt.date(2020, 1, 1), 0.05, 100.0, 0.2)
+    heston = hh.HestonInputs(dt.date(2020, 1, 1), 0.03, 100.0, 0.04, 2.0, 0.04, 0.3, -0.7)
+
+    # C1: Black-Scholes European call, exact GBM, 1e6 paths x 1 step — launch-bound: latency, not a roofline fraction
+    n = max(int(1e6 * scale), 1000)
+    m = hh.MonteCarlo(hh.LognormalDynamics(), hh.BlackScholesExact(), hh.SimulationConfig(n, steps=1, base_seed=42), ensemble=False)
+    p = hh.PricingProblem(call(), bs)
+    hh.solve(p, m, engine=eng)
+    sol, w = _wall(lambda: hh.solve(p, m, engine=eng), 5)
+    m2 = hh.MonteCarlo(hh.LognormalDynamics(), hh.BlackScholesExact(), hh.SimulationConfig(n, steps=1, base_seed=42), ensemble=True)
+    _, w2 = _wall(lambda: hh.solve(p, m2, engine=eng), 5)
+    ref = anchors.get("c1_black_scholes_call")
+    out["C1"] = {"workload": f"Black-Scholes European call, exact GBM, {n} paths x 1 step, f64", "value": n / (w * 1e-3),
+                 "unit": "paths/s (e2e)", "kernel_ms": sol.stats["kernel_ms"], "e2e_ms": w, "e2e_ms_with_ensemble": w2,
+                 "roofline": {"bound": "launch latency", "frac": None,
+                              "note": "microseconds of compute: the figure of merit is the latency of one solve"},
+                 "check": {"price": sol.price, "std_error": sol.std_error, "black_scholes": ref,
+                           "z": (sol.price - ref) / sol.std_error if ref else None}}
+
+    # C3: American put, LSM under exact GBM steps, 1e7 paths x 50 dates, degree 3 — HBM-bound
+    n = max(int(1e7 * scale), 10000)
+    put = call(100.0, hh.American(), hh.Put())
+    lsm = hh.LSM(hh.MonteCarlo(hh.LognormalDynamics(), hh.BlackScholesExact(), hh.SimulationConfig(n, steps=50, base_seed=12345)), 3)
+    p = hh.PricingProblem(put, bs)
+    hh.solve(p, lsm, engine=eng, stopping_info=False)
+    sol, w = _wall(lambda: hh.solve(p, lsm, engine=eng, stopping_info=False), 3)
+    _, w_info = _wall(lambda: hh.solve(p, lsm, engine=eng, stopping_info="arrays"), 2)
+    kms = sol.stats["kernel_ms"]
+    gbs = n * 50 * LSM_BYTES_PER_PATH_DATE / (kms * 1e-3) / 1e9
+    kc = ncu_consts.get("lsm_backward_kernel<3, 0>") or {}
+    crr, berm = anchors.get("c3_crr_american_put_1000"), anchors.get("c3_crr_bermudan_put_50_dates")
+    out["C3"] = {"workload": f"American put, Longstaff-Schwartz degree 3, exact GBM, {n} paths x 50 dates, f64",
+                 "value": n * 50 / (kms * 1e-3), "unit": "path-dates/s", "kernel_ms": kms, "path_ms": sol.stats["path_ms"],
+                 "regress_ms": sol.stats["regress_ms"], "e2e_ms": w, "e2e_ms_with_stopping_info": w_info,
+                 "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+                              "peak_source": hbm_peak_source,
+                              "convention": "algorithmic 32 B per path-date (8 store + 8 read S_t + 16 read/write cash flow)",
+                              "traffic": kc.get("dram_bytes_per_launch"), "traffic_source": kc.get("source"),
+                              "backward_only": {"achieved": n * 49 * 24.0 / (sol.stats["regress_ms"] * 1e-3) / 1e9,
+                                                "convention": "24 B per path-date of the induction alone (the cash-flow vector is "
+                                                              "served from the persisting L2 window, so DRAM sees ~16 B)"}},
+                 "check": {"price": sol.price, "std_error": sol.std_error, "crr_american_1000_steps": crr,
+                           "crr_bermudan_50_dates": berm, "rel_diff_vs_crr": (sol.price - crr) / crr if crr else None,
+                           "z_vs_bermudan": (sol.price - berm) / sol.std_error if berm else None,
+                           "tolerance": "rtol 2e-2 against CRR is the reference's own bar (test/agreement/american_options.jl:49); "
+                                        "LSM with a cubic basis is biased low against the lattice by construction"}}
+
+    # C4: Heston European call, Broadie-Kaya exact simulation, 1e7 paths x 12 dates — compute-bound, divergent
+    n = max(int(1e7 * scale), 10000)
+    m = hh.MonteCarlo(hh.HestonDynamics(), hh.HestonBroadieKaya(), hh.SimulationConfig(n, steps=12, base_seed=42), ensemble=False,
+                      bk_steps_from_config=True)
+    p = hh.PricingProblem(call(), heston)
+    hh.solve(p, m, engine=eng)
+    sol, w = _wall(lambda: hh.solve(p, m, engine=eng), 2)
+    st = eng.bk_last_stats()
+    kms = sol.stats["kernel_ms"]
+    cf_per_transition = 3.0 + st["mean_series_terms"]   # moments_from_cf: 3 evaluations; the series: one per term (tabulated once)
+    cm = anchors.get("c2_carr_madan_call")
+    out["C4"] = {"workload": f"Heston European call, Broadie-Kaya exact, {n} paths x 12 dates, f64", "value": n * 12 / (kms * 1e-3),
+                 "unit": "transitions/s", "kernel_ms": kms, "e2e_ms": w,
+                 "cf_evaluations_per_s": n * 12 * cf_per_transition / (kms * 1e-3),
+                 "cf_evaluations_per_transition": cf_per_transition, "bk_stats": st,
+                 "roofline": {"bound": "fp64 (latency- and divergence-bound)", "frac": None,
+                              "note": "algorithmic flops are data dependent (SURVEY 8d): transitions/s and CF evaluations/s are "
+                                      "reported with the mean series length and CDF evaluations per inversion"},
+                 "check": {"price": sol.price, "std_error": sol.std_error, "carr_madan": cm,
+                           "z": (sol.price - cm) / sol.std_error if cm else None, "n_fallback": sol.stats.get("n_fallback")}}
+
+    # C5: BatchGreekProblem on Heston Euler: delta, gamma, vega (V0), rho (rate), kappa, theta, sigma, rho on 64 strikes
+    n = max(int(1e7 * scale), 10000)
+    strikes = np.linspace(60.0, 140.0, 64)
+    lenses = [hh.SpotLens(), hh.optic("market_inputs.V0"), hh.ZeroRateSpineLens(1), hh.optic("market_inputs.kappa"),
+              hh.optic("market_inputs.theta"), hh.optic("market_inputs.sigma"), hh.optic("market_inputs.rho")]
+    names = ["delta", "vega_V0", "rho_rate", "kappa", "theta", "sigma", "rho_corr"]
+    m = hh.MonteCarlo(hh.HestonDynamics(), hh.EulerMaruyama(), hh.SimulationConfig(n, steps=252, base_seed=42), ensemble=False)
+    p = hh.PricingProblem(call(), heston)
+    bump = 0.5
+    hh.strike_grid_greeks(p, strikes, lenses, m, engine=eng, gamma_bump=bump)
+    (prices, g, se, sec), w = _wall(lambda: hh.strike_grid_greeks(p, strikes, lenses, m, engine=eng, gamma_bump=bump), 3)
+    (_, _, _), w_nogamma = _wall(lambda: hh.strike_grid_greeks(p, strikes, lenses, m, engine=eng), 2)
+    kms = eng.last_tangent_ms
+    tf = FLOP_PER_PATH_STEP_C5 * n * 252 / (kms * 1e-3) * 1e-12
+    a5 = anchors.get("c5") or {}
+    keys = ["d_S0", "d_V0", "d_r", "d_kappa", "d_theta", "d_sigma", "d_rho"]
+    k = 32
+    table = {}
+    if a5:
+        sel = slice(8, 56)
+
+        def row(est, err, ref):
+            ref = np.array(ref)
+            return {"mc": float(est[k]), "std_error": float(err[k]), "carr_madan_fd": float(ref[k]),
+                    "rel_diff": float((est[k] - ref[k]) / ref[k]),
+                    "max_abs_rel_diff_strikes_70_130": float(np.max(np.abs(est[sel] - ref[sel]) / np.abs(ref[sel]))),
+                    "max_abs_z_strikes_70_130": float(np.max(np.abs(est[sel] - ref[sel]) / err[sel]))}
+        table["price"] = row(prices, np.full(64, float("nan")), a5["price"])
+        for i, (nm, key) in enumerate(zip(names, keys)):
+            table[nm] = row(g[:, i], se[:, i], a5[key])
+        table["gamma_fd"] = row(sec["fd"], sec["fd_stderr"], a5["d2_S0"])
+        table["gamma_pathwise"] = row(sec["pathwise"], sec["pathwise_stderr"], a5["d2_S0"])
+    kc5 = ncu_consts.get("heston_tangent_kernel<0, 1, 5, 8>") or {}
+    executed5 = None
+    if kc5.get("flop_per_path_step"):
+        tfe = kc5["flop_per_path_step"] * n * 252 / (kms * 1e-3) * 1e-12
+        executed5 = {"tflops": tfe, "frac_of_fp64_peak": tfe / fp64_peak, "flop_per_path_step": kc5["flop_per_path_step"],
+                     "fp64_instr_per_path_step": kc5.get("fp64_instr_per_path_step"), "instr_per_path_step": kc5.get("instr_per_path_step"),
+                     "fp64_pipe_busy_pct_under_ncu": kc5.get("fp64_pipe_pct"), "kernel": "heston_tangent_kernel<0, 1, 5, 8>",
+                     "source": kc5.get("source")}
+    out["C5"] = {"workload": f"Heston Euler-Maruyama Greeks, {n} paths x 252 steps, 64 strikes on [60, 140], f64",
+                 "sensitivities": names[:1] + ["gamma"] + names[1:], "n_sensitivities": 8, "strikes": 64,
+                 "value": n * 252 / (kms * 1e-3), "unit": "path-steps/s (all 8 sensitivities x 64 strikes from one launch)",
+                 "kernel_ms": kms, "e2e_ms": w, "e2e_ms_without_gamma": w_nogamma,
+                 "gamma": "second difference of the payoff under the absolute spot bump %.2g on the same trajectories (the reference's "
+                          "FiniteDifference form, greeks_problem.jl:395-412) and the pathwise-delta difference; both in the launch" % bump,
+                 "roofline": {"bound": "fp64", "achieved": tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": tf / fp64_peak,
+                              "convention": "263 FLOP per path-step (SURVEY 8d: 25 + 17 x 2P, P = 7); OVERCOUNTS the executed work: the "
+                                            "specialised kernel skips the structural zeros (delta and the rate direction cost nothing "
+                                            "per step, 5 directions cost 10 FP64 instructions each)",
+                              "executed": executed5},
+                 "check": {"strike": float(strikes[k]), "at_strike_and_over_the_grid": table,
+                           "tolerance": "the reference's own Monte Carlo Greeks test accepts rtol 3e-2 (delta, rho), 1e-1 (vega), 2e-1 "
+                                        "(gamma) against analytic values (test/agreement/greeks_agreement.jl:207-236)",
+                           "note": "anchors: finite differences of the Carr-Madan price (tests/golden/config_anchors.json). With 1e7 "
+                                   "trajectories the standard errors are ~1e-4 relative, so |z| of a few units measures the "
+                                   "Euler-Maruyama full-truncation bias at 252 steps (0.06 % on the price, up to ~1 % on the variance "
+                                   "sensitivities), not sampling error: rel_diff is the figure to read"}}
+    return out
+
+
+def run_multi_gpu(hh, eng, rank, world, args, barrier, max_over_ranks, anchors):
+    """N > 1: strong scaling of C2 (1e8 TOTAL trajectories through solve) and C3 with the in-kernel peer exchange."""
+    import datetime as dt
+
+    import numpy as np
+    import torch.distributed as dist
+    out = {}
+    scale = args.config_scale
+    # c2_strong: the north star's wording is a strong-scaling statement (1e8 paths in total)
+    total = max(int(1e8 * scale), 10000 * world)
+    for k in range(2):
+        hh.solve(*c2_problem(hh, total, args.nsteps, base_seed=500 + k), engine=eng)
+    barrier()
+    t0 = time.perf_counter()
+    sol = None
+    for k in range(args.steps):
+        sol = hh.solve(*c2_problem(hh, total, args.nsteps, base_seed=600 + k), engine=eng)
+    barrier()
+    dt_s = max_over_ranks(time.perf_counter() - t0) / args.steps
+    kms = max_over_ranks(sol.stats["kernel_ms"])
+    cm = anchors.get("c2_carr_madan_call")
+    out["c2_strong"] = {"workload": f"C2 with {total} trajectories in TOTAL over {world} GPUs, through solve (e2e)", "scaling": "strong",
+                        "value": total * args.nsteps / dt_s, "unit": UNIT, "e2e_ms": dt_s * 1e3, "kernel_ms_max_over_ranks": kms,
+                        "price": sol.price, "std_error": sol.std_error,
+                        "z_vs_carr_madan_plus_bias": (sol.price - cm - EULER_BIAS_252) / sol.std_error if cm and args.nsteps == 252 else None}
+
+    # c3_lsm_peer: 1e7 columns in total, the regression moments of the 49 dates exchanged inside the kernel over peer memory
+    from hedgehog_jl_b200.distributed import connect_peers
+    n = max(int(1e7 * scale), 10000 * world)
+    put = hh.VanillaOption(100.0, dt.date(2020, 12, 31), hh.American(), hh.Put(), hh.Spot())
+    bs = hh.BlackScholesInputs(dt.date(2020, 1, 1), 0.05, 100.0, 0.2)
+    lsm = hh.LSM(hh.MonteCarlo(hh.LognormalDynamics(), hh.BlackScholesExact(), hh.SimulationConfig(n, steps=50, base_seed=12345)), 3)
+    p = hh.PricingProblem(put, bs)
+    connect_peers(eng)
+    hh.solve(p, lsm, engine=eng, stopping_info=False)
+    barrier()
+    best, sol = None, None
+    for _ in range(3):
+        barrier()
+        t0 = time.perf_counter()
+        sol = hh.solve(p, lsm, engine=eng, stopping_info=False)
+        t = max_over_ranks(time.perf_counter() - t0)
+        best = t if best is None or t < best else best
+    kms = max_over_ranks(sol.stats["kernel_ms"])
+    rms = max_over_ranks(sol.stats["regress_ms"])
+    eng.peer_disconnect()
+    barrier()
+    single = None
+    if rank == 0:  # the same 1e7 columns on ONE GPU (no exchange): same trajectories by global index
+        s1 = hh.solve(p, lsm, engine=eng, stopping_info=False, shard=(0, 1))
+        single = {"price": s1.price, "kernel_ms": s1.stats["kernel_ms"]}
+    barrier()
+    out["c3_lsm_peer"] = {"workload": f"C3 with {n} columns in TOTAL over {world} GPUs, moments exchanged in-kernel over peer memory",
+                          "scaling": "strong", "value": n * 50 / (kms * 1e-3), "unit": "path-dates/s", "kernel_ms_max_over_ranks": kms,
+                          "regress_ms_max_over_ranks": rms, "e2e_ms": best * 1e3, "price": sol.price, "std_error": sol.std_error,
+                          "one_gpu": single, "price_bit_equal_to_one_gpu": (single["price"] == sol.price) if single else None,
+                          "crr_american_1000_steps": anchors.get("c3_crr_american_put_1000")}
+    return out
 
 
 if __name__ == "__main__":

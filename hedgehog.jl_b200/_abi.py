@@ -121,7 +121,7 @@ SYMBOLS = {
                                          C.POINTER(hh_sim), C.POINTER(hh_payoff), C.c_int, C.c_double,
                                          C.POINTER(hh_result), _dp, _dp]),
     "hh_mc_european_tangent_sums": (C.c_int, [C.c_void_p, C.POINTER(hh_model), C.POINTER(hh_tangent), C.c_int,
-                                              C.POINTER(hh_sim), C.POINTER(hh_payoff), C.c_int, _dp, _dp]),
+                                              C.POINTER(hh_sim), C.POINTER(hh_payoff), C.c_int, _dp, C.c_double, _dp, _dp]),
     "hh_lsm_american": (C.c_int, [C.c_void_p, C.POINTER(hh_model), C.POINTER(hh_sim), C.POINTER(hh_payoff), C.c_int,
                                   C.c_double, C.POINTER(hh_comm), C.POINTER(hh_lsm_result), C.POINTER(C.c_int32),
                                   _dp, _dp]),

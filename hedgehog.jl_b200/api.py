@@ -198,6 +198,8 @@ class MonteCarlo:  # montecarlo.jl:127-131
     normals: Optional[np.ndarray] = None  # parity mode: pre-generated standard normals [path, step, comp]
     bk_steps_from_config: bool = False    # False: exact strategies ignore `steps` like the reference (Q6)
     control_variate: Any = None           # pathdep.BlackScholesControlVariate(): Heston + EulerMaruyama vanilla prices
+    rng: str = "philox"                   # "philox": Philox4x32-10, 52-bit uniforms, one block per Heston step (default);
+                                          # "philox64": opt-in HH_RNG_PHILOX_64, one block per TWO steps (Heston + EulerMaruyama, f64)
 
 
 B200MonteCarlo = MonteCarlo
@@ -308,6 +310,12 @@ def _sim_of(method: MonteCarlo, scheme: int, shard=None) -> SimSpec:
                   n_steps=cfg.steps if (not exact or method.bk_steps_from_config) else 1,
                   vr=abi.HH_VR_ANTITHETIC if isinstance(cfg.variance_reduction, Antithetic) else abi.HH_VR_NONE,
                   precision=abi.HH_PREC_F32 if method.precision == "f32" else abi.HH_PREC_F64)
+    if method.rng not in ("philox", "philox64"):
+        raise ValueError(f"unknown rng {method.rng!r} (philox | philox64)")
+    if method.rng == "philox64":
+        if method.normals is not None:
+            raise ValueError("rng='philox64' selects an in-kernel stream; it cannot be combined with pre-generated normals")
+        sim.rng_mode = abi.HH_RNG_PHILOX_64
     if method.normals is not None:
         sim.rng_mode = abi.HH_RNG_NORMALS
         z = np.asarray(method.normals, dtype=np.float64)
@@ -322,8 +330,9 @@ def _sim_of(method: MonteCarlo, scheme: int, shard=None) -> SimSpec:
     return sim
 
 
-def _shard_and_reduce(shard, group):
-    """(rank, world) and a function that sum-reduces a float64 vector over ranks (torch.distributed)."""
+def _shard_and_reduce(shard, group, device=None):
+    """(rank, world) and a function that sum-reduces a float64 vector over ranks (torch.distributed). `device`: the
+    engine's CUDA device, where the NCCL collectives of this rank run."""
     if shard is not None:
         return shard, None
     try:
@@ -333,7 +342,7 @@ def _shard_and_reduce(shard, group):
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return None, None
     from .distributed import allreduce_sum_f64
-    return (dist.get_rank(group), dist.get_world_size(group)), (lambda v: allreduce_sum_f64(v, group))
+    return (dist.get_rank(group), dist.get_world_size(group)), (lambda v: allreduce_sum_f64(v, group, device))
 
 
 # ---- solve: European Monte Carlo (montecarlo.jl:478-493) ---------------------------------------------------------
@@ -341,7 +350,7 @@ def _solve_european(prob, method, engine, shard, group, strikes=None):
     if not isinstance(prob.payoff.underlying, Spot):
         raise TypeError("MonteCarlo prices options on the Spot underlying")  # dispatch: VanillaOption{..,European,C,Spot}
     eng = engine or default_engine()
-    shard, reduce = _shard_and_reduce(shard, group)
+    shard, reduce = _shard_and_reduce(shard, group, getattr(eng, "device", None))
     mdl = _model_of(prob, method)
     sim = _sim_of(method, _scheme_of(method), shard)
     cp = prob.payoff.call_put()

@@ -10,7 +10,7 @@ static thread_local std::string g_create_error;
 
 namespace hh {
 int tangent_sums(hh_ctx *ctx, const hh_model *model, const hh_tangent *tangents, int ntangents, const hh_sim *sim,
-                 const hh_payoff *payoffs, int npayoffs, double *sums, double *kernel_ms);
+                 const hh_payoff *payoffs, int npayoffs, double *sums, double spot_bump, double *second_sums, double *kernel_ms);
 int lsm_american(hh_ctx *ctx, const hh_model *model, const hh_sim *sim, const hh_payoff *payoff, int degree,
                  double step_discount, const hh_comm *comm, hh_lsm_result *out, int32_t *stop_idx, double *stop_val,
                  double *spot_paths);
@@ -279,11 +279,11 @@ int hh_mc_path_dependent(hh_ctx *ctx, const hh_model *model, const hh_sim *sim, 
 
 int hh_mc_european_tangent_sums(hh_ctx *ctx, const hh_model *model, const hh_tangent *tangents, int ntangents,
                                 const hh_sim *sim, const hh_payoff *payoffs, int npayoffs, double *sums,
-                                double *kernel_ms) {
+                                double spot_bump, double *second_sums, double *kernel_ms) {
   if (!ctx) return HH_ERR_ARG;
   std::lock_guard<std::mutex> lk(ctx->mu);
   NvtxRange nv("hh_mc_european_tangent_sums");
-  return hh::tangent_sums(ctx, model, tangents, ntangents, sim, payoffs, npayoffs, sums, kernel_ms);
+  return hh::tangent_sums(ctx, model, tangents, ntangents, sim, payoffs, npayoffs, sums, spot_bump, second_sums, kernel_ms);
 }
 
 int hh_mc_european_tangent(hh_ctx *ctx, const hh_model *model, const hh_tangent *tangents, int ntangents,
@@ -298,7 +298,7 @@ int hh_mc_european_tangent(hh_ctx *ctx, const hh_model *model, const hh_tangent 
   double *sums = new (std::nothrow) double[(size_t)npayoffs * stride];
   if (!sums) return HH_ERR_NOMEM;
   double ms = 0.0;
-  int rc = hh_mc_european_tangent_sums(ctx, model, tangents, ntangents, sim, payoffs, npayoffs, sums, &ms);
+  int rc = hh_mc_european_tangent_sums(ctx, model, tangents, ntangents, sim, payoffs, npayoffs, sums, 0.0, nullptr, &ms);
   if (rc == HH_OK) {
     const double N = (double)sim->n_paths;
     for (int k = 0; k < npayoffs; ++k) {

@@ -53,11 +53,29 @@ struct EuroArgs {
   uint32_t f32_one;           // 0x3F800000 (1.0f)
   uint32_t lo_fill;           // 0x00080000: the half-ulp bit behind the 32 random mantissa bits (HH_RNG_PHILOX_64)
   int rng64;                  // HH_RNG_PHILOX_64
+  // Second order in the spot on the SAME trajectories (SecondOrderGreekProblem(spot, spot), greeks_problem.jl:395-412: absolute
+  // bump eps, common random numbers). Every scheme here is linear in S0 (log-space state, or S-space steps that multiply S),
+  // so a re-solve at S0 +- eps with the same seeds has terminal spots S_T (S0 +- eps) / S0: the bumped payoffs are evaluated
+  // in the payoff stage of the one simulation. Per trajectory (pair-averaged when antithetic):
+  //   sd = pay(S_T up) - 2 pay(S_T) + pay(S_T dn)                         -> gamma_fd = D mean(sd) / eps^2   (the reference's form)
+  //   dd = delta_path(S0 + eps) - delta_path(S0 - eps),  delta_path = cp 1{cp (S - K) > 0} S / S0   -> gamma_pw = D mean(dd) / (2 eps)
+  int g_on;
+  double g_up, g_dn, g_iu, g_id;  // (S0 + eps) / S0, (S0 - eps) / S0, 1 / (S0 + eps), 1 / (S0 - eps)
 };
 
-// number of accumulators per (block, payoff): sum, sumsq, nonfinite, then per tangent: dsum, dsumsq
+// second-order contributions of one terminal spot at one strike
+__device__ __forceinline__ void gamma_terms(const EuroArgs &a, double sp, double ep, double cp, double strike, double &s2, double &dd) {
+  const double su = sp * a.g_up, sl = sp * a.g_dn;
+  const double eu = cp * (su - strike), el = cp * (sl - strike);
+  s2 = fmax(eu, 0.0) - 2.0 * fmax(ep, 0.0) + fmax(el, 0.0);
+  dd = (eu > 0.0 ? cp * su * a.g_iu : 0.0) - (el > 0.0 ? cp * sl * a.g_id : 0.0);
+}
+
+// number of accumulators per (block, payoff): sum, sumsq, nonfinite, then per tangent: dsum, dsumsq, and — in the tangent
+// kernels — the four second-order sums of the spot bump (see GammaArgs)
+constexpr int kNGamma = 4;
 template <class T>
-__host__ __device__ constexpr int nacc_of() { return 3 + 2 * num_traits<T>::ntan; }
+__host__ __device__ constexpr int nacc_of() { return 3 + 2 * num_traits<T>::ntan + (num_traits<T>::ntan > 0 ? kNGamma : 0); }
 
 template <class T>
 __device__ __forceinline__ T lift(double v, const double *dv) {
@@ -233,7 +251,8 @@ __global__ void __launch_bounds__(kThreads) european_kernel(const EuroArgs a, co
   constexpr int NV = 1 + NT;                 // values per terminal state: S, dS_1..dS_NT
   constexpr int NSIDE = ANTI ? 2 : 1;
   constexpr int STAGE = NV * NSIDE * kThreads;
-  constexpr int RED = NACC * kThreads;
+  constexpr int RCH = NACC < 19 ? NACC : 19;  // accumulators reduced per pass (keeps the static shared memory under 48 KB)
+  constexpr int RED = RCH * kThreads;
   __shared__ double smem[STAGE > RED ? STAGE : RED];
 
   __shared__ FastNormalTables s_tables;  // Box-Muller lookup tables (native-RNG mode)
@@ -306,22 +325,44 @@ __global__ void __launch_bounds__(kThreads) european_kernel(const EuroArgs a, co
           acc[3 + q] += dpay;
           acc[3 + NT + q] = fma(dpay, dpay, acc[3 + NT + q]);
         }
+        if constexpr (NT > 0) {
+          if (a.g_on) {
+            double s2, dd;
+            gamma_terms(a, sp, ep, cp, strike, s2, dd);
+            if (ANTI) {
+              const double sm = smem[NV * kThreads + j];
+              double s2m, ddm;
+              gamma_terms(a, sm, cp * (sm - strike), cp, strike, s2m, ddm);
+              s2 = 0.5 * (s2 + s2m);
+              dd = 0.5 * (dd + ddm);
+            }
+            acc[3 + 2 * NT + 0] += s2;
+            acc[3 + 2 * NT + 1] = fma(s2, s2, acc[3 + 2 * NT + 1]);
+            acc[3 + 2 * NT + 2] += dd;
+            acc[3 + 2 * NT + 3] = fma(dd, dd, acc[3 + 2 * NT + 3]);
+          }
+        }
       }
     }
     __syncthreads();
   }
 
-  // fixed-order reduction over the path groups that share a strike
+  // fixed-order reduction over the path groups that share a strike, RCH accumulators per pass
 #pragma unroll
-  for (int c = 0; c < NACC; ++c) smem[c * kThreads + tid] = acc[c];
-  __syncthreads();
-  if (tid < a.npay) {
-    double *out = a.partials + ((size_t)blockIdx.x * a.npay + tid) * NACC;
-    for (int c = 0; c < NACC; ++c) {
-      double t = 0.0;
-      for (int gg = 0; gg < G; ++gg) t += smem[c * kThreads + (gg << a.kp_log2) + tid];
-      out[c] = t;
+  for (int c0 = 0; c0 < NACC; c0 += RCH) {
+#pragma unroll
+    for (int c = 0; c < RCH; ++c)
+      if (c0 + c < NACC) smem[c * kThreads + tid] = acc[c0 + c < NACC ? c0 + c : 0];
+    __syncthreads();
+    if (tid < a.npay) {
+      double *out = a.partials + ((size_t)blockIdx.x * a.npay + tid) * NACC;
+      for (int c = 0; c < RCH && c0 + c < NACC; ++c) {
+        double t = 0.0;
+        for (int gg = 0; gg < G; ++gg) t += smem[c * kThreads + (gg << a.kp_log2) + tid];
+        out[c0 + c] = t;
+      }
     }
+    __syncthreads();
   }
 }
 
@@ -976,8 +1017,8 @@ __device__ __forceinline__ void heston_tangent_step(const HestonFolded &f, const
 }
 
 template <bool ANTI, bool SPLIT, int NF, int P>
-__global__ void __launch_bounds__(kThreads) heston_tangent_kernel(const EuroArgs a, const HestonTanConsts c) {
-  constexpr int NACC = 3 + 2 * P;
+__global__ void __launch_bounds__(kThreads, 2) heston_tangent_kernel(const EuroArgs a, const HestonTanConsts c) {
+  constexpr int NACC = 3 + 2 * P + kNGamma;
   constexpr int NV = 1 + P;
   constexpr int NSIDE = ANTI ? 2 : 1;
   constexpr int STAGE = NV * NSIDE * kThreads;
@@ -1084,6 +1125,21 @@ __global__ void __launch_bounds__(kThreads) heston_tangent_kernel(const EuroArgs
           if (ANTI) dpay = 0.5 * (dpay + im * smem[(NV + 1 + q) * kThreads + j]);
           acc[3 + q] += dpay;
           acc[3 + P + q] = fma(dpay, dpay, acc[3 + P + q]);
+        }
+        if (a.g_on) {  // second order in the spot from the same trajectories (GammaArgs in EuroArgs)
+          double s2, dd;
+          gamma_terms(a, sp, ep, cp, strike, s2, dd);
+          if (ANTI) {
+            const double sm = smem[NV * kThreads + j];
+            double s2m, ddm;
+            gamma_terms(a, sm, cp * (sm - strike), cp, strike, s2m, ddm);
+            s2 = 0.5 * (s2 + s2m);
+            dd = 0.5 * (dd + ddm);
+          }
+          acc[3 + 2 * P + 0] += s2;
+          acc[3 + 2 * P + 1] = fma(s2, s2, acc[3 + 2 * P + 1]);
+          acc[3 + 2 * P + 2] += dd;
+          acc[3 + 2 * P + 3] = fma(dd, dd, acc[3 + 2 * P + 3]);
         }
       }
     }
@@ -1394,7 +1450,7 @@ template <bool ANTI, bool SPLIT, int NF, int P>
 static cudaError_t launch_tangent_one(const EuroArgs &a, const HestonTanConsts &c, int sm_count, cudaStream_t st, int *nblocks,
                                       bool query_only) {
   auto kern = heston_tangent_kernel<ANTI, SPLIT, NF, P>;
-  constexpr int NACC = 3 + 2 * P, STAGE = (1 + P) * (ANTI ? 2 : 1) * kThreads, RED = NACC * kThreads;
+  constexpr int NACC = 3 + 2 * P + kNGamma, STAGE = (1 + P) * (ANTI ? 2 : 1) * kThreads, RED = NACC * kThreads;
   constexpr int smem = (STAGE > RED ? STAGE : RED) * 8 + kLogRepBytes + kTrigRepBytes + kExp2Bytes;
   static PerDeviceOnce opted;  // per instantiation and device
   if (cudaError_t e0 = smem_opt_in(opted, kern, smem); e0 != cudaSuccess) return e0;
@@ -1840,7 +1896,7 @@ int european_collect(hh_ctx *ctx, double discount, hh_result *results, double *t
 }
 
 int tangent_sums(hh_ctx *ctx, const hh_model *m, const hh_tangent *tg, int ntan, const hh_sim *s,
-                 const hh_payoff *payoffs, int npay, double *sums, double *kernel_ms) {
+                 const hh_payoff *payoffs, int npay, double *sums, double spot_bump, double *second_sums, double *kernel_ms) {
   int rc = validate_model_sim(ctx, m, s);
   if (rc) return rc;
   if (!tg || ntan < 1 || ntan > kMaxTan) return ctx->fail(HH_ERR_ARG, "ntangents must be in [1, %d] (got %d)", kMaxTan, ntan);
@@ -1855,11 +1911,20 @@ int tangent_sums(hh_ctx *ctx, const hh_model *m, const hh_tangent *tg, int ntan,
 
   const bool anti = s->vr == HH_VR_ANTITHETIC;
   const int P = ntan <= 1 ? 1 : ntan <= 2 ? 2 : ntan <= 4 ? 4 : 8;
-  const int NACC = 3 + 2 * P;
+  const int NACC = 3 + 2 * P + kNGamma;
   EuroArgs a;
   TangentPack tp;
   int kind = 0;
   build_args(ctx, m, s, tg, ntan, a, tp, kind);
+  if (second_sums) {
+    if (!(spot_bump > 0.0) || !(spot_bump < m->S0))
+      return ctx->fail(HH_ERR_ARG, "second order: the absolute spot bump must be in (0, S0) (got %g)", spot_bump);
+    a.g_on = 1;
+    a.g_up = (m->S0 + spot_bump) / m->S0;
+    a.g_dn = (m->S0 - spot_bump) / m->S0;
+    a.g_iu = 1.0 / (m->S0 + spot_bump);
+    a.g_id = 1.0 / (m->S0 - spot_bump);
+  }
 
   HH_CUDA(ctx, cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
@@ -1932,6 +1997,8 @@ int tangent_sums(hh_ctx *ctx, const hh_model *m, const hh_tangent *tg, int ntan,
       o[2 + order[kq]] = f[3 + kq];
       o[2 + ntan + order[kq]] = f[3 + P + kq];
     }
+    if (second_sums)
+      for (int c = 0; c < kNGamma; ++c) second_sums[(size_t)k * kNGamma + c] = f[3 + 2 * P + c];
   }
   return HH_OK;
 }

@@ -13,14 +13,35 @@ import numpy as np
 from . import _abi as abi
 
 
-def allreduce_sum_f64(v: np.ndarray, group=None) -> np.ndarray:
+def _cuda_device(device=None):
+    """The CUDA device a rank's collectives run on: the engine's device (LOCAL_RANK), NOT torch's current device — under
+    plain torchrun a user who never called torch.cuda.set_device would otherwise put every rank on cuda:0."""
+    import os
+    import torch
+    if device is None:
+        device = int(os.environ.get("LOCAL_RANK", "0"))
+    return torch.device("cuda", int(device))
+
+
+def allreduce_sum_f64(v: np.ndarray, group=None, device=None) -> np.ndarray:
     import torch
     import torch.distributed as dist
     t = torch.from_numpy(np.ascontiguousarray(v, dtype=np.float64).copy())
     if dist.get_backend(group) == "nccl":
-        t = t.cuda()
+        t = t.to(_cuda_device(device))
     dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
     return t.cpu().numpy().reshape(np.shape(v))
+
+
+def allreduce_max_int(x: int, group=None, device=None) -> int:
+    """Max over ranks of a small integer (return codes: every rank learns whether ANY rank failed)."""
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([int(x)], dtype=torch.int64)
+    if dist.get_backend(group) == "nccl":
+        t = t.to(_cuda_device(device))
+    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    return int(t.cpu().item())
 
 
 class _DevArray:
@@ -31,8 +52,9 @@ class _DevArray:
                                          "strides": None, "stream": stream or 1}
 
 
-def make_comm(shard, group=None):
-    """hh_comm whose callback sum-allreduces a device buffer in place with torch.distributed (NCCL)."""
+def make_comm(shard, group=None, device=None):
+    """hh_comm whose callback sum-allreduces a device buffer in place with torch.distributed (NCCL). `device`: the
+    engine's CUDA device (default LOCAL_RANK)."""
     import torch
     import torch.distributed as dist
     rank, world = shard
@@ -40,12 +62,14 @@ def make_comm(shard, group=None):
     def _cb(user, dev_ptr, count, stream):
         try:
             if dist.get_backend(group) == "nccl":
-                ext = torch.cuda.ExternalStream(stream) if stream else torch.cuda.current_stream()
-                with torch.cuda.stream(ext):
-                    # stream-ordered: ProcessGroupNCCL makes `ext` wait for its collective, so the library's next kernel
-                    # (the fit) sees the reduced moments without a host round trip
-                    t = torch.as_tensor(_DevArray(dev_ptr, count, stream), device="cuda")
-                    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+                dev = _cuda_device(device)
+                with torch.cuda.device(dev):
+                    ext = torch.cuda.ExternalStream(stream, device=dev) if stream else torch.cuda.current_stream(dev)
+                    with torch.cuda.stream(ext):
+                        # stream-ordered: ProcessGroupNCCL makes `ext` wait for its collective, so the library's next
+                        # kernel (the fit) sees the reduced moments without a host round trip
+                        t = torch.as_tensor(_DevArray(dev_ptr, count, stream), device=dev)
+                        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
             else:  # gloo (CPU tests with an injected engine): dev_ptr is a host pointer
                 buf = (C.c_double * count).from_address(dev_ptr)
                 t = torch.frombuffer(buf, dtype=torch.float64)

@@ -171,6 +171,7 @@ class CudaEngine:
 
     # -- peer mailboxes (multi-GPU LSM without a collective library) ------------------------------------------------
     peers = None  # (rank, world) once connected
+    last_tangent_ms = 0.0  # device ms of the last hh_mc_european_tangent_sums call
 
     def peer_export(self) -> bytes:
         buf = (C.c_ubyte * abi.HH_IPC_HANDLE_BYTES)()
@@ -189,18 +190,24 @@ class CudaEngine:
         self.peers = None
 
     # -- tangents --------------------------------------------------------------------------------
-    def tangent_sums(self, model, tangents: Sequence[abi.hh_tangent], sim: SimSpec, payoffs):
-        """Raw sums [npay, 2 + 2*ntan] and kernel ms."""
+    def tangent_sums(self, model, tangents: Sequence[abi.hh_tangent], sim: SimSpec, payoffs, spot_bump: float = 0.0):
+        """Raw sums [npay, 2 + 2*ntan] and kernel ms; with spot_bump > 0 also the second-order sums [npay, 4]
+        (sum sd, sum sd^2, sum dd, sum dd^2; include/hedgehog_mc.h) as a third element."""
         s, keep = sim.to_c(self.lib)
         pa = _payoff_array(payoffs)
         nt = len(tangents)
         ta = (abi.hh_tangent * nt)(*tangents)
         out = np.zeros((len(payoffs), 2 + 2 * nt), dtype=np.float64)
+        second = np.zeros((len(payoffs), 4), dtype=np.float64) if spot_bump > 0 else None
         ms = C.c_double()
         rc = self.lib.hh_mc_european_tangent_sums(self.h, C.byref(model), ta, nt, C.byref(s), pa, len(payoffs),
-                                                  _dp(out), C.byref(ms))
+                                                  _dp(out), float(spot_bump), _dp(second) if second is not None else None,
+                                                  C.byref(ms))
         self._check(rc, "hh_mc_european_tangent_sums")
         del keep
+        self.last_tangent_ms = ms.value
+        if second is not None:
+            return out, ms.value, second
         return out, ms.value
 
     # -- LSM ---------------------------------------------------------------------------------------

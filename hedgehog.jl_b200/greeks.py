@@ -160,14 +160,17 @@ def tangent_of(prob, method, lens) -> abi.hh_tangent:
     return t
 
 
-def _forward_ad(prob, lenses, method, engine, shard, group, strikes=None):
-    """d price / d lens for all lenses (chunks of 8 directions per launch). Returns (greeks, stderrs, prices)."""
+def _forward_ad(prob, lenses, method, engine, shard, group, strikes=None, spot_bump=None):
+    """d price / d lens for all lenses (chunks of 8 directions per launch). Returns (greeks, stderrs, prices), and with
+    `spot_bump` (absolute, greeks_problem.jl:395-412) a fourth element: the second derivative in the spot from the SAME
+    launch, {"fd": D mean(sd)/eps^2 (the reference's three-solve form), "pathwise": D mean(dd)/(2 eps), and their standard
+    errors} per payoff (include/hedgehog_mc.h, hh_mc_european_tangent_sums)."""
     if isinstance(method, api.LSM):
         raise NotImplementedError("ForwardAD through LSM is not on the GPU path; use FiniteDifference")
     if not isinstance(prob.payoff.exercise_style, api.European):
         raise TypeError("pathwise Greeks are defined for European payoffs")
     eng = engine or api.default_engine()
-    shard, reduce = api._shard_and_reduce(shard, group)
+    shard, reduce = api._shard_and_reduce(shard, group, getattr(eng, "device", None))
     mdl = api._model_of(prob, method)
     scheme = api._scheme_of(method)
     sim = api._sim_of(method, scheme, shard)
@@ -177,16 +180,32 @@ def _forward_ad(prob, lenses, method, engine, shard, group, strikes=None):
     greeks = np.zeros((len(payoffs), len(lenses)))
     stderrs = np.zeros_like(greeks)
     prices = np.zeros(len(payoffs))
+    second = None
     for c0 in range(0, len(lenses), 8):
         chunk = lenses[c0:c0 + 8]
         tans = [tangent_of(prob, method, L) for L in chunk]
         nt = len(tans)
-        sums, _ = eng.tangent_sums(mdl, tans, sim, payoffs)
+        sec = None
+        if spot_bump and c0 == 0:
+            sums, _, sec = eng.tangent_sums(mdl, tans, sim, payoffs, spot_bump=float(spot_bump))
+        else:
+            sums, _ = eng.tangent_sums(mdl, tans, sim, payoffs)
         n = np.array([float(sim.n_paths)])
         if reduce is not None:
-            flat = reduce(np.concatenate([sums.ravel(), n]))
-            sums, n = flat[:-1].reshape(sums.shape), flat[-1:]
+            parts = [sums.ravel(), n] + ([sec.ravel()] if sec is not None else [])
+            flat = reduce(np.concatenate(parts))
+            k = sums.size
+            if sec is not None:
+                sec = flat[k + 1:].reshape(sec.shape)
+            sums, n = flat[:k].reshape(sums.shape), flat[k:k + 1]
         N = n[0]
+        if sec is not None:
+            eps = float(spot_bump)
+            m_sd, m_dd = sec[:, 0] / N, sec[:, 2] / N
+            v_sd = np.maximum((sec[:, 1] - N * m_sd * m_sd) / max(N - 1, 1), 0.0)
+            v_dd = np.maximum((sec[:, 3] - N * m_dd * m_dd) / max(N - 1, 1), 0.0)
+            second = {"fd": D * m_sd / eps ** 2, "fd_stderr": D * np.sqrt(v_sd / N) / eps ** 2,
+                      "pathwise": D * m_dd / (2 * eps), "pathwise_stderr": D * np.sqrt(v_dd / N) / (2 * eps), "bump": eps}
         mean = sums[:, 0] / N
         prices[:] = D * mean
         for q, t in enumerate(tans):
@@ -195,6 +214,8 @@ def _forward_ad(prob, lenses, method, engine, shard, group, strikes=None):
             greeks[:, c0 + q] = t.ddiscount * mean + D * dmean
             var = np.maximum((sums[:, 2 + nt + q] - N * dmean * dmean) / max(N - 1, 1), 0.0)
             stderrs[:, c0 + q] = D * np.sqrt(var / N)
+    if spot_bump:
+        return greeks, stderrs, prices, second
     return greeks, stderrs, prices
 
 
@@ -233,6 +254,14 @@ def solve_greek(gprob, gmethod, pricing_method, *, engine=None, shard=None, grou
         x0, y0 = l1(prob), l2(prob)
         if isinstance(gmethod, FiniteDifference):  # :395-422, ABSOLUTE bump
             eps = gmethod.bump
+            if (_is_spot(l1) and _is_spot(l2) and isinstance(pricing_method, api.MonteCarlo)
+                    and isinstance(prob.payoff.exercise_style, api.European)
+                    and not isinstance(pricing_method.strategy, api.HestonBroadieKaya) and pricing_method.precision == "f64"
+                    and pricing_method.control_variate is None and 0 < eps < x0):
+                # gamma: the reference's three solves at S0 - eps, S0, S0 + eps share their seeds, and every scheme here is
+                # linear in S0, so the three payoffs come from ONE simulation (hh_mc_european_tangent_sums, second_sums)
+                _, _, _, sec = _forward_ad(prob, [SpotLens()], pricing_method, engine, shard, group, spot_bump=eps)
+                return GreekResult(float(sec["fd"][0]), float(sec["fd_stderr"][0]))
             f = lambda x, y: _price(set(set(prob, l1, x), l2, y), pricing_method, engine, shard, group)
             if l1 == l2:
                 return GreekResult((f(x0 + eps, y0 + eps) - 2 * f(x0, y0) + f(x0 - eps, y0 - eps)) / eps ** 2)
@@ -243,13 +272,27 @@ def solve_greek(gprob, gmethod, pricing_method, *, engine=None, shard=None, grou
             # a.s. zero (its own MC test uses FD "due to AD instability", test/agreement/greeks_agreement.jl:219-224).
             # Here: central difference, on common random numbers, of the in-kernel first-order tangent.
             eps = 1e-2 * abs(x0) if x0 != 0 else 1e-4
+            if _is_spot(l1) and _is_spot(l2) and isinstance(pricing_method, api.MonteCarlo) and x0 > 0:
+                # both bumped deltas come from the one simulation (linear in S0): no extra launches
+                _, _, _, sec = _forward_ad(prob, [SpotLens()], pricing_method, engine, shard, group, spot_bump=eps)
+                return GreekResult(float(sec["pathwise"][0]), float(sec["pathwise_stderr"][0]))
             up, _, _ = _forward_ad(set(prob, l1, x0 + eps), [l2], pricing_method, engine, shard, group)
             dn, _, _ = _forward_ad(set(prob, l1, x0 - eps), [l2], pricing_method, engine, shard, group)
             return GreekResult(float((up[0, 0] - dn[0, 0]) / (2 * eps)))
     raise TypeError(f"unknown Greek problem {gprob!r}")
 
 
-def strike_grid_greeks(prob, strikes, lenses, pricing_method, *, engine=None, shard=None, group=None):
-    """Config C5: all `lenses` x all `strikes` from ONE simulation. Returns (prices[k], greeks[k, lens], stderr[k, lens])."""
-    g, se, prices = _forward_ad(prob, list(lenses), pricing_method, engine, shard, group, strikes=list(strikes))
+def strike_grid_greeks(prob, strikes, lenses, pricing_method, *, engine=None, shard=None, group=None, gamma_bump=None):
+    """Config C5: all `lenses` x all `strikes` from ONE simulation. Returns (prices[k], greeks[k, lens], stderr[k, lens]);
+    with `gamma_bump` (the absolute spot bump of SecondOrderGreekProblem + FiniteDifference, greeks_problem.jl:395-412) a
+    fourth element {"fd", "fd_stderr", "pathwise", "pathwise_stderr"}: gamma per strike from the same launch."""
+    out = _forward_ad(prob, list(lenses), pricing_method, engine, shard, group, strikes=list(strikes), spot_bump=gamma_bump)
+    if gamma_bump:
+        g, se, prices, second = out
+        return prices, g, se, second
+    g, se, prices = out
     return prices, g, se
+
+
+def _is_spot(lens):
+    return isinstance(lens, SpotLens) or (isinstance(lens, FieldLens) and lens.name == "spot")

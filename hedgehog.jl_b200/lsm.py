@@ -16,7 +16,7 @@ def solve_lsm(prob, method, *, engine=None, shard=None, group=None, stopping_inf
         raise TypeError("solve(::PricingProblem, ::LSM) is defined for American exercise")
     mc = method.mc_method
     eng = engine or api.default_engine()
-    shard, reduce = api._shard_and_reduce(shard, group)
+    shard, reduce = api._shard_and_reduce(shard, group, getattr(eng, "device", None))
     mdl = api._model_of(prob, mc)
     scheme = api._scheme_of(mc, for_lsm=True)
     if scheme == abi.HH_SCHEME_HESTON_BK:   # exact transitions between config.steps exercise dates
@@ -28,14 +28,35 @@ def solve_lsm(prob, method, *, engine=None, shard=None, group=None, stopping_inf
     step_discount = api.df(m.rate, api.add_yearfrac(m.referenceDate, T / sim.n_steps))   # lsm.jl:110
     comm = None
     keep = None
+    err = None
     if reduce is not None:
-        from .distributed import make_comm, peer_comm
-        if getattr(eng, "peers", None) == tuple(shard):
+        from .distributed import allreduce_max_int, make_comm, peer_comm
+        dev = getattr(eng, "device", None)
+        peer = getattr(eng, "peers", None) == tuple(shard)
+        if peer:
             comm = peer_comm(eng)              # moments exchanged in the pass kernel's tail over peer memory
+            # the in-kernel wait for a peer is bounded (hh_peer_set_timeout): enter the solve together, so that ordinary skew
+            # between ranks (module load, a 4 GB allocation, garbage collection) cannot be mistaken for a dead peer
+            import torch.distributed as dist
+            dist.barrier(group)
         else:
-            comm, keep = make_comm(shard, group)  # NCCL all-reduce through the hh_comm callback
-    out, tau, val, paths = eng.lsm_american(mdl, sim, (prob.payoff.strike, prob.payoff.call_put()), method.degree,
-                                            step_discount, want_stopping=stopping_info, want_paths=spot_paths, comm=comm)
+            comm, keep = make_comm(shard, group, dev)  # NCCL all-reduce through the hh_comm callback
+        try:
+            out, tau, val, paths = eng.lsm_american(mdl, sim, (prob.payoff.strike, prob.payoff.call_put()), method.degree,
+                                                    step_discount, want_stopping=stopping_info, want_paths=spot_paths, comm=comm)
+        except Exception as e:  # noqa: BLE001 - re-raised below, after every rank has learnt about it
+            err = e
+        if peer:
+            # every rank learns whether ANY rank failed before the sums are reduced: no rank is left waiting in a collective
+            # for one that raised (a timed-out exchange already fails on all ranks together, see hh_peer_set_timeout)
+            if allreduce_max_int(0 if err is None else 1, group, dev):
+                raise err if err is not None else abi.HedgehogB200Error(
+                    "hh_lsm_american failed on another rank; the peer connection is dead: connect_peers() again")
+        elif err is not None:
+            raise err
+    else:
+        out, tau, val, paths = eng.lsm_american(mdl, sim, (prob.payoff.strike, prob.payoff.call_put()), method.degree,
+                                                step_discount, want_stopping=stopping_info, want_paths=spot_paths, comm=comm)
     del keep
     s = np.array([out.sum, out.sumsq, float(out.n)])
     if reduce is not None:

@@ -163,7 +163,7 @@ def solve_path_dependent(payoffs: Sequence, market_inputs, method, *, engine=Non
         if getattr(p, "monitoring", Monitoring(every)).every != every:
             raise ValueError("payoffs priced on common trajectories must share the monitoring dates")
     eng = engine or api.default_engine()
-    shard, reduce = api._shard_and_reduce(shard, group)
+    shard, reduce = api._shard_and_reduce(shard, group, getattr(eng, "device", None))
     prob0 = api.PricingProblem(p0, market_inputs)
     mdl = api._model_of(prob0, method)
     scheme = api._scheme_of(method, for_lsm=True)                             # stepping form of BlackScholesExact
@@ -234,7 +234,7 @@ def solve_bs_control(prob, method, *, engine=None, shard=None, group=None):
     if not isinstance(prob.payoff, api.VanillaOption) or not isinstance(prob.payoff.underlying, api.Spot):
         raise TypeError("BlackScholesControlVariate prices European vanilla options on the Spot underlying")
     eng = engine or api.default_engine()
-    shard, reduce = api._shard_and_reduce(shard, group)
+    shard, reduce = api._shard_and_reduce(shard, group, getattr(eng, "device", None))
     mdl = api._model_of(prob, method)
     sim = api._sim_of(method, abi.HH_SCHEME_EM, shard)
     K, cp = prob.payoff.strike, prob.payoff.call_put()
@@ -243,7 +243,9 @@ def solve_bs_control(prob, method, *, engine=None, shard=None, group=None):
     bs = black_scholes_closed_form(mdl.S0, K, mdl.r, sigma_cv, mdl.T, cp)
     beta = cv.beta
     if beta is None:  # Cov(X, Y) = (Var X + Var Y - Var(X - Y)) / 2 from three sums of ONE pilot launch
-        seed = (int(method.config.base_seed) ^ 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
+        # explicit per-trajectory seeds leave base_seed unset: the pilot's key then derives from the first seed
+        base = method.config.base_seed if method.config.base_seed is not None else int(method.config.seeds[0])
+        seed = (int(base) ^ 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
         pilot = SimSpec(n_paths=max(2, min(cv.pilot, method.config.trajectories)), n_steps=sim.n_steps, scheme=abi.HH_SCHEME_EM,
                         vr=sim.vr, base_seed=seed)
         px, py, pd = eng.mc_path_dependent(mdl, pilot, [(abi.HH_PD_VANILLA, K, cp, 0.0, 0.0), (abi.HH_PD_BS_CONTROL, K, cp, 0.0, 0.0),

@@ -231,10 +231,19 @@ int hh_mc_european_tangent(hh_ctx *ctx, const hh_model *model, const hh_tangent 
                            double discount, hh_result *results, double *tangent_results,
                            double *tangent_stderr);
 /* Raw sums for multi-GPU reduction: out[k*(2+2*ntangents) + {0: sum payoff, 1: sum payoff^2,
- * 2+p: sum dpayoff_p, 2+ntangents+p: sum dpayoff_p^2}] over local trajectories. */
+ * 2+p: sum dpayoff_p, 2+ntangents+p: sum dpayoff_p^2}] over local trajectories.
+ *
+ * Second order in the spot from the SAME simulation (SecondOrderGreekProblem(spot, spot) + FiniteDifference(eps),
+ * greeks_problem.jl:395-412: ABSOLUTE bump, and the same seeds at S0 - eps, S0, S0 + eps): every scheme here is linear in
+ * S0, so the re-solved terminal spots are S_T (S0 +- eps) / S0 and the bumped payoffs are evaluated on the trajectories
+ * already simulated. second_sums: nullable, [npayoffs][4] = {sum sd, sum sd^2, sum dd, sum dd^2} with, per trajectory,
+ *   sd = payoff(S0 + eps) - 2 payoff(S0) + payoff(S0 - eps)      gamma = discount * mean(sd) / eps^2   (the reference's form)
+ *   dd = pathwise delta at S0 + eps minus at S0 - eps            gamma = discount * mean(dd) / (2 eps) (lower variance)
+ * spot_bump = eps in (0, S0); ignored when second_sums is NULL. */
 int hh_mc_european_tangent_sums(hh_ctx *ctx, const hh_model *model, const hh_tangent *tangents,
                                 int ntangents, const hh_sim *sim, const hh_payoff *payoffs,
-                                int npayoffs, double *sums, double *kernel_ms);
+                                int npayoffs, double *sums, double spot_bump, double *second_sums,
+                                double *kernel_ms);
 
 /* ---- Path-dependent payoffs on the simulation grid ------------------------------
  * Not in the reference yet: its roadmap lists them as Phase 5 (derivatives_pricing_roadmap.md:73-80: arithmetic /

@@ -28,6 +28,18 @@ int hho_threads(void) {
   return 1;
 #endif
 }
+/* threads an OpenMP parallel region really gets (what bench.py prints as `cores`) */
+int hho_threads_used(void) {
+  int n = 1;
+#ifdef _OPENMP
+#pragma omp parallel
+  {
+#pragma omp single
+    n = omp_get_num_threads();
+  }
+#endif
+  return n;
+}
 void hho_set_threads(int n) {
   g_threads = n;
 #ifdef _OPENMP
@@ -686,6 +698,59 @@ int hho_mc_european_tangent_sums(const hh_model *model, const hh_tangent *tangen
     free(dm);
   }
   for (size_t j = 0; j < tot; ++j) sums[j] = (double)acc[j];
+  free(acc);
+  return HH_OK;
+}
+
+/* Second order in the spot: SecondOrderGreekProblem(spot, spot) with FiniteDifference(eps), greeks.jl:395-412 — THREE
+ * solves at S0 - eps, S0, S0 + eps (absolute bump) on the same seeds, restated literally: every trajectory is simulated
+ * three times. second_sums[k][4] = {sum sd, sum sd^2, sum dd, sum dd^2} over trajectories (pair-averaged when antithetic),
+ *   sd = payoff(S0 + eps) - 2 payoff(S0) + payoff(S0 - eps),
+ *   dd = cp 1{..} S_T / S0 evaluated at S0 + eps minus the same at S0 - eps (the pathwise delta of each bumped solve). */
+int hho_mc_european_second_sums(const hh_model *model, const hh_sim *sim, const hh_payoff *payoffs, int npayoffs,
+                                double spot_bump, double *second_sums) {
+  int rc = check_args(model, sim);
+  if (rc) return rc;
+  if (npayoffs <= 0 || !payoffs || !second_sums || !(spot_bump > 0.0) || !(spot_bump < model->S0)) return HH_ERR_ARG;
+  const int64_t N = sim->n_paths;
+  const int anti = sim->vr == HH_VR_ANTITHETIC;
+  hh_model mu = *model, md = *model;
+  mu.S0 = model->S0 + spot_bump;
+  md.S0 = model->S0 - spot_bump;
+  const size_t tot = (size_t)npayoffs * 4;
+  long double *acc = calloc(tot, sizeof(long double));
+#pragma omp parallel
+  {
+    long double *la = calloc(tot, sizeof(long double));
+#pragma omp for schedule(static)
+    for (int64_t i = 0; i < N; ++i) {
+      terminal_t t0 = simulate_one(model, sim, i, NULL, NULL, 0);
+      terminal_t tu = simulate_one(&mu, sim, i, NULL, NULL, 0);
+      terminal_t td = simulate_one(&md, sim, i, NULL, NULL, 0);
+      for (int k = 0; k < npayoffs; ++k) {
+        const hh_payoff *po = &payoffs[k];
+        double sd = payoff_of(po, tu.Sp) - 2.0 * payoff_of(po, t0.Sp) + payoff_of(po, td.Sp);
+        double dd = (po->cp * (tu.Sp - po->strike) > 0 ? po->cp * tu.Sp / mu.S0 : 0.0) -
+                    (po->cp * (td.Sp - po->strike) > 0 ? po->cp * td.Sp / md.S0 : 0.0);
+        if (anti) {
+          double sdm = payoff_of(po, tu.Sm) - 2.0 * payoff_of(po, t0.Sm) + payoff_of(po, td.Sm);
+          double ddm = (po->cp * (tu.Sm - po->strike) > 0 ? po->cp * tu.Sm / mu.S0 : 0.0) -
+                       (po->cp * (td.Sm - po->strike) > 0 ? po->cp * td.Sm / md.S0 : 0.0);
+          sd = (sd + sdm) / 2;
+          dd = (dd + ddm) / 2;
+        }
+        long double *a = la + (size_t)k * 4;
+        a[0] += sd;
+        a[1] += (long double)sd * sd;
+        a[2] += dd;
+        a[3] += (long double)dd * dd;
+      }
+    }
+#pragma omp critical
+    for (size_t j = 0; j < tot; ++j) acc[j] += la[j];
+    free(la);
+  }
+  for (size_t j = 0; j < tot; ++j) second_sums[j] = (double)acc[j];
   free(acc);
   return HH_OK;
 }

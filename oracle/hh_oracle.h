@@ -36,6 +36,7 @@ void hho_normal_pair64(uint64_t key, uint64_t idx, uint32_t step, double *z1, do
 void hho_fill_normals(const hh_model *model, const hh_sim *sim, double *Z);
 
 int hho_threads(void);
+int hho_threads_used(void); /* measured inside a parallel region */
 void hho_set_threads(int n);
 
 /* solve(::PricingProblem, ::MonteCarlo)  montecarlo.jl:478-493 */
@@ -47,6 +48,11 @@ int hho_heston_em_terminal_v(const hh_model *model, const hh_sim *sim, double *v
 /* ForwardDiff through solve  greeks_problem.jl:249-262 — hand-derived tangent recursions. */
 int hho_mc_european_tangent_sums(const hh_model *model, const hh_tangent *tangents, int ntangents,
                                  const hh_sim *sim, const hh_payoff *payoffs, int npayoffs, double *sums);
+
+/* SecondOrderGreekProblem(spot, spot) + FiniteDifference(eps): three solves at S0 - eps, S0, S0 + eps on the same seeds
+ * (greeks_problem.jl:395-412), restated literally; second_sums[k][4] as in hh_mc_european_tangent_sums. */
+int hho_mc_european_second_sums(const hh_model *model, const hh_sim *sim, const hh_payoff *payoffs, int npayoffs,
+                                double spot_bump, double *second_sums);
 
 /* solve(::PricingProblem{American}, ::LSM)  least_squares_montecarlo.jl:99-136.
  * beta_out: nullable, [n_steps+1][degree+1] raw-monomial coefficients per date (0 where skipped). */

@@ -192,6 +192,7 @@ def lib():
         L.hho_normal_pair64.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, dp, dp]
         L.hho_fill_normals.argtypes = [C.POINTER(o_model), C.POINTER(o_sim), dp]
         L.hho_threads.restype = C.c_int
+        L.hho_threads_used.restype = C.c_int
         L.hho_set_threads.argtypes = [C.c_int]
         L.hho_mc_european.argtypes = [C.POINTER(o_model), C.POINTER(o_sim), C.POINTER(o_payoff), C.c_int,
                                       C.c_double, C.POINTER(o_result), dp, C.c_size_t]
@@ -200,6 +201,8 @@ def lib():
         L.hho_heston_em_terminal_v.argtypes = [C.POINTER(o_model), C.POINTER(o_sim), dp]
         L.hho_mc_european_tangent_sums.argtypes = [C.POINTER(o_model), C.POINTER(o_tangent), C.c_int,
                                                    C.POINTER(o_sim), C.POINTER(o_payoff), C.c_int, dp]
+        L.hho_mc_european_second_sums.argtypes = [C.POINTER(o_model), C.POINTER(o_sim), C.POINTER(o_payoff), C.c_int,
+                                                  C.c_double, dp]
         L.hho_lsm_american.argtypes = [C.POINTER(o_model), C.POINTER(o_sim), C.POINTER(o_payoff), C.c_int,
                                        C.c_double, C.POINTER(o_lsm_result), C.POINTER(C.c_int32), dp, dp, dp]
         L.hho_lsm_backward.argtypes = [dp, C.c_int64, C.c_int, C.POINTER(o_payoff), C.c_int, C.c_double,
@@ -251,6 +254,11 @@ class OracleEngine:
     def threads(self):
         return self.lib.hho_threads()
 
+    @property
+    def threads_used(self):
+        """OpenMP threads a parallel region really gets (omp_get_num_threads inside one)."""
+        return self.lib.hho_threads_used()
+
     def fill_normals(self, model, sim):
         s, keep = _sim_c(sim)
         ncomp = 2 if model.kind == HH_MODEL_HESTON else 1
@@ -288,7 +296,7 @@ class OracleEngine:
         _raise(self.lib.hho_heston_em_terminal_v(C.byref(_model_c(model)), C.byref(s), _dp(v)), "terminal_v")
         return v
 
-    def tangent_sums(self, model, tangents, sim, payoffs):
+    def tangent_sums(self, model, tangents, sim, payoffs, spot_bump: float = 0.0):
         s, keep = _sim_c(sim)
         pa = _payoff_array(payoffs)
         nt = len(tangents)
@@ -296,6 +304,11 @@ class OracleEngine:
         out = np.zeros((len(payoffs), 2 + 2 * nt))
         _raise(self.lib.hho_mc_european_tangent_sums(C.byref(_model_c(model)), ta, nt, C.byref(s), pa, len(payoffs), _dp(out)),
                "tangent_sums")
+        if spot_bump > 0:
+            second = np.zeros((len(payoffs), 4))
+            _raise(self.lib.hho_mc_european_second_sums(C.byref(_model_c(model)), C.byref(s), pa, len(payoffs),
+                                                        float(spot_bump), _dp(second)), "second_sums")
+            return out, 0.0, second
         return out, 0.0
 
     def lsm_american(self, model, sim, payoff, degree, step_discount, want_stopping=False, want_paths=False,

@@ -124,3 +124,68 @@ def test_specialised_heston_tangent_kernel_equals_generic_dual_kernel(cuda, orac
     scale = np.abs(s_oracle).max()
     assert np.allclose(s_special, s_generic, rtol=1e-10, atol=1e-10 * scale)
     assert np.allclose(s_special, s_oracle, rtol=1e-10, atol=1e-9 * scale)
+
+
+# ---- second order in the spot (gamma): SecondOrderGreekProblem(spot, spot), greeks_problem.jl:395-412 ----------------------
+@pytest.mark.parametrize("anti", [False, True])
+@pytest.mark.parametrize("kind", ["heston", "heston_parity", "gbm_em", "gbm_steps", "gbm_terminal"])
+def test_second_order_sums_equal_three_solves_of_the_oracle(cuda, oracle, kind, anti):
+    """The kernel evaluates the bumped payoffs on the trajectories it has (every scheme is linear in S0); the oracle
+    re-simulates every trajectory at S0 - eps, S0, S0 + eps like the reference's FiniteDifference does. Same sums."""
+    n, eps = 6000, 0.35
+    pay = [(k, 1.0) for k in (80.0, 100.0, 120.0)] + [(100.0, -1.0)]
+    if kind.startswith("heston"):
+        m, steps, scheme = heston_model(), 40, abi.HH_SCHEME_EM
+        tans = heston_dirs(m)[:3]
+    else:
+        m = gbm_model(T=366 / 365)
+        steps = 1 if kind == "gbm_terminal" else 20
+        scheme = {"gbm_em": abi.HH_SCHEME_EM, "gbm_steps": abi.HH_SCHEME_EXACT_STEPS, "gbm_terminal": abi.HH_SCHEME_EXACT_TERMINAL}[kind]
+        tans = [_tan(dS0=1.0), _tan(dsigma=1.0)]
+    sim = SimSpec(n_paths=n, n_steps=steps, scheme=scheme, vr=int(anti), base_seed=31)
+    if kind == "heston_parity":   # the generic Dual<P> template instead of the specialised tangent kernel
+        sim = SimSpec(n_paths=n, n_steps=steps, scheme=scheme, vr=int(anti), rng_mode=abi.HH_RNG_NORMALS,
+                      normals=oracle.fill_normals(m, sim))
+    sg, _, g2 = cuda.tangent_sums(m, tans, sim, pay, spot_bump=eps)
+    so, _, o2 = oracle.tangent_sums(m, tans, sim, pay, spot_bump=eps)
+    assert np.allclose(sg, so, rtol=1e-10, atol=1e-9 * np.abs(so).max())
+    # sd is a difference of O(10) payoffs: absolute agreement at the rounding level of the payoffs
+    assert np.allclose(g2[:, 0], o2[:, 0], rtol=1e-9, atol=1e-9)
+    assert np.allclose(g2[:, 1], o2[:, 1], rtol=1e-8, atol=1e-9)
+    assert np.allclose(g2[:, 2:], o2[:, 2:], rtol=1e-9, atol=1e-10)
+    # first-order sums do not change when the second-order ones are requested
+    s0, _ = cuda.tangent_sums(m, tans, sim, pay)
+    assert np.array_equal(s0, sg)
+    with pytest.raises(ValueError):
+        cuda.tangent_sums(m, tans, sim, pay, spot_bump=m.S0 + 1.0)
+
+
+def test_heston_delta_gamma_vega_against_carr_madan(cuda):
+    """Heston delta / gamma / vega (dV0) of the C5 problem on a strike grid, from ONE launch, within 3 standard errors (+ the
+    Euler-Maruyama bias allowance) of finite differences of the Carr-Madan price (tests/golden/config_anchors.json)."""
+    import datetime as dt
+    import json
+    import os
+    anchors = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "config_anchors.json")))["c5"]
+    strikes = np.array(anchors["strikes"])
+    payoff = hh.VanillaOption(100.0, dt.date(2020, 12, 31), hh.European(), hh.Call(), hh.Spot())
+    market = hh.HestonInputs(dt.date(2020, 1, 1), 0.03, 100.0, 0.04, 2.0, 0.04, 0.3, -0.7)
+    prob = hh.PricingProblem(payoff, market)
+    mc = hh.MonteCarlo(hh.HestonDynamics(), hh.EulerMaruyama(), hh.SimulationConfig(4_000_000, steps=252, base_seed=17), ensemble=False)
+    lenses = [hh.SpotLens(), hh.optic("market_inputs.V0")]
+    prices, g, se, sec = hh.strike_grid_greeks(prob, strikes, lenses, mc, engine=cuda, gamma_bump=0.5)
+    sel = slice(8, 56)  # strikes 70..130: away from the wings where the estimators have few in-the-money paths
+    for name, est, err, ref, bias in (("delta", g[:, 0], se[:, 0], np.array(anchors["d_S0"]), 2e-3),
+                                      ("vega", g[:, 1], se[:, 1], np.array(anchors["d_V0"]), 0.6),
+                                      ("gamma_fd", sec["fd"], sec["fd_stderr"], np.array(anchors["d2_S0"]), 4e-4),
+                                      ("gamma_pw", sec["pathwise"], sec["pathwise_stderr"], np.array(anchors["d2_S0"]), 4e-4)):
+        z = np.abs(est[sel] - ref[sel]) / (3 * err[sel] + bias)
+        assert z.max() < 1.0, (name, float(z.max()), int(z.argmax()))
+    assert np.all(np.abs(prices[sel] - np.array(anchors["price"])[sel]) < 3 * 0.008 + 0.012)
+    # both gamma estimators agree with each other and the delta-difference form has the smaller standard error
+    assert np.all(np.abs(sec["fd"][sel] - sec["pathwise"][sel]) < 4 * np.hypot(sec["fd_stderr"][sel], sec["pathwise_stderr"][sel]))
+    # SecondOrderGreekProblem through solve takes the same launch
+    gam = hh.solve(hh.SecondOrderGreekProblem(hh.PricingProblem(hh.VanillaOption(float(strikes[32]), dt.date(2020, 12, 31), hh.European(),
+                                                                                hh.Call(), hh.Spot()), market),
+                                              hh.SpotLens(), hh.SpotLens()), hh.FiniteDifference(0.5), mc, engine=cuda)
+    assert gam.greek == pytest.approx(sec["fd"][32], rel=1e-12)
