@@ -104,7 +104,7 @@ int hh_destroy(hh_ctx *ctx) {
   hh::DeviceBuffer *bufs[] = {&ctx->d_payoffs,  &ctx->d_partials, &ctx->d_final, &ctx->d_terminal,
                               &ctx->d_seeds,    &ctx->d_normals,  &ctx->d_tangents, &ctx->d_grid,
                               &ctx->d_cash,     &ctx->d_tau,      &ctx->d_lsm_partials, &ctx->d_lsm_state,
-                              &ctx->d_misc,     &ctx->d_counters, &ctx->d_bk_slab};
+                              &ctx->d_misc,     &ctx->d_counters, &ctx->d_bk_slab, &ctx->d_bk_work};
   for (auto *b : bufs) b->release();
   for (int q = 0; q < ctx->peer_world; ++q)
     if (q != ctx->peer_rank && ctx->peer_mail[q]) cudaIpcCloseMemHandle(ctx->peer_mail[q]);

@@ -246,6 +246,16 @@ __device__ BkInversion bk_sample_integral(const BkParams &p, double V0, double V
   return r;
 }
 
+// series_rk[k] = 1 / (k (nu + k)), hankel_bk[k] = (4 nu^2 - (2k-1)^2) / (8 k), by all threads of the block (IEEE division: once)
+__device__ __forceinline__ void bk_fill_order_tables(double nu, double *rk, double *bk) {
+  for (int k = threadIdx.x; k < kSeriesMaxTerms; k += blockDim.x) rk[k] = k ? 1.0 / ((double)k * (nu + (double)k)) : 0.0;
+  for (int k = threadIdx.x; k < kHankelMaxTerms; k += blockDim.x) {
+    const double odd = (double)(2 * k - 1);
+    bk[k] = k ? (4.0 * nu * nu - odd * odd) / (8.0 * (double)k) : 0.0;
+  }
+}
+
+#ifdef HH_TUNING  // the one-thread-per-trajectory kernel of round 1 (49 % idle lanes): kept for reference, not built
 struct BkArgs {
   int64_t n, path_offset;
   uint64_t base_seed;
@@ -264,15 +274,6 @@ struct BkArgs {
   int64_t slab_stride;
   unsigned long long *counters;  // [0] fallbacks, [1] sum J, [2] sum root-finder evaluations, [3] transitions, [4] unbracketed accepted
 };
-
-// series_rk[k] = 1 / (k (nu + k)), hankel_bk[k] = (4 nu^2 - (2k-1)^2) / (8 k), by all threads of the block (IEEE division: once)
-__device__ __forceinline__ void bk_fill_order_tables(double nu, double *rk, double *bk) {
-  for (int k = threadIdx.x; k < kSeriesMaxTerms; k += blockDim.x) rk[k] = k ? 1.0 / ((double)k * (nu + (double)k)) : 0.0;
-  for (int k = threadIdx.x; k < kHankelMaxTerms; k += blockDim.x) {
-    const double odd = (double)(2 * k - 1);
-    bk[k] = k ? (4.0 * nu * nu - odd * odd) / (8.0 * (double)k) : 0.0;
-  }
-}
 
 // MINB = resident blocks per SM the register allocation is bounded for (3: 168 registers; 6: 85). The kernel is
 // latency-bound (issue slots 30 % busy at 12 warps per SM, ncu), so the bound is chosen by measurement: HH_BK_MINB.
@@ -366,6 +367,231 @@ __global__ void __launch_bounds__(kBkThreads, MINB) bk_paths_kernel(const BkArgs
     atomicAdd(&a.counters[2], sumIt);
     atomicAdd(&a.counters[3], ntr);
     atomicAdd(&a.counters[4], nsec);
+  }
+}
+
+#endif  // HH_TUNING
+
+// ---- the transition-sorted pipeline (what hh_mc_european / hh_lsm_american / hh_mc_path_dependent launch) --------------
+// The variance chain V_0 -> V_1 -> ... does not depend on the integrals or on the spot, so all n_paths x n_dates
+// transitions (V0, VT, u) are independent units of work. ncu on the one-thread-per-trajectory kernel above showed 49 % of
+// the lanes idle: lanes of a warp sit at the same series index j but at unrelated (V0, VT), and the Bessel arguments of
+// C4 straddle the series / Hankel boundary (|z| ~ 20), so half of the warps executed both branches one after the other.
+// Here (1) bk_chain_kernel draws every V', u, z from the trajectory's Philox stream (same counters, same draws as above)
+// and histograms the transitions by log2(V0 VT) (32 buckets per octave); (2) a counting sort orders the transitions by
+// that key; (3) bk_integral_sorted_kernel inverts them in sorted order — the 32 lanes of a warp now hold near-identical
+// z_kappa, hence the same Bessel branch, similar series lengths and the same J (+-1); (4) bk_assemble_kernel walks each
+// trajectory through its dates. Results are the ones of the kernel above to the last bit (same device functions, and
+// no lane depends on its neighbours); the extra HBM traffic (~100 B per transition) is ~1 % of the run time.
+constexpr int kBkBuckets = 1024;
+constexpr int kBkKeyBase = (1023 - 26) << 5;  // hi word >> 15 of 2^-26: sqrt(V0 VT) from 1.2e-4 (below: bucket 0) to 8
+constexpr int kBkScatterTile = 4096;
+
+__device__ __forceinline__ int bk_bucket(double v0, double vt) {
+  const int k = (__double2hiint(v0 * vt) >> 15) - kBkKeyBase;  // exponent and 5 mantissa bits of the product
+  return min(max(k, 0), kBkBuckets - 1);
+}
+
+struct BkChainArgs {
+  int64_t n, path_offset;  // trajectories of this chunk, global index of its first trajectory
+  uint64_t base_seed;
+  const uint64_t *seeds;   // nullable, already offset to the chunk
+  int n_dates;
+  BkParams p;
+  double v0;
+  double *V;       // (n_dates + 1) x n, date-major
+  double *U, *Z;   // n_dates x n
+  unsigned *hist;  // kBkBuckets
+};
+
+__global__ void __launch_bounds__(256) bk_chain_kernel(const BkChainArgs a) {
+  __shared__ unsigned s_hist[kBkBuckets];
+  for (int k = threadIdx.x; k < kBkBuckets; k += blockDim.x) s_hist[k] = 0;
+  __syncthreads();
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (int64_t)gridDim.x * blockDim.x) {
+    BkRng rng;
+    uint64_t key = a.base_seed, idx = (uint64_t)(a.path_offset + i);
+    if (a.seeds) {
+      key = a.seeds[i];
+      idx = 0;
+    }
+    rng.c0 = (uint32_t)idx;
+    rng.c1 = (uint32_t)(idx >> 32);
+    rng.k0 = (uint32_t)key;
+    rng.k1 = (uint32_t)(key >> 32);
+    double v = a.v0;
+    a.V[i] = v;
+    for (int n = 0; n < a.n_dates; ++n) {
+      rng.c2 = (uint32_t)n;
+      rng.draw = 0;
+      const double vt = fmax(a.p.c_scale * bk_ncx2(rng, a.p.dof, a.p.lam_scale * v), 1e-300);  // sample_V_T
+      double u, z, dummy;
+      rng.uniforms(u, dummy);
+      rng.normals(z, dummy);
+      atomicAdd(&s_hist[bk_bucket(fmax(v, 1e-300), vt)], 1u);
+      a.V[(int64_t)(n + 1) * a.n + i] = vt;
+      a.U[(int64_t)n * a.n + i] = u;
+      a.Z[(int64_t)n * a.n + i] = z;
+      v = vt;
+    }
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < kBkBuckets; k += blockDim.x)
+    if (s_hist[k]) atomicAdd(&a.hist[k], s_hist[k]);
+}
+
+// hist -> exclusive prefix sums, in place (one block of kBkBuckets threads)
+__global__ void __launch_bounds__(kBkBuckets) bk_scan_kernel(unsigned *hist) {
+  __shared__ unsigned s[kBkBuckets];
+  const int t = threadIdx.x;
+  const unsigned own = hist[t];
+  s[t] = own;
+  __syncthreads();
+  for (int o = 1; o < kBkBuckets; o <<= 1) {
+    const unsigned add = t >= o ? s[t - o] : 0u;
+    __syncthreads();
+    s[t] += add;
+    __syncthreads();
+  }
+  hist[t] = s[t] - own;
+}
+
+// perm[sorted position] = transition index t = date * n + trajectory. Every block ranks a tile of transitions in a
+// shared-memory histogram and reserves one range per non-empty bucket (the order inside a bucket is irrelevant).
+__global__ void __launch_bounds__(256) bk_scatter_kernel(const double *V, int64_t n, int64_t items, unsigned *cursor,
+                                                         unsigned *perm) {
+  __shared__ unsigned s_cnt[kBkBuckets], s_base[kBkBuckets];
+  constexpr int PER = kBkScatterTile / 256;
+  for (int64_t tile = blockIdx.x; tile * kBkScatterTile < items; tile += gridDim.x) {
+    for (int k = threadIdx.x; k < kBkBuckets; k += 256) s_cnt[k] = 0;
+    __syncthreads();
+    int key[PER];
+    unsigned rank[PER];
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+      const int64_t t = tile * kBkScatterTile + k * 256 + threadIdx.x;
+      key[k] = -1;
+      if (t < items) {
+        key[k] = bk_bucket(fmax(V[t], 1e-300), V[t + n]);
+        rank[k] = atomicAdd(&s_cnt[key[k]], 1u);
+      }
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < kBkBuckets; k += 256) {
+      const unsigned c = s_cnt[k];
+      s_base[k] = c ? atomicAdd(&cursor[k], c) : 0u;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < PER; ++k)
+      if (key[k] >= 0) perm[s_base[key[k]] + rank[k]] = (unsigned)(tile * kBkScatterTile + k * 256 + threadIdx.x);
+    __syncthreads();
+  }
+}
+
+struct BkIntArgs {
+  int64_t items, n;
+  BkParams p;
+  const double *V, *U;
+  const unsigned *perm;
+  double *I;
+  double *slab;
+  int64_t slab_stride;
+  unsigned long long *counters;
+};
+
+template <int MINB>
+__global__ void __launch_bounds__(kBkThreads, MINB) bk_integral_sorted_kernel(const BkIntArgs a) {
+  extern __shared__ double s_tab[];
+  BkTable tb;
+  tb.sh = s_tab + threadIdx.x;
+  tb.sh_stride = kBkThreads;
+  tb.cap = kBkTable;
+  tb.slab = a.slab + ((int64_t)blockIdx.x * kBkThreads + threadIdx.x);
+  tb.slab_stride = a.slab_stride;
+  __shared__ BkParams s_p;
+  __shared__ double s_rk[kSeriesMaxTerms], s_bk[kHankelMaxTerms];
+  bk_fill_order_tables(a.p.ord.nu, s_rk, s_bk);
+  if (threadIdx.x == 0) {
+    s_p = a.p;
+    s_p.ord.series_rk = s_rk;
+    s_p.ord.hankel_bk = s_bk;
+  }
+  __syncthreads();
+  const BkParams &p = s_p;
+  unsigned long long nfall = 0, sumJ = 0, sumIt = 0, ntr = 0, nsec = 0;
+  for (int64_t k = (int64_t)blockIdx.x * kBkThreads + threadIdx.x; k < a.items; k += (int64_t)gridDim.x * kBkThreads) {
+    const int64_t t = a.perm[k];
+    const BkInversion inv = bk_sample_integral(p, fmax(a.V[t], 1e-300), a.V[t + a.n], a.U[t], tb);  // sample_integral_V
+    a.I[t] = inv.x;
+    nfall += inv.status == 2;
+    nsec += inv.status == 1;
+    sumJ += (unsigned)inv.J;
+    sumIt += (unsigned)inv.iters;
+    ++ntr;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    nfall += __shfl_down_sync(0xffffffffu, nfall, o);
+    sumJ += __shfl_down_sync(0xffffffffu, sumJ, o);
+    sumIt += __shfl_down_sync(0xffffffffu, sumIt, o);
+    ntr += __shfl_down_sync(0xffffffffu, ntr, o);
+    nsec += __shfl_down_sync(0xffffffffu, nsec, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(&a.counters[0], nfall);
+    atomicAdd(&a.counters[1], sumJ);
+    atomicAdd(&a.counters[2], sumIt);
+    atomicAdd(&a.counters[3], ntr);
+    atomicAdd(&a.counters[4], nsec);
+  }
+}
+
+struct BkAsmArgs {
+  int64_t n;        // trajectories of this chunk
+  int64_t n_total;  // trajectories of the whole launch (row length of `stats`)
+  int n_dates;
+  BkParams p;
+  double x0, s0;
+  const double *V, *Z, *I;
+  double *terminal, *vterm, *grid, *stats;  // already offset to the chunk's first trajectory; vterm / grid / stats nullable
+  int64_t grid_stride;
+  int monitor_every;
+  double inv_m;
+};
+
+// sample_log_S_T (heston.jl:278-300) along the dates of each trajectory, with the HestonNoise restart (:82-91)
+__global__ void __launch_bounds__(256) bk_assemble_kernel(const BkAsmArgs a) {
+  const BkParams &p = a.p;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (int64_t)gridDim.x * blockDim.x) {
+    double x = a.x0, v = a.V[i];
+    if (a.grid) a.grid[i] = a.s0;
+    double sum_s = 0.0, sum_x = 0.0, max_x = -INFINITY, min_x = INFINITY;  // running statistics (a.stats only)
+    int due = a.monitor_every;
+    for (int n = 0; n < a.n_dates; ++n) {
+      const int64_t t = (int64_t)n * a.n + i;
+      const double vt = a.V[t + a.n], iv = a.I[t], z = a.Z[t];
+      const double mu = x + p.r_tau - 0.5 * iv + p.rho_over_xi * (vt - v - p.kappa_theta_tau + p.kappa * iv);
+      x = mu + sqrt(p.one_m_rho2 * iv) * z;
+      v = vt;
+      if (a.grid) a.grid[(int64_t)(n + 1) * a.grid_stride + i] = exp(x);
+      if (a.stats && --due == 0) {  // a monitoring date: the transition is exact, so the statistics carry no time-stepping bias
+        due = a.monitor_every;
+        sum_x += x;
+        max_x = fmax(max_x, x);
+        min_x = fmin(min_x, x);
+        sum_s += exp(x);
+      }
+    }
+    a.terminal[i] = exp(x);
+    if (a.vterm) a.vterm[i] = v;
+    if (a.stats) {  // S_T, A, G, max S, min S
+      a.stats[i] = exp(x);
+      a.stats[a.n_total + i] = sum_s * a.inv_m;
+      a.stats[2 * a.n_total + i] = exp(sum_x * a.inv_m);
+      a.stats[3 * a.n_total + i] = exp(max_x);
+      a.stats[4 * a.n_total + i] = exp(min_x);
+    }
   }
 }
 
@@ -472,26 +698,27 @@ static int bk_set_smem(hh_ctx *ctx) {
   static PerDeviceOnce done;
   if (done.done(ctx->device)) return HH_OK;
   const int bytes = kBkThreads * kBkTable * (int)sizeof(double);
-  HH_CUDA(ctx, cudaFuncSetAttribute(bk_paths_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-  HH_CUDA(ctx, cudaFuncSetAttribute(bk_paths_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-  HH_CUDA(ctx, cudaFuncSetAttribute(bk_paths_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-  HH_CUDA(ctx, cudaFuncSetAttribute(bk_paths_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  HH_CUDA(ctx, cudaFuncSetAttribute(bk_integral_sorted_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  HH_CUDA(ctx, cudaFuncSetAttribute(bk_integral_sorted_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  HH_CUDA(ctx, cudaFuncSetAttribute(bk_integral_sorted_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  HH_CUDA(ctx, cudaFuncSetAttribute(bk_integral_sorted_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   HH_CUDA(ctx, cudaFuncSetAttribute(bk_integral_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   done.set(ctx->device);
   return HH_OK;
 }
 
-// Launches the path kernel for `s` (validated by the caller); terminal spots land in ctx->d_terminal, path statistics in
-// `d_stats` when non-null. Records ev0 before the kernel.
-static int bk_paths_launch(hh_ctx *ctx, const hh_model *m, const hh_sim *s, double *d_stats, int monitor_every, BkArgs &a,
+// Runs the pipeline for `s` (validated by the caller); terminal spots land in ctx->d_terminal, path statistics in
+// `d_stats` when non-null. Records ev0 before the first kernel. Large jobs are cut into chunks of trajectories so that the
+// work arrays (36 B per transition) stay below ~5 GB.
+static int bk_paths_launch(hh_ctx *ctx, const hh_model *m, const hh_sim *s, double *d_stats, int monitor_every,
                            double *d_grid = nullptr, int64_t grid_stride = 0) {
   if (s->rng_mode != HH_RNG_PHILOX)
     return ctx->fail(HH_ERR_UNSUPPORTED, "Broadie-Kaya draws from the in-kernel Philox stream only; the deterministic "
                                          "pieces have their own parity probes (hh_bk_chf, hh_bk_integral)");
   if (s->precision != HH_PREC_F64) return ctx->fail(HH_ERR_UNSUPPORTED, "Broadie-Kaya runs in f64 only");
   const int ndates = s->n_steps > 0 ? s->n_steps : 1;
-  memset(&a, 0, sizeof a);
-  int rc = make_params(ctx, m, m->T / ndates, &s->bk, a.p);
+  BkParams p;
+  int rc = make_params(ctx, m, m->T / ndates, &s->bk, p);
   if (rc) return rc;
   const int64_t N = s->n_paths;
   HH_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -501,52 +728,101 @@ static int bk_paths_launch(hh_ctx *ctx, const hh_model *m, const hh_sim *s, doub
   const int smem = kBkThreads * kBkTable * (int)sizeof(double);
   static const int minb_env = getenv("HH_BK_MINB") ? atoi(getenv("HH_BK_MINB")) : kBkDefaultMinb;
   const int minb = minb_env < 3 ? 3 : (minb_env > 6 ? 6 : minb_env);
-  void (*kern)(const BkArgs) = minb == 3 ? bk_paths_kernel<3> : minb == 4 ? bk_paths_kernel<4> : minb == 5 ? bk_paths_kernel<5>
-                                                                                                             : bk_paths_kernel<6>;
+  void (*kern)(const BkIntArgs) = minb == 3   ? bk_integral_sorted_kernel<3>
+                                  : minb == 4 ? bk_integral_sorted_kernel<4>
+                                  : minb == 5 ? bk_integral_sorted_kernel<5>
+                                              : bk_integral_sorted_kernel<6>;
   int occ = 1;
   HH_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kBkThreads, smem));
   if (occ < 1) occ = 1;
-  const int64_t want_blocks = (N + kBkThreads - 1) / kBkThreads;
-  int64_t grid = (int64_t)ctx->sm_count * occ;
-  if (grid > want_blocks) grid = want_blocks;
-  rc = ensure_slab(ctx, (int)grid, a.p, &a.slab, &a.slab_stride);
+  // chunks of trajectories: at most 2^27 transitions each
+  const int64_t max_items = (int64_t)1 << 27;
+  int64_t chunk = max_items / ndates;
+  if (chunk < 1) chunk = 1;
+  if (chunk > N) chunk = N;
+  const int64_t chunk_items = chunk * ndates;
+  int64_t igrid = (int64_t)ctx->sm_count * occ;
+  const int64_t want_blocks = (chunk_items + kBkThreads - 1) / kBkThreads;
+  if (igrid > want_blocks) igrid = want_blocks;
+  BkIntArgs ia;
+  memset(&ia, 0, sizeof ia);
+  rc = ensure_slab(ctx, (int)igrid, p, &ia.slab, &ia.slab_stride);
   if (rc) return rc;
+  // work arrays: V (ndates + 1) x chunk, U, Z, I: ndates x chunk (f64), perm: ndates x chunk (u32), histogram
+  const size_t nV = (size_t)(ndates + 1) * (size_t)chunk, nI = (size_t)chunk_items;
+  HH_CUDA(ctx, ctx->d_bk_work.ensure(sizeof(double) * (nV + 3 * nI) + sizeof(unsigned) * (nI + kBkBuckets) + 64));
+  double *dV = ctx->d_bk_work.as<double>(), *dU = dV + nV, *dZ = dU + nI, *dI = dZ + nI;
+  unsigned *dperm = reinterpret_cast<unsigned *>(dI + nI), *dhist = dperm + nI;
   HH_CUDA(ctx, ctx->d_terminal.ensure(sizeof(double) * (size_t)N));
   HH_CUDA(ctx, ctx->d_counters.ensure(sizeof(unsigned long long) * 8));
   HH_CUDA(ctx, cudaMemsetAsync(ctx->d_counters.ptr, 0, sizeof(unsigned long long) * 8, st));
-  a.n = N;
-  a.path_offset = s->path_offset;
-  a.base_seed = s->base_seed;
   if (s->seeds) {
     const size_t bytes = sizeof(uint64_t) * (size_t)N;
     HH_CUDA(ctx, ctx->d_seeds.ensure(bytes));
     HH_CUDA(ctx, cudaMemcpyAsync(ctx->d_seeds.ptr, s->seeds, bytes, cudaMemcpyHostToDevice, st));
-    a.seeds = ctx->d_seeds.as<uint64_t>();
   }
-  a.n_dates = ndates;
-  a.x0 = log(m->S0);
-  a.v0 = m->V0;
-  a.s0 = m->S0;
-  a.grid = d_grid;
-  a.grid_stride = grid_stride;
-  a.terminal = ctx->d_terminal.as<double>();
-  a.counters = ctx->d_counters.as<unsigned long long>();
-  a.stats = d_stats;
-  a.monitor_every = monitor_every > 0 ? monitor_every : 1;
-  a.inv_m = 1.0 / (double)(ndates / a.monitor_every > 0 ? ndates / a.monitor_every : 1);
   HH_CUDA(ctx, cudaEventRecord(ctx->ev0, st));
-  kern<<<(unsigned)grid, kBkThreads, smem, st>>>(a);
-  HH_CUDA(ctx, cudaGetLastError());
+  const int mon = monitor_every > 0 ? monitor_every : 1;
+  for (int64_t c0 = 0; c0 < N; c0 += chunk) {
+    const int64_t cn = N - c0 < chunk ? N - c0 : chunk, items = cn * ndates;
+    const int64_t path_blocks = (cn + 255) / 256, cap = (int64_t)ctx->sm_count * 8;
+    HH_CUDA(ctx, cudaMemsetAsync(dhist, 0, sizeof(unsigned) * kBkBuckets, st));
+    BkChainArgs ca;
+    memset(&ca, 0, sizeof ca);
+    ca.n = cn;
+    ca.path_offset = s->path_offset + c0;
+    ca.base_seed = s->base_seed;
+    ca.seeds = s->seeds ? ctx->d_seeds.as<uint64_t>() + c0 : nullptr;
+    ca.n_dates = ndates;
+    ca.p = p;
+    ca.v0 = m->V0;
+    ca.V = dV;
+    ca.U = dU;
+    ca.Z = dZ;
+    ca.hist = dhist;
+    bk_chain_kernel<<<(unsigned)(path_blocks < cap ? path_blocks : cap), 256, 0, st>>>(ca);
+    bk_scan_kernel<<<1, kBkBuckets, 0, st>>>(dhist);
+    const int64_t tiles = (items + kBkScatterTile - 1) / kBkScatterTile;
+    bk_scatter_kernel<<<(unsigned)(tiles < cap ? tiles : cap), 256, 0, st>>>(dV, cn, items, dhist, dperm);
+    ia.items = items;
+    ia.n = cn;
+    ia.p = p;
+    ia.V = dV;
+    ia.U = dU;
+    ia.perm = dperm;
+    ia.I = dI;
+    ia.counters = ctx->d_counters.as<unsigned long long>();
+    const int64_t wb = (items + kBkThreads - 1) / kBkThreads;
+    kern<<<(unsigned)(igrid < wb ? igrid : wb), kBkThreads, smem, st>>>(ia);
+    BkAsmArgs aa;
+    memset(&aa, 0, sizeof aa);
+    aa.n = cn;
+    aa.n_total = N;
+    aa.n_dates = ndates;
+    aa.p = p;
+    aa.x0 = log(m->S0);
+    aa.s0 = m->S0;
+    aa.V = dV;
+    aa.Z = dZ;
+    aa.I = dI;
+    aa.terminal = ctx->d_terminal.as<double>() + c0;
+    aa.grid = d_grid ? d_grid + c0 : nullptr;
+    aa.grid_stride = grid_stride;
+    aa.stats = d_stats ? d_stats + c0 : nullptr;
+    aa.monitor_every = mon;
+    aa.inv_m = 1.0 / (double)(ndates / mon > 0 ? ndates / mon : 1);
+    bk_assemble_kernel<<<(unsigned)(path_blocks < cap ? path_blocks : cap), 256, 0, st>>>(aa);
+    HH_CUDA(ctx, cudaGetLastError());
+  }
   return HH_OK;
 }
 
 int bk_european_launch(hh_ctx *ctx, const hh_model *m, const hh_sim *s, const hh_payoff *payoffs, int npay,
                        int want_terminal) {
   if (npay < 1 || npay > 256 || !payoffs) return ctx->fail(HH_ERR_ARG, "npayoffs must be in [1, 256] (got %d)", npay);
-  BkArgs a;
-  int rc = bk_paths_launch(ctx, m, s, nullptr, 1, a);
+  int rc = bk_paths_launch(ctx, m, s, nullptr, 1);
   if (rc) return rc;
-  rc = terminal_payoffs_launch(ctx, a.terminal, s->n_paths, payoffs, npay, 0);
+  rc = terminal_payoffs_launch(ctx, ctx->d_terminal.as<double>(), s->n_paths, payoffs, npay, 0);
   if (rc) return rc;
   ctx->pend.want_terminal = want_terminal != 0;
   ctx->pend.bk = true;
@@ -558,13 +834,11 @@ int bk_european_launch(hh_ctx *ctx, const hh_model *m, const hh_sim *s, const hh
 // into `d_stats` (device), the inversion counters into ctx->bk_stats after the caller has synchronised and called
 // bk_read_counters.
 int bk_path_stats_launch(hh_ctx *ctx, const hh_model *m, const hh_sim *s, int monitor_every, double *d_stats) {
-  BkArgs a;
-  return bk_paths_launch(ctx, m, s, d_stats, monitor_every, a);
+  return bk_paths_launch(ctx, m, s, d_stats, monitor_every);
 }
 
 int bk_path_grid_launch(hh_ctx *ctx, const hh_model *m, const hh_sim *s, double *d_grid, int64_t grid_stride) {
-  BkArgs a;
-  return bk_paths_launch(ctx, m, s, nullptr, 1, a, d_grid, grid_stride);
+  return bk_paths_launch(ctx, m, s, nullptr, 1, d_grid, grid_stride);
 }
 
 int bk_read_counters(hh_ctx *ctx, int64_t *n_fallback) {  // after the stream has been synchronised

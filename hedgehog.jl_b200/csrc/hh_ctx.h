@@ -89,7 +89,7 @@ struct hh_ctx {
   std::string err;
 
   hh::DeviceBuffer d_payoffs, d_partials, d_final, d_terminal, d_seeds, d_normals, d_tangents;
-  hh::DeviceBuffer d_grid, d_cash, d_tau, d_lsm_partials, d_lsm_state, d_misc, d_counters, d_bk_slab;
+  hh::DeviceBuffer d_grid, d_cash, d_tau, d_lsm_partials, d_lsm_state, d_misc, d_counters, d_bk_slab, d_bk_work;
   // peer mailboxes (hh_peer_*): own buffer + the peers' buffers mapped through CUDA IPC
   void *mailbox = nullptr;
   void *peer_mail[HH_MAX_PEERS] = {};
