@@ -23,6 +23,7 @@ int bk_european_launch(hh_ctx *ctx, const hh_model *model, const hh_sim *sim, co
 int bk_integral(hh_ctx *ctx, const hh_model *m, double tau, const hh_bk_config *cfg, const double *V0, const double *VT,
                 const double *U, int n, double *out8);
 int bk_variance(hh_ctx *ctx, const hh_model *m, double tau, const double *V0, int n, uint64_t seed, double *VT);
+int bk_elementary(hh_ctx *ctx, int kind, const double *x, const double *y, int n, double *out_a, double *out_b);
 int fp64_peak(hh_ctx *ctx, double *tflops, double *ms);
 int heston_ablation(hh_ctx *ctx, int64_t n_paths, int n_steps, int rng_mode, int part, double *ms);
 }  // namespace hh
@@ -366,6 +367,13 @@ int hh_bk_variance(hh_ctx *ctx, const hh_model *model, double tau, const double 
   std::lock_guard<std::mutex> lk(ctx->mu);
   NvtxRange nv("hh_bk_variance");
   return hh::bk_variance(ctx, model, tau, V0, n, seed, VT);
+}
+
+int hh_bk_elementary(hh_ctx *ctx, int kind, const double *x, const double *y, int n, double *out_a, double *out_b) {
+  if (!ctx) return HH_ERR_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  NvtxRange nv("hh_bk_elementary");
+  return hh::bk_elementary(ctx, kind, x, y, n, out_a, out_b);
 }
 
 int hh_bk_last_stats(hh_ctx *ctx, double *out5) {

@@ -48,7 +48,6 @@ HH_HD cplx operator-(double s, cplx a) { return cplx{s - a.re, -a.im}; }
 HH_HD cplx conj(cplx a) { return cplx{a.re, -a.im}; }
 HH_HD double cabs2(cplx a) { return a.re * a.re + a.im * a.im; }
 HH_HD double cabs(cplx a) { return sqrt(a.re * a.re + a.im * a.im); }  // magnitudes here are far from over/underflow
-HH_HD_OUTLINE double carg(cplx a) { return atan2(a.im, a.re); }
 // 1 / x to ~1 ulp for normal-range x: on the device MUFU.RCP64H + two Newton steps instead of the IEEE division
 // sequence (the Bessel series and the complex divisions below are dependent chains of them)
 HH_HD double rcp_fast(double x) {
@@ -102,14 +101,191 @@ HH_HD cplx operator/(cplx a, double s) {
   const double is = rcp_fast(s);
   return cplx{a.re * is, a.im * is};
 }
-HH_HD_OUTLINE cplx cexp_(cplx a) {
-  const double e = exp(a.re);
+
+// ---- elementary functions of the hot path --------------------------------------------------------------------------------
+// ncu on the Broadie-Kaya kernel put 55-60 % of the executed instructions inside the CUDA math library's exp / sincos / log /
+// atan2 (~125 instructions per call, serial Horner chains, slow-path tests). The versions below read small shared-memory
+// tables (11 KB per block, filled by bk_fill_fast_tables) and finish with short polynomials: exp 10, sincos ~20, log ~11,
+// atan2 ~26 FP64 instructions, branch free on the fast path, |error| <= ~2e-16 (absolute for log / atan2 / sincos, relative
+// for exp). With a null table pointer (host build, tools) they are the library functions.
+struct alignas(16) BkFastTables {
+  double exp2t[256];  // 2^(j/256)
+  double logt[512];   // {r_j, -log r_j}, r_j = 1 / (1 + (j + 1/2) / 256) rounded to double
+  double trig[512];   // {cos, sin}(2 pi j / 256)
+  double atant[130];  // atan(j / 128), j = 0..128
+};
+constexpr unsigned kFtExp = 0, kFtLog = 2048, kFtTrig = 2048 + 4096, kFtAtan = 2048 + 4096 + 4096;  // byte offsets
+
+// Shared-window address of a block's tables (0: none — the host build, and callers without tables). The tables are read
+// with ld.shared through this address: a generic pointer handed to an out-of-line function compiles to LD.E (generic
+// loads, ~10 cycles more than LDS and on the global-memory path), which ncu showed as the first stall of the series loops.
+struct FastRef {
+  unsigned saddr;
+};
+
+#ifdef __CUDACC__
+__device__ __forceinline__ double lds_f64(unsigned saddr) {
+  double v;
+  asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(saddr));
+  return v;
+}
+__device__ __forceinline__ void lds_f64x2(unsigned saddr, double &a, double &b) {
+  asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(b) : "r"(saddr));
+}
+#endif
+
+#ifdef __CUDACC__
+// all threads of the block; the caller synchronises
+__device__ __forceinline__ void bk_fill_fast_tables(BkFastTables *t) {
+  for (int j = threadIdx.x; j < 256; j += blockDim.x) {
+    t->exp2t[j] = exp2((double)j * (1.0 / 256.0));
+    const double r = 1.0 / (1.0 + ((double)j + 0.5) * (1.0 / 256.0));
+    t->logt[2 * j] = r;
+    t->logt[2 * j + 1] = -log(r);
+    double sn, cs;
+    sincospi((double)j * (1.0 / 128.0), &sn, &cs);
+    t->trig[2 * j] = cs;
+    t->trig[2 * j + 1] = sn;
+  }
+  for (int j = threadIdx.x; j <= 128; j += blockDim.x) t->atant[j] = atan((double)j * (1.0 / 128.0));
+}
+#endif
+
+#ifdef __CUDA_ARCH__
+static __device__ __noinline__ double fexp_slow(double x) { return exp(x); }
+static __device__ __noinline__ void fsincos_slow(double x, double *s, double *c) { sincos(x, s, c); }
+#endif
+
+// exp(x): x = (256 k + j) ln2 / 256 + r, exp(x) = 2^k T_j exp(r), |r| <= ln2 / 512
+HH_HD double fexp(FastRef ft, double x) {
+#ifdef __CUDA_ARCH__
+  if (ft.saddr) {
+    if ((unsigned)(__double2hiint(x) & 0x7fffffff) >= 0x4085E000u) return fexp_slow(x);  // |x| >= 700, inf, nan
+    const double magic = 6755399441055744.0;                    // 1.5 2^52: the nearest integer lands in the low word
+    const double t = fma(x, 369.3299304675746, magic);          // 256 / ln 2
+    const int n = __double2loint(t);
+    const double nf = t - magic;
+    double r = fma(nf, -2.7076061740622863e-03, x);             // ln 2 / 256, high part
+    r = fma(nf, -9.058776616587108e-20, r);                     // low part  (hi + lo = ln2/256 to 1e-36)
+    const double e = lds_f64(ft.saddr + kFtExp + 8u * (unsigned)(n & 255));
+    double q = fma(r, 4.1666666666666664e-02, 1.6666666666666666e-01);
+    q = fma(q, r, 0.5);
+    q = fma(q, r, 1.0);
+    const double v = fma(e * r, q, e);
+    return __hiloint2double(__double2hiint(v) + ((n >> 8) << 20), __double2loint(v));
+  }
+#endif
+  (void)ft;
+  return exp(x);
+}
+
+// sin x, cos x: x = (256 k + j) 2 pi / 256 + r, |r| <= pi / 256; rotation of the tabulated (cos, sin) by r
+HH_HD void fsincos(FastRef ft, double x, double &sn, double &cs) {
+#ifdef __CUDA_ARCH__
+  if (ft.saddr) {
+    if ((unsigned)(__double2hiint(x) & 0x7fffffff) >= 0x41300000u) {  // |x| >= 2^20, inf, nan
+      fsincos_slow(x, &sn, &cs);
+      return;
+    }
+    const double magic = 6755399441055744.0;
+    const double t = fma(x, 40.74366543152521, magic);        // 256 / (2 pi)
+    const int n = __double2loint(t);
+    const double nf = t - magic;
+    double r = fma(nf, -2.454369260617026e-02, x);              // 2 pi / 256, high part
+    r = fma(nf, -9.567553118338697e-19, r);                     // low part
+    double2 cs0;
+    lds_f64x2(ft.saddr + kFtTrig + 16u * (unsigned)(n & 255), cs0.x, cs0.y);
+    const double r2 = r * r;
+    double ps = fma(r2, -1.9841269841269841e-04, 8.3333333333333332e-03);
+    ps = fma(ps, r2, -1.6666666666666666e-01);
+    const double ds = (r * r2) * ps;                            // sin r - r
+    double pc = fma(r2, -1.3888888888888889e-03, 4.1666666666666664e-02);
+    pc = fma(pc, r2, -0.5);
+    const double dc = r2 * pc;                                  // cos r - 1
+    const double sr = r + ds;
+    cs = cs0.x + fma(cs0.x, dc, -(cs0.y * sr));
+    sn = cs0.y + fma(cs0.y, dc, cs0.x * sr);
+    return;
+  }
+#endif
+  (void)ft;
+#if defined(__CUDA_ARCH__) || defined(__GNUC__)
+  sincos(x, &sn, &cs);
+#else
+  sn = sin(x);
+  cs = cos(x);
+#endif
+}
+
+// log x for normal x > 0: x = 2^e m, m r_j = 1 + s with |s| <= 2^-9: log x = e ln2 - log r_j + log1p(s)
+HH_HD double flog(FastRef ft, double x) {
+#ifdef __CUDA_ARCH__
+  if (ft.saddr) {
+    const int hi = __double2hiint(x);
+    if (hi >= 0x00100000 && hi < 0x7ff00000) {
+      const int e = (hi >> 20) - 1023, j = (hi >> 12) & 255;
+      const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(x));
+      double2 rl;
+      lds_f64x2(ft.saddr + kFtLog + 16u * (unsigned)j, rl.x, rl.y);
+      const double sft = fma(m, rl.x, -1.0);
+      double q = fma(sft, -1.6666666666666666e-01, 0.2);
+      q = fma(q, sft, -0.25);
+      q = fma(q, sft, 3.3333333333333331e-01);
+      q = fma(q, sft, -0.5);
+      const double s2 = sft * sft;
+      const double l1p = fma(s2, q, sft);
+      const double ef = (double)e;
+      return fma(ef, 6.9314718055994529e-01, rl.y + fma(ef, 2.3190468138462996e-17, l1p));
+    }
+  }
+#endif
+  (void)ft;
+  return log(x);
+}
+
+// atan2(y, x) in (-pi, pi]: t = min/max in [0, 1], c = nearest multiple of 1/128, atan t = atan c + atan((t - c)/(1 + t c))
+HH_HD double fatan2(FastRef ft, double y, double x) {
+#ifdef __CUDA_ARCH__
+  if (ft.saddr) {
+    const double ax = fabs(x), ay = fabs(y);
+    const double mx = fmax(ax, ay), mn = fmin(ax, ay);
+    const int hm = __double2hiint(mx);
+    if (hm >= 0x00200000 && hm < 0x7fd00000) {  // otherwise (0, tiny, huge, inf, nan): the library
+      double ir;
+      asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(ir) : "d"(mx));
+      const double magic = 6755399441055744.0;
+      const double tt = fma(mn * ir, 128.0, magic);
+      const int j = __double2loint(tt);
+      const double c = (tt - magic) * 0.0078125;
+      const double num = fma(-c, mx, mn), den = fma(c, mn, mx);
+      double yd;
+      asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(yd) : "d"(den));
+      double e = fma(-den, yd, 1.0);
+      yd = fma(yd, e, yd);
+      e = fma(-den, yd, 1.0);
+      yd = fma(yd, e, yd);
+      const double u = num * yd, u2 = u * u;
+      double q = fma(u2, -1.4285714285714285e-01, 0.2);
+      q = fma(q, u2, -3.3333333333333331e-01);
+      double a = lds_f64(ft.saddr + kFtAtan + 8u * (unsigned)j) + fma(u * u2, q, u);
+      if (ay > ax) a = 1.5707963267948966 - a;
+      if (x < 0.0) a = 3.1415926535897931 - a;
+      return copysign(a, y);
+    }
+  }
+#endif
+  (void)ft;
+  return atan2(y, x);
+}
+
+HH_HD cplx cexp_(FastRef ft, cplx a) {
+  const double e = fexp(ft, a.re);
   double s, c;
-  sincos(a.im, &s, &c);
+  fsincos(ft, a.im, s, c);
   return cplx{e * c, e * s};
 }
 // log|a| = log(re^2 + im^2) / 2: no hypot, no sqrt (the arguments here are far from the over/underflow of the squares)
-HH_HD cplx clog_(cplx a) { return cplx{0.5 * log(cabs2(a)), carg(a)}; }
+HH_HD cplx clog_(FastRef ft, cplx a) { return cplx{0.5 * flog(ft, cabs2(a)), fatan2(ft, a.im, a.re)}; }
 HH_HD cplx csqrt_(cplx a) {
   // principal branch, Re >= 0
   const double m = sqrt_fast(cabs2(a));
@@ -133,39 +309,107 @@ struct BesselEF {
 
 constexpr int kSeriesMaxTerms = 100, kHankelMaxTerms = 60;
 
-// sum_k (w^2/4)^k / (k! (nu+1)_k): the ascending series without its prefactor. `rk` (nullable) tabulates
-// 1 / (k (nu + k)); the convergence test runs on every second term (one extra term at most).
-HH_HD cplx bessel_series_sum(double nu, cplx w, const double *rk) {
+// Host-prepared constants of one order, plus the shared-window addresses of the block's coefficient tables (device).
+struct BesselOrder {
+  double nu;        // order, > -1
+  double lgam_nu1;  // lgamma(nu + 1)
+  double r_asym;    // |w| from which the Hankel expansion is used
+  // device: tables filled by bk_fill_order_tables in shared memory (the order is fixed per launch), 0 on the host
+  //   series: groups of four, R_{k,i} = prod_{m=k}^{k+i-1} 1 / (m (nu + m)), k = 1, 5, 9, ...
+  //   hankel: pairs {b_k, b_k b_{k+1}}, b_k = (4 nu^2 - (2k - 1)^2) / (8 k), k = 1, 3, 5, ...
+  unsigned series_saddr, hankel_saddr;
+  FastRef ft;       // tables of the elementary functions (saddr 0: the math library)
+  unsigned pad_;
+};
+HH_HD BesselOrder make_bessel_order(double nu) {
+  BesselOrder o;
+  o.nu = nu;
+  o.lgam_nu1 = lgamma(nu + 1.0);
+  o.r_asym = 20.0 + 0.5 * nu * nu;
+  o.series_saddr = 0;
+  o.hankel_saddr = 0;
+  o.ft.saddr = 0;
+  o.pad_ = 0;
+  return o;
+}
+
+// sum_k (w^2/4)^k / (k! (nu+1)_k): the ascending series without its prefactor.
+// Device: four terms per iteration from ONE previous term, t_{k+i-1} = t_{k-1} q^i R_{k,i} with q^2, q^3, q^4 formed once —
+// the dependent chain is one complex product per four terms instead of four, the scalings are folded into the FMAs of
+// the sum (33 instructions per four terms; the term-by-term loop with its reciprocals issued 46 per two). The
+// convergence test runs once per group (three extra terms at most).
+HH_HD cplx bessel_series_sum(const BesselOrder &o, cplx w) {
   const cplx q = 0.25 * (w * w);
   cplx term = mk(1.0), sum = mk(1.0);
+#ifdef __CUDA_ARCH__
+  const cplx q2 = q * q, q3 = q2 * q, q4 = q2 * q2;
+  unsigned addr = o.series_saddr;
 #pragma unroll 1
-  for (int k = 1; k + 1 < kSeriesMaxTerms; k += 2) {
-    const double r1 = rk ? rk[k] : rcp_fast((double)k * (nu + (double)k));
-    const double r2 = rk ? rk[k + 1] : rcp_fast((double)(k + 1) * (nu + (double)(k + 1)));
-    term = (term * q) * r1;
-    sum = sum + term;
-    term = (term * q) * r2;
-    sum = sum + term;
-    // |term| <= 1e-17 |sum| in the 1-norm (within sqrt 2 of the 2-norm test; two instructions fewer per pair of terms)
+  for (int g = 0; g < kSeriesMaxTerms / 4; ++g, addr += 32) {
+    double r1, r2, r3, r4;
+    lds_f64x2(addr, r1, r2);
+    lds_f64x2(addr + 16, r3, r4);
+    const cplx u1 = term * q, u2 = term * q2, u3 = term * q3, u4 = term * q4;
+    term = r4 * u4;
+    double sr = fma(r1, u1.re, sum.re), si = fma(r1, u1.im, sum.im);
+    double tr = fma(r2, u2.re, term.re), ti = fma(r2, u2.im, term.im);
+    sr = fma(r3, u3.re, sr);
+    si = fma(r3, u3.im, si);
+    sum = cplx{sr + tr, si + ti};
+    // |term| <= 1e-17 |sum| in the 1-norm (within sqrt 2 of the 2-norm test)
     if (fabs(term.re) + fabs(term.im) < 1e-17 * (fabs(sum.re) + fabs(sum.im))) break;
   }
+#else
+  const double nu = o.nu;
+  for (int k = 1; k + 1 < kSeriesMaxTerms; k += 2) {
+    term = (term * q) * (1.0 / ((double)k * (nu + (double)k)));
+    sum = sum + term;
+    term = (term * q) * (1.0 / ((double)(k + 1) * (nu + (double)(k + 1))));
+    sum = sum + term;
+    if (fabs(term.re) + fabs(term.im) < 1e-17 * (fabs(sum.re) + fabs(sum.im))) break;
+  }
+#endif
   return sum;
 }
 
 // Hankel sums s1 = sum (-1)^k a_k / w^k, s2 = sum a_k / w^k, a_k = prod (4 nu^2 - (2j-1)^2) / (8 j), stopped at the
-// smallest term. `bk` (nullable) tabulates (4 nu^2 - (2k-1)^2) / (8 k).
-HH_HD void bessel_hankel_sums(double nu, cplx w, const double *bk, cplx &s1, cplx &s2) {
-  const double mu4 = 4.0 * nu * nu;
+// smallest term. Device: two terms per iteration from one previous term (1/w^2 formed once), scalings folded into the
+// FMAs of the two sums: 24 instructions per pair (the term-by-term loop issued 45 per term).
+HH_HD void bessel_hankel_sums(const BesselOrder &o, cplx w, cplx &s1, cplx &s2) {
   const cplx iw = crecip(w);
   cplx t = mk(1.0);
   s1 = mk(1.0);
   s2 = mk(1.0);
   double last = 1.0;  // |t|^2 of the previous term
+#ifdef __CUDA_ARCH__
+  const cplx iw2 = iw * iw;
+  unsigned addr = o.hankel_saddr;
 #pragma unroll 1
+  for (int k = 1; k + 1 < kHankelMaxTerms; k += 2, addr += 16) {
+    double b1, bb;
+    lds_f64x2(addr, b1, bb);
+    const cplx u1 = t * iw, u2 = t * iw2;
+    const cplx t2 = bb * u2;  // a_{k+1} / w^{k+1}
+    const double m2 = cabs2(t2);
+    if (m2 > last) {  // the expansion has started to diverge inside this pair: keep a_k / w^k if it still decreases
+      const cplx t1 = b1 * u1;
+      if (cabs2(t1) <= last) {
+        s1 = s1 - t1;
+        s2 = s2 + t1;
+      }
+      break;
+    }
+    last = m2;
+    s2 = cplx{fma(b1, u1.re, s2.re + t2.re), fma(b1, u1.im, s2.im + t2.im)};
+    s1 = cplx{fma(-b1, u1.re, s1.re + t2.re), fma(-b1, u1.im, s1.im + t2.im)};
+    t = t2;
+    if (m2 < 1e-34) break;
+  }
+#else
+  const double mu4 = 4.0 * o.nu * o.nu;
   for (int k = 1; k < kHankelMaxTerms; ++k) {
     const double odd = (double)(2 * k - 1);
-    const double b = bk ? bk[k] : (mu4 - odd * odd) * rcp_fast(8.0 * (double)k);
-    t = (t * iw) * b;  // a_k / w^k
+    t = (t * iw) * ((mu4 - odd * odd) / (8.0 * (double)k));  // a_k / w^k
     const double m = cabs2(t);
     if (m > last) break;  // the expansion has started to diverge
     last = m;
@@ -173,38 +417,39 @@ HH_HD void bessel_hankel_sums(double nu, cplx w, const double *bk, cplx &s1, cpl
     s2 = s2 + t;
     if (m < 1e-34) break;
   }
+#endif
 }
 
-HH_HD BesselEF besseli_series_ef(double nu, double lgam_nu1, cplx w, double log_aw, double arg_w, const double *rk) {
-  const cplx sum = bessel_series_sum(nu, w, rk);
+HH_HD BesselEF besseli_series_ef(const BesselOrder &o, cplx w, double log_aw, double arg_w) {
+  const cplx sum = bessel_series_sum(o, w);
   // (w/2)^nu / Gamma(nu+1) * sum
-  return BesselEF{cplx{nu * (log_aw - 0.6931471805599453) - lgam_nu1, nu * arg_w}, sum};
+  return BesselEF{cplx{o.nu * (log_aw - 0.6931471805599453) - o.lgam_nu1, o.nu * arg_w}, sum};
 }
 
-HH_HD BesselEF besseli_asymptotic_ef(double nu, cplx w, double log_aw, double arg_w, const double *bk) {
+HH_HD BesselEF besseli_asymptotic_ef(const BesselOrder &o, cplx w, double log_aw, double arg_w) {
   cplx s1, s2;
-  bessel_hankel_sums(nu, w, bk, s1, s2);
+  bessel_hankel_sums(o, w, s1, s2);
   // I = e^w / sqrt(2 pi w) [ s1 + e^{-2w +- i pi (nu + 1/2)} s2 ],  + for Im w >= 0
   const double sgn = w.im >= 0.0 ? 1.0 : -1.0;
-  const cplx e2 = cexp_(cplx{-2.0 * w.re, -2.0 * w.im + sgn * kBesselPi * (nu + 0.5)});
+  const cplx e2 = cexp_(o.ft, cplx{-2.0 * w.re, -2.0 * w.im + sgn * kBesselPi * (o.nu + 0.5)});
   return BesselEF{cplx{w.re - 0.5 * (1.8378770664093453 + log_aw), w.im - 0.5 * arg_w}, s1 + e2 * s2};  // log(2 pi)
 }
 
 // ---- ascending series: |w| - Re w <= 5, |w| <~ 25 ---------------------------------------------------------------
-HH_HD cplx log_besseli_series(double nu, double lgam_nu1, cplx w, const double *rk) {
-  const cplx sum = bessel_series_sum(nu, w, rk);
+HH_HD cplx log_besseli_series(const BesselOrder &o, cplx w) {
+  const cplx sum = bessel_series_sum(o, w);
   // (w/2)^nu / Gamma(nu+1) * sum
-  return nu * clog_(0.5 * w) - lgam_nu1 + clog_(sum);
+  return o.nu * clog_(o.ft, 0.5 * w) - o.lgam_nu1 + clog_(o.ft, sum);
 }
 
 // ---- Hankel expansion: |w| large, Re w >= 0 -----------------------------------------------------------------
-HH_HD cplx log_besseli_asymptotic(double nu, cplx w, const double *bk) {
+HH_HD cplx log_besseli_asymptotic(const BesselOrder &o, cplx w) {
   cplx s1, s2;
-  bessel_hankel_sums(nu, w, bk, s1, s2);
+  bessel_hankel_sums(o, w, s1, s2);
   // I = e^w / sqrt(2 pi w) [ s1 + e^{-2w +- i pi (nu + 1/2)} s2 ],  + for Im w >= 0
   const double sgn = w.im >= 0.0 ? 1.0 : -1.0;
-  const cplx e2 = cexp_(cplx{-2.0 * w.re, -2.0 * w.im + sgn * kBesselPi * (nu + 0.5)});
-  return w - 0.5 * clog_((2.0 * kBesselPi) * w) + clog_(s1 + e2 * s2);
+  const cplx e2 = cexp_(o.ft, cplx{-2.0 * w.re, -2.0 * w.im + sgn * kBesselPi * (o.nu + 0.5)});
+  return w - 0.5 * clog_(o.ft, (2.0 * kBesselPi) * w) + clog_(o.ft, s1 + e2 * s2);
 }
 
 // ---- continued fractions + Wronskian: 2 <= |w|, Re w >= 0, order xnu >= 0 ------------------------------------------
@@ -276,27 +521,7 @@ HH_HD_OUTLINE cplx log_besseli_cf(double xnu, cplx x, cplx *ratio_deriv) {
   const cplx rimu_scaled = xi / (f * rkmu - rkmup);                // I_mu e^{-x}
   if (ratio_deriv) *ratio_deriv = h;
   // I_xnu = I_mu * ril1 / ril
-  return x + clog_(rimu_scaled) + clog_(ril1 / ril);
-}
-
-// Host-prepared constants of one order.
-struct BesselOrder {
-  double nu;        // order, > -1
-  double lgam_nu1;  // lgamma(nu + 1)
-  double r_asym;    // |w| from which the Hankel expansion is used
-  // optional coefficient tables (the order is fixed per launch; the Broadie-Kaya kernel fills them in shared memory):
-  // series_rk[k] = 1 / (k (nu + k)), hankel_bk[k] = (4 nu^2 - (2k - 1)^2) / (8 k). NULL: computed on the fly.
-  const double *series_rk;
-  const double *hankel_bk;
-};
-inline BesselOrder make_bessel_order(double nu) {
-  BesselOrder o;
-  o.nu = nu;
-  o.lgam_nu1 = lgamma(nu + 1.0);
-  o.r_asym = 20.0 + 0.5 * nu * nu;
-  o.series_rk = nullptr;
-  o.hankel_bk = nullptr;
-  return o;
+  return x + clog_(FastRef{0}, rimu_scaled) + clog_(FastRef{0}, ril1 / ril);
 }
 
 // log I_nu(z), any complex z != 0. The imaginary part is a valid argument of I_nu(z) (branch unspecified).
@@ -311,16 +536,16 @@ HH_HD_OUTLINE cplx log_besseli(const BesselOrder &o, cplx z) {
   const double aw = cabs(w);
   cplx r;
   if (aw <= 5.0 || (aw < o.r_asym && aw - w.re <= 5.0)) {
-    r = log_besseli_series(nu, o.lgam_nu1, w, o.series_rk);
+    r = log_besseli_series(o, w);
   } else if (aw >= o.r_asym) {
-    r = log_besseli_asymptotic(nu, w, o.hankel_bk);
+    r = log_besseli_asymptotic(o, w);
   } else if (nu >= 0.0) {
     r = log_besseli_cf(nu, w, nullptr);
   } else {
     // I_nu = I'_(nu+1) + ((nu+1)/w) I_(nu+1)
     cplx dl;
     const cplx l1 = log_besseli_cf(nu + 1.0, w, &dl);
-    r = l1 + clog_(dl + (nu + 1.0) / w);
+    r = l1 + clog_(o.ft, dl + (nu + 1.0) / w);
   }
   r.im += rot;
   return r;
@@ -341,9 +566,9 @@ HH_HD BesselEF besseli_ef(const BesselOrder &o, cplx z, double log_az, double ar
   const double aw2 = cabs2(w), ra2 = o.r_asym * o.r_asym, edge = 5.0 + w.re;
   BesselEF r;
   if (aw2 <= 25.0 || (aw2 < ra2 && aw2 <= edge * edge)) {
-    r = besseli_series_ef(nu, o.lgam_nu1, w, log_az, arg_w, o.series_rk);
+    r = besseli_series_ef(o, w, log_az, arg_w);
   } else if (aw2 >= ra2) {
-    r = besseli_asymptotic_ef(nu, w, log_az, arg_w, o.hankel_bk);
+    r = besseli_asymptotic_ef(o, w, log_az, arg_w);
   } else {
     r.E = log_besseli(o, w);  // continued fractions (rare: strongly rotated arguments of moderate size)
     r.F = mk(1.0);
@@ -385,14 +610,15 @@ HH_HD BkCf bk_cf_init(const BkParams &p, double V0, double VT) {
 // Phi(a) with the unwrapped angle of z_gamma carried in theta_prev (NaN = first evaluation), heston.jl:184-212.
 HH_HD_OUTLINE cplx bk_chf(const BkParams &p, const BkCf &it, double a, double &theta_prev) {
   const cplx g = csqrt_(cplx{p.kappa * p.kappa, -2.0 * p.xi2 * a});        // gamma            :190
-  const cplx egh = cexp_((-0.5 * p.tau) * g);  // e^{-g tau / 2}
+  const FastRef ft = p.ord.ft;
+  const cplx egh = cexp_(ft, (-0.5 * p.tau) * g);  // e^{-g tau / 2}
   const cplx eg = egh * egh;
   const cplx omeg = 1.0 - eg;
   // one complex reciprocal serves the three quotients of :191-193 (1 / zeta_g = g / (1 - e^{-g tau}))
   const cplx g_io = g * crecip(omeg);
   const cplx eta_g = g_io * (1.0 + eg);                                       // :192
   const cplx zg = it.sv4_xi2 * (g_io * egh);                                  // nu_gamma         :193
-  const double th = carg(zg);                                                 // :198
+  const double th = fatan2(ft, zg.im, zg.re);                                 // :198
   double thu = th;
   if (!(theta_prev != theta_prev)) {                                          // :199-205
     double dlt = th - theta_prev;
@@ -401,11 +627,11 @@ HH_HD_OUTLINE cplx bk_chf(const BkParams &p, const BkCf &it, double a, double &t
   }
   theta_prev = thu;
   // I_nu(z_gamma) = exp(E) F with log|z_gamma| and the angle already in hand                       :206-207
-  BesselEF ig = besseli_ef(p.ord, zg, 0.5 * log(cabs2(zg)), th);
+  BesselEF ig = besseli_ef(p.ord, zg, 0.5 * flog(ft, cabs2(zg)), th);
   ig.E.im += p.ord.nu * (thu - th);
   // phi = exp(-(g - k) tau / 2) (zeta_k / zeta_g) exp((V0+VT)/s^2 (eta_k - eta_g)) exp(logIg - logIk)   :195-211
   const cplx ex = (-0.5 * p.tau) * (g - p.kappa) + it.vsum_s * (p.eta_k - eta_g) + (ig.E - it.logIk);
-  return ((p.zeta_k * g_io) * ig.F) * cexp_(ex);  // zeta_k / zeta_g (:191)
+  return ((p.zeta_k * g_io) * ig.F) * cexp_(ft, ex);  // zeta_k / zeta_g (:191)
 }
 
 }  // namespace hh

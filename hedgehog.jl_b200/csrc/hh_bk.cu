@@ -119,17 +119,19 @@ struct BkInversion {
   int J, status, iters;  // status: 0 Newton inside the bracket, 1 unbracketed secant accepted, 2 fell back to max_guess
 };
 
-// Coefficient table: the first `cap` entries in shared memory (stride = blockDim.x doubles), the rest in a global slab.
+// Coefficient table: the first `cap` entries in shared memory (stride = blockDim.x doubles; read and written through the
+// shared window, see FastRef), the rest in a global slab.
 struct BkTable {
-  double *sh;
+  unsigned sh_saddr;  // shared-window address of this thread's first entry
+  unsigned sh_stride_bytes;
   double *slab;
   int64_t slab_stride;
-  int cap, sh_stride;
+  int cap;
   __device__ __forceinline__ double get(int j) const {
-    return j < cap ? sh[j * sh_stride] : slab[(int64_t)(j - cap) * slab_stride];
+    return j < cap ? lds_f64(sh_saddr + (unsigned)j * sh_stride_bytes) : slab[(int64_t)(j - cap) * slab_stride];
   }
   __device__ __forceinline__ void set(int j, double v) const {
-    if (j < cap) sh[j * sh_stride] = v;
+    if (j < cap) asm volatile("st.shared.f64 [%0], %1;" ::"r"(sh_saddr + (unsigned)j * sh_stride_bytes), "d"(v) : "memory");
     else slab[(int64_t)(j - cap) * slab_stride] = v;
   }
 };
@@ -246,131 +248,48 @@ __device__ BkInversion bk_sample_integral(const BkParams &p, double V0, double V
   return r;
 }
 
-// series_rk[k] = 1 / (k (nu + k)), hankel_bk[k] = (4 nu^2 - (2k-1)^2) / (8 k), by all threads of the block (IEEE division: once)
-__device__ __forceinline__ void bk_fill_order_tables(double nu, double *rk, double *bk) {
-  for (int k = threadIdx.x; k < kSeriesMaxTerms; k += blockDim.x) rk[k] = k ? 1.0 / ((double)k * (nu + (double)k)) : 0.0;
-  for (int k = threadIdx.x; k < kHankelMaxTerms; k += blockDim.x) {
-    const double odd = (double)(2 * k - 1);
-    bk[k] = k ? (4.0 * nu * nu - odd * odd) / (8.0 * (double)k) : 0.0;
+// Coefficient tables of the fixed order nu, by all threads of the block (IEEE divisions: once per block).
+//   rk4: groups of four, R_{k,i} = prod_{m=k}^{k+i-1} 1 / (m (nu + m)), k = 1, 5, 9, ...   (bessel_series_sum)
+//   bk2: pairs {b_k, b_k b_{k+1}}, b_k = (4 nu^2 - (2k - 1)^2) / (8 k), k = 1, 3, 5, ...   (bessel_hankel_sums)
+__device__ __forceinline__ void bk_fill_order_tables(double nu, double *rk4, double *bk2) {
+  for (int g = threadIdx.x; g < kSeriesMaxTerms / 4; g += blockDim.x) {
+    double r = 1.0;
+    for (int i = 0; i < 4; ++i) {
+      const double k = (double)(4 * g + 1 + i);
+      r *= 1.0 / (k * (nu + k));
+      rk4[4 * g + i] = r;
+    }
+  }
+  for (int g = threadIdx.x; g < kHankelMaxTerms / 2; g += blockDim.x) {
+    const double k1 = (double)(2 * g + 1), k2 = (double)(2 * g + 2);
+    const double o1 = 2.0 * k1 - 1.0, o2 = 2.0 * k2 - 1.0;
+    const double b1 = (4.0 * nu * nu - o1 * o1) / (8.0 * k1), b2 = (4.0 * nu * nu - o2 * o2) / (8.0 * k2);
+    bk2[2 * g] = b1;
+    bk2[2 * g + 1] = b1 * b2;
   }
 }
 
-#ifdef HH_TUNING  // the one-thread-per-trajectory kernel of round 1 (49 % idle lanes): kept for reference, not built
-struct BkArgs {
-  int64_t n, path_offset;
-  uint64_t base_seed;
-  const uint64_t *seeds;
-  int n_dates;
+// Per-block copy of the parameters (the outlined functions take them by reference: a reference to the kernel arguments
+// would be copied to every thread's local memory) with the coefficient tables of the fixed order nu and the tables of the
+// elementary functions. Every kernel that evaluates the characteristic function — the product kernel and the parity
+// probes alike — goes through this, so the probes exercise the arithmetic the product runs.
+struct alignas(16) BkShared {
+  BkFastTables ft;
+  double rk4[kSeriesMaxTerms], bk2[kHankelMaxTerms];
   BkParams p;
-  double x0, v0, s0;
-  double *terminal;  // S_T per trajectory
-  double *vterm;     // nullable: V_T per trajectory
-  double *grid;      // nullable: spots at dates 0..n_dates, date-major with `grid_stride` columns per date (LSM)
-  int64_t grid_stride;
-  double *stats;     // nullable: HH_PD_NSTATS x n path statistics over the monitoring dates (hh_mc_path_dependent)
-  int monitor_every; // every k-th date is a monitoring date
-  double inv_m;      // 1 / number of monitoring dates
-  double *slab;
-  int64_t slab_stride;
-  unsigned long long *counters;  // [0] fallbacks, [1] sum J, [2] sum root-finder evaluations, [3] transitions, [4] unbracketed accepted
 };
-
-// MINB = resident blocks per SM the register allocation is bounded for (3: 168 registers; 6: 85). The kernel is
-// latency-bound (issue slots 30 % busy at 12 warps per SM, ncu), so the bound is chosen by measurement: HH_BK_MINB.
-template <int MINB>
-__global__ void __launch_bounds__(kBkThreads, MINB) bk_paths_kernel(const BkArgs a) {
-  extern __shared__ double s_tab[];
-  BkTable tb;
-  tb.sh = s_tab + threadIdx.x;
-  tb.sh_stride = kBkThreads;
-  tb.cap = kBkTable;
-  tb.slab = a.slab + ((int64_t)blockIdx.x * kBkThreads + threadIdx.x);
-  tb.slab_stride = a.slab_stride;
-  // The parameters live in shared memory (the outlined functions take them by reference: a reference to the kernel
-  // arguments would be copied to every thread's local memory), next to the coefficient tables of the fixed order nu.
-  __shared__ BkParams s_p;
-  __shared__ double s_rk[kSeriesMaxTerms], s_bk[kHankelMaxTerms];
-  bk_fill_order_tables(a.p.ord.nu, s_rk, s_bk);
+__device__ __forceinline__ const BkParams &bk_block_setup(const BkParams &src, BkShared &sh) {
+  bk_fill_order_tables(src.ord.nu, sh.rk4, sh.bk2);
+  bk_fill_fast_tables(&sh.ft);
   if (threadIdx.x == 0) {
-    s_p = a.p;
-    s_p.ord.series_rk = s_rk;
-    s_p.ord.hankel_bk = s_bk;
+    sh.p = src;
+    sh.p.ord.series_saddr = (unsigned)__cvta_generic_to_shared(sh.rk4);
+    sh.p.ord.hankel_saddr = (unsigned)__cvta_generic_to_shared(sh.bk2);
+    sh.p.ord.ft.saddr = (unsigned)__cvta_generic_to_shared(&sh.ft);
   }
   __syncthreads();
-  const BkParams &p = s_p;
-  unsigned long long nfall = 0, sumJ = 0, sumIt = 0, ntr = 0, nsec = 0;
-  for (int64_t i = (int64_t)blockIdx.x * kBkThreads + threadIdx.x; i < a.n; i += (int64_t)gridDim.x * kBkThreads) {
-    BkRng rng;
-    uint64_t key = a.base_seed, idx = (uint64_t)(a.path_offset + i);
-    if (a.seeds) {
-      key = a.seeds[i];
-      idx = 0;
-    }
-    rng.c0 = (uint32_t)idx;
-    rng.c1 = (uint32_t)(idx >> 32);
-    rng.k0 = (uint32_t)key;
-    rng.k1 = (uint32_t)(key >> 32);
-    double x = a.x0, v = a.v0;
-    if (a.grid) a.grid[i] = a.s0;
-    double sum_s = 0.0, sum_x = 0.0, max_x = -INFINITY, min_x = INFINITY;  // running statistics (a.stats only)
-    int due = a.monitor_every;
-    for (int n = 0; n < a.n_dates; ++n) {
-      rng.c2 = (uint32_t)n;
-      rng.draw = 0;
-      // 1. V' (sample_V_T)
-      const double vt = fmax(p.c_scale * bk_ncx2(rng, p.dof, p.lam_scale * v), 1e-300);
-      // 2.-4. int V (sample_integral_V)
-      double u, z, dummy;
-      rng.uniforms(u, dummy);
-      const BkInversion inv = bk_sample_integral(p, fmax(v, 1e-300), vt, u, tb);
-      // 5. log S' (sample_log_S_T)
-      rng.normals(z, dummy);
-      const double mu = x + p.r_tau - 0.5 * inv.x + p.rho_over_xi * (vt - v - p.kappa_theta_tau + p.kappa * inv.x);
-      x = mu + sqrt(p.one_m_rho2 * inv.x) * z;
-      v = vt;
-      nfall += inv.status == 2;
-      nsec += inv.status == 1;
-      sumJ += (unsigned)inv.J;
-      sumIt += (unsigned)inv.iters;
-      ++ntr;
-      if (a.grid) a.grid[(int64_t)(n + 1) * a.grid_stride + i] = exp(x);
-      if (a.stats && --due == 0) {  // a monitoring date: the transition is exact, so the statistics carry no time-stepping bias
-        due = a.monitor_every;
-        sum_x += x;
-        max_x = fmax(max_x, x);
-        min_x = fmin(min_x, x);
-        sum_s += exp(x);
-      }
-    }
-    a.terminal[i] = exp(x);
-    if (a.vterm) a.vterm[i] = v;
-    if (a.stats) {  // S_T, A, G, max S, min S
-      a.stats[i] = exp(x);
-      a.stats[a.n + i] = sum_s * a.inv_m;
-      a.stats[2 * a.n + i] = exp(sum_x * a.inv_m);
-      a.stats[3 * a.n + i] = exp(max_x);
-      a.stats[4 * a.n + i] = exp(min_x);
-    }
-  }
-  // warp-aggregate the statistics
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    nfall += __shfl_down_sync(0xffffffffu, nfall, o);
-    sumJ += __shfl_down_sync(0xffffffffu, sumJ, o);
-    sumIt += __shfl_down_sync(0xffffffffu, sumIt, o);
-    ntr += __shfl_down_sync(0xffffffffu, ntr, o);
-    nsec += __shfl_down_sync(0xffffffffu, nsec, o);
-  }
-  if ((threadIdx.x & 31) == 0) {
-    atomicAdd(&a.counters[0], nfall);
-    atomicAdd(&a.counters[1], sumJ);
-    atomicAdd(&a.counters[2], sumIt);
-    atomicAdd(&a.counters[3], ntr);
-    atomicAdd(&a.counters[4], nsec);
-  }
+  return sh.p;
 }
-
-#endif  // HH_TUNING
 
 // ---- the transition-sorted pipeline (what hh_mc_european / hh_lsm_american / hh_mc_path_dependent launch) --------------
 // The variance chain V_0 -> V_1 -> ... does not depend on the integrals or on the spot, so all n_paths x n_dates
@@ -504,21 +423,13 @@ template <int MINB>
 __global__ void __launch_bounds__(kBkThreads, MINB) bk_integral_sorted_kernel(const BkIntArgs a) {
   extern __shared__ double s_tab[];
   BkTable tb;
-  tb.sh = s_tab + threadIdx.x;
-  tb.sh_stride = kBkThreads;
+  tb.sh_saddr = (unsigned)__cvta_generic_to_shared(s_tab + threadIdx.x);
+  tb.sh_stride_bytes = kBkThreads * (unsigned)sizeof(double);
   tb.cap = kBkTable;
   tb.slab = a.slab + ((int64_t)blockIdx.x * kBkThreads + threadIdx.x);
   tb.slab_stride = a.slab_stride;
-  __shared__ BkParams s_p;
-  __shared__ double s_rk[kSeriesMaxTerms], s_bk[kHankelMaxTerms];
-  bk_fill_order_tables(a.p.ord.nu, s_rk, s_bk);
-  if (threadIdx.x == 0) {
-    s_p = a.p;
-    s_p.ord.series_rk = s_rk;
-    s_p.ord.hankel_bk = s_bk;
-  }
-  __syncthreads();
-  const BkParams &p = s_p;
+  __shared__ BkShared s_sh;
+  const BkParams &p = bk_block_setup(a.p, s_sh);
   unsigned long long nfall = 0, sumJ = 0, sumIt = 0, ntr = 0, nsec = 0;
   for (int64_t k = (int64_t)blockIdx.x * kBkThreads + threadIdx.x; k < a.items; k += (int64_t)gridDim.x * kBkThreads) {
     const int64_t t = a.perm[k];
@@ -596,8 +507,10 @@ __global__ void __launch_bounds__(256) bk_assemble_kernel(const BkAsmArgs a) {
 }
 
 // ---- probes (parity of the deterministic pieces) ---------------------------------------------------------------------
-__global__ void bk_chf_kernel(const BkParams p, const double *V0, const double *VT, int n, const double *a, int na,
+__global__ void bk_chf_kernel(const BkParams p_in, const double *V0, const double *VT, int n, const double *a, int na,
                               double *ore, double *oim) {
+  __shared__ BkShared s_sh;
+  const BkParams &p = bk_block_setup(p_in, s_sh);
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const BkCf it = bk_cf_init(p, V0[i], VT[i]);
@@ -609,7 +522,11 @@ __global__ void bk_chf_kernel(const BkParams p, const double *V0, const double *
   }
 }
 
-__global__ void bk_log_besseli_kernel(const BesselOrder o, const double *zr, const double *zi, int n, double *ore, double *oim) {
+__global__ void bk_log_besseli_kernel(const BesselOrder o_in, const double *zr, const double *zi, int n, double *ore, double *oim) {
+  __shared__ BkShared s_sh;
+  BkParams pin;
+  pin.ord = o_in;
+  const BesselOrder &o = bk_block_setup(pin, s_sh).ord;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const cplx r = log_besseli(o, cplx{zr[i], zi[i]});
@@ -617,17 +534,32 @@ __global__ void bk_log_besseli_kernel(const BesselOrder o, const double *zr, con
   oim[i] = r.im;
 }
 
+__global__ void bk_elementary_kernel(int kind, const double *x, const double *y, int n, double *oa, double *ob) {
+  __shared__ BkShared s_sh;
+  BkParams pin;
+  pin.ord = make_bessel_order(0.0);
+  const FastRef ft = bk_block_setup(pin, s_sh).ord.ft;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (kind == 0) oa[i] = fexp(ft, x[i]);
+  else if (kind == 1) fsincos(ft, x[i], oa[i], ob[i]);
+  else if (kind == 2) oa[i] = flog(ft, x[i]);
+  else oa[i] = fatan2(ft, y[i], x[i]);
+}
+
 // out[i] = {x, mean, var, h, J, status, resid, iters}
-__global__ void __launch_bounds__(kBkThreads) bk_integral_kernel(const BkParams p, const double *V0, const double *VT,
+__global__ void __launch_bounds__(kBkThreads) bk_integral_kernel(const BkParams p_in, const double *V0, const double *VT,
                                                                  const double *U, int n, double *out, double *slab,
                                                                  int64_t slab_stride) {
   extern __shared__ double s_tab[];
   BkTable tb;
-  tb.sh = s_tab + threadIdx.x;
-  tb.sh_stride = kBkThreads;
+  tb.sh_saddr = (unsigned)__cvta_generic_to_shared(s_tab + threadIdx.x);
+  tb.sh_stride_bytes = kBkThreads * (unsigned)sizeof(double);
   tb.cap = kBkTable;
   tb.slab = slab + ((int64_t)blockIdx.x * kBkThreads + threadIdx.x);
   tb.slab_stride = slab_stride;
+  __shared__ BkShared s_sh;
+  const BkParams &p = bk_block_setup(p_in, s_sh);
   const int i = blockIdx.x * kBkThreads + threadIdx.x;
   if (i >= n) return;
   const BkInversion r = bk_sample_integral(p, V0[i], VT[i], U[i], tb);
@@ -914,6 +846,24 @@ int bk_integral(hh_ctx *ctx, const hh_model *m, double tau, const hh_bk_config *
   bk_integral_kernel<<<nblocks, kBkThreads, smem, st>>>(p, dV0, dVT, dU, n, dout, slab, stride);
   HH_CUDA(ctx, cudaGetLastError());
   HH_CUDA(ctx, cudaMemcpyAsync(out8, dout, 8 * nv, cudaMemcpyDeviceToHost, st));
+  HH_CUDA(ctx, cudaStreamSynchronize(st));
+  return HH_OK;
+}
+
+int bk_elementary(hh_ctx *ctx, int kind, const double *x, const double *y, int n, double *out_a, double *out_b) {
+  if (!x || !out_a || n < 1 || kind < 0 || kind > 3 || (kind == 3 && !y) || (kind == 1 && !out_b))
+    return ctx->fail(HH_ERR_ARG, "hh_bk_elementary: bad argument");
+  HH_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const size_t nv = sizeof(double) * (size_t)n;
+  HH_CUDA(ctx, ctx->d_misc.ensure(4 * nv));
+  double *dx = ctx->d_misc.as<double>(), *dy = dx + n, *da = dy + n, *db = da + n;
+  HH_CUDA(ctx, cudaMemcpyAsync(dx, x, nv, cudaMemcpyHostToDevice, st));
+  if (y) HH_CUDA(ctx, cudaMemcpyAsync(dy, y, nv, cudaMemcpyHostToDevice, st));
+  bk_elementary_kernel<<<(n + 127) / 128, 128, 0, st>>>(kind, dx, dy, n, da, db);
+  HH_CUDA(ctx, cudaGetLastError());
+  HH_CUDA(ctx, cudaMemcpyAsync(out_a, da, nv, cudaMemcpyDeviceToHost, st));
+  if (out_b) HH_CUDA(ctx, cudaMemcpyAsync(out_b, db, nv, cudaMemcpyDeviceToHost, st));
   HH_CUDA(ctx, cudaStreamSynchronize(st));
   return HH_OK;
 }

@@ -269,6 +269,15 @@ class CudaEngine:
                     "hh_bk_log_besseli")
         return re + 1j * im
 
+    def bk_elementary(self, kind: str, x, y=None):
+        """The table-driven exp / sincos / log / atan2 of the Broadie-Kaya kernels (accuracy probes)."""
+        k = {"exp": 0, "sincos": 1, "log": 2, "atan2": 3}[kind]
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        yy = np.ascontiguousarray(y, dtype=np.float64) if y is not None else None
+        a = np.empty(x.shape[0]); b = np.empty(x.shape[0])
+        self._check(self.lib.hh_bk_elementary(self.h, k, _dp(x), _dp(yy) if yy is not None else None, x.shape[0], _dp(a), _dp(b)),
+                    "hh_bk_elementary")
+        return (a, b) if k == 1 else a
 
     def bk_integral(self, model, tau: float, V0, VT, U, cfg: Optional[abi.hh_bk_config] = None):
         """sample_from_cf for given (V0, VT, u) triples -> dict of arrays (x, mean, var, h, J, status, resid, evals)."""

@@ -312,6 +312,10 @@ int hh_bk_chf(hh_ctx *ctx, const hh_model *model, double tau, const double *V0, 
 /* log I_nu(z) for complex z, real order nu > -1 (SpecialFunctions.besseli, heston.jl:173,207). */
 int hh_bk_log_besseli(hh_ctx *ctx, double nu, const double *z_re, const double *z_im, int n,
                       double *out_re, double *out_im);
+/* The table-driven elementary functions of the Broadie-Kaya kernels (csrc/hh_bessel.cuh), for accuracy tests:
+ * kind 0: out_a = exp(x); 1: out_a = sin(x), out_b = cos(x); 2: out_a = log(x); 3: out_a = atan2(y, x). y and out_b
+ * may be NULL for the kinds that do not use them. */
+int hh_bk_elementary(hh_ctx *ctx, int kind, const double *x, const double *y, int n, double *out_a, double *out_b);
 /* sample_from_cf (sample_from_cf.jl:27-41) for n independent (V0, VT, u) triples, u = the uniform the reference draws
  * at :29. out8[i] = {x = sampled integral of V, mean, variance (moments_from_cf :50-64), h (:37), J = number of series
  * terms (:84-93), status (0 root inside [0, max_guess], 1 secant accepted without a bracket, 2 fell back to max_guess),

@@ -27,6 +27,29 @@ Q8 = dict(kappa=0.04, theta=0.3, xi=-0.6, rho=0.04, V0=1.5, r=0.05)       # mont
 BK1 = dict(kappa=6.21, theta=0.019, xi=0.61, rho=-0.7, V0=0.010201, r=0.0319)  # Broadie-Kaya (2006) case 1
 
 
+def test_elementary_functions_against_libm(cuda):
+    """The table-driven exp / sincos / log / atan2 of csrc/hh_bessel.cuh (they replace the CUDA math library in the
+    characteristic function) against numpy in binary64: a few ulp, over the ranges the kernels use and past them."""
+    rng = np.random.default_rng(11)
+    x = np.concatenate([rng.uniform(-690, 690, 20000), rng.uniform(-2, 2, 20000), [0.0, -0.0, 1e-300, 709.0, -745.0, 800.0, -800.0]])
+    got = cuda.bk_elementary("exp", x)
+    ref = np.exp(x)
+    ok = (ref > 1e-300) & np.isfinite(ref)
+    assert np.max(np.abs(got[ok] / ref[ok] - 1.0)) < 4e-16
+    assert got[-2] == np.inf and got[-1] == 0.0 and np.all(got[ref <= 1e-300] <= 1.1e-300)
+    x = np.concatenate([rng.uniform(-1e3, 1e3, 30000), rng.uniform(-7, 7, 20000), rng.uniform(-1e6, 1e6, 5000), [0.0, 1e7, -3e9]])
+    s, c = cuda.bk_elementary("sincos", x)
+    assert np.max(np.abs(s - np.sin(x))) < 3e-16 and np.max(np.abs(c - np.cos(x))) < 3e-16
+    x = np.concatenate([np.exp(rng.uniform(-600, 600, 30000)), rng.uniform(0.5, 2.0, 20000), [1.0, 2.0, 0.5, 1e-310]])
+    got = cuda.bk_elementary("log", x)
+    ref = np.log(x)
+    assert np.max(np.abs(got - ref) / np.maximum(1.0, np.abs(ref))) < 3e-16
+    y = np.concatenate([rng.normal(size=30000) * np.exp(rng.uniform(-20, 20, 30000)), [0.0, 0.0, 1.0, -1.0, 0.0, -0.0, 1e-320]])
+    xx = np.concatenate([rng.normal(size=30000) * np.exp(rng.uniform(-20, 20, 30000)), [1.0, -1.0, 0.0, 0.0, 0.0, -1.0, 1.0]])
+    got = cuda.bk_elementary("atan2", xx, y)
+    assert np.max(np.abs(got - np.arctan2(y, xx))) < 5e-16
+
+
 @pytest.mark.parametrize("nu", [-0.933, -0.5, -0.366, 0.0, 0.778, 2.5, 12.0])
 def test_log_besseli_matches_amos(cuda, nu):
     rng = np.random.default_rng(3)
