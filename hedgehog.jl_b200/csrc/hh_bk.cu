@@ -668,7 +668,9 @@ static int bk_paths_launch(hh_ctx *ctx, const hh_model *m, const hh_sim *s, doub
   HH_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kBkThreads, smem));
   if (occ < 1) occ = 1;
   // chunks of trajectories: at most 2^27 transitions each
-  const int64_t max_items = (int64_t)1 << 27;
+  // (HH_BK_MAX_ITEMS: test hook that forces small chunks)
+  static const int64_t max_items_env = getenv("HH_BK_MAX_ITEMS") ? atoll(getenv("HH_BK_MAX_ITEMS")) : 0;
+  const int64_t max_items = max_items_env > 0 ? max_items_env : (int64_t)1 << 27;
   int64_t chunk = max_items / ndates;
   if (chunk < 1) chunk = 1;
   if (chunk > N) chunk = N;

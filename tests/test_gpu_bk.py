@@ -186,3 +186,32 @@ def test_bk_errors_and_shards(cuda):
                                 [(100.0, 1.0)], 1.0, want_terminal=True)
         parts.append(t)
     assert np.array_equal(np.concatenate(parts), full)
+
+
+def test_bk_chunked_launch_is_bit_identical(cuda):
+    """Jobs above 2^27 transitions are cut into chunks of trajectories (hh_bk.cu: bk_paths_launch). HH_BK_MAX_ITEMS forces
+    small chunks in a second process; the terminal spots, the payoff sums and the inversion counters must not move."""
+    import json
+    import os
+    import subprocess
+    import sys
+    code = (
+        "import sys, json, hashlib, numpy as np; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "import hedgehog_jl_b200 as hh\n"
+        "from hedgehog_jl_b200 import _abi as abi\n"
+        "from hedgehog_jl_b200.engine import SimSpec\n"
+        "from helpers import heston_model\n"
+        "eng = hh.default_engine(0)\n"
+        "sim = SimSpec(n_paths=5000, n_steps=3, scheme=abi.HH_SCHEME_HESTON_BK, base_seed=9)\n"
+        "r, t = eng.mc_european(heston_model(), sim, [(100.0, 1.0), (90.0, -1.0)], 1.0, want_terminal=True)\n"
+        "print(json.dumps({'sha': hashlib.sha256(np.ascontiguousarray(t).tobytes()).hexdigest(), 'sum': [x.sum for x in r],\n"
+        "                  'stats': eng.bk_last_stats()}))\n"
+    ) % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for extra in ({}, {"HH_BK_MAX_ITEMS": "3500"}):   # 3500 // 3 = 1166 trajectories per chunk: five chunks, the last one ragged
+        env = dict(os.environ, **extra)
+        p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
+        assert p.returncode == 0, p.stderr[-2000:]
+        outs.append(json.loads(p.stdout.strip().splitlines()[-1]))
+    assert outs[0] == outs[1]
+    assert outs[0]["stats"]["transitions"] == 15000
