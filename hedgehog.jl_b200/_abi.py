@@ -130,6 +130,7 @@ SYMBOLS = {
     "hh_bk_chf": (C.c_int, [C.c_void_p, C.POINTER(hh_model), C.c_double, _dp, _dp, C.c_int, _dp, C.c_int, _dp, _dp]),
     "hh_bk_log_besseli": (C.c_int, [C.c_void_p, C.c_double, _dp, _dp, C.c_int, _dp, _dp]),
     "hh_bk_elementary": (C.c_int, [C.c_void_p, C.c_int, _dp, _dp, C.c_int, _dp, _dp]),
+    "hh_debug_check_guards": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
     "hh_bk_integral": (C.c_int, [C.c_void_p, C.POINTER(hh_model), C.c_double, C.POINTER(hh_bk_config), _dp, _dp, _dp,
                                  C.c_int, _dp]),
     "hh_bk_variance": (C.c_int, [C.c_void_p, C.POINTER(hh_model), C.c_double, _dp, C.c_int, C.c_uint64, _dp]),

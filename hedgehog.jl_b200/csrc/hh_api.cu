@@ -102,11 +102,7 @@ int hh_destroy(hh_ctx *ctx) {
   if (!ctx) return HH_ERR_ARG;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
-  hh::DeviceBuffer *bufs[] = {&ctx->d_payoffs,  &ctx->d_partials, &ctx->d_final, &ctx->d_terminal,
-                              &ctx->d_seeds,    &ctx->d_normals,  &ctx->d_tangents, &ctx->d_grid,
-                              &ctx->d_cash,     &ctx->d_tau,      &ctx->d_lsm_partials, &ctx->d_lsm_state,
-                              &ctx->d_misc,     &ctx->d_counters, &ctx->d_bk_slab, &ctx->d_bk_work};
-  for (auto *b : bufs) b->release();
+  ctx->for_each_buffer([](hh::DeviceBuffer &b) { b.release(); });
   for (int q = 0; q < ctx->peer_world; ++q)
     if (q != ctx->peer_rank && ctx->peer_mail[q]) cudaIpcCloseMemHandle(ctx->peer_mail[q]);
   if (ctx->mailbox) cudaFree(ctx->mailbox);
@@ -374,6 +370,23 @@ int hh_bk_elementary(hh_ctx *ctx, int kind, const double *x, const double *y, in
   std::lock_guard<std::mutex> lk(ctx->mu);
   NvtxRange nv("hh_bk_elementary");
   return hh::bk_elementary(ctx, kind, x, y, n, out_a, out_b);
+}
+
+int hh_debug_check_guards(hh_ctx *ctx, int64_t *violations) {
+  if (!ctx || !violations) return HH_ERR_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  HH_CUDA(ctx, cudaSetDevice(ctx->device));
+  HH_CUDA(ctx, cudaDeviceSynchronize());
+  long long bad = 0;
+  bool failed = false;
+  ctx->for_each_buffer([&](hh::DeviceBuffer &b) {
+    const long long v = b.guard_violations();
+    if (v < 0) failed = true;
+    else bad += v;
+  });
+  if (failed) return ctx->fail(HH_ERR_CUDA, "hh_debug_check_guards: reading a guard band failed");
+  *violations = hh::debug_guards() ? (int64_t)bad : -1;
+  return HH_OK;
 }
 
 int hh_bk_last_stats(hh_ctx *ctx, double *out5) {

@@ -7,6 +7,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <mutex>
 #include <string>
 
@@ -14,23 +15,59 @@
 
 namespace hh {
 
+// HH_DEBUG_GUARDS=1 (read once per process): every scratch buffer is allocated with a 4 KB guard band on each side, the
+// whole allocation is filled with 0xFF bytes (NaN as f64, huge as integers: a read of memory the kernels never wrote
+// shows up as a non-finite result) and hh_debug_check_guards counts guard bytes that changed (a write out of bounds).
+// compute-sanitizer is closed on the GPU pool this library is developed on; this is the stand-in for its memcheck /
+// initcheck on the small cases of tools/sanity_small.py (tests/test_gpu_guards.py).
+constexpr size_t kGuardBytes = 4096;
+inline bool debug_guards() {
+  static const bool on = getenv("HH_DEBUG_GUARDS") && atoi(getenv("HH_DEBUG_GUARDS")) != 0;
+  return on;
+}
+
 struct DeviceBuffer {
   void *ptr = nullptr;
   size_t cap = 0;
+  size_t guard = 0;  // bytes of guard band on each side of [ptr, ptr + cap)
   cudaError_t ensure(size_t bytes) {
     if (bytes <= cap) return cudaSuccess;
-    if (ptr) cudaFree(ptr);
-    ptr = nullptr;
-    cap = 0;
+    release();
     size_t want = bytes + bytes / 8 + 256;
-    cudaError_t e = cudaMalloc(&ptr, want);
-    if (e == cudaSuccess) cap = want;
-    return e;
+    want = (want + 255) & ~(size_t)255;
+    const size_t g = debug_guards() ? kGuardBytes : 0;
+    void *base = nullptr;
+    cudaError_t e = cudaMalloc(&base, want + 2 * g);
+    if (e != cudaSuccess) return e;
+    if (g) {
+      e = cudaMemset(base, 0xFF, want + 2 * g);
+      if (e != cudaSuccess) {
+        cudaFree(base);
+        return e;
+      }
+    }
+    ptr = static_cast<char *>(base) + g;
+    cap = want;
+    guard = g;
+    return cudaSuccess;
   }
   void release() {
-    if (ptr) cudaFree(ptr);
+    if (ptr) cudaFree(static_cast<char *>(ptr) - guard);
     ptr = nullptr;
     cap = 0;
+    guard = 0;
+  }
+  // guard bytes that no longer hold 0xFF (0 without HH_DEBUG_GUARDS); the device must be idle
+  long long guard_violations() const {
+    if (!ptr || !guard) return 0;
+    unsigned char host[kGuardBytes];
+    long long bad = 0;
+    for (int side = 0; side < 2; ++side) {
+      const char *src = side ? static_cast<char *>(ptr) + cap : static_cast<char *>(ptr) - guard;
+      if (cudaMemcpy(host, src, guard, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+      for (size_t i = 0; i < guard; ++i) bad += host[i] != 0xFF;
+    }
+    return bad;
   }
   template <class T>
   T *as() const {
@@ -105,6 +142,13 @@ struct hh_ctx {
   cudaStream_t copy_stream = nullptr;     // device -> host copies that overlap the kernels on `stream`
   cudaEvent_t ev_seg[16] = {};            // segment i of a segmented launch has finished
   hh::PendingEuropean pend;
+
+  template <class F>
+  void for_each_buffer(F f) {
+    hh::DeviceBuffer *bufs[] = {&d_payoffs, &d_partials, &d_final, &d_terminal, &d_seeds, &d_normals, &d_tangents, &d_grid, &d_cash,
+                                &d_tau, &d_lsm_partials, &d_lsm_state, &d_misc, &d_counters, &d_bk_slab, &d_bk_work};
+    for (auto *b : bufs) f(*b);
+  }
 
   int fail(int code, const char *fmt, ...) {
     char buf[512];

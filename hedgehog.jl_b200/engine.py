@@ -297,6 +297,12 @@ class CudaEngine:
                                             int(seed) & 0xFFFFFFFFFFFFFFFF, _dp(VT)), "hh_bk_variance")
         return VT
 
+    def debug_check_guards(self) -> int:
+        """Guard-band bytes overwritten so far (HH_DEBUG_GUARDS=1), -1 when the guards are off."""
+        v = C.c_int64(0)
+        self._check(self.lib.hh_debug_check_guards(self.h, C.byref(v)), "hh_debug_check_guards")
+        return int(v.value)
+
     def bk_last_stats(self) -> dict:
         out = np.zeros(5)
         self._check(self.lib.hh_bk_last_stats(self.h, _dp(out)), "hh_bk_last_stats")

@@ -206,6 +206,11 @@ int hh_bench_fp64_peak(hh_ctx *ctx, double *tflops, double *ms);
  *   part 2: Philox only (the words are XOR-folded into the state; no FP64 work)
  * Results are not prices; `ms` is the device time of the one launch. bench.py reports the split. */
 int hh_bench_heston_ablation(hh_ctx *ctx, int64_t n_paths, int n_steps, int rng_mode, int part, double *ms);
+/* Debug aid (the stand-in for compute-sanitizer's memcheck / initcheck where that tool is unavailable): with the
+ * environment variable HH_DEBUG_GUARDS=1 set before the first hh_create, every device scratch buffer of a context carries
+ * a 4 KB guard band on each side and is pre-filled with 0xFF bytes (NaN as f64). *violations = number of guard bytes that
+ * were overwritten so far (an out-of-bounds write), or -1 when the variable is not set. Synchronises the device. */
+int hh_debug_check_guards(hh_ctx *ctx, int64_t *violations);
 
 /* ---- European Monte Carlo: solve(::PricingProblem, ::MonteCarlo), montecarlo.jl:478-493 ------
  * One simulation prices `npayoffs` vanilla payoffs on the same paths (npayoffs = 1 is the

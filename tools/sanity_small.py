@@ -1,6 +1,8 @@
 #!/usr/bin/env python
-"""One small invocation of every kernel family (for compute-sanitizer runs): European f64 / f32 / generic / GBM / tangents
-(specialised and generic), Broadie-Kaya, LSM persistent and with outputs, peer-mailbox loopback."""
+"""One small invocation of every kernel family: European f64 / f32 / generic / GBM / tangents (specialised and generic),
+Broadie-Kaya, path-dependent payoffs, LSM persistent and with outputs, peer-mailbox loopback. Written for compute-sanitizer;
+that tool is closed on the GPU pool (profiles/r2_e_sanitizer.txt), so tests/test_gpu_guards.py runs this script with
+HH_DEBUG_GUARDS=1 instead: guard bands around every device buffer, buffers pre-filled with NaN bytes."""
 import math
 import os
 import sys
@@ -37,9 +39,28 @@ for anti in (0, 1):
                                             (100.0, -1.0), 3, math.exp(-0.05 / 12), want_stopping=True, want_paths=True)
     assert np.isfinite(out.price)
 eng.mc_european(m, SimSpec(n_paths=600, n_steps=3, scheme=abi.HH_SCHEME_HESTON_BK, base_seed=6), pay, 0.97, want_terminal=True)
+# the opt-in 64-bit Philox stream, path-dependent payoffs (generic, specialised Heston, Broadie-Kaya dates), log-space and
+# Broadie-Kaya LSM generators, second-order sums, the Broadie-Kaya probes
+eng.mc_european(m, SimSpec(n_paths=3001, n_steps=8, rng_mode=abi.HH_RNG_PHILOX_64, base_seed=8), pay, 0.97, want_terminal=True)
+pd = [(abi.HH_PD_ASIAN_ARITH, 100.0, 1.0, 0.0, 0.0), (abi.HH_PD_ASIAN_GEOM, 100.0, -1.0, 0.0, 0.0),
+      (abi.HH_PD_UP_OUT, 100.0, 1.0, 125.0, 0.5), (abi.HH_PD_DOWN_IN, 100.0, -1.0, 80.0, 0.0), (abi.HH_PD_DIGITAL_CASH, 100.0, 1.0, 0.0, 2.0)]
+for anti in (0, 1):
+    eng.mc_path_dependent(m, SimSpec(n_paths=2001, n_steps=12, vr=anti, base_seed=9), pd, 0.97, monitor_every=3, want_stats=True)
+    eng.mc_path_dependent(g, SimSpec(n_paths=2001, n_steps=12, vr=anti, base_seed=10), pd, 0.95, monitor_every=4, want_stats=True)
+eng.mc_path_dependent(m, SimSpec(n_paths=700, n_steps=4, scheme=abi.HH_SCHEME_HESTON_BK, base_seed=11), pd, 0.97, monitor_every=2)
+eng.mc_path_dependent(m, SimSpec(n_paths=1500, n_steps=10, base_seed=12), [(abi.HH_PD_BS_CONTROL, 100.0, 1.0, 0.0, 0.0),
+                                                                         (abi.HH_PD_VANILLA_MINUS_BS, 100.0, 1.0, 0.0, 0.8)], 0.97)
+eng.lsm_american(m, SimSpec(n_paths=3000, n_steps=10, scheme=abi.HH_SCHEME_EM, base_seed=13), (100.0, -1.0), 3, 0.997, want_stopping=True)
+eng.lsm_american(m, SimSpec(n_paths=900, n_steps=4, scheme=abi.HH_SCHEME_HESTON_BK, base_seed=14), (100.0, -1.0), 2, 0.99, want_paths=True)
+eng.tangent_sums(m, tans, SimSpec(n_paths=2000, n_steps=11, base_seed=15), pay, spot_bump=0.5)
+eng.bk_chf(m, 0.25, np.full(40, 0.04), np.linspace(0.01, 0.1, 40), np.tile(np.linspace(0.5, 60.0, 30), (40, 1)))
+eng.bk_integral(m, 0.25, np.full(200, 0.04), np.linspace(0.005, 0.12, 200), np.linspace(0.01, 0.99, 200))
+eng.bk_log_besseli(0.778, np.linspace(0.1, 80, 300) * np.exp(1j * np.linspace(-1.5, 1.5, 300)))
+eng.bk_elementary("atan2", np.linspace(-3, 3, 100), np.linspace(3, -3, 100))
 h = eng.peer_export()
 eng.peer_connect(0, 1, [h])
 eng.lsm_american(g, SimSpec(n_paths=2000, n_steps=5, scheme=abi.HH_SCHEME_EXACT_STEPS, base_seed=7), (100.0, -1.0), 2, 0.99,
                  comm=abi.hh_comm(abi.hh_allreduce_fn(), None, 0, 1))
 eng.peer_disconnect()
+print("guard violations", eng.debug_check_guards())   # -1 unless HH_DEBUG_GUARDS=1
 print("sanity_small ok")
