@@ -48,6 +48,17 @@ EULER_BIAS_252 = 0.005651  # price(252 steps) - Carr-Madan, 2e8 paths, std error
 HEADLINE_KERNEL = "heston_fast2_kernel<0, 1, 1, 1, 1024, 1, 0, 0>"  # what hh_mc_european launches for C2 (hh_european.cu)
 
 
+def json_safe(x):
+    """NaN / Inf are not JSON: the driver parses the line strictly."""
+    if isinstance(x, dict):
+        return {k: json_safe(v) for k, v in x.items()}
+    if isinstance(x, (list, tuple)):
+        return [json_safe(v) for v in x]
+    if isinstance(x, float) and not math.isfinite(x):
+        return None
+    return x
+
+
 def load_json(*rel):
     try:
         with open(os.path.join(ROOT, *rel)) as f:
@@ -173,7 +184,7 @@ def run_reference(args, rank, world):
         "gpu_launches": 0,
         "loaded_product_modules": sorted(k for k in sys.modules if k.startswith("hedgehog")),
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(json_safe(line), allow_nan=False), flush=True)
 
 
 # ---- our arm --------------------------------------------------------------------------------------------------------------
@@ -410,7 +421,7 @@ def main():
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": info["cores"], "kind": "port",
                                     "sample": f"{info['paths']} paths x {args.nsteps} steps in {info['seconds']:.1f} s, "
                                               "C restatement (oracle/) with OpenMP on all host threads"}
-        print(json.dumps(line), flush=True)
+        print(json.dumps(json_safe(line), allow_nan=False), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
@@ -470,7 +481,12 @@ def run_configs(hh, eng, scale, fp64_peak, hbm_peak, hbm_peak_source, anchors, n
                  "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
                               "peak_source": hbm_peak_source,
                               "convention": "algorithmic 32 B per path-date (8 store + 8 read S_t + 16 read/write cash flow)",
-                              "traffic": kc.get("dram_bytes_per_launch"), "traffic_source": kc.get("source"),
+                              "traffic": (kc.get("dram_bytes_per_launch") or 0.0) + ((ncu_consts.get("lsm_paths_kernel<0, 0, 1>") or {})
+                                                                                       .get("dram_bytes_per_launch") or 0.0) or None,
+                              "traffic_source": kc.get("source"),
+                              "traffic_note": "ncu DRAM bytes of lsm_paths_kernel (the 4.0 GB store) + lsm_backward_kernel (8.4 GB: "
+                                              "two date slices per pass; the cash-flow vector stays in the persisting L2 window) "
+                                              "against 16 GB algorithmic",
                               "backward_only": {"achieved": n * 49 * 24.0 / (sol.stats["regress_ms"] * 1e-3) / 1e9,
                                                 "convention": "24 B per path-date of the induction alone (the cash-flow vector is "
                                                               "served from the persisting L2 window, so DRAM sees ~16 B)"}},
@@ -495,9 +511,23 @@ def run_configs(hh, eng, scale, fp64_peak, hbm_peak, hbm_peak_source, anchors, n
                  "unit": "transitions/s", "kernel_ms": kms, "e2e_ms": w,
                  "cf_evaluations_per_s": n * 12 * cf_per_transition / (kms * 1e-3),
                  "cf_evaluations_per_transition": cf_per_transition, "bk_stats": st,
-                 "roofline": {"bound": "fp64 (latency- and divergence-bound)", "frac": None,
+                 "roofline": {"bound": "fp64 (dependent-issue latency in the characteristic function)", "frac": None,
                               "note": "algorithmic flops are data dependent (SURVEY 8d): transitions/s and CF evaluations/s are "
-                                      "reported with the mean series length and CDF evaluations per inversion"},
+                                      "reported with the mean series length and CDF evaluations per inversion",
+                              "executed": (lambda kc4: {
+                                  "kernel": "bk_integral_sorted_kernel<3>", "source": kc4.get("source"),
+                                  "fp64_flop_per_transition": kc4.get("flop_per_unit"),
+                                  "instr_per_transition": kc4.get("instr_per_unit"),
+                                  "tflops": (kc4.get("flop_per_unit") or 0.0) * n * 12 / (kms * 1e-3) * 1e-12,
+                                  "frac_of_fp64_peak": (kc4.get("flop_per_unit") or 0.0) * n * 12 / (kms * 1e-3) * 1e-12 / fp64_peak,
+                                  "lane_utilisation": (kc4.get("thread_inst_per_warp_inst") or 0.0) / 32.0,
+                                  "fp64_pipe_busy_pct_under_ncu": kc4.get("fp64_pipe_pct"),
+                                  "issue_slots_busy_pct_under_ncu": kc4.get("issue_active_pct"),
+                                  "note": "executed FP64 work of the inversion kernel (95 % of the pipeline's time; the variance "
+                                          "chain, the counting sort and the assembly are the rest) x this run's transitions/s"}
+                              )(ncu_consts.get("bk_integral_sorted_kernel<3>") or {}),
+                              "pipeline": "bk_chain_kernel -> bk_scan_kernel -> bk_scatter_kernel -> bk_integral_sorted_kernel -> "
+                                          "bk_assemble_kernel (transitions sorted by log2(V0 VT): DESIGN.md section 4.5)"},
                  "check": {"price": sol.price, "std_error": sol.std_error, "carr_madan": cm,
                            "z": (sol.price - cm) / sol.std_error if cm else None, "n_fallback": sol.stats.get("n_fallback")}}
 
@@ -528,7 +558,8 @@ def run_configs(hh, eng, scale, fp64_peak, hbm_peak, hbm_peak_source, anchors, n
                     "rel_diff": float((est[k] - ref[k]) / ref[k]),
                     "max_abs_rel_diff_strikes_70_130": float(np.max(np.abs(est[sel] - ref[sel]) / np.abs(ref[sel]))),
                     "max_abs_z_strikes_70_130": float(np.max(np.abs(est[sel] - ref[sel]) / err[sel]))}
-        table["price"] = row(prices, np.full(64, float("nan")), a5["price"])
+        table["price"] = row(prices, np.full(64, float("nan")), a5["price"])   # no standard error is returned for the grid prices
+        table["price"]["std_error"] = table["price"]["max_abs_z_strikes_70_130"] = None
         for i, (nm, key) in enumerate(zip(names, keys)):
             table[nm] = row(g[:, i], se[:, i], a5[key])
         table["gamma_fd"] = row(sec["fd"], sec["fd_stderr"], a5["d2_S0"])

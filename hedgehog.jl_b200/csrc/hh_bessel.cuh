@@ -151,6 +151,24 @@ __device__ __forceinline__ void bk_fill_fast_tables(BkFastTables *t) {
 }
 #endif
 
+#ifdef __CUDACC__
+// Constants that need all 64 bits live in constant memory: a DFMA takes them as a c[bank][offset] operand, where an
+// immediate costs two UMOV / MOV instructions per use (ncu: 56 UMOV + 58 IMAD.MOV of the 518 straight-line instructions of
+// one characteristic-function evaluation).
+struct BkConsts {
+  double inv_ln2_256, ln2_256_hi, ln2_256_lo, e4, e3;            // fexp
+  double inv_2pi_256, twopi_256_hi, twopi_256_lo, s7, s5, s3, c6, c4;  // fsincos
+  double l6, l5, l3, ln2_hi, ln2_lo;                              // flog
+  double a7, a5, a3, half_pi, pi;                                 // fatan2
+};
+static __constant__ BkConsts kBkC = {
+    369.3299304675746, -2.7076061740622863e-03, -9.058776616587108e-20, 4.1666666666666664e-02, 1.6666666666666666e-01,
+    40.74366543152521, -2.454369260617026e-02, -9.567553118338697e-19, -1.9841269841269841e-04, 8.3333333333333332e-03,
+    -1.6666666666666666e-01, -1.3888888888888889e-03, 4.1666666666666664e-02,
+    -1.6666666666666666e-01, 0.2, 3.3333333333333331e-01, 6.9314718055994529e-01, 2.3190468138462996e-17,
+    -1.4285714285714285e-01, 0.2, -3.3333333333333331e-01, 1.5707963267948966, 3.1415926535897931};
+#endif
+
 #ifdef __CUDA_ARCH__
 static __device__ __noinline__ double fexp_slow(double x) { return exp(x); }
 static __device__ __noinline__ void fsincos_slow(double x, double *s, double *c) { sincos(x, s, c); }
@@ -162,13 +180,13 @@ HH_HD double fexp(FastRef ft, double x) {
   if (ft.saddr) {
     if ((unsigned)(__double2hiint(x) & 0x7fffffff) >= 0x4085E000u) return fexp_slow(x);  // |x| >= 700, inf, nan
     const double magic = 6755399441055744.0;                    // 1.5 2^52: the nearest integer lands in the low word
-    const double t = fma(x, 369.3299304675746, magic);          // 256 / ln 2
+    const double t = fma(x, kBkC.inv_ln2_256, magic);           // 256 / ln 2
     const int n = __double2loint(t);
     const double nf = t - magic;
-    double r = fma(nf, -2.7076061740622863e-03, x);             // ln 2 / 256, high part
-    r = fma(nf, -9.058776616587108e-20, r);                     // low part  (hi + lo = ln2/256 to 1e-36)
+    double r = fma(nf, kBkC.ln2_256_hi, x);                     // -(ln 2 / 256), high part
+    r = fma(nf, kBkC.ln2_256_lo, r);                            // low part  (hi + lo = ln2/256 to 1e-36)
     const double e = lds_f64(ft.saddr + kFtExp + 8u * (unsigned)(n & 255));
-    double q = fma(r, 4.1666666666666664e-02, 1.6666666666666666e-01);
+    double q = fma(r, kBkC.e4, kBkC.e3);
     q = fma(q, r, 0.5);
     q = fma(q, r, 1.0);
     const double v = fma(e * r, q, e);
@@ -188,18 +206,18 @@ HH_HD void fsincos(FastRef ft, double x, double &sn, double &cs) {
       return;
     }
     const double magic = 6755399441055744.0;
-    const double t = fma(x, 40.74366543152521, magic);        // 256 / (2 pi)
+    const double t = fma(x, kBkC.inv_2pi_256, magic);         // 256 / (2 pi)
     const int n = __double2loint(t);
     const double nf = t - magic;
-    double r = fma(nf, -2.454369260617026e-02, x);              // 2 pi / 256, high part
-    r = fma(nf, -9.567553118338697e-19, r);                     // low part
+    double r = fma(nf, kBkC.twopi_256_hi, x);                   // -(2 pi / 256), high part
+    r = fma(nf, kBkC.twopi_256_lo, r);                          // low part
     double2 cs0;
     lds_f64x2(ft.saddr + kFtTrig + 16u * (unsigned)(n & 255), cs0.x, cs0.y);
     const double r2 = r * r;
-    double ps = fma(r2, -1.9841269841269841e-04, 8.3333333333333332e-03);
-    ps = fma(ps, r2, -1.6666666666666666e-01);
+    double ps = fma(r2, kBkC.s7, kBkC.s5);
+    ps = fma(ps, r2, kBkC.s3);
     const double ds = (r * r2) * ps;                            // sin r - r
-    double pc = fma(r2, -1.3888888888888889e-03, 4.1666666666666664e-02);
+    double pc = fma(r2, kBkC.c6, kBkC.c4);
     pc = fma(pc, r2, -0.5);
     const double dc = r2 * pc;                                  // cos r - 1
     const double sr = r + ds;
@@ -228,14 +246,14 @@ HH_HD double flog(FastRef ft, double x) {
       double2 rl;
       lds_f64x2(ft.saddr + kFtLog + 16u * (unsigned)j, rl.x, rl.y);
       const double sft = fma(m, rl.x, -1.0);
-      double q = fma(sft, -1.6666666666666666e-01, 0.2);
+      double q = fma(sft, kBkC.l6, kBkC.l5);
       q = fma(q, sft, -0.25);
-      q = fma(q, sft, 3.3333333333333331e-01);
+      q = fma(q, sft, kBkC.l3);
       q = fma(q, sft, -0.5);
       const double s2 = sft * sft;
       const double l1p = fma(s2, q, sft);
       const double ef = (double)e;
-      return fma(ef, 6.9314718055994529e-01, rl.y + fma(ef, 2.3190468138462996e-17, l1p));
+      return fma(ef, kBkC.ln2_hi, rl.y + fma(ef, kBkC.ln2_lo, l1p));
     }
   }
 #endif
@@ -265,11 +283,11 @@ HH_HD double fatan2(FastRef ft, double y, double x) {
       e = fma(-den, yd, 1.0);
       yd = fma(yd, e, yd);
       const double u = num * yd, u2 = u * u;
-      double q = fma(u2, -1.4285714285714285e-01, 0.2);
-      q = fma(q, u2, -3.3333333333333331e-01);
+      double q = fma(u2, kBkC.a7, kBkC.a5);
+      q = fma(q, u2, kBkC.a3);
       double a = lds_f64(ft.saddr + kFtAtan + 8u * (unsigned)j) + fma(u * u2, q, u);
-      if (ay > ax) a = 1.5707963267948966 - a;
-      if (x < 0.0) a = 3.1415926535897931 - a;
+      if (ay > ax) a = kBkC.half_pi - a;
+      if (x < 0.0) a = kBkC.pi - a;
       return copysign(a, y);
     }
   }

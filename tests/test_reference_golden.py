@@ -301,9 +301,10 @@ def check_bk_cuda(cuda, abi, A, meta, tag):
     assert np.array_equal(g["J"].astype(int), out[5].astype(int))
     assert rel(g["mean"], out[2]) < 1e-7 and np.max(np.abs(g["h"] / out[4] - 1)) < 5e-3
     ok = g["status"] != 2
-    # the package's root satisfies |F(x) - u| <= 1e-4; F' ~ 1 / sd, so the two roots differ by at most ~2e-4 sd
+    # the package's root satisfies |F(x) - u| <= 1e-4 (secant; F' ~ 1 / sd) or sits in a bracket of width 1e-4 (bisection,
+    # xtol = atol, sample_from_cf.jl:128); the kernel's root is exact to rounding
     sd = np.sqrt(np.maximum(out[3], 1e-12))
-    assert np.all(np.abs(g["x"][ok] - out[6][ok]) <= 1e-3 * sd[ok] + 1e-12)
+    assert np.all(np.abs(g["x"][ok] - out[6][ok]) <= 1e-3 * sd[ok] + 1.1e-4)
 
 
 # ---- the real dump --------------------------------------------------------------------------------------------------------

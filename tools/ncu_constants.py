@@ -16,7 +16,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OUT = os.path.join(ROOT, "profiles", "ncu_constants.json")
 FAMILY = {"heston_fast2_kernel": ("c2", "c2_64"), "lsm_backward_kernel": ("c3",), "lsm_paths_kernel": ("c3",),
-          "bk_paths_kernel": ("c4",), "heston_tangent_kernel": ("c5",)}
+          "bk_integral_sorted_kernel": ("c4",), "heston_tangent_kernel": ("c5",)}
 
 
 def fnum(x):
