@@ -11,6 +11,8 @@ constexpr int NCH = 8;
 // MODE 0: DFMA reuse (x = x*a+b)   1: DFMA distinct (x_i = x_i*y_i + z_i, y,z rotate)   2: LOP3 only   3: IMAD.WIDE only
 // 4: DFMA + LOP3 1:1   5: DFMA + IMAD.WIDE 1:1   6: IMAD.WIDE + LOP3 1:1   7: DFMA+IMAD.WIDE+LOP3 1:1:1  8: DMUL distinct
 // 9: IMAD (32-bit) only  10: DFMA + IMAD32 1:1  11: DADD distinct
+// 12: half a Philox round with mul.wide.u32 (IMAD.WIDE + LOP3)   13: the same with mul.lo.u32 + mul.hi.u32 (IMAD + IMAD.HI + LOP3)
+// 14 / 15: modes 12 / 13 interleaved 1:1 with a DFMA (what the Heston step does)
 template <int MODE>
 __global__ void __launch_bounds__(256) k(double *out, double a, double b, uint32_t m) {
   double x[NCH], y[NCH], z[NCH];
@@ -32,6 +34,20 @@ __global__ void __launch_bounds__(256) k(double *out, double a, double b, uint32
       if (MODE == 2 || MODE == 4 || MODE == 6 || MODE == 7) u[c] = (u[c] ^ v[(c + 1) % NCH]) ^ m;
       if (MODE == 3 || MODE == 5 || MODE == 6 || MODE == 7) w[c] = (uint64_t)(uint32_t)w[c] * m + (w[c] >> 32);
       if (MODE == 9 || MODE == 10) v[c] = v[c] * m + 12345u;
+      if (MODE == 12 || MODE == 14) {
+        uint32_t lo, hi;
+        asm("{ .reg .b64 t; mul.wide.u32 t, %2, %3; mov.b64 {%0, %1}, t; }" : "=r"(lo), "=r"(hi) : "r"(u[c]), "r"(0xD2511F53u));
+        u[c] = hi ^ v[c] ^ m;
+        v[c] = lo;
+      }
+      if (MODE == 13 || MODE == 15) {
+        uint32_t lo, hi;
+        asm("mul.lo.u32 %0, %1, %2;" : "=r"(lo) : "r"(u[c]), "r"(0xD2511F53u));
+        asm("mul.hi.u32 %0, %1, %2;" : "=r"(hi) : "r"(u[c]), "r"(0xD2511F53u));
+        u[c] = hi ^ v[c] ^ m;
+        v[c] = lo;
+      }
+      if (MODE == 14 || MODE == 15) x[c] = fma(x[c], a, b);
     }
   }
   double s = 0; uint64_t t = 0;
@@ -71,5 +87,9 @@ int main() {
   run<10>("DFMA + IMAD32", 1);
   run<6>("IMAD.WIDE + LOP3", 1);
   run<7>("DFMA + IMAD.WIDE + LOP3", 1);
+  run<12>("Philox half-round, mul.wide", 1);
+  run<13>("Philox half-round, mul.lo + mul.hi", 1);
+  run<14>("Philox half-round, mul.wide, + DFMA", 1);
+  run<15>("Philox half-round, lo + hi, + DFMA", 1);
   return 0;
 }
