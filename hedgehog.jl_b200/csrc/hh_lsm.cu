@@ -57,8 +57,10 @@ constexpr int kLsmPathSmem = kLogRepBytes + kTrigRepBytes + kExp2Bytes + kExpm1T
 // the top stall)
 constexpr int kLsmPathThreads = 512;
 
-template <bool ANTI, bool PARITY, bool UKEY>
-__global__ void __launch_bounds__(kLsmPathThreads) lsm_paths_kernel(const LsmPathArgs a) {
+// SMALL: the host has proven |(r - s^2/2) dt +- s sqrt(dt) z| <= 1/2 for every normal the in-kernel stream can produce
+// (|z| <= 8.6), so fast_expm1_small runs without its range test (never with caller-supplied normals).
+template <bool ANTI, bool PARITY, bool UKEY, bool SMALL>
+__global__ void __launch_bounds__(kLsmPathThreads, 2) lsm_paths_kernel(const LsmPathArgs a) {
   extern __shared__ __align__(16) unsigned char dsm[];
   char *s_log = reinterpret_cast<char *>(dsm);
   char *s_trig = s_log + kLogRepBytes;
@@ -106,11 +108,11 @@ __global__ void __launch_bounds__(kLsmPathThreads) lsm_paths_kernel(const LsmPat
         if (n + h < M) {
           const double zz = h ? zb : za;
           // GeometricBrownianMotionProcess increment [upstream]: S += S (exp((r - s^2/2) dt + s sqrt(dt) Z) - 1)
-          Sp = fma(Sp, fast_expm1_small(s_exp, fma(a.sig_sqdt, zz, a.dt_drift)), Sp);
+          Sp = fma(Sp, fast_expm1_small<!SMALL>(s_exp, fma(a.sig_sqdt, zz, a.dt_drift)), Sp);
           gp += a.stride;
           *gp = Sp;
           if (ANTI) {  // same normals, sigma -> -sigma (montecarlo.jl:270-284)
-            Sm = fma(Sm, fast_expm1_small(s_exp, fma(-a.sig_sqdt, zz, a.dt_drift)), Sm);
+            Sm = fma(Sm, fast_expm1_small<!SMALL>(s_exp, fma(-a.sig_sqdt, zz, a.dt_drift)), Sm);
             gm += a.stride;
             *gm = Sm;
           }
@@ -1342,15 +1344,22 @@ int lsm_american(hh_ctx *ctx, const hh_model *m, const hh_sim *s, const hh_payof
   } else {
     const bool ukey = pa.seeds == nullptr;
     cudaError_t le = cudaSuccess;
-#define HH_LSM_PATHS(A, P, U)                                                                                           \
+    // the largest exponent argument the in-kernel stream can produce: |z| <= sqrt(-2 ln 2^-52) = 8.49
+    const bool small = !parity && fabs(pa.dt_drift) + 8.6 * fabs(pa.sig_sqdt) <= 0.5;
+#define HH_LSM_PATHS(A, P, U, S)                                                                                        \
   do {                                                                                                                  \
     static PerDeviceOnce opted;                                                                                         \
-    le = smem_opt_in(opted, lsm_paths_kernel<A, P, U>, kLsmPathSmem);                                                   \
-    if (le == cudaSuccess) lsm_paths_kernel<A, P, U><<<grid_paths, kLsmPathThreads, kLsmPathSmem, st>>>(pa);                \
+    le = smem_opt_in(opted, lsm_paths_kernel<A, P, U, S>, kLsmPathSmem);                                                \
+    if (le == cudaSuccess) lsm_paths_kernel<A, P, U, S><<<grid_paths, kLsmPathThreads, kLsmPathSmem, st>>>(pa);         \
   } while (0)
-    if (parity) { if (anti) HH_LSM_PATHS(true, true, true); else HH_LSM_PATHS(false, true, true); }
-    else if (ukey) { if (anti) HH_LSM_PATHS(true, false, true); else HH_LSM_PATHS(false, false, true); }
-    else { if (anti) HH_LSM_PATHS(true, false, false); else HH_LSM_PATHS(false, false, false); }
+#define HH_LSM_PATHS_S(A, P, U)                                              \
+  do {                                                                       \
+    if (small) HH_LSM_PATHS(A, P, U, true); else HH_LSM_PATHS(A, P, U, false); \
+  } while (0)
+    if (parity) { if (anti) HH_LSM_PATHS(true, true, true, false); else HH_LSM_PATHS(false, true, true, false); }
+    else if (ukey) { if (anti) HH_LSM_PATHS_S(true, false, true); else HH_LSM_PATHS_S(false, false, true); }
+    else { if (anti) HH_LSM_PATHS_S(true, false, false); else HH_LSM_PATHS_S(false, false, false); }
+#undef HH_LSM_PATHS_S
 #undef HH_LSM_PATHS
     HH_CUDA(ctx, le);
   }
