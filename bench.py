@@ -629,26 +629,34 @@ def run_multi_gpu(hh, eng, rank, world, args, barrier, max_over_ranks, anchors):
     connect_peers(eng)
     hh.solve(p, lsm, engine=eng, stopping_info=False)
     barrier()
-    best, sol = None, None
-    for _ in range(3):
+    best, sol, kms, rms = None, None, None, None
+    for _ in range(4):
         barrier()
         t0 = time.perf_counter()
         sol = hh.solve(p, lsm, engine=eng, stopping_info=False)
         t = max_over_ranks(time.perf_counter() - t0)
-        best = t if best is None or t < best else best
-    kms = max_over_ranks(sol.stats["kernel_ms"])
-    rms = max_over_ranks(sol.stats["regress_ms"])
+        # a rank that enters the persistent kernel first spends the skew waiting inside it: take the repetition whose slowest
+        # rank was fastest, for the wall time and for the kernel times alike
+        k, r = max_over_ranks(sol.stats["kernel_ms"]), max_over_ranks(sol.stats["regress_ms"])
+        if best is None or t < best:
+            best, kms, rms = t, k, r
     eng.peer_disconnect()
     barrier()
     single = None
     if rank == 0:  # the same 1e7 columns on ONE GPU (no exchange): same trajectories by global index
+        hh.solve(p, lsm, engine=eng, stopping_info=False, shard=(0, 1))
+        t0 = time.perf_counter()
         s1 = hh.solve(p, lsm, engine=eng, stopping_info=False, shard=(0, 1))
-        single = {"price": s1.price, "kernel_ms": s1.stats["kernel_ms"]}
+        single = {"price": s1.price, "kernel_ms": s1.stats["kernel_ms"], "e2e_ms": (time.perf_counter() - t0) * 1e3}
     barrier()
     out["c3_lsm_peer"] = {"workload": f"C3 with {n} columns in TOTAL over {world} GPUs, moments exchanged in-kernel over peer memory",
-                          "scaling": "strong", "value": n * 50 / (kms * 1e-3), "unit": "path-dates/s", "kernel_ms_max_over_ranks": kms,
-                          "regress_ms_max_over_ranks": rms, "e2e_ms": best * 1e3, "price": sol.price, "std_error": sol.std_error,
-                          "one_gpu": single, "price_bit_equal_to_one_gpu": (single["price"] == sol.price) if single else None,
+                          "scaling": "strong", "value": n * 50 / best, "unit": "path-dates/s (e2e, slowest rank)",
+                          "e2e_ms": best * 1e3, "kernel_ms_max_over_ranks": kms, "regress_ms_max_over_ranks": rms,
+                          "price": sol.price, "std_error": sol.std_error, "one_gpu": single,
+                          "price_rel_diff_vs_one_gpu": (abs(single["price"] - sol.price) / single["price"]) if single else None,
+                          "price_note": "every rank fits bit-identical polynomials (moments added in rank order), so the exercise "
+                                        "decisions are the one-GPU decisions; the price is a sum over columns, reduced per rank and "
+                                        "then across ranks: it can differ from the one-GPU sum in the last bits (order of additions)",
                           "crr_american_1000_steps": anchors.get("c3_crr_american_put_1000")}
     return out
 
