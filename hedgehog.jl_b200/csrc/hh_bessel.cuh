@@ -65,10 +65,17 @@ HH_HD double rcp_fast(double x) {
 
 // sqrt x for x well inside the normal range (the moduli here): on the device the MUFU.RSQ64H seed (2^-22.9) and one cubic
 // step, s = s0 (1 + e + 3/2 e^2) with s0 = x y0, e = (1 - x y0^2) / 2 — 5 FP64 instructions instead of IEEE sqrt's ~14, ~1 ulp
+#ifdef __CUDA_ARCH__
+// the IEEE square root (an inline expansion of ~40 instructions with its own slow path) is kept OUT of the hot functions:
+// ncu shows ~1 cycle of instruction-fetch stall per issued instruction in the inversion kernel, and more than half of the
+// 1500 instructions of bk_chf were never-executed fallbacks interleaved with the hot path
+static __device__ __noinline__ double sqrt_slow(double x) { return sqrt(x); }
+#endif
 HH_HD double sqrt_fast(double x) {
 #ifdef __CUDA_ARCH__
   const int hi = __double2hiint(x);
-  if (hi >= 0x00200000 && hi < 0x7fd00000) {
+  if (hi < 0x00200000 || hi >= 0x7fd00000) return sqrt_slow(x);
+  {
     double y0;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(x));
     const double h0 = __hiloint2double(__double2hiint(y0) - 0x00100000, 0);  // y0 / 2 (the seed's low word is zero)
@@ -77,8 +84,9 @@ HH_HD double sqrt_fast(double x) {
     const double pp = fma(e * 1.5, e, e);
     return fma(s0, pp, s0);
   }
-#endif
+#else
   return sqrt(x);
+#endif
 }
 
 // 1 / z = conj(z) / |z|^2 for moduli far from the over/underflow of the square (one reciprocal; Smith's form takes two)
@@ -170,8 +178,12 @@ static __constant__ BkConsts kBkC = {
 #endif
 
 #ifdef __CUDA_ARCH__
+// library fallbacks (arguments outside the fast paths, callers without tables): out of line, so that the inline expansions of
+// the CUDA math library (~140 instructions per exp + sincos) do not sit between the hot instructions of every call site
 static __device__ __noinline__ double fexp_slow(double x) { return exp(x); }
 static __device__ __noinline__ void fsincos_slow(double x, double *s, double *c) { sincos(x, s, c); }
+static __device__ __noinline__ double flog_slow(double x) { return log(x); }
+static __device__ __noinline__ double fatan2_slow(double y, double x) { return atan2(y, x); }
 #endif
 
 // exp(x): x = (256 k + j) ln2 / 256 + r, exp(x) = 2^k T_j exp(r), |r| <= ln2 / 512
@@ -192,9 +204,11 @@ HH_HD double fexp(FastRef ft, double x) {
     const double v = fma(e * r, q, e);
     return __hiloint2double(__double2hiint(v) + ((n >> 8) << 20), __double2loint(v));
   }
-#endif
+  return fexp_slow(x);
+#else
   (void)ft;
   return exp(x);
+#endif
 }
 
 // sin x, cos x: x = (256 k + j) 2 pi / 256 + r, |r| <= pi / 256; rotation of the tabulated (cos, sin) by r
@@ -225,11 +239,9 @@ HH_HD void fsincos(FastRef ft, double x, double &sn, double &cs) {
     sn = cs0.y + fma(cs0.y, dc, cs0.x * sr);
     return;
   }
-#endif
-  (void)ft;
-#if defined(__CUDA_ARCH__) || defined(__GNUC__)
-  sincos(x, &sn, &cs);
+  fsincos_slow(x, &sn, &cs);
 #else
+  (void)ft;
   sn = sin(x);
   cs = cos(x);
 #endif
@@ -256,9 +268,11 @@ HH_HD double flog(FastRef ft, double x) {
       return fma(ef, kBkC.ln2_hi, rl.y + fma(ef, kBkC.ln2_lo, l1p));
     }
   }
-#endif
+  return flog_slow(x);
+#else
   (void)ft;
   return log(x);
+#endif
 }
 
 // atan2(y, x) in (-pi, pi]: t = min/max in [0, 1], c = nearest multiple of 1/128, atan t = atan c + atan((t - c)/(1 + t c))
@@ -291,9 +305,11 @@ HH_HD double fatan2(FastRef ft, double y, double x) {
       return copysign(a, y);
     }
   }
-#endif
+  return fatan2_slow(y, x);
+#else
   (void)ft;
   return atan2(y, x);
+#endif
 }
 
 HH_HD cplx cexp_(FastRef ft, cplx a) {
@@ -314,6 +330,13 @@ HH_HD cplx csqrt_(cplx a) {
   }
   const double t = sqrt_fast(0.5 * (m - a.re));
   return cplx{0.5 * fabs(a.im) * rcp_fast(t), a.im >= 0.0 ? t : -t};
+}
+
+// sqrt(a) for Re a > 0 (gamma^2 = kappa^2 - 2 sigma^2 a i in the characteristic function): the first branch of csqrt_ alone
+HH_HD cplx csqrt_pos_(cplx a) {
+  const double m = sqrt_fast(cabs2(a));
+  const double t = sqrt_fast(0.5 * (m + a.re));
+  return cplx{t, 0.5 * a.im * rcp_fast(t)};
 }
 
 constexpr double kBesselPi = 3.14159265358979323846;
@@ -627,7 +650,7 @@ HH_HD BkCf bk_cf_init(const BkParams &p, double V0, double VT) {
 
 // Phi(a) with the unwrapped angle of z_gamma carried in theta_prev (NaN = first evaluation), heston.jl:184-212.
 HH_HD_OUTLINE cplx bk_chf(const BkParams &p, const BkCf &it, double a, double &theta_prev) {
-  const cplx g = csqrt_(cplx{p.kappa * p.kappa, -2.0 * p.xi2 * a});        // gamma            :190
+  const cplx g = csqrt_pos_(cplx{p.kappa * p.kappa, -2.0 * p.xi2 * a});    // gamma            :190  (Re gamma^2 = kappa^2 > 0)
   const FastRef ft = p.ord.ft;
   const cplx egh = cexp_(ft, (-0.5 * p.tau) * g);  // e^{-g tau / 2}
   const cplx eg = egh * egh;
