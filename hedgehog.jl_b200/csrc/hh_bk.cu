@@ -137,21 +137,41 @@ struct BkTable {
 };
 
 // F(x) - u and F'(x) for F(x) = h x / pi + sum_j c_j sin(j h x)   (cdf_from_cf, sample_from_cf.jl:75-96)
-__device__ __noinline__ void bk_cdf(const BkTable &tb, int J, double h, double x, double &F, double &dF) {
+// sin(j th), cos(j th) by the Chebyshev recurrence, two terms per iteration (ping-pong registers, no moves); the
+// shared-memory part of the table is read through the shared window without a per-term range test.
+__device__ __noinline__ void bk_cdf(const BkTable &tb, FastRef ft, int J, double h, double x, double &F, double &dF) {
   const double th = h * x;
   double s1, c1;
-  sincos(th, &s1, &c1);
+  fsincos(ft, th, s1, c1);
   const double two_c = 2.0 * c1;
-  double sp = 0.0, s = s1;    // sin((j-1) th), sin(j th)
-  double cp = 1.0, c = c1;    // cos((j-1) th), cos(j th)
-  double acc = 0.0, dacc = 0.0;
-  for (int j = 1; j <= J; ++j) {
-    const double cj = tb.get(j - 1);
-    acc = fma(cj, s, acc);
-    dacc = fma(cj * (double)j, c, dacc);
-    const double sn = fma(two_c, s, -sp), cn = fma(two_c, c, -cp);
-    sp = s; s = sn;
-    cp = c; c = cn;
+  double sa = 0.0, sb = s1;  // sin((j-1) th), sin(j th)
+  double ca = 1.0, cb = c1;  // cos((j-1) th), cos(j th)
+  double acc = 0.0, dacc = 0.0, dj = 1.0;
+  const int J1 = J < tb.cap ? J : tb.cap;
+  unsigned addr = tb.sh_saddr;
+  const unsigned st = tb.sh_stride_bytes;
+  int j = 0;
+#pragma unroll 1
+  for (; j + 2 <= J1; j += 2, addr += 2 * st) {
+    const double c0 = lds_f64(addr), c1j = lds_f64(addr + st);
+    acc = fma(c0, sb, acc);
+    dacc = fma(c0 * dj, cb, dacc);
+    sa = fma(two_c, sb, -sa);  // sin((j+1) th)
+    ca = fma(two_c, cb, -ca);
+    acc = fma(c1j, sa, acc);
+    dacc = fma(c1j * (dj + 1.0), ca, dacc);
+    sb = fma(two_c, sa, -sb);  // sin((j+2) th)
+    cb = fma(two_c, ca, -cb);
+    dj += 2.0;
+  }
+  for (; j < J; ++j) {  // the odd term, and terms beyond the shared-memory table (global slab)
+    const double cj = tb.get(j);
+    acc = fma(cj, sb, acc);
+    dacc = fma(cj * dj, cb, dacc);
+    const double sn = fma(two_c, sb, -sa), cn = fma(two_c, cb, -ca);
+    sa = sb; sb = sn;
+    ca = cb; cb = cn;
+    dj += 1.0;
   }
   constexpr double kInvPi = 1.0 / kBesselPi;
   F = fma(h * x, kInvPi, acc);
@@ -191,7 +211,7 @@ __device__ BkInversion bk_sample_integral(const BkParams &p, double V0, double V
   r.J = J;
   // inverse_cdf :105-135
   double F, dF;
-  bk_cdf(tb, J, h, max_guess, F, dF);
+  bk_cdf(tb, p.ord.ft, J, h, max_guess, F, dF);
   const double fmax_ = F - u;
   int iters = 1;
   if (fmax_ >= 0.0 && u > 0.0) {
@@ -200,7 +220,7 @@ __device__ BkInversion bk_sample_integral(const BkParams &p, double V0, double V
     double x = fmin(fmax(guess, 0.0), max_guess);
     double f = 0.0;
     for (int k = 0; k < 100; ++k) {
-      bk_cdf(tb, J, h, x, F, dF);
+      bk_cdf(tb, p.ord.ft, J, h, x, F, dF);
       ++iters;
       f = F - u;
       if (f < 0.0) lo = x; else hi = x;
@@ -221,16 +241,16 @@ __device__ BkInversion bk_sample_integral(const BkParams &p, double V0, double V
     // F(max_guess) < u: no sign change. The reference first lets its secant iteration run (<= maxiter evaluations) and
     // accepts x >= 0 with |F(x) - u| <= atol; otherwise it returns max_guess with a warning (:123-126).
     double x0 = guess, x1 = guess * 1.001 + 1e-12, f0, f1;
-    bk_cdf(tb, J, h, x0, F, dF);
+    bk_cdf(tb, p.ord.ft, J, h, x0, F, dF);
     f0 = F - u;
-    bk_cdf(tb, J, h, x1, F, dF);
+    bk_cdf(tb, p.ord.ft, J, h, x1, F, dF);
     f1 = F - u;
     iters += 2;
     for (int k = 2; k < 10; ++k) {
       if (f1 == f0) break;
       const double x2 = x1 - f1 * (x1 - x0) / (f1 - f0);
       x0 = x1; f0 = f1; x1 = x2;
-      bk_cdf(tb, J, h, x1, F, dF);
+      bk_cdf(tb, p.ord.ft, J, h, x1, F, dF);
       f1 = F - u;
       ++iters;
     }
