@@ -357,7 +357,7 @@ struct BesselOrder {
   double r_asym;    // |w| from which the Hankel expansion is used
   // device: tables filled by bk_fill_order_tables in shared memory (the order is fixed per launch), 0 on the host
   //   series: groups of four, R_{k,i} = prod_{m=k}^{k+i-1} 1 / (m (nu + m)), k = 1, 5, 9, ...
-  //   hankel: pairs {b_k, b_k b_{k+1}}, b_k = (4 nu^2 - (2k - 1)^2) / (8 k), k = 1, 3, 5, ...
+  //   hankel: groups of four running products b_k, b_k b_{k+1}, ..., b_k = (4 nu^2 - (2k - 1)^2) / (8 k), k = 1, 5, 9, ...
   unsigned series_saddr, hankel_saddr;
   FastRef ft;       // tables of the elementary functions (saddr 0: the math library)
   unsigned pad_;
@@ -414,43 +414,42 @@ HH_HD cplx bessel_series_sum(const BesselOrder &o, cplx w) {
 }
 
 // Hankel sums s1 = sum (-1)^k a_k / w^k, s2 = sum a_k / w^k, a_k = prod (4 nu^2 - (2j-1)^2) / (8 j), stopped at the
-// smallest term. Device: two terms per iteration from one previous term (1/w^2 formed once), scalings folded into the
-// FMAs of the two sums: 24 instructions per pair (the term-by-term loop issued 45 per term).
+// smallest term. Device: four terms per iteration from one previous term (1/w^2, 1/w^3, 1/w^4 formed once; the table holds the
+// running products of the b_k inside each group of four), scalings folded into the FMAs of the two sums: ~41 instructions
+// per four terms (the term-by-term loop issued 45 per term). A group whose last term is not smaller than the previous
+// group's (the expansion is about to diverge: never for |w| >= r_asym) is left to the term-by-term tail.
 HH_HD void bessel_hankel_sums(const BesselOrder &o, cplx w, cplx &s1, cplx &s2) {
   const cplx iw = crecip(w);
+  const double mu4 = 4.0 * o.nu * o.nu;
   cplx t = mk(1.0);
   s1 = mk(1.0);
   s2 = mk(1.0);
   double last = 1.0;  // |t|^2 of the previous term
+  int k = 1;
 #ifdef __CUDA_ARCH__
-  const cplx iw2 = iw * iw;
+  const cplx iw2 = iw * iw, iw3 = iw2 * iw, iw4 = iw2 * iw2;
   unsigned addr = o.hankel_saddr;
 #pragma unroll 1
-  for (int k = 1; k + 1 < kHankelMaxTerms; k += 2, addr += 16) {
-    double b1, bb;
-    lds_f64x2(addr, b1, bb);
-    const cplx u1 = t * iw, u2 = t * iw2;
-    const cplx t2 = bb * u2;  // a_{k+1} / w^{k+1}
-    const double m2 = cabs2(t2);
-    if (m2 > last) {  // the expansion has started to diverge inside this pair: keep a_k / w^k if it still decreases
-      const cplx t1 = b1 * u1;
-      if (cabs2(t1) <= last) {
-        s1 = s1 - t1;
-        s2 = s2 + t1;
-      }
-      break;
-    }
-    last = m2;
-    s2 = cplx{fma(b1, u1.re, s2.re + t2.re), fma(b1, u1.im, s2.im + t2.im)};
-    s1 = cplx{fma(-b1, u1.re, s1.re + t2.re), fma(-b1, u1.im, s1.im + t2.im)};
-    t = t2;
-    if (m2 < 1e-34) break;
+  for (; k + 3 < kHankelMaxTerms; k += 4, addr += 32) {
+    double b1, b2, b3, b4;
+    lds_f64x2(addr, b1, b2);
+    lds_f64x2(addr + 16, b3, b4);
+    const cplx u1 = t * iw, u2 = t * iw2, u3 = t * iw3, u4 = t * iw4;
+    const cplx t4 = b4 * u4;  // a_{k+3} / w^{k+3}
+    const double m4 = cabs2(t4);
+    if (m4 > last) break;
+    last = m4;
+    t = t4;
+    const cplx ev = cplx{fma(b2, u2.re, t4.re), fma(b2, u2.im, t4.im)};          // the two even-numbered terms (k odd first)
+    const cplx od = cplx{fma(b3, u3.re, b1 * u1.re), fma(b3, u3.im, b1 * u1.im)};  // the two odd-numbered terms
+    s2 = cplx{s2.re + (ev.re + od.re), s2.im + (ev.im + od.im)};
+    s1 = cplx{s1.re + (ev.re - od.re), s1.im + (ev.im - od.im)};
+    if (m4 < 1e-34) return;
   }
-#else
-  const double mu4 = 4.0 * o.nu * o.nu;
-  for (int k = 1; k < kHankelMaxTerms; ++k) {
+#endif
+  for (; k < kHankelMaxTerms; ++k) {
     const double odd = (double)(2 * k - 1);
-    t = (t * iw) * ((mu4 - odd * odd) / (8.0 * (double)k));  // a_k / w^k
+    t = (t * iw) * ((mu4 - odd * odd) * rcp_fast(8.0 * (double)k));  // a_k / w^k
     const double m = cabs2(t);
     if (m > last) break;  // the expansion has started to diverge
     last = m;
@@ -458,7 +457,6 @@ HH_HD void bessel_hankel_sums(const BesselOrder &o, cplx w, cplx &s1, cplx &s2) 
     s2 = s2 + t;
     if (m < 1e-34) break;
   }
-#endif
 }
 
 HH_HD BesselEF besseli_series_ef(const BesselOrder &o, cplx w, double log_aw, double arg_w) {

@@ -270,7 +270,7 @@ __device__ BkInversion bk_sample_integral(const BkParams &p, double V0, double V
 
 // Coefficient tables of the fixed order nu, by all threads of the block (IEEE divisions: once per block).
 //   rk4: groups of four, R_{k,i} = prod_{m=k}^{k+i-1} 1 / (m (nu + m)), k = 1, 5, 9, ...   (bessel_series_sum)
-//   bk2: pairs {b_k, b_k b_{k+1}}, b_k = (4 nu^2 - (2k - 1)^2) / (8 k), k = 1, 3, 5, ...   (bessel_hankel_sums)
+//   bk2: groups of four running products of b_k = (4 nu^2 - (2k - 1)^2) / (8 k), k = 1, 5, 9, ...   (bessel_hankel_sums)
 __device__ __forceinline__ void bk_fill_order_tables(double nu, double *rk4, double *bk2) {
   for (int g = threadIdx.x; g < kSeriesMaxTerms / 4; g += blockDim.x) {
     double r = 1.0;
@@ -280,12 +280,13 @@ __device__ __forceinline__ void bk_fill_order_tables(double nu, double *rk4, dou
       rk4[4 * g + i] = r;
     }
   }
-  for (int g = threadIdx.x; g < kHankelMaxTerms / 2; g += blockDim.x) {
-    const double k1 = (double)(2 * g + 1), k2 = (double)(2 * g + 2);
-    const double o1 = 2.0 * k1 - 1.0, o2 = 2.0 * k2 - 1.0;
-    const double b1 = (4.0 * nu * nu - o1 * o1) / (8.0 * k1), b2 = (4.0 * nu * nu - o2 * o2) / (8.0 * k2);
-    bk2[2 * g] = b1;
-    bk2[2 * g + 1] = b1 * b2;
+  for (int g = threadIdx.x; g < kHankelMaxTerms / 4; g += blockDim.x) {
+    double b = 1.0;
+    for (int i = 0; i < 4; ++i) {
+      const double k = (double)(4 * g + 1 + i), odd = 2.0 * k - 1.0;
+      b *= (4.0 * nu * nu - odd * odd) / (8.0 * k);
+      bk2[4 * g + i] = b;
+    }
   }
 }
 
