@@ -637,12 +637,56 @@ struct BkCf {       // per (V0, VT) pair: HestonCFIterator
   cplx logIk;       // log I_nu(z_kappa)
 };
 
+// log I_nu(x) for real x > 0 (z_kappa, heston.jl:169-173): the same two expansions in real arithmetic — a quarter of the
+// floating-point work of the complex routine, once per transition. The e^{-2x} part of the Hankel form is below
+// 2e-18 relative from r_asym on and is dropped. Orders in (-1, 0) and tiny or non-finite x take the general routine.
+HH_HD double log_besseli_real(const BesselOrder &o, double x) {
+  if (!(x > 1e-300) || !(x < 1e300)) return log_besseli(o, mk(x)).re;
+  if (x < o.r_asym) {
+    const double q = 0.25 * x * x;
+    double term = 1.0, sum = 1.0;
+#ifdef __CUDA_ARCH__
+    const double q2 = q * q, q3 = q2 * q, q4 = q2 * q2;
+    unsigned addr = o.series_saddr;
+#pragma unroll 1
+    for (int g = 0; g < kSeriesMaxTerms / 4; ++g, addr += 32) {
+      double r1, r2, r3, r4;
+      lds_f64x2(addr, r1, r2);
+      lds_f64x2(addr + 16, r3, r4);
+      const double t4 = (term * q4) * r4;
+      sum += fma(term * q, r1, (term * q3) * r3) + fma(term * q2, r2, t4);
+      term = t4;
+      if (term < 1e-17 * sum) break;
+    }
+#else
+    for (int k = 1; k < kSeriesMaxTerms; ++k) {
+      term *= q / ((double)k * (o.nu + (double)k));
+      sum += term;
+      if (term < 1e-17 * sum) break;
+    }
+#endif
+    return o.nu * (flog(o.ft, x) - 0.6931471805599453) - o.lgam_nu1 + flog(o.ft, sum);
+  }
+  const double ix = rcp_fast(x), mu4 = 4.0 * o.nu * o.nu;
+  double t = 1.0, s1 = 1.0, last = 1.0;
+  for (int k = 1; k < kHankelMaxTerms; ++k) {
+    const double odd = (double)(2 * k - 1);
+    t *= -ix * ((mu4 - odd * odd) * rcp_fast(8.0 * (double)k));  // (-1)^k a_k / x^k
+    const double m = fabs(t);
+    if (m > last) break;
+    last = m;
+    s1 += t;
+    if (m < 1e-17) break;
+  }
+  return x - 0.5 * (1.8378770664093453 + flog(o.ft, x)) + flog(o.ft, s1);  // log(2 pi)
+}
+
 HH_HD BkCf bk_cf_init(const BkParams &p, double V0, double VT) {
   BkCf it;
-  it.sv = sqrt(V0 * VT);
+  it.sv = sqrt_fast(V0 * VT);
   it.vsum_s = (V0 + VT) / p.xi2;
   it.sv4_xi2 = it.sv * 4.0 / p.xi2;
-  it.logIk = log_besseli(p.ord, mk(it.sv * p.wk));
+  it.logIk = mk(p.ord.nu >= 0.0 ? log_besseli_real(p.ord, it.sv * p.wk) : log_besseli(p.ord, mk(it.sv * p.wk)).re);
   return it;
 }
 

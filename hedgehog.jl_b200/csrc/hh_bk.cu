@@ -11,7 +11,8 @@
 // One trajectory per thread, all dates in registers. Per transition the thread
 //   1. draws V' (noncentral chi-square: chi2(d-1) + (Z + sqrt(lambda))^2 for d > 1, Poisson mixture otherwise;
 //      gamma variates by Marsaglia-Tsang) from its own Philox counter stream,
-//   2. evaluates the characteristic function of int V at +-h0, 0 (finite-difference moments, as the reference),
+//   2. evaluates the characteristic function of int V at +h0 (finite-difference moments of the reference through
+//      Phi(0) = 1, Phi(-a) = conj Phi(a)),
 //   3. evaluates Phi(h j) ONCE per term into a shared-memory table c_j = (2/pi) Re Phi(h j) / j — the reference
 //      recomputes the whole series (one complex Bessel function per term) for every root-finder iteration although
 //      it does not depend on x (sample_from_cf.jl:38, 84-93); terms beyond the table spill to a global slab,
@@ -182,13 +183,16 @@ __device__ __noinline__ void bk_cdf(const BkTable &tb, FastRef ft, int J, double
 __device__ BkInversion bk_sample_integral(const BkParams &p, double V0, double VT, double u, const BkTable &tb) {
   BkInversion r;
   const BkCf it = bk_cf_init(p, V0, VT);
-  // moments_from_cf :50-64 — the three evaluations share the unwrapping state, in the reference's order
+  // moments_from_cf :50-64 differences Phi at +h0, 0, -h0. A characteristic function has Phi(0) = 1 and
+  // Phi(-a) = conj Phi(a), so ONE evaluation gives the same central differences: mean = Im Phi(h0) / h0,
+  // var = (2 - 2 Re Phi(h0)) / h0^2 - mean^2. The reference's three evaluations carry that identity only to rounding, and
+  // its second difference amplifies the rounding of Phi(0) by 1 / h0^2 = 1e4 (its variance scatters by ~1e-4 relative
+  // between machines and libraries, tests/test_gpu_bk.py); this form is inside that scatter and saves two of the
+  // ~16 Bessel evaluations of a transition.
   double th = nan("");
   const cplx pp = bk_chf(p, it, p.h_fd, th);
-  const cplx p0 = bk_chf(p, it, 0.0, th);
-  const cplx pm = bk_chf(p, it, -p.h_fd, th);
-  const double mean = (pp.im - pm.im) / (2.0 * p.h_fd);                                  // real(-i (pp - pm) / 2h)
-  const double var = -(pp.re - 2.0 * p0.re + pm.re) / (p.h_fd * p.h_fd) - mean * mean;  // :60-61
+  const double mean = pp.im / p.h_fd;                                                    // real(-i (pp - pm) / 2h)
+  const double var = (2.0 - 2.0 * pp.re) / (p.h_fd * p.h_fd) - mean * mean;              // :60-61
   const double s2 = fmax(var, 1e-12);                                                    // :32
   const double sd = sqrt(s2);
   const double ns = mean + sd * normcdfinv(u);                                           // :33
