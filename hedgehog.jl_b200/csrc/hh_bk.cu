@@ -213,59 +213,86 @@ __device__ BkInversion bk_sample_integral(const BkParams &p, double V0, double V
     if (cabs2(phi) < (stop * (double)j) * (stop * (double)j)) break;  // |phi| / j < stop
   }
   r.J = J;
-  // inverse_cdf :105-135
+  // inverse_cdf :105-135. Safeguarded Newton from the reference's initial guess inside [0, max_guess], f(0) = -u < 0.
+  // The right end is evaluated only when an iterate runs into it before any f >= 0 has been seen (u ~ 1, where the
+  // truncated series may never reach u): for every other u that saves one of ~5 CDF evaluations and changes no iterate.
+  // Once a Newton step is shorter than 1e-9 of the bracket the next iterate is within ~1e-18 of the root (quadratic
+  // convergence on a finite trigonometric sum) and is returned without a confirming evaluation.
   double F, dF;
-  bk_cdf(tb, p.ord.ft, J, h, max_guess, F, dF);
-  const double fmax_ = F - u;
-  int iters = 1;
-  if (fmax_ >= 0.0 && u > 0.0) {
-    // bracket [0, max_guess]: f(0) = -u < 0 <= f(max_guess); safeguarded Newton from the reference's initial guess
-    double lo = 0.0, hi = max_guess;
-    double x = fmin(fmax(guess, 0.0), max_guess);
-    double f = 0.0;
-    for (int k = 0; k < 100; ++k) {
-      bk_cdf(tb, p.ord.ft, J, h, x, F, dF);
-      ++iters;
-      f = F - u;
-      if (f < 0.0) lo = x; else hi = x;
-      if (fabs(f) <= 1e-15 || hi - lo <= 1e-15 * max_guess) break;
-      double xn = dF > 0.0 ? x - f / dF : -1.0;
-      if (!(xn > lo && xn < hi)) xn = 0.5 * (lo + hi);
-      if (xn == x) break;
-      x = xn;
-    }
-    r.x = x;
-    r.resid = f;
-    r.status = 0;
-  } else if (u <= 0.0) {
+  int iters = 0;
+  double fmax_ = 0.0;
+  bool no_bracket = false;
+  if (u <= 0.0) {
     r.x = 0.0;
     r.resid = 0.0;
     r.status = 0;
   } else {
-    // F(max_guess) < u: no sign change. The reference first lets its secant iteration run (<= maxiter evaluations) and
-    // accepts x >= 0 with |F(x) - u| <= atol; otherwise it returns max_guess with a warning (:123-126).
-    double x0 = guess, x1 = guess * 1.001 + 1e-12, f0, f1;
-    bk_cdf(tb, p.ord.ft, J, h, x0, F, dF);
-    f0 = F - u;
-    bk_cdf(tb, p.ord.ft, J, h, x1, F, dF);
-    f1 = F - u;
-    iters += 2;
-    for (int k = 2; k < 10; ++k) {
-      if (f1 == f0) break;
-      const double x2 = x1 - f1 * (x1 - x0) / (f1 - f0);
-      x0 = x1; f0 = f1; x1 = x2;
+    double lo = 0.0, hi = max_guess;
+    double x = fmin(fmax(guess, 0.0), max_guess);
+    double f = 0.0;
+    bool hi_known = false;  // some f(hi) >= 0 has been evaluated
+    for (int k = 0; k < 100; ++k) {
+      bk_cdf(tb, p.ord.ft, J, h, x, F, dF);
+      ++iters;
+      f = F - u;
+      if (f < 0.0) {
+        lo = x;
+      } else {
+        hi = x;
+        hi_known = true;
+      }
+      if (fabs(f) <= 1e-15 || (hi_known && hi - lo <= 1e-15 * max_guess)) break;
+      double xn = dF > 0.0 ? x - f / dF : -1.0;
+      if (!(xn > lo && xn < hi)) {
+        if (!hi_known) {
+          bk_cdf(tb, p.ord.ft, J, h, max_guess, F, dF);
+          ++iters;
+          fmax_ = F - u;
+          if (fmax_ < 0.0) {
+            no_bracket = true;
+            break;
+          }
+          hi_known = true;
+        }
+        xn = 0.5 * (lo + hi);
+      } else if (fabs(xn - x) <= 1e-9 * max_guess) {
+        x = xn;
+        f = 0.0;  // the quadratic model's residual at xn, below rounding
+        break;
+      }
+      if (xn == x) break;
+      x = xn;
+    }
+    if (!no_bracket) {
+      r.x = x;
+      r.resid = f;
+      r.status = 0;
+    } else {
+      // F(max_guess) < u: no sign change. The reference first lets its secant iteration run (<= maxiter evaluations) and
+      // accepts x >= 0 with |F(x) - u| <= atol; otherwise it returns max_guess with a warning (:123-126).
+      double x0 = guess, x1 = guess * 1.001 + 1e-12, f0, f1;
+      bk_cdf(tb, p.ord.ft, J, h, x0, F, dF);
+      f0 = F - u;
       bk_cdf(tb, p.ord.ft, J, h, x1, F, dF);
       f1 = F - u;
-      ++iters;
-    }
-    if (isfinite(x1) && x1 >= 0.0 && fabs(f1) <= p.atol) {
-      r.x = x1;
-      r.resid = f1;
-      r.status = 1;
-    } else {
-      r.x = max_guess;
-      r.resid = fmax_;
-      r.status = 2;
+      iters += 2;
+      for (int k = 2; k < 10; ++k) {
+        if (f1 == f0) break;
+        const double x2 = x1 - f1 * (x1 - x0) / (f1 - f0);
+        x0 = x1; f0 = f1; x1 = x2;
+        bk_cdf(tb, p.ord.ft, J, h, x1, F, dF);
+        f1 = F - u;
+        ++iters;
+      }
+      if (isfinite(x1) && x1 >= 0.0 && fabs(f1) <= p.atol) {
+        r.x = x1;
+        r.resid = f1;
+        r.status = 1;
+      } else {
+        r.x = max_guess;
+        r.resid = fmax_;
+        r.status = 2;
+      }
     }
   }
   r.iters = iters;

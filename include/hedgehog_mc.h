@@ -324,7 +324,8 @@ int hh_bk_elementary(hh_ctx *ctx, int kind, const double *x, const double *y, in
 /* sample_from_cf (sample_from_cf.jl:27-41) for n independent (V0, VT, u) triples, u = the uniform the reference draws
  * at :29. out8[i] = {x = sampled integral of V, mean, variance (moments_from_cf :50-64), h (:37), J = number of series
  * terms (:84-93), status (0 root inside [0, max_guess], 1 secant accepted without a bracket, 2 fell back to max_guess),
- * F(x) - u, number of CDF evaluations}. cfg NULL = reference defaults. */
+ * F(x) - u (0 when the last Newton step was below 1e-9 of the bracket: F is not re-evaluated at the returned x),
+ * number of CDF evaluations}. cfg NULL = reference defaults. */
 int hh_bk_integral(hh_ctx *ctx, const hh_model *model, double tau, const hh_bk_config *cfg, const double *V0,
                    const double *VT, const double *u, int n, double *out8);
 /* sample_V_T (heston.jl:125-133): VT[i] = c * NoncentralChisq(d, lambda(V0[i])), one draw per i from Philox key `seed`. */
