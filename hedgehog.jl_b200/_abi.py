@@ -20,7 +20,7 @@ HH_ERR_COMM = 3
 
 HH_MODEL_GBM, HH_MODEL_HESTON = 0, 1
 HH_SCHEME_EM, HH_SCHEME_EXACT_TERMINAL, HH_SCHEME_EXACT_STEPS, HH_SCHEME_HESTON_BK = 0, 1, 2, 3
-HH_VR_NONE, HH_VR_ANTITHETIC = 0, 1
+HH_VR_NONE, HH_VR_ANTITHETIC, HH_VR_QUASI_RANDOM = 0, 1, 2
 HH_PREC_F64, HH_PREC_F32 = 0, 1
 HH_RNG_PHILOX, HH_RNG_NORMALS, HH_RNG_PHILOX_64 = 0, 1, 2
 HH_FLAG_SPLIT_STEP, HH_FLAG_Q1_SQRT_MEAN = 1, 2

@@ -157,6 +157,7 @@ class LognormalDynamics: pass
 class HestonDynamics: pass
 class NoVarianceReduction: pass
 class Antithetic: pass
+class QuasiRandom: pass   # HH_VR_QUASI_RANDOM: randomised van der Corput points in the one-draw exact sampler (roadmap :164)
 class EulerMaruyama: pass
 class HestonBroadieKaya: pass
 class BlackScholesExact: pass
@@ -308,7 +309,8 @@ def _sim_of(method: MonteCarlo, scheme: int, shard=None) -> SimSpec:
         n, off = hi - lo, lo
     sim = SimSpec(n_paths=n, path_offset=off, scheme=scheme,
                   n_steps=cfg.steps if (not exact or method.bk_steps_from_config) else 1,
-                  vr=abi.HH_VR_ANTITHETIC if isinstance(cfg.variance_reduction, Antithetic) else abi.HH_VR_NONE,
+                  vr=(abi.HH_VR_ANTITHETIC if isinstance(cfg.variance_reduction, Antithetic) else
+                      abi.HH_VR_QUASI_RANDOM if isinstance(cfg.variance_reduction, QuasiRandom) else abi.HH_VR_NONE),
                   precision=abi.HH_PREC_F32 if method.precision == "f32" else abi.HH_PREC_F64)
     if method.rng not in ("philox", "philox64"):
         raise ValueError(f"unknown rng {method.rng!r} (philox | philox64)")

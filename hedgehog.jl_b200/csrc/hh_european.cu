@@ -61,7 +61,18 @@ struct EuroArgs {
   //   dd = delta_path(S0 + eps) - delta_path(S0 - eps),  delta_path = cp 1{cp (S - K) > 0} S / S0   -> gamma_pw = D mean(dd) / (2 eps)
   int g_on;
   double g_up, g_dn, g_iu, g_id;  // (S0 + eps) / S0, (S0 - eps) / S0, 1 / (S0 + eps), 1 / (S0 - eps)
+  // HH_VR_QUASI_RANDOM (K_GBM_TERMINAL): randomised van der Corput points instead of Philox normals
+  int qmc;
+  uint64_t qmc_shift;  // Cranley-Patterson rotation on the 2^-64 grid, from base_seed (qmc_shift_of)
 };
+
+// splitmix64 (Steele, Lea & Flood 2014) of the seed: the rotation of the quasi-random points. Restated in oracle/oracle.py.
+__host__ __device__ inline uint64_t qmc_shift_of(uint64_t seed) {
+  uint64_t z = seed + 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
 
 // second-order contributions of one terminal spot at one strike
 __device__ __forceinline__ void gamma_terms(const EuroArgs &a, double sp, double ep, double cp, double strike, double &s2, double &dd) {
@@ -172,8 +183,16 @@ __device__ __forceinline__ void simulate(const EuroArgs &a, const PathParams<T> 
     // marginal_law + final_sample, montecarlo.jl:293-303, 384-390
     NormalSource src(a, tb, parity, i, 1);
     double z1, z2;
-    if (parity) z1 = src.z[0];
-    else src.pair(false, 0, z1, z2);
+    if (parity) {
+      z1 = src.z[0];
+    } else if (a.qmc) {
+      // u = frac(van der Corput_2(g) + shift) on the 2^-64 grid (the addition wraps), taken at the midpoints of the
+      // 2^-53 grid so that 0 < u < 1; g = global trajectory index
+      const uint64_t pt = __brevll((uint64_t)(a.path_offset + i)) + a.qmc_shift;
+      z1 = normcdfinv(((double)(pt >> 11) + 0.5) * 0x1p-53);
+    } else {
+      src.pair(false, 0, z1, z2);
+    }
     const T X = fma_(p.sd, z1, p.mu);
     Sp = exp_(X);
     if (ANTI) Sm = exp_(p.mu * 2.0 - X);
@@ -1226,8 +1245,12 @@ int validate_model_sim(hh_ctx *ctx, const hh_model *m, const hh_sim *s) {
   if (s->n_paths <= 0) return ctx->fail(HH_ERR_ARG, "n_paths must be positive (got %lld)", (long long)s->n_paths);
   if (s->scheme != HH_SCHEME_EXACT_TERMINAL && s->n_steps <= 0)
     return ctx->fail(HH_ERR_ARG, "n_steps must be positive (got %d)", s->n_steps);
-  if (s->vr != HH_VR_NONE && s->vr != HH_VR_ANTITHETIC)
+  if (s->vr != HH_VR_NONE && s->vr != HH_VR_ANTITHETIC && s->vr != HH_VR_QUASI_RANDOM)
     return ctx->fail(HH_ERR_ARG, "unknown variance reduction %d", s->vr);
+  if (s->vr == HH_VR_QUASI_RANDOM && !(m->kind == HH_MODEL_GBM && s->scheme == HH_SCHEME_EXACT_TERMINAL &&
+                                       s->rng_mode == HH_RNG_PHILOX && s->precision == HH_PREC_F64 && !s->seeds))
+    return ctx->fail(HH_ERR_UNSUPPORTED, "HH_VR_QUASI_RANDOM is defined for the one-draw exact sampler (LognormalDynamics + "
+                                         "BlackScholesExact, European), in-kernel stream keyed by base_seed, f64");
   if (s->rng_mode != HH_RNG_NORMALS && s->rng_mode != HH_RNG_PHILOX && s->rng_mode != HH_RNG_PHILOX_64)
     return ctx->fail(HH_ERR_ARG, "unknown rng_mode %d", s->rng_mode);
   if (s->rng_mode == HH_RNG_NORMALS && !s->normals)
@@ -1573,6 +1596,8 @@ static int build_args(hh_ctx *ctx, const hh_model *m, const hh_sim *s, const hh_
   a.f32_one = 0x3F800000u;
   a.lo_fill = 0x00080000u;
   a.rng64 = s->rng_mode == HH_RNG_PHILOX_64;
+  a.qmc = s->vr == HH_VR_QUASI_RANDOM;
+  a.qmc_shift = qmc_shift_of(s->base_seed);
   PathParams<double> &p = a.p;
   const double dt = m->T / nsteps;  // montecarlo.jl:349
   const double sqdt = sqrt(dt);

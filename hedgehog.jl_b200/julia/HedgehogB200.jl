@@ -32,7 +32,7 @@ using ForwardDiff: Dual, Partials, value, partials
 using Libdl
 
 export B200MonteCarlo, B200LSM, b200_library!, AsianOption, BarrierOption, DigitalOption, solve_with_bs_control,
-       peer_export, peer_connect
+       peer_export, peer_connect, QuasiRandom
 
 # ---- library handle -----------------------------------------------------------------------------------------------
 const LIB = Ref{String}(get(ENV, "HEDGEHOG_MC_LIB", joinpath(@__DIR__, "..", "libhedgehog_mc.so")))
@@ -249,6 +249,9 @@ scheme_of(::BlackScholesExact, for_lsm) = for_lsm ? HH_SCHEME_EXACT_STEPS : HH_S
 scheme_of(::HestonBroadieKaya, for_lsm) = HH_SCHEME_HESTON_BK
 vr_of(::NoVarianceReduction) = Cint(0)
 vr_of(::Antithetic) = Cint(1)
+# randomised van der Corput points in the one-draw exact sampler (HH_VR_QUASI_RANDOM; roadmap "quasi-random", not in Hedgehog)
+struct QuasiRandom <: Hedgehog.VarianceReductionStrategy end
+vr_of(::QuasiRandom) = Cint(2)
 
 # this process's share [lo, hi) of the job's trajectories (contiguous blocks of the global index, SURVEY 8e)
 shard(method::B200MonteCarlo) = (N = method.config.trajectories;

@@ -58,6 +58,14 @@ extern "C" {
 /* variance reduction                                           montecarlo.jl:36,43 */
 #define HH_VR_NONE 0
 #define HH_VR_ANTITHETIC 1
+/* Quasi-random sampling of the one-draw exact sampler (roadmap "Stratified sampling / quasi-random",
+ * docs/src/derivatives_pricing_roadmap.md:164; not in the reference): HH_SCHEME_EXACT_TERMINAL only. Trajectory g (GLOBAL
+ * index: path_offset + i, so the points do not depend on how the job is sharded) takes the base-2 van der Corput point of g
+ * under one Cranley-Patterson rotation derived from base_seed,
+ *     u_g = frac(bitreverse64(g) 2^-64 + shift(base_seed)),   Z_g = Phi^-1(u_g)   (midpoints of the 2^-53 grid),
+ * instead of a pseudo-random normal: an unbiased estimator whose error falls like log N / N. hh_result.std_error is still
+ * the plain sample standard error: an UPPER bound here (the points are not independent). */
+#define HH_VR_QUASI_RANDOM 2
 
 #define HH_PREC_F64 0
 #define HH_PREC_F32 1 /* fast mode (Heston Euler-Maruyama, in-kernel RNG): f32 state and normals from 32-bit uniforms, \

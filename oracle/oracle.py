@@ -30,7 +30,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 HH_OK, HH_ERR_ARG, HH_ERR_UNSUPPORTED = 0, -1, -2
 HH_MODEL_GBM, HH_MODEL_HESTON = 0, 1
 HH_SCHEME_EM, HH_SCHEME_EXACT_TERMINAL, HH_SCHEME_EXACT_STEPS, HH_SCHEME_HESTON_BK = 0, 1, 2, 3
-HH_VR_NONE, HH_VR_ANTITHETIC = 0, 1
+HH_VR_NONE, HH_VR_ANTITHETIC, HH_VR_QUASI_RANDOM = 0, 1, 2
 HH_PREC_F64, HH_PREC_F32 = 0, 1
 HH_RNG_PHILOX, HH_RNG_NORMALS, HH_RNG_PHILOX_64 = 0, 1, 2
 HH_FLAG_SPLIT_STEP, HH_FLAG_Q1_SQRT_MEAN = 1, 2
@@ -229,6 +229,26 @@ def normal_pair64(key, idx, step):
     a, b = C.c_double(), C.c_double()
     lib().hho_normal_pair64(key, idx, step, C.byref(a), C.byref(b))
     return a.value, b.value
+
+
+def quasi_random_normals(base_seed: int, path_offset: int, n: int) -> np.ndarray:
+    """Restatement of HH_VR_QUASI_RANDOM (include/hedgehog_mc.h): Z_g = Phi^-1(u_g), u_g the base-2 van der Corput point of the
+    global trajectory index g under the splitmix64(base_seed) rotation, at the midpoints of the 2^-53 grid. The oracle's
+    exact-terminal sampler consumes them in parity mode (rng_mode = HH_RNG_NORMALS)."""
+    from scipy.special import ndtri
+    M = (1 << 64) - 1
+    z = (int(base_seed) + 0x9E3779B97F4A7C15) & M
+    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & M
+    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & M
+    shift = z ^ (z >> 31)
+    g = np.arange(path_offset, path_offset + n, dtype=np.uint64)
+    r = np.zeros(n, dtype=np.uint64)
+    for b in range(64):   # 64-bit bit reversal
+        r |= ((g >> np.uint64(b)) & np.uint64(1)) << np.uint64(63 - b)
+    with np.errstate(over="ignore"):
+        pt = r + np.uint64(shift)   # wraps modulo 2^64
+    u = ((pt >> np.uint64(11)).astype(np.float64) + 0.5) * 2.0 ** -53
+    return ndtri(u)
 
 
 def _raise(rc, what):
