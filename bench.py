@@ -472,6 +472,11 @@ def run_configs(hh, eng, scale, fp64_peak, hbm_peak, hbm_peak_source, anchors, n
     sol, w = _wall(lambda: hh.solve(p, lsm, engine=eng, stopping_info=False), 3)
     _, w_info = _wall(lambda: hh.solve(p, lsm, engine=eng, stopping_info="arrays"), 2)
     kms = sol.stats["kernel_ms"]
+    # opt-in: the generator on the HH_RNG_PHILOX_64 stream (one Philox block per FOUR steps); reported beside, never as `value`
+    lsm64 = hh.LSM(hh.MonteCarlo(hh.LognormalDynamics(), hh.BlackScholesExact(), hh.SimulationConfig(n, steps=50, base_seed=12345),
+                                 rng="philox64"), 3)
+    hh.solve(p, lsm64, engine=eng, stopping_info=False)
+    sol64, _ = _wall(lambda: hh.solve(p, lsm64, engine=eng, stopping_info=False), 3)
     gbs = n * 50 * LSM_BYTES_PER_PATH_DATE / (kms * 1e-3) / 1e9
     kc = ncu_consts.get("lsm_backward_kernel<3, 0>") or {}
     crr, berm = anchors.get("c3_crr_american_put_1000"), anchors.get("c3_crr_bermudan_put_50_dates")
@@ -490,6 +495,10 @@ def run_configs(hh, eng, scale, fp64_peak, hbm_peak, hbm_peak_source, anchors, n
                               "backward_only": {"achieved": n * 49 * 24.0 / (sol.stats["regress_ms"] * 1e-3) / 1e9,
                                                 "convention": "24 B per path-date of the induction alone (the cash-flow vector is "
                                                               "served from the persisting L2 window, so DRAM sees ~16 B)"}},
+                 "philox64": {"kernel_ms": sol64.stats["kernel_ms"], "path_ms": sol64.stats["path_ms"], "price": sol64.price,
+                              "roofline_frac_algorithmic": n * 50 * LSM_BYTES_PER_PATH_DATE / (sol64.stats["kernel_ms"] * 1e-3) / 1e9 / hbm_peak,
+                              "note": "HH_RNG_PHILOX_64 in the path generator (opt-in): one Philox4x32-10 block per FOUR steps, "
+                                      "restated in the oracle (tests/test_gpu_lsm.py::test_lsm_philox64_stream_matches_oracle)"},
                  "check": {"price": sol.price, "std_error": sol.std_error, "crr_american_1000_steps": crr,
                            "crr_bermudan_50_dates": berm, "rel_diff_vs_crr": (sol.price - crr) / crr if crr else None,
                            "z_vs_bermudan": (sol.price - berm) / sol.std_error if berm else None,

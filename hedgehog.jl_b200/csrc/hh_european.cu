@@ -1255,9 +1255,13 @@ int validate_model_sim(hh_ctx *ctx, const hh_model *m, const hh_sim *s) {
     return ctx->fail(HH_ERR_ARG, "unknown rng_mode %d", s->rng_mode);
   if (s->rng_mode == HH_RNG_NORMALS && !s->normals)
     return ctx->fail(HH_ERR_ARG, "rng_mode = HH_RNG_NORMALS needs a normals buffer");
-  if (s->rng_mode == HH_RNG_PHILOX_64 &&
-      !(m->kind == HH_MODEL_HESTON && s->scheme == HH_SCHEME_EM && s->precision == HH_PREC_F64))
-    return ctx->fail(HH_ERR_UNSUPPORTED, "HH_RNG_PHILOX_64 is defined for HestonDynamics + EulerMaruyama in f64");
+  if (s->rng_mode == HH_RNG_PHILOX_64 && s->precision == HH_PREC_F64 && m->kind == HH_MODEL_GBM &&
+      s->scheme == HH_SCHEME_EXACT_STEPS) {
+    // the LSM path generator's form of the stream (hh_lsm.cu); every other entry point rejects it below
+  } else if (s->rng_mode == HH_RNG_PHILOX_64 &&
+             !(m->kind == HH_MODEL_HESTON && s->scheme == HH_SCHEME_EM && s->precision == HH_PREC_F64))
+    return ctx->fail(HH_ERR_UNSUPPORTED, "HH_RNG_PHILOX_64 is defined for HestonDynamics + EulerMaruyama in f64 (European "
+                                         "pricing) and for the exact GBM generator of hh_lsm_american");
   // the lengths behind the caller's pointers (the copies below read exactly this many elements)
   if (s->rng_mode == HH_RNG_NORMALS) {
     const uint64_t ncomp = m->kind == HH_MODEL_HESTON ? 2 : 1;
@@ -1699,6 +1703,9 @@ int european_launch(hh_ctx *ctx, const hh_model *m, const hh_sim *s, const hh_pa
   if (npay < 1 || npay > kThreads || !payoffs)
     return ctx->fail(HH_ERR_ARG, "npayoffs must be in [1, %d] (got %d)", kThreads, npay);
   if (s->scheme == HH_SCHEME_HESTON_BK) return ctx->fail(HH_ERR_UNSUPPORTED, "use the Broadie-Kaya driver");
+  if (s->rng_mode == HH_RNG_PHILOX_64 && m->kind != HH_MODEL_HESTON)
+    return ctx->fail(HH_ERR_UNSUPPORTED, "HH_RNG_PHILOX_64 prices HestonDynamics + EulerMaruyama; under LognormalDynamics it is the "
+                                         "LSM path generator's stream only");
   if (s->precision == HH_PREC_F32 && (m->kind != HH_MODEL_HESTON || s->scheme != HH_SCHEME_EM || s->rng_mode != HH_RNG_PHILOX))
     return ctx->fail(HH_ERR_UNSUPPORTED, "the f32 fast mode covers Heston Euler-Maruyama with the in-kernel RNG (config C2)");
   if (s->precision != HH_PREC_F64 && s->precision != HH_PREC_F32) return ctx->fail(HH_ERR_ARG, "unknown precision %d", s->precision);

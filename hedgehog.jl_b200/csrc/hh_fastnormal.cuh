@@ -309,6 +309,19 @@ __device__ __forceinline__ void fast_normal_pair_v2(const char *__restrict__ log
   z1 = rad * c;
   z2 = rad * s_;
 }
+// The same pair from 64 random bits (HH_RNG_PHILOX_64: 32-bit angle word wa, 32-bit radius word wb; see above)
+__device__ __forceinline__ void fast_normal_pair64_v2(const char *__restrict__ log_lane, const char *__restrict__ exp_biased,
+                                                      const char *__restrict__ trig_lane, uint32_t wa, uint32_t wb,
+                                                      uint32_t one_hi, uint32_t magic_hi, double &z1, double &z2) {
+  const double R2 = fast_neg2log_32(log_lane, exp_biased, wb, one_hi, 0x00080000u);
+  double sn, cs;
+  const uint32_t poff = fast_angle_v2(wa, wa, magic_hi, sn, cs) >> 1;  // j * 128
+  const double2 t = *reinterpret_cast<const double2 *>(trig_lane + poff);
+  const double rad = fast_sqrt_pos5(max_tiny_hi(R2));
+  const double c = fma(t.x, cs, -(t.y * sn)), s_ = fma(t.y, cs, t.x * sn);
+  z1 = rad * c;
+  z2 = rad * s_;
+}
 constexpr int kTrigRepBytes = tables::kTrigN * kRep * 16;  // 32 KB
 
 // sqrt(x), x in [1e-300, 1e300]: MUFU.RSQ64H seed y0 (2^-22.9), then s = s0 (1 + e + 3/2 e^2) with s0 = x y0,

@@ -59,7 +59,10 @@ constexpr int kLsmPathThreads = 512;
 
 // SMALL: the host has proven |(r - s^2/2) dt +- s sqrt(dt) z| <= 1/2 for every normal the in-kernel stream can produce
 // (|z| <= 8.6), so fast_expm1_small runs without its range test (never with caller-supplied normals).
-template <bool ANTI, bool PARITY, bool UKEY, bool SMALL>
+// R64: the opt-in HH_RNG_PHILOX_64 stream — 64 random bits per Box-Muller pair (hh_fastnormal.cuh), i.e. ONE Philox block
+// per FOUR steps: steps 4b .. 4b+3 take the pairs of words (0, 1) and (2, 3) of block b (counter stream word 2), which is
+// hho_normal_pair64(key, idx, n >> 1) component n & 1 in the oracle.
+template <bool ANTI, bool PARITY, bool UKEY, bool SMALL, bool R64>
 __global__ void __launch_bounds__(kLsmPathThreads, 2) lsm_paths_kernel(const LsmPathArgs a) {
   extern __shared__ __align__(16) unsigned char dsm[];
   char *s_log = reinterpret_cast<char *>(dsm);
@@ -93,20 +96,25 @@ __global__ void __launch_bounds__(kLsmPathThreads, 2) lsm_paths_kernel(const Lsm
     double *gm = a.grid + a.n + i;
     gp[0] = Sp;
     if (ANTI) gm[0] = Sm;
+    constexpr int NB = R64 ? 4 : 2;  // steps per Philox block
 #pragma unroll 1
-    for (int n = 0; n < M; n += 2) {
-      double za, zb;
+    for (int n = 0; n < M; n += NB) {
+      double zq[NB];
       if (PARITY) {
-        za = z[n];
-        zb = n + 1 < M ? z[n + 1] : 0.0;
+#pragma unroll
+        for (int h = 0; h < NB; ++h) zq[h] = n + h < M ? z[n + h] : 0.0;
+      } else if (R64) {
+        const u32x4 w = philox4x32_10_rk((uint32_t)idx, (uint32_t)(idx >> 32), (uint32_t)(n >> 2), 2u, UKEY ? a.rk : rk_own);
+        fast_normal_pair64_v2(log_lane, exp_biased, trig_lane, w.x, w.y, a.one_hi, a.magic_hi, zq[0], zq[1]);
+        fast_normal_pair64_v2(log_lane, exp_biased, trig_lane, w.z, w.w, a.one_hi, a.magic_hi, zq[NB - 2], zq[NB - 1]);
       } else {
         const u32x4 w = philox4x32_10_rk((uint32_t)idx, (uint32_t)(idx >> 32), (uint32_t)(n >> 1), 0u, UKEY ? a.rk : rk_own);
-        fast_normal_pair_v2(log_lane, exp_biased, trig_lane, w.x, w.y, w.z, w.w, a.one_hi, a.magic_hi, za, zb);
+        fast_normal_pair_v2(log_lane, exp_biased, trig_lane, w.x, w.y, w.z, w.w, a.one_hi, a.magic_hi, zq[0], zq[1]);
       }
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
+      for (int h = 0; h < NB; ++h) {
         if (n + h < M) {
-          const double zz = h ? zb : za;
+          const double zz = zq[h];
           // GeometricBrownianMotionProcess increment [upstream]: S += S (exp((r - s^2/2) dt + s sqrt(dt) Z) - 1)
           Sp = fma(Sp, fast_expm1_small<!SMALL>(s_exp, fma(a.sig_sqdt, zz, a.dt_drift)), Sp);
           gp += a.stride;
@@ -1187,7 +1195,9 @@ int lsm_american(hh_ctx *ctx, const hh_model *m, const hh_sim *s, const hh_payof
   if (rc) return rc;
   if (!payoff || !out) return ctx->fail(HH_ERR_ARG, "payoff/out is NULL");
   if (ctx->pend.active) return ctx->fail(HH_ERR_ARG, "a European launch is pending on this context: collect it first");
-  if (s->rng_mode == HH_RNG_PHILOX_64) return ctx->fail(HH_ERR_UNSUPPORTED, "HH_RNG_PHILOX_64 covers European pricing only");
+  if (s->rng_mode == HH_RNG_PHILOX_64 && !(m->kind == HH_MODEL_GBM && s->scheme == HH_SCHEME_EXACT_STEPS))
+    return ctx->fail(HH_ERR_UNSUPPORTED, "HH_RNG_PHILOX_64 under LSM is defined for the exact GBM generator "
+                                         "(LognormalDynamics + BlackScholesExact): four steps per Philox block");
   if (degree < 0 || degree > kLsmMaxDeg) return ctx->fail(HH_ERR_ARG, "degree must be in [0, %d] (got %d)", kLsmMaxDeg, degree);
   // Q7: the reference reads component 1 of the saved state as the spot (least_squares_montecarlo.jl:53), which is
   // only true for the S-space BlackScholesExact generator — the only LSM configuration it tests.
@@ -1346,17 +1356,19 @@ int lsm_american(hh_ctx *ctx, const hh_model *m, const hh_sim *s, const hh_payof
     cudaError_t le = cudaSuccess;
     // the largest exponent argument the in-kernel stream can produce: |z| <= sqrt(-2 ln 2^-52) = 8.49
     const bool small = !parity && fabs(pa.dt_drift) + 8.6 * fabs(pa.sig_sqdt) <= 0.5;
-#define HH_LSM_PATHS(A, P, U, S)                                                                                        \
+    const bool r64 = s->rng_mode == HH_RNG_PHILOX_64;
+#define HH_LSM_PATHS(A, P, U, S, R)                                                                                     \
   do {                                                                                                                  \
     static PerDeviceOnce opted;                                                                                         \
-    le = smem_opt_in(opted, lsm_paths_kernel<A, P, U, S>, kLsmPathSmem);                                                \
-    if (le == cudaSuccess) lsm_paths_kernel<A, P, U, S><<<grid_paths, kLsmPathThreads, kLsmPathSmem, st>>>(pa);         \
+    le = smem_opt_in(opted, lsm_paths_kernel<A, P, U, S, R>, kLsmPathSmem);                                             \
+    if (le == cudaSuccess) lsm_paths_kernel<A, P, U, S, R><<<grid_paths, kLsmPathThreads, kLsmPathSmem, st>>>(pa);      \
   } while (0)
-#define HH_LSM_PATHS_S(A, P, U)                                              \
-  do {                                                                       \
-    if (small) HH_LSM_PATHS(A, P, U, true); else HH_LSM_PATHS(A, P, U, false); \
+#define HH_LSM_PATHS_S(A, P, U)                                                                  \
+  do {                                                                                           \
+    if (r64) { if (small) HH_LSM_PATHS(A, P, U, true, true); else HH_LSM_PATHS(A, P, U, false, true); }   \
+    else { if (small) HH_LSM_PATHS(A, P, U, true, false); else HH_LSM_PATHS(A, P, U, false, false); }     \
   } while (0)
-    if (parity) { if (anti) HH_LSM_PATHS(true, true, true, false); else HH_LSM_PATHS(false, true, true, false); }
+    if (parity) { if (anti) HH_LSM_PATHS(true, true, true, false, false); else HH_LSM_PATHS(false, true, true, false, false); }
     else if (ukey) { if (anti) HH_LSM_PATHS_S(true, false, true); else HH_LSM_PATHS_S(false, false, true); }
     else { if (anti) HH_LSM_PATHS_S(true, false, false); else HH_LSM_PATHS_S(false, false, false); }
 #undef HH_LSM_PATHS_S

@@ -77,7 +77,9 @@ extern "C" {
                               feeds TWO steps, each step taking 64 random bits — a 32-bit radius uniform \
                               u1 = 1 - (k + 1/2) 2^-32 and a 32-bit angle theta = 2 pi w 2^-32 — evaluated in f64 by the \
                               same table-driven Box-Muller. Counter stream word 2: never reuses HH_RNG_PHILOX numbers. \
-                              Same law up to the 2^-32 grid (|z| <= 6.7); restated bit for bit in the oracle. */
+                              Same law up to the 2^-32 grid (|z| <= 6.7); restated bit for bit in the oracle. \
+                              hh_lsm_american accepts it for the exact GBM generator (LognormalDynamics + BlackScholesExact): \
+                              one normal per step, so ONE block feeds FOUR steps. */
 
 /* hh_model.flags */
 #define HH_FLAG_SPLIT_STEP 1u   /* EM{split=true}: diffusion evaluated at K = u + dt f(u) [StochasticDiffEq default] */

@@ -152,6 +152,13 @@ static inline void draw(const hh_model *m, const hh_sim *sim, int64_t i, int n, 
     hho_normal_pair64(key, idx, (uint32_t)n, z1, z2);
   } else if (nc == 2) {
     hho_normal_pair(key, idx, (uint32_t)n, 0u, z1, z2);
+  } else if (sim->rng_mode == HH_RNG_PHILOX_64) {
+    /* the exact GBM generator of LSM under the 64-bit stream: one Philox block per FOUR steps — step n takes component
+     * n & 1 of the pair built from 64 bits, hho_normal_pair64(key, idx, n >> 1) (hedgehog.jl_b200/csrc/hh_lsm.cu) */
+    double a, b;
+    hho_normal_pair64(key, idx, (uint32_t)(n >> 1), &a, &b);
+    *z1 = (n & 1) ? b : a;
+    *z2 = 0.0;
   } else {
     double a, b;
     hho_normal_pair(key, idx, (uint32_t)(n >> 1), 0u, &a, &b);
@@ -363,9 +370,11 @@ static int check_args(const hh_model *m, const hh_sim *sim) {
   if (!m || !sim || sim->n_paths <= 0) return HH_ERR_ARG;
   if (sim->scheme != HH_SCHEME_EXACT_TERMINAL && sim->n_steps <= 0) return HH_ERR_ARG;
   if (sim->rng_mode == HH_RNG_NORMALS && !sim->normals) return HH_ERR_ARG;
-  if (sim->rng_mode == HH_RNG_PHILOX_64 &&
-      !(m->kind == HH_MODEL_HESTON && sim->scheme == HH_SCHEME_EM && sim->precision == HH_PREC_F64))
+  if (sim->rng_mode == HH_RNG_PHILOX_64 && sim->precision == HH_PREC_F64 &&
+      !(m->kind == HH_MODEL_HESTON && sim->scheme == HH_SCHEME_EM) &&
+      !(m->kind == HH_MODEL_GBM && sim->scheme == HH_SCHEME_EXACT_STEPS)) /* the latter: the LSM generator's stream */
     return HH_ERR_UNSUPPORTED;
+  if (sim->rng_mode == HH_RNG_PHILOX_64 && sim->precision != HH_PREC_F64) return HH_ERR_UNSUPPORTED;
   if (sim->scheme == HH_SCHEME_HESTON_BK) return HH_ERR_UNSUPPORTED; /* BK oracle lives in oracle/bk_ref.py (scipy AMOS) */
   if (m->kind == HH_MODEL_HESTON && sim->scheme != HH_SCHEME_EM) return HH_ERR_ARG;
   if (m->kind == HH_MODEL_GBM && sim->scheme == HH_SCHEME_HESTON_BK) return HH_ERR_ARG;

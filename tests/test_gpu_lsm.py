@@ -61,6 +61,32 @@ def test_lsm_native_rng_matches_oracle(cuda, oracle, cp, strike):
     _check(*_run_both(cuda, oracle, m, sim, (strike, cp), 4, D))
 
 
+@pytest.mark.parametrize("anti,steps,seeded", [(False, 50, False), (True, 49, False), (False, 7, True), (True, 2, False)])
+def test_lsm_philox64_stream_matches_oracle(cuda, oracle, anti, steps, seeded):
+    """HH_RNG_PHILOX_64 in the exact GBM generator: ONE Philox block per FOUR steps (32-bit radius + 32-bit angle per
+    Box-Muller pair), restated in the oracle as hho_normal_pair64(key, idx, n >> 1) component n & 1. Step counts that are
+    not multiples of four, antithetic columns, per-path keys; stored paths 1e-12, decisions equal up to counted ties."""
+    n = 30_001
+    m = gbm_model(S0=100.0, r=0.05, sigma=0.25, T=0.5)
+    kw = dict(seeds=np.random.Generator(np.random.Philox(5)).integers(0, 2**64, size=n, dtype=np.uint64)) if seeded else dict(base_seed=777)
+    sim = SimSpec(n_paths=n, n_steps=steps, scheme=abi.HH_SCHEME_EXACT_STEPS, vr=int(anti), rng_mode=abi.HH_RNG_PHILOX_64, **kw)
+    g, o = _run_both(cuda, oracle, m, sim, (100.0, -1.0), 3, math.exp(-m.r * m.T / steps))
+    _check(g, o)
+    # a different stream from HH_RNG_PHILOX (counter stream word 2): the same law, other numbers
+    sim0 = SimSpec(n_paths=n, n_steps=steps, scheme=abi.HH_SCHEME_EXACT_STEPS, vr=int(anti), **kw)
+    o0 = cuda.lsm_american(m, sim0, (100.0, -1.0), 3, math.exp(-m.r * m.T / steps))[0]
+    assert g[0].price != o0.price and abs(g[0].price - o0.price) < 5 * (g[0].std_error + o0.std_error)
+
+
+def test_lsm_philox64_is_rejected_where_it_is_not_defined(cuda):
+    with pytest.raises(NotImplementedError):   # European pricing under LognormalDynamics
+        cuda.mc_european(gbm_model(), SimSpec(n_paths=100, n_steps=4, scheme=abi.HH_SCHEME_EXACT_STEPS, rng_mode=abi.HH_RNG_PHILOX_64),
+                         [(100.0, 1.0)], 1.0)
+    with pytest.raises(NotImplementedError):   # LSM with the log-space generators
+        cuda.lsm_american(gbm_model(), SimSpec(n_paths=100, n_steps=4, scheme=abi.HH_SCHEME_EM, rng_mode=abi.HH_RNG_PHILOX_64),
+                          (100.0, -1.0), 2, 0.99)
+
+
 def test_lsm_per_path_seeds(cuda, oracle):
     n, steps = 20_000, 30
     m = gbm_model()

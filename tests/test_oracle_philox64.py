@@ -90,3 +90,22 @@ def test_only_heston_em_f64():
     g.kind, g.S0, g.r, g.T, g.sigma = O.HH_MODEL_GBM, 100.0, 0.05, 1.0, 0.2
     with pytest.raises(NotImplementedError):
         eng.mc_european(g, O.OSim(n_paths=10, n_steps=4, rng_mode=O.HH_RNG_PHILOX_64), [(100.0, 1.0)], 1.0)
+
+
+def test_lsm_generator_stream_four_steps_per_block(oracle):
+    """The exact GBM generator under HH_RNG_PHILOX_64 takes ONE normal per step: step n is component n & 1 of the 64-bit
+    Box-Muller pair hho_normal_pair64(key, idx, n >> 1), i.e. one Philox block per four steps. Law and independence."""
+    from scipy import stats
+    m = O.o_model()
+    m.kind, m.flags = O.HH_MODEL_GBM, O.HH_FLAG_SPLIT_STEP | O.HH_FLAG_Q1_SQRT_MEAN
+    m.S0, m.r, m.T, m.sigma = 100.0, 0.05, 1.0, 0.2
+    z = oracle.fill_normals(m, O.OSim(n_paths=100_000, n_steps=9, scheme=O.HH_SCHEME_EXACT_STEPS, rng_mode=O.HH_RNG_PHILOX_64,
+                                      base_seed=3))[:, :, 0]
+    for n in range(9):
+        assert stats.kstest(z[:, n], "norm").pvalue > 1e-3
+        a, b = O.normal_pair64(3, 17, n >> 1)
+        assert z[17, n] == (b if n & 1 else a)
+    c = np.corrcoef(z.T)
+    assert np.max(np.abs(c - np.eye(9))) < 0.015
+    z0 = oracle.fill_normals(m, O.OSim(n_paths=1000, n_steps=9, scheme=O.HH_SCHEME_EXACT_STEPS, base_seed=3))[:, :, 0]
+    assert not np.allclose(z0, z[:1000])   # counter stream word 2: never the HH_RNG_PHILOX numbers
