@@ -1036,7 +1036,10 @@ __device__ __forceinline__ void heston_tangent_step(const HestonFolded &f, const
 }
 
 template <bool ANTI, bool SPLIT, int NF, int P>
-__global__ void __launch_bounds__(kThreads, 2) heston_tangent_kernel(const EuroArgs a, const HestonTanConsts c) {
+#ifndef HH_TAN_MINB
+#define HH_TAN_MINB 2  // resident blocks the register allocation is bounded for (A/B: -DHH_TAN_MINB=1)
+#endif
+__global__ void __launch_bounds__(kThreads, HH_TAN_MINB) heston_tangent_kernel(const EuroArgs a, const HestonTanConsts c) {
   constexpr int NACC = 3 + 2 * P + kNGamma;
   constexpr int NV = 1 + P;
   constexpr int NSIDE = ANTI ? 2 : 1;
