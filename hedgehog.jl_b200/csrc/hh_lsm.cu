@@ -825,6 +825,13 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
 }
 
+// 16-byte load from the shared window (ordered after the mbarrier wait that precedes it: volatile, memory clobber)
+__device__ __forceinline__ double2 lds_v2(unsigned int saddr) {
+  double2 v;
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(saddr) : "memory");
+  return v;
+}
+
 // Warp-specialised: warp 8 is the producer (one lane issues the bulk copies as ring slots drain), warps 0-7 consume.
 // ncu on the version whose consumers met at a __syncthreads per chunk (profiles/r1_j_ncu_lsm_backward.csv): "barrier" was the
 // top stall (2.4 cycles per issue), issue slots 49 % busy, DRAM 49 %. Here a consumer warp announces that it has taken
@@ -858,6 +865,7 @@ __global__ void __launch_bounds__(kBackThreads) lsm_backward_kernel(const LsmBac
   }
   __syncthreads();
   const double cpK = a.cp * a.strike;
+  const unsigned int ring_saddr = smem_addr(ring) + (unsigned)tid * 16u;  // this thread's first column pair of stage 0
   const int64_t neven = a.ncols & ~(int64_t)1;
   const int64_t nchunks = (neven + kBackChunk - 1) / kBackChunk;
   const int64_t cstep = (int64_t)gridDim.x * kBackChunk;
@@ -920,38 +928,66 @@ __global__ void __launch_bounds__(kBackThreads) lsm_backward_kernel(const LsmBac
       auto chunks = [&](auto first_c, auto last_c) {
         constexpr bool F = decltype(first_c)::value, L = decltype(last_c)::value;
         int64_t c0 = (int64_t)blockIdx.x * kBackChunk;
-        for (int i = 0; i < my_chunks; ++i, ++seq, c0 += cstep) {
-          const int s = (int)(seq % kBackStages);
-          const uint32_t parity = (seq / kBackStages) & 1u;
-          const int ncol = (int)(neven - c0 < kBackChunk ? neven - c0 : kBackChunk);
+        // stage and phase advance incrementally; the ring is addressed through the shared window (a 32-bit address kept in a
+        // register: the generic form recomputes the window base every chunk). Only the last chunk of the grid can be ragged:
+        // every other chunk takes the path without per-column predicates (SASS: 138 -> ~115 instructions per chunk and thread).
+        unsigned int s = seq % kBackStages, parity = (seq / kBackStages) & 1u;
+        for (int i = 0; i < my_chunks; ++i, c0 += cstep) {
           mbar_wait(&s_full[s], parity);
-          // kBackCpt / 2 column pairs per thread, a block-wide stride apart (conflict-free 16 B shared loads)
-          double2 sn[kBackCpt / 2], sc[kBackCpt / 2], zi[kBackCpt / 2];
+          const unsigned int st_addr = ring_saddr + s * (unsigned)(3 * kBackChunk * sizeof(double));
+          if (c0 + kBackChunk <= neven) {
+            double2 sn[kBackCpt / 2], sc[kBackCpt / 2], zi[kBackCpt / 2];
 #pragma unroll
-          for (int h = 0; h < kBackCpt / 2; ++h) {
-            const int pr = tid + h * kLsmThreads;
-            sn[h] = sc[h] = zi[h] = make_double2(0.0, 0.0);
-            if (2 * pr < ncol) {
-              sn[h] = reinterpret_cast<const double2 *>(s_next(s))[pr];
-              if (!L) sc[h] = reinterpret_cast<const double2 *>(s_cur(s))[pr];
-              if (!F) zi[h] = reinterpret_cast<const double2 *>(s_z(s))[pr];
+            for (int h = 0; h < kBackCpt / 2; ++h) {
+              const unsigned int ad = st_addr + (unsigned)(h * kLsmThreads * 16);
+              sn[h] = lds_v2(ad);
+              sc[h] = L ? make_double2(0.0, 0.0) : lds_v2(ad + (unsigned)(kBackChunk * sizeof(double)));
+              zi[h] = F ? make_double2(0.0, 0.0) : lds_v2(ad + (unsigned)(2 * kBackChunk * sizeof(double)));
             }
-          }
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&s_empty[s]);  // this warp has taken its columns out of stage s
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_empty[s]);  // this warp has taken its columns out of stage s
 #pragma unroll
-          for (int h = 0; h < kBackCpt / 2; ++h) {
-            const int pr = tid + h * kLsmThreads;
-            if (2 * pr < ncol) {
-              const int64_t col = c0 + 2 * pr;
+            for (int h = 0; h < kBackCpt / 2; ++h) {
+              const int64_t col = c0 + 2 * (tid + h * kLsmThreads);
               double2 zo;
               bool cx, cy;
               lsm_column<DEG, F, L, TAU>(ca, q, cpK, sn[h].x, sc[h].x, zi[h].x, col, zo.x, cx, acc, cnt);
               lsm_column<DEG, F, L, TAU>(ca, q, cpK, sn[h].y, sc[h].y, zi[h].y, col + 1, zo.y, cy, acc, cnt);
               if (cx || cy) *reinterpret_cast<double2 *>(a.z + col) = zo;
             }
+          } else {
+            const int ncol = (int)(neven - c0);
+            // kBackCpt / 2 column pairs per thread, a block-wide stride apart (conflict-free 16 B shared loads)
+            double2 sn[kBackCpt / 2], sc[kBackCpt / 2], zi[kBackCpt / 2];
+#pragma unroll
+            for (int h = 0; h < kBackCpt / 2; ++h) {
+              const int pr = tid + h * kLsmThreads;
+              sn[h] = sc[h] = zi[h] = make_double2(0.0, 0.0);
+              if (2 * pr < ncol) {
+                sn[h] = reinterpret_cast<const double2 *>(s_next((int)s))[pr];
+                if (!L) sc[h] = reinterpret_cast<const double2 *>(s_cur((int)s))[pr];
+                if (!F) zi[h] = reinterpret_cast<const double2 *>(s_z((int)s))[pr];
+              }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_empty[s]);
+#pragma unroll
+            for (int h = 0; h < kBackCpt / 2; ++h) {
+              const int pr = tid + h * kLsmThreads;
+              if (2 * pr < ncol) {
+                const int64_t col = c0 + 2 * pr;
+                double2 zo;
+                bool cx, cy;
+                lsm_column<DEG, F, L, TAU>(ca, q, cpK, sn[h].x, sc[h].x, zi[h].x, col, zo.x, cx, acc, cnt);
+                lsm_column<DEG, F, L, TAU>(ca, q, cpK, sn[h].y, sc[h].y, zi[h].y, col + 1, zo.y, cy, acc, cnt);
+                if (cx || cy) *reinterpret_cast<double2 *>(a.z + col) = zo;
+              }
+            }
           }
+          s = (s + 1) & (kBackStages - 1);
+          parity ^= (s == 0);
         }
+        seq += (unsigned)my_chunks;
         if ((a.ncols & 1) && blockIdx.x == 0 && tid == 0) {
           const int64_t p = a.ncols - 1;
           double zo;
