@@ -356,6 +356,18 @@ def main():
         ms32, r32 = timed_launches(c2_problem(hh, total_paths, args.nsteps, "f32")[1], 7000)
         f32 = {"value": path_steps_per_step * K / (ms32 * 1e-3), "unit": UNIT, "ms_per_step": ms32 / K, "price": r32.price,
                "std_error": r32.std_error, "note": "f32 state and normals (32-bit uniforms, MUFU lg2/sin/cos/sqrt), f64 payoff sums"}
+        # SFU throughput (north star: "FP64/FP32 FLOP/s and SFU (exp/log/sqrt) throughput against the B200 peak"): four MUFU per
+        # path-step (lg2, sqrt, sin, cos: SASS of heston_f32_kernel, tools/sass_loop.py); the XU pipe has 4 lanes per SM
+        # sub-partition (a warp-wide MUFU holds it 8 cycles: ncu 46.7 % busy at 33.5 busy cycles per warp-step), 16 per SM
+        k32 = ncu_consts.get("heston_f32_kernel<0, 1, 1, 4, 3>") or {}
+        sfu_peak = eng.device_info()["sm_count"] * 16 * 1.965e9
+        per_gpu32 = float(args.paths) * args.nsteps / (ms32 / K * 1e-3)
+        f32["sfu"] = {"mufu_per_path_step": 4, "achieved": 4 * per_gpu32, "peak": sfu_peak, "unit": "MUFU/s per GPU",
+                      "frac": 4 * per_gpu32 / sfu_peak, "xu_pipe_busy_pct_under_ncu": k32.get("xu_pipe_pct"),
+                      "instr_per_path_step": k32.get("instr_per_path_step"), "source": k32.get("source"),
+                      "fp32_note": "FP32 work: ~11 FFMA / FMUL / FADD per path-step = %.2f TFLOP/s-equivalent instructions; the kernel "
+                                   "is bound by the dispatch port (Philox: 12 IMAD.WIDE + 15 LOP3 per step), not by the FP32 or SFU pipes"
+                                   % (13 * 2 * per_gpu32 * 1e-12)}
     if args.precision == "f64":
         ms64, r64 = timed_launches(c2_problem(hh, total_paths, args.nsteps, "f64", rng="philox64")[1], 9000)
         a64 = FLOP_PER_PATH_STEP * float(args.paths) * args.nsteps / (ms64 / K * 1e-3) * 1e-12

@@ -15,7 +15,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OUT = os.path.join(ROOT, "profiles", "ncu_constants.json")
-FAMILY = {"heston_fast2_kernel": ("c2", "c2_64"), "lsm_backward_kernel": ("c3",), "lsm_paths_kernel": ("c3",),
+FAMILY = {"heston_fast2_kernel": ("c2", "c2_64"), "heston_f32_kernel": ("c2_f32",), "lsm_backward_kernel": ("c3",), "lsm_paths_kernel": ("c3",),
           "bk_integral_sorted_kernel": ("c4",), "heston_tangent_kernel": ("c5",)}
 
 
@@ -87,6 +87,7 @@ def main():
                  "fp64_pipe_pct": get("sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active"),
                  "alu_pipe_pct": get("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"),
                  "fma_pipe_pct": get("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active"),
+                 "xu_pipe_pct": get("sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active"),
                  "dram_throughput_pct": get("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"),
                  "registers_per_thread": get("launch__registers_per_thread"),
                  "warps_active_pct": get("sm__warps_active.avg.pct_of_peak_sustained_active"),

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Launches the kernels whose ncu captures feed profiles/ncu_constants.json, at sizes that select the SAME instantiation
 bench.py launches. One warm-up of each family, then one measured launch. usage: python tools/ncu_targets.py [which ...]
-   which in {c2, c2_64, c3, c4, c5}; prints the work units of each measured launch as JSON (read by tools/ncu_constants.py)."""
+   which in {c2, c2_64, c2_f32, c3, c4, c5}; prints the work units of each measured launch as JSON (read by tools/ncu_constants.py)."""
 import datetime as dt
 import json
 import os
@@ -12,7 +12,7 @@ import numpy as np
 
 import hedgehog_jl_b200 as hh
 
-which = sys.argv[1:] or ["c2", "c2_64", "c3", "c4", "c5"]
+which = sys.argv[1:] or ["c2", "c2_64", "c2_f32", "c3", "c4", "c5"]
 eng = hh.default_engine(0)
 call = lambda K=100.0, ex=None, cp=None: hh.VanillaOption(K, dt.date(2020, 12, 31), ex or hh.European(), cp or hh.Call(), hh.Spot())
 bs = hh.BlackScholesInputs(dt.date(2020, 1, 1), 0.05, 100.0, 0.2)
@@ -23,6 +23,13 @@ for w in which:
         n = 4_000_000  # >= 4 x 148 x 1024: the 1024-thread instantiation of the headline kernel
         m = hh.MonteCarlo(hh.HestonDynamics(), hh.EulerMaruyama(), hh.SimulationConfig(n, steps=252, base_seed=42), ensemble=False,
                           rng="philox64" if w == "c2_64" else "philox")
+        for _ in range(2):
+            hh.solve(hh.PricingProblem(call(), heston), m, engine=eng)
+        units[w] = {"path_steps": n * 252}
+    elif w == "c2_f32":
+        n = 4_000_000
+        m = hh.MonteCarlo(hh.HestonDynamics(), hh.EulerMaruyama(), hh.SimulationConfig(n, steps=252, base_seed=42), ensemble=False,
+                          precision="f32")
         for _ in range(2):
             hh.solve(hh.PricingProblem(call(), heston), m, engine=eng)
         units[w] = {"path_steps": n * 252}
