@@ -146,7 +146,7 @@ struct LsmLogArgs {
 constexpr int kLsmLogSmem = kLogRepBytes + kTrigRepBytes + kExpFullBytes + kExp2Bytes;
 
 template <bool HESTON, bool ANTI, bool PARITY, bool UKEY>
-__global__ void __launch_bounds__(kLsmPathThreads) lsm_logspace_paths_kernel(const LsmLogArgs a) {
+__global__ void __launch_bounds__(kLsmPathThreads, 2) lsm_logspace_paths_kernel(const LsmLogArgs a) {
   extern __shared__ __align__(16) unsigned char dsm[];
   char *s_log = reinterpret_cast<char *>(dsm);
   char *s_trig = s_log + kLogRepBytes;
