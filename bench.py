@@ -439,12 +439,21 @@ def main():
 
 
 def _wall(f, reps):
-    best, res = None, None
+    """(result, best wall ms) over `reps` calls. The result returned is the one of the repetition with the smallest device time
+    (stats["kernel_ms"]) when the call reports one, so that kernel_ms and e2e_ms are both best-of-reps figures: a single
+    repetition can be hit by an unrelated hiccup (one in ~10 bench runs showed a 3.8 ms backward pass against 2.04 +- 0.005
+    over 30 back-to-back solves, tools/lsm_repeat.py)."""
+    best, res, res_k = None, None, None
     for _ in range(reps):
         t0 = time.perf_counter()
-        res = f()
+        r = f()
         t = (time.perf_counter() - t0) * 1e3
         best = t if best is None or t < best else best
+        k = (getattr(r, "stats", None) or {}).get("kernel_ms") if not isinstance(r, tuple) else None
+        if res is None or (k is not None and (res_k is None or k < res_k)):
+            res, res_k = r, k
+        elif k is None:
+            res = r
     return res, best
 
 
@@ -481,7 +490,7 @@ def run_configs(hh, eng, scale, fp64_peak, hbm_peak, hbm_peak_source, anchors, n
     lsm = hh.LSM(hh.MonteCarlo(hh.LognormalDynamics(), hh.BlackScholesExact(), hh.SimulationConfig(n, steps=50, base_seed=12345)), 3)
     p = hh.PricingProblem(put, bs)
     hh.solve(p, lsm, engine=eng, stopping_info=False)
-    sol, w = _wall(lambda: hh.solve(p, lsm, engine=eng, stopping_info=False), 3)
+    sol, w = _wall(lambda: hh.solve(p, lsm, engine=eng, stopping_info=False), 5)
     _, w_info = _wall(lambda: hh.solve(p, lsm, engine=eng, stopping_info="arrays"), 2)
     kms = sol.stats["kernel_ms"]
     # opt-in: the generator on the HH_RNG_PHILOX_64 stream (one Philox block per FOUR steps); reported beside, never as `value`
