@@ -8,17 +8,20 @@
 //   sample_log_S_T                            heston.jl:278-300
 //   HestonNoise stepping (multi-date)         :82-91  (restart from (S, V) each date)
 //
-// One trajectory per thread, all dates in registers. Per transition the thread
-//   1. draws V' (noncentral chi-square: chi2(d-1) + (Z + sqrt(lambda))^2 for d > 1, Poisson mixture otherwise;
-//      gamma variates by Marsaglia-Tsang) from its own Philox counter stream,
-//   2. evaluates the characteristic function of int V at +h0 (finite-difference moments of the reference through
-//      Phi(0) = 1, Phi(-a) = conj Phi(a)),
-//   3. evaluates Phi(h j) ONCE per term into a shared-memory table c_j = (2/pi) Re Phi(h j) / j — the reference
-//      recomputes the whole series (one complex Bessel function per term) for every root-finder iteration although
-//      it does not depend on x (sample_from_cf.jl:38, 84-93); terms beyond the table spill to a global slab,
-//   4. inverts F(x) = h x / pi + sum_j c_j sin(h j x) at its uniform by safeguarded Newton inside [0, mean + 11 sd],
+// A transition (V, S) -> (V', S') over one date interval is
+//   1. V' (noncentral chi-square: chi2(d-1) + (Z + sqrt(lambda))^2 for d > 1, Poisson mixture otherwise; gamma variates by
+//      Marsaglia-Tsang) from the trajectory's own Philox counter stream,
+//   2. the characteristic function of int V at +h0 (the finite-difference moments of the reference through Phi(0) = 1,
+//      Phi(-a) = conj Phi(a)),
+//   3. Phi(h j) ONCE per term into a shared-memory table c_j = (2/pi) Re Phi(h j) / j — the reference recomputes the whole
+//      series (one complex Bessel function per term) for every root-finder iteration although it does not depend on x
+//      (sample_from_cf.jl:38, 84-93); terms beyond the table spill to a global slab,
+//   4. the inversion of F(x) = h x / pi + sum_j c_j sin(h j x) at its uniform by safeguarded Newton inside [0, mean + 11 sd],
 //      to machine precision (the reference accepts |F(x) - u| <= 1e-4; any root of the same F satisfies that),
-//   5. draws log S'.
+//   5. log S'.
+// Step 1 of ALL dates runs first, one trajectory per thread (the variance chain depends neither on the integrals nor on the
+// spot); steps 2-4 then run over all transitions of the job in an order sorted by log2(V V'), so that the lanes of a warp
+// take the same Bessel branch; step 5 walks each trajectory through its dates ("the transition-sorted pipeline" below).
 // Payoffs are then reduced from the terminal spots by hh_european.cu's terminal_payoff kernel.
 #include <cmath>
 #include <cstdlib>
