@@ -20,6 +20,8 @@ Keys of the JSON line (see the task contract):
   f32_fast_mode config C2's Float32 fast mode — reported beside
   configs       C1, C3, C4, C5 (N = 1): value + unit, kernel_ms, e2e_ms, roofline, check against the closed-form /
                 Carr-Madan / CRR anchors of tests/golden/config_anchors.json (written by tools/gen_anchors.py)
+                configs.next_rows: the SURVEY 8(f) N4 rows (path-dependent baskets under GBM / Heston, American put under Heston)
+                with timings and closed-form checks
   multi_gpu     N > 1: c2_strong (1e8 TOTAL trajectories through solve) and c3_lsm_peer (1e7 total columns, moments
                 exchanged inside the kernel over peer memory)
   cpu_baseline  the CPU oracle (a C restatement of the reference's arithmetic, "port") on a bounded sample
@@ -622,6 +624,46 @@ def run_configs(hh, eng, scale, fp64_peak, hbm_peak, hbm_peak_source, anchors, n
                                    "trajectories the standard errors are ~1e-4 relative, so |z| of a few units measures the "
                                    "Euler-Maruyama full-truncation bias at 252 steps (0.06 % on the price, up to ~1 % on the variance "
                                    "sensitivities), not sampling error: rel_diff is the figure to read"}}
+
+    # "next" rows of SURVEY 8(f) N4 (path-dependent payoffs, American options under Heston): timings and closed-form checks
+    try:
+        nx = {}
+        n = max(int(4e6 * scale), 10000)
+        exp_ = dt.date(2020, 12, 31)
+        mon = hh.Monitoring(21)   # 12 monitoring dates on 252 steps
+        contracts = lambda: [hh.AsianOption(100.0, exp_, hh.Call(), hh.GeometricAverage(), mon), hh.DigitalOption(100.0, exp_, hh.Call(), hh.CashOrNothing(1.0), monitoring=mon),
+                             hh.AsianOption(100.0, exp_, hh.Call(), monitoring=mon),
+                             hh.BarrierOption(100.0, 130.0, exp_, hh.Call(), hh.Up(), hh.KnockOut(), monitoring=mon),
+                             hh.BarrierOption(100.0, 80.0, exp_, hh.Put(), hh.Down(), hh.KnockIn(), monitoring=mon)]
+        for name, dyn, mkt in (("gbm", hh.LognormalDynamics(), bs), ("heston", hh.HestonDynamics(), heston)):
+            mc = hh.MonteCarlo(dyn, hh.EulerMaruyama(), hh.SimulationConfig(n, steps=252, base_seed=77), ensemble=False)
+            bp = hh.BasketPricingProblem(contracts(), mkt)
+            hh.solve(bp, mc, engine=eng)
+            sols, w = _wall(lambda: hh.solve(bp, mc, engine=eng), 3)
+            kms = min(s_.stats["kernel_ms"] for s_ in sols)
+            e = {"workload": f"5 path-dependent contracts (geometric / arithmetic Asian, cash digital, up-and-out call, down-and-in put) on "
+                             f"common trajectories, {n} x 252 steps, 12 monitoring dates, {name}", "kernel_ms": kms, "e2e_ms": w,
+                 "value": n * 252 / (kms * 1e-3), "unit": "column-steps/s", "prices": [s_.price for s_ in sols]}
+            if name == "gbm":
+                ga, dg = anchors.get("next_geometric_asian_call_12_dates"), anchors.get("next_digital_cash_call")
+                e["check"] = {"geometric_asian": {"mc": sols[0].price, "closed_form": ga, "z": (sols[0].price - ga) / sols[0].std_error if ga else None},
+                              "digital_cash": {"mc": sols[1].price, "closed_form": dg, "z": (sols[1].price - dg) / sols[1].std_error if dg else None},
+                              "note": "log-space Euler-Maruyama is exact for the log-GBM at the monitoring dates: no time-stepping bias"}
+            nx["path_dependent_" + name] = e
+        n = max(int(1e7 * scale), 10000)
+        lsmh = hh.LSM(hh.MonteCarlo(hh.HestonDynamics(), hh.EulerMaruyama(), hh.SimulationConfig(n, steps=50, base_seed=12345)), 3)
+        ph = hh.PricingProblem(call(100.0, hh.American(), hh.Put()), heston)
+        hh.solve(ph, lsmh, engine=eng, stopping_info=False)
+        sol, w = _wall(lambda: hh.solve(ph, lsmh, engine=eng, stopping_info=False), 3)
+        eu = anchors.get("next_heston_european_put")
+        nx["lsm_heston"] = {"workload": f"American put under Heston (log-space Euler-Maruyama, spots extracted as exp(x)), {n} paths x 50 dates, degree 3",
+                            "kernel_ms": sol.stats["kernel_ms"], "path_ms": sol.stats["path_ms"], "regress_ms": sol.stats["regress_ms"], "e2e_ms": w,
+                            "value": n * 50 / (sol.stats["kernel_ms"] * 1e-3), "unit": "path-dates/s",
+                            "check": {"price": sol.price, "std_error": sol.std_error, "heston_european_put_carr_madan": eu,
+                                      "early_exercise_premium": sol.price - eu if eu else None}}
+        out["next_rows"] = nx
+    except Exception as ex:  # the next rows must never cost the record its five configurations
+        out["next_rows"] = {"error": repr(ex)}
     return out
 
 

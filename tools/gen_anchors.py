@@ -54,6 +54,11 @@ def main():
         c5["d_" + name] = [d1(float(K), name, h) for K in strikes]
     c5["d2_S0"] = [d2(float(K), "S0", 1.0) for K in strikes]
     out["c5"] = c5
+    # "next" rows: closed forms under Black-Scholes r = 0.05, sigma = 0.2, S0 = K = 100, T = 1 (12 monitoring dates),
+    # and the Heston European put at the C2 parameters (put-call parity): the American put under Heston must exceed it
+    out["next_geometric_asian_call_12_dates"] = A.geometric_asian_price(100.0, 100.0, 0.05, 0.2, 1.0, 12, 1.0)
+    out["next_digital_cash_call"] = A.digital_price(100.0, 100.0, 0.05, 0.2, 1.0, 1.0, 1.0)
+    out["next_heston_european_put"] = out["c2_carr_madan_call"] - 100.0 + 100.0 * math.exp(-0.03)
     json.dump(out, open(OUT, "w"), indent=1)
     print("wrote", OUT)
 
