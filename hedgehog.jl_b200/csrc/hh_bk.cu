@@ -31,6 +31,7 @@
 #include "hh_bessel.cuh"
 #include "hh_ctx.h"
 #include "hh_device.cuh"
+#include "hh_fastnormal.cuh"
 
 namespace hh {
 
@@ -44,8 +45,12 @@ int terminal_payoffs_launch(hh_ctx *ctx, const double *d_terminal, int64_t n, co
 
 struct BkRng {  // Philox counter stream of one trajectory: counter = (idx_lo, idx_hi, date, draw)
   uint32_t c0, c1, c2, draw, k0, k1;
+  const FastNormalTables *tb;  // shared-memory Box-Muller tables (hh_fastnormal.cuh): the same pair as libm's to ~4e-16
   __device__ __forceinline__ u32x4 block() { return philox4x32_10(c0, c1, c2, draw++, k0, k1); }
-  __device__ __forceinline__ void normals(double &z1, double &z2) { normal_pair_libm(block(), z1, z2); }
+  __device__ __forceinline__ void normals(double &z1, double &z2) {
+    const u32x4 w = block();
+    fast_normal_pair(tb, w.x, w.y, w.z, w.w, z1, z2);
+  }
   __device__ __forceinline__ void uniforms(double &u1, double &u2) {  // both in (0, 1)
     const u32x4 w = block();
     u1 = u01_for_log(w.x, w.y);
@@ -380,10 +385,13 @@ struct BkChainArgs {
 
 __global__ void __launch_bounds__(256) bk_chain_kernel(const BkChainArgs a) {
   __shared__ unsigned s_hist[kBkBuckets];
+  __shared__ FastNormalTables s_tables;
+  load_fast_tables(&s_tables);
   for (int k = threadIdx.x; k < kBkBuckets; k += blockDim.x) s_hist[k] = 0;
   __syncthreads();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (int64_t)gridDim.x * blockDim.x) {
     BkRng rng;
+    rng.tb = &s_tables;
     uint64_t key = a.base_seed, idx = (uint64_t)(a.path_offset + i);
     if (a.seeds) {
       key = a.seeds[i];
@@ -624,9 +632,13 @@ __global__ void __launch_bounds__(kBkThreads) bk_integral_kernel(const BkParams 
 }
 
 __global__ void bk_variance_kernel(const BkParams p, const double *V0, int n, uint64_t seed, double *VT) {
+  __shared__ FastNormalTables s_tables;
+  load_fast_tables(&s_tables);
+  __syncthreads();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   BkRng rng;
+  rng.tb = &s_tables;
   rng.c0 = (uint32_t)i;
   rng.c1 = 0;
   rng.c2 = 0;
@@ -750,6 +762,7 @@ static int bk_paths_launch(hh_ctx *ctx, const hh_model *m, const hh_sim *s, doub
     HH_CUDA(ctx, ctx->d_seeds.ensure(bytes));
     HH_CUDA(ctx, cudaMemcpyAsync(ctx->d_seeds.ptr, s->seeds, bytes, cudaMemcpyHostToDevice, st));
   }
+  HH_CUDA(ctx, upload_fast_tables(ctx->device, st));
   HH_CUDA(ctx, cudaEventRecord(ctx->ev0, st));
   const int mon = monitor_every > 0 ? monitor_every : 1;
   for (int64_t c0 = 0; c0 < N; c0 += chunk) {
@@ -935,6 +948,7 @@ int bk_variance(hh_ctx *ctx, const hh_model *m, double tau, const double *V0, in
   const size_t nv = sizeof(double) * (size_t)n;
   HH_CUDA(ctx, ctx->d_misc.ensure(2 * nv));
   double *dV0 = ctx->d_misc.as<double>(), *dVT = dV0 + n;
+  HH_CUDA(ctx, upload_fast_tables(ctx->device, st));
   HH_CUDA(ctx, cudaMemcpyAsync(dV0, V0, nv, cudaMemcpyHostToDevice, st));
   bk_variance_kernel<<<(n + 127) / 128, 128, 0, st>>>(p, dV0, n, seed, dVT);
   HH_CUDA(ctx, cudaGetLastError());
