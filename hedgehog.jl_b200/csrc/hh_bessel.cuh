@@ -13,6 +13,10 @@
 //                        I_nu(|w|) / |I_nu(w)| ~ e^{|w| - Re w} <= e^5, whatever |w| (no cancellation at all on the real
 //                        axis), so arguments near the real axis never need the continued fractions (~50x dearer)
 //   |w| >= 20 + nu^2/2   Hankel expansion with BOTH exponentials (DLMF 10.40.5)
+//   nu >= 12.5, between the two (the series would need more than its 100 tabulated terms, the Hankel terms grow first):
+//                        Debye's uniform expansion in the order (DLMF 10.41.3, u_0..u_8) in a sector round the real axis —
+//                        low vol of vol means a large order (nu = 2 kappa theta / sigma^2 - 1: 15 at sigma = 0.1, 89 at
+//                        kappa theta = 0.45), and |z| there is a few times nu
 //   otherwise            continued fractions: CF1 for I'/I (modified Lentz), Steed's CF2 for K_mu, K_mu+1, |mu| <= 1/2,
 //                        and the Wronskian I K' - I' K = -1/w (Temme 1975; Thompson & Barnett 1987 for complex w);
 //                        orders in (-1, 0) are reached from nu + 1 through I_(nu) = I'_(nu+1) + ((nu+1)/w) I_(nu+1).
@@ -355,6 +359,7 @@ struct BesselOrder {
   double nu;        // order, > -1
   double lgam_nu1;  // lgamma(nu + 1)
   double r_asym;    // |w| from which the Hankel expansion is used
+  double r_near;    // min(r_asym, largest |w| whose series reaches 1e-17 within the tabulated terms)
   // device: tables filled by bk_fill_order_tables in shared memory (the order is fixed per launch), 0 on the host
   //   series: groups of four, R_{k,i} = prod_{m=k}^{k+i-1} 1 / (m (nu + m)), k = 1, 5, 9, ...
   //   hankel: groups of four running products b_k, b_k b_{k+1}, ..., b_k = (4 nu^2 - (2k - 1)^2) / (8 k), k = 1, 5, 9, ...
@@ -362,11 +367,33 @@ struct BesselOrder {
   FastRef ft;       // tables of the elementary functions (saddr 0: the math library)
   unsigned pad_;
 };
+// Largest |w| <= r_hi for which the ascending series reaches its 1e-17 test within 92 terms (the device sums groups of
+// four up to 100): term_N / term_peak <= 1e-17 e^{-6}, the e^{-6} for the cancellation allowed off the real axis
+// (|w| - Re w <= 5) and for the peak term against the sum. log term_k = k log q - lgamma(k+1) - lgamma(nu+k+1) + const.
+HH_HD bool bessel_series_enough(double nu, double r) {
+  const double N = 92.0;
+  const double q = 0.25 * r * r, lq = log(q);
+  const double kp = fmax(0.0, 0.5 * (sqrt(nu * nu + 4.0 * q) - nu));  // k (k + nu) = q
+  if (kp >= N - 1.0) return false;
+  const double tn = N * lq - lgamma(N + 1.0) - lgamma(nu + N + 1.0);
+  const double tp = kp * lq - lgamma(kp + 1.0) - lgamma(nu + kp + 1.0);
+  return tn - tp <= -39.14394658089878 - 6.0;  // log 1e-17
+}
+HH_HD double bessel_series_radius(double nu, double r_hi) {
+  if (r_hi <= 5.0 || bessel_series_enough(nu, r_hi)) return r_hi;
+  double lo = 5.0, hi = r_hi;
+  for (int i = 0; i < 60; ++i) {
+    const double mid = 0.5 * (lo + hi);
+    if (bessel_series_enough(nu, mid)) lo = mid; else hi = mid;
+  }
+  return lo;
+}
 HH_HD BesselOrder make_bessel_order(double nu) {
   BesselOrder o;
   o.nu = nu;
   o.lgam_nu1 = lgamma(nu + 1.0);
   o.r_asym = 20.0 + 0.5 * nu * nu;
+  o.r_near = bessel_series_radius(nu, o.r_asym);
   o.series_saddr = 0;
   o.hankel_saddr = 0;
   o.ft.saddr = 0;
@@ -491,6 +518,51 @@ HH_HD cplx log_besseli_asymptotic(const BesselOrder &o, cplx w) {
   return w - 0.5 * clog_(o.ft, (2.0 * kBesselPi) * w) + clog_(o.ft, s1 + e2 * s2);
 }
 
+// ---- Debye's uniform expansion for large orders (DLMF 10.41.3, 10.41.7-9): Re w > 0 ---------------------------------
+//   I_nu(nu z) ~ e^{nu eta} / sqrt(2 pi nu s) sum_k u_k(t) / nu^k,  s = sqrt(1 + z^2), t = 1/s, eta = s + log(z / (1 + s))
+// u_k(t) = t^k P_k(t^2), P_k of degree k (generated by the recurrence 10.41.9 in rational arithmetic, tools/gen_tables.py
+// --debye). Used where kDebyeMinOrder <= nu and r_near <= |w| < r_asym, inside the sector bessel_debye_sector: there
+// |z| >= r_near / nu keeps |t| small and nine terms are exact to rounding (measured against 30-digit values: 5e-16
+// relative for nu from 12.7 to 1000; six terms already are) and the recessive exponential is below e^{-160}.
+constexpr double kDebyeMinOrder = 12.5;
+constexpr int kDebyeTerms = 8;
+HH_HD bool bessel_debye_sector(double nu, double aw, cplx w) {  // Re w >= 0
+  if (aw - w.re <= 5.0) return true;                            // the strip the series uses below r_near
+  if (nu >= 100.0) return fabs(w.im) <= 3.6 * w.re;             // |arg w| <= 1.3
+  return nu >= 30.0 && fabs(w.im) <= 0.7 * w.re;                // |arg w| <= 0.61
+}
+HH_HD_OUTLINE cplx log_besseli_debye(const BesselOrder &o, cplx w) {
+  constexpr double c[(kDebyeTerms + 1) * (kDebyeTerms + 2) / 2] = {
+      1.0,
+      0.125, -0.20833333333333334,
+      0.0703125, -0.4010416666666667, 0.3342013888888889,
+      0.0732421875, -0.8912109375, 1.8464626736111112, -1.0258125964506173,
+      0.112152099609375, -2.3640869140625, 8.78912353515625, -11.207002616222994, 4.669584423426247,
+      0.22710800170898438, -7.368794359479632, 42.53499874538846, -91.81824154324002, 84.63621767460073, -28.212072558200244,
+      0.5725014209747314, -26.491430486951554, 218.1905117442116, -699.5796273761325, 1059.9904525279999, -765.2524681411817,
+      212.57013003921713,
+      1.7277275025844574, -108.09091978839466, 1200.9029132163525, -5305.646978613403, 11655.393336864534, -13586.550006434138,
+      8061.722181737309, -1919.457662318407,
+      6.074042001273483, -493.915304773088, 7109.514302489364, -41192.65496889755, 122200.46498301746, -203400.17728041555,
+      192547.00123253153, -96980.59838863752, 20204.29133096615};
+  const double inu = 1.0 / o.nu;
+  const cplx z = inu * w;
+  const cplx s = csqrt_(1.0 + z * z);  // principal branch: Re s > 0 for Re z > 0
+  const cplx t = crecip(s), t2 = t * t, x = inu * t;
+  cplx acc = mk(0.0);
+#pragma unroll
+  for (int k = kDebyeTerms; k >= 0; --k) {
+    const int base = k * (k + 1) / 2;
+    cplx pk = mk(c[base + k]);
+#pragma unroll
+    for (int j = k - 1; j >= 0; --j) pk = pk * t2 + c[base + j];
+    acc = acc * x + pk;
+  }
+  const cplx eta = s + clog_(o.ft, z / (1.0 + s));
+  // -1/2 log(2 pi nu s)
+  return o.nu * eta - 0.5 * (clog_(o.ft, s) + (1.8378770664093453 + log(o.nu))) + clog_(o.ft, acc);
+}
+
 // ---- continued fractions + Wronskian: 2 <= |w|, Re w >= 0, order xnu >= 0 ------------------------------------------
 // Returns log I_xnu(w); if dlog is non-null also I'_xnu / I_xnu.
 HH_HD_OUTLINE cplx log_besseli_cf(double xnu, cplx x, cplx *ratio_deriv) {
@@ -502,7 +574,7 @@ HH_HD_OUTLINE cplx log_besseli_cf(double xnu, cplx x, cplx *ratio_deriv) {
   cplx h = xnu * xi;
   if (fabs(h.re) + fabs(h.im) < FPMIN) h = mk(FPMIN);
   cplx b = xnu * xi2, d = mk(0.0), c = h;
-  const int maxit = 400 + 2 * (int)cabs(x);
+  const int maxit = 400 + 2 * (int)fmin(cabs(x), 1e5);
 #pragma unroll 1
   for (int i = 0; i < maxit; ++i) {
     b = b + xi2;
@@ -513,19 +585,20 @@ HH_HD_OUTLINE cplx log_besseli_cf(double xnu, cplx x, cplx *ratio_deriv) {
     if (fabs(del.re - 1.0) + fabs(del.im) < EPS) break;
   }
   // downward recurrence to order xmu
-  cplx ril = mk(1.0), ripl = h, ril1 = ril, rip1 = ripl;
-  cplx fact = xnu * xi;
+  cplx ril = mk(1.0), ripl = h;
+  double lscale = 0.0;  // log of the factors taken out of (ril, ripl): I_mu / I_xnu = ril e^{lscale}, which leaves the
+  cplx fact = xnu * xi; // binary64 range for large orders (e^{nu^2 / 2|x|})
 #pragma unroll 1
   for (int l = nl; l >= 1; --l) {
     const cplx ritemp = fact * ril + ripl;
     fact = fact - xi;
     ripl = fact * ritemp + ril;
     ril = ritemp;
-    // rescale to stay in range (ratios are all that matter)
     const double m = cabs2(ril);
     if (m > 1e200) {
       const double sc = 1e-100;
-      ril = sc * ril; ripl = sc * ripl; ril1 = sc * ril1; rip1 = sc * rip1;
+      ril = sc * ril; ripl = sc * ripl;
+      lscale += 230.25850929940458;  // 100 log 10
     }
   }
   const cplx f = ripl / ril;
@@ -559,8 +632,8 @@ HH_HD_OUTLINE cplx log_besseli_cf(double xnu, cplx x, cplx *ratio_deriv) {
   const cplx rkmup = xmu * xi * rkmu - rk1;                        // K'_mu e^{x}
   const cplx rimu_scaled = xi / (f * rkmu - rkmup);                // I_mu e^{-x}
   if (ratio_deriv) *ratio_deriv = h;
-  // I_xnu = I_mu * ril1 / ril
-  return x + clog_(FastRef{0}, rimu_scaled) + clog_(FastRef{0}, ril1 / ril);
+  // I_xnu = I_mu / (ril e^{lscale})
+  return x + clog_(FastRef{0}, rimu_scaled) - clog_(FastRef{0}, ril) - lscale;
 }
 
 // log I_nu(z), any complex z != 0. The imaginary part is a valid argument of I_nu(z) (branch unspecified).
@@ -574,10 +647,12 @@ HH_HD_OUTLINE cplx log_besseli(const BesselOrder &o, cplx z) {
   }
   const double aw = cabs(w);
   cplx r;
-  if (aw <= 5.0 || (aw < o.r_asym && aw - w.re <= 5.0)) {
+  if (aw <= 5.0 || (aw < o.r_near && aw - w.re <= 5.0)) {
     r = log_besseli_series(o, w);
   } else if (aw >= o.r_asym) {
     r = log_besseli_asymptotic(o, w);
+  } else if (nu >= kDebyeMinOrder && aw >= o.r_near && bessel_debye_sector(nu, aw, w)) {
+    r = log_besseli_debye(o, w);
   } else if (nu >= 0.0) {
     r = log_besseli_cf(nu, w, nullptr);
   } else {
@@ -604,12 +679,12 @@ HH_HD BesselEF besseli_ef(const BesselOrder &o, cplx z, double log_az, double ar
   // region tests on |w|^2 (Re w >= 0 here: |w| - Re w <= 5  <=>  |w|^2 <= (5 + Re w)^2): no square root
   const double aw2 = cabs2(w), ra2 = o.r_asym * o.r_asym, edge = 5.0 + w.re;
   BesselEF r;
-  if (aw2 <= 25.0 || (aw2 < ra2 && aw2 <= edge * edge)) {
+  if (aw2 <= 25.0 || (aw2 < o.r_near * o.r_near && aw2 <= edge * edge)) {
     r = besseli_series_ef(o, w, log_az, arg_w);
   } else if (aw2 >= ra2) {
     r = besseli_asymptotic_ef(o, w, log_az, arg_w);
   } else {
-    r.E = log_besseli(o, w);  // continued fractions (rare: strongly rotated arguments of moderate size)
+    r.E = log_besseli(o, w);  // Debye (large orders) or continued fractions (rare: strongly rotated arguments)
     r.F = mk(1.0);
   }
   r.E.im += rot;
@@ -642,7 +717,8 @@ struct BkCf {       // per (V0, VT) pair: HestonCFIterator
 // 2e-18 relative from r_asym on and is dropped. Orders in (-1, 0) and tiny or non-finite x take the general routine.
 HH_HD double log_besseli_real(const BesselOrder &o, double x) {
   if (!(x > 1e-300) || !(x < 1e300)) return log_besseli(o, mk(x)).re;
-  if (x < o.r_asym) {
+  if (x >= o.r_near && x < o.r_asym) return log_besseli(o, mk(x)).re;  // large orders: Debye
+  if (x < o.r_near) {
     const double q = 0.25 * x * x;
     double term = 1.0, sum = 1.0;
 #ifdef __CUDA_ARCH__
