@@ -520,8 +520,8 @@ HH_HD cplx log_besseli_asymptotic(const BesselOrder &o, cplx w) {
 
 // ---- Debye's uniform expansion for large orders (DLMF 10.41.3, 10.41.7-9): Re w > 0 ---------------------------------
 //   I_nu(nu z) ~ e^{nu eta} / sqrt(2 pi nu s) sum_k u_k(t) / nu^k,  s = sqrt(1 + z^2), t = 1/s, eta = s + log(z / (1 + s))
-// u_k(t) = t^k P_k(t^2), P_k of degree k (generated by the recurrence 10.41.9 in rational arithmetic, tools/gen_tables.py
-// --debye). Used where kDebyeMinOrder <= nu and r_near <= |w| < r_asym, inside the sector bessel_debye_sector: there
+// u_k(t) = t^k P_k(t^2), P_k of degree k (generated by the recurrence 10.41.9 in rational arithmetic,
+// tools/gen_debye.py). Used where kDebyeMinOrder <= nu and r_near <= |w| < r_asym, inside the sector bessel_debye_sector: there
 // |z| >= r_near / nu keeps |t| small and nine terms are exact to rounding (measured against 30-digit values: 5e-16
 // relative for nu from 12.7 to 1000; six terms already are) and the recessive exponential is below e^{-160}.
 constexpr double kDebyeMinOrder = 12.5;
@@ -574,7 +574,8 @@ HH_HD_OUTLINE cplx log_besseli_cf(double xnu, cplx x, cplx *ratio_deriv) {
   cplx h = xnu * xi;
   if (fabs(h.re) + fabs(h.im) < FPMIN) h = mk(FPMIN);
   cplx b = xnu * xi2, d = mk(0.0), c = h;
-  const int maxit = 400 + 2 * (int)fmin(cabs(x), 1e5);
+  const double ax = cabs(x);
+  const int maxit = 400 + 2 * (ax < 1e5 ? (int)ax : (ax == ax ? 100000 : 0));  // NaN in, NaN out, without the long loop
 #pragma unroll 1
   for (int i = 0; i < maxit; ++i) {
     b = b + xi2;
@@ -646,6 +647,7 @@ HH_HD_OUTLINE cplx log_besseli(const BesselOrder &o, cplx z) {
     rot = (z.im >= 0.0 ? 1.0 : -1.0) * kBesselPi * nu;
   }
   const double aw = cabs(w);
+  if (aw != aw) return cplx{aw, aw};  // NaN in, NaN out (no branch below would terminate early)
   cplx r;
   if (aw <= 5.0 || (aw < o.r_near && aw - w.re <= 5.0)) {
     r = log_besseli_series(o, w);
@@ -759,6 +761,11 @@ HH_HD double log_besseli_real(const BesselOrder &o, double x) {
 
 HH_HD BkCf bk_cf_init(const BkParams &p, double V0, double VT) {
   BkCf it;
+  // A variance that has underflowed (degrees of freedom << 1: the chi-square draw is a power 1/d of a uniform) is held at
+  // 1e-100: V0 VT, |z_gamma|^2 and their logarithms stay normal numbers. The reference has sqrt(0) = 0 there, then
+  // besseli(nu < 0, 0) = Inf and Inf - Inf.
+  V0 = fmax(V0, 1e-100);
+  VT = fmax(VT, 1e-100);
   it.sv = sqrt_fast(V0 * VT);
   it.vsum_s = (V0 + VT) / p.xi2;
   it.sv4_xi2 = it.sv * 4.0 / p.xi2;

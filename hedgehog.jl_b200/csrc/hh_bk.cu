@@ -210,6 +210,14 @@ __device__ BkInversion bk_sample_integral(const BkParams &p, double V0, double V
   r.mean = mean;
   r.var = var;
   r.h = h;
+  if (!(fabs(mean) < 1e300) || !(fabs(var) < 1e300) || !(h > 0.0) || !(h < 1e300)) {
+    // non-finite moments (non-finite inputs): the reference propagates NaN; so does this, without running the loops below
+    r.x = r.resid = nan("");
+    r.J = 0;
+    r.status = 2;
+    r.iters = 0;
+    return r;
+  }
   // series coefficients, x-independent (:84-93)
   th = nan("");
   int J = 0;
