@@ -192,3 +192,64 @@ def test_broadie_kaya_on_random_models(cuda, seed):
     assert np.all(np.isfinite(ens)) and np.all(ens > 0)
     price, se = res[0].price, res[0].std_error
     assert abs(price - cm) < 4.0 * se + 3.0 * abs(cm - cm2) + 2e-4 * max(cm, 0.05), (price, cm, se, pars)
+
+
+@pytest.mark.parametrize("seed", range(16))
+def test_philox64_streams_on_random_models(cuda, oracle, seed):
+    """The opt-in HH_RNG_PHILOX_64 stream on harsh random models: the Heston Euler-Maruyama kernel (one block per two
+    steps) per path in log space, and the exact GBM generator of the LSM (one block per four steps) through the stored
+    paths and the stopping decisions."""
+    rng = np.random.default_rng(6000 + seed)
+    m = _random_heston(rng)
+    steps = int(rng.integers(1, 60))
+    anti = int(rng.integers(0, 2))
+    n = int(rng.integers(1, 3000))
+    sim = SimSpec(n_paths=n, n_steps=steps, vr=anti, rng_mode=abi.HH_RNG_PHILOX_64, base_seed=int(rng.integers(0, 2 ** 62)),
+                  path_offset=int(rng.integers(0, 2 ** 40)))
+    pay = [(m.S0, 1.0), (m.S0 * 0.9, -1.0)]
+    rg, tg = cuda.mc_european(m, sim, pay, 0.97, want_terminal=True)
+    ro, to = oracle.mc_european(m, sim, pay, 0.97, want_terminal=True)
+    fin = np.isfinite(to)
+    assert np.array_equal(np.isfinite(tg), fin)
+    dlog = np.abs(np.log(tg[fin]) - np.log(to[fin]))
+    assert np.quantile(dlog, 0.99) < 1e-10 and dlog.max() < 1e-6, (np.quantile(dlog, 0.99), dlog.max())
+    g = gbm_model(S0=float(rng.uniform(20, 200)), r=float(rng.uniform(0.0, 0.12)), sigma=float(rng.uniform(0.05, 0.9)),
+                  T=float(rng.uniform(0.1, 3.0)))
+    steps = int(rng.integers(2, 30))
+    sim = SimSpec(n_paths=int(rng.integers(5000, 20000)), n_steps=steps, scheme=abi.HH_SCHEME_EXACT_STEPS, vr=anti,
+                  rng_mode=abi.HH_RNG_PHILOX_64, base_seed=int(rng.integers(0, 2 ** 62)))
+    D = math.exp(-g.r * g.T / steps)
+    K = g.S0 * float(rng.uniform(0.9, 1.1))
+    og, tg, vg, pg = cuda.lsm_american(g, sim, (K, -1.0), 3, D, want_stopping=True, want_paths=True)
+    oo, to, vo, po = oracle.lsm_american(g, sim, (K, -1.0), 3, D, want_stopping=True, want_paths=True)
+    assert rel_err(pg, po) < 1e-12
+    flips = int(np.sum(tg != to))
+    assert flips <= max(3, 3e-4 * len(to)), (flips, len(to))
+    assert abs(og.price - oo.price) <= (1e-9 if flips == 0 else 2e-5) * max(abs(oo.price), 1e-3)
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_lsm_under_heston_on_random_models(cuda, oracle, seed):
+    """American puts and calls under random Heston models through the log-space generator: stored spots
+    1e-10, decisions equal to the oracle's up to counted ties."""
+    rng = np.random.default_rng(7000 + seed)
+    m = heston_model(S0=float(rng.uniform(20, 200)), r=float(rng.uniform(0.0, 0.1)), T=float(rng.uniform(0.1, 2.0)),
+                     V0=float(10 ** rng.uniform(-2.5, -0.5)), kappa=float(10 ** rng.uniform(-1, 1)), theta=float(10 ** rng.uniform(-2.5, -0.5)),
+                     xi=float(rng.uniform(0.05, 1.2)), rho=float(rng.uniform(-0.95, 0.5)), split=bool(rng.integers(0, 2)))
+    steps = int(rng.integers(2, 40))
+    anti = int(rng.integers(0, 2))
+    cp = float(rng.choice([-1.0, -1.0, 1.0]))
+    K = m.S0 * float(rng.uniform(0.9, 1.1))
+    deg = int(rng.integers(1, 5))
+    sim = SimSpec(n_paths=int(rng.integers(5000, 30000)), n_steps=steps, scheme=abi.HH_SCHEME_EM, vr=anti,
+                  base_seed=int(rng.integers(0, 2 ** 62)), path_offset=int(rng.integers(0, 2 ** 40)))
+    D = math.exp(-m.r * m.T / steps)
+    og, tg, vg, pg = cuda.lsm_american(m, sim, (K, cp), deg, D, want_stopping=True, want_paths=True)
+    oo, to, vo, po = oracle.lsm_american(m, sim, (K, cp), deg, D, want_stopping=True, want_paths=True)
+    fin = np.isfinite(po) & (po > 0)
+    assert np.array_equal(np.isfinite(pg) & (pg > 0), fin)
+    dlog = np.abs(np.log(pg[fin]) - np.log(po[fin]))
+    assert np.quantile(dlog, 0.999) < 1e-10 and dlog.max() < 1e-6, (np.quantile(dlog, 0.999), dlog.max())
+    flips = int(np.sum(tg != to))
+    assert flips <= max(3, 5e-4 * len(to)), (flips, len(to))
+    assert abs(og.price - oo.price) <= (1e-9 if flips == 0 else 5e-5) * max(abs(oo.price), 1e-3), (og.price, oo.price, flips)
