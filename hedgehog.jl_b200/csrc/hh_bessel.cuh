@@ -701,6 +701,7 @@ struct BkParams {
   double wk;               // z_kappa = sqrt(V0 VT) wk  (:169)
   double h_fd, cf_tol, atol;
   int n_std, max_terms;
+  int widen_fd, pad_;      // re-read a noise-dominated variance at a wider step (hh_bk.cu: bk_sample_integral)
   BesselOrder ord;         // nu = d/2 - 1  (:164-165)
   // transition constants (sample_V_T :128-131, sample_log_S_T :285-297)
   double dof, c_scale, lam_scale;  // d, c, lambda = lam_scale * V

@@ -71,7 +71,7 @@ struct HHBkConfig         # hh_bk_config
     maxiter_newton::Int32
     maxiter_bisection::Int32
     max_terms::Int32
-    h_fd::Float64
+    h_fd::Float64             # > 0: noise-aware (see include/hedgehog_mc.h); < 0: plain finite differences at |h_fd|
     cf_tol::Float64
     atol::Float64
 end

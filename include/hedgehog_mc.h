@@ -110,7 +110,10 @@ typedef struct hh_bk_config {
   int32_t maxiter_newton;   /* secant evaluations */
   int32_t maxiter_bisection;
   int32_t max_terms;        /* safety cap on the Fourier series length (reference: 10^9) */
-  double h_fd;              /* finite-difference step for the CF moments */
+  double h_fd;              /* finite-difference step for the CF moments (moments_from_cf h = 1e-2). > 0: where the
+                             * rounding noise of that second difference exceeds 2 % of the variance (short horizons,
+                             * low vol of vol: sigma * tau < ~0.01) the variance is re-read at a step scaled to the
+                             * law; < 0: plain finite differences at |h_fd| always, as the reference computes them */
   double cf_tol;
   double atol;
 } hh_bk_config;

@@ -251,3 +251,71 @@ def test_bk_chunked_launch_is_bit_identical(cuda):
         outs.append(json.loads(p.stdout.strip().splitlines()[-1]))
     assert outs[0] == outs[1]
     assert outs[0]["stats"]["transitions"] == 15000
+
+
+def _mp_cumulants(kappa, theta, xi, V0, VT, tau):
+    """Mean and variance of int V dt given (V0, VT) from the characteristic function of heston.jl:184-212 in 50-digit
+    arithmetic (derivatives of log Phi at 0): the ground truth the finite-difference moments approximate."""
+    import mpmath as mp
+    mp.mp.dps = 50
+    k, s2, nu = mp.mpf(kappa), mp.mpf(xi) ** 2, 2 * mp.mpf(kappa) * theta / mp.mpf(xi) ** 2 - 1
+    sv, vs, t = mp.sqrt(mp.mpf(V0) * VT), mp.mpf(V0) + VT, mp.mpf(tau)
+
+    def parts(g):
+        e = mp.exp(-g * t)
+        return (1 - e) / g, g * (1 + e) / (1 - e), sv * 4 * g * mp.exp(-g * t / 2) / (s2 * (1 - e))
+
+    zk, ek, wk = parts(k)
+
+    def logphi(a):
+        g = mp.sqrt(k * k - 2 * s2 * a * 1j)
+        zg, eg, wg = parts(g)
+        return -(g - k) * t / 2 + mp.log(zk / zg) + vs / s2 * (ek - eg) + mp.log(mp.besseli(nu, wg) / mp.besseli(nu, wk))
+
+    d1 = mp.diff(logphi, 0, 1, h=mp.mpf(10) ** -12)
+    d2 = mp.diff(logphi, 0, 2, h=mp.mpf(10) ** -12)
+    return float(mp.im(d1)), float(-mp.re(d2))
+
+
+@pytest.mark.parametrize("pars,tau", [(LOWXI, 1 / 52), (C2, 1 / 252), (C2, 1 / 52), (HIGHNU, 1 / 52), (C2, 1 / 12)])
+def test_moments_where_the_finite_difference_is_noise(cuda, pars, tau):
+    """sigma tau < ~0.01: the rounding of Phi (exponential of a difference of terms ~8 V / (sigma^2 tau)) divided by h0^2 = 1e-4
+    exceeds the variance of the integral, and moments_from_cf (sample_from_cf.jl:50-64) returns noise — negative half of
+    the time. The kernel then re-reads the variance from |Phi| at a step scaled to the law (hh_bk.cu: bk_sample_integral);
+    checked against 50-digit cumulants. With h_fd < 0 (the reference's plain differences) the same call is off by the
+    noise; at C4's monthly horizon the two modes are the same numbers to the last bit."""
+    m = heston_model(S0=100.0, T=tau, **pars)
+    rng = np.random.default_rng(21)
+    n = 6
+    d, lam_s, c = B.vt_params(pars["kappa"], pars["theta"], pars["xi"], 1.0, tau)
+    V0 = pars["V0"] * rng.uniform(0.5, 1.5, n)
+    VT = np.array([c * stats.ncx2.rvs(d, lam_s * v, random_state=rng) for v in V0])
+    U = rng.uniform(0.05, 0.95, n)
+    g = cuda.bk_integral(m, tau, V0, VT, U)
+    plain = abi.hh_bk_config()
+    cuda.lib.hh_default_bk_config(plain)
+    plain.h_fd = -plain.h_fd
+    gp = cuda.bk_integral(m, tau, V0, VT, U, cfg=plain)
+    truth = np.array([_mp_cumulants(pars["kappa"], pars["theta"], pars["xi"], V0[i], VT[i], tau) for i in range(n)])
+    assert np.max(np.abs(g["mean"] / truth[:, 0] - 1.0)) < 1e-5
+    if tau >= 1 / 12:
+        assert np.array_equal(g["var"], gp["var"]) and np.array_equal(g["x"], gp["x"])
+        assert np.max(np.abs(g["var"] / truth[:, 1] - 1.0)) < 2e-3      # the finite difference's own truncation + noise
+        return
+    assert np.max(np.abs(g["var"] / truth[:, 1] - 1.0)) < 2e-2
+    assert np.max(np.abs(gp["var"] / truth[:, 1] - 1.0)) > 0.05         # what the plain differences give there
+    # and the sample is a root of the CDF on a grid that covers the law
+    assert np.all(g["status"] == 0) and np.all(np.abs(g["x"] - truth[:, 0]) < 8 * np.sqrt(truth[:, 1]))
+
+
+@pytest.mark.parametrize("pars,dates,xi_note", [(LOWXI, 52, "sigma tau = 0.002"), (C2, 252, "sigma tau = 0.0012")])
+def test_bk_price_on_many_dates(cuda, pars, dates, xi_note):
+    """Weekly and daily exact transitions (path-dependent payoffs and American exercise on Broadie-Kaya dates use them):
+    within 3.5 standard errors of Carr-Madan. Before the variance was re-read in the noise-dominated regime the first case
+    was 25 standard errors high."""
+    n = 200_000
+    prob, mc = _bk_problem(pars, 365, n, steps=dates)
+    sol = hh.solve(prob, mc, engine=cuda)
+    cm = A.heston_price(100.0, 100.0, pars["r"], 1.0, pars["V0"], pars["kappa"], pars["theta"], pars["xi"], pars["rho"], bound=200.0)
+    assert abs(sol.price - cm) < 3.5 * sol.std_error + 2e-4 * cm, (sol.price, cm, sol.std_error)
+    assert sol.stats["n_nonfinite"] == 0 and sol.stats["n_fallback"] <= 1e-4 * n * dates
