@@ -13,7 +13,7 @@
 //                        I_nu(|w|) / |I_nu(w)| ~ e^{|w| - Re w} <= e^5, whatever |w| (no cancellation at all on the real
 //                        axis), so arguments near the real axis never need the continued fractions (~50x dearer)
 //   |w| >= 20 + nu^2/2   Hankel expansion with BOTH exponentials (DLMF 10.40.5)
-//   nu >= 12.5, between the two (the series would need more than its 100 tabulated terms, the Hankel terms grow first):
+//   nu >= 11.5, between the two (the series would need more than its 100 tabulated terms, the Hankel terms grow first):
 //                        Debye's uniform expansion in the order (DLMF 10.41.3, u_0..u_8) in a sector round the real axis —
 //                        low vol of vol means a large order (nu = 2 kappa theta / sigma^2 - 1: 15 at sigma = 0.1, 89 at
 //                        kappa theta = 0.45), and |z| there is a few times nu
@@ -353,6 +353,9 @@ struct BesselEF {
 };
 
 constexpr int kSeriesMaxTerms = 100, kHankelMaxTerms = 60;
+// Orders from which Debye's expansion fills the gap between the series and the Hankel expansion. Below it the tabulated
+// series reaches r_asym (it does up to nu = 11.9), and r_near == r_asym exactly: the hot region test relies on that.
+constexpr double kDebyeMinOrder = 11.5;
 
 // Host-prepared constants of one order, plus the shared-window addresses of the block's coefficient tables (device).
 struct BesselOrder {
@@ -360,6 +363,7 @@ struct BesselOrder {
   double lgam_nu1;  // lgamma(nu + 1)
   double r_asym;    // |w| from which the Hankel expansion is used
   double r_near;    // min(r_asym, largest |w| whose series reaches 1e-17 within the tabulated terms)
+  double r_asym2, r_near2;  // their squares (region tests on |w|^2)
   // device: tables filled by bk_fill_order_tables in shared memory (the order is fixed per launch), 0 on the host
   //   series: groups of four, R_{k,i} = prod_{m=k}^{k+i-1} 1 / (m (nu + m)), k = 1, 5, 9, ...
   //   hankel: groups of four running products b_k, b_k b_{k+1}, ..., b_k = (4 nu^2 - (2k - 1)^2) / (8 k), k = 1, 5, 9, ...
@@ -393,7 +397,9 @@ HH_HD BesselOrder make_bessel_order(double nu) {
   o.nu = nu;
   o.lgam_nu1 = lgamma(nu + 1.0);
   o.r_asym = 20.0 + 0.5 * nu * nu;
-  o.r_near = bessel_series_radius(nu, o.r_asym);
+  o.r_near = nu < kDebyeMinOrder ? o.r_asym : bessel_series_radius(nu, o.r_asym);
+  o.r_asym2 = o.r_asym * o.r_asym;
+  o.r_near2 = o.r_near * o.r_near;
   o.series_saddr = 0;
   o.hankel_saddr = 0;
   o.ft.saddr = 0;
@@ -524,37 +530,44 @@ HH_HD cplx log_besseli_asymptotic(const BesselOrder &o, cplx w) {
 // tools/gen_debye.py). Used where kDebyeMinOrder <= nu and r_near <= |w| < r_asym, inside the sector bessel_debye_sector: there
 // |z| >= r_near / nu keeps |t| small and nine terms are exact to rounding (measured against 30-digit values: 5e-16
 // relative for nu from 12.7 to 1000; six terms already are) and the recessive exponential is below e^{-160}.
-constexpr double kDebyeMinOrder = 12.5;
 constexpr int kDebyeTerms = 8;
 HH_HD bool bessel_debye_sector(double nu, double aw, cplx w) {  // Re w >= 0
   if (aw - w.re <= 5.0) return true;                            // the strip the series uses below r_near
   if (nu >= 100.0) return fabs(w.im) <= 3.6 * w.re;             // |arg w| <= 1.3
   return nu >= 30.0 && fabs(w.im) <= 0.7 * w.re;                // |arg w| <= 0.61
 }
+#define HH_DEBYE_COEFFS                                                                                                   \
+  {1.0,                                                                                                                   \
+   0.125, -0.20833333333333334,                                                                                           \
+   0.0703125, -0.4010416666666667, 0.3342013888888889,                                                                    \
+   0.0732421875, -0.8912109375, 1.8464626736111112, -1.0258125964506173,                                                  \
+   0.112152099609375, -2.3640869140625, 8.78912353515625, -11.207002616222994, 4.669584423426247,                         \
+   0.22710800170898438, -7.368794359479632, 42.53499874538846, -91.81824154324002, 84.63621767460073, -28.212072558200244, \
+   0.5725014209747314, -26.491430486951554, 218.1905117442116, -699.5796273761325, 1059.9904525279999, -765.2524681411817, \
+   212.57013003921713,                                                                                                    \
+   1.7277275025844574, -108.09091978839466, 1200.9029132163525, -5305.646978613403, 11655.393336864534, -13586.550006434138, \
+   8061.722181737309, -1919.457662318407,                                                                                 \
+   6.074042001273483, -493.915304773088, 7109.514302489364, -41192.65496889755, 122200.46498301746, -203400.17728041555,  \
+   192547.00123253153, -96980.59838863752, 20204.29133096615}
+#ifdef __CUDACC__
+__device__ __constant__ double kDebyeDev[(kDebyeTerms + 1) * (kDebyeTerms + 2) / 2] = HH_DEBYE_COEFFS;
+#endif
 HH_HD_OUTLINE cplx log_besseli_debye(const BesselOrder &o, cplx w) {
-  constexpr double c[(kDebyeTerms + 1) * (kDebyeTerms + 2) / 2] = {
-      1.0,
-      0.125, -0.20833333333333334,
-      0.0703125, -0.4010416666666667, 0.3342013888888889,
-      0.0732421875, -0.8912109375, 1.8464626736111112, -1.0258125964506173,
-      0.112152099609375, -2.3640869140625, 8.78912353515625, -11.207002616222994, 4.669584423426247,
-      0.22710800170898438, -7.368794359479632, 42.53499874538846, -91.81824154324002, 84.63621767460073, -28.212072558200244,
-      0.5725014209747314, -26.491430486951554, 218.1905117442116, -699.5796273761325, 1059.9904525279999, -765.2524681411817,
-      212.57013003921713,
-      1.7277275025844574, -108.09091978839466, 1200.9029132163525, -5305.646978613403, 11655.393336864534, -13586.550006434138,
-      8061.722181737309, -1919.457662318407,
-      6.074042001273483, -493.915304773088, 7109.514302489364, -41192.65496889755, 122200.46498301746, -203400.17728041555,
-      192547.00123253153, -96980.59838863752, 20204.29133096615};
+#ifdef __CUDA_ARCH__
+  const double *c = kDebyeDev;  // rolled loops over a constant-memory table: cold code, kept small (instruction cache)
+#else
+  static const double c[(kDebyeTerms + 1) * (kDebyeTerms + 2) / 2] = HH_DEBYE_COEFFS;
+#endif
   const double inu = 1.0 / o.nu;
   const cplx z = inu * w;
   const cplx s = csqrt_(1.0 + z * z);  // principal branch: Re s > 0 for Re z > 0
   const cplx t = crecip(s), t2 = t * t, x = inu * t;
   cplx acc = mk(0.0);
-#pragma unroll
+#pragma unroll 1
   for (int k = kDebyeTerms; k >= 0; --k) {
     const int base = k * (k + 1) / 2;
     cplx pk = mk(c[base + k]);
-#pragma unroll
+#pragma unroll 1
     for (int j = k - 1; j >= 0; --j) pk = pk * t2 + c[base + j];
     acc = acc * x + pk;
   }
@@ -679,11 +692,12 @@ HH_HD BesselEF besseli_ef(const BesselOrder &o, cplx z, double log_az, double ar
     arg_w = arg_z - sg * kBesselPi;  // arg(-z) in (-pi/2, pi/2)
   }
   // region tests on |w|^2 (Re w >= 0 here: |w| - Re w <= 5  <=>  |w|^2 <= (5 + Re w)^2): no square root
-  const double aw2 = cabs2(w), ra2 = o.r_asym * o.r_asym, edge = 5.0 + w.re;
+  const double aw2 = cabs2(w), rn2 = o.r_near2, edge = 5.0 + w.re;
   BesselEF r;
-  if (aw2 <= 25.0 || (aw2 < o.r_near * o.r_near && aw2 <= edge * edge)) {
+  if (aw2 <= 25.0 || (aw2 < rn2 && aw2 <= edge * edge)) {
     r = besseli_series_ef(o, w, log_az, arg_w);
-  } else if (aw2 >= ra2) {
+  } else if (aw2 >= rn2 && (o.nu < kDebyeMinOrder || aw2 >= o.r_asym2)) {
+    // r_near == r_asym below kDebyeMinOrder: the order is the same for every lane, and the second load and test are skipped
     r = besseli_asymptotic_ef(o, w, log_az, arg_w);
   } else {
     r.E = log_besseli(o, w);  // Debye (large orders) or continued fractions (rare: strongly rotated arguments)
@@ -701,7 +715,8 @@ struct BkParams {
   double wk;               // z_kappa = sqrt(V0 VT) wk  (:169)
   double h_fd, cf_tol, atol;
   int n_std, max_terms;
-  int widen_fd, pad_;      // re-read a noise-dominated variance at a wider step (hh_bk.cu: bk_sample_integral)
+  int widen_fd, pad_;      // re-read a noise-dominated variance at a wider step (hh_bk.cu: bk_variance_from_modulus)
+  double noise_scale;      // 4 eps / h_fd^2 / 0.02
   BesselOrder ord;         // nu = d/2 - 1  (:164-165)
   // transition constants (sample_V_T :128-131, sample_log_S_T :285-297)
   double dof, c_scale, lam_scale;  // d, c, lambda = lam_scale * V

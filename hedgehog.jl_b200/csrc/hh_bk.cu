@@ -187,6 +187,24 @@ __device__ __noinline__ void bk_cdf(const BkTable &tb, FastRef ft, int J, double
   dF = fma(h, kInvPi, h * dacc);
 }
 
+// Phi is the exponential of a difference of terms of size |log I_nu(z_kappa)| + (V0 + VT) eta_kappa / sigma^2 =: L, so it
+// carries ~4 eps L of rounding, and the second difference of moments_from_cf divides that by h0^2 = 1e-4. For short horizons
+// or a low vol of vol (sigma tau < ~0.01: L ~ 8 V / (sigma^2 tau), var ~ sigma^2 V tau^3 / 3) that noise EXCEEDS the
+// variance: the reference's estimate is then a random number, negative half of the time (-> the 1e-12 floor, a Fourier
+// grid narrower than the law, a wrapped CDF: the call of sigma = 0.1 on 52 dates came out 25 standard errors high).
+// Called when the noise is above 2 % of the estimate (noise_scale = 4 eps / h0^2 / 0.02): the variance is re-read from
+// the modulus at a step scaled to the law, h1 = 0.1 / mean:  log |Phi(h1)|^2 = -var h1^2 + O(kappa_4 h1^4), signal
+// 0.01 (sd / mean)^2 against the same 4 eps L. Out of line: C4 never gets here.
+__device__ __noinline__ double bk_variance_from_modulus(const BkParams &p, const BkCf &it, double mean, double var) {
+  const double h1 = 0.1 / mean;
+  if (!(h1 > p.h_fd) || !(h1 < 1e300)) return var;
+  double th1 = nan("");
+  const cplx q = bk_chf(p, it, h1, th1);
+  const double e = 1.0 - q.re;
+  const double m2 = 2.0 * e - e * e - q.im * q.im;  // 1 - |Phi(h1)|^2
+  return (m2 > 0.0 && m2 < 0.5) ? -flog(p.ord.ft, 1.0 - m2) / (h1 * h1) : var;  // m2 >~ 1e-7: log(1 - m2) is good to 1e-9
+}
+
 // sample_from_cf (sample_from_cf.jl:27-41) for a given uniform u.
 __device__ BkInversion bk_sample_integral(const BkParams &p, double V0, double VT, double u, const BkTable &tb) {
   BkInversion r;
@@ -201,24 +219,8 @@ __device__ BkInversion bk_sample_integral(const BkParams &p, double V0, double V
   const cplx pp = bk_chf(p, it, p.h_fd, th);
   const double mean = pp.im / p.h_fd;                                                    // real(-i (pp - pm) / 2h)
   double var = (2.0 - 2.0 * pp.re) / (p.h_fd * p.h_fd) - mean * mean;                    // :60-61
-  if (p.widen_fd) {
-    // Phi is the exponential of a difference of terms of size |log I_nu(z_kappa)| + (V0 + VT) eta_kappa / sigma^2 =: L, so it
-    // carries ~4 eps L of rounding, and the second difference divides that by h0^2 = 1e-4. For short horizons or a low
-    // vol of vol (sigma tau < ~0.01: L ~ 8 V / (sigma^2 tau), var ~ sigma^2 V tau^3 / 3) that noise EXCEEDS the variance:
-    // the reference's estimate is then a random number, negative half of the time (-> the 1e-12 floor, a Fourier grid
-    // narrower than the law, a wrapped CDF: the call of sigma = 0.1 on 52 dates came out 25 standard errors high).
-    // When the noise is above 2 % of the estimate the variance is re-read from the modulus at a step scaled to the law,
-    // h1 = 0.1 / mean:  log |Phi(h1)|^2 = -var h1^2 + O(kappa_4 h1^4), signal 0.01 (sd / mean)^2 against the same 4 eps L.
-    const double noise = 8.9e-16 * (fabs(it.logIk.re) + it.vsum_s * p.eta_k) / (p.h_fd * p.h_fd);
-    const double h1 = 0.1 / mean;
-    if (!(noise <= 0.02 * var) && h1 > p.h_fd && h1 < 1e300) {
-      double th1 = nan("");
-      const cplx q = bk_chf(p, it, h1, th1);
-      const double e = 1.0 - q.re;
-      const double m2 = 2.0 * e - e * e - q.im * q.im;  // 1 - |Phi(h1)|^2
-      if (m2 > 0.0 && m2 < 0.5) var = -log1p(-m2) / (h1 * h1);
-    }
-  }
+  // rounding noise of that second difference against the estimate (see bk_variance_from_modulus)
+  if (p.widen_fd && !(p.noise_scale * (fabs(it.logIk.re) + it.vsum_s * p.eta_k) <= var)) var = bk_variance_from_modulus(p, it, mean, var);
   const double s2 = fmax(var, 1e-12);                                                    // :32
   const double sd = sqrt(s2);
   const double ns = mean + sd * normcdfinv(u);                                           // :33
@@ -697,6 +699,7 @@ static int make_params(hh_ctx *ctx, const hh_model *m, double tau, const hh_bk_c
   else hh_default_bk_config(&c);
   p.h_fd = fabs(c.h_fd);
   p.widen_fd = c.h_fd > 0.0;  // h_fd < 0: the reference's plain finite differences at |h_fd| whatever their noise
+  p.noise_scale = 8.9e-16 / (p.h_fd * p.h_fd) / 0.02;
   p.cf_tol = c.cf_tol;
   p.atol = c.atol;
   p.n_std = c.n_std;
