@@ -253,3 +253,31 @@ def test_lsm_under_heston_on_random_models(cuda, oracle, seed):
     flips = int(np.sum(tg != to))
     assert flips <= max(3, 5e-4 * len(to)), (flips, len(to))
     assert abs(og.price - oo.price) <= (1e-9 if flips == 0 else 5e-5) * max(abs(oo.price), 1e-3), (og.price, oo.price, flips)
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_broadie_kaya_monitoring_dates_on_random_models(cuda, seed):
+    """Path statistics on exact Broadie-Kaya dates over the parameter space: S_T is the European path's to the last bit,
+    min <= geometric <= arithmetic <= max, everything finite, and — the scheme being exact — the discounted spot is a
+    martingale on EVERY date: mean of the arithmetic average = S0 mean_k e^{r t_k} within 4 standard errors."""
+    pars, days, _, _ = _random_bk_case(100 + seed)
+    rng = np.random.default_rng(8000 + seed)
+    dates = int(rng.choice([2, 5, 13, 52]))
+    T = days / 365
+    m = heston_model(S0=100.0, T=T, **pars)
+    n = 100_000
+    cfg = abi.hh_bk_config()
+    cuda.lib.hh_default_bk_config(cfg)
+    cfg.n_std = 12
+    sim = SimSpec(n_paths=n, n_steps=dates, scheme=abi.HH_SCHEME_HESTON_BK, base_seed=500 + seed, bk=cfg)
+    pays = [(abi.HH_PD_VANILLA, 100.0, 1.0, 0.0, 0.0), (abi.HH_PD_ASIAN_ARITH, 0.0, 1.0, 0.0, 0.0), (abi.HH_PD_ASIAN_GEOM, 100.0, -1.0, 0.0, 0.0)]
+    res, st = cuda.mc_path_dependent(m, sim, pays, 1.0, 1, want_stats=True)
+    eur, term = cuda.mc_european(m, sim, [(100.0, 1.0)], 1.0, want_terminal=True)
+    assert np.array_equal(st[0], term)
+    assert np.all(np.isfinite(st)) and np.all(st > 0)
+    assert np.all(st[4] <= st[2] * (1 + 1e-13)) and np.all(st[2] <= st[1] * (1 + 1e-13)) and np.all(st[1] <= st[3] * (1 + 1e-13))
+    assert all(r.n_nonfinite == 0 for r in res)
+    # strike 0 call on the arithmetic average = its mean
+    tk = T * np.arange(1, dates + 1) / dates
+    want = 100.0 * np.mean(np.exp(pars["r"] * tk))
+    assert abs(res[1].price - want) < 4.0 * res[1].std_error + 1e-4 * want, (res[1].price, want, res[1].std_error, pars, dates)
