@@ -313,7 +313,7 @@ function european_prices(inputs::AbstractMarketInputs, expiry, cp::Float64, stri
         end
         sums = method.allreduce(vcat([[r.sum, Float64(r.n)] for r in res]...))   # [sum_k, n_k] per payoff, over all processes
         prices = [plain(discount) * sums[2k-1] / sums[2k] for k in 1:npay]       # :490
-        ensemble = anti ? (terminal[1:nloc], terminal[nloc+1:end]) : terminal     # final_sample :398-402
+        ensemble = (anti && method.ensemble) ? (terminal[1:nloc], terminal[nloc+1:end]) : terminal     # final_sample :398-402
         return prices, ensemble
     end
     # ---- Dual inputs -----------------------------------------------------------------------------------------------------
@@ -416,7 +416,7 @@ function Hedgehog.solve(prob::PricingProblem{VanillaOption{TS,TE,American,C,S},I
     # (allreduce_sum_f64 == NULL, hedgehog_mc.h "peer mailboxes"); peer_connect must have been called on every rank
     comm = Ref(HHComm(C_NULL, C_NULL, mc.rank, mc.world))
     with_sim(mc, scheme; dates_from_config = scheme == HH_SCHEME_HESTON_BK) do sim
-        GC.@preserve stop_idx stop_val spot begin
+        GC.@preserve stop_idx stop_val spot comm begin
             rc = ccall((:hh_lsm_american, LIB[]), Cint,
                        (Ptr{Cvoid}, Ref{HHModel}, Ref{HHSim}, Ref{HHPayoff}, Cint, Cdouble, Ptr{HHComm}, Ref{HHLsmResult},
                         Ptr{Int32}, Ptr{Float64}, Ptr{Float64}),
