@@ -1458,8 +1458,11 @@ int lsm_american(hh_ctx *ctx, const hh_model *m, const hh_sim *s, const hh_payof
   // pass moves 16 B per column through HBM (the two date slices) instead of 32 B.
   static const int l2_mode = getenv("HH_LSM_L2") ? atoi(getenv("HH_LSM_L2")) : 1;
   bool l2_window = false;
-  if (l2_mode && ctx->l2_persist_max > 0 && ctx->l2_window_max > 0) {
-    const size_t zbytes = sizeof(double) * (size_t)stride;
+  // Only when z fits in the carve-out (C3: 80 MB of 82.9). Beyond it a partly persisting window is slower than no window
+  // at all (1.5e7 columns 3.64 / 3.43 ms, 4.5e7 10.2 / 9.5 ms, with equal DRAM traffic: ncu, profiles/r2_n_*): the
+  // evict-last hint on the bulk loads of z (z_policy below) is what helps there.
+  const size_t zbytes = sizeof(double) * (size_t)stride;
+  if (l2_mode && ctx->l2_persist_max > 0 && ctx->l2_window_max > 0 && (l2_mode == 2 || zbytes <= ctx->l2_persist_max)) {
     size_t carve = ctx->l2_persist_max;
     if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve) == cudaSuccess) {
       cudaStreamAttrValue attr;
