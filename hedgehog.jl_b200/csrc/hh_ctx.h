@@ -126,7 +126,7 @@ struct hh_ctx {
   std::string err;
 
   hh::DeviceBuffer d_payoffs, d_partials, d_final, d_terminal, d_seeds, d_normals, d_tangents;
-  hh::DeviceBuffer d_grid, d_cash, d_tau, d_lsm_partials, d_lsm_state, d_misc, d_counters, d_bk_slab, d_bk_work;
+  hh::DeviceBuffer d_grid, d_cash, d_tau, d_lsm_partials, d_lsm_state, d_misc, d_counters, d_bk_slab, d_bk_work, d_lsm_uab;
   // peer mailboxes (hh_peer_*): own buffer + the peers' buffers mapped through CUDA IPC
   void *mailbox = nullptr;
   void *peer_mail[HH_MAX_PEERS] = {};
@@ -146,7 +146,7 @@ struct hh_ctx {
   template <class F>
   void for_each_buffer(F f) {
     hh::DeviceBuffer *bufs[] = {&d_payoffs, &d_partials, &d_final, &d_terminal, &d_seeds, &d_normals, &d_tangents, &d_grid, &d_cash,
-                                &d_tau, &d_lsm_partials, &d_lsm_state, &d_misc, &d_counters, &d_bk_slab, &d_bk_work};
+                                &d_tau, &d_lsm_partials, &d_lsm_state, &d_misc, &d_counters, &d_bk_slab, &d_bk_work, &d_lsm_uab};
     for (auto *b : bufs) f(*b);
   }
 

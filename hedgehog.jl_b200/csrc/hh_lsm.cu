@@ -271,6 +271,7 @@ struct LsmPassArgs {
   const LsmFit *fit_next;
   double *partials;      // [grid][nacc]
   double Dp, rscale, strike, cp, ua, ub;  // Dp = D^(t+1); rscale = D^-t turns the time-0 sums into date-t money for the fit
+  double ua_n, ub_n;       // the Chebyshev variable of date t+1 (the fitted polynomial of that date is in it); ua, ub: date t
   int t_next;
   int first;  // t+1 is the terminal date: z = payoff(S_M)
   int last;   // t = 0: no regression, accumulate sum / sumsq of D z
@@ -314,7 +315,7 @@ __host__ __device__ constexpr int lsm_nacc() { return 3 * DEG + 3; }
 
 // One column of one pass, branch free. The pass kernel is bound by the SM's dispatch port, not by HBM, unless the
 // per-column instruction count is kept near the minimum (profiles/r1_c_ncu_lsm_pass_2e6.csv: DRAM 25 %, issue 57 %):
-//   decision at t+1:  e = cp S - cp K;  cont = Horner(q, ua S + ub);  exercise iff e > 0 and e > cont (strict, :163-164)
+//   decision at t+1:  e = cp S - cp K;  cont = Horner(q, ua_n S + ub_n);  exercise iff e > 0 and e > cont (strict, :163-164)
 //   moments at t:     g = 1{cp S_t - cp K > 0};  T_0 = g, T_1 = g u, T_k = 2 u T_{k-1} - T_{k-2}: the indicator rides
 //                     through the linear recurrence, so every sum is an unconditional add / fma.
 // Sign tests read the high word of the double on the integer pipe (x > 0 <=> hi(x) > 0 for the values that occur:
@@ -334,7 +335,7 @@ __device__ __forceinline__ void lsm_column(const A &a, const double *q, double c
     zz = __double2hiint(e) > 0 ? e_now : 0.0;  // stopping_info = (nsteps, payoff(S_T))  :112
     changed = true;
   } else {
-    const double un = fma(a.ua, sn, a.ub);
+    const double un = fma(a.ua_n, sn, a.ub_n);
     double cont = q[DEG];  // poly.(x)  :127  (in date-(t+1) money, like e)
 #pragma unroll
     for (int k = DEG - 1; k >= 0; --k) cont = fma(cont, un, q[k]);
@@ -791,13 +792,14 @@ struct LsmBackArgs {
   unsigned int *gflag;     // generation of gmom
   double *moments_out;     // final [sum, sumsq, count]
   LsmFit *fits;            // [M+1], written by block 0 (statistics for the host)
-  double logD, strike, cp, ua, ub;  // logD = log of the one-step discount factor
+  double logD, strike, cp;  // logD = log of the one-step discount factor
+  const double *uab;       // [M+1][2]: Chebyshev variable u = ua S + ub of every date (lsm_u_intervals)
   int M;
   PeerX px;                // px.epoch = epoch of the first exchanged date minus one
   int z_policy, cur_policy;  // L2 hints of the bulk loads: 0 none, 1 evict_last, 2 evict_first
 };
 struct LsmColArgs {
-  double cp, ua, ub, Dp;
+  double cp, ua, ub, ua_n, ub_n, Dp;
   int32_t *tau;
   int t_next;
 };
@@ -875,8 +877,6 @@ __global__ void __launch_bounds__(kBackThreads) lsm_backward_kernel(const LsmBac
   unsigned int seq = 0;  // chunks of this block so far, over all dates (same count on both sides): ring slot and phase
   LsmColArgs ca;
   ca.cp = a.cp;
-  ca.ua = a.ua;
-  ca.ub = a.ub;
   ca.tau = a.tau;
 
   // one lane of the producer warp: chunk i of date `td` (its S_next = G[td+1]) into ring position `at`, after the
@@ -911,6 +911,10 @@ __global__ void __launch_bounds__(kBackThreads) lsm_backward_kernel(const LsmBac
     const double *S_cur = a.G + (size_t)t * a.stride;
     ca.t_next = t + 1;
     ca.Dp = exp((double)(t + 1) * a.logD);
+    ca.ua = __ldg(a.uab + 2 * t);
+    ca.ub = __ldg(a.uab + 2 * t + 1);
+    ca.ua_n = __ldg(a.uab + 2 * t + 2);
+    ca.ub_n = __ldg(a.uab + 2 * t + 3);
     double q[DEG + 1];
 #pragma unroll
     for (int k = 0; k <= DEG; ++k) q[k] = first ? 0.0 : s_fit.q[k];
@@ -1419,19 +1423,35 @@ int lsm_american(hh_ctx *ctx, const hh_model *m, const hh_sim *s, const hh_payof
     HH_CUDA(ctx, cudaGetLastError());
   }
 
-  // Chebyshev variable u = ua S + ub: the in-the-money side of the strike mapped to about [-1, 1]
-  double ua, ub;
-  if (payoff->cp < 0) {  // put: S in (0, K)
-    ua = 2.0 / payoff->strike;
-    ub = -1.0;
-  } else {  // call: S in (K, Smax), Smax = a 6-sigma excursion of the terminal spot
-    // Heston: the larger of the initial and the long-run volatility stands in for sigma (the map only conditions the basis)
+  // Chebyshev variable u = ua_t S + ub_t of date t: the in-the-money side of the strike, as far as the spot of THAT date
+  // reaches (a 5-sigma excursion of its lognormal law), mapped to [-1, 1]. The map only conditions the basis — the fitted
+  // polynomial is the same — but the fit solves NORMAL equations: with one interval for all dates (the put's (0, K), or the
+  // call's (K, 6-sigma excursion of the TERMINAL spot)) the early dates of a volatile call, or of a short-dated low-volatility
+  // put, had all their data in a few per cent of [-1, 1], the Gram matrix lost its rank in binary64 and up to 4 % of the
+  // stopping decisions differed from the QR fit of the reference (found by HH_FUZZ_SCALE=8 tests/test_gpu_fuzz.py).
+  std::vector<double> uab((size_t)(2 * (M + 1)));
+  {
+    // Heston: the larger of the initial and the long-run volatility stands in for sigma
     const double sg = m->kind == HH_MODEL_HESTON ? sqrt(fmax(fmax(m->V0, m->theta), 0.0)) : fabs(m->sigma);
-    const double drift = fmax((m->r - 0.5 * sg * sg) * m->T, 0.0);
-    const double smax = fmax(m->S0, payoff->strike) * exp(drift + 6.0 * sg * sqrt(m->T));
-    ua = 2.0 / (smax - payoff->strike);
-    ub = -1.0 - ua * payoff->strike;
+    const double K = payoff->strike;
+    for (int t = 0; t <= M; ++t) {
+      const double ty = m->T * (double)(t > 0 ? t : 1) / (double)M;  // (date 0 has no regression)
+      const double med = m->S0 * exp((m->r - 0.5 * sg * sg) * ty), reach = exp(5.0 * sg * sqrt(ty));
+      double lo, hi;
+      if (payoff->cp < 0) {  // put: S in (lo, K)
+        hi = K;
+        lo = fmin(med / reach, 0.9 * K);
+      } else {               // call: S in (K, hi)
+        lo = K;
+        hi = fmax(med * reach, 1.1 * K);
+      }
+      if (!(hi > lo) || !(hi < 1e300)) { lo = payoff->cp < 0 ? 0.0 : K; hi = payoff->cp < 0 ? K : 2.0 * K + 1.0; }
+      uab[2 * t] = 2.0 / (hi - lo);
+      uab[2 * t + 1] = -1.0 - uab[2 * t] * lo;
+    }
   }
+  HH_CUDA(ctx, ctx->d_lsm_uab.ensure(sizeof(double) * uab.size()));
+  HH_CUDA(ctx, cudaMemcpyAsync(ctx->d_lsm_uab.ptr, uab.data(), sizeof(double) * uab.size(), cudaMemcpyHostToDevice, st));
 
   LsmPassArgs a;
   memset(&a, 0, sizeof a);
@@ -1441,8 +1461,6 @@ int lsm_american(hh_ctx *ctx, const hh_model *m, const hh_sim *s, const hh_payof
   a.partials = ctx->d_lsm_partials.as<double>();
   a.strike = payoff->strike;
   a.cp = payoff->cp;
-  a.ua = ua;
-  a.ub = ub;
   a.done = reinterpret_cast<unsigned int *>(static_cast<char *>(ctx->d_lsm_state.ptr) + done_off);
   a.moments = d_moments;
   a.px.world = 1;
@@ -1496,8 +1514,7 @@ int lsm_american(hh_ctx *ctx, const hh_model *m, const hh_sim *s, const hh_payof
     bk.logD = log(step_discount);
     bk.strike = payoff->strike;
     bk.cp = payoff->cp;
-    bk.ua = ua;
-    bk.ub = ub;
+    bk.uab = ctx->d_lsm_uab.as<double>();
     bk.M = M;
     // z (the discounted cash flows, 8 B per column) is re-read on every date: evict_last keeps as much of it in the
     // 126 MB L2 as fits. Neutral at C3 (80 MB, resident anyway: 2.043 / 2.047 ms), -40 % beyond it (2e7 columns 7.82 ->
@@ -1528,6 +1545,10 @@ int lsm_american(hh_ctx *ctx, const hh_model *m, const hh_sim *s, const hh_payof
     a.S_cur = G + (size_t)t * stride;
     a.fit_next = d_fits + (t + 1);
     a.t_next = t + 1;
+    a.ua = uab[2 * t];
+    a.ub = uab[2 * t + 1];
+    a.ua_n = uab[2 * t + 2];
+    a.ub_n = uab[2 * t + 3];
     a.Dp = pow(step_discount, (double)(t + 1));
     a.rscale = pow(step_discount, -(double)t);
     a.first = (t + 1 == M);

@@ -331,3 +331,26 @@ def test_lsm_broadie_kaya_bermudan_put_through_solve(cuda):
     assert bk.price > euro_put + 3 * bk.std_error
     assert abs(bk.price - em.price) < 0.02 * bk.price
     assert bk.stats["n_cols_total"] == 400_000
+
+
+@pytest.mark.parametrize("case", [
+    dict(S0=79.52269401822332, r=0.014583956816892861, sigma=0.5471058154187945, T=1.811123699654538, steps=18, deg=4, anti=1, cp=1.0,
+         K=84.6995352661219, n=6444),      # volatile call: 479 of 12888 decisions differed before the per-date Chebyshev interval
+    dict(S0=44.27014586154759, r=0.04242860160990872, sigma=0.08016317337524555, T=1.568259129916532, steps=4, deg=4, anti=0, cp=-1.0,
+         K=39.0076598804521, n=7957),      # low-volatility out-of-the-money put, degree 4
+    dict(S0=23.0020217126248, r=0.0037183838025878343, sigma=0.3367368057225824, T=2.9504215302361443, steps=18, deg=4, anti=1, cp=1.0,
+         K=24.128030401113264, n=23345),
+])
+def test_lsm_regression_is_well_conditioned_on_every_date(cuda, oracle, case):
+    """The fit solves normal equations in a Chebyshev variable u = ua_t S + ub_t; the interval mapped to [-1, 1] follows the
+    reach of the spot at EACH date. With one interval for all dates these cases (from HH_FUZZ_SCALE=8 tests/test_gpu_fuzz.py)
+    had the data of the early dates in a few per cent of [-1, 1], a Gram matrix without rank in binary64, and up to 4 % of
+    the decisions (1.4 % of the price) away from the reference's QR fit. Now: no decision differs."""
+    m = gbm_model(S0=case["S0"], r=case["r"], sigma=case["sigma"], T=case["T"])
+    sim = SimSpec(n_paths=case["n"], n_steps=case["steps"], scheme=abi.HH_SCHEME_EXACT_STEPS, vr=case["anti"], base_seed=2024)
+    D = math.exp(-m.r * m.T / case["steps"])
+    og, tg, vg, pg = cuda.lsm_american(m, sim, (case["K"], case["cp"]), case["deg"], D, want_stopping=True, want_paths=True)
+    oo, to, vo, po = oracle.lsm_american(m, sim, (case["K"], case["cp"]), case["deg"], D, want_stopping=True, want_paths=True)
+    assert rel_err(pg, po) < 1e-12
+    assert int(np.sum(tg != to)) <= 1
+    assert abs(og.price - oo.price) <= 1e-9 * abs(oo.price) + (5e-4 * abs(oo.price) if np.any(tg != to) else 0.0)
