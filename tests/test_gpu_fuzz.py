@@ -312,3 +312,41 @@ def test_broadie_kaya_monitoring_dates_on_random_models(cuda, seed):
     tk = T * np.arange(1, dates + 1) / dates
     want = 100.0 * np.mean(np.exp(pars["r"] * tk))
     assert abs(res[1].price - want) < 4.0 * res[1].std_error + 1e-4 * want, (res[1].price, want, res[1].std_error, pars, dates)
+
+
+@pytest.mark.parametrize("seed", range(10 * SCALE))
+def test_second_order_sums_and_control_variates_on_random_models(cuda, oracle, seed):
+    """Gamma by bumped payoffs on the kernel's own trajectories (second_sums, greeks_problem.jl:395-412) and the
+    Black-Scholes control-variate contracts, on random Heston models of moderate harshness: the sums the host layer
+    combines agree with the oracle's (three re-simulations / a log-GBM trajectory on the same increments)."""
+    rng = np.random.default_rng(9000 + seed)
+    m = _random_heston(rng)
+    m.S0 = float(rng.uniform(20, 300))
+    m.T = float(rng.uniform(0.05, 2.0))
+    m.xi = float(rng.uniform(0.05, 0.8))
+    m.kappa = float(rng.uniform(0.2, 6.0))
+    m.V0, m.theta = float(rng.uniform(0.01, 0.2)), float(rng.uniform(0.01, 0.2))
+    (m.m11, m.m12, m.m21, m.m22), dM = hh.corr_factor(m.rho, "cholesky")
+    steps = int(rng.integers(2, 40))
+    anti = int(rng.integers(0, 2))
+    n = 2000
+    pay = [(m.S0 * 0.9, 1.0), (m.S0, 1.0), (m.S0 * 1.1, -1.0)]
+    tans = [abi.hh_tangent(dS0=1.0), abi.hh_tangent(dV0=1.0)]
+    sim = SimSpec(n_paths=n, n_steps=steps, vr=anti, base_seed=int(rng.integers(0, 2 ** 62)))
+    eps = m.S0 * float(rng.uniform(1e-3, 2e-2))
+    sg, _, g2 = cuda.tangent_sums(m, tans, sim, pay, spot_bump=eps)
+    so, _, o2 = oracle.tangent_sums(m, tans, sim, pay, spot_bump=eps)
+    scale = np.abs(o2).max(axis=0, keepdims=True) + 1e-300
+    assert np.max(np.abs(g2 - o2) / scale) < 1e-7, np.max(np.abs(g2 - o2) / scale)
+    cols = [0, 1, 2, 3]
+    sc = np.maximum(np.abs(so[:, cols]), 1e-8 * np.abs(so[:, cols]).max() + 1e-300)
+    assert np.max(np.abs(sg[:, cols] - so[:, cols]) / sc) < 1e-6
+    # control variates (Heston Euler-Maruyama only): the control, and the payoff minus beta times the control
+    pays = [(abi.HH_PD_VANILLA, m.S0, 1.0, 0.0, 0.0), (abi.HH_PD_BS_CONTROL, m.S0, 1.0, 0.0, 0.0),
+            (abi.HH_PD_VANILLA_MINUS_BS, m.S0 * 0.95, -1.0, 0.0, float(rng.uniform(0.3, 1.2)))]
+    rg, _ = cuda.mc_path_dependent(m, sim, pays, 0.98, 1)
+    ro, _ = oracle.mc_path_dependent(m, sim, pays, 0.98, 1)
+    for g, o in zip(rg, ro):
+        assert g.sum == pytest.approx(o.sum, rel=1e-7, abs=1e-7 * m.S0)
+        assert g.sumsq == pytest.approx(o.sumsq, rel=1e-6, abs=1e-7 * m.S0 ** 2)
+        assert g.n_nonfinite == 0
