@@ -659,6 +659,12 @@ HH_HD_OUTLINE cplx log_besseli(const BesselOrder &o, cplx z) {
     w = -z;
     rot = (z.im >= 0.0 ? 1.0 : -1.0) * kBesselPi * nu;
   }
+  if (fabs(w.re) < 1e-140 && fabs(w.im) < 1e-140) {
+    // |w|^2 would underflow. I_nu(w) = (w/2)^nu / Gamma(nu+1) (1 + O(|w|^2)): the first term, with the logarithm taken of
+    // the rescaled argument (exact power of two)
+    const cplx l = clog_(o.ft, cplx{w.re * 0x1p+600, w.im * 0x1p+600});  // log 0 = -inf: I_nu(0) = 0 or Inf, as it should
+    return cplx{nu * (l.re - 601.0 * 0.6931471805599453) - o.lgam_nu1, nu * l.im + rot};
+  }
   const double aw = cabs(w);
   if (aw != aw) return cplx{aw, aw};  // NaN in, NaN out (no branch below would terminate early)
   cplx r;
