@@ -127,7 +127,7 @@ def test_lsm_on_random_contracts(cuda, oracle, seed):
     m = gbm_model(S0=float(rng.uniform(20, 200)), r=float(rng.uniform(0.0, 0.12)), sigma=float(rng.uniform(0.05, 0.6)),
                   T=float(rng.uniform(0.1, 3.0)))
     steps = int(rng.integers(2, 30))
-    deg = int(rng.integers(1, 5))
+    deg = int(rng.integers(1, 7))
     anti = int(rng.integers(0, 2))
     cp = float(rng.choice([-1.0, -1.0, 1.0]))
     K = m.S0 * float(rng.uniform(0.85, 1.15))
@@ -271,7 +271,7 @@ def test_lsm_under_heston_on_random_models(cuda, oracle, seed):
     anti = int(rng.integers(0, 2))
     cp = float(rng.choice([-1.0, -1.0, 1.0]))
     K = m.S0 * float(rng.uniform(0.9, 1.1))
-    deg = int(rng.integers(1, 5))
+    deg = int(rng.integers(1, 7))
     sim = SimSpec(n_paths=int(rng.integers(5000, 30000)), n_steps=steps, scheme=abi.HH_SCHEME_EM, vr=anti,
                   base_seed=int(rng.integers(0, 2 ** 62)), path_offset=int(rng.integers(0, 2 ** 40)))
     D = math.exp(-m.r * m.T / steps)
@@ -283,7 +283,8 @@ def test_lsm_under_heston_on_random_models(cuda, oracle, seed):
     assert np.quantile(dlog, 0.999) < 1e-10 and dlog.max() < 1e-6, (np.quantile(dlog, 0.999), dlog.max())
     flips = int(np.sum(tg != to))
     assert flips <= max(3, 5e-4 * len(to)), (flips, len(to))
-    assert abs(og.price - oo.price) <= (1e-9 if flips == 0 else 5e-5) * max(abs(oo.price), 1e-3), (og.price, oo.price, flips)
+    # a flipped decision replaces one column's cash flow by another realisation: O(price) / columns each
+    assert abs(og.price - oo.price) <= (1e-9 if flips == 0 else 1e-4 * flips) * max(abs(oo.price), 1e-3), (og.price, oo.price, flips)
 
 
 @pytest.mark.parametrize("seed", range(12 * SCALE))
