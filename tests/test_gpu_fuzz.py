@@ -126,7 +126,7 @@ def test_lsm_on_random_contracts(cuda, oracle, seed):
     rng = np.random.default_rng(4000 + seed)
     m = gbm_model(S0=float(rng.uniform(20, 200)), r=float(rng.uniform(0.0, 0.12)), sigma=float(rng.uniform(0.05, 0.6)),
                   T=float(rng.uniform(0.1, 3.0)))
-    steps = int(rng.integers(2, 30))
+    steps = int(rng.integers(2, 30)) if rng.random() < 0.75 else int(rng.integers(30, 150))
     deg = int(rng.integers(1, 7))
     anti = int(rng.integers(0, 2))
     cp = float(rng.choice([-1.0, -1.0, 1.0]))
@@ -138,8 +138,12 @@ def test_lsm_on_random_contracts(cuda, oracle, seed):
     oo, to, vo, po = oracle.lsm_american(m, sim, (K, cp), deg, D, want_stopping=True, want_paths=True)
     assert rel_err(pg, po) < 1e-12
     flips = int(np.sum(tg != to))
-    assert flips <= max(3, 3e-4 * len(to)), (flips, len(to))
-    assert abs(og.price - oo.price) <= (1e-9 if flips == 0 else 2e-5) * max(abs(oo.price), 1e-3), (og.price, oo.price, flips)
+    # ties: a column whose exercise value equals the fitted continuation value to rounding, on any of its dates
+    assert flips <= max(3, 3e-4 * len(to) * max(1.0, steps / 30)), (flips, len(to), steps)
+    # a flipped decision replaces one column's cash flow by another realisation: O(price) / columns each
+    # (deep out of the money the price is a few cash flows: the bound is per column, not relative to the price)
+    tol = 1e-9 * max(abs(oo.price), 1e-3) if flips == 0 else flips * (0.2 * K / len(to) + 1e-4 * abs(oo.price))
+    assert abs(og.price - oo.price) <= tol, (og.price, oo.price, flips)
     assert og.n_dates_skipped == oo.n_dates_skipped
 
 
@@ -284,7 +288,8 @@ def test_lsm_under_heston_on_random_models(cuda, oracle, seed):
     flips = int(np.sum(tg != to))
     assert flips <= max(3, 5e-4 * len(to)), (flips, len(to))
     # a flipped decision replaces one column's cash flow by another realisation: O(price) / columns each
-    assert abs(og.price - oo.price) <= (1e-9 if flips == 0 else 1e-4 * flips) * max(abs(oo.price), 1e-3), (og.price, oo.price, flips)
+    tol = 1e-9 * max(abs(oo.price), 1e-3) if flips == 0 else flips * (0.2 * K / len(to) + 1e-4 * abs(oo.price))
+    assert abs(og.price - oo.price) <= tol, (og.price, oo.price, flips)
 
 
 @pytest.mark.parametrize("seed", range(12 * SCALE))
