@@ -180,14 +180,18 @@ def test_path_dependent_kernels_on_random_models(cuda, oracle, seed):
         assert rg[0].n_nonfinite == 0
 
 
+WIDE = os.environ.get("HH_FUZZ_WIDE", "0") == "1"   # soak option: vol of vol down to 0.03 (orders ~1e3), up to 52 dates
+
+
 def _random_bk_case(seed):
     rng = np.random.default_rng(5000 + seed)
-    kappa = float(10 ** rng.uniform(-1, 1))
+    kappa = float(10 ** rng.uniform(-1, 1.3 if WIDE else 1))
     theta = float(10 ** rng.uniform(-2.5, -0.5))
-    xi = float(10 ** rng.uniform(-1.2, 0.2))
+    xi = float(10 ** rng.uniform(-1.5 if WIDE else -1.2, 0.2))
     pars = dict(kappa=kappa, theta=theta, xi=xi, rho=float(rng.uniform(-0.95, 0.5)), V0=theta * float(rng.uniform(0.3, 2.5)),
                 r=float(rng.uniform(-0.01, 0.08)))
-    return pars, int(rng.integers(20, 730)), int(rng.choice([1, 1, 4])), 100.0 * float(rng.uniform(0.9, 1.1))
+    return (pars, int(rng.integers(20, 730)), int(rng.choice([1, 4, 12, 52] if WIDE else [1, 1, 4])),
+            100.0 * float(rng.uniform(0.9, 1.1)))
 
 
 @pytest.mark.parametrize("seed", range(24 * SCALE))
