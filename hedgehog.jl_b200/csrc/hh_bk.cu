@@ -679,7 +679,8 @@ __global__ void bk_variance_kernel(const BkParams p, const double *V0, int n, ui
 // ---- host side ---------------------------------------------------------------------------------------------------------
 static int make_params(hh_ctx *ctx, const hh_model *m, double tau, const hh_bk_config *cfg, BkParams &p) {
   if (!(m->kappa > 0.0)) return ctx->fail(HH_ERR_ARG, "Broadie-Kaya needs kappa > 0");
-  if (m->xi == 0.0) return ctx->fail(HH_ERR_ARG, "Broadie-Kaya needs a non-zero vol of vol");
+  if (m->xi == 0.0 || !(fabs(m->xi) < 1e300)) return ctx->fail(HH_ERR_ARG, "Broadie-Kaya needs a finite non-zero vol of vol");
+  if (!(m->kappa < 1e300) || !(m->theta < 1e300)) return ctx->fail(HH_ERR_ARG, "Broadie-Kaya needs finite kappa and theta");
   if (!(m->theta > 0.0)) return ctx->fail(HH_ERR_ARG, "Broadie-Kaya needs theta > 0");
   if (!(tau > 0.0)) return ctx->fail(HH_ERR_ARG, "transition horizon must be positive");
   memset(&p, 0, sizeof p);

@@ -1289,8 +1289,19 @@ int validate_model_sim(hh_ctx *ctx, const hh_model *m, const hh_sim *s) {
   } else {
     return ctx->fail(HH_ERR_ARG, "unknown model kind %d", m->kind);
   }
-  if (!(m->S0 > 0.0)) return ctx->fail(HH_ERR_ARG, "spot must be positive");
-  if (!(m->T > 0.0)) return ctx->fail(HH_ERR_ARG, "time to expiry must be positive");
+  if (!(m->S0 > 0.0) || !(m->S0 < 1e300)) return ctx->fail(HH_ERR_ARG, "spot must be positive");
+  if (!(m->T > 0.0) || !(m->T < 1e300)) return ctx->fail(HH_ERR_ARG, "time to expiry must be positive");
+  // A NaN parameter does not always surface as a NaN price: the full-truncation max(v, 0) and the clamps of the table-driven
+  // functions swallow it (a NaN kappa priced a call at 2.62 with n_nonfinite = 0). Non-finite parameters are an argument error.
+  if (!(fabs(m->r) < 1e300)) return ctx->fail(HH_ERR_ARG, "the rate must be finite");
+  if (m->kind == HH_MODEL_GBM) {
+    if (!(fabs(m->sigma) < 1e300)) return ctx->fail(HH_ERR_ARG, "the volatility must be finite");
+  } else {
+    const double hp[] = {m->V0, m->kappa, m->theta, m->xi, m->rho, m->m11, m->m12, m->m21, m->m22};
+    const char *hn[] = {"V0", "kappa", "theta", "xi", "rho", "m11", "m12", "m21", "m22"};
+    for (int k = 0; k < 9; ++k)
+      if (!(fabs(hp[k]) < 1e300)) return ctx->fail(HH_ERR_ARG, "Heston parameter %s must be finite", hn[k]);
+  }
   return HH_OK;
 }
 

@@ -37,7 +37,8 @@ extern "C" {
 
 /* ---- error codes ------------------------------------------------------------------- */
 #define HH_OK 0
-#define HH_ERR_ARG (-1)         /* bad argument (mirrors the reference's ArgumentError, montecarlo.jl:65-66) */
+#define HH_ERR_ARG (-1)         /* bad argument (mirrors the reference's ArgumentError, montecarlo.jl:65-66); also any
+                                 * non-finite model parameter: the truncations inside the schemes would swallow a NaN */
 #define HH_ERR_UNSUPPORTED (-2) /* combination the reference itself cannot run (e.g. Q5: Antithetic + BK) */
 #define HH_ERR_CUDA 1           /* CUDA runtime failure, see hh_last_error */
 #define HH_ERR_NOMEM 2          /* device allocation failed */

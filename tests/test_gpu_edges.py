@@ -201,3 +201,24 @@ def test_two_contexts_and_two_threads_in_one_process(cuda, oracle):
     [t.join() for t in th]
     assert not errs, errs[:3]
     assert got == expect
+
+
+def test_non_finite_parameters_are_argument_errors(cuda):
+    """NaN does not always surface as a NaN price (the full-truncation max(v, 0) swallows it: a NaN kappa once priced a call
+    at 2.62 with n_nonfinite = 0): non-finite model parameters are rejected at the boundary, on every entry point
+    (tools/bad_input_probe.py runs the longer list: nothing crashes, nothing fails to return)."""
+    nan, inf = float("nan"), float("inf")
+    sim = SimSpec(n_paths=1000, n_steps=4, base_seed=1)
+    for kw in (dict(kappa=nan), dict(xi=nan), dict(V0=inf), dict(theta=nan), dict(r=nan), dict(S0=inf), dict(T=inf)):
+        m = heston_model(**kw)
+        with pytest.raises(ValueError):
+            cuda.mc_european(m, sim, [(100.0, 1.0)], 0.97)
+        with pytest.raises(ValueError):
+            cuda.lsm_american(m, sim, (100.0, -1.0), 2, 0.99)
+        with pytest.raises(ValueError):
+            cuda.mc_path_dependent(m, sim, [(abi.HH_PD_ASIAN_ARITH, 100.0, 1.0, 0.0, 0.0)], 0.97, 1)
+        with pytest.raises(ValueError):
+            cuda.tangent_sums(m, [abi.hh_tangent(dS0=1.0)], sim, [(100.0, 1.0)])
+    for kw in (dict(sigma=nan), dict(sigma=inf), dict(r=inf)):
+        with pytest.raises(ValueError):
+            cuda.mc_european(gbm_model(**kw), SimSpec(n_paths=1000, n_steps=4, scheme=abi.HH_SCHEME_EXACT_STEPS, base_seed=1), [(100.0, 1.0)], 0.97)
