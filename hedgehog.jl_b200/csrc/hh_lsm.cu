@@ -12,7 +12,8 @@
 //       (warp shuffle -> shared -> per-block partials, fixed order). 32 B of HBM traffic per column-date.
 //   Polynomials.fit (:124-126)                                -> lsm_fit_kernel: the (degree+1)^2 normal equations.
 //       The reference regresses on raw monomials of S (QR); here the same polynomial space is spanned by Chebyshev
-//       polynomials of an affinely mapped spot u = a S + b, so that the Gram matrix is well conditioned (raw
+//       polynomials of an affinely mapped spot u = a_t S + b_t — the interval mapped to [-1, 1] follows the reach of the
+//       spot at each date (see hh_lsm_american: uab) — so that the Gram matrix is well conditioned (raw
 //       monomials of S ~ 100 to degree 5 give entries ~1e20), and T_i T_j = (T_{i+j} + T_{|i-j|}) / 2 means only
 //       2 deg + 1 moment sums are needed for it. The fitted VALUES are those of the reference's least-squares
 //       polynomial up to rounding; this is a reduction, not a dense contraction, so no tensor cores.
@@ -793,7 +794,7 @@ struct LsmBackArgs {
   double *moments_out;     // final [sum, sumsq, count]
   LsmFit *fits;            // [M+1], written by block 0 (statistics for the host)
   double logD, strike, cp;  // logD = log of the one-step discount factor
-  const double *uab;       // [M+1][2]: Chebyshev variable u = ua S + ub of every date (lsm_u_intervals)
+  const double *uab;       // [M+1][2]: Chebyshev variable u = ua S + ub of every date (hh_lsm_american: uab)
   int M;
   PeerX px;                // px.epoch = epoch of the first exchanged date minus one
   int z_policy, cur_policy;  // L2 hints of the bulk loads: 0 none, 1 evict_last, 2 evict_first
