@@ -509,10 +509,11 @@ def run_configs(hh, eng, scale, fp64_peak, hbm_peak, hbm_peak_source, anchors, n
                  "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
                               "peak_source": hbm_peak_source,
                               "convention": "algorithmic 32 B per path-date (8 store + 8 read S_t + 16 read/write cash flow)",
-                              "traffic": (kc.get("dram_bytes_per_launch") or 0.0) + ((ncu_consts.get("lsm_paths_kernel<0, 0, 1, 1>") or {})
+                              "traffic": (kc.get("dram_bytes_per_launch") or 0.0) + ((ncu_consts.get("lsm_paths_kernel<0, 0, 1, 1, 0>")
+                                                                                        or ncu_consts.get("lsm_paths_kernel<0, 0, 1, 1>") or {})
                                                                                        .get("dram_bytes_per_launch") or 0.0) or None,
                               "traffic_source": kc.get("source"),
-                              "traffic_note": "ncu DRAM bytes of lsm_paths_kernel (the 4.0 GB store) + lsm_backward_kernel (8.4 GB: "
+                              "traffic_note": "ncu DRAM bytes of lsm_paths_kernel (the 4.0 GB store) + lsm_backward_kernel (8.9 GB: "
                                               "two date slices per pass; the cash-flow vector stays in the persisting L2 window) "
                                               "against 16 GB algorithmic",
                               "backward_only": {"achieved": n * 49 * 24.0 / (sol.stats["regress_ms"] * 1e-3) / 1e9,
