@@ -1425,13 +1425,29 @@ int lsm_american(hh_ctx *ctx, const hh_model *m, const hh_sim *s, const hh_payof
   }
 
   // Chebyshev variable u = ua_t S + ub_t of date t: the in-the-money side of the strike, as far as the spot of THAT date
-  // reaches (a 5-sigma excursion of its lognormal law), mapped to [-1, 1]. The map only conditions the basis — the fitted
+  // reaches (the expected extreme of ncols draws of its lognormal law), mapped to [-1, 1]. The map only conditions the basis — the fitted
   // polynomial is the same — but the fit solves NORMAL equations: with one interval for all dates (the put's (0, K), or the
   // call's (K, 6-sigma excursion of the TERMINAL spot)) the early dates of a volatile call, or of a short-dated low-volatility
   // put, had all their data in a few per cent of [-1, 1], the Gram matrix lost its rank in binary64 and up to 4 % of the
   // stopping decisions differed from the QR fit of the reference (found by HH_FUZZ_SCALE=8 tests/test_gpu_fuzz.py).
   std::vector<double> uab((size_t)(2 * (M + 1)));
   {
+    // How far the interval reaches: to where the largest of ncols samples is expected, z_n = Phi^-1(1 - 1 / ncols) standard
+    // deviations of log S_t (3.7 at 1e4 columns, 5.2 at 1e7), not further. The Gram matrix of degree 6 is sensitive to this:
+    // on a call with sigma sqrt(T) = 1 and 5e4 columns its condition number is 6e5 for the interval [min, max] of the data,
+    // 1e7 for z_n = 4.1, 2e13 for 5 sigma (where 0.7 % of the decisions left the reference's) and 3e11 for 3 sigma
+    // (points beyond the interval: |u| > 1, T_k(u)^2 explodes). Heston: log S_t has fatter tails than the normal law
+    // with the expected integrated variance, + 0.3.
+    double zn = 4.0;
+    {
+      const double target = 1.0 / (double)(ncols > 2 ? ncols : 2);
+      double lo_z = 0.0, hi_z = 8.5;
+      for (int it = 0; it < 60; ++it) {
+        const double mid = 0.5 * (lo_z + hi_z);
+        if (0.5 * erfc(mid * 0.7071067811865476) > target) lo_z = mid; else hi_z = mid;
+      }
+      zn = fmin(fmax(0.5 * (lo_z + hi_z), 3.0), 6.0) + (m->kind == HH_MODEL_HESTON ? 0.3 : 0.0);
+    }
     const double K = payoff->strike;
     for (int t = 0; t <= M; ++t) {
       const double ty = m->T * (double)(t > 0 ? t : 1) / (double)M;  // (date 0 has no regression)
@@ -1445,7 +1461,7 @@ int lsm_american(hh_ctx *ctx, const hh_model *m, const hh_sim *s, const hh_payof
         const double w = fabs(kt) > 1e-8 ? -expm1(-kt) / m->kappa : ty;
         var_t = fmax(m->theta * ty + (m->V0 - m->theta) * w, 0.0);
       }
-      const double med = m->S0 * exp(m->r * ty - 0.5 * var_t), reach = exp(5.0 * sqrt(var_t));
+      const double med = m->S0 * exp(m->r * ty - 0.5 * var_t), reach = exp(zn * sqrt(var_t));
       double lo, hi;
       if (payoff->cp < 0) {  // put: S in (lo, K)
         hi = K;
