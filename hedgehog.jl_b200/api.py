@@ -307,7 +307,7 @@ def _sim_of(method: MonteCarlo, scheme: int, shard=None) -> SimSpec:
         rank, world = shard
         lo, hi = (cfg.trajectories * rank) // world, (cfg.trajectories * (rank + 1)) // world
         n, off = hi - lo, lo
-    sim = SimSpec(n_paths=n, path_offset=off, scheme=scheme,
+    sim = SimSpec(n_paths=n, path_offset=off, scheme=scheme, job_paths=cfg.trajectories if shard is not None else 0,
                   n_steps=cfg.steps if (not exact or method.bk_steps_from_config) else 1,
                   vr=(abi.HH_VR_ANTITHETIC if isinstance(cfg.variance_reduction, Antithetic) else
                       abi.HH_VR_QUASI_RANDOM if isinstance(cfg.variance_reduction, QuasiRandom) else abi.HH_VR_NONE),

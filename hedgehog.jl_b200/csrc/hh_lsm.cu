@@ -1438,9 +1438,17 @@ int lsm_american(hh_ctx *ctx, const hh_model *m, const hh_sim *s, const hh_payof
     // 1e7 for z_n = 4.1, 2e13 for 5 sigma (where 0.7 % of the decisions left the reference's) and 3e11 for 3 sigma
     // (points beyond the interval: |u| > 1, T_k(u)^2 explodes). Heston: log S_t has fatter tails than the normal law
     // with the expected integrated variance, + 0.3.
+    // The count is that of the JOB, rounded up to a power of two: ranks that hold shards of one job must all use the SAME
+    // variable (their moment sums are added), and shard sizes differ by one. The host layers pass the bit length of the
+    // job's trajectory count in hh_sim.reserved (0: this call is the whole job), so that 1 GPU and 8 GPUs fit in the same
+    // basis and their prices stay equal to the last bit.
     double zn = 4.0;
     {
-      const double target = 1.0 / (double)(ncols > 2 ? ncols : 2);
+      int bits = s->reserved;
+      if (bits <= 0)
+        for (bits = 1; bits < 62 && ((int64_t)1 << bits) <= N; ++bits) {}
+      const double job_cols = ldexp(anti ? 2.0 : 1.0, bits < 62 ? bits : 62);
+      const double target = 1.0 / job_cols;
       double lo_z = 0.0, hi_z = 8.5;
       for (int it = 0; it < 60; ++it) {
         const double mid = 0.5 * (lo_z + hi_z);

@@ -28,12 +28,14 @@ class SimSpec:
     seeds: Optional[np.ndarray] = None      # uint64[n_paths]
     normals: Optional[np.ndarray] = None    # float64[n_paths, n_steps, ncomp]
     bk: Optional[abi.hh_bk_config] = None
+    job_paths: int = 0                      # trajectories of the whole job when this is one shard of it (hh_sim.reserved)
 
     def to_c(self, lib):
         s = abi.hh_sim()
         s.n_paths, s.path_offset = int(self.n_paths), int(self.path_offset)
         s.n_steps, s.scheme, s.vr = int(self.n_steps), int(self.scheme), int(self.vr)
         s.precision, s.rng_mode = int(self.precision), int(self.rng_mode)
+        s.reserved = int(self.job_paths).bit_length() if self.job_paths else 0
         s.base_seed = int(self.base_seed) & 0xFFFFFFFFFFFFFFFF
         keep = []
         if self.seeds is not None:

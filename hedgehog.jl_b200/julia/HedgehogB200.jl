@@ -267,14 +267,17 @@ function with_sim(f, method::B200MonteCarlo, scheme::Cint; dates_from_config::Bo
     lo, hi = shard(method)
     prec = method.precision === :f32 ? Cint(1) : Cint(0)          # HH_PREC_F32 / HH_PREC_F64
     rng = method.rng === :philox64 ? HH_RNG_PHILOX_64 : HH_RNG_PHILOX
+    # hh_sim.reserved: bit length of the JOB's trajectory count when this process simulates one shard of it (the LSM regression
+    # fixes its Chebyshev interval from it, identically on every rank)
+    job_bits = method.world > 1 ? Int32(ndigits(cfg.trajectories, base = 2)) : Int32(0)
     if method.base_seed !== nothing || exact
         key = method.base_seed === nothing ? UInt64(cfg.seeds[1]) : method.base_seed   # Xoshiro(seeds[1]) :456 -> ONE stream
-        sim = HHSim(hi - lo, lo, steps, scheme, vr_of(cfg.variance_reduction), prec, rng, 0, key, C_NULL, C_NULL, 0, 0, HHBkConfig())
+        sim = HHSim(hi - lo, lo, steps, scheme, vr_of(cfg.variance_reduction), prec, rng, job_bits, key, C_NULL, C_NULL, 0, 0, HHBkConfig())
         return f(sim)
     end
     seeds = Vector{UInt64}(cfg.seeds[lo+1:hi])                      # remake(prob; seed = seeds[i]) :331
     GC.@preserve seeds begin
-        sim = HHSim(hi - lo, lo, steps, scheme, vr_of(cfg.variance_reduction), prec, rng, 0, 0,
+        sim = HHSim(hi - lo, lo, steps, scheme, vr_of(cfg.variance_reduction), prec, rng, job_bits, 0,
                     pointer(seeds), C_NULL, length(seeds), 0, HHBkConfig())
         f(sim)
     end

@@ -128,7 +128,9 @@ typedef struct hh_sim {
   int32_t vr;          /* HH_VR_* */
   int32_t precision;   /* HH_PREC_* */
   int32_t rng_mode;    /* HH_RNG_* */
-  int32_t reserved;
+  int32_t reserved;    /* hh_lsm_american only: bit length of the JOB's trajectory count when this call simulates one shard
+                        * of it (0: this call is the whole job). Every rank of a job must pass the same value: it fixes the
+                        * interval of the regression's Chebyshev variable, and the ranks' moment sums are added. */
   uint64_t base_seed;  /* Philox key when seeds == NULL; counter carries the global path index */
   const uint64_t *seeds;  /* host, nullable: one key per local trajectory (config.seeds), len >= n_paths */
   const double *normals;  /* host, parity mode only: Z[path][step][component] contiguous */
