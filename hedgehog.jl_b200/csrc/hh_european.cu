@@ -1835,20 +1835,23 @@ int terminal_payoffs_launch(hh_ctx *ctx, const double *d_terminal, int64_t n, co
   return HH_OK;
 }
 
-// Large device -> host copies into the CALLER's pageable buffer (MonteCarloSolution.ensemble: 800 MB at config C2).
-// A plain cudaMemcpy to pageable memory runs at ~4 GB/s here (the driver stages it and the fresh pages fault in one by
-// one). Instead: 32 MB chunks DMA into a pinned double buffer on the stream while a few host threads copy the previous
-// chunk into the caller's buffer (first-touch page faults in parallel).
+// Large device -> host copies into the CALLER's pageable buffer (MonteCarloSolution.ensemble: 800 MB at config C2;
+// LSMSolution.stopping_info: 40 + 80 MB at config C3). A plain cudaMemcpy to pageable memory runs at ~4 GB/s here (the
+// driver stages it and the fresh pages fault in one by one). Instead: chunks DMA into a pinned double buffer on the
+// stream while a few host threads copy the previous chunk into the caller's buffer (first-touch page faults in
+// parallel). Chunks are a quarter of the job, between 4 and 32 MB, so that medium-sized outputs are pipelined too.
 int copy_to_pageable_host(hh_ctx *ctx, void *dst, const void *src_dev, size_t bytes, cudaStream_t st) {
-  constexpr size_t kChunk = (size_t)32 << 20;
-  if (bytes < 2 * kChunk) {
+  constexpr size_t kMaxChunk = (size_t)32 << 20, kMinChunk = (size_t)4 << 20, kMB = (size_t)1 << 20;
+  if (bytes < 2 * kMinChunk) {
     HH_CUDA(ctx, cudaMemcpyAsync(dst, src_dev, bytes, cudaMemcpyDeviceToHost, st));
     return HH_OK;
   }
   for (int b = 0; b < 2; ++b) {
-    if (!ctx->h_stage[b]) HH_CUDA(ctx, cudaHostAlloc(&ctx->h_stage[b], kChunk, cudaHostAllocDefault));
+    if (!ctx->h_stage[b]) HH_CUDA(ctx, cudaHostAlloc(&ctx->h_stage[b], kMaxChunk, cudaHostAllocDefault));
     if (!ctx->ev_stage[b]) HH_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_stage[b], cudaEventDisableTiming));
   }
+  size_t quarter = ((bytes / 4) + kMB - 1) & ~(kMB - 1);
+  const size_t kChunk = quarter < kMinChunk ? kMinChunk : quarter > kMaxChunk ? kMaxChunk : quarter;
   const size_t nchunks = (bytes + kChunk - 1) / kChunk;
   auto chunk_bytes = [&](size_t i) { return i + 1 < nchunks ? kChunk : bytes - i * kChunk; };
   auto issue = [&](size_t i) -> cudaError_t {
@@ -1858,7 +1861,7 @@ int copy_to_pageable_host(hh_ctx *ctx, void *dst, const void *src_dev, size_t by
     return e;
   };
   unsigned hw = std::thread::hardware_concurrency();
-  const int nthreads = (int)(hw == 0 ? 4 : hw > 8 ? 8 : hw);
+  const int nthreads = (int)(hw == 0 ? 4 : hw > 16 ? 16 : hw);
   HH_CUDA(ctx, issue(0));
   if (nchunks > 1) HH_CUDA(ctx, issue(1));
   for (size_t i = 0; i < nchunks; ++i) {
